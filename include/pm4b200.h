@@ -1,0 +1,257 @@
+/* pm4b200.h -- C ABI of the B200-native NUTS/HMC sampling backend for PyMC4's pm.sample path.
+ *
+ * The reference has no FFI: its seam is the Python call
+ *   results, sample_stats = self._run_chains(init_state, burn_in)
+ * (/root/reference/pymc4/mcmc/samplers.py:136, body :172-189) which hands the vectorised
+ * log-density (samplers.py:117-119, built at :729-817 from flow/executor.py:171-187) to
+ * tfp.mcmc.sample_chain(NoUTurnSampler | HamiltonianMonteCarlo wrapped in
+ * DualAveragingStepSizeAdaptation).  This header is what a maintainer binds (ctypes) in place
+ * of that call; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - every function returns 0 on success or a negative PM4_E* code; pm4_last_error() gives
+ *     the thread-local message.
+ *   - "dev" pointers are device memory owned by the caller (e.g. torch tensors) and must stay
+ *     alive until the stream has been synchronised; "host" pointers are ordinary host memory.
+ *   - dtype: PM4_F32 or PM4_F64 selects the arithmetic type of every `void*` real buffer.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and is asynchronous unless stated otherwise.
+ */
+#ifndef PM4B200_H
+#define PM4B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM4_ABI_VERSION 1
+
+/* error codes */
+#define PM4_OK 0
+#define PM4_EINVAL (-22)   /* bad argument / malformed IR                      */
+#define PM4_ENOMOD (-2)    /* specialised kernel module missing or mismatched  */
+#define PM4_ECUDA (-5)     /* a CUDA runtime call failed                       */
+#define PM4_ENOMEM (-12)
+#define PM4_ENOSYS (-38)   /* requested feature not built into this module     */
+
+/* arithmetic type of real-valued buffers */
+#define PM4_F32 0
+#define PM4_F64 1
+
+/* ------------------------------------------------------------------------------------------
+ * Flat model IR: what flow.TransformedSamplingExecutor's log_prob pass
+ * (/root/reference/pymc4/flow/transformed_executor.py:22-138, executor.py:171-187) is lowered to.
+ *
+ *   theta[D]   unconstrained state of one chain; free variables are laid out in the reference's
+ *              trace order (untransformed first, then transformed; executor.py:24-35,163).
+ *   x[D]       constrained values, x = shift + scale * f(theta), f per variable (transform).
+ *   terms      joint log-density = sum over terms of sum over the term's n elements of
+ *              lpdf_kind(value_i, params_i)  (kind POTENTIAL: just value_i).
+ *   ops        per-term straight-line tape evaluated for element i = 0..n-1 in SSA registers.
+ * ------------------------------------------------------------------------------------------ */
+
+/* transforms (pymc4/distributions/transforms.py:137-181) */
+#define PM4_TR_IDENTITY 0
+#define PM4_TR_EXP 1      /* Log / LowerBound / UpperBound: x = shift + scale*exp(z)      */
+#define PM4_TR_SIGMOID 2  /* Sigmoid / Interval:            x = shift + scale*sigmoid(z)  */
+
+typedef struct pm4_rv {
+  int32_t offset;    /* first position in theta                 */
+  int32_t size;      /* number of scalars (prod of core shape)  */
+  int32_t transform; /* PM4_TR_*                                */
+  int32_t _pad;
+  double shift, scale;
+} pm4_rv_t;
+
+/* term kinds (pymc4/distributions/continuous.py:49,176,620; discrete.py:32,452) */
+#define PM4_T_POTENTIAL 0  /* value                                   */
+#define PM4_T_NORMAL 1     /* value, loc, scale                       */
+#define PM4_T_HALFNORMAL 2 /* value, scale                            */
+#define PM4_T_HALFCAUCHY 3 /* value, scale  (loc = 0)                 */
+#define PM4_T_BERNOULLI 4  /* value, probs                            */
+#define PM4_T_POISSON 5    /* value, rate                             */
+
+typedef struct pm4_term {
+  int32_t kind;        /* PM4_T_*                                       */
+  int32_t n;           /* number of elements                            */
+  int32_t op_begin;    /* [op_begin, op_end) into ops                   */
+  int32_t op_end;
+  int32_t n_regs;      /* SSA registers used by the tape                */
+  int32_t value_reg;   /* register holding the value                    */
+  int32_t param_reg[3];/* registers holding the parameters (-1 unused)  */
+  int32_t flags;       /* reserved                                      */
+} pm4_term_t;
+
+/* tape opcodes */
+#define PM4_OP_LD_CONST 0 /* dst = imm                                                     */
+#define PM4_OP_LD_DATA 1  /* dst = dataf[blob + (mode==ELEM ? i : 0)]                      */
+#define PM4_OP_LD_X 2     /* dst = x[base + (SCALAR:0 | ELEM:i | GATHER:datai[blob+i])]     */
+#define PM4_OP_LD_Z 3     /* same addressing, reads theta                                   */
+#define PM4_OP_ADD 10
+#define PM4_OP_SUB 11
+#define PM4_OP_MUL 12
+#define PM4_OP_DIV 13
+#define PM4_OP_POW 14
+#define PM4_OP_NEG 20
+#define PM4_OP_EXP 21
+#define PM4_OP_LOG 22
+#define PM4_OP_LOG1P 23
+#define PM4_OP_SQRT 24
+#define PM4_OP_SQUARE 25
+#define PM4_OP_SIGMOID 26
+#define PM4_OP_SOFTPLUS 27
+#define PM4_OP_TANH 28
+#define PM4_OP_ABS 29
+#define PM4_OP_RECIP 30
+#define PM4_OP_LGAMMA 31
+
+#define PM4_MODE_SCALAR 0
+#define PM4_MODE_ELEM 1
+#define PM4_MODE_GATHER 2
+
+typedef struct pm4_op {
+  int32_t opcode;
+  int32_t dst, a, b; /* SSA register numbers (-1 unused)          */
+  int32_t mode;      /* PM4_MODE_* for loads                      */
+  int32_t base;      /* theta/x offset for LD_X / LD_Z            */
+  int64_t blob;      /* offset into dataf (LD_DATA) / datai (GATHER) */
+  double imm;        /* LD_CONST                                  */
+} pm4_op_t;
+
+/* a traced output: deterministics and back-transformed variables
+ * (/root/reference/pymc4/mcmc/samplers.py:796-809) */
+typedef struct pm4_det {
+  int32_t n;
+  int32_t op_begin, op_end;
+  int32_t n_regs;
+  int32_t value_reg;
+  int32_t out_offset; /* position of element 0 inside one draw's output row */
+} pm4_det_t;
+
+typedef struct pm4_ir {
+  int32_t abi_version; /* PM4_ABI_VERSION */
+  int32_t D;
+  int32_t n_rv;
+  int32_t n_terms;
+  int32_t n_ops;
+  int32_t n_dets;
+  int32_t det_row;     /* scalars per draw produced by the dets tapes */
+  int32_t _pad;
+  const pm4_rv_t* rvs;
+  const pm4_term_t* terms;
+  const pm4_op_t* ops;
+  const pm4_det_t* dets;
+  int64_t n_dataf;
+  const double* dataf;  /* constant real data pool (observed values, covariates) */
+  int64_t n_datai;
+  const int32_t* datai; /* constant index pool (gather indices)                  */
+  uint64_t struct_hash; /* hash of everything except n, blob offsets and data    */
+} pm4_ir_t;
+
+typedef struct pm4_model pm4_model_t;
+
+/* Create a model on `device` from the IR (copied; caller may free it afterwards) and bind the
+ * specialised kernel module built for ir->struct_hash (`module_path`: a shared object produced
+ * by pymc4_b200.codegen; it is dlopen'ed and its embedded hash is checked).  Synchronous. */
+int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int device, pm4_model_t** out);
+int pm4_model_destroy(pm4_model_t* m);
+int pm4_model_dim(const pm4_model_t* m);
+
+/* Replace the constant data pools (same sizes) -- new observed values for the same model
+ * (reference: pm.sample(..., observed={...}), samplers.py:85-108).  Synchronous. */
+int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n_dataf,
+                       const int32_t* datai, int64_t n_datai);
+
+/* Parity check (a): joint log-density and its gradient in unconstrained space for C chains.
+ * Replaces parallel_logpfn + GradientTape (samplers.py:117-119, 762-770).
+ *   theta_dev [C, D], lp_dev [C], grad_dev [C, D] (grad_dev may be NULL). */
+int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta_dev, void* lp_dev,
+                  void* grad_dev, void* stream);
+
+/* Traced outputs for a batch of states: theta_dev [M, D] -> out_dev [M, det_row]. */
+int pm4_deterministics(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev,
+                       void* out_dev, void* stream);
+
+/* Step-size policy (tfp DualAveragingStepSizeAdaptation) */
+#define PM4_EPS_POOLED 0    /* one scalar shared by all chains (reference default, scalar step_size) */
+#define PM4_EPS_PER_CHAIN 1 /* step_size carries a leading chain axis: independent adaptation       */
+
+typedef struct pm4_adapt_cfg {
+  int32_t mode;                 /* PM4_EPS_*                                  */
+  int32_t num_adaptation_steps; /* = burn_in (inference/sampling.py:155-156)  */
+  double target_accept_prob;    /* 0.75                                       */
+  double exploration_shrinkage; /* 0.05                                       */
+  double step_count_smoothing;  /* 10                                         */
+  double decay_rate;            /* 0.75                                       */
+  int32_t enabled;              /* 0: fixed step size                         */
+  int32_t _pad;
+} pm4_adapt_cfg_t;
+
+typedef struct pm4_hmc_cfg {
+  int32_t C;                  /* chains                                                    */
+  int32_t num_results;        /* S                                                         */
+  int32_t num_burnin;         /* B : total transitions = B + S (tfp sample_chain, App. A.0) */
+  int32_t num_leapfrog_steps; /* L (reference default 3, samplers.py:305)                  */
+  double step_size;           /* initial epsilon                                           */
+  uint64_t seed;
+  pm4_adapt_cfg_t adapt;
+  int32_t warps_per_block;    /* 0 = library default                                       */
+  int32_t _pad;
+} pm4_hmc_cfg_t;
+
+/* Fixed-L HMC (tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC); App. A.4).
+ *   theta0_dev [C, D]            initial state (every chain may differ)
+ *   step_scale_dev [D] or NULL   per-dimension multiplier of epsilon
+ *   momenta_dev [B+S, C, D] or NULL   injected momenta (parity check (b)); NULL = Philox
+ *   uniforms_dev [B+S, C] or NULL     injected accept uniforms; NULL = Philox
+ * outputs (any may be NULL): states_dev [S, C, D], lp_dev [S, C], log_accept_dev [S, C],
+ *   accepted_dev [S, C] (u8), step_size_dev [C] final epsilon, traj_dev [B+S, C, D] the *proposed*
+ *   end point of every trajectory (parity check (b) compares these). */
+int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0_dev,
+                const void* step_scale_dev, const void* momenta_dev, const void* uniforms_dev,
+                void* states_dev, void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev,
+                void* step_size_dev, void* traj_dev, void* stream);
+
+typedef struct pm4_nuts_cfg {
+  int32_t C;
+  int32_t num_results;     /* S */
+  int32_t num_burnin;      /* B */
+  int32_t max_tree_depth;  /* 10  (tfp NoUTurnSampler default)      */
+  double max_energy_diff;  /* 1000                                   */
+  double step_size;        /* initial epsilon (reference default 0.1, samplers.py:406) */
+  uint64_t seed;
+  pm4_adapt_cfg_t adapt;
+  int32_t warps_per_block; /* 0 = library default */
+  int32_t _pad;
+} pm4_nuts_cfg_t;
+
+/* NUTS (tfp NoUTurnSampler: iterative tree doubling, generalised U-turn with checkpoints,
+ * multinomial sampling, biased progressive merge) under dual averaging.
+ * Replaces _BaseSampler._run_chains for sampler "nuts" (samplers.py:172-189, 342-419).
+ *   theta0_dev [C, D]; step_scale_dev [D] or NULL; momenta_dev [B+S, C, D] or NULL (replay).
+ * outputs (any may be NULL), all for the S kept draws, reference layout [S, C, ...]:
+ *   states_dev [S,C,D], lp_dev [S,C], leapfrogs_dev [S,C] i32, diverging_dev [S,C] u8,
+ *   energy_dev [S,C], log_accept_dev [S,C], depth_dev [S,C] i32, step_size_dev [C] final epsilon,
+ *   total_leapfrogs_dev [C] i64: leapfrogs over ALL B+S transitions (throughput accounting). */
+int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
+                 const void* step_scale_dev, const void* momenta_dev, void* states_dev,
+                 void* lp_dev, int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev,
+                 void* log_accept_dev, int32_t* depth_dev, void* step_size_dev,
+                 int64_t* total_leapfrogs_dev, void* stream);
+
+/* Bytes of device scratch pm4_nuts_run / pm4_hmc_run allocate internally for C chains. */
+int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth);
+
+/* Number of kernels launched by this library on the calling thread since the last reset. */
+int64_t pm4_launch_count(int reset);
+
+const char* pm4_last_error(void);
+int pm4_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM4B200_H */

@@ -1,0 +1,141 @@
+/* pm4_oracle.c -- CPU oracle for the pm.sample NUTS/HMC hot path.
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library; the product (pymc4_b200) never does and fails
+ * loudly when its CUDA library is missing.
+ *
+ * What it restates (plain C, float and double):
+ *   - the joint log-density of a lowered model: sum of reduce_sum(dist.log_prob(value)) plus
+ *     potentials (/root/reference/pymc4/flow/executor.py:171-187), evaluated in unconstrained
+ *     space with the transform log-det potentials (flow/transformed_executor.py:69-105), and its
+ *     gradient by reverse-mode differentiation of the same tape;
+ *   - the sampler the reference hands that density to
+ *     (/root/reference/pymc4/mcmc/samplers.py:172-189): tfp.mcmc.sample_chain over
+ *     NoUTurnSampler / HamiltonianMonteCarlo wrapped in DualAveragingStepSizeAdaptation.
+ *
+ * Provenance of the sampler arithmetic: it lives in the third-party dependency
+ * tensorflow-probability (`tfp-nightly`, UNPINNED in /root/reference/requirements.txt:4; the API
+ * the reference uses dates it to TFP ~0.12 / TF ~2.4), which is absent from /root/reference and
+ * not installable here.  The algorithm is restated from the published TFP sources
+ * (tensorflow_probability/python/mcmc/{nuts.py, sample.py, hmc.py,
+ * dual_averaging_step_size_adaptation.py, internal/leapfrog_integrator.py}); SURVEY.md App. A is
+ * the spec.  Parity pinning: the log-density part is pinned by the reference's own golden value
+ * (tests/test_8schools.py:61, -42.876114) and scipy cross-checks (tests/test_sampling.py:43-61);
+ * the NUTS/HMC internals are "parity unpinned" -- the reference holds no golden chains, tree
+ * sizes, divergence counts or step-size traces (tests/test_8schools.py:65-66 says so) and TFP
+ * cannot be run here.  Random numbers are a counter-based Philox4x32-10 stream shared with the
+ * CUDA kernels (not TF's stateless RNG), so oracle and device consume identical draws.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/pm4b200.h"
+
+/* purposes: 4th word of the Philox counter (must match csrc/pm4_philox.cuh) */
+#define PM4_RNG_MOMENTUM 0u
+#define PM4_RNG_DIRECTION 1u
+#define PM4_RNG_LEAF 2u
+#define PM4_RNG_MERGE 3u
+#define PM4_RNG_HMC 4u
+
+void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ---- float instantiation ---- */
+#define REAL float
+#define REAL_IS_DOUBLE 0
+#define NAME(x) x##_f32
+#define REXP expf
+#define RLOG logf
+#define RLOG1P log1pf
+#define RSQRT sqrtf
+#define RPOW powf
+#define RTANH tanhf
+#define RABS fabsf
+#define RLGAMMA lgammaf
+#define RCOS cosf
+#define RSIN sinf
+#include "pm4_oracle_impl.h"
+#undef REAL
+#undef REAL_IS_DOUBLE
+#undef NAME
+#undef REXP
+#undef RLOG
+#undef RLOG1P
+#undef RSQRT
+#undef RPOW
+#undef RTANH
+#undef RABS
+#undef RLGAMMA
+#undef RCOS
+#undef RSIN
+
+/* ---- double instantiation ---- */
+#define REAL double
+#define REAL_IS_DOUBLE 1
+#define NAME(x) x##_f64
+#define REXP exp
+#define RLOG log
+#define RLOG1P log1p
+#define RSQRT sqrt
+#define RPOW pow
+#define RTANH tanh
+#define RABS fabs
+#define RLGAMMA lgamma
+#define RCOS cos
+#define RSIN sin
+#include "pm4_oracle_impl.h"
+
+/* ---- dtype-dispatching entry points (signatures mirror include/pm4b200.h, host pointers) ---- */
+int pm4o_logp_grad(const pm4_ir_t* ir, int dtype, int C, const void* theta, void* lp, void* grad) {
+  return dtype == PM4_F64 ? pm4o_logp_grad_f64(ir, C, theta, lp, grad)
+                          : pm4o_logp_grad_f32(ir, C, theta, lp, grad);
+}
+
+int pm4o_deterministics(const pm4_ir_t* ir, int dtype, int64_t M, const void* theta, void* out) {
+  return dtype == PM4_F64 ? pm4o_deterministics_f64(ir, M, theta, out)
+                          : pm4o_deterministics_f32(ir, M, theta, out);
+}
+
+int pm4o_nuts_run(const pm4_ir_t* ir, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0,
+                  const void* step_scale, const void* momenta, void* states, void* lp,
+                  int32_t* leapfrogs, uint8_t* diverging, void* energy, void* log_accept,
+                  int32_t* depth, void* step_size_out, int64_t* total_leapfrogs) {
+  return dtype == PM4_F64
+             ? pm4o_nuts_run_f64(ir, cfg, theta0, step_scale, momenta, states, lp, leapfrogs,
+                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs)
+             : pm4o_nuts_run_f32(ir, cfg, theta0, step_scale, momenta, states, lp, leapfrogs,
+                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs);
+}
+
+int pm4o_hmc_run(const pm4_ir_t* ir, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0,
+                 const void* step_scale, const void* momenta, const void* uniforms, void* states,
+                 void* lp, void* log_accept, uint8_t* accepted, void* step_size_out, void* traj) {
+  return dtype == PM4_F64 ? pm4o_hmc_run_f64(ir, cfg, theta0, step_scale, momenta, uniforms, states,
+                                             lp, log_accept, accepted, step_size_out, traj)
+                          : pm4o_hmc_run_f32(ir, cfg, theta0, step_scale, momenta, uniforms, states,
+                                             lp, log_accept, accepted, step_size_out, traj);
+}
+
+/* momentum draw exposed for tests (device/host stream equality) */
+void pm4o_draw_momentum(int dtype, uint64_t seed, uint32_t chain, uint32_t t, int D, void* p) {
+  if (dtype == PM4_F64) draw_momentum_f64(seed, chain, t, D, (double*)p);
+  else draw_momentum_f32(seed, chain, t, D, (float*)p);
+}
+
+int pm4o_abi_version(void) { return PM4_ABI_VERSION; }

@@ -1,0 +1,144 @@
+"""ctypes front-end of the CPU oracle (oracle/pm4_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of bench.py.  The product package
+never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from pymc4_b200._cstructs import HMCCfg, NUTSCfg, PM4_F32, PM4_F64
+from pymc4_b200.ir import CIR, ModelIR, PackedIR
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpm4oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, -O2, OpenMP)."""
+    srcs = [os.path.join(_HERE, f) for f in ("pm4_oracle.c", "pm4_oracle_impl.h")]
+    srcs.append(os.path.join(_HERE, "..", "include", "pm4b200.h"))
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "libpm4oracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        irp = ctypes.POINTER(CIR)
+        L.pm4o_logp_grad.argtypes = [irp, i32, i32, vp, vp, vp]
+        L.pm4o_deterministics.argtypes = [irp, i32, i64, vp, vp]
+        L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 12
+        L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
+        L.pm4o_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
+                                         ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
+        L.pm4o_philox4x32_10.restype = None
+        L.pm4o_draw_momentum.argtypes = [i32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, i32, vp]
+        L.pm4o_draw_momentum.restype = None
+        _lib = L
+    return _lib
+
+
+def _np_dtype(dtype):
+    return np.float64 if dtype == PM4_F64 else np.float32
+
+
+def _code(dtype) -> int:
+    return PM4_F64 if np.dtype(dtype) == np.float64 else PM4_F32
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("oracle {} failed with code {}".format(what, rc))
+
+
+def philox4x32_10(ctr, key):
+    c = (ctypes.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
+    out = (ctypes.c_uint32 * 4)()
+    lib().pm4o_philox4x32_10(c, int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF, out)
+    return [int(v) for v in out]
+
+
+def draw_momentum(seed, chain, t, D, dtype=np.float32):
+    out = np.empty(D, dtype=dtype)
+    lib().pm4o_draw_momentum(_code(dtype), int(seed), int(chain), int(t), int(D), _ptr(out))
+    return out
+
+
+class Oracle:
+    """The oracle bound to one lowered model."""
+
+    def __init__(self, ir: ModelIR):
+        self.ir = ir
+        self.packed = PackedIR(ir)
+
+    def logp_grad(self, theta, dtype=np.float64, want_grad=True):
+        theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=dtype)
+        C, D = theta.shape
+        assert D == self.ir.D
+        lp = np.empty(C, dtype=dtype)
+        grad = np.empty((C, D), dtype=dtype) if want_grad else None
+        _check(lib().pm4o_logp_grad(self.packed.byref(), _code(dtype), C, _ptr(theta), _ptr(lp), _ptr(grad)),
+               "logp_grad")
+        return lp, grad
+
+    def deterministics(self, theta, dtype=np.float64):
+        theta = np.ascontiguousarray(theta, dtype=dtype).reshape(-1, self.ir.D)
+        out = np.empty((theta.shape[0], self.ir.det_row), dtype=dtype)
+        _check(lib().pm4o_deterministics(self.packed.byref(), _code(dtype), theta.shape[0], _ptr(theta), _ptr(out)),
+               "deterministics")
+        return out
+
+    def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None):
+        C, S, D = cfg.C, cfg.num_results, self.ir.D
+        theta0 = np.ascontiguousarray(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D)))
+        step_scale = None if step_scale is None else np.ascontiguousarray(step_scale, dtype=dtype)
+        momenta = None if momenta is None else np.ascontiguousarray(momenta, dtype=dtype)
+        out = dict(
+            states=np.empty((S, C, D), dtype=dtype), lp=np.empty((S, C), dtype=dtype),
+            leapfrogs=np.empty((S, C), dtype=np.int32), diverging=np.empty((S, C), dtype=np.uint8),
+            energy=np.empty((S, C), dtype=dtype), log_accept=np.empty((S, C), dtype=dtype),
+            depth=np.empty((S, C), dtype=np.int32), step_size=np.empty(C, dtype=dtype),
+            total_leapfrogs=np.empty(C, dtype=np.int64),
+        )
+        rc = lib().pm4o_nuts_run(
+            self.packed.byref(), _code(dtype), ctypes.byref(cfg), _ptr(theta0), _ptr(step_scale), _ptr(momenta),
+            _ptr(out["states"]), _ptr(out["lp"]), _ptr(out["leapfrogs"]), _ptr(out["diverging"]),
+            _ptr(out["energy"]), _ptr(out["log_accept"]), _ptr(out["depth"]), _ptr(out["step_size"]),
+            _ptr(out["total_leapfrogs"]))
+        _check(rc, "nuts_run")
+        return out
+
+    def hmc(self, cfg: HMCCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, uniforms=None):
+        C, S, D, T = cfg.C, cfg.num_results, self.ir.D, cfg.num_results + cfg.num_burnin
+        theta0 = np.ascontiguousarray(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D)))
+        step_scale = None if step_scale is None else np.ascontiguousarray(step_scale, dtype=dtype)
+        momenta = None if momenta is None else np.ascontiguousarray(momenta, dtype=dtype)
+        uniforms = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=dtype)
+        out = dict(
+            states=np.empty((S, C, D), dtype=dtype), lp=np.empty((S, C), dtype=dtype),
+            log_accept=np.empty((S, C), dtype=dtype), accepted=np.empty((S, C), dtype=np.uint8),
+            step_size=np.empty(C, dtype=dtype), traj=np.empty((T, C, D), dtype=dtype),
+        )
+        rc = lib().pm4o_hmc_run(
+            self.packed.byref(), _code(dtype), ctypes.byref(cfg), _ptr(theta0), _ptr(step_scale), _ptr(momenta),
+            _ptr(uniforms), _ptr(out["states"]), _ptr(out["lp"]), _ptr(out["log_accept"]),
+            _ptr(out["accepted"]), _ptr(out["step_size"]), _ptr(out["traj"]))
+        _check(rc, "hmc_run")
+        return out

@@ -1,0 +1,690 @@
+/* pm4_oracle_impl.h -- body of the CPU oracle, compiled twice (REAL = float, double).
+ *
+ * TEST INFRASTRUCTURE ONLY.  See pm4_oracle.c for the header comment and provenance.
+ * Every function is suffixed with SFX (f32 / f64) through the NAME() macro.
+ */
+
+/* ----------------------------------------------------------------------------------------
+ * Log-densities: the TFP log_prob closed forms the reference delegates to
+ * (/root/reference/pymc4/distributions/continuous.py:108-112 Normal -> tfd.Normal,
+ *  :234-238 HalfNormal, :659-663 HalfCauchy(loc=0); discrete.py:75-78 Bernoulli(probs=),
+ *  :500-503 Poisson(rate=)); SURVEY App. B.  Each returns lp and the partial derivatives
+ *  w.r.t. value and parameters.
+ * -------------------------------------------------------------------------------------- */
+static inline REAL NAME(lpdf)(int kind, REAL x, const REAL* q, REAL* dx, REAL* dq) {
+  const REAL HALF_LOG_2PI = (REAL)0.91893853320467274178;
+  const REAL HALF_LOG_HALF_PI = (REAL)0.22579135264472743236;
+  const REAL LOG_2_OVER_PI = (REAL)-0.45158270528945486473;
+  dq[0] = dq[1] = dq[2] = 0;
+  *dx = 0;
+  switch (kind) {
+    case PM4_T_POTENTIAL:
+      *dx = 1;
+      return x;
+    case PM4_T_NORMAL: {
+      REAL mu = q[0], s = q[1];
+      REAL w = x / s - mu / s; /* tfd.Normal divides before subtracting */
+      *dx = -w / s;
+      dq[0] = w / s;
+      dq[1] = (w * w - 1) / s;
+      return (REAL)-0.5 * w * w - HALF_LOG_2PI - RLOG(s);
+    }
+    case PM4_T_HALFNORMAL: {
+      REAL s = q[0];
+      REAL w = x / s;
+      *dx = -w / s;
+      dq[0] = (w * w - 1) / s;
+      if (x < 0) return -(REAL)INFINITY;
+      return (REAL)-0.5 * w * w - HALF_LOG_HALF_PI - RLOG(s);
+    }
+    case PM4_T_HALFCAUCHY: {
+      REAL s = q[0];
+      REAL w = x / s;
+      REAL den = 1 + w * w;
+      *dx = -2 * w / (s * den);
+      dq[0] = (2 * w * w / den - 1) / s;
+      if (x < 0) return -(REAL)INFINITY;
+      return LOG_2_OVER_PI - RLOG(s) - RLOG1P(w * w);
+    }
+    case PM4_T_BERNOULLI: {
+      REAL p = q[0];
+      /* xlogy(x, p) + xlog1py(1 - x, -p) */
+      REAL a = (x == 0) ? 0 : x * RLOG(p);
+      REAL b = (1 - x == 0) ? 0 : (1 - x) * RLOG1P(-p);
+      dq[0] = ((x == 0) ? 0 : x / p) - ((1 - x == 0) ? 0 : (1 - x) / (1 - p));
+      *dx = RLOG(p) - RLOG1P(-p);
+      return a + b;
+    }
+    case PM4_T_POISSON: {
+      REAL lam = q[0];
+      REAL a = (x == 0) ? 0 : x * RLOG(lam);
+      dq[0] = ((x == 0) ? 0 : x / lam) - 1;
+      *dx = 0; /* free Poisson values are rejected by the host (discrete + gradient sampler) */
+      return a - lam - RLGAMMA(x + 1);
+    }
+  }
+  return (REAL)NAN;
+}
+
+static inline REAL NAME(digamma)(REAL x) {
+  REAL r = 0;
+  while (x < 6) { r -= 1 / x; x += 1; }
+  REAL f = 1 / (x * x);
+  return r + RLOG(x) - (REAL)0.5 / x -
+         f * ((REAL)(1.0 / 12) - f * ((REAL)(1.0 / 120) - f * ((REAL)(1.0 / 252) - f * ((REAL)(1.0 / 240)))));
+}
+
+static inline REAL NAME(sigmoid)(REAL v) { return 1 / (1 + REXP(-v)); }
+static inline REAL NAME(softplus)(REAL v) { return v > 0 ? v + RLOG1P(REXP(-v)) : RLOG1P(REXP(v)); }
+
+/* ----------------------------------------------------------------------------------------
+ * Tape VM: one term, all n elements.  Follows SamplingState.collect_log_prob
+ * (/root/reference/pymc4/flow/executor.py:171-187): sum over distributions of
+ * reduce_sum(dist.log_prob(value)) + sum over potentials of reduce_sum(value).
+ * Adjoint sweep = reverse-mode autodiff of the same tape (what tf.GradientTape does for
+ * tfp.math.value_and_gradient in the leapfrog integrator).
+ * -------------------------------------------------------------------------------------- */
+#define PM4O_MAXREG 256
+
+static void NAME(tape_forward)(const pm4_ir_t* ir, int ob, int oe, int i, const REAL* x,
+                               const REAL* z, REAL* v) {
+  for (int k = ob; k < oe; ++k) {
+    const pm4_op_t* o = &ir->ops[k];
+    REAL a = o->a >= 0 ? v[o->a] : 0, b = o->b >= 0 ? v[o->b] : 0, r = 0;
+    switch (o->opcode) {
+      case PM4_OP_LD_CONST: r = (REAL)o->imm; break;
+      case PM4_OP_LD_DATA: r = (REAL)ir->dataf[o->blob + (o->mode == PM4_MODE_ELEM ? i : 0)]; break;
+      case PM4_OP_LD_X:
+      case PM4_OP_LD_Z: {
+        int64_t pos = o->base;
+        if (o->mode == PM4_MODE_ELEM) pos += i;
+        else if (o->mode == PM4_MODE_GATHER) pos += ir->datai[o->blob + i];
+        r = (o->opcode == PM4_OP_LD_X) ? x[pos] : z[pos];
+      } break;
+      case PM4_OP_ADD: r = a + b; break;
+      case PM4_OP_SUB: r = a - b; break;
+      case PM4_OP_MUL: r = a * b; break;
+      case PM4_OP_DIV: r = a / b; break;
+      case PM4_OP_POW: r = RPOW(a, b); break;
+      case PM4_OP_NEG: r = -a; break;
+      case PM4_OP_EXP: r = REXP(a); break;
+      case PM4_OP_LOG: r = RLOG(a); break;
+      case PM4_OP_LOG1P: r = RLOG1P(a); break;
+      case PM4_OP_SQRT: r = RSQRT(a); break;
+      case PM4_OP_SQUARE: r = a * a; break;
+      case PM4_OP_SIGMOID: r = NAME(sigmoid)(a); break;
+      case PM4_OP_SOFTPLUS: r = NAME(softplus)(a); break;
+      case PM4_OP_TANH: r = RTANH(a); break;
+      case PM4_OP_ABS: r = RABS(a); break;
+      case PM4_OP_RECIP: r = 1 / a; break;
+      case PM4_OP_LGAMMA: r = RLGAMMA(a); break;
+    }
+    v[o->dst] = r;
+  }
+}
+
+static void NAME(tape_backward)(const pm4_ir_t* ir, int ob, int oe, int i, const REAL* v, REAL* adj,
+                                REAL* gx, REAL* gz) {
+  for (int k = oe - 1; k >= ob; --k) {
+    const pm4_op_t* o = &ir->ops[k];
+    REAL g = adj[o->dst];
+    if (g == 0) continue;
+    REAL a = o->a >= 0 ? v[o->a] : 0, b = o->b >= 0 ? v[o->b] : 0, r = v[o->dst];
+    switch (o->opcode) {
+      case PM4_OP_LD_X:
+      case PM4_OP_LD_Z: {
+        int64_t pos = o->base;
+        if (o->mode == PM4_MODE_ELEM) pos += i;
+        else if (o->mode == PM4_MODE_GATHER) pos += ir->datai[o->blob + i];
+        if (o->opcode == PM4_OP_LD_X) gx[pos] += g; else gz[pos] += g;
+      } break;
+      case PM4_OP_ADD: adj[o->a] += g; adj[o->b] += g; break;
+      case PM4_OP_SUB: adj[o->a] += g; adj[o->b] -= g; break;
+      case PM4_OP_MUL: adj[o->a] += g * b; adj[o->b] += g * a; break;
+      case PM4_OP_DIV: adj[o->a] += g / b; adj[o->b] -= g * r / b; break;
+      case PM4_OP_POW: adj[o->a] += g * b * RPOW(a, b - 1); if (a > 0) adj[o->b] += g * r * RLOG(a); break;
+      case PM4_OP_NEG: adj[o->a] -= g; break;
+      case PM4_OP_EXP: adj[o->a] += g * r; break;
+      case PM4_OP_LOG: adj[o->a] += g / a; break;
+      case PM4_OP_LOG1P: adj[o->a] += g / (1 + a); break;
+      case PM4_OP_SQRT: adj[o->a] += g / (2 * r); break;
+      case PM4_OP_SQUARE: adj[o->a] += 2 * g * a; break;
+      case PM4_OP_SIGMOID: adj[o->a] += g * r * (1 - r); break;
+      case PM4_OP_SOFTPLUS: adj[o->a] += g * NAME(sigmoid)(a); break;
+      case PM4_OP_TANH: adj[o->a] += g * (1 - r * r); break;
+      case PM4_OP_ABS: adj[o->a] += (a > 0) ? g : ((a < 0) ? -g : 0); break;
+      case PM4_OP_RECIP: adj[o->a] -= g * r * r; break;
+      case PM4_OP_LGAMMA: adj[o->a] += g * NAME(digamma)(a); break;
+      default: break;
+    }
+  }
+}
+
+/* workspace for one chain */
+typedef struct NAME(ws) {
+  int D;
+  REAL *x, *gx, *gz;
+} NAME(ws_t);
+
+/* x = shift + scale * f(theta): inverse of the unconstraining transform
+ * (/root/reference/pymc4/flow/transformed_executor.py:73-75; transforms.py:116-181) */
+static void NAME(constrain)(const pm4_ir_t* ir, const REAL* theta, REAL* x) {
+  for (int r = 0; r < ir->n_rv; ++r) {
+    const pm4_rv_t* rv = &ir->rvs[r];
+    for (int j = rv->offset; j < rv->offset + rv->size; ++j) {
+      if (rv->transform == PM4_TR_EXP) x[j] = (REAL)rv->shift + (REAL)rv->scale * REXP(theta[j]);
+      else if (rv->transform == PM4_TR_SIGMOID) x[j] = (REAL)rv->shift + (REAL)rv->scale * NAME(sigmoid)(theta[j]);
+      else x[j] = theta[j];
+    }
+  }
+}
+
+/* joint log-density and gradient in unconstrained space for ONE chain */
+static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta, REAL* grad) {
+  const int D = ir->D;
+  REAL *x = ws->x, *gx = ws->gx, *gz = ws->gz;
+  NAME(constrain)(ir, theta, x);
+  for (int j = 0; j < D; ++j) gx[j] = gz[j] = 0;
+  REAL v[PM4O_MAXREG], adj[PM4O_MAXREG];
+  REAL lp = 0;
+  for (int t = 0; t < ir->n_terms; ++t) {
+    const pm4_term_t* tm = &ir->terms[t];
+    REAL term_sum = 0;
+    for (int i = 0; i < tm->n; ++i) {
+      NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, theta, v);
+      REAL q[3] = {0, 0, 0}, dq[3], dx;
+      for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+      term_sum += NAME(lpdf)(tm->kind, v[tm->value_reg], q, &dx, dq);
+      if (grad) {
+        for (int k = 0; k < tm->n_regs; ++k) adj[k] = 0;
+        adj[tm->value_reg] += dx;
+        for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) adj[tm->param_reg[k]] += dq[k];
+        NAME(tape_backward)(ir, tm->op_begin, tm->op_end, i, v, adj, gx, gz);
+      }
+    }
+    lp += term_sum; /* reduce_sum per distribution, then sum over distributions */
+  }
+  if (grad) {
+    for (int r = 0; r < ir->n_rv; ++r) {
+      const pm4_rv_t* rv = &ir->rvs[r];
+      for (int j = rv->offset; j < rv->offset + rv->size; ++j) {
+        REAL dxdz = 1;
+        if (rv->transform == PM4_TR_EXP) dxdz = x[j] - (REAL)rv->shift;
+        else if (rv->transform == PM4_TR_SIGMOID) {
+          REAL s = (x[j] - (REAL)rv->shift) / (REAL)rv->scale;
+          dxdz = (REAL)rv->scale * s * (1 - s);
+        }
+        grad[j] = gx[j] * dxdz + gz[j];
+      }
+    }
+  }
+  return lp;
+}
+
+static NAME(ws_t) NAME(ws_new)(int D) {
+  NAME(ws_t) w;
+  w.D = D;
+  w.x = (REAL*)calloc((size_t)(3 * D + 3), sizeof(REAL));
+  w.gx = w.x + D;
+  w.gz = w.gx + D;
+  return w;
+}
+static void NAME(ws_free)(NAME(ws_t)* w) { free(w->x); }
+
+int NAME(pm4o_logp_grad)(const pm4_ir_t* ir, int C, const REAL* theta, REAL* lp, REAL* grad) {
+  if (!ir || !theta || !lp) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  const int D = ir->D;
+#pragma omp parallel
+  {
+    NAME(ws_t) ws = NAME(ws_new)(D);
+#pragma omp for schedule(static)
+    for (int c = 0; c < C; ++c)
+      lp[c] = NAME(logp_grad1)(ir, &ws, theta + (size_t)c * D, grad ? grad + (size_t)c * D : NULL);
+    NAME(ws_free)(&ws);
+  }
+  return PM4_OK;
+}
+
+int NAME(pm4o_deterministics)(const pm4_ir_t* ir, int64_t M, const REAL* theta, REAL* out) {
+  const int D = ir->D;
+#pragma omp parallel
+  {
+    REAL* x = (REAL*)malloc(sizeof(REAL) * (size_t)(D + 1));
+    REAL v[PM4O_MAXREG];
+#pragma omp for schedule(static)
+    for (int64_t m = 0; m < M; ++m) {
+      const REAL* th = theta + (size_t)m * D;
+      NAME(constrain)(ir, th, x);
+      for (int d = 0; d < ir->n_dets; ++d) {
+        const pm4_det_t* dt = &ir->dets[d];
+        for (int i = 0; i < dt->n; ++i) {
+          NAME(tape_forward)(ir, dt->op_begin, dt->op_end, i, x, th, v);
+          out[(size_t)m * ir->det_row + dt->out_offset + i] = v[dt->value_reg];
+        }
+      }
+    }
+    free(x);
+  }
+  return PM4_OK;
+}
+
+/* ----------------------------------------------------------------------------------------
+ * Random numbers: Philox4x32-10 (Salmon et al., SC'11), counter = (chain, transition, slot,
+ * purpose), key = seed.  The CUDA kernels use the identical stream (csrc/pm4_philox.cuh), which
+ * is what makes the sampler host-replayable.  TFP uses TF stateless RNG with split seeds
+ * (SURVEY App. A.1 "RNG consumption is positional"); the counter layout below reproduces that
+ * positional structure: one momentum draw per transition, one direction bit + one merge uniform
+ * per doubling, one uniform per leaf.
+ * -------------------------------------------------------------------------------------- */
+static inline REAL NAME(u01)(const uint32_t* r) {
+#if REAL_IS_DOUBLE
+  return (REAL)((((uint64_t)(r[0] >> 5)) * 67108864.0 + (double)(r[1] >> 6)) * (1.0 / 9007199254740992.0));
+#else
+  return (REAL)(r[0] >> 8) * (REAL)(1.0 / 16777216.0);
+#endif
+}
+
+static inline void NAME(box_muller)(uint32_t xa, uint32_t xb, REAL* n0, REAL* n1) {
+#if REAL_IS_DOUBLE
+  REAL u1 = ((REAL)xa + 1.0) * (1.0 / 4294967296.0);
+  REAL u2 = (REAL)xb * (1.0 / 4294967296.0);
+#else
+  REAL u1 = (REAL)((xa >> 8) + 1u) * (REAL)(1.0 / 16777216.0);
+  REAL u2 = (REAL)(xb >> 8) * (REAL)(1.0 / 16777216.0);
+#endif
+  REAL rad = RSQRT((REAL)-2 * RLOG(u1));
+  REAL ang = (REAL)6.283185307179586476925 * u2;
+  *n0 = rad * RCOS(ang);
+  *n1 = rad * RSIN(ang);
+}
+
+/* momentum for every dimension of one chain at one transition; dimension j is owned by
+ * lane j%32, register j/32 of the chain's warp and four registers share one Philox call */
+static void NAME(draw_momentum)(uint64_t seed, uint32_t chain, uint32_t t, int D, REAL* p) {
+  for (int j = 0; j < D; ++j) {
+    int lane = j & 31, r = j >> 5, q = r >> 2, e = r & 3;
+    uint32_t ctr[4] = {chain, t, (uint32_t)(q * 32 + lane), PM4_RNG_MOMENTUM}, out[4];
+    pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+    REAL n[4];
+    NAME(box_muller)(out[0], out[1], &n[0], &n[1]);
+    NAME(box_muller)(out[2], out[3], &n[2], &n[3]);
+    p[j] = n[e];
+  }
+}
+
+static inline REAL NAME(draw_u)(uint64_t seed, uint32_t chain, uint32_t t, uint32_t slot, uint32_t purpose) {
+  uint32_t ctr[4] = {chain, t, slot, purpose}, out[4];
+  pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+  return NAME(u01)(out);
+}
+
+static inline int NAME(draw_bit)(uint64_t seed, uint32_t chain, uint32_t t, uint32_t slot, uint32_t purpose) {
+  uint32_t ctr[4] = {chain, t, slot, purpose}, out[4];
+  pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), out);
+  return (int)(out[0] & 1u);
+}
+
+/* ----------------------------------------------------------------------------------------
+ * Leapfrog: tfp SimpleLeapfrogIntegrator: half kick, L x (drift, full kick),
+ * half un-kick.  eps[j] = signed step * per-dimension scale.
+ * -------------------------------------------------------------------------------------- */
+static void NAME(leapfrog)(const pm4_ir_t* ir, NAME(ws_t)* ws, int L, REAL eps, const REAL* scale,
+                           REAL* theta, REAL* p, REAL* grad, REAL* lp) {
+  const int D = ir->D;
+  for (int j = 0; j < D; ++j) {
+    REAL e = scale ? eps * scale[j] : eps;
+    p[j] = p[j] + ((REAL)0.5 * e) * grad[j];
+  }
+  for (int l = 0; l < L; ++l) {
+    for (int j = 0; j < D; ++j) {
+      REAL e = scale ? eps * scale[j] : eps;
+      theta[j] = theta[j] + e * p[j];
+    }
+    *lp = NAME(logp_grad1)(ir, ws, theta, grad);
+    for (int j = 0; j < D; ++j) {
+      REAL e = scale ? eps * scale[j] : eps;
+      p[j] = p[j] + e * grad[j];
+    }
+  }
+  for (int j = 0; j < D; ++j) {
+    REAL e = scale ? eps * scale[j] : eps;
+    p[j] = p[j] - ((REAL)0.5 * e) * grad[j];
+  }
+}
+
+static inline REAL NAME(dot)(const REAL* a, const REAL* b, int D) {
+  REAL s = 0;
+  for (int j = 0; j < D; ++j) s += a[j] * b[j];
+  return s;
+}
+
+static inline REAL NAME(logaddexp)(REAL a, REAL b) {
+  if (a == -(REAL)INFINITY) return b;
+  if (b == -(REAL)INFINITY) return a;
+  REAL m = a > b ? a : b;
+  return m + RLOG1P(REXP(-RABS(a - b)));
+}
+
+/* ----------------------------------------------------------------------------------------
+ * Dual averaging: tfp DualAveragingStepSizeAdaptation.one_step, as wired by
+ * PyMC4 (/root/reference/pymc4/mcmc/samplers.py:400-405; inference/sampling.py:155-156).
+ * -------------------------------------------------------------------------------------- */
+typedef struct NAME(da) {
+  REAL eps0, eps, error_sum, log_avg, log_shrink_target;
+} NAME(da_t);
+
+static void NAME(da_init)(NAME(da_t)* s, REAL eps0) {
+  s->eps0 = eps0;
+  s->eps = eps0;
+  s->error_sum = 0;
+  s->log_avg = 0;
+  s->log_shrink_target = RLOG((REAL)10 * eps0);
+}
+
+/* called after transition t (0-based) with the (cross-chain or per-chain) mean accept prob */
+static void NAME(da_update)(NAME(da_t)* s, const pm4_adapt_cfg_t* a, int t, REAL accept) {
+  if (!a->enabled) return;
+  REAL step = (REAL)(t + 1);
+  s->error_sum += (REAL)a->target_accept_prob - accept;
+  REAL log_eps = s->log_shrink_target -
+                 s->error_sum * RSQRT(step) / (((REAL)a->step_count_smoothing + step) * (REAL)a->exploration_shrinkage);
+  REAL eta = RPOW(step, -(REAL)a->decay_rate);
+  s->log_avg = eta * log_eps + (1 - eta) * s->log_avg;
+  if (t < a->num_adaptation_steps) s->eps = REXP(log_eps);
+  else if (t == a->num_adaptation_steps) s->eps = REXP(s->log_avg);
+}
+
+/* ----------------------------------------------------------------------------------------
+ * One NUTS transition for one chain: tfp NoUTurnSampler.one_step -> _loop_tree_doubling ->
+ * _build_sub_tree -> _loop_build_sub_tree, in its per-chain-equivalent form
+ * (a chain stops where TFP's mask for it turns false).
+ * -------------------------------------------------------------------------------------- */
+typedef struct NAME(nuts_buf) {
+  REAL *p0, *cur_th, *cur_p, *cur_g, *oth_th, *oth_p, *oth_g, *cand_th, *cand_g, *sub_th, *sub_g,
+      *rho, *rho_sub, *rho_prev, *tmp, *mem_p, *mem_rho;
+} NAME(nuts_buf_t);
+
+typedef struct NAME(nuts_out) {
+  REAL lp, energy, log_accept;
+  int leapfrogs, diverging, depth;
+} NAME(nuts_out_t);
+
+static void NAME(nuts_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, NAME(nuts_buf_t)* b,
+                                  const pm4_nuts_cfg_t* cfg, uint32_t chain, uint32_t t, REAL eps,
+                                  const REAL* scale, const REAL* injected_p, REAL* theta, REAL* grad,
+                                  REAL* lp, NAME(nuts_out_t)* out) {
+  const int D = ir->D;
+  const size_t nb = sizeof(REAL) * (size_t)D;
+  const REAL NEG_INF = -(REAL)INFINITY;
+  if (injected_p) memcpy(b->p0, injected_p, nb);
+  else NAME(draw_momentum)(cfg->seed, chain, t, D, b->p0);
+  const REAL H0 = *lp - (REAL)0.5 * NAME(dot)(b->p0, b->p0, D);
+
+  /* both ends of the trajectory start at the current point; `cur` is the end being extended,
+   * `oth` the far end; cur_is_right tells which is which */
+  memcpy(b->cur_th, theta, nb); memcpy(b->cur_p, b->p0, nb); memcpy(b->cur_g, grad, nb);
+  memcpy(b->oth_th, theta, nb); memcpy(b->oth_p, b->p0, nb); memcpy(b->oth_g, grad, nb);
+  REAL cur_lp = *lp, oth_lp = *lp;
+  int cur_is_right = 1;
+
+  memcpy(b->cand_th, theta, nb); memcpy(b->cand_g, grad, nb);
+  REAL cand_lp = *lp, cand_energy = H0, w = 0;
+  memcpy(b->rho, b->p0, nb);
+  REAL ediff_sum = 0;
+  int nleap = 0, cont = 1, not_div = 1, depth = 0;
+
+  while (depth < cfg->max_tree_depth && cont) {
+    const int dir = NAME(draw_bit)(cfg->seed, chain, t, (uint32_t)depth, PM4_RNG_DIRECTION);
+    if (dir != cur_is_right) { /* extend the other end: swap roles */
+      REAL* s;
+      s = b->cur_th; b->cur_th = b->oth_th; b->oth_th = s;
+      s = b->cur_p; b->cur_p = b->oth_p; b->oth_p = s;
+      s = b->cur_g; b->cur_g = b->oth_g; b->oth_g = s;
+      REAL tl = cur_lp; cur_lp = oth_lp; oth_lp = tl;
+      cur_is_right = dir;
+    }
+    const REAL eps_s = dir ? eps : -eps;
+    const int nsteps = 1 << depth;
+    for (int j = 0; j < D; ++j) b->rho_sub[j] = 0;
+    REAL w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
+    memcpy(b->sub_th, b->cur_th, nb); memcpy(b->sub_g, b->cur_g, nb);
+    int cont_sub = 1, sub_leaps = 0;
+
+    for (int i = 0; i < nsteps && cont_sub; ++i) {
+      NAME(leapfrog)(ir, ws, 1, eps_s, scale, b->cur_th, b->cur_p, b->cur_g, &cur_lp);
+      sub_leaps += 1;
+      memcpy(b->rho_prev, b->rho_sub, nb);
+      for (int j = 0; j < D; ++j) b->rho_sub[j] += b->cur_p[j];
+
+      /* U-turn checks against the checkpoints that close a balanced sub-subtree at leaf i:
+       * slots [popcount(i) - trailing_ones(i), popcount(i)) -- the closed form of tfp's
+       * build_tree_uturn_instruction + generate_efficient_write_read_instruction tables */
+      int no_uturn = 1;
+      if (i & 1) {
+        int pc = __builtin_popcount((unsigned)i), t1 = __builtin_ctz(~(unsigned)i);
+        for (int s = pc - t1; s < pc && no_uturn; ++s) {
+          const REAL* mp = b->mem_p + (size_t)s * D;
+          const REAL* mr = b->mem_rho + (size_t)s * D;
+          for (int j = 0; j < D; ++j) b->tmp[j] = b->rho_sub[j] - mr[j];
+          no_uturn = (NAME(dot)(b->tmp, mp, D) > 0) && (NAME(dot)(b->tmp, b->cur_p, D) > 0);
+        }
+      } else { /* even leaves are checkpointed into slot popcount(i) */
+        int s = __builtin_popcount((unsigned)i);
+        memcpy(b->mem_p + (size_t)s * D, b->cur_p, nb);
+        memcpy(b->mem_rho + (size_t)s * D, b->rho_prev, nb);
+      }
+
+      REAL energy = cur_lp - (REAL)0.5 * NAME(dot)(b->cur_p, b->cur_p, D);
+      if (isnan(energy)) energy = NEG_INF;
+      const REAL dH = energy - H0;
+      const int not_divergent = (-dH < (REAL)cfg->max_energy_diff);
+      const REAL w_new = NAME(logaddexp)(w_sub, dH);
+      const REAL thresh = dH - w_new;
+      const REAL u = RLOG1P(-NAME(draw_u)(cfg->seed, chain, t, ((uint32_t)depth << 20) | (uint32_t)i, PM4_RNG_LEAF));
+      if (u <= thresh) {
+        memcpy(b->sub_th, b->cur_th, nb); memcpy(b->sub_g, b->cur_g, nb);
+        sub_lp = cur_lp; sub_energy = energy;
+      }
+      w_sub = w_new;
+      const int cont_leaf = not_divergent; /* & continue_tree_previous, which is 1 here */
+      not_div = not_div && not_divergent;
+      if (cont_leaf) sub_ediff += REXP(dH < 0 ? dH : 0);
+      cont_sub = no_uturn && cont_leaf;
+    }
+
+    /* merge the subtree into the trajectory (biased progressive sampling) */
+    ediff_sum += sub_ediff;
+    nleap += sub_leaps;
+    const REAL tree_w = cont_sub ? w_sub : NEG_INF;
+    const REAL thresh = tree_w - w;
+    const REAL um = RLOG1P(-NAME(draw_u)(cfg->seed, chain, t, (uint32_t)depth, PM4_RNG_MERGE));
+    if ((um <= thresh) && cont_sub) {
+      memcpy(b->cand_th, b->sub_th, nb); memcpy(b->cand_g, b->sub_g, nb);
+      cand_lp = sub_lp; cand_energy = sub_energy;
+    }
+    w = NAME(logaddexp)(tree_w, w);
+    for (int j = 0; j < D; ++j) b->rho[j] += b->rho_sub[j];
+    const REAL *p_left = cur_is_right ? b->oth_p : b->cur_p, *p_right = cur_is_right ? b->cur_p : b->oth_p;
+    const int no_uturn_traj = (NAME(dot)(b->rho, p_left, D) > 0) && (NAME(dot)(b->rho, p_right, D) > 0);
+    cont = cont_sub && no_uturn_traj;
+    depth += 1;
+  }
+  memcpy(theta, b->cand_th, nb); memcpy(grad, b->cand_g, nb);
+  *lp = cand_lp;
+  out->lp = cand_lp;
+  out->energy = cand_energy;
+  out->log_accept = RLOG(ediff_sum / (REAL)nleap);
+  out->leapfrogs = nleap;
+  out->diverging = !not_div;
+  out->depth = depth;
+}
+
+static NAME(nuts_buf_t) NAME(nuts_buf_new)(int D, int max_depth) {
+  NAME(nuts_buf_t) b;
+  size_t nvec = 15 + 2 * (size_t)(max_depth + 1);
+  REAL* base = (REAL*)calloc(nvec * (size_t)(D + 1), sizeof(REAL));
+  REAL** f[] = {&b.p0, &b.cur_th, &b.cur_p, &b.cur_g, &b.oth_th, &b.oth_p, &b.oth_g, &b.cand_th,
+                &b.cand_g, &b.sub_th, &b.sub_g, &b.rho, &b.rho_sub, &b.rho_prev, &b.tmp};
+  for (int k = 0; k < 15; ++k) *f[k] = base + (size_t)k * D;
+  b.mem_p = base + (size_t)15 * D;
+  b.mem_rho = b.mem_p + (size_t)(max_depth + 1) * D;
+  return b;
+}
+/* the base pointer may have been swapped between cur_* and oth_*: free the smallest */
+static void NAME(nuts_buf_free)(NAME(nuts_buf_t)* b) { free(b->p0); }
+
+/* sample_chain(num_results=S, num_burnin_steps=B) with NUTS under dual averaging
+ * (/root/reference/pymc4/mcmc/samplers.py:172-189). */
+int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REAL* theta0,
+                        const REAL* step_scale, const REAL* momenta, REAL* states, REAL* lp_out,
+                        int32_t* leapfrogs, uint8_t* diverging, REAL* energy, REAL* log_accept,
+                        int32_t* depth_out, REAL* step_size_out, int64_t* total_leapfrogs) {
+  const int D = ir->D, C = cfg->C, B = cfg->num_burnin, S = cfg->num_results, T = B + S;
+  if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 20) return PM4_EINVAL;
+  REAL* th = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* gr = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* lp = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  REAL* acc = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  int64_t* tot = (int64_t*)calloc((size_t)C, sizeof(int64_t));
+  memcpy(th, theta0, sizeof(REAL) * (size_t)C * D);
+  const int pooled = cfg->adapt.mode == PM4_EPS_POOLED;
+  NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)(pooled ? 1 : C));
+  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init)(&da[c], (REAL)cfg->step_size);
+
+#pragma omp parallel
+  {
+    NAME(ws_t) ws = NAME(ws_new)(D);
+    NAME(nuts_buf_t) nb = NAME(nuts_buf_new)(D, cfg->max_tree_depth);
+    REAL* base = nb.p0;
+    /* bootstrap_results: log-density and gradient at the initial point */
+#pragma omp for schedule(static)
+    for (int c = 0; c < C; ++c) lp[c] = NAME(logp_grad1)(ir, &ws, th + (size_t)c * D, gr + (size_t)c * D);
+
+    if (pooled) {
+      for (int t = 0; t < T; ++t) {
+#pragma omp for schedule(dynamic, 1)
+        for (int c = 0; c < C; ++c) {
+          NAME(nuts_out_t) o;
+          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)c, (uint32_t)t, da[0].eps, step_scale,
+                                momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
+                                gr + (size_t)c * D, &lp[c], &o);
+          acc[c] = REXP(o.log_accept);
+          tot[c] += o.leapfrogs;
+          if (t >= B) {
+            size_t k = (size_t)(t - B) * C + c;
+            if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
+            if (lp_out) lp_out[k] = o.lp;
+            if (leapfrogs) leapfrogs[k] = o.leapfrogs;
+            if (diverging) diverging[k] = (uint8_t)o.diverging;
+            if (energy) energy[k] = o.energy;
+            if (log_accept) log_accept[k] = o.log_accept;
+            if (depth_out) depth_out[k] = o.depth;
+          }
+        }
+#pragma omp single
+        {
+          /* reduce_logmeanexp over all chains, then exp: the arithmetic mean accept prob */
+          REAL s = 0;
+          for (int c = 0; c < C; ++c) s += acc[c];
+          NAME(da_update)(&da[0], &cfg->adapt, t, s / (REAL)C);
+        }
+      }
+    } else {
+#pragma omp for schedule(dynamic, 1)
+      for (int c = 0; c < C; ++c) {
+        for (int t = 0; t < T; ++t) {
+          NAME(nuts_out_t) o;
+          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)c, (uint32_t)t, da[c].eps, step_scale,
+                                momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
+                                gr + (size_t)c * D, &lp[c], &o);
+          NAME(da_update)(&da[c], &cfg->adapt, t, REXP(o.log_accept));
+          tot[c] += o.leapfrogs;
+          if (t >= B) {
+            size_t k = (size_t)(t - B) * C + c;
+            if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
+            if (lp_out) lp_out[k] = o.lp;
+            if (leapfrogs) leapfrogs[k] = o.leapfrogs;
+            if (diverging) diverging[k] = (uint8_t)o.diverging;
+            if (energy) energy[k] = o.energy;
+            if (log_accept) log_accept[k] = o.log_accept;
+            if (depth_out) depth_out[k] = o.depth;
+          }
+        }
+      }
+    }
+    nb.p0 = base;
+    NAME(nuts_buf_free)(&nb);
+    NAME(ws_free)(&ws);
+  }
+  for (int c = 0; c < C; ++c) {
+    if (step_size_out) step_size_out[c] = da[pooled ? 0 : c].eps;
+    if (total_leapfrogs) total_leapfrogs[c] = tot[c];
+  }
+  free(th); free(gr); free(lp); free(acc); free(tot); free(da);
+  return PM4_OK;
+}
+
+/* sample_chain with tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC)
+ * (/root/reference/pymc4/mcmc/samplers.py:265-315). */
+int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL* theta0,
+                       const REAL* step_scale, const REAL* momenta, const REAL* uniforms, REAL* states,
+                       REAL* lp_out, REAL* log_accept, uint8_t* accepted, REAL* step_size_out, REAL* traj) {
+  const int D = ir->D, C = cfg->C, B = cfg->num_burnin, S = cfg->num_results, T = B + S;
+  const int L = cfg->num_leapfrog_steps;
+  const int pooled = cfg->adapt.mode == PM4_EPS_POOLED;
+  REAL* th = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* gr = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* lp = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  REAL* acc = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  memcpy(th, theta0, sizeof(REAL) * (size_t)C * D);
+  NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)(pooled ? 1 : C));
+  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init)(&da[c], (REAL)cfg->step_size);
+  NAME(ws_t) ws = NAME(ws_new)(D);
+  REAL* pth = (REAL*)malloc(sizeof(REAL) * (size_t)D * 3);
+  REAL *pp = pth + D, *pg = pp + D;
+  for (int c = 0; c < C; ++c) lp[c] = NAME(logp_grad1)(ir, &ws, th + (size_t)c * D, gr + (size_t)c * D);
+  for (int t = 0; t < T; ++t) {
+    for (int c = 0; c < C; ++c) {
+      REAL eps = da[pooled ? 0 : c].eps;
+      REAL *cth = th + (size_t)c * D, *cgr = gr + (size_t)c * D;
+      if (momenta) memcpy(pp, momenta + ((size_t)t * C + c) * D, sizeof(REAL) * (size_t)D);
+      else NAME(draw_momentum)(cfg->seed, (uint32_t)c, (uint32_t)t, D, pp);
+      const REAL k0 = (REAL)0.5 * NAME(dot)(pp, pp, D);
+      memcpy(pth, cth, sizeof(REAL) * (size_t)D);
+      memcpy(pg, cgr, sizeof(REAL) * (size_t)D);
+      REAL plp = lp[c];
+      NAME(leapfrog)(ir, &ws, L, eps, step_scale, pth, pp, pg, &plp);
+      const REAL k1 = (REAL)0.5 * NAME(dot)(pp, pp, D);
+      REAL lar = (plp - lp[c]) + (k0 - k1);
+      if (!isfinite(lar)) lar = -(REAL)INFINITY;
+      REAL u = uniforms ? uniforms[(size_t)t * C + c]
+                        : NAME(draw_u)(cfg->seed, (uint32_t)c, (uint32_t)t, 0, PM4_RNG_HMC);
+      const int ok = RLOG(u) < lar;
+      if (traj) memcpy(traj + ((size_t)t * C + c) * D, pth, sizeof(REAL) * (size_t)D);
+      if (ok) {
+        memcpy(cth, pth, sizeof(REAL) * (size_t)D);
+        memcpy(cgr, pg, sizeof(REAL) * (size_t)D);
+        lp[c] = plp;
+      }
+      acc[c] = REXP(lar < 0 ? lar : 0);
+      if (!pooled) NAME(da_update)(&da[c], &cfg->adapt, t, acc[c]);
+      if (t >= B) {
+        size_t k = (size_t)(t - B) * C + c;
+        if (states) memcpy(states + k * D, cth, sizeof(REAL) * (size_t)D);
+        if (lp_out) lp_out[k] = lp[c];
+        if (log_accept) log_accept[k] = lar;
+        if (accepted) accepted[k] = (uint8_t)ok;
+      }
+    }
+    if (pooled) {
+      REAL s = 0;
+      for (int c = 0; c < C; ++c) s += acc[c];
+      NAME(da_update)(&da[0], &cfg->adapt, t, s / (REAL)C);
+    }
+  }
+  for (int c = 0; c < C; ++c) if (step_size_out) step_size_out[c] = da[pooled ? 0 : c].eps;
+  NAME(ws_free)(&ws);
+  free(pth); free(th); free(gr); free(lp); free(acc); free(da);
+  return PM4_OK;
+}

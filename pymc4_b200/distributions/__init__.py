@@ -1,0 +1,8 @@
+"""Model nodes: distributions, potentials, deterministics and transforms."""
+from .continuous import *  # noqa: F401,F403
+from .discrete import *  # noqa: F401,F403
+from .distribution import Potential, Deterministic, Distribution  # noqa: F401
+from . import transforms  # noqa: F401
+from . import continuous, discrete
+
+__all__ = list(continuous.__all__) + list(discrete.__all__) + ["Potential", "Deterministic", "Distribution", "transforms"]

@@ -1,0 +1,511 @@
+"""Lowering of a coroutine model's transformed log-density to the flat model IR.
+
+What the reference does at run time -- ``logpfn`` = ``SamplingState.from_values`` ->
+``evaluate_model_transformed`` -> ``collect_log_prob`` (pymc4/mcmc/samplers.py:762-770,
+pymc4/flow/executor.py:171-187) -- is done here *once*, symbolically: the transformed
+executor runs with every free variable bound to a symbolic view, and the distributions,
+potentials and deterministics it registers are flattened into
+
+  * a table of free variables (offset, size, transform) in the reference's trace order
+    (untransformed first, then transformed; executor.py:24-35,163),
+  * a list of log-density terms, each an element-wise SSA tape over ``n`` elements,
+  * tapes for the traced outputs (deterministics and back-transformed variables;
+    samplers.py:796-809),
+  * two constant pools (reals, indices).
+
+The layout of the packed structs is include/pm4b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import struct
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import symbolic as sym
+from .coroutine_model import Model
+from .utils import NameParts
+
+ABI_VERSION = 1
+
+TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
+
+TERM_KINDS = {
+    "potential": 0,
+    "normal": 1,
+    "halfnormal": 2,
+    "halfcauchy": 3,
+    "bernoulli": 4,
+    "poisson": 5,
+}
+TERM_NPARAMS = {0: 0, 1: 2, 2: 1, 3: 1, 4: 1, 5: 1}
+
+OP = {
+    "ld_const": 0, "ld_data": 1, "ld_x": 2, "ld_z": 3,
+    "add": 10, "sub": 11, "mul": 12, "div": 13, "pow": 14,
+    "neg": 20, "exp": 21, "log": 22, "log1p": 23, "sqrt": 24, "square": 25,
+    "sigmoid": 26, "softplus": 27, "tanh": 28, "abs": 29, "recip": 30, "lgamma": 31,
+}
+OP_NAME = {v: k for k, v in OP.items()}
+MODE_SCALAR, MODE_ELEM, MODE_GATHER = 0, 1, 2
+
+
+# ---------------------------------------------------------------------------
+# Python-side IR
+# ---------------------------------------------------------------------------
+@dataclass
+class RV:
+    name: str            # sampled name, e.g. "m/__log_tau" or "m/mu"
+    shape: Tuple[int, ...]
+    offset: int
+    size: int
+    transform: int = TR_IDENTITY
+    shift: float = 0.0
+    scale: float = 1.0
+    untransformed_name: Optional[str] = None  # "m/tau" for transformed variables
+
+
+@dataclass
+class Op:
+    opcode: int
+    dst: int
+    a: int = -1
+    b: int = -1
+    mode: int = 0
+    base: int = 0
+    blob: int = 0
+    imm: float = 0.0
+    sorted_idx: bool = False   # GATHER loads: index array is non-decreasing
+    blob_len: int = 0
+    uniform: bool = False      # value does not depend on the element index
+
+
+@dataclass
+class Term:
+    kind: int
+    n: int
+    ops: List[Op]
+    value_reg: int
+    param_regs: List[int]
+    label: str = ""
+
+    @property
+    def n_regs(self) -> int:
+        return max([o.dst for o in self.ops] + [-1]) + 1
+
+
+@dataclass
+class Det:
+    name: str
+    shape: Tuple[int, ...]
+    n: int
+    ops: List[Op]
+    value_reg: int
+    out_offset: int
+
+    @property
+    def n_regs(self) -> int:
+        return max([o.dst for o in self.ops] + [-1]) + 1
+
+
+@dataclass
+class ModelIR:
+    D: int
+    rvs: List[RV]
+    terms: List[Term]
+    dets: List[Det]
+    dataf: np.ndarray
+    datai: np.ndarray
+    observed: Dict[str, np.ndarray] = field(default_factory=dict)
+
+    @property
+    def det_row(self) -> int:
+        return sum(d.n for d in self.dets)
+
+    # -- structural hash: everything the generated code depends on ---------
+    def struct_key(self) -> bytes:
+        h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<i", self.D)]
+        for rv in self.rvs:
+            h.append(struct.pack("<iiidd", rv.offset, rv.size, rv.transform, rv.shift, rv.scale))
+
+        def ops_key(ops, n):
+            for o in ops:
+                h.append(struct.pack("<iiiiii?d", o.opcode, o.dst, o.a, o.b, o.mode, o.base,
+                                     o.sorted_idx, o.imm))
+            # n matters structurally only for terms aligned with a variable (ELEM x loads)
+            if any(o.opcode in (OP["ld_x"], OP["ld_z"]) and o.mode == MODE_ELEM for o in ops):
+                h.append(struct.pack("<i", n))
+
+        for t in self.terms:
+            h.append(struct.pack("<iii", t.kind, t.value_reg, len(t.ops)))
+            h.append(struct.pack("<%di" % len(t.param_regs), *t.param_regs))
+            ops_key(t.ops, t.n)
+        for d in self.dets:
+            h.append(struct.pack("<iii", d.value_reg, len(d.ops), d.n))
+            ops_key(d.ops, d.n)
+        return b"".join(h)
+
+    @property
+    def struct_hash(self) -> int:
+        return int.from_bytes(hashlib.sha256(self.struct_key()).digest()[:8], "little")
+
+    @property
+    def struct_hash_hex(self) -> str:
+        return "%016x" % self.struct_hash
+
+    # -- helpers -----------------------------------------------------------
+    def rv_by_name(self, name: str) -> RV:
+        for rv in self.rvs:
+            if rv.name == name:
+                return rv
+        raise KeyError(name)
+
+    def split_theta(self, theta: np.ndarray) -> Dict[str, np.ndarray]:
+        """[..., D] -> {sampled name: [..., *shape]}"""
+        lead = theta.shape[:-1]
+        return {rv.name: theta[..., rv.offset: rv.offset + rv.size].reshape(lead + rv.shape)
+                for rv in self.rvs}
+
+    def join_theta(self, parts: Dict[str, Any]) -> np.ndarray:
+        out = np.zeros(self.D, dtype=np.float64)
+        for rv in self.rvs:
+            out[rv.offset: rv.offset + rv.size] = np.asarray(parts[rv.name], dtype=np.float64).reshape(-1)
+        return out
+
+    def constrain(self, theta: np.ndarray) -> np.ndarray:
+        """x = shift + scale * f(theta), NumPy (host bookkeeping / tests)."""
+        x = np.array(theta, dtype=np.float64, copy=True)
+        for rv in self.rvs:
+            sl = slice(rv.offset, rv.offset + rv.size)
+            if rv.transform == TR_EXP:
+                x[..., sl] = rv.shift + rv.scale * np.exp(theta[..., sl])
+            elif rv.transform == TR_SIGMOID:
+                x[..., sl] = rv.shift + rv.scale / (1.0 + np.exp(-theta[..., sl]))
+        return x
+
+
+# ---------------------------------------------------------------------------
+# expression -> tape lowering
+# ---------------------------------------------------------------------------
+class _Pools:
+    def __init__(self):
+        self.f: List[np.ndarray] = []
+        self.i: List[np.ndarray] = []
+        self.f_len = 0
+        self.i_len = 0
+        self._fkey: Dict[bytes, int] = {}
+        self._ikey: Dict[bytes, int] = {}
+
+    def add_f(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        key = arr.tobytes()
+        if key in self._fkey:
+            return self._fkey[key]
+        # keep every blob 4-element aligned so 128-bit loads stay legal
+        pad = (-self.f_len) % 4
+        if pad:
+            self.f.append(np.zeros(pad))
+            self.f_len += pad
+        off = self.f_len
+        self.f.append(arr)
+        self.f_len += arr.size
+        self._fkey[key] = off
+        return off
+
+    def add_i(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, dtype=np.int32).reshape(-1)
+        key = arr.tobytes()
+        if key in self._ikey:
+            return self._ikey[key]
+        pad = (-self.i_len) % 4
+        if pad:
+            self.i.append(np.zeros(pad, dtype=np.int32))
+            self.i_len += pad
+        off = self.i_len
+        self.i.append(arr)
+        self.i_len += arr.size
+        self._ikey[key] = off
+        return off
+
+
+class _TapeBuilder:
+    """Lower expressions to one SSA tape over ``n`` elements."""
+
+    def __init__(self, n: int, rvs: Dict[str, RV], pools: _Pools):
+        self.n = n
+        self.rvs = rvs
+        self.pools = pools
+        self.ops: List[Op] = []
+        self._memo: Dict[Tuple[int, bytes], int] = {}
+        self._keepalive: List[Any] = []
+
+    def _emit(self, **kw) -> int:
+        dst = len(self.ops)
+        self.ops.append(Op(dst=dst, **kw))
+        return dst
+
+    def lower(self, node: sym.Expr, emap: np.ndarray) -> int:
+        """Register holding ``node.reshape(-1)[emap[i]]`` for element i."""
+        key = (id(node), hashlib.blake2b(emap.tobytes(), digest_size=8).digest())
+        if key in self._memo:
+            return self._memo[key]
+        self._keepalive.append(node)
+        reg = self._lower(node, emap)
+        self._memo[key] = reg
+        return reg
+
+    def _lower(self, node: sym.Expr, emap: np.ndarray) -> int:
+        n = self.n
+        op = node.op
+        if op == "const":
+            vals = node.data.reshape(-1)[emap]
+            if vals.size == 0 or np.all(vals == vals[0]) or (np.all(np.isnan(vals))):
+                return self._emit(opcode=OP["ld_const"], imm=float(vals[0]) if vals.size else 0.0,
+                                  uniform=True)
+            blob = self.pools.add_f(vals)
+            return self._emit(opcode=OP["ld_data"], mode=MODE_ELEM, blob=blob, blob_len=n)
+        if op == "view":
+            rv = self.rvs[node.rv]
+            idx = node.index.reshape(-1)[emap].astype(np.int64)
+            opcode = OP["ld_x"] if node.space == "x" else OP["ld_z"]
+            if rv.transform == TR_IDENTITY:
+                opcode = OP["ld_x"]  # identical arrays; keep one spelling
+            if idx.size == 0 or np.all(idx == idx[0]):
+                return self._emit(opcode=opcode, mode=MODE_SCALAR, base=rv.offset + int(idx[0]),
+                                  uniform=True)
+            if np.array_equal(idx, idx[0] + np.arange(n)):
+                return self._emit(opcode=opcode, mode=MODE_ELEM, base=rv.offset + int(idx[0]))
+            blob = self.pools.add_i(idx)
+            return self._emit(opcode=opcode, mode=MODE_GATHER, base=rv.offset, blob=blob,
+                              blob_len=n, sorted_idx=bool(np.all(np.diff(idx) >= 0)))
+        if op in sym.UNARY_OPS:
+            a = self.lower(node.args[0], emap)
+            return self._emit(opcode=OP[op], a=a, uniform=self.ops[a].uniform)
+        if op in sym.BINARY_OPS:
+            regs = []
+            for arg in node.args:
+                regs.append(self.lower(arg, _broadcast_map(emap, node.shape, arg.shape)))
+            return self._emit(opcode=OP[op], a=regs[0], b=regs[1],
+                              uniform=self.ops[regs[0]].uniform and self.ops[regs[1]].uniform)
+        if op == "broadcast":
+            arg = node.args[0]
+            return self.lower(arg, _broadcast_map(emap, node.shape, arg.shape))
+        if op == "reshape":
+            return self.lower(node.args[0], emap)
+        if op == "take":
+            return self.lower(node.args[0], node.index.reshape(-1).astype(np.int64)[emap])
+        raise NotImplementedError(
+            "op {!r} on random variables cannot be lowered to the element-wise model IR yet "
+            "(supported: arithmetic, exp/log/sigmoid/..., static indexing, gather, broadcasting)"
+            .format(op)
+        )
+
+
+def _broadcast_map(emap: np.ndarray, out_shape: Tuple[int, ...], arg_shape: Tuple[int, ...]) -> np.ndarray:
+    """Map flat positions of a broadcast result to flat positions of one argument."""
+    if tuple(arg_shape) == tuple(out_shape):
+        return emap
+    size = int(np.prod(arg_shape, dtype=np.int64)) if arg_shape else 1
+    if size == 1:
+        return np.zeros_like(emap)
+    pos = np.arange(size, dtype=np.int64).reshape(arg_shape)
+    return np.broadcast_to(pos, out_shape).reshape(-1)[emap]
+
+
+def _identity_map(n: int) -> np.ndarray:
+    return np.arange(n, dtype=np.int64)
+
+
+def _lower_term(kind: str, value, params: List[Any], rvs, pools, label="") -> Term:
+    exprs = [sym.as_expr(value)] + [sym.as_expr(p) for p in params]
+    shape = tuple(np.broadcast_shapes(*[e.shape for e in exprs]))
+    n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+    tb = _TapeBuilder(n, rvs, pools)
+    regs = [tb.lower(e, _broadcast_map(_identity_map(n), shape, e.shape)) for e in exprs]
+    return Term(kind=TERM_KINDS[kind], n=n, ops=tb.ops, value_reg=regs[0], param_regs=regs[1:], label=label)
+
+
+def _lower_det(name: str, value, rvs, pools, out_offset: int) -> Det:
+    e = sym.as_expr(value)
+    n = e.size
+    tb = _TapeBuilder(n, rvs, pools)
+    reg = tb.lower(e, _identity_map(n))
+    return Det(name=name, shape=e.shape, n=n, ops=tb.ops, value_reg=reg, out_offset=out_offset)
+
+
+# ---------------------------------------------------------------------------
+# model -> IR
+# ---------------------------------------------------------------------------
+def _transform_record(dist) -> Tuple[int, float, float]:
+    tr = dist.transform
+    if tr is None:
+        return TR_IDENTITY, 0.0, 1.0
+    return int(tr.ir_code), float(tr.ir_shift), float(tr.ir_scale)
+
+
+def lower_model(model: Model, observed: Optional[dict] = None, state=None) -> Tuple[ModelIR, Any, List[str]]:
+    """Trace ``model`` and return (IR, initial sampling state, deterministic names).
+
+    The initial state and the deterministic-name list are exactly what the reference's
+    ``initialize_sampling_state`` returns (pymc4/mcmc/utils.py:14-36).
+    """
+    from . import flow
+    from .mcmc.utils import initialize_sampling_state
+
+    if not isinstance(model, Model):
+        raise TypeError(
+            "`sample` function only supports `pymc4.Model` objects, but you've passed `{}`".format(type(model))
+        )
+    init_state, deterministic_names = initialize_sampling_state(model, observed=observed, state=state)
+    if not init_state.all_unobserved_values:
+        raise ValueError(
+            "Can not calculate a log probability: the model {} has no unobserved values.".format(model.name or "")
+        )
+
+    # pass 1 (meta, concrete) gave names + shapes; build symbolic stand-ins
+    rvs: Dict[str, RV] = {}
+    sym_values: Dict[str, sym.Expr] = {}
+    offset = 0
+    for name, value in init_state.all_unobserved_values.items():
+        shape = tuple(np.shape(sym.as_numpy(value)))
+        size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        parts = NameParts.from_name(name)
+        rvs[name] = RV(name=name, shape=shape, offset=offset, size=size,
+                       untransformed_name=parts.full_untransformed_name if parts.is_transformed else None)
+        sym_values[name] = sym.free_rv(name, shape, space="z" if parts.is_transformed else "x")
+        offset += size
+    D = offset
+
+    # pass 2 (transformed executor, symbolic)
+    st = flow.SamplingState.from_values(sym_values, observed_values=init_state.observed_values)
+    _, st = flow.evaluate_model_transformed(model, state=st)
+
+    # fill in transform records now that the distributions are known
+    all_dists = dict(st.discrete_distributions)
+    all_dists.update(st.continuous_distributions)
+    for name, dist in all_dists.items():
+        if name in st.observed_values:
+            continue
+        if dist.transform is not None:
+            tname = NameParts.from_name(name).replace_transform(dist.transform.name).full_original_name
+            if tname in rvs:
+                rvs[tname].transform, rvs[tname].shift, rvs[tname].scale = _transform_record(dist)
+                continue
+        if name in rvs and not dist._grad_support:
+            raise ValueError("Discrete distributions can't be used with gradient-based sampler")
+        if name in rvs and dist._kind in ("bernoulli", "poisson"):
+            raise ValueError("Discrete distributions can't be used with gradient-based sampler")
+
+    pools = _Pools()
+    terms: List[Term] = []
+    for name, dist in all_dists.items():
+        if dist._kind is None:
+            raise NotImplementedError(
+                "{} has no device log-density (supported kinds: {})".format(type(dist).__name__, sorted(TERM_KINDS))
+            )
+        value = st.all_values[name]
+        params = [dist.params[p] for p in dist._param_names]
+        terms.append(_lower_term(dist._kind, value, params, rvs, pools, label=name))
+    for k, pot in enumerate(st.potentials):
+        terms.append(_lower_term("potential", pot.value, [], rvs, pools, label="potential_%d" % k))
+
+    # traced outputs, in the order the reference's deterministics_callback returns them
+    dets: List[Det] = []
+    out_off = 0
+    det_values = dict(st.deterministics_values)
+    for tname in st.transformed_values:
+        uname = NameParts.from_name(tname).full_untransformed_name
+        if uname in st.untransformed_values:
+            det_values[uname] = st.untransformed_values[uname]
+    for name in deterministic_names:
+        if name not in det_values:
+            continue
+        d = _lower_det(name, det_values[name], rvs, pools, out_off)
+        dets.append(d)
+        out_off += d.n
+
+    dataf = np.concatenate(pools.f) if pools.f else np.zeros(0)
+    datai = np.concatenate(pools.i).astype(np.int32) if pools.i else np.zeros(0, dtype=np.int32)
+    observed_np = {k: sym.as_numpy(v) for k, v in st.observed_values.items()}
+    ir = ModelIR(D=D, rvs=list(rvs.values()), terms=terms, dets=dets, dataf=dataf, datai=datai,
+                 observed=observed_np)
+    return ir, init_state, deterministic_names
+
+
+# ---------------------------------------------------------------------------
+# ctypes packing (layout: include/pm4b200.h)
+# ---------------------------------------------------------------------------
+class CRV(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_int32), ("size", ctypes.c_int32), ("transform", ctypes.c_int32),
+                ("_pad", ctypes.c_int32), ("shift", ctypes.c_double), ("scale", ctypes.c_double)]
+
+
+class CTerm(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("n", ctypes.c_int32), ("op_begin", ctypes.c_int32),
+                ("op_end", ctypes.c_int32), ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32),
+                ("param_reg", ctypes.c_int32 * 3), ("flags", ctypes.c_int32)]
+
+
+class COp(ctypes.Structure):
+    _fields_ = [("opcode", ctypes.c_int32), ("dst", ctypes.c_int32), ("a", ctypes.c_int32),
+                ("b", ctypes.c_int32), ("mode", ctypes.c_int32), ("base", ctypes.c_int32),
+                ("blob", ctypes.c_int64), ("imm", ctypes.c_double)]
+
+
+class CDet(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("op_begin", ctypes.c_int32), ("op_end", ctypes.c_int32),
+                ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32), ("out_offset", ctypes.c_int32)]
+
+
+class CIR(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("D", ctypes.c_int32), ("n_rv", ctypes.c_int32),
+                ("n_terms", ctypes.c_int32), ("n_ops", ctypes.c_int32), ("n_dets", ctypes.c_int32),
+                ("det_row", ctypes.c_int32), ("_pad", ctypes.c_int32),
+                ("rvs", ctypes.POINTER(CRV)), ("terms", ctypes.POINTER(CTerm)),
+                ("ops", ctypes.POINTER(COp)), ("dets", ctypes.POINTER(CDet)),
+                ("n_dataf", ctypes.c_int64), ("dataf", ctypes.POINTER(ctypes.c_double)),
+                ("n_datai", ctypes.c_int64), ("datai", ctypes.POINTER(ctypes.c_int32)),
+                ("struct_hash", ctypes.c_uint64)]
+
+
+class PackedIR:
+    """Owns the ctypes arrays a ``pm4_ir_t`` points into."""
+
+    def __init__(self, ir: ModelIR):
+        self.ir = ir
+        all_ops: List[Op] = []
+        cterms = (CTerm * max(len(ir.terms), 1))()
+        for k, t in enumerate(ir.terms):
+            begin = len(all_ops)
+            all_ops.extend(t.ops)
+            pr = list(t.param_regs) + [-1] * (3 - len(t.param_regs))
+            cterms[k] = CTerm(t.kind, t.n, begin, len(all_ops), t.n_regs, t.value_reg,
+                              (ctypes.c_int32 * 3)(*pr), 0)
+        cdets = (CDet * max(len(ir.dets), 1))()
+        for k, d in enumerate(ir.dets):
+            begin = len(all_ops)
+            all_ops.extend(d.ops)
+            cdets[k] = CDet(d.n, begin, len(all_ops), d.n_regs, d.value_reg, d.out_offset)
+        cops = (COp * max(len(all_ops), 1))()
+        for k, o in enumerate(all_ops):
+            cops[k] = COp(o.opcode, o.dst, o.a, o.b, o.mode, o.base, o.blob, o.imm)
+        crvs = (CRV * max(len(ir.rvs), 1))()
+        for k, rv in enumerate(ir.rvs):
+            crvs[k] = CRV(rv.offset, rv.size, rv.transform, 0, rv.shift, rv.scale)
+        self._dataf = np.ascontiguousarray(ir.dataf, dtype=np.float64)
+        self._datai = np.ascontiguousarray(ir.datai, dtype=np.int32)
+        self._keep = (cterms, cdets, cops, crvs)
+        self.c = CIR(
+            ABI_VERSION, ir.D, len(ir.rvs), len(ir.terms), len(all_ops), len(ir.dets), ir.det_row, 0,
+            ctypes.cast(crvs, ctypes.POINTER(CRV)), ctypes.cast(cterms, ctypes.POINTER(CTerm)),
+            ctypes.cast(cops, ctypes.POINTER(COp)), ctypes.cast(cdets, ctypes.POINTER(CDet)),
+            self._dataf.size, self._dataf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            self._datai.size, self._datai.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            ir.struct_hash,
+        )
+
+    def byref(self):
+        return ctypes.byref(self.c)
