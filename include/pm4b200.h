@@ -199,7 +199,7 @@ typedef struct pm4_hmc_cfg {
   uint64_t seed;
   pm4_adapt_cfg_t adapt;
   int32_t warps_per_block;    /* 0 = library default                                       */
-  int32_t _pad;
+  int32_t chain_offset;       /* global index of chain 0 (RNG stream id) when chains are sharded */
 } pm4_hmc_cfg_t;
 
 /* Fixed-L HMC (tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC); App. A.4).
@@ -225,7 +225,7 @@ typedef struct pm4_nuts_cfg {
   uint64_t seed;
   pm4_adapt_cfg_t adapt;
   int32_t warps_per_block; /* 0 = library default */
-  int32_t _pad;
+  int32_t chain_offset;    /* global index of chain 0 (RNG stream id) when chains are sharded */
 } pm4_nuts_cfg_t;
 
 /* NUTS (tfp NoUTurnSampler: iterative tree doubling, generalised U-turn with checkpoints,

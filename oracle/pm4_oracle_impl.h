@@ -313,16 +313,23 @@ static void NAME(draw_momentum)(uint64_t seed, uint32_t chain, uint32_t t, int D
   }
 }
 
-static inline REAL NAME(draw_u)(uint64_t seed, uint32_t chain, uint32_t t, uint32_t slot, uint32_t purpose) {
+/* a uniform in [0,1): words (2*pair, 2*pair+1) of the Philox block at `slot` */
+static inline REAL NAME(draw_u)(uint64_t seed, uint32_t chain, uint32_t t, uint32_t slot, uint32_t purpose, int pair) {
   uint32_t ctr[4] = {chain, t, slot, purpose}, out[4];
   pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), out);
-  return NAME(u01)(out);
+  return NAME(u01)(out + 2 * pair);
 }
 
-static inline int NAME(draw_bit)(uint64_t seed, uint32_t chain, uint32_t t, uint32_t slot, uint32_t purpose) {
-  uint32_t ctr[4] = {chain, t, slot, purpose}, out[4];
+/* the uniform of leaf i of the subtree at `depth`: two leaves share one Philox block */
+static inline REAL NAME(draw_leaf_u)(uint64_t seed, uint32_t chain, uint32_t t, int depth, int i) {
+  return NAME(draw_u)(seed, chain, t, ((uint32_t)depth << 20) | ((uint32_t)i >> 1), PM4_RNG_LEAF, i & 1);
+}
+
+/* direction bits of all doublings of one transition come from one Philox word */
+static inline int NAME(draw_direction)(uint64_t seed, uint32_t chain, uint32_t t, int depth) {
+  uint32_t ctr[4] = {chain, t, 0u, PM4_RNG_DIRECTION}, out[4];
   pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), out);
-  return (int)(out[0] & 1u);
+  return (int)((out[0] >> depth) & 1u);
 }
 
 /* ----------------------------------------------------------------------------------------
@@ -435,7 +442,7 @@ static void NAME(nuts_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, NAME(nuts_
   int nleap = 0, cont = 1, not_div = 1, depth = 0;
 
   while (depth < cfg->max_tree_depth && cont) {
-    const int dir = NAME(draw_bit)(cfg->seed, chain, t, (uint32_t)depth, PM4_RNG_DIRECTION);
+    const int dir = NAME(draw_direction)(cfg->seed, chain, t, depth);
     if (dir != cur_is_right) { /* extend the other end: swap roles */
       REAL* s;
       s = b->cur_th; b->cur_th = b->oth_th; b->oth_th = s;
@@ -481,7 +488,7 @@ static void NAME(nuts_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, NAME(nuts_
       const int not_divergent = (-dH < (REAL)cfg->max_energy_diff);
       const REAL w_new = NAME(logaddexp)(w_sub, dH);
       const REAL thresh = dH - w_new;
-      const REAL u = RLOG1P(-NAME(draw_u)(cfg->seed, chain, t, ((uint32_t)depth << 20) | (uint32_t)i, PM4_RNG_LEAF));
+      const REAL u = RLOG1P(-NAME(draw_leaf_u)(cfg->seed, chain, t, depth, i));
       if (u <= thresh) {
         memcpy(b->sub_th, b->cur_th, nb); memcpy(b->sub_g, b->cur_g, nb);
         sub_lp = cur_lp; sub_energy = energy;
@@ -498,7 +505,7 @@ static void NAME(nuts_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, NAME(nuts_
     nleap += sub_leaps;
     const REAL tree_w = cont_sub ? w_sub : NEG_INF;
     const REAL thresh = tree_w - w;
-    const REAL um = RLOG1P(-NAME(draw_u)(cfg->seed, chain, t, (uint32_t)depth, PM4_RNG_MERGE));
+    const REAL um = RLOG1P(-NAME(draw_u)(cfg->seed, chain, t, (uint32_t)depth, PM4_RNG_MERGE, 0));
     if ((um <= thresh) && cont_sub) {
       memcpy(b->cand_th, b->sub_th, nb); memcpy(b->cand_g, b->sub_g, nb);
       cand_lp = sub_lp; cand_energy = sub_energy;
@@ -566,7 +573,7 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
 #pragma omp for schedule(dynamic, 1)
         for (int c = 0; c < C; ++c) {
           NAME(nuts_out_t) o;
-          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)c, (uint32_t)t, da[0].eps, step_scale,
+          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[0].eps, step_scale,
                                 momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
                                 gr + (size_t)c * D, &lp[c], &o);
           acc[c] = REXP(o.log_accept);
@@ -595,7 +602,7 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
       for (int c = 0; c < C; ++c) {
         for (int t = 0; t < T; ++t) {
           NAME(nuts_out_t) o;
-          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)c, (uint32_t)t, da[c].eps, step_scale,
+          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[c].eps, step_scale,
                                 momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
                                 gr + (size_t)c * D, &lp[c], &o);
           NAME(da_update)(&da[c], &cfg->adapt, t, REXP(o.log_accept));
@@ -649,7 +656,7 @@ int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL*
       REAL eps = da[pooled ? 0 : c].eps;
       REAL *cth = th + (size_t)c * D, *cgr = gr + (size_t)c * D;
       if (momenta) memcpy(pp, momenta + ((size_t)t * C + c) * D, sizeof(REAL) * (size_t)D);
-      else NAME(draw_momentum)(cfg->seed, (uint32_t)c, (uint32_t)t, D, pp);
+      else NAME(draw_momentum)(cfg->seed, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, D, pp);
       const REAL k0 = (REAL)0.5 * NAME(dot)(pp, pp, D);
       memcpy(pth, cth, sizeof(REAL) * (size_t)D);
       memcpy(pg, cgr, sizeof(REAL) * (size_t)D);
@@ -659,7 +666,7 @@ int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL*
       REAL lar = (plp - lp[c]) + (k0 - k1);
       if (!isfinite(lar)) lar = -(REAL)INFINITY;
       REAL u = uniforms ? uniforms[(size_t)t * C + c]
-                        : NAME(draw_u)(cfg->seed, (uint32_t)c, (uint32_t)t, 0, PM4_RNG_HMC);
+                        : NAME(draw_u)(cfg->seed, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, 0, PM4_RNG_HMC, 0);
       const int ok = RLOG(u) < lar;
       if (traj) memcpy(traj + ((size_t)t * C + c) * D, pth, sizeof(REAL) * (size_t)D);
       if (ok) {

@@ -9,6 +9,9 @@ from . import flow
 from .flow import evaluate_model_transformed, evaluate_model, evaluate_meta_model
 from .distributions import *  # noqa: F401,F403
 from . import mcmc
+from . import inference
 from .mcmc.utils import initialize_sampling_state, trace_to_arviz
+from .mcmc.samplers import *  # noqa: F401,F403
+from .inference.sampling import sample
 
 __version__ = "0.1.0"

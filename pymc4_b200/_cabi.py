@@ -1,0 +1,253 @@
+"""ctypes binding of libpm4b200.so (include/pm4b200.h) + torch hand-off of device buffers.
+
+There is no CPU fallback: importing this module is cheap, but any compute call raises
+``BackendUnavailable`` when the CUDA library cannot be built/loaded or no CUDA device is visible.
+PyTorch is used only to allocate device memory, to pass ``data_ptr()`` / the current stream, and
+to copy results to the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import codegen
+from ._cstructs import HMCCfg, NUTSCfg, PM4_F32, PM4_F64
+from .ir import CIR, ModelIR, PackedIR
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpm4b200.so")
+_CORE_SRC = os.path.join(_HERE, "csrc", "pm4_core.cu")
+_HEADER = os.path.join(_HERE, "..", "include", "pm4b200.h")
+_lock = threading.Lock()
+_lib = None
+
+EXPORTS = [
+    "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_logp_grad",
+    "pm4_deterministics", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
+    "pm4_last_error", "pm4_abi_version",
+]
+
+
+class BackendUnavailable(RuntimeError):
+    """The CUDA backend cannot run here (no device, or the library failed to build/load)."""
+
+
+def build_core(force: bool = False) -> str:
+    """Compile libpm4b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    deps = [_CORE_SRC, _HEADER, os.path.join(_HERE, "csrc", "pm4_module.h")]
+    with _lock:
+        fresh = os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps)
+        if fresh and not force:
+            return LIB_PATH
+        cmd = [codegen.find_nvcc()] + codegen.NVCC_FLAGS + ["-shared", "-o", LIB_PATH + ".tmp", _CORE_SRC, "-ldl"]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            raise BackendUnavailable("nvcc failed building libpm4b200.so:\n" + proc.stdout[-4000:])
+        os.replace(LIB_PATH + ".tmp", LIB_PATH)
+        return LIB_PATH
+
+
+def load_library():
+    """dlopen the C-ABI library (building it first if the source is newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        path = build_core()
+    except RuntimeError as e:
+        if not os.path.exists(LIB_PATH):
+            raise BackendUnavailable(str(e)) from e
+        path = LIB_PATH
+    L = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    L.pm4_model_create.argtypes = [ctypes.POINTER(CIR), ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+    L.pm4_model_destroy.argtypes = [vp]
+    L.pm4_model_dim.argtypes = [vp]
+    L.pm4_model_set_data.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i64, ctypes.POINTER(ctypes.c_int32), i64]
+    L.pm4_logp_grad.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.pm4_deterministics.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
+    L.pm4_nuts_run.argtypes = [vp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
+    L.pm4_scratch_bytes.argtypes = [vp, i32, i32, i32]
+    L.pm4_scratch_bytes.restype = i64
+    L.pm4_launch_count.argtypes = [i32]
+    L.pm4_launch_count.restype = i64
+    L.pm4_last_error.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise BackendUnavailable(
+            "pymc4_b200 needs a CUDA device: there is no CPU fallback for the sampler hot path"
+        )
+    return torch
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load_library().pm4_launch_count(1 if reset else 0))
+
+
+def _tdtype(torch, dtype):
+    return torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+
+
+def _code(dtype) -> int:
+    return PM4_F64 if np.dtype(dtype) == np.float64 else PM4_F32
+
+
+class DeviceModel:
+    """A lowered model resident on one GPU (wraps ``pm4_model_t``)."""
+
+    def __init__(self, ir: ModelIR, device: int = 0, f64: bool = False, module_path: Optional[str] = None):
+        self.ir = ir
+        self.torch = _torch()
+        self.lib = load_library()
+        self.device = int(device)
+        self.packed = PackedIR(ir)
+        self.module_path = module_path or codegen.build_module(ir, has_f64=f64)
+        self.handle = ctypes.c_void_p()
+        rc = self.lib.pm4_model_create(self.packed.byref(), self.module_path.encode(), self.device,
+                                       ctypes.byref(self.handle))
+        self._check(rc)
+
+    # -- plumbing --------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError("libpm4b200: %s (code %d)" % (self.lib.pm4_last_error().decode(), rc))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.pm4_model_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self):
+        return self.torch.device("cuda", self.device)
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self._dev()).cuda_stream)
+
+    def to_device(self, arr, dtype):
+        """Host array (or tensor) -> contiguous device tensor of the compute dtype."""
+        torch = self.torch
+        if arr is None:
+            return None
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self._dev(), dtype=_tdtype(torch, dtype)).contiguous()
+        host = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+        return host.to(self._dev(), non_blocking=False)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self._dev())
+
+    # -- API ---------------------------------------------------------------------
+    def set_data(self, ir: ModelIR):
+        """New constant pools for the same structure (new observed values)."""
+        if ir.struct_hash != self.ir.struct_hash:
+            raise ValueError("set_data needs an IR with the same structure")
+        self.packed = PackedIR(ir)
+        self.ir = ir
+        c = self.packed.c
+        self._check(self.lib.pm4_model_set_data(self.handle, c.dataf, c.n_dataf, c.datai, c.n_datai))
+
+    def logp_grad(self, theta, dtype=np.float32, want_grad: bool = True):
+        """theta [C, D] (host or device) -> (lp [C], grad [C, D]) device tensors."""
+        torch = self.torch
+        th = self.to_device(theta, dtype)
+        if th.dim() == 1:
+            th = th[None]
+        C, D = th.shape
+        if D != self.ir.D:
+            raise ValueError("theta has %d columns, the model has D=%d" % (D, self.ir.D))
+        td = _tdtype(torch, dtype)
+        lp = self.empty((C,), td)
+        grad = self.empty((C, D), td) if want_grad else None
+        with torch.cuda.device(self._dev()):
+            self._check(self.lib.pm4_logp_grad(self.handle, _code(dtype), C, self._p(th), self._p(lp),
+                                               self._p(grad), self._stream()))
+        return lp, grad
+
+    def deterministics(self, theta, dtype=np.float32):
+        """theta [..., D] device/host -> [..., det_row] device tensor."""
+        torch = self.torch
+        th = self.to_device(theta, dtype)
+        lead = tuple(th.shape[:-1])
+        flat = th.reshape(-1, self.ir.D)
+        out = self.empty((flat.shape[0], self.ir.det_row), _tdtype(torch, dtype))
+        with torch.cuda.device(self._dev()):
+            self._check(self.lib.pm4_deterministics(self.handle, _code(dtype), flat.shape[0], self._p(flat),
+                                                    self._p(out), self._stream()))
+        return out.reshape(lead + (self.ir.det_row,))
+
+    def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None,
+             want_states: bool = True) -> Dict[str, "object"]:
+        """Run NUTS; every result is a device tensor in the reference layout [S, C, ...]."""
+        torch = self.torch
+        td = _tdtype(torch, dtype)
+        C, S, D = cfg.C, cfg.num_results, self.ir.D
+        th0 = self.to_device(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D))
+                             if not isinstance(theta0, torch.Tensor) else theta0, dtype)
+        sc = self.to_device(step_scale, dtype)
+        mom = self.to_device(momenta, dtype)
+        out = dict(
+            states=self.empty((S, C, D), td) if want_states else None,
+            lp=self.empty((S, C), td),
+            leapfrogs=self.empty((S, C), torch.int32),
+            diverging=self.empty((S, C), torch.uint8),
+            energy=self.empty((S, C), td),
+            log_accept=self.empty((S, C), td),
+            depth=self.empty((S, C), torch.int32),
+            step_size=self.empty((C,), td),
+            total_leapfrogs=self.empty((C,), torch.int64),
+        )
+        with torch.cuda.device(self._dev()):
+            rc = self.lib.pm4_nuts_run(
+                self.handle, _code(dtype), ctypes.byref(cfg), self._p(th0), self._p(sc), self._p(mom),
+                self._p(out["states"]), self._p(out["lp"]), self._p(out["leapfrogs"]), self._p(out["diverging"]),
+                self._p(out["energy"]), self._p(out["log_accept"]), self._p(out["depth"]),
+                self._p(out["step_size"]), self._p(out["total_leapfrogs"]), self._stream())
+        self._check(rc)
+        out["_keepalive"] = (th0, sc, mom)
+        return out
+
+    def hmc(self, cfg: HMCCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, uniforms=None,
+            want_traj: bool = False) -> Dict[str, "object"]:
+        torch = self.torch
+        td = _tdtype(torch, dtype)
+        C, S, D, T = cfg.C, cfg.num_results, self.ir.D, cfg.num_results + cfg.num_burnin
+        th0 = self.to_device(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D))
+                             if not isinstance(theta0, torch.Tensor) else theta0, dtype)
+        sc = self.to_device(step_scale, dtype)
+        mom = self.to_device(momenta, dtype)
+        uni = self.to_device(uniforms, dtype)
+        out = dict(
+            states=self.empty((S, C, D), td), lp=self.empty((S, C), td), log_accept=self.empty((S, C), td),
+            accepted=self.empty((S, C), torch.uint8), step_size=self.empty((C,), td),
+            traj=self.empty((T, C, D), td) if want_traj else None,
+        )
+        with torch.cuda.device(self._dev()):
+            rc = self.lib.pm4_hmc_run(
+                self.handle, _code(dtype), ctypes.byref(cfg), self._p(th0), self._p(sc), self._p(mom), self._p(uni),
+                self._p(out["states"]), self._p(out["lp"]), self._p(out["log_accept"]), self._p(out["accepted"]),
+                self._p(out["step_size"]), self._p(out["traj"]), self._stream())
+        self._check(rc)
+        out["_keepalive"] = (th0, sc, mom, uni)
+        return out

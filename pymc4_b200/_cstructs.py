@@ -28,7 +28,7 @@ class HMCCfg(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("adapt", AdaptCfg),
         ("warps_per_block", ctypes.c_int32),
-        ("_pad", ctypes.c_int32),
+        ("chain_offset", ctypes.c_int32),
     ]
 
 
@@ -43,7 +43,7 @@ class NUTSCfg(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("adapt", AdaptCfg),
         ("warps_per_block", ctypes.c_int32),
-        ("_pad", ctypes.c_int32),
+        ("chain_offset", ctypes.c_int32),
     ]
 
 
@@ -56,15 +56,16 @@ def make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=0, target_accept_prob=0
 
 
 def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_depth=10,
-                  max_energy_diff=1000.0, adapt=None, warps_per_block=0) -> NUTSCfg:
+                  max_energy_diff=1000.0, adapt=None, warps_per_block=0, chain_offset=0) -> NUTSCfg:
     adapt = adapt if adapt is not None else make_adapt(num_adaptation_steps=num_burnin)
     return NUTSCfg(int(C), int(num_results), int(num_burnin), int(max_tree_depth),
                    float(max_energy_diff), float(step_size), int(seed) & (2**64 - 1), adapt,
-                   int(warps_per_block), 0)
+                   int(warps_per_block), int(chain_offset))
 
 
 def make_hmc_cfg(C, num_results, num_burnin, step_size=0.1, num_leapfrog_steps=3, seed=0,
-                 adapt=None, warps_per_block=0) -> HMCCfg:
+                 adapt=None, warps_per_block=0, chain_offset=0) -> HMCCfg:
     adapt = adapt if adapt is not None else make_adapt(num_adaptation_steps=num_burnin)
     return HMCCfg(int(C), int(num_results), int(num_burnin), int(num_leapfrog_steps),
-                  float(step_size), int(seed) & (2**64 - 1), adapt, int(warps_per_block), 0)
+                  float(step_size), int(seed) & (2**64 - 1), adapt, int(warps_per_block),
+                  int(chain_offset))

@@ -1,0 +1,372 @@
+// pm4_core.cu -- libpm4b200.so: the C ABI of include/pm4b200.h.
+//
+// Owns model handles (device copies of the constant pools + the dlopen'ed specialised kernel
+// module) and drives the sampler launches: bootstrap, per-transition lock-step launches while a
+// pooled step size is adapting (tfp DualAveragingStepSizeAdaptation with a scalar step size
+// couples all chains every burn-in transition), one persistent launch otherwise.
+// Replaces the hand-off _BaseSampler._run_chains -> tfp.mcmc.sample_chain
+// (/root/reference/pymc4/mcmc/samplers.py:172-189).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pm4b200.h"
+#include "pm4_module.h"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail(PM4_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define MOD(expr, what)                                                                                \
+  do {                                                                                                 \
+    int rc_ = (expr);                                                                                  \
+    ++g_launches;                                                                                      \
+    if (rc_ == -38) return fail(PM4_ENOSYS, "%s: dtype not compiled into this module", what);          \
+    if (rc_ != 0) return fail(PM4_ECUDA, "%s: launch failed: %s", what, cudaGetErrorString((cudaError_t)rc_)); \
+  } while (0)
+
+typedef int (*pm4m_export_eps_fn)(int dtype, const pm4_mod_run_t*, void* out, void* stream);
+
+}  // namespace
+
+struct pm4_model {
+  int device = 0;
+  int D = 0, n_terms = 0, n_ops = 0, n_dets = 0, det_row = 0;
+  int64_t n_dataf = 0, n_datai = 0;
+  std::vector<double> dataf;
+  void* module = nullptr;
+  pm4_mod_info_t info{};
+  pm4m_logp_grad_fn f_logp = nullptr;
+  pm4m_dets_fn f_dets = nullptr;
+  pm4m_init_fn f_init = nullptr;
+  pm4m_run_fn f_nuts = nullptr, f_hmc = nullptr;
+  pm4m_da_pooled_fn f_da = nullptr;
+  pm4m_export_eps_fn f_eps = nullptr;
+  float* d_f32 = nullptr;
+  double* d_f64 = nullptr;
+  int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
+
+  pm4_mod_args_t args(int dtype) const {
+    pm4_mod_args_t a;
+    a.dataf = dtype == PM4_F64 ? (const void*)d_f64 : (const void*)d_f32;
+    a.datai = d_datai;
+    a.term_n = d_term_n;
+    a.op_blob = d_op_blob;
+    return a;
+  }
+};
+
+static int upload_pools(pm4_model* m, const double* dataf, int64_t nf, const int32_t* datai, int64_t ni) {
+  m->dataf.assign(dataf, dataf + nf);
+  std::vector<float> f32((size_t)nf);
+  for (int64_t k = 0; k < nf; ++k) f32[(size_t)k] = (float)dataf[k];
+  if (nf) {
+    CU(cudaMemcpy(m->d_f32, f32.data(), sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_f64, dataf, sizeof(double) * (size_t)nf, cudaMemcpyHostToDevice));
+  }
+  if (ni) CU(cudaMemcpy(m->d_datai, datai, sizeof(int32_t) * (size_t)ni, cudaMemcpyHostToDevice));
+  return PM4_OK;
+}
+
+extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int device, pm4_model_t** out) {
+  if (!ir || !module_path || !out) return fail(PM4_EINVAL, "pm4_model_create: null argument");
+  if (ir->abi_version != PM4_ABI_VERSION) return fail(PM4_EINVAL, "IR ABI version %d != %d", ir->abi_version, PM4_ABI_VERSION);
+  if (ir->D <= 0 || ir->n_terms <= 0) return fail(PM4_EINVAL, "IR has no free variables or no terms");
+  for (int t = 0; t < ir->n_terms; ++t) {
+    const pm4_term_t& tm = ir->terms[t];
+    if (tm.op_begin < 0 || tm.op_end > ir->n_ops || tm.op_begin > tm.op_end || tm.n < 0)
+      return fail(PM4_EINVAL, "term %d has a malformed tape range", t);
+  }
+  for (int k = 0; k < ir->n_ops; ++k) {
+    const pm4_op_t& o = ir->ops[k];
+    const bool is_ld = o.opcode == PM4_OP_LD_X || o.opcode == PM4_OP_LD_Z;
+    if (is_ld && (o.base < 0 || o.base >= ir->D)) return fail(PM4_EINVAL, "op %d reads outside theta", k);
+    if (o.opcode == PM4_OP_LD_DATA && (o.blob < 0 || o.blob >= ir->n_dataf)) return fail(PM4_EINVAL, "op %d reads outside the real pool", k);
+    if (is_ld && o.mode == PM4_MODE_GATHER && (o.blob < 0 || o.blob >= ir->n_datai)) return fail(PM4_EINVAL, "op %d reads outside the index pool", k);
+  }
+  pm4_model* m = new pm4_model();
+  m->device = device;
+  m->D = ir->D; m->n_terms = ir->n_terms; m->n_ops = ir->n_ops; m->n_dets = ir->n_dets; m->det_row = ir->det_row;
+  m->n_dataf = ir->n_dataf; m->n_datai = ir->n_datai;
+
+  m->module = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+  if (!m->module) {
+    int rc = fail(PM4_ENOMOD, "cannot load kernel module %s: %s", module_path, dlerror());
+    delete m;
+    return rc;
+  }
+  pm4m_info_fn f_info = (pm4m_info_fn)dlsym(m->module, "pm4m_info");
+  m->f_logp = (pm4m_logp_grad_fn)dlsym(m->module, "pm4m_logp_grad");
+  m->f_dets = (pm4m_dets_fn)dlsym(m->module, "pm4m_dets");
+  m->f_init = (pm4m_init_fn)dlsym(m->module, "pm4m_init");
+  m->f_nuts = (pm4m_run_fn)dlsym(m->module, "pm4m_nuts");
+  m->f_hmc = (pm4m_run_fn)dlsym(m->module, "pm4m_hmc");
+  m->f_da = (pm4m_da_pooled_fn)dlsym(m->module, "pm4m_da_pooled");
+  m->f_eps = (pm4m_export_eps_fn)dlsym(m->module, "pm4m_export_eps");
+  if (!f_info || !m->f_logp || !m->f_dets || !m->f_init || !m->f_nuts || !m->f_hmc || !m->f_da || !m->f_eps) {
+    int rc = fail(PM4_ENOMOD, "kernel module %s lacks a required entry point", module_path);
+    pm4_model_destroy(m);
+    return rc;
+  }
+  f_info(&m->info);
+  if (m->info.abi != PM4_MODULE_ABI || m->info.struct_hash != ir->struct_hash || m->info.D != ir->D ||
+      m->info.n_terms != ir->n_terms || m->info.n_ops != ir->n_ops || m->info.det_row != ir->det_row) {
+    int rc = fail(PM4_ENOMOD, "kernel module %s was built for another model structure (hash %016llx, IR %016llx)",
+                  module_path, (unsigned long long)m->info.struct_hash, (unsigned long long)ir->struct_hash);
+    pm4_model_destroy(m);
+    return rc;
+  }
+
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    int rc = fail(PM4_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    pm4_model_destroy(m);
+    return rc;
+  }
+  std::vector<int32_t> term_n((size_t)(ir->n_terms + ir->n_dets) + 1), op_blob((size_t)ir->n_ops + 1);
+  for (int t = 0; t < ir->n_terms; ++t) term_n[(size_t)t] = ir->terms[t].n;
+  for (int d = 0; d < ir->n_dets; ++d) term_n[(size_t)(ir->n_terms + d)] = ir->dets[d].n;
+  for (int k = 0; k < ir->n_ops; ++k) op_blob[(size_t)k] = (int32_t)ir->ops[k].blob;
+  auto alloc = [&]() -> int {
+    CU(cudaMalloc(&m->d_f32, sizeof(float) * (size_t)(ir->n_dataf + 4)));
+    CU(cudaMalloc(&m->d_f64, sizeof(double) * (size_t)(ir->n_dataf + 4)));
+    CU(cudaMalloc(&m->d_datai, sizeof(int32_t) * (size_t)(ir->n_datai + 4)));
+    CU(cudaMalloc(&m->d_term_n, sizeof(int32_t) * term_n.size()));
+    CU(cudaMalloc(&m->d_op_blob, sizeof(int32_t) * op_blob.size()));
+    CU(cudaMemcpy(m->d_term_n, term_n.data(), sizeof(int32_t) * term_n.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_op_blob, op_blob.data(), sizeof(int32_t) * op_blob.size(), cudaMemcpyHostToDevice));
+    return upload_pools(m, ir->dataf, ir->n_dataf, ir->datai, ir->n_datai);
+  };
+  int rc = alloc();
+  if (rc != PM4_OK) {
+    std::string keep = g_err;
+    pm4_model_destroy(m);
+    g_err = keep;
+    return rc;
+  }
+  *out = m;
+  return PM4_OK;
+}
+
+extern "C" int pm4_model_destroy(pm4_model_t* m) {
+  if (!m) return PM4_OK;
+  cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_datai); cudaFree(m->d_term_n); cudaFree(m->d_op_blob);
+  if (m->module) dlclose(m->module);
+  delete m;
+  return PM4_OK;
+}
+
+extern "C" int pm4_model_dim(const pm4_model_t* m) { return m ? m->D : PM4_EINVAL; }
+
+extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n_dataf, const int32_t* datai, int64_t n_datai) {
+  if (!m) return fail(PM4_EINVAL, "null model");
+  if (n_dataf != m->n_dataf || n_datai != m->n_datai)
+    return fail(PM4_EINVAL, "pool sizes differ from the model's (%lld/%lld vs %lld/%lld)", (long long)n_dataf,
+                (long long)n_datai, (long long)m->n_dataf, (long long)m->n_datai);
+  CU(cudaSetDevice(m->device));
+  CU(cudaDeviceSynchronize());
+  return upload_pools(m, dataf, n_dataf, datai, n_datai);
+}
+
+static int check_dtype(const pm4_model* m, int dtype) {
+  if (dtype != PM4_F32 && dtype != PM4_F64) return fail(PM4_EINVAL, "dtype must be PM4_F32 or PM4_F64");
+  if (dtype == PM4_F64 && !m->info.has_f64) return fail(PM4_ENOSYS, "this kernel module was built without double precision");
+  return PM4_OK;
+}
+
+extern "C" int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta_dev, void* lp_dev, void* grad_dev, void* stream) {
+  if (!m || !theta_dev || !lp_dev || C < 0) return fail(PM4_EINVAL, "pm4_logp_grad: bad argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (C == 0) return PM4_OK;
+  CU(cudaSetDevice(m->device));
+  pm4_mod_args_t a = m->args(dtype);
+  MOD(m->f_logp(dtype, &a, C, theta_dev, lp_dev, grad_dev, stream), "logp_grad");
+  return PM4_OK;
+}
+
+extern "C" int pm4_deterministics(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, void* out_dev, void* stream) {
+  if (!m || M < 0) return fail(PM4_EINVAL, "pm4_deterministics: bad argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (M == 0 || m->det_row == 0) return PM4_OK;
+  if (!theta_dev || !out_dev) return fail(PM4_EINVAL, "pm4_deterministics: null buffer");
+  CU(cudaSetDevice(m->device));
+  pm4_mod_args_t a = m->args(dtype);
+  MOD(m->f_dets(dtype, &a, M, theta_dev, out_dev, stream), "deterministics");
+  return PM4_OK;
+}
+
+static size_t real_size(int dtype) { return dtype == PM4_F64 ? 8 : 4; }
+
+extern "C" int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth) {
+  if (!m) return PM4_EINVAL;
+  const size_t rs = real_size(dtype), DP = (size_t)m->info.DP;
+  const size_t slots = (size_t)PM4_SLOT_MEM + 2 * (size_t)(max_tree_depth + 1);
+  return (int64_t)(((size_t)C * DP * (2 + slots) + (size_t)C * 6) * rs);
+}
+
+namespace {
+// device buffers of one run; freed on scope exit (stream-ordered)
+struct RunBuffers {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit RunBuffers(cudaStream_t s) : st(s) {}
+  ~RunBuffers() {
+    for (void* p : ptrs) cudaFreeAsync(p, st);
+  }
+  int get(void** out, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, st);
+    if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(*out);
+    return PM4_OK;
+  }
+};
+
+int fill_adapt(pm4_mod_run_t& r, const pm4_adapt_cfg_t& a) {
+  if (a.mode != PM4_EPS_POOLED && a.mode != PM4_EPS_PER_CHAIN) return fail(PM4_EINVAL, "unknown step-size mode %d", a.mode);
+  r.adapt_enabled = a.enabled ? 1 : 0;
+  r.adapt_pooled = a.mode == PM4_EPS_POOLED ? 1 : 0;
+  r.num_adapt = a.num_adaptation_steps;
+  r.target_accept = a.target_accept_prob;
+  r.shrinkage = a.exploration_shrinkage;
+  r.smoothing = a.step_count_smoothing;
+  r.decay = a.decay_rate;
+  return PM4_OK;
+}
+
+// run T transitions: lock-step single-transition launches while a pooled step size still moves
+// (transitions 0..num_adapt), then one launch for the rest
+int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, cudaStream_t st) {
+  pm4m_run_fn f = nuts ? m->f_nuts : m->f_hmc;
+  int t = 0;
+  if (r.adapt_enabled && r.adapt_pooled) {
+    const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
+    for (; t < coupled; ++t) {
+      r.t_begin = t;
+      r.t_count = 1;
+      MOD(f(dtype, &r, wpb, st), nuts ? "nuts (lock-step)" : "hmc (lock-step)");
+      MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");
+    }
+  }
+  if (t < T) {
+    r.t_begin = t;
+    r.t_count = T - t;
+    MOD(f(dtype, &r, wpb, st), nuts ? "nuts" : "hmc");
+  }
+  return PM4_OK;
+}
+}  // namespace
+
+extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
+                            const void* step_scale_dev, const void* momenta_dev, void* states_dev, void* lp_dev,
+                            int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev, void* log_accept_dev,
+                            int32_t* depth_dev, void* step_size_dev, int64_t* total_leapfrogs_dev, void* stream) {
+  if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_nuts_run: null argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0) return fail(PM4_EINVAL, "pm4_nuts_run: bad chain/draw counts");
+  if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 20) return fail(PM4_EINVAL, "max_tree_depth must be in [1, 20]");
+  if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
+  const int T = cfg->num_burnin + cfg->num_results;
+  const size_t slots = (size_t)PM4_SLOT_MEM + 2 * (size_t)(cfg->max_tree_depth + 1);
+
+  pm4_mod_run_t r;
+  memset(&r, 0, sizeof r);
+  r.A = m->args(dtype);
+  r.C = cfg->C; r.B = cfg->num_burnin; r.S = cfg->num_results;
+  r.max_depth = cfg->max_tree_depth;
+  r.chain_offset = cfg->chain_offset;
+  r.max_energy_diff = cfg->max_energy_diff;
+  r.seed_lo = (uint32_t)cfg->seed; r.seed_hi = (uint32_t)(cfg->seed >> 32);
+  if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  RunBuffers buf(st);
+  if ((rc = buf.get(&r.th, C * DP * rs))) return rc;
+  if ((rc = buf.get(&r.gr, C * DP * rs))) return rc;
+  if ((rc = buf.get(&r.lp, C * rs))) return rc;
+  if ((rc = buf.get(&r.da, C * 4 * rs))) return rc;
+  if ((rc = buf.get(&r.accept, C * rs))) return rc;
+  if ((rc = buf.get(&r.scratch, slots * C * DP * rs))) return rc;
+  r.step_scale = step_scale_dev; r.momenta = momenta_dev;
+  r.states = states_dev; r.lp_out = lp_dev; r.leapfrogs = leapfrogs_dev; r.diverging = diverging_dev;
+  r.energy = energy_dev; r.log_accept = log_accept_dev; r.depth = depth_dev;
+  r.total_leapfrogs = total_leapfrogs_dev;
+
+  MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
+  if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, st))) return rc;
+  if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  return PM4_OK;
+}
+
+extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0_dev,
+                           const void* step_scale_dev, const void* momenta_dev, const void* uniforms_dev,
+                           void* states_dev, void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev,
+                           void* step_size_dev, void* traj_dev, void* stream) {
+  if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_hmc_run: null argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0 || cfg->num_leapfrog_steps < 1)
+    return fail(PM4_EINVAL, "pm4_hmc_run: bad chain/draw/leapfrog counts");
+  if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
+  const int T = cfg->num_burnin + cfg->num_results;
+
+  pm4_mod_run_t r;
+  memset(&r, 0, sizeof r);
+  r.A = m->args(dtype);
+  r.C = cfg->C; r.B = cfg->num_burnin; r.S = cfg->num_results;
+  r.num_leapfrog = cfg->num_leapfrog_steps;
+  r.chain_offset = cfg->chain_offset;
+  r.seed_lo = (uint32_t)cfg->seed; r.seed_hi = (uint32_t)(cfg->seed >> 32);
+  if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  RunBuffers buf(st);
+  if ((rc = buf.get(&r.th, C * DP * rs))) return rc;
+  if ((rc = buf.get(&r.gr, C * DP * rs))) return rc;
+  if ((rc = buf.get(&r.lp, C * rs))) return rc;
+  if ((rc = buf.get(&r.da, C * 4 * rs))) return rc;
+  if ((rc = buf.get(&r.accept, C * rs))) return rc;
+  r.step_scale = step_scale_dev; r.momenta = momenta_dev; r.uniforms = uniforms_dev;
+  r.states = states_dev; r.lp_out = lp_dev; r.log_accept = log_accept_dev; r.diverging = accepted_dev;
+  r.traj = traj_dev;
+
+  MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
+  if ((rc = drive(m, dtype, r, false, cfg->warps_per_block, T, st))) return rc;
+  if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  return PM4_OK;
+}
+
+extern "C" int64_t pm4_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+extern "C" const char* pm4_last_error(void) { return g_err.c_str(); }
+extern "C" int pm4_abi_version(void) { return PM4_ABI_VERSION; }

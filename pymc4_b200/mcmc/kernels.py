@@ -1,0 +1,77 @@
+"""Parameter carriers with the constructor signatures of the TFP kernels the reference binds.
+
+The reference routes ``pm.sample(**kwargs)`` to the kernel, the step-size adaptation and
+``sample_chain`` by *introspecting their signatures* (pymc4/mcmc/samplers.py:191-207).  These
+classes keep that routing intact -- same parameter names and defaults as
+``tfp.mcmc.NoUTurnSampler`` / ``HamiltonianMonteCarlo`` /
+``DualAveragingStepSizeAdaptation`` / ``sample_chain`` (TFP ~0.12) -- but they
+only hold configuration: the transition itself runs in the CUDA kernels
+(csrc/pm4_kernels.cuh).
+"""
+from typing import Any, Callable, Optional
+
+
+class NoUTurnSampler:
+    def __init__(self, target_log_prob_fn, step_size, max_tree_depth=10, max_energy_diff=1000.0,
+                 unrolled_leapfrog_steps=1, parallel_iterations=10, seed=None, name=None):
+        if int(unrolled_leapfrog_steps) != 1:
+            raise NotImplementedError("unrolled_leapfrog_steps != 1 is not supported by the CUDA NUTS kernel")
+        self.target_log_prob_fn = target_log_prob_fn
+        self.step_size = step_size
+        self.max_tree_depth = int(max_tree_depth)
+        self.max_energy_diff = float(max_energy_diff)
+        self.unrolled_leapfrog_steps = 1
+        self.parallel_iterations = parallel_iterations
+        self.seed = seed
+        self.name = name
+
+    is_calibrated = True
+
+    @property
+    def parameters(self):
+        return dict(step_size=self.step_size, max_tree_depth=self.max_tree_depth,
+                    max_energy_diff=self.max_energy_diff)
+
+
+class HamiltonianMonteCarlo:
+    def __init__(self, target_log_prob_fn, step_size, num_leapfrog_steps, state_gradients_are_stopped=False,
+                 step_size_update_fn=None, seed=None, store_parameters_in_results=False, name=None):
+        if step_size_update_fn is not None:
+            raise NotImplementedError("step_size_update_fn is not supported; use the dual-averaging adaptation")
+        self.target_log_prob_fn = target_log_prob_fn
+        self.step_size = step_size
+        self.num_leapfrog_steps = int(num_leapfrog_steps)
+        self.seed = seed
+        self.name = name
+
+    is_calibrated = True
+
+    @property
+    def parameters(self):
+        return dict(step_size=self.step_size, num_leapfrog_steps=self.num_leapfrog_steps)
+
+
+class DualAveragingStepSizeAdaptation:
+    def __init__(self, inner_kernel, num_adaptation_steps, target_accept_prob=0.75, exploration_shrinkage=0.05,
+                 shrinkage_target=None, step_count_smoothing=10, decay_rate=0.75,
+                 step_size_setter_fn: Optional[Callable] = None, step_size_getter_fn: Optional[Callable] = None,
+                 log_accept_prob_getter_fn: Optional[Callable] = None, reduce_fn: Any = None,
+                 validate_args=False, name=None):
+        if shrinkage_target is not None:
+            raise NotImplementedError("shrinkage_target other than the default 10 * step_size is not supported")
+        self.inner_kernel = inner_kernel
+        self.num_adaptation_steps = int(num_adaptation_steps)
+        self.target_accept_prob = float(target_accept_prob)
+        self.exploration_shrinkage = float(exploration_shrinkage)
+        self.step_count_smoothing = float(step_count_smoothing)
+        self.decay_rate = float(decay_rate)
+        self.name = name
+
+    is_calibrated = True
+
+
+def sample_chain(num_results, current_state, previous_kernel_results=None, kernel=None, num_burnin_steps=0,
+                 num_steps_between_results=0, trace_fn=None, return_final_kernel_results=False,
+                 parallel_iterations=10, seed=None, name=None):
+    """Signature carrier only (see module docstring); the chain loop runs on the device."""
+    raise NotImplementedError("sample_chain is executed by libpm4b200 (pm4_nuts_run / pm4_hmc_run)")

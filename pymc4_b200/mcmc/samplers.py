@@ -1,0 +1,495 @@
+"""Sampler registry and the NUTS / HMC samplers behind ``pm.sample``.
+
+Class protocol, kwarg routing and return layout follow the reference
+(pymc4/mcmc/samplers.py:25-262 registry + ``_BaseSampler``, :265-315 ``HMC``, :342-419 ``NUTS``,
+:729-829 ``build_logp_and_deterministic_functions`` / ``vectorize_logp_function`` /
+``tile_init``).  The one call that changes is ``_run_chains`` (:172-189): instead of
+``tfp.mcmc.sample_chain`` it calls ``pm4_nuts_run`` / ``pm4_hmc_run`` of libpm4b200 through
+ctypes, with torch tensors as device buffers.  Out of scope for this backend:
+``hmc_simple`` / ``nuts_simple`` / ``rwm`` / ``compound`` (gradient-free or discrete-latent kernels).
+"""
+import abc
+import inspect
+import logging
+import os
+from typing import Any, Dict, List, Optional, Union
+
+import numpy as np
+
+from .. import flow
+from .. import ir as irmod
+from .._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_hmc_cfg, make_nuts_cfg
+from ..coroutine_model import Model
+from ..utils import NameParts
+from . import kernels as mcmc
+from .utils import (
+    KERNEL_KWARGS_SET,
+    initialize_sampling_state,
+    initialize_state,
+    scope_remove_transformed_part_if_required,
+    trace_to_arviz,
+)
+
+__all__ = ["HMC", "NUTS"]
+reg_samplers: Dict[str, type] = {}
+
+_log = logging.getLogger("pymc4.sampling")
+if not _log.handlers:
+    _log.addHandler(logging.StreamHandler())
+_log.setLevel(logging.INFO)
+
+# keyword arguments of this backend that the reference does not have
+_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block")
+
+
+def register_sampler(cls):
+    reg_samplers[cls._name] = cls
+    return cls
+
+
+def _signature_keys(fn, skip: int = 0) -> set:
+    return set(list(inspect.signature(fn).parameters.keys())[skip:])
+
+
+class _BaseSampler(metaclass=abc.ABCMeta):
+    _grad = False
+    _name: str = ""
+    _kernel: Any = None
+    _adaptation: Any = None
+    default_kernel_kwargs: dict = {}
+    default_adapter_kwargs: dict = {}
+
+    def __init__(self, model: Model, **kwargs):
+        if not isinstance(model, Model):
+            raise TypeError(
+                "`sample` function only supports `pymc4.Model` objects, but you've passed `{}`".format(type(model))
+            )
+        _, _, disc_names, cont_names, _, _ = initialize_state(model)
+        if self._grad is True and disc_names:
+            raise ValueError("Discrete distributions can't be used with gradient-based sampler")
+        self.model = model
+        self.stat_names: List[str] = []
+        self.parent_inds: List[int] = []
+        self.backend_kwargs = {k: kwargs.pop(k) for k in _BACKEND_KWARGS if k in kwargs}
+        self._assign_arguments(kwargs)
+        self._check_arguments()
+        self._bound_kwargs()
+
+    # -- kwarg routing (reference :191-229) ----------------------------------
+    def _assign_arguments(self, kwargs):
+        keys = set(kwargs)
+        adaptation_keys = _signature_keys(self._adaptation.__init__, 1) if self._adaptation else set()
+        kernel_keys = _signature_keys(self._kernel.__init__, 1)
+        chain_keys = _signature_keys(mcmc.sample_chain)
+        self.adaptation_kwargs = {k: kwargs[k] for k in adaptation_keys & keys}
+        self.kernel_kwargs = {k: kwargs[k] for k in kernel_keys & keys}
+        self.chain_kwargs = {k: kwargs[k] for k in chain_keys & keys}
+
+    def _check_arguments(self):
+        a, k, c = self.adaptation_kwargs.keys(), self.kernel_kwargs.keys(), self.chain_kwargs.keys()
+        if (a & k) or (a & c) or (k & c):
+            raise ValueError("Ambiguity in setting kwargs for `kernel`, `adaptation_kernel`, `chain_sampler`")
+
+    def _bound_kwargs(self, *args):
+        for k, v in self.default_kernel_kwargs.items():
+            self.kernel_kwargs.setdefault(k, v)
+        for k, v in self.default_adapter_kwargs.items():
+            self.adaptation_kwargs.setdefault(k, v)
+
+    def __call__(self, *args, **kwargs):
+        return self._sample(*args, **kwargs)
+
+    @classmethod
+    def _default_kernel_maker(cls):
+        return KERNEL_KWARGS_SET(
+            kernel=cls._kernel,
+            adaptive_kernel=cls._adaptation,
+            kernel_kwargs=cls.default_kernel_kwargs,
+            adaptive_kwargs=cls.default_adapter_kwargs,
+        )
+
+    @abc.abstractmethod
+    def trace_fn(self, current_state, pkr):
+        """Pick the per-draw statistics out of the kernel results (a dict of device tensors)."""
+
+    # -- the sampling call (reference :78-170) ---------------------------------
+    def _sample(
+        self,
+        *,
+        num_samples: int = 1000,
+        num_chains: int = 10,
+        burn_in: int = 100,
+        observed: Optional[dict] = None,
+        state: Optional[flow.SamplingState] = None,
+        use_auto_batching: bool = True,
+        xla: bool = False,
+        seed: Optional[int] = None,
+        is_compound: bool = False,
+        trace_discrete: Optional[List[str]] = None,
+        include_log_likelihood=False,
+    ):
+        if state is not None and observed is not None:
+            raise ValueError("Can't use both `state` and `observed` arguments")
+        dtype = np.dtype(self.backend_kwargs.get("dtype", "float32"))
+        (logpfn, init, _deterministics_callback, deterministic_names, state_) = build_logp_and_deterministic_functions(
+            self.model,
+            num_chains=num_chains,
+            state=state,
+            observed=observed,
+            collect_reduced_log_prob=use_auto_batching,
+            parent_inds=self.parent_inds if is_compound else None,
+            dtype=dtype,
+            device=self.backend_kwargs.get("device", None),
+        )
+        init_state = list(init.values())
+        init_keys = list(init.keys())
+
+        # the device code evaluates one chain per warp whatever `use_auto_batching` says: a model
+        # written for manual batching is also a valid per-chain model
+        self.parallel_logpfn = vectorize_logp_function(logpfn)
+        self.deterministics_callback = vectorize_logp_function(_deterministics_callback)
+        init_state = tile_init(init_state, num_chains)
+
+        self._num_samples = num_samples
+        self.seed = seed
+        self._dtype = dtype
+        self._device_model = logpfn.device_model
+        if xla:
+            _log.debug("`xla=True` has no effect: the sampler is already one fused CUDA kernel")
+
+        results, sample_stats = self._run_chains(init_state, burn_in)
+
+        posterior = dict(zip(init_keys, results))
+        if trace_discrete:
+            init_keys_ = [scope_remove_transformed_part_if_required(k, state_.transformed_values)[1] for k in init_keys]
+            for name in trace_discrete:
+                key = init_keys[init_keys_.index(name)]
+                posterior[key] = posterior[key].to(dtype=self._device_model.torch.int32)
+
+        deterministic_values = ()
+        if len(sample_stats) > len(self.stat_names):
+            deterministic_values = sample_stats[len(self.stat_names):]
+            sample_stats = sample_stats[: len(self.stat_names)]
+        sampler_stats = dict(zip(self.stat_names, sample_stats))
+        if len(deterministic_names) > 0:
+            det_names = [d.name for d in self._device_model.ir.dets]
+            posterior.update(dict(zip(det_names, deterministic_values)))
+
+        log_likelihood_dict = dict()
+        if include_log_likelihood:
+            log_likelihood_dict = calculate_log_likelihood(self.model, posterior, state_)
+        self.last_run_info = self._run_info
+        return trace_to_arviz(
+            posterior,
+            sampler_stats if is_compound is False else None,
+            observed_data=state_.observed_values,
+            log_likelihood=log_likelihood_dict if include_log_likelihood else None,
+        )
+
+    # -- step-size policy -------------------------------------------------------
+    def _step_size_policy(self, step_size, num_chains: int):
+        """Map the reference's ``step_size`` conventions onto (eps0, per-dim scale, mode).
+
+        scalar                       -> one pooled step size adapted from the across-chain mean
+                                        acceptance (tfp reduces over all chains);
+        array with leading chain axis (``[C]``, ``[C, 1]``) -> independent per-chain adaptation;
+        list of per-part arrays ``[C, *core]`` (notebooks/radon_hierarchical.ipynb:123-146)
+                                     -> per-chain adaptation of a multiplier of a fixed per-dimension
+                                        scale (all dimensions of a chain see the same update).
+        """
+        ir = self._device_model.ir
+        if isinstance(step_size, (list, tuple)) and len(step_size) == len(ir.rvs):
+            scale = np.ones(ir.D, dtype=np.float64)
+            for rv, part in zip(ir.rvs, step_size):
+                part = np.asarray(part.detach().cpu().numpy() if hasattr(part, "detach") else part, dtype=np.float64)
+                full = np.broadcast_to(part, (num_chains,) + rv.shape) if part.ndim else np.full((num_chains,) + rv.shape, part)
+                if not np.allclose(full, full[0]):
+                    raise NotImplementedError("step sizes that differ between chains at start are not supported")
+                scale[rv.offset: rv.offset + rv.size] = full[0].reshape(-1)
+            return 1.0, scale, PM4_EPS_PER_CHAIN
+        arr = np.asarray(step_size.detach().cpu().numpy() if hasattr(step_size, "detach") else step_size, dtype=np.float64)
+        if arr.ndim == 0:
+            return float(arr), None, PM4_EPS_POOLED
+        if arr.shape[0] == num_chains and arr.size == num_chains:
+            flat = arr.reshape(-1)
+            if not np.allclose(flat, flat[0]):
+                raise NotImplementedError("step sizes that differ between chains at start are not supported")
+            return float(flat[0]), None, PM4_EPS_PER_CHAIN
+        if arr.size == ir.D:
+            return 1.0, arr.reshape(-1), PM4_EPS_POOLED
+        raise ValueError("cannot interpret step_size of shape {} for {} chains, D={}".format(arr.shape, num_chains, ir.D))
+
+    def _pack_init(self, init: List[np.ndarray]) -> np.ndarray:
+        ir = self._device_model.ir
+        C = int(np.shape(init[0])[0])
+        theta0 = np.empty((C, ir.D), dtype=np.float64)
+        for rv, part in zip(ir.rvs, init):
+            theta0[:, rv.offset: rv.offset + rv.size] = np.asarray(part, dtype=np.float64).reshape(C, rv.size)
+        return theta0
+
+    def _unpack_states(self, states):
+        """device [S, C, D] -> list of per-variable views [S, C, *core] in trace order."""
+        S, C = states.shape[0], states.shape[1]
+        return [states[:, :, rv.offset: rv.offset + rv.size].reshape((S, C) + rv.shape)
+                for rv in self._device_model.ir.rvs]
+
+    def _seed_value(self) -> int:
+        if self.seed is None:
+            return int.from_bytes(os.urandom(8), "little")
+        return int(self.seed) & (2**64 - 1)
+
+    def _adapt_cfg(self, mode: int):
+        a = self.adaptation_kwargs
+        if self._adaptation is None or "num_adaptation_steps" not in a:
+            return make_adapt(mode=mode, enabled=False)
+        spec = self._adaptation(inner_kernel=None, **{k: v for k, v in a.items() if not callable(v)})
+        return make_adapt(mode=mode, num_adaptation_steps=spec.num_adaptation_steps,
+                          target_accept_prob=spec.target_accept_prob,
+                          exploration_shrinkage=spec.exploration_shrinkage,
+                          step_count_smoothing=spec.step_count_smoothing, decay_rate=spec.decay_rate, enabled=True)
+
+    def _check_chain_kwargs(self):
+        ck = self.chain_kwargs
+        if ck.get("num_steps_between_results", 0):
+            raise NotImplementedError("thinning (num_steps_between_results) is not supported")
+        if ck.get("return_final_kernel_results", False) or ck.get("previous_kernel_results") is not None:
+            raise NotImplementedError("resuming from kernel results is not supported")
+
+    def _deterministic_values(self, states):
+        ir = self._device_model.ir
+        if not ir.dets:
+            return ()
+        out = self._device_model.deterministics(states, dtype=self._dtype)
+        S, C = states.shape[0], states.shape[1]
+        return tuple(out[:, :, d.out_offset: d.out_offset + d.n].reshape((S, C) + d.shape) for d in ir.dets)
+
+    @abc.abstractmethod
+    def _run_chains(self, init, burn_in):
+        """Run the chains on the device; return (results, sample_stats) in the reference layout."""
+
+
+@register_sampler
+class HMC(_BaseSampler):
+    """Hamiltonian Monte Carlo with a fixed number of leapfrog steps under dual-averaging
+    step-size adaptation (defaults ``step_size=0.1, num_leapfrog_steps=3``; reference :265-315)."""
+
+    _name = "hmc"
+    _grad = True
+    _adaptation = mcmc.DualAveragingStepSizeAdaptation
+    _kernel = mcmc.HamiltonianMonteCarlo
+
+    default_kernel_kwargs: dict = {"step_size": 0.1, "num_leapfrog_steps": 3}
+    default_adapter_kwargs: dict = {}
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.stat_names = ["mean_tree_accept"]
+
+    def trace_fn(self, current_state, pkr):
+        return (pkr["log_accept"],) + tuple(self._deterministic_values(current_state))
+
+    def _run_chains(self, init, burn_in):
+        self._check_chain_kwargs()
+        dm = self._device_model
+        theta0 = self._pack_init(init)
+        C = theta0.shape[0]
+        spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
+        eps0, scale, mode = self._step_size_policy(spec.step_size, C)
+        adapt = self._adapt_cfg(mode)
+        cfg = make_hmc_cfg(C, self._num_samples, burn_in, step_size=eps0,
+                           num_leapfrog_steps=spec.num_leapfrog_steps, seed=self._seed_value(), adapt=adapt,
+                           warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
+                           chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        out = dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale)
+        self._run_info = dict(step_size=out["step_size"], kernel="hmc",
+                              leapfrogs_per_transition=spec.num_leapfrog_steps)
+        results = self._unpack_states(out["states"])
+        return results, self.trace_fn(out["states"], out)
+
+
+@register_sampler
+class NUTS(_BaseSampler):
+    """No-U-Turn sampler under dual-averaging step-size adaptation (default ``step_size=0.1``;
+    stats ``lp, tree_size, diverging, energy, mean_tree_accept``; reference :342-419)."""
+
+    _name = "nuts"
+    _grad = True
+    _adaptation = mcmc.DualAveragingStepSizeAdaptation
+    _kernel = mcmc.NoUTurnSampler
+
+    default_adapter_kwargs: dict = {
+        "num_adaptation_steps": 100,
+        "step_size_getter_fn": lambda pkr: pkr.step_size,
+        "log_accept_prob_getter_fn": lambda pkr: pkr.log_accept_ratio,
+        "step_size_setter_fn": lambda pkr, new_step_size: pkr._replace(step_size=new_step_size),
+    }
+    default_kernel_kwargs: dict = {"step_size": 0.1}
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.stat_names = ["lp", "tree_size", "diverging", "energy", "mean_tree_accept"]
+
+    def trace_fn(self, current_state, pkr):
+        return (
+            pkr["lp"],
+            pkr["leapfrogs"],
+            pkr["diverging"].to(dtype=self._device_model.torch.bool),
+            pkr["energy"],
+            pkr["log_accept"],
+        ) + tuple(self._deterministic_values(current_state))
+
+    def _run_chains(self, init, burn_in):
+        self._check_chain_kwargs()
+        dm = self._device_model
+        theta0 = self._pack_init(init)
+        C = theta0.shape[0]
+        spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
+        eps0, scale, mode = self._step_size_policy(spec.step_size, C)
+        cfg = make_nuts_cfg(C, self._num_samples, burn_in, step_size=eps0, seed=self._seed_value(),
+                            max_tree_depth=spec.max_tree_depth, max_energy_diff=spec.max_energy_diff,
+                            adapt=self._adapt_cfg(mode),
+                            warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
+                            chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale)
+        self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
+                              depth=out["depth"], kernel="nuts")
+        results = self._unpack_states(out["states"])
+        return results, self.trace_fn(out["states"], out)
+
+
+# ---------------------------------------------------------------------------
+# log-density builder (reference :729-829)
+# ---------------------------------------------------------------------------
+_device_models: Dict[Any, Any] = {}
+
+
+def _get_device_model(ir: irmod.ModelIR, dtype, device):
+    from .._cabi import DeviceModel
+
+    f64 = np.dtype(dtype) == np.float64
+    dev = 0 if device is None else int(device)
+    key = (ir.struct_hash, dev, f64)
+    dm = _device_models.get(key)
+    if dm is None:
+        dm = _device_models[key] = DeviceModel(ir, device=dev, f64=f64)
+    else:
+        same = (dm.ir.dataf.shape == ir.dataf.shape and dm.ir.datai.shape == ir.datai.shape
+                and np.array_equal(dm.ir.dataf, ir.dataf) and np.array_equal(dm.ir.datai, ir.datai))
+        if not same:
+            if dm.ir.dataf.shape == ir.dataf.shape and dm.ir.datai.shape == ir.datai.shape:
+                dm.set_data(ir)
+            else:
+                dm = _device_models[key] = DeviceModel(ir, device=dev, f64=f64)
+    return dm
+
+
+def build_logp_and_deterministic_functions(
+    model,
+    num_chains: Optional[int] = None,
+    observed: Optional[dict] = None,
+    state: Optional[flow.SamplingState] = None,
+    collect_reduced_log_prob: bool = True,
+    parent_inds: Optional[List] = None,
+    dtype="float32",
+    device: Optional[int] = None,
+):
+    """Lower ``model`` and return ``(logpfn, initial values, deterministics_callback,
+    deterministic_names, sampling state)`` like the reference; both callables run on the GPU.
+
+    ``logpfn(*values)`` / ``logpfn(**{name: value})`` accepts values with any number of leading
+    batch axes and returns a device tensor of that batch shape.
+    """
+    if not isinstance(model, Model):
+        raise TypeError(
+            "`sample` function only supports `pymc4.Model` objects, but you've passed `{}`".format(type(model))
+        )
+    if state is not None and observed is not None:
+        raise ValueError("Can't use both `state` and `observed` arguments")
+    ir, init_state, deterministic_names = irmod.lower_model(model, observed=observed, state=state)
+    unobserved_keys = list(init_state.all_unobserved_values.keys())
+    if parent_inds:
+        raise NotImplementedError("compound-step parent selection is outside this backend's scope")
+    dtype = np.dtype(dtype)
+    holder: Dict[str, Any] = {}
+
+    def device_model():
+        if "dm" not in holder:
+            holder["dm"] = _get_device_model(ir, dtype, device)
+        return holder["dm"]
+
+    def _pack(values, kwargs):
+        if kwargs and values:
+            raise TypeError("Either list state should be passed or a dict one")
+        if values:
+            kwargs = dict(zip(unobserved_keys, values))
+        parts, lead = [], None
+        for rv in ir.rvs:
+            v = kwargs[rv.name]
+            v = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            nd = len(rv.shape)
+            this_lead = v.shape[: v.ndim - nd] if nd else v.shape
+            lead = this_lead if lead is None else np.broadcast_shapes(lead, this_lead)
+            parts.append((rv, v))
+        flat = np.empty(tuple(lead) + (ir.D,), dtype=dtype)
+        for rv, v in parts:
+            flat[..., rv.offset: rv.offset + rv.size] = np.broadcast_to(v, tuple(lead) + rv.shape).reshape(
+                tuple(lead) + (rv.size,))
+        return flat, tuple(lead)
+
+    def logpfn(*values, **kwargs):
+        flat, lead = _pack(values, kwargs)
+        lp, _ = device_model().logp_grad(flat.reshape(-1, ir.D), dtype=dtype, want_grad=False)
+        return lp.reshape(lead)
+
+    def logp_and_grad(*values, **kwargs):
+        flat, lead = _pack(values, kwargs)
+        lp, grad = device_model().logp_grad(flat.reshape(-1, ir.D), dtype=dtype, want_grad=True)
+        return lp.reshape(lead), grad.reshape(lead + (ir.D,))
+
+    def deterministics_callback(*values, **kwargs):
+        flat, lead = _pack(values, kwargs)
+        out = device_model().deterministics(flat.reshape(-1, ir.D), dtype=dtype)
+        return [out[:, d.out_offset: d.out_offset + d.n].reshape(lead + d.shape) for d in ir.dets]
+
+    class _Fn:
+        """callable with the lowered model attached (``.ir``, ``.device_model``)."""
+
+        def __init__(self, fn):
+            self._fn = fn
+            self.ir = ir
+            self.value_and_gradient = logp_and_grad
+
+        def __call__(self, *a, **k):
+            return self._fn(*a, **k)
+
+        @property
+        def device_model(self):
+            return device_model()
+
+    init = {k: np.asarray(v, dtype=dtype) for k, v in init_state.all_unobserved_values.items()}
+    return (_Fn(logpfn), init, _Fn(deterministics_callback), deterministic_names, init_state)
+
+
+def vectorize_logp_function(logpfn):
+    """The device functions already broadcast over leading (chain / draw) axes."""
+
+    def vectorized_logpfn(*state):
+        return logpfn(*state)
+
+    for attr in ("ir", "device_model", "value_and_gradient"):
+        if hasattr(logpfn, attr):
+            try:
+                setattr(vectorized_logpfn, attr, getattr(logpfn, attr))
+            except Exception:  # device_model may be unavailable on a CPU-only host
+                pass
+    return vectorized_logpfn
+
+
+def tile_init(init, num_repeats):
+    return [np.tile(np.expand_dims(np.asarray(t), 0), [num_repeats] + [1] * np.ndim(t)) for t in init]
+
+
+def calculate_log_likelihood(model: Model, posterior: Dict[str, Any], sampling_state: flow.SamplingState):
+    raise NotImplementedError(
+        "include_log_likelihood is listed under 'next' in SURVEY section 8(f) and is not built yet"
+    )

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances are the ones BASELINE.json's north_star states:
+  (a) per-state log_prob and gradients within 1e-5 relative in FP32, 1e-12 in FP64;
+  (b) fixed-L HMC trajectories with injected identical momenta within 1e-4 after 100 steps;
+  (c) NUTS posterior means / variances within 3 Monte Carlo standard errors, R-hat < 1.01;
+  (d) integer tree-depth and divergence counts bit-exact on the injected-RNG replay.
+"""
+import numpy as np
+import pytest
+
+from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_hmc_cfg, make_nuts_cfg
+from pymc4_b200.ir import lower_model
+from tests import models as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _dm(ir, f64=False):
+    from pymc4_b200._cabi import DeviceModel
+
+    return DeviceModel(ir, device=0, f64=f64)
+
+
+MODELS = {
+    "eight_schools": lambda: M.schools_pm4(),
+    "radon_real": lambda: M.radon_model(real=True),
+    "radon_synth": lambda: M.radon_model(real=False),
+    "logistic": lambda: M.logistic_model(*M.logistic_data()),
+    "poisson": lambda: M.poisson_model(*M.poisson_data()),
+    "nested": lambda: M.outer_model(),
+}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_logp_grad_parity_fp32(name, oracle_mod):
+    ir, _, _ = lower_model(MODELS[name]())
+    rng = np.random.default_rng(11)
+    theta = rng.normal(0, 0.4, (96, ir.D))
+    theta[0] = 0.0  # the test point every chain starts from
+    lp_ref, g_ref = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    lp, g = _dm(ir).logp_grad(theta.astype(np.float32), dtype=np.float32)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    assert np.all(np.isfinite(lp))
+    # (a) 1e-5 relative, per state: log-density against its own magnitude, gradient norm-wise
+    assert np.max(np.abs(lp - lp_ref) / np.maximum(np.abs(lp_ref), 1.0)) < 1e-5
+    for c in range(theta.shape[0]):
+        assert _rel(g[c], g_ref[c]) < 1e-5, (name, c)
+
+
+@pytest.mark.parametrize("name", ["eight_schools", "radon_real", "logistic", "poisson"])
+def test_logp_grad_parity_fp64(name, oracle_mod):
+    ir, _, _ = lower_model(MODELS[name]())
+    rng = np.random.default_rng(12)
+    theta = rng.normal(0, 0.4, (40, ir.D))
+    lp_ref, g_ref = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    lp, g = _dm(ir, f64=True).logp_grad(theta, dtype=np.float64)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    assert np.max(np.abs(lp - lp_ref) / np.maximum(np.abs(lp_ref), 1.0)) < 1e-12
+    for c in range(theta.shape[0]):
+        assert _rel(g[c], g_ref[c]) < 1e-12, (name, c)
+
+
+def test_golden_logp_values(golden):
+    # the reference's own golden value (tests/test_8schools.py:61) and the radon.csv values
+    ir, _, _ = lower_model(M.schools_pm4())
+    th = ir.join_theta({"schools_pm4/eta": np.zeros(8), "schools_pm4/mu": 0.0, "schools_pm4/__log_tau": 1.0})
+    lp64, _ = _dm(ir, f64=True).logp_grad(th[None], dtype=np.float64)
+    assert abs(float(lp64[0]) - golden["eight_schools"]["scipy_f64"]) < 1e-11
+    assert np.float32(float(lp64[0])) == np.float32(golden["eight_schools"]["reference_assert_f32"])
+    lp32, _ = _dm(ir).logp_grad(th[None].astype(np.float32), dtype=np.float32)
+    np.testing.assert_allclose(float(lp32[0]), golden["eight_schools"]["reference_assert_f32"], rtol=1e-6)
+
+    ir, _, _ = lower_model(M.radon_model(real=True))
+    dm = _dm(ir, f64=True)
+    D = ir.D
+    pts = np.stack([np.zeros(D), np.array(golden["radon_919"]["theta_rand"])])
+    lp, _ = dm.logp_grad(pts, dtype=np.float64)
+    np.testing.assert_allclose(lp.cpu().numpy(), [golden["radon_919"]["logp_at_zero"], golden["radon_919"]["logp_at_rand"]],
+                               rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["eight_schools", "radon_synth"])
+def test_hmc_trajectory_parity(name, oracle_mod):
+    """(b) one 100-leapfrog trajectory per chain from identical injected momenta."""
+    ir, _, _ = lower_model(MODELS[name]())
+    C, D, L = 16, ir.D, 100
+    rng = np.random.default_rng(5)
+    theta0 = rng.normal(0, 0.2, (C, D))
+    momenta = rng.standard_normal((1, C, D))
+    uniforms = rng.random((1, C))
+    eps = 0.005 if name == "radon_synth" else 0.05  # inside the stable region of the integrator
+    cfg = make_hmc_cfg(C, 1, 0, step_size=eps, num_leapfrog_steps=L, seed=1, adapt=make_adapt(enabled=False))
+    ref = oracle_mod.Oracle(ir).hmc(cfg, theta0, dtype=np.float64, momenta=momenta, uniforms=uniforms)
+    out = _dm(ir).hmc(cfg, theta0.astype(np.float32), dtype=np.float32, momenta=momenta, uniforms=uniforms, want_traj=True)
+    traj = out["traj"].cpu().numpy()
+    assert np.max(np.abs(traj - ref["traj"])) < 1e-4
+    np.testing.assert_allclose(out["log_accept"].cpu().numpy(), ref["log_accept"], atol=5e-3, rtol=1e-4)
+    # and the accept decisions + kept states agree
+    assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+    assert np.max(np.abs(out["states"].cpu().numpy() - ref["states"])) < 1e-4
+
+
+def test_hmc_chain_parity_with_adaptation(oracle_mod):
+    """A short adaptive HMC chain (pooled and per-chain dual averaging) replayed from injected randomness."""
+    ir, _, _ = lower_model(M.schools_pm4())
+    C, D, B, S = 8, ir.D, 15, 10
+    rng = np.random.default_rng(7)
+    momenta = rng.standard_normal((B + S, C, D))
+    uniforms = rng.random((B + S, C))
+    for mode in (PM4_EPS_POOLED, PM4_EPS_PER_CHAIN):
+        cfg = make_hmc_cfg(C, S, B, step_size=0.1, num_leapfrog_steps=3, seed=3,
+                           adapt=make_adapt(mode=mode, num_adaptation_steps=B))
+        ref = oracle_mod.Oracle(ir).hmc(cfg, np.zeros(D), dtype=np.float64, momenta=momenta, uniforms=uniforms)
+        out = _dm(ir, f64=True).hmc(cfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta, uniforms=uniforms)
+        assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+        np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-9)
+        np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name,mode", [("eight_schools", PM4_EPS_POOLED), ("eight_schools", PM4_EPS_PER_CHAIN),
+                                       ("radon_synth", PM4_EPS_PER_CHAIN)])
+def test_nuts_replay_bit_exact_integers(name, mode, oracle_mod):
+    """(d) FP64 replay with injected momenta: tree depth, leapfrog and divergence counts are bit-exact."""
+    ir, _, _ = lower_model(MODELS[name]())
+    C, D = 12, ir.D
+    B, S = (25, 25) if name == "eight_schools" else (12, 10)
+    rng = np.random.default_rng(21)
+    momenta = rng.standard_normal((B + S, C, D))
+    cfg = make_nuts_cfg(C, S, B, step_size=0.1, seed=99, adapt=make_adapt(mode=mode, num_adaptation_steps=B))
+    ref = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(D), dtype=np.float64, momenta=momenta)
+    out = _dm(ir, f64=True).nuts(cfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta)
+    for key in ("leapfrogs", "depth", "diverging"):
+        assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
+    assert np.array_equal(out["total_leapfrogs"].cpu().numpy(), ref["total_leapfrogs"])
+    np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-8)
+    np.testing.assert_allclose(out["energy"].cpu().numpy(), ref["energy"], rtol=1e-9, atol=1e-8)
+    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
+
+
+def test_philox_momentum_stream_matches_host(oracle_mod):
+    """Device and host draw the same Philox momenta (FP64 Box-Muller, 1 ulp-level agreement)."""
+    ir, _, _ = lower_model(M.radon_model(real=False))
+    C, D = 4, ir.D
+    cfg = make_hmc_cfg(C, 1, 0, step_size=1e-9, num_leapfrog_steps=1, seed=1234, adapt=make_adapt(enabled=False),
+                       chain_offset=5)
+    # with a vanishing step the proposal equals the start: recover p from the kinetic-energy difference is
+    # not possible, so compare through the trajectory of a *unit* step on a flat direction instead:
+    ref = oracle_mod.Oracle(ir).hmc(cfg, np.zeros(D), dtype=np.float64)
+    out = _dm(ir, f64=True).hmc(cfg, np.zeros((C, D)), dtype=np.float64, want_traj=True)
+    # theta' = theta + eps * (p + eps/2 * grad)  ->  identical momenta give identical proposals
+    np.testing.assert_allclose(out["traj"].cpu().numpy(), ref["traj"], rtol=0, atol=1e-20)
+    for c in range(C):
+        host = oracle_mod.draw_momentum(1234, 5 + c, 0, D, dtype=np.float64)
+        assert np.all(np.isfinite(host)) and abs(host.mean()) < 0.5
+
+
+def _split_rhat(x):
+    """x: [chain, draw] -> classic split R-hat."""
+    C, S = x.shape
+    h = S // 2
+    parts = np.concatenate([x[:, :h], x[:, h:2 * h]], axis=0)
+    m = parts.mean(axis=1)
+    w = parts.var(axis=1, ddof=1).mean()
+    b = h * m.var(ddof=1)
+    return np.sqrt(((h - 1) / h * w + b / h) / w)
+
+
+def test_nuts_posterior_matches_oracle(oracle_mod):
+    """(c) GPU FP32 NUTS (Philox stream) vs the oracle's FP64 NUTS on eight schools."""
+    ir, _, _ = lower_model(M.schools_pm4())
+    D = ir.D
+    B, S = 300, 400
+    Cg, Co = 512, 64
+    adapt = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)
+    out = _dm(ir).nuts(make_nuts_cfg(Cg, S, B, step_size=0.28, seed=2026, adapt=adapt), np.zeros((Cg, D), np.float32),
+                       dtype=np.float32)
+    ref = oracle_mod.Oracle(ir).nuts(make_nuts_cfg(Co, S, B, step_size=0.28, seed=77, adapt=adapt), np.zeros(D),
+                                     dtype=np.float64)
+    xs = out["states"].cpu().numpy().astype(np.float64)  # [S, C, D]
+    xr = ref["states"]
+    assert not np.any(np.isnan(xs))
+    for fn in (lambda v: v, lambda v: v * v):  # means and second moments (-> variances)
+        mg, mo = fn(xs).mean(axis=0), fn(xr).mean(axis=0)  # per-chain means [C, D]
+        se = np.sqrt(mg.var(axis=0, ddof=1) / Cg + mo.var(axis=0, ddof=1) / Co)
+        z = np.abs(mg.mean(axis=0) - mo.mean(axis=0)) / se
+        assert np.all(z < 3.0), z
+    for d in range(D):
+        assert _split_rhat(xs[:, :, d].T) < 1.01
+    # sampler health mirrors the oracle's
+    assert abs(np.exp(out["log_accept"].cpu().numpy()).mean() - np.exp(ref["log_accept"]).mean()) < 0.03
+    assert out["diverging"].float().mean().item() < 0.02
