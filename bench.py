@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- leapfrog gradient-evaluations/sec of the NUTS hot path on the radon-shaped model.
+
+Workload (BASELINE.json configs[1]): synthetic radon hierarchical model, 919 observations /
+85 counties (D = 175), 4096 chains of NUTS per GPU.  One "step" = one complete sampling call of
+the hot path for that batch of chains: bootstrap + `burn_in` adaptive transitions + `draws`
+kept transitions from the common test point (dual averaging with a per-chain step size, i.e.
+`step_size` carrying a leading chain axis -- the reference's no-collective configuration).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the CPU implementation on the host cores)
+
+Rank 0 prints ONE JSON line.  value = leapfrog gradient evaluations of all chains of all ranks
+divided by the device time (CUDA events, max over ranks).  e2e = the same metric through the
+public sampler API with host buffers (H2D of inputs and D2H of the trace inside the timing).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OBS, N_GROUPS, CHAINS_PER_GPU = 919, 85, 4096
+METRIC = "leapfrog_grad_evals_per_sec"
+UNIT = "grad-evals/s"
+# algorithmic cost of one unit (one leapfrog gradient evaluation of one chain), SURVEY section 8(d):
+# F = 8 N + 14 G + 15 D flops; shared-data bytes = 12 N (idx, x, y read from on-chip memory)
+D_MODEL = 2 * N_GROUPS + 5
+FLOPS_PER_UNIT = 8 * N_OBS + 14 * N_GROUPS + 15 * D_MODEL
+ONCHIP_BYTES_PER_UNIT = 12 * N_OBS
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--burn-in", type=int, default=100)
+    ap.add_argument("--draws", type=int, default=100)
+    ap.add_argument("--step-size", type=float, default=0.1)
+    ap.add_argument("--seed", type=int, default=20261019)
+    ap.add_argument("--cpu-chains", type=int, default=0, help="chains of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--warps-per-block", type=int, default=0)
+    return ap.parse_args()
+
+
+def build_model():
+    from pymc4_b200.ir import lower_model
+    from tests import models as M
+
+    idx, x, y, g = M.radon_synthetic(N_OBS, N_GROUPS)
+    model = M.hierarchical_model(idx, x, y, g)
+    ir, _, _ = lower_model(model)
+    assert ir.D == D_MODEL
+    return model, ir
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "radon_hierarchical varying-intercept/slope, synthetic %d obs / %d counties (D=%d), "
+                    "%d chains NUTS per GPU" % (N_OBS, N_GROUPS, D_MODEL, args.chains),
+        "chains_per_gpu": args.chains,
+        "global_chains": args.chains * n_gpus,
+        "burn_in": args.burn_in,
+        "draws": args.draws,
+        "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept NUTS transitions",
+        "step_size": "per-chain dual averaging from %.3g (leading chain axis; no cross-chain coupling)" % args.step_size,
+        "max_tree_depth": 10,
+        "parallelism": "chains sharded, %d per GPU; no data-path collective" % args.chains,
+        "l2": "L2 flushed (256 MiB write) between timed steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (TFP-semantics restatement, oracle/pm4_oracle.c) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_sample_rate(ir, args, chains, seed):
+    from oracle import pm4_oracle
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, make_adapt, make_nuts_cfg
+
+    orc = pm4_oracle.Oracle(ir)
+    cfg = make_nuts_cfg(chains, args.draws, args.burn_in, step_size=args.step_size, seed=seed,
+                        adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=args.burn_in))
+    t0 = time.perf_counter()
+    out = orc.nuts(cfg, np.zeros(ir.D), dtype=np.float32)
+    dt = time.perf_counter() - t0
+    return float(out["total_leapfrogs"].sum()), dt
+
+
+def cpu_baseline(ir, args):
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    chains = args.cpu_chains or cores
+    # calibrate so the sample costs roughly 10-30 s of CPU work
+    evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
+    rate = evals / dt
+    if dt < 8.0 and not args.cpu_chains:
+        chains = int(min(args.chains, max(chains, chains * 15.0 / max(dt, 1e-3)) // cores * cores))
+        evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
+        rate = evals / dt
+    return {
+        "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "%d of the %d chains, same burn_in/draws, float32, OpenMP over chains (%d threads); "
+                  "%.3g grad-evals in %.1f s" % (chains, args.chains, cores, evals, dt),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, ir = build_model()
+    from oracle import pm4_oracle
+
+    pm4_oracle.build()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    chains = args.cpu_chains or 2 * cores
+    for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU code
+        cpu_sample_rate(ir, args, cores, args.seed + 1)
+    evals, secs = 0.0, 0.0
+    for k in range(args.steps):
+        e, dt = cpu_sample_rate(ir, args, chains, args.seed + k)
+        evals += e
+        secs += dt
+    value = evals / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "each step = %d of the %d chains per GPU, same burn_in/draws; TFP-semantics CPU oracle "
+                      "(the reference's TF/TFP stack is not installable in this image), OpenMP over chains" %
+                      (chains, args.chains),
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def onchip_peaks(torch):
+    """FP32-FMA and shared-memory peaks measured now on this GPU (csrc/pm4_peaks.cu)."""
+    import ctypes
+
+    from pymc4_b200 import codegen
+
+    src = os.path.join(ROOT, "pymc4_b200", "csrc", "pm4_peaks.cu")
+    lib = os.path.join(ROOT, "pymc4_b200", "libpm4peaks.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.run([codegen.find_nvcc()] + codegen.NVCC_FLAGS + ["-shared", "-o", lib, src], check=True)
+    L = ctypes.CDLL(lib)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    fp32, smem = ctypes.c_double(0), ctypes.c_double(0)
+    rc1 = L.pm4_peak_fp32_tflops(2, 20000, st, ctypes.byref(fp32))
+    rc2 = L.pm4_peak_smem_tbs(20000, st, ctypes.byref(smem))
+    return (fp32.value if rc1 == 0 else None), (smem.value if rc2 == 0 else None)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sampler has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pymc4_b200 import _cabi, diagnostics
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, make_adapt, make_nuts_cfg
+    from pymc4_b200.mcmc.samplers import NUTS
+
+    model, ir = build_model()
+    dm = _cabi.DeviceModel(ir, device=local_rank)
+    C, B, S = args.chains, args.burn_in, args.draws
+    adapt = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)
+
+    def cfg_for(step):
+        return make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + step, adapt=adapt,
+                             warps_per_block=args.warps_per_block, chain_offset=rank * C)
+
+    theta0 = torch.zeros((C, ir.D), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs already in HBM ------------------------------------
+    for w in range(args.warmup):
+        out = dm.nuts(cfg_for(1000 + w), theta0, dtype=np.float32)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    _cabi.launch_count(reset=True)
+    step_ms, leaps = [], 0
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # evict L2 between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = dm.nuts(cfg_for(k), theta0, dtype=np.float32)
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        leaps += int(out["total_leapfrogs"].sum().item())
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _cabi.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_secs = sum(step_ms) / 1e3
+    t = torch.tensor([dev_secs, float(leaps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_secs_max, total_leaps = float(tmax[0]), float(tsum[1])
+    else:
+        dev_secs_max, total_leaps = dev_secs, float(leaps)
+    value = total_leaps / dev_secs_max
+
+    # ---- diagnostics on the last step (all-gather of the monitored columns over NCCL) ---
+    cols = [0, 1, 2, 2 + N_GROUPS, ir.D - 3, ir.D - 2, ir.D - 1]  # mu_a, mu_b, alpha[0], beta[0], log sigmas, log eps
+    summ = diagnostics.summarize(out["states"], columns=cols)
+    ess_per_sec = summ["min_ess"] / (dev_secs_max / max(args.steps, 1))
+    mean_accept = float(torch.exp(out["log_accept"]).mean().item())
+    divergent = float(out["diverging"].float().mean().item())
+    mean_tree = float(out["leapfrogs"].float().mean().item())
+
+    # ---- end-to-end arm: public sampler API, host buffers in, host trace out --------------
+    e2e = None
+    if not args.no_e2e:
+        step_arr = np.full((C, 1), args.step_size, dtype=np.float32)
+        nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C)
+        e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
+        n_e2e = max(1, min(args.steps, 2))
+        for k in range(1 + n_e2e):  # first pass untimed (allocator / pinned-buffer warm-up)
+            barrier()
+            t0 = time.perf_counter()
+            trace = nuts(num_samples=S, num_chains=C, burn_in=B, seed=args.seed + 500 + k)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if k == 0:
+                continue
+            e2e_secs += dt
+            e2e_leaps += float(nuts.last_run_info["total_leapfrogs"].sum().item())
+            h2d = C * ir.D * 4 + ir.dataf.size * 4 + ir.datai.size * 4
+            d2h = sum(v.nbytes for v in trace.posterior.values()) + sum(v.nbytes for v in trace.sample_stats.values())
+        te = torch.tensor([e2e_secs, e2e_leaps], dtype=torch.float64, device=dev)
+        if world > 1:
+            a = te.clone()
+            dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = te.clone()
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            e2e_secs, e2e_leaps = float(a[0]), float(b[1])
+        e2e = {"value": e2e_leaps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_secs / n_e2e,
+               "api": "pymc4_b200.mcmc.samplers.NUTS(model, step_size=[C,1])(num_samples, num_chains, burn_in)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peaks_src = measured_peaks()
+    fp32_peak, smem_peak = onchip_peaks(torch)
+    units_per_step_gpu = leaps / max(args.steps, 1)
+    kernel_secs = float(np.mean(step_ms)) / 1e3
+    ach_tflops = units_per_step_gpu * FLOPS_PER_UNIT / kernel_secs / 1e12
+    ach_smem_tbs = units_per_step_gpu * ONCHIP_BYTES_PER_UNIT / kernel_secs / 1e12
+    roofline = {
+        "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": (ach_tflops / fp32_peak) if fp32_peak else None, "traffic": None,
+        "kernel": "pm4::nuts_kernel (one launch per step; bootstrap + export kernels are <0.1% of the step)",
+        "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
+        "peak_source": "FFMA microbenchmark run by this bench on this GPU (csrc/pm4_peaks.cu); "
+                       "MEASURED_PEAKS.json has no FP32-pipe entry",
+        "smem": {"achieved": ach_smem_tbs, "peak": smem_peak, "unit": "TB/s",
+                 "frac": (ach_smem_tbs / smem_peak) if smem_peak else None,
+                 "algorithmic_bytes_per_unit": ONCHIP_BYTES_PER_UNIT},
+        "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "source": peaks_src,
+                "note": "state and data are on-chip for this shape; HBM carries only the trace writes"},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dev_secs_max / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, world),
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "ess_per_sec": ess_per_sec,
+        "diagnostics": {"min_bulk_ess": summ["min_ess"], "max_split_rhat": summ["max_rhat"],
+                        "columns": cols, "chains": summ["n_chains"], "draws": summ["n_draws"],
+                        "mean_accept": mean_accept, "divergent_frac": divergent,
+                        "mean_leapfrogs_per_draw": mean_tree},
+        "wall_s_timed_region": wall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(ir, args)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

