@@ -82,8 +82,20 @@ typedef struct pm4_term {
   int32_t n_regs;      /* SSA registers used by the tape                */
   int32_t value_reg;   /* register holding the value                    */
   int32_t param_reg[3];/* registers holding the parameters (-1 unused)  */
-  int32_t flags;       /* reserved                                      */
+  int32_t plan;        /* index into plans, or -1                       */
 } pm4_term_t;
+
+/* Device execution plan of a term that gathers from free variables: its elements regrouped by
+ * gather target into length-sorted chunks dealt 32 at a time to the lanes of the chain's warp
+ * (pymc4_b200/plan.py).  Data-dependent, hence run-time pools; the CPU oracle ignores plans. */
+typedef struct pm4_plan {
+  int32_t term;       /* the term it belongs to                        */
+  int32_t n_gather;   /* gather loads sharing the plan's index array   */
+  int32_t n_slices;   /* slices of 32 chunk slots                      */
+  int32_t width;      /* reals per record: 1, 2 or 4                   */
+  int64_t meta;       /* offset of the plan metadata in plani          */
+  int64_t recs;       /* offset of the records in planf (in reals)     */
+} pm4_plan_t;
 
 /* tape opcodes */
 #define PM4_OP_LD_CONST 0 /* dst = imm                                                     */
@@ -149,6 +161,13 @@ typedef struct pm4_ir {
   int64_t n_datai;
   const int32_t* datai; /* constant index pool (gather indices)                  */
   uint64_t struct_hash; /* hash of everything except n, blob offsets and data    */
+  int32_t n_plans;
+  int32_t _pad2;
+  const pm4_plan_t* plans;
+  int64_t n_planf;
+  const double* planf;  /* plan records (permuted copies of observed data), multiple of 4 */
+  int64_t n_plani;
+  const int32_t* plani; /* plan metadata, multiple of 4                                   */
 } pm4_ir_t;
 
 typedef struct pm4_model pm4_model_t;
@@ -164,6 +183,10 @@ int pm4_model_dim(const pm4_model_t* m);
  * (reference: pm.sample(..., observed={...}), samplers.py:85-108).  Synchronous. */
 int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n_dataf,
                        const int32_t* datai, int64_t n_datai);
+
+/* Companion of pm4_model_set_data: replace the execution-plan pools (ir->plans / planf / plani,
+ * same sizes) after the observed data or gather indices changed.  Synchronous. */
+int pm4_model_set_plans(pm4_model_t* m, const pm4_ir_t* ir);
 
 /* Parity check (a): joint log-density and its gradient in unconstrained space for C chains.
  * Replaces parallel_logpfn + GradientTape (samplers.py:117-119, 762-770).

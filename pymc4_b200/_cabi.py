@@ -27,7 +27,8 @@ _lock = threading.Lock()
 _lib = None
 
 EXPORTS = [
-    "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_logp_grad",
+    "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_model_set_plans",
+    "pm4_logp_grad",
     "pm4_deterministics", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
 ]
@@ -69,6 +70,7 @@ def load_library():
     L.pm4_model_destroy.argtypes = [vp]
     L.pm4_model_dim.argtypes = [vp]
     L.pm4_model_set_data.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i64, ctypes.POINTER(ctypes.c_int32), i64]
+    L.pm4_model_set_plans.argtypes = [vp, ctypes.POINTER(CIR)]
     L.pm4_logp_grad.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.pm4_deterministics.argtypes = [vp, i32, i64, vp, vp, vp]
     L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
@@ -167,6 +169,7 @@ class DeviceModel:
         self.ir = ir
         c = self.packed.c
         self._check(self.lib.pm4_model_set_data(self.handle, c.dataf, c.n_dataf, c.datai, c.n_datai))
+        self._check(self.lib.pm4_model_set_plans(self.handle, self.packed.byref()))
 
     def logp_grad(self, theta, dtype=np.float32, want_grad: bool = True):
         """theta [C, D] (host or device) -> (lp [C], grad [C, D]) device tensors."""

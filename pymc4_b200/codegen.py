@@ -6,8 +6,19 @@ RNG).  This module only emits the *glue*: a ``Model`` struct whose ``terms`` mem
 model's tape unrolled into straight-line code with the reverse sweep written out, so that
 nvcc inlines the density functions into the persistent leapfrog / NUTS kernel and keeps
 the chain state in registers.  One shared object is built per IR *structure*
-(``ModelIR.struct_hash``); data values, element counts and pool offsets stay run-time
-arguments, so new observed data reuses the same module.
+(``ModelIR.struct_hash``); data values, element counts, pool offsets and execution plans stay
+run-time arguments, so new observed data reuses the same module.
+
+Every term is emitted in one of four loop shapes:
+  uniform   n == 1 and nothing depends on the element index: evaluated once, on lane 0;
+  aligned   the term is element-wise over ONE free vector variable: lane l walks the elements it
+            already holds in registers (value from ``x[r]``, adjoint into ``gr[r]``);
+  planned   the term gathers from free variables through one index array: sliced-ELL walk over
+            chunks of equal gather target (pymc4_b200/plan.py), gathered values and their
+            adjoints in registers, records from the staged shared-memory pool;
+  general   lane-strided loop over the elements (adjoints of gathers fall back to atomics).
+Normal terms with a chain-uniform scale use the factored form: only r = value - loc and the sums
+of r, r*x ..., r*r are formed per element; 1/scale^2 multiplies the sums once.
 
 Reference semantics being lowered: ``collect_log_prob`` (pymc4/flow/executor.py:171-187)
 through ``TransformedSamplingExecutor`` (pymc4/flow/transformed_executor.py:22-138).
@@ -36,7 +47,7 @@ _UNARY_FWD = {
     "softplus": "pm4::m_softplus<real>({a})", "tanh": "pm4::m_tanh({a})", "abs": "pm4::m_abs({a})",
     "recip": "pm4::m_rcp({a})", "lgamma": "pm4::m_lgamma({a})",
 }
-# d(out)/d(a) as an expression of a (input) and r (output)
+# d(out)/d(a) as an expression of a (input), r (output) and the incoming adjoint g
 _UNARY_BWD = {
     "neg": "-{g}", "exp": "{g} * {r}", "log": "{g} / {a}", "log1p": "{g} / ((real)1 + {a})",
     "sqrt": "{g} / ((real)2 * {r})", "square": "(real)2 * {g} * {a}", "sigmoid": "{g} * {r} * ((real)1 - {r})",
@@ -44,6 +55,7 @@ _UNARY_BWD = {
     "abs": "(({a} > 0) ? {g} : (({a} < 0) ? -{g} : (real)0))", "recip": "-{g} * {r} * {r}",
     "lgamma": "{g} * pm4::m_digamma<real>({a})",
 }
+_KIND = {v: k for k, v in I.TERM_KINDS.items()}
 
 
 def _lit(v: float) -> str:
@@ -54,11 +66,10 @@ def _lit(v: float) -> str:
     return "(real)%r" % float(v)
 
 
-class _TermGen:
-    """Emit forward + reverse code for one tape."""
+class _Tape:
+    """Forward / reverse expressions of one SSA tape."""
 
-    def __init__(self, gen: "_ModuleGen", ops: List[I.Op], op_index0: int, tag: str):
-        self.gen = gen
+    def __init__(self, ops: List[I.Op], op_index0: int, tag: str):
         self.ops = ops
         self.op0 = op_index0
         self.tag = tag
@@ -66,17 +77,15 @@ class _TermGen:
     def v(self, reg: int) -> str:
         return "%s_v%d" % (self.tag, reg)
 
-    # forward expression of one op; `idx` is the element index expression, `xsrc` how x is read
-    def fwd(self, o: I.Op, idx: str, xread) -> str:
+    def fwd(self, o: I.Op, idx: str, xread, dread) -> str:
         name = I.OP_NAME[o.opcode]
         if name == "ld_const":
             return _lit(o.imm)
         if name == "ld_data":
-            blob = "c_blob(%d)" % (self.op0 + o.dst)
-            return "A.dataf[%s + %s]" % (blob, idx if o.mode == I.MODE_ELEM else "0")
-        if name in ("ld_x", "ld_z"):
-            if name == "ld_z":
-                raise NotImplementedError("unconstrained-space loads (ld_z) are not generated yet")
+            return dread(o, idx)
+        if name == "ld_z":
+            raise NotImplementedError("unconstrained-space loads (ld_z) are not generated yet")
+        if name == "ld_x":
             return xread(o, idx)
         a = self.v(o.a)
         if name in _UNARY_FWD:
@@ -85,13 +94,14 @@ class _TermGen:
         return {"add": "%s + %s", "sub": "%s - %s", "mul": "%s * %s", "div": "%s / %s",
                 "pow": "pm4::m_pow(%s, %s)"}[name] % (a, b)
 
-    # contributions of adjoint g of op o to its inputs: list of (input reg, expr)
     def bwd(self, o: I.Op, g: str) -> List[Tuple[int, str]]:
         name = I.OP_NAME[o.opcode]
         r = self.v(o.dst)
         if name in _UNARY_BWD:
             return [(o.a, _UNARY_BWD[name].format(g=g, a=self.v(o.a), r=r))]
-        a, b = (self.v(o.a), self.v(o.b)) if o.b >= 0 else (None, None)
+        if o.b < 0:
+            return []
+        a, b = self.v(o.a), self.v(o.b)
         if name == "add":
             return [(o.a, g), (o.b, g)]
         if name == "sub":
@@ -144,12 +154,14 @@ class _ModuleGen:
     def gen_terms(self) -> str:
         body: List[str] = []
         self.lines = body
-        op0 = 0
+        op0, plan_idx = 0, 0
         for k, t in enumerate(self.ir.terms):
-            self.gen_one_term(k, t, op0)
+            self.gen_one_term(k, t, op0, plan_idx)
             op0 += len(t.ops)
-        head = ["  template <typename real>",
-                "  static __device__ __forceinline__ real terms(const real (&x)[R], real (&gr)[R], pm4::Ctx<real>& c) {",
+            if t.plan is not None:
+                plan_idx += 1
+        head = ["  template <typename real, class CtxT>",
+                "  static __device__ __forceinline__ real terms(const real (&x)[R], real (&gr)[R], CtxT& c) {",
                 "    const int lane = c.lane; (void)lane;",
                 "    const pm4::ModelArgs<real>& A = c.A; (void)A;",
                 "    auto c_blob = [&](int op) -> int { return __ldg(A.op_blob + op); }; (void)c_blob;",
@@ -163,114 +175,67 @@ class _ModuleGen:
         tail += ["    return lp;", "  }"]
         return "\n".join(head + body + tail)
 
-    def gen_one_term(self, k: int, t: I.Term, op0: int):
-        ops = t.ops
-        tag = "t%d" % k
-        tg = _TermGen(self, ops, op0, tag)
-        kind = t.kind
-        uniform = [o.uniform for o in ops]
-        elem_bases = sorted({o.base for o in ops
-                             if I.OP_NAME[o.opcode] == "ld_x" and o.mode == I.MODE_ELEM})
-        all_uniform = all(uniform)
-        aligned = (len(elem_bases) == 1)
+    def gen_one_term(self, k: int, t: I.Term, op0: int, plan_idx: int):
+        ops, kind, tag = t.ops, t.kind, "t%d" % k
+        tp = _Tape(ops, op0, tag)
         E = self.emit
-        E("// ---- term %d: %s (%s), n=%s" % (k, t.label, [n for n, c in I.TERM_KINDS.items() if c == kind][0], t.n))
+        ld_x = I.OP["ld_x"]
+        uniform = [o.uniform for o in ops]
+        elem_bases = sorted({o.base for o in ops if o.opcode == ld_x and o.mode == I.MODE_ELEM})
+        plan = t.plan
+        if all(uniform) and t.n == 1:
+            shape = "uniform"
+        elif plan is not None:
+            shape = "planned"
+        elif len(elem_bases) == 1:
+            shape = "aligned"
+        else:
+            shape = "general"
+
+        n_par = I.TERM_NPARAMS[kind]
+        preg = list(t.param_regs[:n_par])
+        scale_reg = preg[1] if kind == I.TERM_KINDS["normal"] else (
+            preg[0] if kind in (I.TERM_KINDS["halfnormal"], I.TERM_KINDS["halfcauchy"]) else None)
+        scale_uniform = scale_reg is not None and uniform[scale_reg]
+        # the factored form needs the scale to enter the term only as the scale parameter
+        scale_feeds = scale_reg is not None and (any(o.a == scale_reg or o.b == scale_reg for o in ops)
+                                                 or scale_reg in (t.value_reg, preg[0]))
+        normal_fast = (kind == I.TERM_KINDS["normal"] and scale_uniform and shape != "uniform"
+                       and not scale_feeds)
+        K = "%s_K" % tag  # deferred adjoint multiplier 1/scale^2 of the factored Normal form
+
+        def sink(expr: str) -> str:
+            return "%s * (%s)" % (K, expr) if normal_fast else expr
+
+        E("// ---- term %d: %s (%s), n=%d, %s%s" % (k, t.label, _KIND[kind], t.n, shape,
+                                                      ", factored normal" if normal_fast else ""))
         E("{")
         touched_gx = [False]
+        gather_names: Dict[int, str] = {}
+        rec_field: Dict[int, str] = {}
+        if shape == "planned":
+            for j, dst in enumerate(plan.gather_ops):
+                gather_names[dst] = "%s_g%d" % (tag, j)
+            fields = ["x", "y", "z", "w"]
+            for j, dst in enumerate(plan.record_ops):
+                rec_field[dst] = ("%s_rec" % tag) if plan.width == 1 else "%s_rec.%s" % (tag, fields[j])
 
         def xread(o: I.Op, idx: str) -> str:
             if o.mode == I.MODE_SCALAR:
                 self._sacc(o.base)
                 return "sx_%d" % o.base
             if o.mode == I.MODE_ELEM:
-                if aligned:
-                    return "x[r]"
-                return "c.xs[%d + %s]" % (o.base, idx)
+                return "x[r]" if shape == "aligned" else "c.xs[%d + %s]" % (o.base, idx)
+            if o.dst in gather_names:
+                return gather_names[o.dst] + "v"
             return "c.xs[%d + A.datai[c_blob(%d) + %s]]" % (o.base, op0 + o.dst, idx)
 
-        # adjoint bookkeeping -------------------------------------------------
-        # uniform registers accumulate lane-partial adjoints across the element loop
-        def is_u(reg: int) -> bool:
-            return uniform[reg]
+        def dread(o: I.Op, idx: str) -> str:
+            if o.dst in rec_field:
+                return rec_field[o.dst]
+            return "A.dataf[c_blob(%d) + %s]" % (op0 + o.dst, idx if o.mode == I.MODE_ELEM else "0")
 
-        # 1. prologue: uniform forward ops
-        for o in ops:
-            if o.uniform:
-                E("const real %s = %s;" % (tg.v(o.dst), tg.fwd(o, "0", xread)), 3)
-        u_need_adj = [False] * len(ops)
-
-        # registers needing adjoints: reachable from value/params
-        roots = [t.value_reg] + [p for p in t.param_regs if p >= 0]
-
-        # lpdf partial wiring
-        n_par = I.TERM_NPARAMS[kind]
-        preg = list(t.param_regs[:n_par])
-        scale_reg = None
-        if kind in (I.TERM_KINDS["normal"],):
-            scale_reg = preg[1]
-        elif kind in (I.TERM_KINDS["halfnormal"], I.TERM_KINDS["halfcauchy"]):
-            scale_reg = preg[0]
-        scale_uniform = scale_reg is not None and is_u(scale_reg)
-        if scale_uniform:
-            E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
-              % (tag, tg.v(scale_reg), tag, tg.v(scale_reg)), 3)
-        # accumulators for uniform registers (declared lazily)
-        uacc_declared: Dict[int, bool] = {}
-
-        def uacc(reg: int) -> str:
-            if reg not in uacc_declared:
-                uacc_declared[reg] = True
-            return "%s_ua%d" % (tag, reg)
-
-        # we need to know which uniform regs receive adjoints before emitting the loop, so
-        # generate the loop body into a buffer first
-        saved = self.lines
-        loop: List[str] = []
-        self.lines = loop
-
-        idx = "i"
-        for o in ops:
-            if not o.uniform:
-                E("const real %s = %s;" % (tg.v(o.dst), tg.fwd(o, idx, xread)), 4)
-        # lpdf
-        val = tg.v(t.value_reg)
-        adj_terms: Dict[int, List[str]] = {}
-
-        def add_adj(reg: int, expr: str):
-            adj_terms.setdefault(reg, []).append(expr)
-
-        if kind == I.TERM_KINDS["potential"]:
-            E("lp += %s;" % val, 4)
-            add_adj(t.value_reg, "(real)1")
-        else:
-            E("real %s_dx, %s_d0, %s_d1; (void)%s_dx; (void)%s_d0; (void)%s_d1;" % ((tag,) * 6), 4)
-            if scale_reg is not None and not scale_uniform:
-                E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
-                  % (tag, tg.v(scale_reg), tag, tg.v(scale_reg)), 4)
-            if kind == I.TERM_KINDS["normal"]:
-                E("lp += pm4::normal_lpdf<real>(%s, %s, %s_inv_s, %s_log_s, %s_dx, %s_d0, %s_d1);"
-                  % (val, tg.v(preg[0]), tag, tag, tag, tag, tag), 4)
-                add_adj(preg[0], "%s_d0" % tag)
-                add_adj(preg[1], "%s_d1" % tag)
-            elif kind == I.TERM_KINDS["halfnormal"]:
-                E("lp += pm4::halfnormal_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0);"
-                  % (val, tag, tag, tag, tag), 4)
-                add_adj(preg[0], "%s_d0" % tag)
-            elif kind == I.TERM_KINDS["halfcauchy"]:
-                E("lp += pm4::halfcauchy_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0);"
-                  % (val, tag, tag, tag, tag), 4)
-                add_adj(preg[0], "%s_d0" % tag)
-            elif kind == I.TERM_KINDS["bernoulli"]:
-                E("lp += pm4::bernoulli_lpdf<real>(%s, %s, %s_dx, %s_d0);" % (val, tg.v(preg[0]), tag, tag), 4)
-                add_adj(preg[0], "%s_d0" % tag)
-            elif kind == I.TERM_KINDS["poisson"]:
-                E("lp += pm4::poisson_lpdf<real>(%s, %s, %s_dx, %s_d0);" % (val, tg.v(preg[0]), tag, tag), 4)
-                add_adj(preg[0], "%s_d0" % tag)
-            else:  # pragma: no cover
-                raise NotImplementedError(kind)
-            add_adj(t.value_reg, "%s_dx" % tag)
-
-        # which registers depend on a free variable at all (others need no adjoint)
+        # registers that depend on a free variable (the others need no adjoint)
         depends = [False] * len(ops)
         for o in ops:
             nm = I.OP_NAME[o.opcode]
@@ -279,53 +244,102 @@ class _ModuleGen:
             elif nm not in ("ld_const", "ld_data"):
                 depends[o.dst] = depends[o.a] or (o.b >= 0 and depends[o.b])
 
-        def leaf_adj(o: I.Op, g: str, ind: int):
-            """adjoint g arrives at a load of x."""
-            if o.mode == I.MODE_SCALAR:
-                E("%s += %s;" % (self._sacc(o.base), g), ind)
+        # 1. prologue: element-independent forward ops
+        for o in ops:
+            if o.uniform:
+                E("const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "0", xread, dread)), 3)
+        if scale_uniform:
+            E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
+              % (tag, tp.v(scale_reg), tag, tp.v(scale_reg)), 3)
+        if normal_fast:
+            E("const real %s = %s_inv_s * %s_inv_s; real %s_S2 = 0;" % (K, tag, tag, tag), 3)
+
+        # 2. the element body, generated into a buffer (we need to know which uniform registers
+        #    receive adjoints before the loop header is written)
+        uacc: Dict[int, bool] = {}
+        saved, loop = self.lines, []
+        self.lines = loop
+        idx = "i"
+        for o in ops:
+            if not o.uniform:
+                E("const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, idx, xread, dread)), 5)
+        val = tp.v(t.value_reg)
+        adj: Dict[int, List[str]] = {}
+
+        def add_adj(reg: int, expr: str):
+            if reg >= 0 and depends[reg]:
+                adj.setdefault(reg, []).append(expr)
+
+        if kind == I.TERM_KINDS["potential"]:
+            E("lp += %s;" % val, 5)
+            add_adj(t.value_reg, "(real)1")
+        elif normal_fast:
+            E("const real %s_r = %s - %s;" % (tag, val, tp.v(preg[0])), 5)
+            E("%s_S2 += %s_r * %s_r;" % (tag, tag, tag), 5)
+            add_adj(preg[0], "%s_r" % tag)
+            add_adj(t.value_reg, "-%s_r" % tag)
+        else:
+            E("real %s_dx, %s_d0, %s_d1; (void)%s_dx; (void)%s_d0; (void)%s_d1;" % ((tag,) * 6), 5)
+            if scale_reg is not None and not scale_uniform:
+                E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
+                  % (tag, tp.v(scale_reg), tag, tp.v(scale_reg)), 5)
+            call = {
+                "normal": "normal_lpdf<real>(%s, %s, %s_inv_s, %s_log_s, %s_dx, %s_d0, %s_d1)"
+                          % (val, tp.v(preg[0]) if n_par else "", tag, tag, tag, tag, tag),
+                "halfnormal": "halfnormal_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
+                "halfcauchy": "halfcauchy_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
+                "bernoulli": "bernoulli_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, tp.v(preg[0]) if n_par else "", tag, tag),
+                "poisson": "poisson_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, tp.v(preg[0]) if n_par else "", tag, tag),
+            }[_KIND[kind]]
+            E("lp += pm4::%s;" % call, 5)
+            add_adj(preg[0], "%s_d0" % tag)
+            if kind == I.TERM_KINDS["normal"]:
+                add_adj(preg[1], "%s_d1" % tag)
+            add_adj(t.value_reg, "%s_dx" % tag)
+
+        def leaf_adj(o: I.Op, g: str):
+            if o.mode == I.MODE_SCALAR:  # only reachable for non-uniform... never: scalar loads are uniform
+                E("%s += %s;" % (self._sacc(o.base), sink(g)), 5)
             elif o.mode == I.MODE_ELEM:
-                if aligned:
-                    E("gr[r] += %s;" % g, ind)
+                if shape == "aligned":
+                    E("gr[r] += %s;" % sink(g), 5)
                 else:
-                    E("c.gx[%d + %s] += %s;" % (o.base, idx, g), ind)
+                    E("c.gx[%d + %s] += %s;" % (o.base, idx, sink(g)), 5)
                     touched_gx[0] = True
+            elif o.dst in gather_names:
+                E("%sa += %s;" % (gather_names[o.dst], g), 5)  # scaled by K in the group pass
             else:
-                E("atomicAdd(&c.gx[%d + A.datai[c_blob(%d) + %s]], %s);" % (o.base, op0 + o.dst, idx, g), ind)
+                E("atomicAdd(&c.gx[%d + A.datai[c_blob(%d) + %s]], %s);" % (o.base, op0 + o.dst, idx, sink(g)), 5)
                 touched_gx[0] = True
 
-        # 2. reverse sweep over non-uniform ops (inside the loop); adjoints that reach a
-        #    uniform register are accumulated for the epilogue
         for o in reversed(ops):
-            if o.dst not in adj_terms or not depends[o.dst]:
+            if o.dst not in adj:
                 continue
-            terms_ = adj_terms.pop(o.dst)
+            terms_ = adj.pop(o.dst)
             if o.uniform:
-                E("%s += %s;" % (uacc(o.dst), " + ".join(terms_)), 4)
-                u_need_adj[o.dst] = True
+                uacc[o.dst] = True
+                E("%s_ua%d += %s;" % (tag, o.dst, " + ".join(terms_)), 5)
                 continue
             g = "%s_a%d" % (tag, o.dst)
-            E("const real %s = %s;" % (g, " + ".join(terms_)), 4)
-            nm = I.OP_NAME[o.opcode]
-            if nm == "ld_x":
-                leaf_adj(o, g, 4)
+            E("const real %s = %s;" % (g, " + ".join(terms_)), 5)
+            if o.opcode == ld_x:
+                leaf_adj(o, g)
             else:
-                for reg, expr in tg.bwd(o, g):
-                    if reg >= 0 and depends[reg]:
-                        add_adj(reg, expr)
+                for reg, expr in tp.bwd(o, g):
+                    add_adj(reg, expr)
         self.lines = saved
 
-        # declare uniform accumulators
-        for reg in sorted(uacc_declared):
+        for reg in sorted(uacc):
             E("real %s_ua%d = 0;" % (tag, reg), 3)
 
-        # 3. emit the loop in the right shape
-        if all_uniform and t.n == 1:
+        # 3. the loop itself
+        n_expr = str(t.n)
+        if shape == "uniform":
             E("if (lane == 0) {", 3)
-            E("const int i = 0; (void)i;", 4)
-            body_ind = loop
-            self.lines.extend(body_ind)
+            E("const int i = 0; (void)i;", 5)
+            self.lines.extend(loop)
             E("}", 3)
-        elif aligned:
+        elif shape == "aligned":
             base = elem_bases[0]
             r_lo, r_hi = base // 32, (base + t.n - 1) // 32
             E("#pragma unroll", 3)
@@ -335,25 +349,86 @@ class _ModuleGen:
             self.lines.extend(loop)
             E("}", 4)
             E("}", 3)
+        elif shape == "planned":
+            n_expr = "n_%s" % tag
+            E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
+            rec_t = "typename pm4::Rec<real, %d>::type" % plan.width
+            E("const int32_t* %s_pm = c.pi + __ldg(A.plan_off + %d);" % (tag, 2 * plan_idx), 3)
+            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d));"
+              % (rec_t, tag, rec_t, 2 * plan_idx + 1), 3)
+            E("const int %s_ns = %s_pm[0], %s_G = %s_pm[1], %s_nslot = %s_pm[2];" % ((tag,) * 6), 3)
+            for nm, slot_ in (("ml", 4), ("rb", 5), ("ct", 6), ("cl", 7), ("gt", 8), ("gp", 9), ("gs", 10)):
+                E("const int32_t* %s_%s = %s_pm + %s_pm[%d];" % (tag, nm, tag, tag, slot_), 3)
+            E("for (int s = 0; s < %s_ns; ++s) {" % tag, 3)
+            E("const int slot = s * 32 + lane;", 4)
+            E("const int tgt = %s_ct[slot], len = %s_cl[slot], ml = %s_ml[s];" % (tag, tag, tag), 4)
+            by_dst = {o.dst: o for o in ops}
+            for dst, nm in gather_names.items():
+                E("const real %sv = c.xs[%d + (tgt < 0 ? 0 : tgt)]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
+            E("const %s* rp = %s_pr + (size_t)%s_rb[s] * 32 + lane;" % (rec_t, tag, tag), 4)
+            E("#pragma unroll 2", 4)
+            E("for (int i = 0; i < ml; ++i) {", 4)
+            E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
+            E("if (i < len) {", 5)
+            self.lines.extend(loop)
+            E("}", 5)
+            E("}", 4)
+            for j, (dst, nm) in enumerate(gather_names.items()):
+                E("c.part[%d * %s_nslot + slot] = %sa;" % (j, tag, nm), 4)
+            E("}", 3)
+            E("__syncwarp();", 3)
+            # group pass: combine the chunk partial sums of every gather target in a fixed order
+            E("for (int g = lane; g < %s_G; g += 32) {" % tag, 3)
+            E("real %s;" % ", ".join("gs%d = 0" % j for j in range(len(gather_names))), 4)
+            E("for (int q = %s_gp[g]; q < %s_gp[g + 1]; ++q) {" % (tag, tag), 4)
+            E("const int sl = %s_gs[q];" % tag, 5)
+            for j in range(len(gather_names)):
+                E("gs%d += c.part[%d * %s_nslot + sl];" % (j, j, tag), 5)
+            E("}", 4)
+            E("const int tg = %s_gt[g];" % tag, 4)
+            for j, (dst, nm) in enumerate(gather_names.items()):
+                E("c.gx[%d + tg] += %s;" % (by_dst[dst].base, sink("gs%d" % j)), 4)
+            E("}", 3)
+            touched_gx[0] = True
         else:
-            E("const int n_%s = __ldg(A.term_n + %d);" % (tag, k), 3)
-            E("for (int i = lane; i < n_%s; i += 32) {" % tag, 3)
+            n_expr = "n_%s" % tag
+            E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
+            E("for (int i = lane; i < %s; i += 32) {" % n_expr, 3)
             self.lines.extend(loop)
             E("}", 3)
 
-        # 4. epilogue: reverse sweep over the uniform ops with lane-partial adjoints
-        u_adj: Dict[int, List[str]] = {reg: ["%s_ua%d" % (tag, reg)] for reg in uacc_declared}
+        # 4. factored Normal: the sums enter the log-density and the scale adjoint once
+        if normal_fast:
+            E("lp += (real)-0.5 * %s * %s_S2;" % (K, tag), 3)
+            E("if (lane == 0) lp -= (real)%s * (pm4::K<real>::HALF_LOG_2PI + %s_log_s);" % (n_expr, tag), 3)
+            if depends[scale_reg]:
+                uacc.setdefault(scale_reg, False)
+                decl = "" if uacc[scale_reg] else "real "
+                # d/d scale = sum (w^2 - 1) / scale = K * S2 / scale - n / scale
+                E("%s%s_ua%d %s %s * %s_S2 * %s_inv_s - (lane == 0 ? (real)%s * %s_inv_s : (real)0);"
+                  % (decl, tag, scale_reg, "+=" if uacc[scale_reg] else "=", K, tag, tag, n_expr, tag), 3)
+                uacc[scale_reg] = True
+
+        # 5. epilogue: reverse sweep over the element-independent ops with lane-partial adjoints
+        u_adj: Dict[int, List[str]] = {}
+        for reg in uacc:
+            # adjoints that flowed out of the loop carry the deferred factor, the scale adjoint does not
+            if normal_fast and reg != scale_reg:
+                u_adj[reg] = ["%s * %s_ua%d" % (K, tag, reg)]
+            elif normal_fast and reg == scale_reg:
+                u_adj[reg] = ["%s_ua%d" % (tag, reg)]
+            else:
+                u_adj[reg] = ["%s_ua%d" % (tag, reg)]
         for o in reversed(ops):
             if not o.uniform or o.dst not in u_adj or not depends[o.dst]:
                 continue
             terms_ = u_adj.pop(o.dst)
             g = "%s_ub%d" % (tag, o.dst)
             E("const real %s = %s;" % (g, " + ".join(terms_)), 3)
-            nm = I.OP_NAME[o.opcode]
-            if nm == "ld_x":
+            if o.opcode == ld_x:
                 E("%s += %s;" % (self._sacc(o.base), g), 3)
             else:
-                for reg, expr in tg.bwd(o, g):
+                for reg, expr in tp.bwd(o, g):
                     if reg >= 0 and depends[reg]:
                         u_adj.setdefault(reg, []).append(expr)
         if touched_gx[0]:
@@ -376,7 +451,7 @@ class _ModuleGen:
                 out.append("    %s xv[j] = th[j];" % rng)
         op0 = sum(len(t.ops) for t in self.ir.terms)
         for k, d in enumerate(self.ir.dets):
-            tg = _TermGen(self, d.ops, op0, "d%d" % k)
+            tp = _Tape(d.ops, op0, "d%d" % k)
 
             def xread(o: I.Op, idx: str, _op0=op0) -> str:
                 if o.mode == I.MODE_SCALAR:
@@ -385,11 +460,14 @@ class _ModuleGen:
                     return "xv[%d + %s]" % (o.base, idx)
                 return "xv[%d + A.datai[c_blob(%d) + %s]]" % (o.base, _op0 + o.dst, idx)
 
+            def dread(o: I.Op, idx: str, _op0=op0) -> str:
+                return "A.dataf[c_blob(%d) + %s]" % (_op0 + o.dst, idx if o.mode == I.MODE_ELEM else "0")
+
             out.append("    // ---- output %d: %s" % (k, d.name))
             out.append("    for (int i = 0; i < %d; ++i) {" % d.n)
             for o in d.ops:
-                out.append("      const real %s = %s;" % (tg.v(o.dst), tg.fwd(o, "i", xread)))
-            out.append("      out[%d + i] = %s;" % (d.out_offset, tg.v(d.value_reg)))
+                out.append("      const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "i", xread, dread)))
+            out.append("      out[%d + i] = %s;" % (d.out_offset, tp.v(d.value_reg)))
             out.append("    }")
             op0 += len(d.ops)
         out.append("  }")
@@ -403,22 +481,17 @@ class _ModuleGen:
         parts = [
             "// generated by pymc4_b200/codegen.py -- do not edit.  IR structure hash %s" % ir.struct_hash_hex,
             "// free variables: " + ", ".join("%s[%d]@%d" % (rv.name, rv.size, rv.offset) for rv in ir.rvs),
-            '#include "pm4_dists.cuh"',
-            '#include "pm4_philox.cuh"',
-            '#include "pm4_module.h"',
-            "#include <cuda_runtime.h>",
-            "namespace pm4 { template <typename real> struct Ctx; template <typename real> struct ModelArgs;",
-            "template <typename real> __device__ __forceinline__ real warp_sum(real v); }",
-            "#define PM4_MODEL %s" % name,
-            "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),
+            '#include "pm4_common.cuh"',
             "struct %s {" % name,
-            "  static constexpr int D = %d, R = %d, DP = %d, DET_ROW = %d, N_TERMS = %d, N_OPS = %d;"
-            % (self.D, self.R, 32 * self.R, ir.det_row, len(ir.terms), n_ops),
+            "  static constexpr int D = %d, R = %d, DP = %d, DET_ROW = %d, N_TERMS = %d, N_OPS = %d, N_PLANS = %d;"
+            % (self.D, self.R, 32 * self.R, ir.det_row, len(ir.terms), n_ops, len(ir.plans)),
             "  static constexpr unsigned long long HASH = 0x%sull;" % ir.struct_hash_hex,
             self.gen_constrain(),
             terms_src,
             self.gen_dets(),
             "};",
+            "#define PM4_MODEL %s" % name,
+            "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),
             '#include "pm4_kernels.cuh"',
             "",
         ]
@@ -445,11 +518,11 @@ def _csrc_mtime() -> float:
                if f.endswith((".cuh", ".h")))
 
 
-def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verbose: bool = False) -> str:
+def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verbose: bool = False,
+                 extra_flags: Optional[List[str]] = None) -> str:
     """Return the path of the compiled module for this IR structure, building it if needed."""
     path = module_path(ir, has_f64)
-    # a module with double precision also serves float requests
-    alt = module_path(ir, True)
+    alt = module_path(ir, True)  # a module with double precision also serves float requests
     with _build_lock:
         for cand in (path, alt):
             if not force and os.path.exists(cand) and os.path.getmtime(cand) >= _csrc_mtime():
@@ -459,7 +532,7 @@ def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verb
         with open(src_path, "w") as f:
             f.write(generate_source(ir, has_f64))
         tmp = tempfile.NamedTemporaryFile(prefix="pm4m_", suffix=".so", dir=CACHE_DIR, delete=False).name
-        cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", CSRC, "-shared", "-o", tmp, src_path]
+        cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags or []) + ["-I", CSRC, "-shared", "-o", tmp, src_path]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

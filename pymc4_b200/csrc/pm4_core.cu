@@ -67,6 +67,12 @@ struct pm4_model {
   float* d_f32 = nullptr;
   double* d_f64 = nullptr;
   int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
+  // execution plans (pymc4_b200/plan.py)
+  int n_plans = 0, part_reals = 0;
+  int64_t n_planf = 0, n_plani = 0;
+  float* d_pf32 = nullptr;
+  double* d_pf64 = nullptr;
+  int32_t *d_plani = nullptr, *d_plan_off = nullptr;
 
   pm4_mod_args_t args(int dtype) const {
     pm4_mod_args_t a;
@@ -74,9 +80,43 @@ struct pm4_model {
     a.datai = d_datai;
     a.term_n = d_term_n;
     a.op_blob = d_op_blob;
+    a.planf = dtype == PM4_F64 ? (const void*)d_pf64 : (const void*)d_pf32;
+    a.plani = d_plani;
+    a.plan_off = d_plan_off;
+    a.n_planf = (int32_t)n_planf;
+    a.n_plani = (int32_t)n_plani;
+    a.part_reals = part_reals;
+    // stage the plan pools in shared memory when they leave room for the per-chain state
+    const size_t pool_bytes = (size_t)n_planf * (dtype == PM4_F64 ? 8 : 4) + (size_t)n_plani * 4;
+    a.stage = (n_plans > 0 && pool_bytes <= 96 * 1024) ? 1 : 0;
     return a;
   }
 };
+
+static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
+  const int64_t nf = ir->n_planf, ni = ir->n_plani;
+  if (nf % 4 || ni % 4) return fail(PM4_EINVAL, "plan pools must be padded to multiples of 4 elements");
+  std::vector<float> f32((size_t)nf);
+  for (int64_t k = 0; k < nf; ++k) f32[(size_t)k] = (float)ir->planf[k];
+  if (nf) {
+    CU(cudaMemcpy(m->d_pf32, f32.data(), sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_pf64, ir->planf, sizeof(double) * (size_t)nf, cudaMemcpyHostToDevice));
+  }
+  if (ni) CU(cudaMemcpy(m->d_plani, ir->plani, sizeof(int32_t) * (size_t)ni, cudaMemcpyHostToDevice));
+  std::vector<int32_t> off((size_t)(2 * ir->n_plans) + 2);
+  int part = 0;
+  for (int k = 0; k < ir->n_plans; ++k) {
+    const pm4_plan_t& pl = ir->plans[k];
+    if (pl.meta < 0 || pl.meta >= ni || pl.recs < 0 || pl.recs > nf) return fail(PM4_EINVAL, "plan %d points outside the plan pools", k);
+    off[(size_t)(2 * k)] = (int32_t)pl.meta;
+    off[(size_t)(2 * k + 1)] = (int32_t)pl.recs;
+    const int need = pl.n_gather * pl.n_slices * 32;
+    if (need > part) part = need;
+  }
+  CU(cudaMemcpy(m->d_plan_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
+  m->part_reals = part;
+  return PM4_OK;
+}
 
 static int upload_pools(pm4_model* m, const double* dataf, int64_t nf, const int32_t* datai, int64_t ni) {
   m->dataf.assign(dataf, dataf + nf);
@@ -157,6 +197,13 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
     CU(cudaMalloc(&m->d_op_blob, sizeof(int32_t) * op_blob.size()));
     CU(cudaMemcpy(m->d_term_n, term_n.data(), sizeof(int32_t) * term_n.size(), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(m->d_op_blob, op_blob.data(), sizeof(int32_t) * op_blob.size(), cudaMemcpyHostToDevice));
+    m->n_plans = ir->n_plans; m->n_planf = ir->n_planf; m->n_plani = ir->n_plani;
+    CU(cudaMalloc(&m->d_pf32, sizeof(float) * (size_t)(ir->n_planf + 4)));
+    CU(cudaMalloc(&m->d_pf64, sizeof(double) * (size_t)(ir->n_planf + 4)));
+    CU(cudaMalloc(&m->d_plani, sizeof(int32_t) * (size_t)(ir->n_plani + 4)));
+    CU(cudaMalloc(&m->d_plan_off, sizeof(int32_t) * (size_t)(2 * ir->n_plans + 2)));
+    int rcp = upload_plans(m, ir);
+    if (rcp != PM4_OK) return rcp;
     return upload_pools(m, ir->dataf, ir->n_dataf, ir->datai, ir->n_datai);
   };
   int rc = alloc();
@@ -173,6 +220,7 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
 extern "C" int pm4_model_destroy(pm4_model_t* m) {
   if (!m) return PM4_OK;
   cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_datai); cudaFree(m->d_term_n); cudaFree(m->d_op_blob);
+  cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
   if (m->module) dlclose(m->module);
   delete m;
   return PM4_OK;
@@ -188,6 +236,15 @@ extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n
   CU(cudaSetDevice(m->device));
   CU(cudaDeviceSynchronize());
   return upload_pools(m, dataf, n_dataf, datai, n_datai);
+}
+
+extern "C" int pm4_model_set_plans(pm4_model_t* m, const pm4_ir_t* ir) {
+  if (!m || !ir) return fail(PM4_EINVAL, "null argument");
+  if (ir->n_plans != m->n_plans || ir->n_planf != m->n_planf || ir->n_plani != m->n_plani)
+    return fail(PM4_EINVAL, "plan pool sizes differ from the model's");
+  CU(cudaSetDevice(m->device));
+  CU(cudaDeviceSynchronize());
+  return upload_plans(m, ir);
 }
 
 static int check_dtype(const pm4_model* m, int dtype) {

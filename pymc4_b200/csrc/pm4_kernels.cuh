@@ -3,7 +3,8 @@
 // trajectory momentum sums) is spread over the 32 lanes, lane l holding elements l, l+32, ...
 // in registers (M::R per vector).  Reductions over dimensions / observations are xor-butterfly
 // warp shuffles, so every lane sees bit-identical sums and all sampler decisions are
-// warp-uniform.
+// warp-uniform.  Observed-data records and execution plans of gather terms are copied once per
+// CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).
 //
 // What this replaces in the reference: the body of tfp.mcmc.sample_chain that
 // _BaseSampler._run_chains hands control to (/root/reference/pymc4/mcmc/samplers.py:172-189):
@@ -12,36 +13,80 @@
 // (samplers.py:117-119).  Algorithm restated in SURVEY App. A; the CPU restatement is
 // oracle/pm4_oracle_impl.h.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include "pm4_dists.cuh"
-#include "pm4_module.h"
-#include "pm4_philox.cuh"
+#include "pm4_common.cuh"
 
 namespace pm4 {
 
-constexpr unsigned FULL = 0xffffffffu;
+// ------------------------------------------------------------------------------------------
+// shared-memory layout of one CTA:
+//   [0, 16)                  mbarrier of the bulk copy
+//   [16, 16 + pool bytes)    plan records (reals) then plan metadata (ints), when staged
+//   then per warp            xs[DP] | gx[DP] | part[part_reals]
+// ------------------------------------------------------------------------------------------
+template <typename real> __host__ __device__ inline size_t pool_bytes(const ModelArgs<real>& A) {
+  return A.stage ? 16 + (size_t)A.n_planf * sizeof(real) + (size_t)A.n_plani * sizeof(int32_t) : 0;
+}
+template <typename real> __host__ __device__ inline size_t warp_reals(const ModelArgs<real>& A, int DP) {
+  return 2 * (size_t)DP + (((size_t)A.part_reals + 3) & ~(size_t)3);
+}
+template <typename real> __host__ inline size_t cta_smem_bytes(const ModelArgs<real>& A, int DP, int wpb) {
+  return pool_bytes(A) + (size_t)wpb * warp_reals(A, DP) * sizeof(real);
+}
 
-template <typename real> struct ModelArgs {
-  const real* __restrict__ dataf;
-  const int32_t* __restrict__ datai;
-  const int32_t* __restrict__ term_n;
-  const int32_t* __restrict__ op_blob;
-};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// per-warp evaluation context handed to the generated model code
-template <typename real> struct Ctx {
-  int lane;
-  real* xs;  // shared memory [DP]: constrained values of this chain (gather source)
-  real* gx;  // shared memory [DP]: adjoint scatter target of this chain
-  ModelArgs<real> A;
-};
-
-template <typename real> __device__ __forceinline__ real warp_sum(real v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
+// Build the per-warp context; when STAGED, thread 0 issues the TMA bulk copies of the plan pools
+// and every thread of the CTA waits on the mbarrier.  Must be called by ALL threads of the CTA.
+template <typename real, bool STAGED>
+__device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned char* smem_raw, int DP) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Ctx<real> c;
+  c.lane = lane;
+  c.A = A;
+  size_t base = 0;
+  if (STAGED) {
+    const uint32_t fbytes = (uint32_t)A.n_planf * (uint32_t)sizeof(real), ibytes = (uint32_t)A.n_plani * 4u;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    unsigned char* sf = smem_raw + 16;
+    unsigned char* si = sf + fbytes;
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(fbytes + ibytes) : "memory");
+      const unsigned char* gf = reinterpret_cast<const unsigned char*>(A.planf);
+      const unsigned char* gi = reinterpret_cast<const unsigned char*>(A.plani);
+      for (uint32_t off = 0; off < fbytes; off += 32768u) {
+        const uint32_t nb = fbytes - off < 32768u ? fbytes - off : 32768u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sf + off)), "l"(gf + off), "r"(nb), "r"(bar) : "memory");
+      }
+      for (uint32_t off = 0; off < ibytes; off += 32768u) {
+        const uint32_t nb = ibytes - off < 32768u ? ibytes - off : 32768u;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(si + off)), "l"(gi + off), "r"(nb), "r"(bar) : "memory");
+      }
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+    c.pf = reinterpret_cast<const real*>(sf);
+    c.pi = reinterpret_cast<const int32_t*>(si);
+    base = 16 + (size_t)fbytes + ibytes;
+  } else {
+    c.pf = A.planf;
+    c.pi = A.plani;
+  }
+  real* w = reinterpret_cast<real*>(smem_raw + base) + (size_t)warp * warp_reals(A, DP);
+  c.xs = w;
+  c.gx = w + DP;
+  c.part = w + 2 * DP;
+  return c;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -76,16 +121,15 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
 // ------------------------------------------------------------------------------------------
 // parity kernel (a): log-density and gradient for C independent states
 // ------------------------------------------------------------------------------------------
-template <class M, typename real>
+template <class M, typename real, bool STAGED>
 __global__ void __launch_bounds__(128) logp_grad_kernel(ModelArgs<real> A, int C, const real* __restrict__ theta,
                                                         real* __restrict__ lp_out, real* __restrict__ grad_out) {
   constexpr int R = M::R, D = M::D, DP = M::DP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* smem = reinterpret_cast<real*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
+  Ctx<real> c = make_ctx<real, STAGED>(A, smem_raw, DP);
+  const int lane = c.lane;
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (chain >= C) return;
-  Ctx<real> c{lane, smem + (size_t)warp * 2 * DP, smem + (size_t)warp * 2 * DP + DP, A};
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -143,7 +187,7 @@ template <typename real> struct RunParams {
 
 template <typename real> __host__ inline RunParams<real> make_run_params(const pm4_mod_run_t& r) {
   RunParams<real> p;
-  p.A = ModelArgs<real>{(const real*)r.A.dataf, r.A.datai, r.A.term_n, r.A.op_blob};
+  p.A = make_model_args<real>(r.A);
   p.C = r.C; p.t_begin = r.t_begin; p.t_count = r.t_count; p.B = r.B; p.S = r.S;
   p.max_depth = r.max_depth; p.num_leapfrog = r.num_leapfrog; p.chain_offset = r.chain_offset;
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
@@ -204,16 +248,20 @@ __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int 
   }
 }
 
+template <typename real> __global__ void export_eps_kernel(RunParams<real> a, real* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.C) out[c] = a.da[a.adapt_pooled ? 0 : (size_t)c * 4];
+}
+
 // initial log-density / gradient of every chain (tfp bootstrap_results) + dual-averaging init
-template <class M, typename real>
+template <class M, typename real, bool STAGED>
 __global__ void __launch_bounds__(128) init_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
   constexpr int R = M::R, D = M::D, DP = M::DP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* smem = reinterpret_cast<real*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
+  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
+  const int lane = c.lane;
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (chain >= a.C) return;
-  Ctx<real> c{lane, smem + (size_t)warp * 2 * DP, smem + (size_t)warp * 2 * DP + DP, a.A};
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -250,7 +298,8 @@ __device__ __forceinline__ void draw_momentum(const RunParams<real>& a, int chai
   }
 #pragma unroll
   for (int q = 0; q < (R + 3) / 4; ++q) {
-    const U4 u = philox4x32_10((uint32_t)(a.chain_offset + chain),(uint32_t)t, (uint32_t)(q * 32 + lane), RNG_MOMENTUM, a.seed_lo, a.seed_hi);
+    const U4 u = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, (uint32_t)(q * 32 + lane),
+                               RNG_MOMENTUM, a.seed_lo, a.seed_hi);
     real n[4];
     box_muller<real>(u.x, u.y, n[0], n[1]);
     box_muller<real>(u.z, u.w, n[2], n[3]);
@@ -263,7 +312,7 @@ __device__ __forceinline__ void draw_momentum(const RunParams<real>& a, int chai
 }
 
 // one leapfrog step: tfp SimpleLeapfrogIntegrator with num_steps = 1:
-// half kick, drift, gradient, full kick, half un-kick.  es[r] = signed eps * per-dim scale.
+// half kick, drift, gradient, full kick, half un-kick.  es[r] = eps * per-dim scale, sgn = +-1.
 template <class M, typename real>
 __device__ __forceinline__ real leapfrog(real (&th)[M::R], real (&p)[M::R], real (&g)[M::R],
                                          const real (&es)[M::R], real sgn, Ctx<real>& c) {
@@ -290,21 +339,25 @@ template <int R, typename real> __device__ __forceinline__ real dot(const real (
   return warp_sum(s);
 }
 
+// tree scratch lives in global memory (L2-resident: every access is one coalesced line per register)
+template <typename real> __device__ __forceinline__ real ldq(const real* p) { return __ldcg(p); }
+template <typename real> __device__ __forceinline__ void stq(real* p, real v) { __stcg(p, v); }
+
 // ------------------------------------------------------------------------------------------
 // NUTS: tfp NoUTurnSampler.one_step -> _loop_tree_doubling -> _build_sub_tree ->
 // _loop_build_sub_tree in per-chain form, t_count transitions per launch.
 // ------------------------------------------------------------------------------------------
-template <class M, typename real, int MAXT>
+template <class M, typename real, int MAXT, bool STAGED>
 __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
   constexpr int R = M::R, D = M::D, DP = M::DP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* smem = reinterpret_cast<real*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
+  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
+  const int lane = c.lane;
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (chain >= a.C) return;
-  Ctx<real> c{lane, smem + (size_t)warp * 2 * DP, smem + (size_t)warp * 2 * DP + DP, a.A};
   const real NEG_INF = -m_inf<real>();
   const size_t C = (size_t)a.C;
+  const uint32_t rng_chain = (uint32_t)(a.chain_offset + chain);
   auto slot = [&](int s) -> real* { return a.scratch + ((size_t)s * C + chain) * DP + lane; };
   const int MEM_P = PM4_SLOT_MEM, MEM_RHO = PM4_SLOT_MEM + a.max_depth + 1;
 
@@ -330,18 +383,18 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
     const real H0 = clp - (real)0.5 * dot<R, real>(p, p);
 
     // merge uniforms (one per doubling, lane d holds depth d) and the direction bits
-    const U4 um = philox4x32_10((uint32_t)(a.chain_offset + chain),(uint32_t)t, (uint32_t)lane, RNG_MERGE, a.seed_lo, a.seed_hi);
-    const U4 ud = philox4x32_10((uint32_t)(a.chain_offset + chain),(uint32_t)t, 0u, RNG_DIRECTION, a.seed_lo, a.seed_hi);
+    const U4 um = philox4x32_10(rng_chain, (uint32_t)t, (uint32_t)lane, RNG_MERGE, a.seed_lo, a.seed_hi);
+    const U4 ud = philox4x32_10(rng_chain, (uint32_t)t, 0u, RNG_DIRECTION, a.seed_lo, a.seed_hi);
 
     // both trajectory ends and the candidate start at the current point
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       th[r] = cth[r]; g[r] = cg[r]; rho[r] = p[r];
-      slot(PM4_SLOT_OTH_TH)[32 * r] = cth[r];
-      slot(PM4_SLOT_OTH_P)[32 * r] = p[r];
-      slot(PM4_SLOT_OTH_G)[32 * r] = cg[r];
-      slot(PM4_SLOT_CAND_TH)[32 * r] = cth[r];
-      slot(PM4_SLOT_CAND_G)[32 * r] = cg[r];
+      stq(slot(PM4_SLOT_OTH_TH) + 32 * r, cth[r]);
+      stq(slot(PM4_SLOT_OTH_P) + 32 * r, p[r]);
+      stq(slot(PM4_SLOT_OTH_G) + 32 * r, cg[r]);
+      stq(slot(PM4_SLOT_CAND_TH) + 32 * r, cth[r]);
+      stq(slot(PM4_SLOT_CAND_G) + 32 * r, cg[r]);
     }
     real cur_lp = clp, oth_lp = clp;
     int cur_is_right = 1;
@@ -355,9 +408,9 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           real v;
-          v = slot(PM4_SLOT_OTH_TH)[32 * r]; slot(PM4_SLOT_OTH_TH)[32 * r] = th[r]; th[r] = v;
-          v = slot(PM4_SLOT_OTH_P)[32 * r]; slot(PM4_SLOT_OTH_P)[32 * r] = p[r]; p[r] = v;
-          v = slot(PM4_SLOT_OTH_G)[32 * r]; slot(PM4_SLOT_OTH_G)[32 * r] = g[r]; g[r] = v;
+          v = ldq(slot(PM4_SLOT_OTH_TH) + 32 * r); stq(slot(PM4_SLOT_OTH_TH) + 32 * r, th[r]); th[r] = v;
+          v = ldq(slot(PM4_SLOT_OTH_P) + 32 * r); stq(slot(PM4_SLOT_OTH_P) + 32 * r, p[r]); p[r] = v;
+          v = ldq(slot(PM4_SLOT_OTH_G) + 32 * r); stq(slot(PM4_SLOT_OTH_G) + 32 * r, g[r]); g[r] = v;
         }
         const real tl = cur_lp; cur_lp = oth_lp; oth_lp = tl;
         cur_is_right = dir;
@@ -374,7 +427,7 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
       for (int i = 0; i < nsteps && cont_sub; ++i) {
         // leaf uniforms: two leaves share a Philox block, lane l holds pair-block (base + l)
         if ((i & 63) == 0)
-          ul = philox4x32_10((uint32_t)(a.chain_offset + chain),(uint32_t)t, ((uint32_t)depth << 20) | (uint32_t)((i >> 1) + lane),
+          ul = philox4x32_10(rng_chain, (uint32_t)t, ((uint32_t)depth << 20) | (uint32_t)((i >> 1) + lane),
                              RNG_LEAF, a.seed_lo, a.seed_hi);
         cur_lp = leapfrog<M, real>(th, p, g, es, sgn, c);
         sub_leaps += 1;
@@ -383,15 +436,14 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
         if (i & 1) {
           // U-turn checks against checkpoints [popcount(i) - trailing_ones(i), popcount(i))
           const int pc = __popc((unsigned)i), t1 = __ffs(~(unsigned)i) - 1;
-          real now[R];
 #pragma unroll
-          for (int r = 0; r < R; ++r) now[r] = rho_sub[r] + p[r];
+          for (int r = 0; r < R; ++r) rho_sub[r] += p[r];
           for (int s = pc - t1; s < pc && no_uturn; ++s) {
             real d1 = 0, d2 = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              const real mp = slot(MEM_P + s)[32 * r];
-              const real df = now[r] - slot(MEM_RHO + s)[32 * r];
+              const real mp = ldq(slot(MEM_P + s) + 32 * r);
+              const real df = rho_sub[r] - ldq(slot(MEM_RHO + s) + 32 * r);
               d1 += df * mp;
               d2 += df * p[r];
             }
@@ -399,15 +451,13 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
             d2 = warp_sum(d2);
             no_uturn = (d1 > 0) && (d2 > 0);
           }
-#pragma unroll
-          for (int r = 0; r < R; ++r) rho_sub[r] = now[r];
         } else {
           // even leaves are checkpointed into slot popcount(i): (p_i, rho before this leaf)
           const int s = __popc((unsigned)i);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            slot(MEM_P + s)[32 * r] = p[r];
-            slot(MEM_RHO + s)[32 * r] = rho_sub[r];
+            stq(slot(MEM_P + s) + 32 * r, p[r]);
+            stq(slot(MEM_RHO + s) + 32 * r, rho_sub[r]);
             rho_sub[r] += p[r];
           }
         }
@@ -425,8 +475,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
         if (u <= thresh) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            slot(PM4_SLOT_SUB_TH)[32 * r] = th[r];
-            slot(PM4_SLOT_SUB_G)[32 * r] = g[r];
+            stq(slot(PM4_SLOT_SUB_TH) + 32 * r, th[r]);
+            stq(slot(PM4_SLOT_SUB_G) + 32 * r, g[r]);
           }
           sub_lp = cur_lp;
           sub_energy = energy;
@@ -447,8 +497,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
       if ((umerge <= thresh) && cont_sub) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          slot(PM4_SLOT_CAND_TH)[32 * r] = slot(PM4_SLOT_SUB_TH)[32 * r];
-          slot(PM4_SLOT_CAND_G)[32 * r] = slot(PM4_SLOT_SUB_G)[32 * r];
+          stq(slot(PM4_SLOT_CAND_TH) + 32 * r, ldq(slot(PM4_SLOT_SUB_TH) + 32 * r));
+          stq(slot(PM4_SLOT_CAND_G) + 32 * r, ldq(slot(PM4_SLOT_SUB_G) + 32 * r));
         }
         cand_lp = sub_lp;
         cand_energy = sub_energy;
@@ -459,7 +509,7 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
       for (int r = 0; r < R; ++r) {
         rho[r] += rho_sub[r];
         d_cur += rho[r] * p[r];
-        d_oth += rho[r] * slot(PM4_SLOT_OTH_P)[32 * r];
+        d_oth += rho[r] * ldq(slot(PM4_SLOT_OTH_P) + 32 * r);
       }
       d_cur = warp_sum(d_cur);
       d_oth = warp_sum(d_oth);
@@ -470,8 +520,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
     // the transition's result is the candidate
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      cth[r] = slot(PM4_SLOT_CAND_TH)[32 * r];
-      cg[r] = slot(PM4_SLOT_CAND_G)[32 * r];
+      cth[r] = ldq(slot(PM4_SLOT_CAND_TH) + 32 * r);
+      cg[r] = ldq(slot(PM4_SLOT_CAND_G) + 32 * r);
     }
     clp = cand_lp;
     total_leaps += nleap;
@@ -486,7 +536,7 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const int j = lane + 32 * r;
-          if (j < D) a.states[k * D + j] = cth[r];
+          if (j < D) __stcs(a.states + k * D + j, cth[r]);
         }
       }
       if (lane == 0) {
@@ -516,15 +566,14 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 // ------------------------------------------------------------------------------------------
 // fixed-L HMC: tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC)
 // ------------------------------------------------------------------------------------------
-template <class M, typename real, int MAXT>
+template <class M, typename real, int MAXT, bool STAGED>
 __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
   constexpr int R = M::R, D = M::D, DP = M::DP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  real* smem = reinterpret_cast<real*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + warp;
+  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
+  const int lane = c.lane;
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (chain >= a.C) return;
-  Ctx<real> c{lane, smem + (size_t)warp * 2 * DP, smem + (size_t)warp * 2 * DP + DP, a.A};
   const size_t C = (size_t)a.C;
   real cth[R], cg[R], scale[R];
   real clp = a.lp[chain];
@@ -563,7 +612,7 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
     real u;
     if (a.uniforms) u = a.uniforms[(size_t)t * C + chain];
     else {
-      const U4 uu = philox4x32_10((uint32_t)(a.chain_offset + chain),(uint32_t)t, 0u, RNG_HMC, a.seed_lo, a.seed_hi);
+      const U4 uu = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, 0u, RNG_HMC, a.seed_lo, a.seed_hi);
       u = u01<real>(uu.x, uu.y);
     }
     const bool ok = m_log(u) < lar;
@@ -616,9 +665,12 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
 // ------------------------------------------------------------------------------------------
 #define PM4_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
-template <class M, typename real, int MAXT, class Kernel>
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+template <class M, typename real, class Kernel>
 inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, int wpb, cudaStream_t st) {
-  const size_t smem = (size_t)wpb * 2 * M::DP * sizeof(real);
+  const size_t smem = cta_smem_bytes(p.A, M::DP, wpb);
+  if (smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
   PM4_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (p.C + wpb - 1) / wpb;
   kernel<<<grid, wpb * 32, smem, st>>>(p);
@@ -627,24 +679,30 @@ inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, int wpb,
 
 // warps per block -> the smallest compiled launch bound that fits (more registers per thread)
 template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_mod_run_t& r, int wpb, cudaStream_t st) {
-  const RunParams<real> p = make_run_params<real>(r);
-  if (wpb <= 0) {  // library default: fill the 148 SMs with one block each, up to 28 warps per block
+  RunParams<real> p = make_run_params<real>(r);
+  if (wpb <= 0) {  // library default: one block per SM, up to 28 warps (= 28 chains) per block
     const int per_sm = (r.C + 147) / 148;
-    wpb = per_sm <= 8 ? 8 : (per_sm <= 16 ? 16 : (per_sm <= 28 ? 28 : 32));
+    wpb = per_sm <= 8 ? 8 : 28;
   }
-  if (wpb > 32) wpb = 32;
+  if (wpb > 28) wpb = 28;
   if (sizeof(real) == 8 && wpb > 8) wpb = 8;  // double precision is only instantiated for 256 threads
-#define PM4_LAUNCH(T) \
-  return NUTS ? launch_chain_kernel<M, real, T>(nuts_kernel<M, real, T>, p, wpb, st) \
-              : launch_chain_kernel<M, real, T>(hmc_kernel<M, real, T>, p, wpb, st)
-  if (wpb <= 8) { PM4_LAUNCH(256); }
-  if constexpr (sizeof(real) == 4) {
-    if (wpb <= 16) { PM4_LAUNCH(512); }
-    if (wpb <= 28) { PM4_LAUNCH(896); }
-    PM4_LAUNCH(1024);
+  // shrink the block until the per-chain state (and the staged pools) fit in shared memory
+  while (wpb > 1 && cta_smem_bytes(p.A, M::DP, wpb) > SMEM_LIMIT) {
+    if (p.A.stage && pool_bytes(p.A) > SMEM_LIMIT / 2) p.A.stage = 0;
+    else wpb -= 1;
   }
+#define PM4_LAUNCH(T)                                                                                       \
+  do {                                                                                                      \
+    if (p.A.stage)                                                                                          \
+      return NUTS ? launch_chain_kernel<M, real>(nuts_kernel<M, real, T, true>, p, wpb, st)                 \
+                  : launch_chain_kernel<M, real>(hmc_kernel<M, real, T, true>, p, wpb, st);                 \
+    return NUTS ? launch_chain_kernel<M, real>(nuts_kernel<M, real, T, false>, p, wpb, st)                  \
+                : launch_chain_kernel<M, real>(hmc_kernel<M, real, T, false>, p, wpb, st);                  \
+  } while (0)
+  if (wpb <= 8) PM4_LAUNCH(256);
+  if constexpr (sizeof(real) == 4) PM4_LAUNCH(896);
 #undef PM4_LAUNCH
-  return -1;
+  return (int)cudaErrorInvalidConfiguration;
 }
 
 }  // namespace pm4
@@ -674,28 +732,42 @@ namespace pm4 {
 template <typename real>
 int mod_logp_grad(const pm4_mod_args_t* A, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
   using M = PM4_MODEL;
-  ModelArgs<real> ma{(const real*)A->dataf, A->datai, A->term_n, A->op_blob};
+  ModelArgs<real> ma = make_model_args<real>(*A);
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * 2 * M::DP * sizeof(real);
-  PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  logp_grad_kernel<M, real><<<(C + wpb - 1) / wpb, wpb * 32, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+  if (cta_smem_bytes(ma, M::DP, wpb) > SMEM_LIMIT) ma.stage = 0;
+  const size_t smem = cta_smem_bytes(ma, M::DP, wpb);
+  const unsigned grid = (unsigned)((C + wpb - 1) / wpb);
+  if (ma.stage) {
+    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    logp_grad_kernel<M, real, true><<<grid, wpb * 32, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+  } else {
+    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    logp_grad_kernel<M, real, false><<<grid, wpb * 32, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+  }
   return (int)cudaGetLastError();
 }
 template <typename real>
 int mod_dets(const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, cudaStream_t st) {
   using M = PM4_MODEL;
   if (M::DET_ROW == 0 || n == 0) return 0;
-  ModelArgs<real> ma{(const real*)A->dataf, A->datai, A->term_n, A->op_blob};
+  ModelArgs<real> ma = make_model_args<real>(*A);
   dets_kernel<M, real><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ma, n, (const real*)theta, (real*)out);
   return (int)cudaGetLastError();
 }
 template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0, double eps0, cudaStream_t st) {
   using M = PM4_MODEL;
-  const RunParams<real> p = make_run_params<real>(*r);
+  RunParams<real> p = make_run_params<real>(*r);
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * 2 * M::DP * sizeof(real);
-  PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  init_kernel<M, real><<<(r->C + wpb - 1) / wpb, wpb * 32, smem, st>>>(p, (const real*)theta0, (real)eps0);
+  if (cta_smem_bytes(p.A, M::DP, wpb) > SMEM_LIMIT) p.A.stage = 0;
+  const size_t smem = cta_smem_bytes(p.A, M::DP, wpb);
+  const unsigned grid = (unsigned)((r->C + wpb - 1) / wpb);
+  if (p.A.stage) {
+    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    init_kernel<M, real, true><<<grid, wpb * 32, smem, st>>>(p, (const real*)theta0, (real)eps0);
+  } else {
+    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    init_kernel<M, real, false><<<grid, wpb * 32, smem, st>>>(p, (const real*)theta0, (real)eps0);
+  }
   return (int)cudaGetLastError();
 }
 }  // namespace pm4
@@ -737,12 +809,6 @@ extern "C" int pm4m_da_pooled(int dtype, const pm4_mod_run_t* r, int t, void* st
   if (dtype == 1) { pm4::da_pooled_kernel<double><<<1, 1024, 0, (cudaStream_t)stream>>>(pm4::make_run_params<double>(*r), t); return (int)cudaGetLastError(); }
   return -22;
 }
-namespace pm4 {
-template <typename real> __global__ void export_eps_kernel(RunParams<real> a, real* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < a.C) out[c] = a.da[a.adapt_pooled ? 0 : (size_t)c * 4];
-}
-}  // namespace pm4
 extern "C" int pm4m_export_eps(int dtype, const pm4_mod_run_t* r, void* out, void* stream) {
   const unsigned grid = (unsigned)((r->C + 255) / 256);
   if (dtype == 0) { pm4::export_eps_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(pm4::make_run_params<float>(*r), (float*)out); return (int)cudaGetLastError(); }

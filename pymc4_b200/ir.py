@@ -91,10 +91,41 @@ class Term:
     value_reg: int
     param_regs: List[int]
     label: str = ""
+    plan: Optional["Plan"] = None
 
     @property
     def n_regs(self) -> int:
         return max([o.dst for o in self.ops] + [-1]) + 1
+
+
+@dataclass
+class Plan:
+    """Device execution plan of a term whose parameters gather from free variables.
+
+    The term's elements are regrouped by gather target ("group"), groups are cut into chunks of
+    at most ``chunk_cap`` elements, chunks are sorted by length and dealt 32 at a time to the lanes
+    of the chain's warp (sliced-ELL).  Within a slice every lane walks one chunk, so the gathered
+    values sit in registers and their adjoints accumulate in registers -- no scatter, no atomics,
+    a fixed summation order.  Per-chunk partial sums are combined per group afterwards.
+
+    Structure (goes into the struct hash): which ops are planned gathers / record fields.
+    Data (run-time pools): everything below.
+    """
+    term: int
+    index_blob: int                 # datai offset of the primary index array
+    gather_ops: List[int]           # op dst of GATHER loads sharing the primary index
+    record_ops: List[int]           # op dst of ELEM data loads, in record order
+    width: int                      # reals per record (1, 2 or 4)
+    n_slices: int = 0
+    n_groups: int = 0
+    n_chunks: int = 0
+    meta_off: int = 0               # offset into plani
+    recs_off: int = 0               # offset into planf (reals)
+    chunk_cap: int = 0
+
+    @property
+    def part_reals(self) -> int:
+        return len(self.gather_ops) * self.n_slices * 32
 
 
 @dataclass
@@ -120,6 +151,12 @@ class ModelIR:
     dataf: np.ndarray
     datai: np.ndarray
     observed: Dict[str, np.ndarray] = field(default_factory=dict)
+    planf: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    plani: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+
+    @property
+    def plans(self) -> List["Plan"]:
+        return [t.plan for t in self.terms if t.plan is not None]
 
     @property
     def det_row(self) -> int:
@@ -143,6 +180,9 @@ class ModelIR:
             h.append(struct.pack("<iii", t.kind, t.value_reg, len(t.ops)))
             h.append(struct.pack("<%di" % len(t.param_regs), *t.param_regs))
             ops_key(t.ops, t.n)
+            if t.plan is not None:
+                pl = t.plan
+                h.append(b"plan" + struct.pack("<i", pl.width) + bytes(pl.gather_ops) + b"|" + bytes(pl.record_ops))
         for d in self.dets:
             h.append(struct.pack("<iii", d.value_reg, len(d.ops), d.n))
             ops_key(d.ops, d.n)
@@ -432,6 +472,9 @@ def lower_model(model: Model, observed: Optional[dict] = None, state=None) -> Tu
     observed_np = {k: sym.as_numpy(v) for k, v in st.observed_values.items()}
     ir = ModelIR(D=D, rvs=list(rvs.values()), terms=terms, dets=dets, dataf=dataf, datai=datai,
                  observed=observed_np)
+    from .plan import attach_plans
+
+    attach_plans(ir)
     return ir, init_state, deterministic_names
 
 
@@ -446,7 +489,12 @@ class CRV(ctypes.Structure):
 class CTerm(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("n", ctypes.c_int32), ("op_begin", ctypes.c_int32),
                 ("op_end", ctypes.c_int32), ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32),
-                ("param_reg", ctypes.c_int32 * 3), ("flags", ctypes.c_int32)]
+                ("param_reg", ctypes.c_int32 * 3), ("plan", ctypes.c_int32)]
+
+
+class CPlan(ctypes.Structure):
+    _fields_ = [("term", ctypes.c_int32), ("n_gather", ctypes.c_int32), ("n_slices", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("meta", ctypes.c_int64), ("recs", ctypes.c_int64)]
 
 
 class COp(ctypes.Structure):
@@ -468,7 +516,10 @@ class CIR(ctypes.Structure):
                 ("ops", ctypes.POINTER(COp)), ("dets", ctypes.POINTER(CDet)),
                 ("n_dataf", ctypes.c_int64), ("dataf", ctypes.POINTER(ctypes.c_double)),
                 ("n_datai", ctypes.c_int64), ("datai", ctypes.POINTER(ctypes.c_int32)),
-                ("struct_hash", ctypes.c_uint64)]
+                ("struct_hash", ctypes.c_uint64),
+                ("n_plans", ctypes.c_int32), ("_pad2", ctypes.c_int32), ("plans", ctypes.POINTER(CPlan)),
+                ("n_planf", ctypes.c_int64), ("planf", ctypes.POINTER(ctypes.c_double)),
+                ("n_plani", ctypes.c_int64), ("plani", ctypes.POINTER(ctypes.c_int32))]
 
 
 class PackedIR:
@@ -477,13 +528,18 @@ class PackedIR:
     def __init__(self, ir: ModelIR):
         self.ir = ir
         all_ops: List[Op] = []
+        plans: List[Plan] = []
         cterms = (CTerm * max(len(ir.terms), 1))()
         for k, t in enumerate(ir.terms):
             begin = len(all_ops)
             all_ops.extend(t.ops)
             pr = list(t.param_regs) + [-1] * (3 - len(t.param_regs))
+            plan_idx = -1
+            if t.plan is not None:
+                plan_idx = len(plans)
+                plans.append(t.plan)
             cterms[k] = CTerm(t.kind, t.n, begin, len(all_ops), t.n_regs, t.value_reg,
-                              (ctypes.c_int32 * 3)(*pr), 0)
+                              (ctypes.c_int32 * 3)(*pr), plan_idx)
         cdets = (CDet * max(len(ir.dets), 1))()
         for k, d in enumerate(ir.dets):
             begin = len(all_ops)
@@ -497,7 +553,12 @@ class PackedIR:
             crvs[k] = CRV(rv.offset, rv.size, rv.transform, 0, rv.shift, rv.scale)
         self._dataf = np.ascontiguousarray(ir.dataf, dtype=np.float64)
         self._datai = np.ascontiguousarray(ir.datai, dtype=np.int32)
-        self._keep = (cterms, cdets, cops, crvs)
+        cplans = (CPlan * max(len(plans), 1))()
+        for k, pl in enumerate(plans):
+            cplans[k] = CPlan(pl.term, len(pl.gather_ops), pl.n_slices, pl.width, pl.meta_off, pl.recs_off)
+        self._planf = np.ascontiguousarray(ir.planf, dtype=np.float64)
+        self._plani = np.ascontiguousarray(ir.plani, dtype=np.int32)
+        self._keep = (cterms, cdets, cops, crvs, cplans)
         self.c = CIR(
             ABI_VERSION, ir.D, len(ir.rvs), len(ir.terms), len(all_ops), len(ir.dets), ir.det_row, 0,
             ctypes.cast(crvs, ctypes.POINTER(CRV)), ctypes.cast(cterms, ctypes.POINTER(CTerm)),
@@ -505,6 +566,9 @@ class PackedIR:
             self._dataf.size, self._dataf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             self._datai.size, self._datai.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
             ir.struct_hash,
+            len(plans), 0, ctypes.cast(cplans, ctypes.POINTER(CPlan)),
+            self._planf.size, self._planf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+            self._plani.size, self._plani.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
         )
 
     def byref(self):
