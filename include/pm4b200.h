@@ -91,7 +91,7 @@ typedef struct pm4_term {
 typedef struct pm4_plan {
   int32_t term;       /* the term it belongs to                        */
   int32_t n_gather;   /* gather loads sharing the plan's index array   */
-  int32_t n_slices;   /* slices of 32 chunk slots                      */
+  int32_t n_part;     /* per-chain scratch reals per gather load       */
   int32_t width;      /* reals per record: 1, 2 or 4                   */
   int64_t meta;       /* offset of the plan metadata in plani          */
   int64_t recs;       /* offset of the records in planf (in reals)     */

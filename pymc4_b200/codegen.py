@@ -255,79 +255,92 @@ class _ModuleGen:
             E("const real %s = %s_inv_s * %s_inv_s; real %s_S2 = 0;" % (K, tag, tag, tag), 3)
 
         # 2. the element body, generated into a buffer (we need to know which uniform registers
-        #    receive adjoints before the loop header is written)
+        #    receive adjoints before the loop header is written).  With `mask` set, the body is
+        #    branch-free: it is evaluated for a padded row too and its contributions are zeroed.
         uacc: Dict[int, bool] = {}
-        saved, loop = self.lines, []
-        self.lines = loop
         idx = "i"
-        for o in ops:
-            if not o.uniform:
-                E("const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, idx, xread, dread)), 5)
         val = tp.v(t.value_reg)
-        adj: Dict[int, List[str]] = {}
 
-        def add_adj(reg: int, expr: str):
-            if reg >= 0 and depends[reg]:
-                adj.setdefault(reg, []).append(expr)
+        def gen_body(mask: Optional[str]) -> List[str]:
+            saved, loop = self.lines, []
+            self.lines = loop
 
-        if kind == I.TERM_KINDS["potential"]:
-            E("lp += %s;" % val, 5)
-            add_adj(t.value_reg, "(real)1")
-        elif normal_fast:
-            E("const real %s_r = %s - %s;" % (tag, val, tp.v(preg[0])), 5)
-            E("%s_S2 += %s_r * %s_r;" % (tag, tag, tag), 5)
-            add_adj(preg[0], "%s_r" % tag)
-            add_adj(t.value_reg, "-%s_r" % tag)
-        else:
-            E("real %s_dx, %s_d0, %s_d1; (void)%s_dx; (void)%s_d0; (void)%s_d1;" % ((tag,) * 6), 5)
-            if scale_reg is not None and not scale_uniform:
-                E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
-                  % (tag, tp.v(scale_reg), tag, tp.v(scale_reg)), 5)
-            call = {
-                "normal": "normal_lpdf<real>(%s, %s, %s_inv_s, %s_log_s, %s_dx, %s_d0, %s_d1)"
-                          % (val, tp.v(preg[0]) if n_par else "", tag, tag, tag, tag, tag),
-                "halfnormal": "halfnormal_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
-                "halfcauchy": "halfcauchy_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
-                "bernoulli": "bernoulli_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, tp.v(preg[0]) if n_par else "", tag, tag),
-                "poisson": "poisson_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, tp.v(preg[0]) if n_par else "", tag, tag),
-            }[_KIND[kind]]
-            E("lp += pm4::%s;" % call, 5)
-            add_adj(preg[0], "%s_d0" % tag)
-            if kind == I.TERM_KINDS["normal"]:
-                add_adj(preg[1], "%s_d1" % tag)
-            add_adj(t.value_reg, "%s_dx" % tag)
+            def m(expr: str) -> str:
+                return "(%s ? %s : (real)0)" % (mask, expr) if mask else expr
 
-        def leaf_adj(o: I.Op, g: str):
-            if o.mode == I.MODE_SCALAR:  # only reachable for non-uniform... never: scalar loads are uniform
-                E("%s += %s;" % (self._sacc(o.base), sink(g)), 5)
-            elif o.mode == I.MODE_ELEM:
-                if shape == "aligned":
-                    E("gr[r] += %s;" % sink(g), 5)
+            for o in ops:
+                if not o.uniform:
+                    E("const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, idx, xread, dread)), 5)
+            adj: Dict[int, List[str]] = {}
+
+            def add_adj(reg: int, expr: str):
+                if reg >= 0 and depends[reg]:
+                    adj.setdefault(reg, []).append(expr)
+
+            if kind == I.TERM_KINDS["potential"]:
+                E("lp += %s;" % m(val), 5)
+                add_adj(t.value_reg, m("(real)1"))
+            elif normal_fast:
+                E("const real %s_r = %s;" % (tag, m("%s - %s" % (val, tp.v(preg[0])))), 5)
+                E("%s_S2 += %s_r * %s_r;" % (tag, tag, tag), 5)
+                add_adj(preg[0], "%s_r" % tag)
+                add_adj(t.value_reg, "-%s_r" % tag)
+            else:
+                E("real %s_dx, %s_d0, %s_d1; (void)%s_dx; (void)%s_d0; (void)%s_d1;" % ((tag,) * 6), 5)
+                if scale_reg is not None and not scale_uniform:
+                    E("const real %s_inv_s = pm4::m_rcp(%s); const real %s_log_s = pm4::m_log(%s);"
+                      % (tag, tp.v(scale_reg), tag, tp.v(scale_reg)), 5)
+                p0 = tp.v(preg[0]) if n_par else ""
+                call = {
+                    "normal": "normal_lpdf<real>(%s, %s, %s_inv_s, %s_log_s, %s_dx, %s_d0, %s_d1)"
+                              % (val, p0, tag, tag, tag, tag, tag),
+                    "halfnormal": "halfnormal_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
+                    "halfcauchy": "halfcauchy_lpdf<real>(%s, %s_inv_s, %s_log_s, %s_dx, %s_d0)" % (val, tag, tag, tag, tag),
+                    "bernoulli": "bernoulli_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, p0, tag, tag),
+                    "poisson": "poisson_lpdf<real>(%s, %s, %s_dx, %s_d0)" % (val, p0, tag, tag),
+                }[_KIND[kind]]
+                E("const real %s_lp = pm4::%s;" % (tag, call), 5)
+                E("lp += %s;" % m("%s_lp" % tag), 5)
+                add_adj(preg[0], m("%s_d0" % tag))
+                if kind == I.TERM_KINDS["normal"]:
+                    add_adj(preg[1], m("%s_d1" % tag))
+                add_adj(t.value_reg, m("%s_dx" % tag))
+
+            def leaf_adj(o: I.Op, g: str):
+                if o.mode == I.MODE_SCALAR:  # scalar loads are element-independent: handled via uacc
+                    E("%s += %s;" % (self._sacc(o.base), sink(g)), 5)
+                elif o.mode == I.MODE_ELEM:
+                    if shape == "aligned":
+                        E("gr[r] += %s;" % sink(g), 5)
+                    else:
+                        E("c.gx[%d + %s] += %s;" % (o.base, idx, sink(g)), 5)
+                        touched_gx[0] = True
+                elif o.dst in gather_names:
+                    E("%sa += %s;" % (gather_names[o.dst], g), 5)  # scaled by K when flushed
                 else:
-                    E("c.gx[%d + %s] += %s;" % (o.base, idx, sink(g)), 5)
+                    E("atomicAdd(&c.gx[%d + A.datai[c_blob(%d) + %s]], %s);" % (o.base, op0 + o.dst, idx, sink(g)), 5)
                     touched_gx[0] = True
-            elif o.dst in gather_names:
-                E("%sa += %s;" % (gather_names[o.dst], g), 5)  # scaled by K in the group pass
-            else:
-                E("atomicAdd(&c.gx[%d + A.datai[c_blob(%d) + %s]], %s);" % (o.base, op0 + o.dst, idx, sink(g)), 5)
-                touched_gx[0] = True
 
-        for o in reversed(ops):
-            if o.dst not in adj:
-                continue
-            terms_ = adj.pop(o.dst)
-            if o.uniform:
-                uacc[o.dst] = True
-                E("%s_ua%d += %s;" % (tag, o.dst, " + ".join(terms_)), 5)
-                continue
-            g = "%s_a%d" % (tag, o.dst)
-            E("const real %s = %s;" % (g, " + ".join(terms_)), 5)
-            if o.opcode == ld_x:
-                leaf_adj(o, g)
-            else:
-                for reg, expr in tp.bwd(o, g):
-                    add_adj(reg, expr)
-        self.lines = saved
+            for o in reversed(ops):
+                if o.dst not in adj:
+                    continue
+                terms_ = adj.pop(o.dst)
+                if o.uniform:
+                    uacc[o.dst] = True
+                    E("%s_ua%d += %s;" % (tag, o.dst, " + ".join(terms_)), 5)
+                    continue
+                g = "%s_a%d" % (tag, o.dst)
+                E("const real %s = %s;" % (g, " + ".join(terms_)), 5)
+                if o.opcode == ld_x:
+                    leaf_adj(o, g)
+                else:
+                    for reg, expr in tp.bwd(o, g):
+                        add_adj(reg, expr)
+            self.lines = saved
+            return loop
+
+        loop = gen_body(None)
+        loop_masked = gen_body("on") if shape == "planned" else []
 
         for reg in sorted(uacc):
             E("real %s_ua%d = 0;" % (tag, reg), 3)
@@ -351,43 +364,57 @@ class _ModuleGen:
             E("}", 3)
         elif shape == "planned":
             n_expr = "n_%s" % tag
-            E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
-            rec_t = "typename pm4::Rec<real, %d>::type" % plan.width
-            E("const int32_t* %s_pm = c.pi + __ldg(A.plan_off + %d);" % (tag, 2 * plan_idx), 3)
-            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d));"
-              % (rec_t, tag, rec_t, 2 * plan_idx + 1), 3)
-            E("const int %s_ns = %s_pm[0], %s_G = %s_pm[1], %s_nslot = %s_pm[2];" % ((tag,) * 6), 3)
-            for nm, slot_ in (("ml", 4), ("rb", 5), ("ct", 6), ("cl", 7), ("gt", 8), ("gp", 9), ("gs", 10)):
-                E("const int32_t* %s_%s = %s_pm + %s_pm[%d];" % (tag, nm, tag, tag, slot_), 3)
-            E("for (int s = 0; s < %s_ns; ++s) {" % tag, 3)
-            E("const int slot = s * 32 + lane;", 4)
-            E("const int tgt = %s_ct[slot], len = %s_cl[slot], ml = %s_ml[s];" % (tag, tag, tag), 4)
             by_dst = {o.dst: o for o in ops}
+            rec_t = "typename pm4::Rec<real, %d>::type" % plan.width
+            E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
+            E("const int32_t* %s_pm = c.pi + __ldg(A.plan_off + %d);" % (tag, 2 * plan_idx), 3)
+            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d)) + lane;"
+              % (rec_t, tag, rec_t, 2 * plan_idx + 1), 3)
+            E("const int4 %s_h0 = *reinterpret_cast<const int4*>(%s_pm);      // n_slices, n_split, n_part, o_slices" % (tag, tag), 3)
+            E("const int4 %s_h1 = *reinterpret_cast<const int4*>(%s_pm + 4);  // o_slots, o_split" % (tag, tag), 3)
+            E("const int4* %s_sl = reinterpret_cast<const int4*>(%s_pm + %s_h0.w);" % (tag, tag, tag), 3)
+            E("const int4* %s_st = reinterpret_cast<const int4*>(%s_pm + %s_h1.x) + lane;" % (tag, tag, tag), 3)
+            E("for (int s = 0; s < %s_h0.x; ++s) {" % tag, 3)
+            E("const int4 sl = %s_sl[s];        // rows all lanes walk, rows in the slice, first record row" % tag, 4)
+            E("const int4 st = %s_st[s * 32];   // gather target, chunk length, scratch index" % tag, 4)
+            E("const int tgt = st.x < 0 ? 0 : st.x, len = st.y;", 4)
             for dst, nm in gather_names.items():
-                E("const real %sv = c.xs[%d + (tgt < 0 ? 0 : tgt)]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
-            E("const %s* rp = %s_pr + (size_t)%s_rb[s] * 32 + lane;" % (rec_t, tag, tag), 4)
-            E("#pragma unroll 2", 4)
-            E("for (int i = 0; i < ml; ++i) {", 4)
+                E("const real %sv = c.xs[%d + tgt]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
+            E("const %s* rp = %s_pr + sl.z * 32;" % (rec_t, tag), 4)
+            E("int i = 0;", 4)
+            E("#pragma unroll 4", 4)
+            E("for (; i < sl.x; ++i) {", 4)
             E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
-            E("if (i < len) {", 5)
             self.lines.extend(loop)
+            E("}", 4)
+            E("for (; i < sl.y; ++i) {", 4)
+            E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
+            E("const bool on = i < len;", 5)
+            self.lines.extend(loop_masked)
+            E("}", 4)
+            E("if (st.x >= 0) {", 4)
+            E("if (st.z < 0) {  // the chunk is a whole group: this lane owns its gradient entries", 5)
+            for dst, nm in gather_names.items():
+                E("c.gx[%d + st.x] += %s;" % (by_dst[dst].base, sink("%sa" % nm)), 6)
+            E("} else {        // chunk of a split group: park the partial sums", 5)
+            for j, (dst, nm) in enumerate(gather_names.items()):
+                E("c.part[%d * %s_h0.z + st.z] = %sa;" % (j, tag, nm), 6)
             E("}", 5)
             E("}", 4)
-            for j, (dst, nm) in enumerate(gather_names.items()):
-                E("c.part[%d * %s_nslot + slot] = %sa;" % (j, tag, nm), 4)
             E("}", 3)
             E("__syncwarp();", 3)
-            # group pass: combine the chunk partial sums of every gather target in a fixed order
-            E("for (int g = lane; g < %s_G; g += 32) {" % tag, 3)
-            E("real %s;" % ", ".join("gs%d = 0" % j for j in range(len(gather_names))), 4)
-            E("for (int q = %s_gp[g]; q < %s_gp[g + 1]; ++q) {" % (tag, tag), 4)
-            E("const int sl = %s_gs[q];" % tag, 5)
+            E("{  // split groups: combine their chunks in a fixed order", 3)
+            E("const int4* %s_sg = reinterpret_cast<const int4*>(%s_pm + %s_h1.y);" % (tag, tag, tag), 4)
+            E("for (int q = lane; q < %s_h0.y; q += 32) {" % tag, 4)
+            E("const int4 sg = %s_sg[q];  // gather target, first scratch index, chunks" % tag, 5)
+            E("real %s;" % ", ".join("gs%d = 0" % j for j in range(len(gather_names))), 5)
+            E("for (int k2 = 0; k2 < sg.z; ++k2) {", 5)
             for j in range(len(gather_names)):
-                E("gs%d += c.part[%d * %s_nslot + sl];" % (j, j, tag), 5)
-            E("}", 4)
-            E("const int tg = %s_gt[g];" % tag, 4)
+                E("gs%d += c.part[%d * %s_h0.z + sg.y + k2];" % (j, j, tag), 6)
+            E("}", 5)
             for j, (dst, nm) in enumerate(gather_names.items()):
-                E("c.gx[%d + tg] += %s;" % (by_dst[dst].base, sink("gs%d" % j)), 4)
+                E("c.gx[%d + sg.x] += %s;" % (by_dst[dst].base, sink("gs%d" % j)), 5)
+            E("}", 4)
             E("}", 3)
             touched_gx[0] = True
         else:
@@ -502,8 +529,32 @@ def generate_source(ir: I.ModelIR, has_f64: bool = False) -> str:
     return _ModuleGen(ir, has_f64).source()
 
 
+_gen_hash_cache: Optional[str] = None
+
+
+def generator_hash() -> str:
+    """Content hash of everything a built module depends on besides the model structure: the
+    device headers and the generator (a module built by an older generator may read execution
+    plans in an older layout).  Part of the module file name, so stale modules are never loaded
+    and file modification times (which do not survive a copy to the GPU box) play no role."""
+    global _gen_hash_cache
+    if _gen_hash_cache is None:
+        import hashlib
+
+        h = hashlib.sha256()
+        deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+        deps += [os.path.join(_HERE, f) for f in ("codegen.py", "plan.py", "ir.py")]
+        for d in deps:
+            with open(d, "rb") as f:
+                h.update(f.read())
+        h.update(" ".join(NVCC_FLAGS).encode())
+        _gen_hash_cache = h.hexdigest()[:8]
+    return _gen_hash_cache
+
+
 def module_path(ir: I.ModelIR, has_f64: bool = False) -> str:
-    return os.path.join(CACHE_DIR, "pm4m_%s%s.so" % (ir.struct_hash_hex, "_f64" if has_f64 else ""))
+    return os.path.join(CACHE_DIR, "pm4m_%s_%s%s.so" % (ir.struct_hash_hex, generator_hash(),
+                                                        "_f64" if has_f64 else ""))
 
 
 def find_nvcc() -> str:
@@ -514,8 +565,11 @@ def find_nvcc() -> str:
 
 
 def _csrc_mtime() -> float:
-    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)
-               if f.endswith((".cuh", ".h")))
+    """Newest modification time of anything a built module depends on (device headers and the
+    generator itself: a module built by an older generator may read plans in an older layout)."""
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps += [os.path.join(_HERE, f) for f in ("codegen.py", "plan.py", "ir.py")]
+    return max(os.path.getmtime(d) for d in deps)
 
 
 def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verbose: bool = False,
@@ -525,10 +579,10 @@ def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verb
     alt = module_path(ir, True)  # a module with double precision also serves float requests
     with _build_lock:
         for cand in (path, alt):
-            if not force and os.path.exists(cand) and os.path.getmtime(cand) >= _csrc_mtime():
+            if not force and os.path.exists(cand):
                 return cand
         os.makedirs(CACHE_DIR, exist_ok=True)
-        src_path = os.path.join(CACHE_DIR, "pm4m_%s%s.cu" % (ir.struct_hash_hex, "_f64" if has_f64 else ""))
+        src_path = path[:-3] + ".cu"
         with open(src_path, "w") as f:
             f.write(generate_source(ir, has_f64))
         tmp = tempfile.NamedTemporaryFile(prefix="pm4m_", suffix=".so", dir=CACHE_DIR, delete=False).name

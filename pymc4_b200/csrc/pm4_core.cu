@@ -110,7 +110,7 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
     if (pl.meta < 0 || pl.meta >= ni || pl.recs < 0 || pl.recs > nf) return fail(PM4_EINVAL, "plan %d points outside the plan pools", k);
     off[(size_t)(2 * k)] = (int32_t)pl.meta;
     off[(size_t)(2 * k + 1)] = (int32_t)pl.recs;
-    const int need = pl.n_gather * pl.n_slices * 32;
+    const int need = pl.n_gather * pl.n_part;
     if (need > part) part = need;
   }
   CU(cudaMemcpy(m->d_plan_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));

@@ -122,10 +122,11 @@ class Plan:
     meta_off: int = 0               # offset into plani
     recs_off: int = 0               # offset into planf (reals)
     chunk_cap: int = 0
+    n_part: int = 1                 # scratch reals per gather op (chunks of split groups)
 
     @property
     def part_reals(self) -> int:
-        return len(self.gather_ops) * self.n_slices * 32
+        return len(self.gather_ops) * self.n_part
 
 
 @dataclass
@@ -493,7 +494,7 @@ class CTerm(ctypes.Structure):
 
 
 class CPlan(ctypes.Structure):
-    _fields_ = [("term", ctypes.c_int32), ("n_gather", ctypes.c_int32), ("n_slices", ctypes.c_int32),
+    _fields_ = [("term", ctypes.c_int32), ("n_gather", ctypes.c_int32), ("n_part", ctypes.c_int32),
                 ("width", ctypes.c_int32), ("meta", ctypes.c_int64), ("recs", ctypes.c_int64)]
 
 
@@ -555,7 +556,7 @@ class PackedIR:
         self._datai = np.ascontiguousarray(ir.datai, dtype=np.int32)
         cplans = (CPlan * max(len(plans), 1))()
         for k, pl in enumerate(plans):
-            cplans[k] = CPlan(pl.term, len(pl.gather_ops), pl.n_slices, pl.width, pl.meta_off, pl.recs_off)
+            cplans[k] = CPlan(pl.term, len(pl.gather_ops), pl.n_part, pl.width, pl.meta_off, pl.recs_off)
         self._planf = np.ascontiguousarray(ir.planf, dtype=np.float64)
         self._plani = np.ascontiguousarray(ir.plani, dtype=np.int32)
         self._keep = (cterms, cdets, cops, crvs, cplans)

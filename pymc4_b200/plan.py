@@ -9,12 +9,24 @@ below removes both: observations are regrouped by gather target, groups are cut 
 most ``cap`` observations, chunks are sorted by length and dealt 32 at a time ("slices") to the
 lanes.  Inside a slice each lane walks ONE chunk: the gathered values live in registers, adjoints
 accumulate in registers, observation records are read with conflict-free shared-memory loads.
-Chunk partial sums are combined per group in a fixed order (deterministic, no atomics).
+A chunk that is a whole group adds its sums straight into the chain's gradient; the chunks of a
+split group park their partial sums in a small scratch array and are combined per group in a
+fixed order afterwards (deterministic, no atomics).
 
 The plan depends on the index *values*, so it lives in two run-time pools (``planf`` records,
 ``plani`` metadata); the generated code only depends on which ops are planned (``Plan.gather_ops``
 / ``record_ops`` / ``width``).  The CPU oracle ignores plans and evaluates the original tape, which
 is what makes the parity tests a check of this layout.
+
+Metadata layout (int32, all offsets relative to the start of the plan's metadata, every table
+16-byte aligned):
+  header[8]   n_slices, n_split_groups, n_part (scratch reals per gather), o_slices, o_slots, o_split, 0, 0
+  slices      int4 per slice: rows every lane walks (min length), rows in the slice (max length),
+              first record row, 0
+  slots       int4 per (slice, lane): gather target (-1 = empty lane), chunk length,
+              scratch index for chunks of split groups (-1 = whole group), 0
+  split       int4 per split group: gather target, first scratch index, number of chunks, 0
+Records (reals): row-major [row][lane][width]; row r of slice s is ``first_row + r``.
 """
 from __future__ import annotations
 
@@ -25,8 +37,7 @@ import numpy as np
 
 from . import ir as I
 
-HEADER = 12  # ints: n_slices, n_groups, n_slots, n_chunks, o_maxlen, o_recbase, o_ctarget, o_clen,
-#                   o_gtarget, o_gptr, o_gslots, total_len
+HEADER = 8
 
 
 def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
@@ -41,12 +52,16 @@ def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
     return out
 
 
-def _cost(chunks: List[Tuple[int, int]]) -> Tuple[float, int, int]:
+def _cost(chunks: List[Tuple[int, int]]) -> float:
     lens = sorted((l for _, l in chunks), reverse=True)
     n_slices = -(-len(lens) // 32)
-    iters = sum(lens[s * 32] for s in range(n_slices))
-    # ~7 issue slots per walked element row, ~14 per slice (prologue/epilogue), ~2 per chunk in the group pass
-    return 7.0 * iters + 14.0 * n_slices + 2.0 * len(lens) / 32.0, n_slices, iters
+    cost = 0.0
+    for s in range(n_slices):
+        sl = lens[s * 32:(s + 1) * 32]
+        full = sl[-1] if len(sl) == 32 else 0
+        cost += 7.0 * full + 9.0 * (sl[0] - full) + 30.0  # unpredicated rows, ragged rows, slice overhead
+    n_groups_split = len({g for g, _ in chunks}) - len({g for g, c in Counter(g for g, _ in chunks).items() if c == 1})
+    return cost + 25.0 * (-(-n_groups_split // 32))
 
 
 def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) -> Optional[Tuple[I.Plan, np.ndarray, np.ndarray]]:
@@ -73,59 +88,66 @@ def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) ->
     starts = np.concatenate([[0], np.cumsum(sizes)])
 
     best = None
-    for cap in sorted({2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 32, 48, 64, int(sizes.max())}):
+    for cap in sorted({2, 3, 4, 6, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, int(sizes.max())}):
         ch = _chunks_for_cap(sizes, cap)
-        c, n_slices, iters = _cost(ch)
+        c = _cost(ch)
         if best is None or c < best[0]:
-            best = (c, cap, ch, n_slices, iters)
-    _, cap, chunks, n_slices, _ = best
+            best = (c, cap, ch)
+    _, cap, chunks = best
 
-    # element ids of every chunk
+    # element ids of every chunk, longest chunks first (ties: by group, so a group's chunks are neighbours)
     chunk_elems: List[Tuple[int, np.ndarray]] = []
     cursor = {}
     for g, length in chunks:
         off = cursor.get(g, 0)
         chunk_elems.append((g, order[starts[g] + off: starts[g] + off + length]))
         cursor[g] = off + length
-    chunk_elems.sort(key=lambda ge: -len(ge[1]))  # stable: ties keep group order
+    chunk_elems.sort(key=lambda ge: (-len(ge[1]), ge[0]))
+    n_chunks_of = Counter(g for g, _ in chunk_elems)
 
+    n_slices = -(-len(chunk_elems) // 32)
     n_slots = n_slices * 32
-    slice_maxlen = np.zeros(n_slices, dtype=np.int32)
-    slice_recbase = np.zeros(n_slices, dtype=np.int32)
-    ctarget = np.full(n_slots, -1, dtype=np.int32)
-    clen = np.zeros(n_slots, dtype=np.int32)
+    slices = np.zeros((n_slices, 4), dtype=np.int32)
+    slots = np.zeros((n_slots, 4), dtype=np.int32)
+    slots[:, 0] = -1
+    slots[:, 2] = -1
     rec_rows = 0
     for s in range(n_slices):
-        slice_maxlen[s] = len(chunk_elems[s * 32][1])
-        slice_recbase[s] = rec_rows
-        rec_rows += int(slice_maxlen[s])
+        lens = [len(e) for _, e in chunk_elems[s * 32:(s + 1) * 32]]
+        slices[s] = (lens[-1] if len(lens) == 32 else 0, lens[0], rec_rows, 0)
+        rec_rows += lens[0]
     recs = np.zeros((rec_rows, 32, width), dtype=np.float64)
     cols = [np.asarray(dataf[o.blob: o.blob + n], dtype=np.float64) for o in rec_ops]
-    group_slots: List[List[int]] = [[] for _ in range(G)]
+
+    # scratch indices: the chunks of a split group get consecutive slots
+    split_groups = sorted(g for g, c in n_chunks_of.items() if c > 1)
+    part_first, nxt = {}, 0
+    for g in split_groups:
+        part_first[g] = nxt
+        nxt += n_chunks_of[g]
+    n_part = nxt
+    part_used = {g: 0 for g in split_groups}
     for slot, (g, elems) in enumerate(chunk_elems):
         s, lane = divmod(slot, 32)
-        ctarget[slot] = targets[g]
-        clen[slot] = len(elems)
-        group_slots[g].append(slot)
+        pidx = -1
+        if g in part_first:
+            pidx = part_first[g] + part_used[g]
+            part_used[g] += 1
+        slots[slot] = (targets[g], len(elems), pidx, 0)
         for w, col in enumerate(cols):
-            recs[slice_recbase[s]: slice_recbase[s] + len(elems), lane, w] = col[elems]
-    gptr = np.zeros(G + 1, dtype=np.int32)
-    gslots: List[int] = []
-    for g in range(G):
-        gslots.extend(sorted(group_slots[g]))
-        gptr[g + 1] = len(gslots)
+            recs[slices[s, 2]: slices[s, 2] + len(elems), lane, w] = col[elems]
+    split = np.zeros((max(len(split_groups), 1), 4), dtype=np.int32)
+    for q, g in enumerate(split_groups):
+        split[q] = (targets[g], part_first[g], n_chunks_of[g], 0)
 
-    body = [slice_maxlen, slice_recbase, ctarget, clen, targets.astype(np.int32), gptr,
-            np.asarray(gslots, dtype=np.int32)]
-    offs, cur = [], HEADER
-    for arr in body:
-        offs.append(cur)
-        cur += len(arr)
-    header = np.array([n_slices, G, n_slots, len(chunk_elems)] + offs + [cur], dtype=np.int32)
-    meta = np.concatenate([header] + body).astype(np.int32)
+    o_slices = HEADER
+    o_slots = o_slices + slices.size
+    o_split = o_slots + slots.size
+    header = np.array([n_slices, len(split_groups), max(n_part, 1), o_slices, o_slots, o_split, 0, 0], dtype=np.int32)
+    meta = np.concatenate([header, slices.reshape(-1), slots.reshape(-1), split.reshape(-1)]).astype(np.int32)
     plan = I.Plan(term=t_idx, index_blob=int(blob), gather_ops=[o.dst for o in gathers],
                   record_ops=[o.dst for o in rec_ops], width=width, n_slices=n_slices, n_groups=G,
-                  n_chunks=len(chunk_elems), chunk_cap=cap)
+                  n_chunks=len(chunk_elems), chunk_cap=cap, n_part=max(n_part, 1))
     return plan, meta, recs.reshape(-1)
 
 
