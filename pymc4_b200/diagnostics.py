@@ -78,10 +78,13 @@ def ess_bulk(x: torch.Tensor, rank_normalise: bool = True) -> float:
     return float(n * m / tau)
 
 
-def summarize(states: torch.Tensor, columns: Optional[list] = None, group=None) -> dict:
-    """min bulk-ESS and max split-R-hat over the selected columns of ``states`` [draw, chain, D]."""
+def summarize(states: torch.Tensor, columns: Optional[list] = None, group=None, gather: bool = True) -> dict:
+    """min bulk-ESS and max split-R-hat over the selected columns of ``states`` [draw, chain, D].
+    With ``gather`` (default) the chains of all ranks are pooled first: a collective every rank must call."""
     cols = list(range(states.shape[2])) if columns is None else list(columns)
-    sel = gather_chains(states[:, :, cols].contiguous(), group=group)
+    sel = states[:, :, cols].contiguous()
+    if gather:
+        sel = gather_chains(sel, group=group)
     ess = [ess_bulk(sel[:, :, k]) for k in range(len(cols))]
     rhat = [split_rhat(sel[:, :, k]) for k in range(len(cols))]
     return dict(min_ess=min(ess), max_rhat=max(rhat), columns=cols, ess=ess, rhat=rhat,

@@ -1,0 +1,120 @@
+"""The C-ABI boundary without a GPU: the library builds for sm_100a, loads, exports every symbol
+include/pm4b200.h declares, its structs have the layout the ctypes mirrors assume, the generated
+kernel modules build and carry Blackwell bulk-copy code, and the product refuses to run on CPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from pymc4_b200 import _cabi, _cstructs, codegen, ir as I
+from pymc4_b200.ir import lower_model
+from tests import models as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pm4b200.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pm4_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = _cabi.build_core()
+    lib = _cabi.load_library()
+    names = _declared_functions()
+    assert len(names) >= 12 and set(names) == set(_cabi.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.pm4_abi_version() == I.ABI_VERSION
+    dyn = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    for n in names:
+        assert re.search(r"\bT %s\b" % n, dyn), n
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """Compile a C probe against the public header and compare sizeof/offsetof with ctypes."""
+    structs = {
+        "pm4_rv_t": (I.CRV, ["offset", "size", "transform", "shift", "scale"]),
+        "pm4_term_t": (I.CTerm, ["kind", "n", "op_begin", "op_end", "n_regs", "value_reg", "param_reg", "plan"]),
+        "pm4_op_t": (I.COp, ["opcode", "dst", "a", "b", "mode", "base", "blob", "imm"]),
+        "pm4_det_t": (I.CDet, ["n", "op_begin", "op_end", "n_regs", "value_reg", "out_offset"]),
+        "pm4_plan_t": (I.CPlan, ["term", "n_gather", "n_part", "width", "meta", "recs"]),
+        "pm4_ir_t": (I.CIR, ["abi_version", "D", "n_rv", "n_terms", "n_ops", "n_dets", "det_row", "rvs", "terms",
+                             "ops", "dets", "n_dataf", "dataf", "n_datai", "datai", "struct_hash", "n_plans",
+                             "plans", "n_planf", "planf", "n_plani", "plani"]),
+        "pm4_adapt_cfg_t": (_cstructs.AdaptCfg, ["mode", "num_adaptation_steps", "target_accept_prob",
+                                                 "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled"]),
+        "pm4_hmc_cfg_t": (_cstructs.HMCCfg, ["C", "num_results", "num_burnin", "num_leapfrog_steps", "step_size",
+                                             "seed", "adapt", "warps_per_block", "chain_offset"]),
+        "pm4_nuts_cfg_t": (_cstructs.NUTSCfg, ["C", "num_results", "num_burnin", "max_tree_depth", "max_energy_diff",
+                                               "step_size", "seed", "adapt", "warps_per_block", "chain_offset"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void) {"]
+    for cname, (_, fields) in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f in fields:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    lines += ["return 0; }"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True).stdout.splitlines())
+    for cname, (ct, fields) in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(ct), cname
+        for f in fields:
+            assert int(out["%s.%s" % (cname, f)]) == getattr(ct, f).offset, (cname, f)
+
+
+def test_generated_module_builds_for_sm100a_with_tma_bulk_copy():
+    ir, _, _ = lower_model(M.radon_model())
+    path = codegen.build_module(ir)
+    assert os.path.exists(path) and ir.struct_hash_hex in path and codegen.generator_hash() in path
+    lib = ctypes.CDLL(path)
+    for sym in ("pm4m_info", "pm4m_logp_grad", "pm4m_dets", "pm4m_init", "pm4m_nuts", "pm4m_hmc",
+                "pm4m_da_pooled", "pm4m_export_eps"):
+        assert hasattr(lib, sym), sym
+    elf = subprocess.run(["cuobjdump", "-lelf", path], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", path], stdout=subprocess.PIPE, text=True).stdout
+    assert "UBLKCP" in sass  # cp.async.bulk (TMA) staging of the plan pools
+    assert "SYNCS" in sass  # mbarrier
+    assert "ATOMS.CAST" not in sass  # the planned radon likelihood needs no shared-memory CAS loops
+    src = codegen.generate_source(ir)
+    assert "planned, factored normal" in src and "atomicAdd" not in src
+
+
+def test_unplanned_gathers_fall_back_to_atomics_in_source():
+    idx, y, g = M.poisson_data(n=40)  # below the planning threshold
+    ir, _, _ = lower_model(M.poisson_model(idx, y, g))
+    assert not ir.plans
+    assert "atomicAdd" in codegen.generate_source(ir)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry refuses loudly (BackendUnavailable), it never routes
+    through the oracle or any host implementation."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ir, _, _ = lower_model(M.schools_pm4())
+    with pytest.raises(_cabi.BackendUnavailable):
+        _cabi.DeviceModel(ir)
+    import pymc4_b200 as pm
+
+    with pytest.raises(_cabi.BackendUnavailable):
+        pm.sample(M.schools_pm4(), num_chains=2, num_samples=2, burn_in=2)
+    # the product package never imports, loads or executes anything under oracle/
+    pkg = os.path.join(ROOT, "pymc4_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "libpm4oracle" not in text, f

@@ -1,0 +1,265 @@
+"""Host-logic tests: coroutine models, name scopes, executors, lowering to the IR, execution plans.
+Mirrors the contracts the reference pins in tests/test_executor.py, tests/test_utils.py and
+tests/test_sampling.py (names, observed handling, errors, nested models, deterministics)."""
+import numpy as np
+import pytest
+
+import pymc4_b200 as pm
+from pymc4_b200 import flow, ir as I
+from pymc4_b200.flow.executor import EvaluationError
+from pymc4_b200.ir import lower_model
+from pymc4_b200.utils import NameParts, biwrap
+from tests import models as M
+
+
+def test_name_parts_and_scopes():
+    p = NameParts.from_name("a/b/__log_tau")
+    assert (p.path, p.transform_name, p.untransformed_name) == (("a", "b"), "log", "tau")
+    assert p.full_untransformed_name == "a/b/tau" and p.full_original_name == "a/b/__log_tau" and p.is_transformed
+    assert NameParts.is_valid_untransformed_name("tau") and not NameParts.is_valid_untransformed_name("__log_tau")
+    with pytest.raises(ValueError):
+        NameParts.from_name("_bad")
+    with pm.name_scope("outer"):
+        with pm.name_scope(None):
+            assert pm.variable_name("x") == "outer/x"
+            assert pm.scopes.transformed_variable_name("log", "x") == "outer/__log_x"
+    assert pm.variable_name(None) is None and pm.variable_name("") is None
+
+
+def test_biwrap_both_spellings():
+    @biwrap
+    def deco(fn, *, k=1):
+        return (fn, k)
+
+    def f():
+        pass
+
+    assert deco(f) == (f, 1)
+    assert deco(k=3)(f) == (f, 3)
+
+
+def test_model_decorator_and_names():
+    @pm.model
+    def plain():
+        yield pm.Normal("n", 0, 1)
+
+    @pm.model(name="custom", keep_return=False)
+    def named():
+        x = yield pm.Normal("n", 0, 1)
+        return x
+
+    assert plain().name == "plain" and named().name == "custom" and named(name="other").name == "other"
+    with pytest.raises(ValueError):
+        plain(name="__log_x")
+    _, st = pm.evaluate_model(named())
+    assert "custom" not in st.deterministics_values and "custom/n" in st.untransformed_values
+
+
+def test_executor_states_and_values():
+    _, st = pm.evaluate_model_transformed(
+        M.schools_pm4(), values={"schools_pm4/eta": np.zeros(8), "schools_pm4/mu": 0.0, "schools_pm4/__log_tau": 1.0})
+    assert set(st.transformed_values) == {"schools_pm4/__log_tau"}
+    assert set(st.observed_values) == {"schools_pm4/obs"}
+    np.testing.assert_allclose(st.untransformed_values["schools_pm4/tau"], np.e)
+    np.testing.assert_allclose(st.collect_log_prob(), -42.87611367240224, rtol=1e-13)  # reference golden
+    assert len(st.potentials) == 1 and "schools_pm4" in st.deterministics_values
+    # the untransformed executor refuses transformed values (reference executor.py:569-574)
+    with pytest.raises(ValueError):
+        pm.evaluate_model(M.schools_pm4(), values={"schools_pm4/__log_tau": 1.0})
+
+
+def test_meta_executor_initial_state():
+    st, det_names = pm.initialize_sampling_state(M.radon_model(real=True))
+    keys = list(st.all_unobserved_values)
+    assert keys[:4] == ["hierarchical_model/mu_alpha", "hierarchical_model/mu_beta",
+                        "hierarchical_model/alpha", "hierarchical_model/beta"]  # untransformed first
+    assert keys[4:] == ["hierarchical_model/__log_sigma_alpha", "hierarchical_model/__log_sigma_beta",
+                        "hierarchical_model/__log_eps"]
+    assert all(np.all(np.asarray(v) == 0) for v in st.all_unobserved_values.values())  # test point: theta = 0
+    assert det_names == ["hierarchical_model/sigma_alpha", "hierarchical_model/sigma_beta", "hierarchical_model/eps"]
+
+
+def test_observed_handling_and_errors():
+    @pm.model
+    def m():
+        x = yield pm.Normal("x", 0, 1, observed=1.0)
+        y = yield pm.Normal("y", x, 1)
+        return y
+
+    _, st = pm.evaluate_model(m())
+    assert "m/x" in st.observed_values and "m/y" in st.untransformed_values
+    # suppress the observation -> it becomes a sampled (posterior-predictive) variable
+    _, st = pm.evaluate_model(m(), observed={"m/x": None})
+    assert "m/x" in st.untransformed_values and "m/x" in st.posterior_predictives
+    # replace the observation
+    _, st = pm.evaluate_model(m(), observed={"m/x": 5.0})
+    assert st.observed_values["m/x"] == 5.0
+    # a value for an observed variable without suppressing it is an error
+    with pytest.raises(EvaluationError):
+        pm.evaluate_model(m(), values={"m/x": 2.0})
+    with pytest.raises(ValueError):
+        pm.Normal(None, 0, 1, observed=1.0)
+
+    @pm.model
+    def dup():
+        yield pm.Normal("x", 0, 1)
+        yield pm.Normal("x", 0, 1)
+
+    with pytest.raises(EvaluationError):
+        pm.evaluate_model(dup())
+
+    @pm.model
+    def bad_yield():
+        yield 3
+
+    with pytest.raises((EvaluationError, flow.StopExecution)):
+        pm.evaluate_model(bad_yield())
+
+    @pm.model
+    def bad_shape():
+        yield pm.Normal("x", np.zeros(3), 1, observed=np.zeros(4))
+
+    with pytest.raises(EvaluationError):
+        pm.evaluate_model(bad_shape())
+
+
+def test_nested_models_and_deterministics():
+    _, st = pm.evaluate_model_transformed(M.outer_model())
+    assert set(st.deterministics_values) == {"outer_model/dcond", "outer_model/nested_model/dx",
+                                             "outer_model/nested_model", "outer_model/ddx", "outer_model"}
+    assert set(st.transformed_values) == {"outer_model/__log_cond"}
+    ir, init, names = lower_model(M.outer_model())
+    assert [rv.name for rv in ir.rvs] == ["outer_model/nested_model/x", "outer_model/__log_cond"]
+    assert names[-1] == "outer_model/cond" and {d.name for d in ir.dets} == set(names)
+
+
+def test_lowering_eight_schools():
+    ir, init, names = lower_model(M.schools_pm4())
+    assert ir.D == 10 and [(rv.name, rv.offset, rv.size, rv.transform) for rv in ir.rvs] == [
+        ("schools_pm4/eta", 0, 8, I.TR_IDENTITY), ("schools_pm4/mu", 8, 1, I.TR_IDENTITY),
+        ("schools_pm4/__log_tau", 9, 1, I.TR_EXP)]
+    kinds = [t.kind for t in ir.terms]
+    assert kinds == [I.TERM_KINDS["normal"], I.TERM_KINDS["normal"], I.TERM_KINDS["halfnormal"],
+                     I.TERM_KINDS["normal"], I.TERM_KINDS["potential"]]
+    assert [t.n for t in ir.terms] == [8, 1, 1, 8, 1]
+    # structure hash ignores data values but not structure
+    y2 = M.Y8 + 1
+
+    @pm.model
+    def schools_pm4():
+        eta = yield pm.Normal("eta", 0, 1, batch_stack=8)
+        mu = yield pm.Normal("mu", 1, 10)
+        tau = yield pm.HalfNormal("tau", 2.0)
+        obs = yield pm.Normal("obs", mu + tau * eta, M.SIGMA8, observed=y2)
+        return obs
+
+    ir2, _, _ = lower_model(schools_pm4())
+    assert ir2.struct_hash == ir.struct_hash and not np.array_equal(ir2.dataf, ir.dataf)
+    ir3, _, _ = lower_model(M.radon_model())
+    assert ir3.struct_hash != ir.struct_hash
+
+
+def test_errors_of_the_logp_builder():
+    from pymc4_b200.mcmc.samplers import build_logp_and_deterministic_functions
+
+    with pytest.raises(ValueError):  # no free variables (reference samplers.py:748-751)
+        lower_model(M.simple_model_no_free_rvs())
+    with pytest.raises(TypeError):  # not a Model (reference samplers.py:737-742)
+        build_logp_and_deterministic_functions(lambda: None)
+    with pytest.raises(ValueError):  # state and observed together (reference samplers.py:743-744)
+        build_logp_and_deterministic_functions(M.simple_model(), observed={"a": 1}, state=flow.SamplingState())
+
+    @pm.model
+    def discrete_free():
+        yield pm.Bernoulli("b", 0.5)
+
+    with pytest.raises(ValueError):  # discrete + gradient sampler (reference samplers.py:62-66)
+        pm.mcmc.samplers.NUTS(discrete_free())
+    with pytest.raises(KeyError):  # unknown sampler (reference tests/test_sampling.py:138-141)
+        pm.sample(M.simple_model(), sampler_type="unknown")
+    with pytest.raises(NotImplementedError):  # kernel options the CUDA kernels do not implement fail loudly
+        pm.mcmc.kernels.NoUTurnSampler(None, 0.1, unrolled_leapfrog_steps=2)
+
+
+def test_kwarg_routing_by_signature():
+    s = pm.mcmc.samplers.NUTS(M.simple_model(), step_size=0.3, max_tree_depth=7, target_accept_prob=0.8,
+                              num_adaptation_steps=5, xla_fixture=True, dtype="float64")
+    assert s.kernel_kwargs["step_size"] == 0.3 and s.kernel_kwargs["max_tree_depth"] == 7
+    assert s.adaptation_kwargs["target_accept_prob"] == 0.8 and s.adaptation_kwargs["num_adaptation_steps"] == 5
+    assert "xla_fixture" not in s.kernel_kwargs and s.backend_kwargs == {"dtype": "float64"}
+    h = pm.mcmc.samplers.HMC(M.simple_model())
+    assert h.kernel_kwargs == {"step_size": 0.1, "num_leapfrog_steps": 3}
+    assert s.stat_names == ["lp", "tree_size", "diverging", "energy", "mean_tree_accept"]
+
+
+@pytest.mark.parametrize("sorted_idx", [True, False])
+def test_execution_plan_is_a_permutation(sorted_idx):
+    rng = np.random.default_rng(1)
+    n, G = 700, 37
+    idx = rng.integers(0, G, n).astype(np.int32)
+    idx[:G] = np.arange(G)
+    if sorted_idx:
+        idx = np.sort(idx)
+    x, y = rng.normal(size=n), rng.normal(size=n)
+    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, G))
+    (pl,) = ir.plans
+    meta = ir.plani[pl.meta_off:]
+    n_slices, n_split, n_part, o_sl, o_st, o_sp = meta[:6]
+    slices = meta[o_sl:o_sl + 4 * n_slices].reshape(-1, 4)
+    slots = meta[o_st:o_st + 4 * 32 * n_slices].reshape(-1, 4)
+    recs = ir.planf[pl.recs_off:].reshape(-1, 32, pl.width)
+    seen = []
+    per_target = {}
+    for slot, (tgt, ln, pidx, _) in enumerate(slots):
+        s, lane = divmod(slot, 32)
+        full, mx, first, _ = slices[s]
+        assert ln <= mx and (tgt < 0) == (ln == 0) and (ln >= full or tgt < 0)
+        if tgt >= 0:
+            rows = recs[first:first + ln, lane]
+            seen.append(rows)
+            per_target.setdefault(int(tgt), []).append((ln, int(pidx)))
+            assert np.all(recs[first + ln:first + mx, lane] == 0)  # padding
+    got = np.concatenate(seen)
+    want = np.stack([y, x], axis=1)  # record order = op order of the data loads: value y first, then x
+    assert got.shape == want.shape
+    assert np.array_equal(np.sort(got.view([("a", float), ("b", float)]), axis=0),
+                          np.sort(want.view([("a", float), ("b", float)]), axis=0))
+    sizes = np.bincount(idx, minlength=G)
+    for tgt, chunks in per_target.items():
+        assert sum(l for l, _ in chunks) == sizes[tgt]
+        if len(chunks) == 1:
+            assert chunks[0][1] == -1
+        else:
+            ps = sorted(p for _, p in chunks)
+            assert ps == list(range(ps[0], ps[0] + len(ps))) and ps[-1] < n_part
+    split = meta[o_sp:o_sp + 4 * n_split].reshape(-1, 4)
+    assert {int(t) for t in split[:, 0]} == {t for t, ch in per_target.items() if len(ch) > 1}
+
+
+def test_step_size_conventions():
+    s = pm.mcmc.samplers.NUTS(M.schools_pm4())
+
+    class _DM:
+        pass
+
+    dm = _DM()
+    dm.ir, _, _ = lower_model(M.schools_pm4())
+    s._device_model = dm
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED
+
+    assert s._step_size_policy(0.28, 4) == (0.28, None, PM4_EPS_POOLED)
+    assert s._step_size_policy(np.full((4, 1), 0.2), 4) == (0.2, None, PM4_EPS_PER_CHAIN)
+    parts = [np.full((4, 8), 0.5), np.full((4,), 0.25), np.full((4,), 2.0)]
+    eps0, scale, mode = s._step_size_policy(parts, 4)
+    assert eps0 == 1.0 and mode == PM4_EPS_PER_CHAIN
+    np.testing.assert_allclose(scale, [0.5] * 8 + [0.25, 2.0])
+
+
+def test_trace_to_arviz_layout():
+    post = {"m/x": np.arange(24.0).reshape(3, 4, 2), "m": np.zeros((3, 4))}  # [draw, chain, core]
+    stats = {"lp": np.arange(12.0).reshape(3, 4)}
+    tr = pm.trace_to_arviz(post, stats, observed_data={"m/y": np.ones(5)})
+    assert set(tr.posterior) == {"m/x"}  # keys without "/" are dropped (reference utils.py:122)
+    assert tr.posterior["m/x"].shape == (4, 3, 2) and tr.sample_stats["lp"].shape == (4, 3)
+    assert tr.posterior["m/x"][1, 2, 0] == post["m/x"][2, 1, 0]
+    assert tr.groups() == ["posterior", "sample_stats", "observed_data"]

@@ -1,0 +1,262 @@
+"""CPU tests of the oracle (oracle/pm4_oracle.c) against the reference's golden values, scipy,
+torch autograd and published known-answer vectors.  No GPU needed."""
+import math
+
+import numpy as np
+import pytest
+import torch
+from scipy import stats
+
+from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_hmc_cfg, make_nuts_cfg
+from pymc4_b200.ir import lower_model
+from tests import models as M
+
+
+def test_eight_schools_golden(oracle_mod, golden):
+    """The reference's own golden value, tests/test_8schools.py:50-61."""
+    ir, _, _ = lower_model(M.schools_pm4())
+    th = ir.join_theta({"schools_pm4/eta": np.zeros(8), "schools_pm4/mu": 0.0, "schools_pm4/__log_tau": 1.0})
+    o = oracle_mod.Oracle(ir)
+    lp64, _ = o.logp_grad(th, dtype=np.float64)
+    lp32, _ = o.logp_grad(th, dtype=np.float32)
+    assert abs(lp64[0] - golden["eight_schools"]["scipy_f64"]) < 1e-12
+    np.testing.assert_almost_equal(lp32[0], golden["eight_schools"]["reference_assert_f32"])  # same assert as the reference
+    assert np.float32(lp64[0]) == np.float32(golden["eight_schools"]["reference_assert_f32"])
+
+
+def test_radon_golden(oracle_mod, golden):
+    ir, _, _ = lower_model(M.radon_model(real=True))
+    assert [rv.name.split("/")[-1] for rv in ir.rvs] == [
+        "mu_alpha", "mu_beta", "alpha", "beta", "__log_sigma_alpha", "__log_sigma_beta", "__log_eps"]
+    o = oracle_mod.Oracle(ir)
+    pts = np.stack([np.zeros(ir.D), np.array(golden["radon_919"]["theta_rand"])])
+    lp, _ = o.logp_grad(pts, dtype=np.float64)
+    np.testing.assert_allclose(lp, [golden["radon_919"]["logp_at_zero"], golden["radon_919"]["logp_at_rand"]], rtol=1e-13)
+
+
+def _torch_radon_logp(theta, idx, x, y, G):
+    mu_a, mu_b = theta[0], theta[1]
+    a, b = theta[2:2 + G], theta[2 + G:2 + 2 * G]
+    lsa, lsb, le = theta[2 + 2 * G], theta[3 + 2 * G], theta[4 + 2 * G]
+    sa, sb, eps = torch.exp(lsa), torch.exp(lsb), torch.exp(le)
+    N = torch.distributions.Normal
+    HC = torch.distributions.HalfCauchy
+    lp = N(0., 1.).log_prob(mu_a) + N(0., 1.).log_prob(mu_b)
+    lp = lp + HC(1.).log_prob(sa) + lsa + HC(1.).log_prob(sb) + lsb + HC(1.).log_prob(eps) + le
+    lp = lp + N(mu_a, sa).log_prob(a).sum() + N(mu_b, sb).log_prob(b).sum()
+    lp = lp + N(a[idx] + b[idx] * x, eps).log_prob(y).sum()
+    return lp
+
+
+def test_radon_gradient_vs_torch_autograd(oracle_mod):
+    idx, x, y, G = M.radon_real()
+    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, G))
+    rng = np.random.default_rng(3)
+    th = rng.normal(0, 0.3, ir.D)
+    lp, g = oracle_mod.Oracle(ir).logp_grad(th, dtype=np.float64)
+    t = torch.tensor(th, dtype=torch.float64, requires_grad=True)
+    ref = _torch_radon_logp(t, torch.tensor(idx, dtype=torch.long), torch.tensor(x), torch.tensor(y), G)
+    ref.backward()
+    assert abs(lp[0] - ref.item()) < 1e-9 * abs(ref.item())
+    np.testing.assert_allclose(g[0], t.grad.numpy(), rtol=1e-8, atol=1e-8)  # x/s - mu/s vs (x - mu)/s
+
+
+@pytest.mark.parametrize("name", ["logistic", "poisson", "nested", "eight_schools"])
+def test_gradient_vs_finite_differences(name, oracle_mod):
+    mk = {"logistic": lambda: M.logistic_model(*M.logistic_data()), "poisson": lambda: M.poisson_model(*M.poisson_data()),
+          "nested": lambda: M.outer_model(), "eight_schools": lambda: M.schools_pm4()}[name]
+    ir, _, _ = lower_model(mk())
+    o = oracle_mod.Oracle(ir)
+    th = np.random.default_rng(4).normal(0, 0.5, ir.D)
+    _, g = o.logp_grad(th)
+    fd = np.zeros(ir.D)
+    for j in range(ir.D):
+        e = np.zeros(ir.D); e[j] = 1e-6
+        fd[j] = (o.logp_grad(th + e)[0][0] - o.logp_grad(th - e)[0][0]) / 2e-6
+    np.testing.assert_allclose(g[0], fd, rtol=2e-6, atol=2e-6)
+
+
+def test_densities_vs_scipy(oracle_mod):
+    """Same recipe as the reference's tests/test_sampling.py:43-61: log-density == scipy sums."""
+    import pymc4_b200 as pm
+
+    rng = np.random.default_rng(8)
+    yn, yb, yp = rng.normal(size=7), (rng.random(9) < 0.4).astype(float), rng.poisson(3.0, 11).astype(float)
+
+    @pm.model
+    def m():
+        mu = yield pm.Normal("mu", 0.5, 2.0)
+        s = yield pm.HalfNormal("s", 1.5)
+        c = yield pm.HalfCauchy("c", 0.7)
+        yield pm.Normal("yn", mu, s, observed=yn)
+        yield pm.Bernoulli("yb", pm.math.sigmoid(mu), observed=yb)
+        yield pm.Poisson("yp", c + 1.0, observed=yp)
+
+    ir, _, _ = lower_model(m())
+    assert [rv.name for rv in ir.rvs] == ["m/mu", "m/__log_s", "m/__log_c"]
+    for _ in range(5):
+        mu, ls, lc = rng.normal(0, 0.7, 3)
+        s, c = math.exp(ls), math.exp(lc)
+        p = 1 / (1 + math.exp(-mu))
+        ref = (stats.norm.logpdf(mu, 0.5, 2.0) + stats.halfnorm.logpdf(s, scale=1.5) + ls
+               + stats.halfcauchy.logpdf(c, scale=0.7) + lc + stats.norm.logpdf(yn, mu, s).sum()
+               + stats.bernoulli.logpmf(yb, p).sum() + stats.poisson.logpmf(yp, c + 1.0).sum())
+        lp, _ = oracle_mod.Oracle(ir).logp_grad(np.array([mu, ls, lc]))
+        np.testing.assert_allclose(lp[0], ref, rtol=1e-12)
+        lp32, _ = oracle_mod.Oracle(ir).logp_grad(np.array([mu, ls, lc]), dtype=np.float32)
+        np.testing.assert_allclose(lp32[0], ref, rtol=1e-5)  # the reference's own tolerance
+
+
+def test_log_transform_density(oracle_mod):
+    """tests/test_executor.py:277-298 restated: HalfNormal through the Log transform equals the
+    density of the transformed distribution."""
+    import pymc4_b200 as pm
+
+    @pm.model
+    def m():
+        yield pm.HalfNormal("n", 1.0)
+
+    ir, _, _ = lower_model(m())
+    for z in (-1.3, 0.0, 0.4, 2.0):
+        lp, _ = oracle_mod.Oracle(ir).logp_grad(np.array([z]))
+        np.testing.assert_allclose(lp[0], stats.halfnorm.logpdf(math.exp(z)) + z, rtol=1e-12)
+
+
+def test_philox_known_answers(oracle_mod):
+    """Random123 kat_vectors for philox4x32-10."""
+    assert oracle_mod.philox4x32_10([0] * 4, [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle_mod.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle_mod.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == [
+        0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    m = np.concatenate([oracle_mod.draw_momentum(7, c, t, 175, np.float64) for c in range(8) for t in range(8)])
+    assert abs(m.mean()) < 0.03 and abs(m.std() - 1) < 0.03  # Box-Muller normals
+
+
+# --- tfp.mcmc.nuts U-turn bookkeeping: published generator restated, against the closed form ---------
+def _build_tree_uturn_instruction(max_depth, init_memory=0):
+    def _buildtree(address, depth):
+        if depth == 0:
+            address += 1
+            return address, address
+        address_left, address_right = _buildtree(address, depth - 1)
+        _, address_right = _buildtree(address_right, depth - 1)
+        instruction.append((address_left, address_right))
+        return address_left, address_right
+
+    instruction = []
+    _buildtree(init_memory, max_depth)
+    return np.array(instruction, dtype=np.int32)
+
+
+def _generate_efficient_write_read_instruction(instruction_array):
+    nsteps = np.max(instruction_array) + 1
+    mat = np.zeros((nsteps, nsteps))
+    for a, b in instruction_array:
+        mat[a, b] = 1
+    for i in range(nsteps):
+        temp = mat[i]
+        endpoint = np.where(temp == 1)[0]
+        if endpoint.size > 0:
+            temp[:i] = -1
+            temp[endpoint[-1] + 1:] = -1
+            mat[i] = temp
+        else:
+            mat[i] = -1
+    to_write = np.sum(mat > -1, axis=0)
+    write = to_write - 1
+    write[np.diag(mat) == -1] = max(to_write)
+    read = []
+    for i in range(nsteps):
+        col = mat[:, i]
+        if np.sum(col == 1) > 0:
+            r = np.where(col[col >= 0] == 1)[0][0]
+            read.append([r, r + np.sum(col == 1)])
+        else:
+            read.append([0, 0])
+    return write, np.asarray(read)
+
+
+@pytest.mark.parametrize("max_depth", [1, 3, 6, 10])
+def test_uturn_checkpoint_closed_form(max_depth):
+    """oracle and kernels use: even leaf i -> write slot popcount(i); odd leaf i -> read slots
+    [popcount(i) - trailing_ones(i), popcount(i)).  Equal to TFP's instruction tables."""
+    write, read = _generate_efficient_write_read_instruction(_build_tree_uturn_instruction(max_depth, init_memory=-1))
+    assert len(write) == 1 << max_depth and max(write) == max_depth
+    for i in range(1 << max_depth):
+        pc = bin(i).count("1")
+        t1 = 0
+        while (i >> t1) & 1:
+            t1 += 1
+        if i % 2 == 0:
+            assert write[i] == pc and tuple(read[i]) == (0, 0)
+        else:
+            assert write[i] == max_depth and tuple(read[i]) == (pc - t1, pc)
+
+
+def test_dual_averaging_recursion(oracle_mod):
+    """Hand-evaluate the tfp DualAveragingStepSizeAdaptation recursion for a chain whose
+    acceptance probability is known: a Gaussian target with a tiny step accepts with probability ~1."""
+    import pymc4_b200 as pm
+
+    @pm.model
+    def m():
+        yield pm.Normal("x", 0.0, 1.0)
+
+    ir, _, _ = lower_model(m())
+    B = 6
+    cfg = make_hmc_cfg(1, 1, B, step_size=1e-4, num_leapfrog_steps=1, seed=5, adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B))
+    out = oracle_mod.Oracle(ir).hmc(cfg, np.zeros(1), dtype=np.float64)
+    eps0, err, log_avg, eps = 1e-4, 0.0, 0.0, 1e-4
+    for t in range(B + 1):
+        step = t + 1.0
+        err += 0.75 - 1.0  # accept prob == 1 to ~1e-8 while eps stays tiny
+        log_eps = math.log(10 * eps0) - err * math.sqrt(step) / ((10 + step) * 0.05)
+        eta = step ** -0.75
+        log_avg = eta * log_eps + (1 - eta) * log_avg
+        eps = math.exp(log_eps) if t < B else math.exp(log_avg)
+        if eps > 0.05:
+            break  # beyond this the acceptance is no longer ~1
+    else:
+        np.testing.assert_allclose(out["step_size"][0], eps, rtol=1e-4)
+    assert out["step_size"][0] > 1e-4  # the step size grew as the recursion demands
+
+
+def test_nuts_standard_normal_and_determinism(oracle_mod):
+    """Statistical sanity of the restated NUTS (reference tests/test_compound.py:124-146: |mean| < 0.1,
+    same seed => same trace)."""
+    import pymc4_b200 as pm
+
+    @pm.model
+    def m():
+        yield pm.Normal("x", 0.0, 1.0, batch_stack=3)
+
+    ir, _, _ = lower_model(m())
+    cfg = make_nuts_cfg(32, 300, 100, step_size=0.1, seed=11, adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=100))
+    o = oracle_mod.Oracle(ir)
+    a = o.nuts(cfg, np.zeros(3), dtype=np.float64)
+    b = o.nuts(cfg, np.zeros(3), dtype=np.float64)
+    assert np.array_equal(a["states"], b["states"]) and np.array_equal(a["leapfrogs"], b["leapfrogs"])
+    x = a["states"].reshape(-1, 3)
+    assert np.all(np.abs(x.mean(0)) < 0.1) and np.all(np.abs(x.var(0) - 1) < 0.15)
+    assert a["diverging"].sum() == 0
+    assert np.all(a["leapfrogs"] == (1 << a["depth"]) - 1) or np.all(a["leapfrogs"] <= (1 << a["depth"]) - 1)
+    c = o.nuts(make_nuts_cfg(32, 300, 100, step_size=0.1, seed=12, adapt=cfg.adapt), np.zeros(3), dtype=np.float64)
+    assert not np.array_equal(a["states"], c["states"])
+    # per-chain adaptation gives different step sizes per chain, pooled a single one
+    d = o.nuts(make_nuts_cfg(8, 10, 50, step_size=0.1, seed=1, adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=50)),
+               np.zeros(3), dtype=np.float64)
+    assert len(set(np.round(d["step_size"], 12))) > 1 and len(set(np.round(a["step_size"], 12))) == 1
+
+
+def test_deterministics_and_float32_path(oracle_mod):
+    ir, _, names = lower_model(M.outer_model())
+    assert [d.name for d in ir.dets] == names
+    th = np.random.default_rng(0).normal(size=(5, ir.D))
+    out = oracle_mod.Oracle(ir).deterministics(th)
+    k = {d.name: d.out_offset for d in ir.dets}
+    cond = np.exp(th[:, ir.rv_by_name("outer_model/__log_cond").offset])
+    x = th[:, ir.rv_by_name("outer_model/nested_model/x").offset]
+    np.testing.assert_allclose(out[:, k["outer_model/dcond"]], 2 * cond)
+    np.testing.assert_allclose(out[:, k["outer_model/nested_model/dx"]], x + 1)
+    np.testing.assert_allclose(out[:, k["outer_model/ddx"]], x + 1)
+    np.testing.assert_allclose(out[:, k["outer_model/cond"]], cond)
