@@ -150,7 +150,10 @@ class DeviceModel:
             return None
         if isinstance(arr, torch.Tensor):
             return arr.to(device=self._dev(), dtype=_tdtype(torch, dtype)).contiguous()
-        host = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype))
+        host = np.ascontiguousarray(arr, dtype=dtype)
+        if not host.flags.writeable:  # e.g. a broadcast view: torch wants a writable buffer
+            host = host.copy()
+        host = torch.from_numpy(host)
         return host.to(self._dev(), non_blocking=False)
 
     @staticmethod

@@ -1,0 +1,120 @@
+"""GPU tests of the drop-in ``pm.sample`` API; they read like the reference's own tests
+(tests/test_8schools.py:64-77, tests/test_sampling.py:8-20,64-123, tests/test_compound.py:124-146)."""
+import numpy as np
+import pytest
+
+import pymc4_b200 as pm
+from tests import models as M
+
+pytestmark = pytest.mark.gpu
+
+
+def test_model_logp_golden():
+    """tests/test_8schools.py:24-61 with the same call."""
+    logp, *_ = pm.mcmc.samplers.build_logp_and_deterministic_functions(
+        M.schools_pm4(), observed={"obs": M.Y8}, state=None)
+    init_value = logp(**{"schools_pm4/eta": np.zeros(8, np.float32), "schools_pm4/mu": np.zeros((), np.float32),
+                         "schools_pm4/__log_tau": np.ones((), np.float32)}).cpu().numpy()
+    np.testing.assert_allclose(init_value, -42.876_114, rtol=1e-6)
+    # leading batch axes are vectorised like the reference's vectorize_logp_function
+    batch = logp(np.zeros((5, 3, 8), np.float32), np.zeros((5, 3), np.float32), np.ones((5, 3), np.float32))
+    assert tuple(batch.shape) == (5, 3) and np.allclose(batch.cpu().numpy(), init_value)
+
+
+def test_sample_eight_schools_keys_and_shapes():
+    chains, samples = 4, 100
+    trace = pm.inference.sampling.sample(M.schools_pm4(), step_size=0.28, num_chains=chains, num_samples=samples,
+                                         burn_in=50, xla=False, seed=3)
+    post = trace.posterior
+    for var_name in ("eta", "mu", "tau", "__log_tau"):
+        assert f"schools_pm4/{var_name}" in post.keys()
+    assert "schools_pm4" not in post  # keys without "/" are dropped
+    assert post["schools_pm4/eta"].shape == (chains, samples, 8) and post["schools_pm4/mu"].shape == (chains, samples)
+    np.testing.assert_allclose(post["schools_pm4/tau"], np.exp(post["schools_pm4/__log_tau"]), rtol=1e-6)
+    ss = trace.sample_stats
+    assert set(ss) == {"lp", "tree_size", "diverging", "energy", "mean_tree_accept"}
+    assert ss["tree_size"].shape == (chains, samples) and ss["tree_size"].dtype == np.int32 and ss["tree_size"].min() >= 1
+    assert ss["diverging"].dtype == np.bool_ and np.all(ss["mean_tree_accept"] <= 1e-6)
+    assert np.array_equal(trace.observed_data["schools_pm4/obs"], M.Y8)
+
+
+@pytest.mark.parametrize("xla", [True, False])
+def test_sample_deterministics(xla):
+    trace = pm.sample(model=M.simple_model_with_deterministic(), num_samples=10, num_chains=4, burn_in=100,
+                      step_size=0.1, xla=xla)
+    norm = "simple_model_with_deterministic/simple_model/norm"
+    determ = "simple_model_with_deterministic/determ"
+    np.testing.assert_allclose(trace.posterior[determ], trace.posterior[norm] * 2)
+
+
+def test_sampling_with_deterministics_in_nested_models():
+    trace = pm.sample(model=M.outer_model(), num_samples=10, num_chains=4, burn_in=100, step_size=0.1)
+    mapping = {
+        "outer_model/dcond": (["outer_model/__log_cond"], lambda x: np.exp(x) * 2),
+        "outer_model/ddx": (["outer_model/nested_model/dx"], lambda x: x),
+        "outer_model/nested_model/dx": (["outer_model/nested_model/x"], lambda x: x + 1),
+    }
+    for det, (inputs, op) in mapping.items():
+        np.testing.assert_allclose(trace.posterior[det], op(*[trace.posterior[i] for i in inputs]), rtol=1e-6)
+
+
+def test_sampling_with_no_free_rvs():
+    with pytest.raises(ValueError):
+        pm.sample(model=M.simple_model_no_free_rvs(), num_samples=1, num_chains=1, burn_in=1)
+
+
+def test_sample_shapes_unvectorized_model():
+    observed = np.zeros((5, 4), dtype="float32")
+
+    @pm.model
+    def model():
+        mu = yield pm.Normal("mu", np.zeros(4), 1)
+        scale = yield pm.HalfNormal("scale", 1)
+        x = yield pm.Normal("x", mu, scale, batch_stack=5, observed=observed)
+
+    trace = pm.sample(model=model(), num_samples=10, num_chains=4, burn_in=1, step_size=0.1)
+    assert trace.posterior["model/mu"].shape == (4, 10, 4) and trace.posterior["model/__log_scale"].shape == (4, 10)
+
+
+@pytest.mark.parametrize("sampler", ["nuts", "hmc"])
+def test_samplers_on_standard_normal_and_seed_determinism(sampler):
+    """tests/test_compound.py:124-146: |posterior mean| < 0.1; the same seed gives the same trace."""
+    kw = dict(sampler_type=sampler, num_chains=50, num_samples=300, burn_in=200, seed=5)
+    if sampler == "hmc":
+        kw.update(step_size=0.5, num_leapfrog_steps=5)
+    t1 = pm.sample(M.simple_model(), **kw)
+    t2 = pm.sample(M.simple_model(), **kw)
+    x1, x2 = t1.posterior["simple_model/norm"], t2.posterior["simple_model/norm"]
+    assert abs(x1.mean()) < 0.1 and abs(x1.std() - 1) < 0.1
+    assert np.array_equal(x1, x2)
+    t3 = pm.sample(M.simple_model(), **dict(kw, seed=6))
+    assert not np.array_equal(x1, t3.posterior["simple_model/norm"])
+    assert "mean_tree_accept" in t1.sample_stats
+
+
+def test_per_part_step_sizes_like_the_radon_notebook():
+    """notebooks/radon_hierarchical.ipynb:123-146: step_size as a list of [C, *core] arrays."""
+    C = 16
+    model = M.radon_model(n_obs=200, n_groups=12)
+    trace = pm.sample(model, num_chains=C, num_samples=20, burn_in=20, step_size=0.05, seed=1)
+    keys = [k for k in trace.posterior if k.split("/")[-1] in ("mu_alpha", "mu_beta", "alpha", "beta", "__log_sigma_alpha",
+                                                              "__log_sigma_beta", "__log_eps")]
+    order = ["mu_alpha", "mu_beta", "alpha", "beta", "__log_sigma_alpha", "__log_sigma_beta", "__log_eps"]
+    parts = []
+    for name in order:
+        x = trace.posterior["hierarchical_model/" + name]
+        std = x.std(axis=(0, 1)) + 1e-3
+        parts.append(np.broadcast_to(std, (C,) + std.shape).astype(np.float32))
+    trace2 = pm.sample(model, num_chains=C, num_samples=30, burn_in=30, step_size=parts, seed=2)
+    assert trace2.posterior["hierarchical_model/alpha"].shape == (C, 30, 12)
+    assert np.all(np.isfinite(trace2.posterior["hierarchical_model/alpha"]))
+
+
+def test_float64_mode_and_chain_offset():
+    a = pm.sample(M.schools_pm4(), num_chains=4, num_samples=20, burn_in=20, seed=9, dtype="float64")
+    assert a.posterior["schools_pm4/mu"].dtype == np.float64
+    # chains 2..3 of a 4-chain run == a 2-chain run with chain_offset=2 under per-chain step sizes
+    step = np.full((4, 1), 0.2)
+    full = pm.sample(M.schools_pm4(), num_chains=4, num_samples=15, burn_in=15, seed=9, step_size=step)
+    part = pm.sample(M.schools_pm4(), num_chains=2, num_samples=15, burn_in=15, seed=9, step_size=step[:2], chain_offset=2)
+    np.testing.assert_array_equal(full.posterior["schools_pm4/eta"][2:], part.posterior["schools_pm4/eta"])
