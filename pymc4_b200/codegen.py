@@ -49,8 +49,8 @@ _UNARY_FWD = {
 }
 # d(out)/d(a) as an expression of a (input), r (output) and the incoming adjoint g
 _UNARY_BWD = {
-    "neg": "-{g}", "exp": "{g} * {r}", "log": "{g} / {a}", "log1p": "{g} / ((real)1 + {a})",
-    "sqrt": "{g} / ((real)2 * {r})", "square": "(real)2 * {g} * {a}", "sigmoid": "{g} * {r} * ((real)1 - {r})",
+    "neg": "-{g}", "exp": "{g} * {r}", "log": "{g} * pm4::m_rcp({a})", "log1p": "{g} * pm4::m_rcp((real)1 + {a})",
+    "sqrt": "{g} * pm4::m_rcp((real)2 * {r})", "square": "(real)2 * {g} * {a}", "sigmoid": "{g} * {r} * ((real)1 - {r})",
     "softplus": "{g} * pm4::m_sigmoid<real>({a})", "tanh": "{g} * ((real)1 - {r} * {r})",
     "abs": "(({a} > 0) ? {g} : (({a} < 0) ? -{g} : (real)0))", "recip": "-{g} * {r} * {r}",
     "lgamma": "{g} * pm4::m_digamma<real>({a})",
@@ -91,7 +91,7 @@ class _Tape:
         if name in _UNARY_FWD:
             return _UNARY_FWD[name].format(a=a)
         b = self.v(o.b)
-        return {"add": "%s + %s", "sub": "%s - %s", "mul": "%s * %s", "div": "%s / %s",
+        return {"add": "%s + %s", "sub": "%s - %s", "mul": "%s * %s", "div": "%s * pm4::m_rcp(%s)",
                 "pow": "pm4::m_pow(%s, %s)"}[name] % (a, b)
 
     def bwd(self, o: I.Op, g: str) -> List[Tuple[int, str]]:
@@ -109,7 +109,7 @@ class _Tape:
         if name == "mul":
             return [(o.a, "%s * %s" % (g, b)), (o.b, "%s * %s" % (g, a))]
         if name == "div":
-            return [(o.a, "%s / %s" % (g, b)), (o.b, "-%s * %s / %s" % (g, r, b))]
+            return [(o.a, "%s * pm4::m_rcp(%s)" % (g, b)), (o.b, "-%s * %s * pm4::m_rcp(%s)" % (g, r, b))]
         if name == "pow":
             return [(o.a, "%s * %s * pm4::m_pow(%s, %s - (real)1)" % (g, b, a, b)),
                     (o.b, "((%s > 0) ? %s * %s * pm4::m_log(%s) : (real)0)" % (a, g, r, a))]
@@ -168,10 +168,30 @@ class _ModuleGen:
                 "    real lp = 0;"]
         for pos in self.scalar_pos:
             head.append("    const real sx_%d = c.xs[%d]; real sacc_%d = 0;" % (pos, pos, pos))
-        tail = []
-        for pos in self.scalar_pos:
-            tail.append("    { const real tot = pm4::warp_sum(sacc_%d); if (lane == %d) gr[%d] += tot; }"
-                        % (pos, pos & 31, pos >> 5))
+        # one transposing butterfly reduces every scalar adjoint and the log-density together; the
+        # first lane of the group that ends up holding a scalar's total adds it to the gradient
+        n_acc = len(self.scalar_pos)
+        P = 1
+        while P < n_acc + 1:
+            P *= 2
+        if P > 32:
+            raise NotImplementedError("more than 31 distinct scalar parameters in one model")
+        per = 32 // P
+        tail = ["    __syncwarp();",
+                "    real red[%d];" % P]
+        for k, pos in enumerate(self.scalar_pos):
+            tail.append("    red[%d] = sacc_%d;" % (k, pos))
+        tail.append("    red[%d] = lp;" % n_acc)
+        for k in range(n_acc + 1, P):
+            tail.append("    red[%d] = 0;" % k)
+        tail.append("    pm4::warp_sum_packed<%d, real>(red, lane);" % P)
+        if n_acc:
+            tail.append("    {")
+            tail.append("      constexpr int spos[%d] = {%s};" % (n_acc, ", ".join(str(p_) for p_ in self.scalar_pos)))
+            tail.append("      const int k = lane / %d;" % per)
+            tail.append("      if ((lane %% %d) == 0 && k < %d) c.gx[spos[k]] += red[0];" % (per, n_acc))
+            tail.append("    }")
+        tail.append("    lp = __shfl_sync(pm4::FULL, red[0], %d);" % (n_acc * per))
         tail += ["    return lp;", "  }"]
         return "\n".join(head + body + tail)
 
@@ -381,16 +401,23 @@ class _ModuleGen:
             for dst, nm in gather_names.items():
                 E("const real %sv = c.xs[%d + tgt]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
             E("const %s* rp = %s_pr + sl.z * 32;" % (rec_t, tag), 4)
-            E("int i = 0;", 4)
-            E("#pragma unroll 4", 4)
-            E("for (; i < sl.x; ++i) {", 4)
+            E("int i0 = 0;", 4)
+            E("for (; i0 < sl.x; i0 += 4) {   // rows every lane has: no mask", 4)
+            E("#pragma unroll", 5)
+            E("for (int u = 0; u < 4; ++u) {", 5)
+            E("const int i = i0 + u; (void)i;", 5)
             E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
             self.lines.extend(loop)
+            E("}", 5)
             E("}", 4)
-            E("for (; i < sl.y; ++i) {", 4)
+            E("for (; i0 < sl.y; i0 += 4) {   // ragged rows: branch-free, padded records contribute zero", 4)
+            E("#pragma unroll", 5)
+            E("for (int u = 0; u < 4; ++u) {", 5)
+            E("const int i = i0 + u;", 5)
             E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
             E("const bool on = i < len;", 5)
             self.lines.extend(loop_masked)
+            E("}", 5)
             E("}", 4)
             E("if (st.x >= 0) {", 4)
             E("if (st.z < 0) {  // the chunk is a whole group: this lane owns its gradient entries", 5)

@@ -54,4 +54,26 @@ template <typename real> __device__ __forceinline__ real warp_sum(real v) {
   return v;
 }
 
+// Sum P (a power of two <= 32) per-lane values over the warp with a transposing butterfly: each
+// exchange step halves the number of live values, so P = 8 costs 4+2+1+1+1 = 9 shuffles instead of
+// 40.  On return v[0] of lane l is the warp total of value (l * P / 32); all 32/P lanes of a group
+// hold bit-identical totals.
+template <int P, typename real> __device__ __forceinline__ void warp_sum_packed(real (&v)[P], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int h = P; h > 1; h >>= 1) {
+    const int half = h >> 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const real send = up ? v[k] : v[k + half];
+      const real keep = up ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(FULL, send, off);
+    }
+    off >>= 1;
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(FULL, v[0], off);
+}
+
 }  // namespace pm4

@@ -108,14 +108,14 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
     }
   }
   __syncwarp();
-  real lp = M::template terms<real>(x, gr, c);
+  const real lp = M::template terms<real>(x, gr, c);  // already summed over the warp
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = c.lane + 32 * r;
     g[r] = (j < D) ? (gr[r] + c.gx[j]) * dxdz[r] : (real)0;
   }
-  return warp_sum(lp);
+  return lp;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -21,8 +21,8 @@ is what makes the parity tests a check of this layout.
 Metadata layout (int32, all offsets relative to the start of the plan's metadata, every table
 16-byte aligned):
   header[8]   n_slices, n_split_groups, n_part (scratch reals per gather), o_slices, o_slots, o_split, 0, 0
-  slices      int4 per slice: rows every lane walks (min length), rows in the slice (max length),
-              first record row, 0
+  slices      int4 per slice: rows every lane walks unmasked (min length rounded down to a multiple
+              of 4), rows in the slice (max length rounded up to a multiple of 4), first record row, 0
   slots       int4 per (slice, lane): gather target (-1 = empty lane), chunk length,
               scratch index for chunks of split groups (-1 = whole group), 0
   split       int4 per split group: gather target, first scratch index, number of chunks, 0
@@ -38,6 +38,7 @@ import numpy as np
 from . import ir as I
 
 HEADER = 8
+ROW_UNROLL = 4
 
 
 def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
@@ -58,8 +59,9 @@ def _cost(chunks: List[Tuple[int, int]]) -> float:
     cost = 0.0
     for s in range(n_slices):
         sl = lens[s * 32:(s + 1) * 32]
-        full = sl[-1] if len(sl) == 32 else 0
-        cost += 7.0 * full + 9.0 * (sl[0] - full) + 30.0  # unpredicated rows, ragged rows, slice overhead
+        full = (sl[-1] if len(sl) == 32 else 0) // ROW_UNROLL * ROW_UNROLL
+        rows = -(-sl[0] // ROW_UNROLL) * ROW_UNROLL
+        cost += 6.5 * full + 8.5 * (rows - full) + 30.0  # unpredicated rows, masked rows, slice overhead
     n_groups_split = len({g for g, _ in chunks}) - len({g for g, c in Counter(g for g, _ in chunks).items() if c == 1})
     return cost + 25.0 * (-(-n_groups_split // 32))
 
@@ -114,8 +116,12 @@ def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) ->
     rec_rows = 0
     for s in range(n_slices):
         lens = [len(e) for _, e in chunk_elems[s * 32:(s + 1) * 32]]
-        slices[s] = (lens[-1] if len(lens) == 32 else 0, lens[0], rec_rows, 0)
-        rec_rows += lens[0]
+        # both loops of the device walk are unrolled by ROW_UNROLL without remainder: the unmasked
+        # prefix is rounded down, the slice's row count up (padding rows are zero records, masked)
+        full = (lens[-1] if len(lens) == 32 else 0) // ROW_UNROLL * ROW_UNROLL
+        rows = -(-lens[0] // ROW_UNROLL) * ROW_UNROLL
+        slices[s] = (full, rows, rec_rows, 0)
+        rec_rows += rows
     recs = np.zeros((rec_rows, 32, width), dtype=np.float64)
     cols = [np.asarray(dataf[o.blob: o.blob + n], dtype=np.float64) for o in rec_ops]
 
