@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(1024) lds_kernel(float* out, int iters) {
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float4 v = sm4[(idx + k * 1024) & 4095];
+      const float4 v = sm4[(idx + k * 512) & 4095];  // 8 distinct rows: no load is redundant
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     idx = (idx + 32) & 4095;
