@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM4_ABI_VERSION 1
+#define PM4_ABI_VERSION 2
 
 /* error codes */
 #define PM4_OK 0
@@ -86,13 +86,14 @@ typedef struct pm4_term {
 } pm4_term_t;
 
 /* Device execution plan of a term that gathers from free variables: its elements regrouped by
- * gather target into length-sorted chunks dealt 32 at a time to the lanes of the chain's warp
- * (pymc4_b200/plan.py).  Data-dependent, hence run-time pools; the CPU oracle ignores plans. */
+ * gather target into length-sorted chunks dealt 32*team_warps at a time to the lanes of the
+ * chain's team of warps (pymc4_b200/plan.py).  Data-dependent, hence run-time pools; the CPU
+ * oracle ignores plans. */
 typedef struct pm4_plan {
   int32_t term;       /* the term it belongs to                        */
   int32_t n_gather;   /* gather loads sharing the plan's index array   */
-  int32_t n_part;     /* per-chain scratch reals per gather load       */
   int32_t width;      /* reals per record: 1, 2 or 4                   */
+  int32_t _pad;
   int64_t meta;       /* offset of the plan metadata in plani          */
   int64_t recs;       /* offset of the records in planf (in reals)     */
 } pm4_plan_t;
@@ -168,6 +169,12 @@ typedef struct pm4_ir {
   const double* planf;  /* plan records (permuted copies of observed data), multiple of 4 */
   int64_t n_plani;
   const int32_t* plani; /* plan metadata, multiple of 4                                   */
+  /* team layout: a chain is evaluated by `team_warps` warps; adjoint partial sums meet in a
+   * per-chain `part` array described by two tables at the end of plani (pymc4_b200/plan.py) */
+  int32_t team_warps;   /* 1, 2, 4, 8, 16 or 32; must match the kernel module              */
+  int32_t part_reals;   /* length of the per-chain part array (multiple of 4)              */
+  int64_t elem_off;     /* plani offset of elem_tab[32*team_warps*R]: first << 12 | count  */
+  int64_t spart_off;    /* plani offset of spart[n_scalar + 1]                             */
 } pm4_ir_t;
 
 typedef struct pm4_model pm4_model_t;
@@ -221,7 +228,7 @@ typedef struct pm4_hmc_cfg {
   double step_size;           /* initial epsilon                                           */
   uint64_t seed;
   pm4_adapt_cfg_t adapt;
-  int32_t warps_per_block;    /* 0 = library default                                       */
+  int32_t warps_per_block;    /* warps per thread block (a multiple of the model's team size); 0 = library default */
   int32_t chain_offset;       /* global index of chain 0 (RNG stream id) when chains are sharded */
 } pm4_hmc_cfg_t;
 

@@ -9,14 +9,20 @@ the chain state in registers.  One shared object is built per IR *structure*
 (``ModelIR.struct_hash``); data values, element counts, pool offsets and execution plans stay
 run-time arguments, so new observed data reuses the same module.
 
-Every term is emitted in one of four loop shapes:
-  uniform   n == 1 and nothing depends on the element index: evaluated once, on lane 0;
-  aligned   the term is element-wise over ONE free vector variable: lane l walks the elements it
+A chain is evaluated by a team of T warps (TL = 32 T lanes, ``ModelIR.team_warps``); lane ``tl`` of
+the team holds elements tl, tl + TL, ... of every D-vector.  Every term is emitted in one of four
+loop shapes:
+  uniform   n == 1 and nothing depends on the element index: evaluated once, on team lane 0;
+  aligned   the term is element-wise over ONE free vector variable: lane tl walks the elements it
             already holds in registers (value from ``x[r]``, adjoint into ``gr[r]``);
   planned   the term gathers from free variables through one index array: sliced-ELL walk over
             chunks of equal gather target (pymc4_b200/plan.py), gathered values and their
-            adjoints in registers, records from the staged shared-memory pool;
-  general   lane-strided loop over the elements (adjoints of gathers fall back to atomics).
+            adjoints in registers, records from the staged shared-memory pool, chunk sums parked
+            in the chain's ``part`` array for the lane that owns the gradient element;
+  general   team-strided loop over the elements (adjoints of gathers fall back to atomics on a
+            shared-memory gradient array, ``NEEDS_GX``).
+Adjoints of parameters read as chain-uniform scalars and the log-density itself are reduced with
+one packed warp butterfly per warp and parked in ``part`` too (one entry per warp).
 Normal terms with a chain-uniform scale use the factored form: only r = value - loc and the sums
 of r, r*x ..., r*r are formed per element; 1/scale^2 multiplies the sums once.
 
@@ -39,6 +45,8 @@ CSRC = os.path.join(_HERE, "csrc")
 CACHE_DIR = os.environ.get("PM4_KERNEL_CACHE", os.path.join(_HERE, "_kcache"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# threads per block of the persistent single-precision kernels (registers per thread = 65536 / MAXT)
+MAXT = int(os.environ.get("PM4_MAXT", "1024"))
 _build_lock = threading.Lock()
 
 _UNARY_FWD = {
@@ -121,9 +129,12 @@ class _ModuleGen:
         self.ir = ir
         self.has_f64 = has_f64
         self.D = ir.D
-        self.R = max(1, (ir.D + 31) // 32)
+        self.T = int(ir.team_warps)
+        self.TL = 32 * self.T
+        self.R = max(1, -(-ir.D // self.TL))
         self.lines: List[str] = []
-        self.scalar_pos: List[int] = []  # distinct scalar x positions used anywhere
+        self.scalar_pos: List[int] = list(ir.scalar_pos)  # scalar x positions, part-array order
+        self.needs_gx = False
 
     def emit(self, s: str = "", ind: int = 2):
         self.lines.append("  " * ind + s)
@@ -131,8 +142,8 @@ class _ModuleGen:
     # -- constrain -----------------------------------------------------------
     def gen_constrain(self) -> str:
         out = ["  template <typename real>",
-               "  static __device__ __forceinline__ void constrain(int r, int lane, real z, real& x, real& dxdz) {",
-               "    const int j = lane + 32 * r; (void)j;",
+               "  static __device__ __forceinline__ void constrain(int r, int tl, real z, real& x, real& dxdz) {",
+               "    const int j = tl + %d * r; (void)j;" % self.TL,
                "    x = z; dxdz = (real)1;"]
         for rv in self.ir.rvs:
             cond = "j >= %d && j < %d" % (rv.offset, rv.offset + rv.size)
@@ -148,7 +159,7 @@ class _ModuleGen:
     # -- terms ---------------------------------------------------------------
     def _sacc(self, pos: int) -> str:
         if pos not in self.scalar_pos:
-            self.scalar_pos.append(pos)
+            raise AssertionError("scalar position %d missing from ModelIR.scalar_pos" % pos)
         return "sacc_%d" % pos
 
     def gen_terms(self) -> str:
@@ -161,39 +172,36 @@ class _ModuleGen:
             if t.plan is not None:
                 plan_idx += 1
         head = ["  template <typename real, class CtxT>",
-                "  static __device__ __forceinline__ real terms(const real (&x)[R], real (&gr)[R], CtxT& c) {",
-                "    const int lane = c.lane; (void)lane;",
+                "  static __device__ __forceinline__ void terms(const real (&x)[R], real (&gr)[R], CtxT& c) {",
+                "    const int lane = c.lane, tl = c.tl; (void)lane; (void)tl;",
                 "    const pm4::ModelArgs<real>& A = c.A; (void)A;",
                 "    auto c_blob = [&](int op) -> int { return __ldg(A.op_blob + op); }; (void)c_blob;",
                 "    real lp = 0;"]
         for pos in self.scalar_pos:
             head.append("    const real sx_%d = c.xs[%d]; real sacc_%d = 0;" % (pos, pos, pos))
-        # one transposing butterfly reduces every scalar adjoint and the log-density together; the
-        # first lane of the group that ends up holding a scalar's total adds it to the gradient
-        n_acc = len(self.scalar_pos)
-        P = 1
-        while P < n_acc + 1:
-            P *= 2
-        if P > 32:
-            raise NotImplementedError("more than 31 distinct scalar parameters in one model")
-        per = 32 // P
-        tail = ["    __syncwarp();",
-                "    real red[%d];" % P]
+        # one transposing butterfly per warp reduces every scalar adjoint and the log-density together;
+        # the first lane of the group that ends up holding value k parks the warp's total in the part
+        # array (c.my_spart = spart[k] + warp), where the owner of the gradient element adds them up
+        n_acc, P = len(self.scalar_pos), self.P
+        tail = ["    real red[%d];" % P]
         for k, pos in enumerate(self.scalar_pos):
             tail.append("    red[%d] = sacc_%d;" % (k, pos))
         tail.append("    red[%d] = lp;" % n_acc)
         for k in range(n_acc + 1, P):
             tail.append("    red[%d] = 0;" % k)
         tail.append("    pm4::warp_sum_packed<%d, real>(red, lane);" % P)
-        if n_acc:
-            tail.append("    {")
-            tail.append("      constexpr int spos[%d] = {%s};" % (n_acc, ", ".join(str(p_) for p_ in self.scalar_pos)))
-            tail.append("      const int k = lane / %d;" % per)
-            tail.append("      if ((lane %% %d) == 0 && k < %d) c.gx[spos[k]] += red[0];" % (per, n_acc))
-            tail.append("    }")
-        tail.append("    lp = __shfl_sync(pm4::FULL, red[0], %d);" % (n_acc * per))
-        tail += ["    return lp;", "  }"]
+        tail.append("    if (c.my_spart >= 0) c.part[c.my_spart] = red[0];")
+        tail += ["  }"]
         return "\n".join(head + body + tail)
+
+    @property
+    def P(self) -> int:
+        P = 1
+        while P < len(self.scalar_pos) + 1:
+            P *= 2
+        if P > 32:
+            raise NotImplementedError("more than 31 distinct scalar parameters in one model")
+        return P
 
     def gen_one_term(self, k: int, t: I.Term, op0: int, plan_idx: int):
         ops, kind, tag = t.ops, t.kind, "t%d" % k
@@ -335,11 +343,13 @@ class _ModuleGen:
                     else:
                         E("c.gx[%d + %s] += %s;" % (o.base, idx, sink(g)), 5)
                         touched_gx[0] = True
+                        self.needs_gx = True
                 elif o.dst in gather_names:
                     E("%sa += %s;" % (gather_names[o.dst], g), 5)  # scaled by K when flushed
                 else:
                     E("atomicAdd(&c.gx[%d + A.datai[c_blob(%d) + %s]], %s);" % (o.base, op0 + o.dst, idx, sink(g)), 5)
                     touched_gx[0] = True
+                    self.needs_gx = True
 
             for o in reversed(ops):
                 if o.dst not in adj:
@@ -368,16 +378,16 @@ class _ModuleGen:
         # 3. the loop itself
         n_expr = str(t.n)
         if shape == "uniform":
-            E("if (lane == 0) {", 3)
+            E("if (tl == 0) {", 3)
             E("const int i = 0; (void)i;", 5)
             self.lines.extend(loop)
             E("}", 3)
         elif shape == "aligned":
             base = elem_bases[0]
-            r_lo, r_hi = base // 32, (base + t.n - 1) // 32
+            r_lo, r_hi = base // self.TL, (base + t.n - 1) // self.TL
             E("#pragma unroll", 3)
             E("for (int r = %d; r <= %d; ++r) {" % (r_lo, r_hi), 3)
-            E("const int i = lane + 32 * r - %d;" % base, 4)
+            E("const int i = tl + %d * r - %d;" % (self.TL, base), 4)
             E("if (i >= 0 && i < %d) {" % t.n, 4)
             self.lines.extend(loop)
             E("}", 4)
@@ -385,28 +395,32 @@ class _ModuleGen:
         elif shape == "planned":
             n_expr = "n_%s" % tag
             by_dst = {o.dst: o for o in ops}
+            TL = self.TL
+            n_g = len(gather_names)
+            SW = -(-(2 + n_g) // 4)
             rec_t = "typename pm4::Rec<real, %d>::type" % plan.width
             E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
             E("const int32_t* %s_pm = c.pi + __ldg(A.plan_off + %d);" % (tag, 2 * plan_idx), 3)
-            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d)) + lane;"
+            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d)) + tl;"
               % (rec_t, tag, rec_t, 2 * plan_idx + 1), 3)
-            E("const int4 %s_h0 = *reinterpret_cast<const int4*>(%s_pm);      // n_slices, n_split, n_part, o_slices" % (tag, tag), 3)
-            E("const int4 %s_h1 = *reinterpret_cast<const int4*>(%s_pm + 4);  // o_slots, o_split" % (tag, tag), 3)
-            E("const int4* %s_sl = reinterpret_cast<const int4*>(%s_pm + %s_h0.w);" % (tag, tag, tag), 3)
-            E("const int4* %s_st = reinterpret_cast<const int4*>(%s_pm + %s_h1.x) + lane;" % (tag, tag, tag), 3)
+            E("const int4 %s_h0 = *reinterpret_cast<const int4*>(%s_pm);      // n_slices, o_slices, o_slots, SW" % (tag, tag), 3)
+            E("const int4* %s_sl = reinterpret_cast<const int4*>(%s_pm + %s_h0.y);" % (tag, tag, tag), 3)
+            E("const int4* %s_st = reinterpret_cast<const int4*>(%s_pm + %s_h0.z) + tl * %d;" % (tag, tag, tag, SW), 3)
             E("for (int s = 0; s < %s_h0.x; ++s) {" % tag, 3)
             E("const int4 sl = %s_sl[s];        // rows all lanes walk, rows in the slice, first record row" % tag, 4)
-            E("const int4 st = %s_st[s * 32];   // gather target, chunk length, scratch index" % tag, 4)
+            E("const int4 st = %s_st[s * %d];   // gather target, chunk length, part index per gather op" % (tag, TL * SW), 4)
+            for w in range(1, SW):
+                E("const int4 st%d = %s_st[s * %d + %d];" % (w, tag, TL * SW, w), 4)
             E("const int tgt = st.x < 0 ? 0 : st.x, len = st.y;", 4)
             for dst, nm in gather_names.items():
                 E("const real %sv = c.xs[%d + tgt]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
-            E("const %s* rp = %s_pr + sl.z * 32;" % (rec_t, tag), 4)
+            E("const %s* rp = %s_pr + sl.z * %d;" % (rec_t, tag, TL), 4)
             E("int i0 = 0;", 4)
             E("for (; i0 < sl.x; i0 += 4) {   // rows every lane has: no mask", 4)
             E("#pragma unroll", 5)
             E("for (int u = 0; u < 4; ++u) {", 5)
             E("const int i = i0 + u; (void)i;", 5)
-            E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
+            E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
             self.lines.extend(loop)
             E("}", 5)
             E("}", 4)
@@ -414,52 +428,34 @@ class _ModuleGen:
             E("#pragma unroll", 5)
             E("for (int u = 0; u < 4; ++u) {", 5)
             E("const int i = i0 + u;", 5)
-            E("const %s %s_rec = rp[i * 32]; (void)%s_rec;" % (rec_t, tag, tag), 5)
+            E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
             E("const bool on = i < len;", 5)
             self.lines.extend(loop_masked)
             E("}", 5)
             E("}", 4)
-            E("if (st.x >= 0) {", 4)
-            E("if (st.z < 0) {  // the chunk is a whole group: this lane owns its gradient entries", 5)
-            for dst, nm in gather_names.items():
-                E("c.gx[%d + st.x] += %s;" % (by_dst[dst].base, sink("%sa" % nm)), 6)
-            E("} else {        // chunk of a split group: park the partial sums", 5)
+            E("if (st.x >= 0) {  // park the chunk's adjoint sums where the owner of the element collects them", 4)
+            fields = ["x", "y", "z", "w"]
             for j, (dst, nm) in enumerate(gather_names.items()):
-                E("c.part[%d * %s_h0.z + st.z] = %sa;" % (j, tag, nm), 6)
-            E("}", 5)
+                word, fld = divmod(2 + j, 4)
+                E("c.part[st%s.%s] = %s;" % ("" if word == 0 else str(word), fields[fld], sink("%sa" % nm)), 5)
             E("}", 4)
             E("}", 3)
-            E("__syncwarp();", 3)
-            E("{  // split groups: combine their chunks in a fixed order", 3)
-            E("const int4* %s_sg = reinterpret_cast<const int4*>(%s_pm + %s_h1.y);" % (tag, tag, tag), 4)
-            E("for (int q = lane; q < %s_h0.y; q += 32) {" % tag, 4)
-            E("const int4 sg = %s_sg[q];  // gather target, first scratch index, chunks" % tag, 5)
-            E("real %s;" % ", ".join("gs%d = 0" % j for j in range(len(gather_names))), 5)
-            E("for (int k2 = 0; k2 < sg.z; ++k2) {", 5)
-            for j in range(len(gather_names)):
-                E("gs%d += c.part[%d * %s_h0.z + sg.y + k2];" % (j, j, tag), 6)
-            E("}", 5)
-            for j, (dst, nm) in enumerate(gather_names.items()):
-                E("c.gx[%d + sg.x] += %s;" % (by_dst[dst].base, sink("gs%d" % j)), 5)
-            E("}", 4)
-            E("}", 3)
-            touched_gx[0] = True
         else:
             n_expr = "n_%s" % tag
             E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
-            E("for (int i = lane; i < %s; i += 32) {" % n_expr, 3)
+            E("for (int i = tl; i < %s; i += %d) {" % (n_expr, self.TL), 3)
             self.lines.extend(loop)
             E("}", 3)
 
         # 4. factored Normal: the sums enter the log-density and the scale adjoint once
         if normal_fast:
             E("lp += (real)-0.5 * %s * %s_S2;" % (K, tag), 3)
-            E("if (lane == 0) lp -= (real)%s * (pm4::K<real>::HALF_LOG_2PI + %s_log_s);" % (n_expr, tag), 3)
+            E("if (tl == 0) lp -= (real)%s * (pm4::K<real>::HALF_LOG_2PI + %s_log_s);" % (n_expr, tag), 3)
             if depends[scale_reg]:
                 uacc.setdefault(scale_reg, False)
                 decl = "" if uacc[scale_reg] else "real "
                 # d/d scale = sum (w^2 - 1) / scale = K * S2 / scale - n / scale
-                E("%s%s_ua%d %s %s * %s_S2 * %s_inv_s - (lane == 0 ? (real)%s * %s_inv_s : (real)0);"
+                E("%s%s_ua%d %s %s * %s_S2 * %s_inv_s - (tl == 0 ? (real)%s * %s_inv_s : (real)0);"
                   % (decl, tag, scale_reg, "+=" if uacc[scale_reg] else "=", K, tag, tag, n_expr, tag), 3)
                 uacc[scale_reg] = True
 
@@ -485,8 +481,6 @@ class _ModuleGen:
                 for reg, expr in tp.bwd(o, g):
                     if reg >= 0 and depends[reg]:
                         u_adj.setdefault(reg, []).append(expr)
-        if touched_gx[0]:
-            E("__syncwarp();", 3)
         E("}")
 
     # -- traced outputs --------------------------------------------------------
@@ -535,10 +529,16 @@ class _ModuleGen:
         parts = [
             "// generated by pymc4_b200/codegen.py -- do not edit.  IR structure hash %s" % ir.struct_hash_hex,
             "// free variables: " + ", ".join("%s[%d]@%d" % (rv.name, rv.size, rv.offset) for rv in ir.rvs),
+            "// team: %d warps per chain" % self.T,
             '#include "pm4_common.cuh"',
             "struct %s {" % name,
-            "  static constexpr int D = %d, R = %d, DP = %d, DET_ROW = %d, N_TERMS = %d, N_OPS = %d, N_PLANS = %d;"
-            % (self.D, self.R, 32 * self.R, ir.det_row, len(ir.terms), n_ops, len(ir.plans)),
+            "  static constexpr int D = %d, T = %d, R = %d, DP = %d, DS = %d, DET_ROW = %d, N_TERMS = %d, N_OPS = %d, N_PLANS = %d;"
+            % (self.D, self.T, self.R, self.TL * self.R, -(-self.D // 32) * 32, ir.det_row, len(ir.terms), n_ops,
+               len(ir.plans)),
+            "  static constexpr int N_ACC = %d, P = %d;  // scalar adjoints reduced with the log-density, packed width"
+            % (len(self.scalar_pos), self.P),
+            "  static constexpr bool NEEDS_GX = %s;  // some term scatters adjoints with atomics"
+            % ("true" if self.needs_gx else "false"),
             "  static constexpr unsigned long long HASH = 0x%sull;" % ir.struct_hash_hex,
             self.gen_constrain(),
             terms_src,
@@ -574,7 +574,7 @@ def generator_hash() -> str:
         for d in deps:
             with open(d, "rb") as f:
                 h.update(f.read())
-        h.update(" ".join(NVCC_FLAGS).encode())
+        h.update((" ".join(NVCC_FLAGS) + " MAXT=%d" % MAXT).encode())
         _gen_hash_cache = h.hexdigest()[:8]
     return _gen_hash_cache
 
@@ -613,7 +613,8 @@ def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verb
         with open(src_path, "w") as f:
             f.write(generate_source(ir, has_f64))
         tmp = tempfile.NamedTemporaryFile(prefix="pm4m_", suffix=".so", dir=CACHE_DIR, delete=False).name
-        cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags or []) + ["-I", CSRC, "-shared", "-o", tmp, src_path]
+        cmd = ([find_nvcc()] + NVCC_FLAGS + ["-DPM4_MAXT=%d" % MAXT] + list(extra_flags or [])
+               + ["-I", CSRC, "-shared", "-o", tmp, src_path])
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

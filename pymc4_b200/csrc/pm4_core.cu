@@ -3,7 +3,9 @@
 // Owns model handles (device copies of the constant pools + the dlopen'ed specialised kernel
 // module) and drives the sampler launches: bootstrap, per-transition lock-step launches while a
 // pooled step size is adapting (tfp DualAveragingStepSizeAdaptation with a scalar step size
-// couples all chains every burn-in transition), one persistent launch otherwise.
+// couples all chains every burn-in transition), otherwise a few persistent launches
+// ("phases"); between phases the chains are re-ordered longest-first by the leapfrogs they took in
+// the previous phase, so the persistent teams of the next launch start the expensive chains first.
 // Replaces the hand-off _BaseSampler._run_chains -> tfp.mcmc.sample_chain
 // (/root/reference/pymc4/mcmc/samplers.py:172-189).
 #include <cuda_runtime.h>
@@ -47,8 +49,6 @@ int fail(int code, const char* fmt, ...) {
     if (rc_ != 0) return fail(PM4_ECUDA, "%s: launch failed: %s", what, cudaGetErrorString((cudaError_t)rc_)); \
   } while (0)
 
-typedef int (*pm4m_export_eps_fn)(int dtype, const pm4_mod_run_t*, void* out, void* stream);
-
 }  // namespace
 
 struct pm4_model {
@@ -64,6 +64,9 @@ struct pm4_model {
   pm4m_run_fn f_nuts = nullptr, f_hmc = nullptr;
   pm4m_da_pooled_fn f_da = nullptr;
   pm4m_export_eps_fn f_eps = nullptr;
+  pm4m_scratch_bytes_fn f_scratch = nullptr;
+  pm4m_lpt_order_fn f_order = nullptr;
+  int elem_off = 0, spart_off = 0;
   float* d_f32 = nullptr;
   double* d_f64 = nullptr;
   int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
@@ -86,9 +89,11 @@ struct pm4_model {
     a.n_planf = (int32_t)n_planf;
     a.n_plani = (int32_t)n_plani;
     a.part_reals = part_reals;
+    a.elem_off = elem_off;
+    a.spart_off = spart_off;
     // stage the plan pools in shared memory when they leave room for the per-chain state
     const size_t pool_bytes = (size_t)n_planf * (dtype == PM4_F64 ? 8 : 4) + (size_t)n_plani * 4;
-    a.stage = (n_plans > 0 && pool_bytes <= 96 * 1024) ? 1 : 0;
+    a.stage = (pool_bytes <= 96 * 1024) ? 1 : 0;
     return a;
   }
 };
@@ -104,17 +109,19 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   }
   if (ni) CU(cudaMemcpy(m->d_plani, ir->plani, sizeof(int32_t) * (size_t)ni, cudaMemcpyHostToDevice));
   std::vector<int32_t> off((size_t)(2 * ir->n_plans) + 2);
-  int part = 0;
   for (int k = 0; k < ir->n_plans; ++k) {
     const pm4_plan_t& pl = ir->plans[k];
     if (pl.meta < 0 || pl.meta >= ni || pl.recs < 0 || pl.recs > nf) return fail(PM4_EINVAL, "plan %d points outside the plan pools", k);
     off[(size_t)(2 * k)] = (int32_t)pl.meta;
     off[(size_t)(2 * k + 1)] = (int32_t)pl.recs;
-    const int need = pl.n_gather * pl.n_part;
-    if (need > part) part = need;
   }
   CU(cudaMemcpy(m->d_plan_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
-  m->part_reals = part;
+  if (ir->team_warps != m->info.T) return fail(PM4_EINVAL, "IR is laid out for teams of %d warps, the kernel module for %d", ir->team_warps, m->info.T);
+  if (ir->elem_off < 0 || ir->elem_off + m->info.DP > ni || ir->spart_off < 0 || ir->spart_off >= ni || ir->part_reals <= 0)
+    return fail(PM4_EINVAL, "part-array tables point outside the plan metadata pool");
+  m->part_reals = ir->part_reals;
+  m->elem_off = (int)ir->elem_off;
+  m->spart_off = (int)ir->spart_off;
   return PM4_OK;
 }
 
@@ -165,7 +172,10 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
   m->f_hmc = (pm4m_run_fn)dlsym(m->module, "pm4m_hmc");
   m->f_da = (pm4m_da_pooled_fn)dlsym(m->module, "pm4m_da_pooled");
   m->f_eps = (pm4m_export_eps_fn)dlsym(m->module, "pm4m_export_eps");
-  if (!f_info || !m->f_logp || !m->f_dets || !m->f_init || !m->f_nuts || !m->f_hmc || !m->f_da || !m->f_eps) {
+  m->f_scratch = (pm4m_scratch_bytes_fn)dlsym(m->module, "pm4m_scratch_bytes");
+  m->f_order = (pm4m_lpt_order_fn)dlsym(m->module, "pm4m_lpt_order");
+  if (!f_info || !m->f_logp || !m->f_dets || !m->f_init || !m->f_nuts || !m->f_hmc || !m->f_da || !m->f_eps ||
+      !m->f_scratch || !m->f_order) {
     int rc = fail(PM4_ENOMOD, "kernel module %s lacks a required entry point", module_path);
     pm4_model_destroy(m);
     return rc;
@@ -281,8 +291,10 @@ static size_t real_size(int dtype) { return dtype == PM4_F64 ? 8 : 4; }
 extern "C" int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth) {
   if (!m) return PM4_EINVAL;
   const size_t rs = real_size(dtype), DP = (size_t)m->info.DP;
-  const size_t slots = (size_t)PM4_SLOT_MEM + 2 * (size_t)(max_tree_depth + 1);
-  return (int64_t)(((size_t)C * DP * (2 + slots) + (size_t)C * 6) * rs);
+  pm4_mod_args_t a = m->args(dtype);
+  const int64_t tree = m->f_scratch(dtype, &a, C, 0, max_tree_depth);  // 0 when the tree state fits on chip
+  if (tree < 0) return tree;
+  return (int64_t)(((size_t)C * DP * 2 + (size_t)C * 6) * rs + (size_t)C * 8 + 16) + tree;
 }
 
 namespace {
@@ -315,10 +327,13 @@ int fill_adapt(pm4_mod_run_t& r, const pm4_adapt_cfg_t& a) {
 }
 
 // run T transitions: lock-step single-transition launches while a pooled step size still moves
-// (transitions 0..num_adapt), then one launch for the rest
-int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, cudaStream_t st) {
+// (transitions 0..num_adapt), then a few persistent launches for the rest.  NUTS chains differ a lot
+// in cost (per-chain step sizes): after each phase the chains are ranked by the leapfrogs they took
+// and the next launch hands them out longest-first (`order_buf`: int32[C], `r.launch_leaps` set).
+int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, int32_t* order_buf, cudaStream_t st) {
   pm4m_run_fn f = nuts ? m->f_nuts : m->f_hmc;
   int t = 0;
+  r.order = nullptr;
   if (r.adapt_enabled && r.adapt_pooled) {
     const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
     for (; t < coupled; ++t) {
@@ -328,10 +343,26 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
       MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");
     }
   }
-  if (t < T) {
+  // phase boundaries: a short first phase (step sizes settle within ~20 transitions), the end of
+  // adaptation, the end of the run
+  std::vector<int> ends;
+  const bool phased = nuts && order_buf && r.launch_leaps;
+  if (phased) {
+    const int freeze = r.adapt_enabled ? r.num_adapt + 1 : 0;
+    if (t + 20 < T - 20) ends.push_back(t + 20);
+    if (freeze > (ends.empty() ? t : ends.back()) + 10 && freeze < T - 10) ends.push_back(freeze);
+  }
+  ends.push_back(T);
+  for (size_t k = 0; k < ends.size(); ++k) {
+    if (ends[k] <= t) continue;
     r.t_begin = t;
-    r.t_count = T - t;
+    r.t_count = ends[k] - t;
     MOD(f(dtype, &r, wpb, st), nuts ? "nuts" : "hmc");
+    t = ends[k];
+    if (phased && t < T) {
+      MOD(m->f_order(r.C, r.launch_leaps, order_buf, st), "longest-first chain order");
+      r.order = order_buf;
+    }
   }
   return PM4_OK;
 }
@@ -351,7 +382,6 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
   const int T = cfg->num_burnin + cfg->num_results;
-  const size_t slots = (size_t)PM4_SLOT_MEM + 2 * (size_t)(cfg->max_tree_depth + 1);
 
   pm4_mod_run_t r;
   memset(&r, 0, sizeof r);
@@ -368,14 +398,22 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   if ((rc = buf.get(&r.lp, C * rs))) return rc;
   if ((rc = buf.get(&r.da, C * 4 * rs))) return rc;
   if ((rc = buf.get(&r.accept, C * rs))) return rc;
-  if ((rc = buf.get(&r.scratch, slots * C * DP * rs))) return rc;
+  const int64_t tree_bytes = m->f_scratch(dtype, &r.A, cfg->C, cfg->warps_per_block, cfg->max_tree_depth);
+  if (tree_bytes < 0) return fail(PM4_EINVAL, "kernel module cannot size its tree scratch");
+  if (tree_bytes > 0 && (rc = buf.get(&r.scratch, (size_t)tree_bytes))) return rc;
+  void *queue = nullptr, *order = nullptr, *leaps = nullptr;
+  if ((rc = buf.get(&queue, 16))) return rc;
+  if ((rc = buf.get(&order, C * sizeof(int32_t)))) return rc;
+  if ((rc = buf.get(&leaps, C * sizeof(int32_t)))) return rc;
+  r.queue = (int32_t*)queue;
+  r.launch_leaps = (int32_t*)leaps;
   r.step_scale = step_scale_dev; r.momenta = momenta_dev;
   r.states = states_dev; r.lp_out = lp_dev; r.leapfrogs = leapfrogs_dev; r.diverging = diverging_dev;
   r.energy = energy_dev; r.log_accept = log_accept_dev; r.depth = depth_dev;
   r.total_leapfrogs = total_leapfrogs_dev;
 
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
-  if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, st))) return rc;
+  if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, (int32_t*)order, st))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   return PM4_OK;
 }
@@ -409,12 +447,15 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   if ((rc = buf.get(&r.lp, C * rs))) return rc;
   if ((rc = buf.get(&r.da, C * 4 * rs))) return rc;
   if ((rc = buf.get(&r.accept, C * rs))) return rc;
+  void* queue = nullptr;
+  if ((rc = buf.get(&queue, 16))) return rc;
+  r.queue = (int32_t*)queue;
   r.step_scale = step_scale_dev; r.momenta = momenta_dev; r.uniforms = uniforms_dev;
   r.states = states_dev; r.lp_out = lp_dev; r.log_accept = log_accept_dev; r.diverging = accepted_dev;
   r.traj = traj_dev;
 
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
-  if ((rc = drive(m, dtype, r, false, cfg->warps_per_block, T, st))) return rc;
+  if ((rc = drive(m, dtype, r, false, cfg->warps_per_block, T, nullptr, st))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   return PM4_OK;
 }

@@ -1,10 +1,14 @@
 // pm4_kernels.cuh -- the sampler kernels, templated on a generated `Model` and on the arithmetic
-// type.  One WARP owns one chain: every D-vector of the chain (position, momentum, gradient,
-// trajectory momentum sums) is spread over the 32 lanes, lane l holding elements l, l+32, ...
-// in registers (M::R per vector).  Reductions over dimensions / observations are xor-butterfly
-// warp shuffles, so every lane sees bit-identical sums and all sampler decisions are
-// warp-uniform.  Observed-data records and execution plans of gather terms are copied once per
-// CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier).
+// type.  One TEAM of T warps owns one chain (T = Model::T): every D-vector of the chain (position,
+// momentum, gradient, trajectory momentum sums) is spread over the TL = 32 T lanes of the team, lane
+// tl holding elements tl, tl + TL, ... in registers (M::R per vector).  Reductions over dimensions /
+// observations are a packed transposing warp butterfly followed by one exchange through shared
+// memory, so every lane of the team sees bit-identical sums and all sampler decisions are
+// team-uniform.  The whole NUTS tree state of the chain (far trajectory end, candidates, U-turn
+// checkpoints) lives in the team's shared memory; observed-data records and execution plans of
+// gather terms are copied once per CTA into shared memory with a TMA bulk copy (cp.async.bulk +
+// mbarrier).  Thread blocks are persistent (one per SM): a team that finishes a chain takes the next
+// one from a global queue, longest expected chains first.
 //
 // What this replaces in the reference: the body of tfp.mcmc.sample_chain that
 // _BaseSampler._run_chains hands control to (/root/reference/pymc4/mcmc/samplers.py:172-189):
@@ -21,27 +25,30 @@ namespace pm4 {
 // shared-memory layout of one CTA:
 //   [0, 16)                  mbarrier of the bulk copy
 //   [16, 16 + pool bytes)    plan records (reals) then plan metadata (ints), when staged
-//   then per warp            xs[DP] | gx[DP] | part[part_reals]
+//   then per team            xs[DP] | gx[DP] (NEEDS_GX) | part[part_reals] | red[8 T] | ctl[4] | scratch[n_slots DS]
 // ------------------------------------------------------------------------------------------
 template <typename real> __host__ __device__ inline size_t pool_bytes(const ModelArgs<real>& A) {
   return A.stage ? 16 + (size_t)A.n_planf * sizeof(real) + (size_t)A.n_plani * sizeof(int32_t) : 0;
 }
-template <typename real> __host__ __device__ inline size_t warp_reals(const ModelArgs<real>& A, int DP) {
-  return 2 * (size_t)DP + (((size_t)A.part_reals + 3) & ~(size_t)3);
-}
-template <typename real> __host__ inline size_t cta_smem_bytes(const ModelArgs<real>& A, int DP, int wpb) {
-  return pool_bytes(A) + (size_t)wpb * warp_reals(A, DP) * sizeof(real);
+// reals of one team without tree scratch
+template <class M, typename real> __host__ __device__ inline size_t team_base_reals(const ModelArgs<real>& A) {
+  return (size_t)M::DP * (M::NEEDS_GX ? 2 : 1) + (((size_t)A.part_reals + 3) & ~(size_t)3) + 8 * (size_t)M::T + 4;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Build the per-warp context; when STAGED, thread 0 issues the TMA bulk copies of the plan pools
+// Build the per-lane context; when STAGED, thread 0 issues the TMA bulk copies of the plan pools
 // and every thread of the CTA waits on the mbarrier.  Must be called by ALL threads of the CTA.
-template <typename real, bool STAGED>
-__device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned char* smem_raw, int DP) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// `team_reals` = reals per team including tree scratch (the host computed the same number).
+template <class M, typename real, bool STAGED>
+__device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned char* smem_raw, int team_reals) {
+  constexpr int T = M::T, TL = 32 * T;
   Ctx<real> c;
-  c.lane = lane;
+  c.tl = threadIdx.x % TL;
+  c.lane = threadIdx.x & 31;
+  c.warp = c.tl >> 5;
+  const int tix = threadIdx.x / TL;
+  c.bar = tix;  // barrier 0 is used CTA-wide only before the teams start
   c.A = A;
   size_t base = 0;
   if (STAGED) {
@@ -82,38 +89,61 @@ __device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned
     c.pf = A.planf;
     c.pi = A.plani;
   }
-  real* w = reinterpret_cast<real*>(smem_raw + base) + (size_t)warp * warp_reals(A, DP);
+  real* w = reinterpret_cast<real*>(smem_raw + base) + (size_t)tix * (size_t)team_reals;
   c.xs = w;
-  c.gx = w + DP;
-  c.part = w + 2 * DP;
+  w += M::DP;
+  c.gx = w;
+  if (M::NEEDS_GX) w += M::DP;
+  c.part = w;
+  w += (A.part_reals + 3) & ~3;
+  c.red = w;
+  w += 8 * T;
+  c.ctl = reinterpret_cast<int32_t*>(w);
+  w += 4;
+  c.scr = w;
+  // the lane that ends up holding packed-reduction value k parks it at spart[k] + warp
+  constexpr int per = 32 / M::P;
+  const int k = c.lane / per;
+  c.my_spart = ((c.lane % per) == 0 && k <= M::N_ACC) ? c.pi[A.spart_off + k] + c.warp : -1;
+  c.lp_first = c.pi[A.spart_off + M::N_ACC];
   return c;
 }
 
+// gradient-element ownership of this lane: elem_tab entries of elements tl, tl + TL, ...
+template <class M, typename real> __device__ __forceinline__ void load_own(const Ctx<real>& c, int (&own)[M::R]) {
+#pragma unroll
+  for (int r = 0; r < M::R; ++r) own[r] = c.pi[c.A.elem_off + c.tl + 32 * M::T * r];
+}
+
 // ------------------------------------------------------------------------------------------
-// joint log-density + gradient in unconstrained space for the chain owned by this warp.
-// `th`/`g` are the lane-distributed theta and gradient; returns the (warp-uniform) log-density.
+// joint log-density + gradient in unconstrained space for the chain owned by this team.
+// `th`/`g` are the lane-distributed theta and gradient; returns the (team-uniform) log-density.
+// Two team barriers: constrained values visible -> terms; partial sums parked -> owners add up.
 // ------------------------------------------------------------------------------------------
 template <class M, typename real>
-__device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R], Ctx<real>& c) {
-  constexpr int R = M::R, D = M::D;
+__device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R], Ctx<real>& c,
+                                          const int (&own)[M::R]) {
+  constexpr int R = M::R, T = M::T, TL = 32 * T;
   real x[R], dxdz[R], gr[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int j = c.lane + 32 * r;
-    M::template constrain<real>(r, c.lane, th[r], x[r], dxdz[r]);
+    const int j = c.tl + TL * r;
+    M::template constrain<real>(r, c.tl, th[r], x[r], dxdz[r]);
     gr[r] = 0;
-    if (j < D) {
-      c.xs[j] = x[r];
-      c.gx[j] = 0;
-    }
+    c.xs[j] = x[r];
+    if (M::NEEDS_GX) c.gx[j] = 0;
   }
-  __syncwarp();
-  const real lp = M::template terms<real>(x, gr, c);  // already summed over the warp
-  __syncwarp();
+  team_sync<T>(c.bar);
+  M::template terms<real>(x, gr, c);  // parks log-density and adjoint partial sums in c.part
+  team_sync<T>(c.bar);
+  const real lp = sum_consecutive<T, real>(c.part + c.lp_first);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int j = c.lane + 32 * r;
-    g[r] = (j < D) ? (gr[r] + c.gx[j]) * dxdz[r] : (real)0;
+    const int first = own[r] >> ELEM_CNT_BITS, cnt = own[r] & ((1 << ELEM_CNT_BITS) - 1);
+    real s = gr[r];
+    for (int k = 0; k < cnt; ++k) s += c.part[first + k];
+    if (M::NEEDS_GX) s += c.gx[c.tl + TL * r];
+    g[r] = s * dxdz[r];
   }
   return lp;
 }
@@ -122,26 +152,29 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
 // parity kernel (a): log-density and gradient for C independent states
 // ------------------------------------------------------------------------------------------
 template <class M, typename real, bool STAGED>
-__global__ void __launch_bounds__(128) logp_grad_kernel(ModelArgs<real> A, int C, const real* __restrict__ theta,
+__global__ void __launch_bounds__(256) logp_grad_kernel(ModelArgs<real> A, int C, int team_reals,
+                                                        const real* __restrict__ theta,
                                                         real* __restrict__ lp_out, real* __restrict__ grad_out) {
-  constexpr int R = M::R, D = M::D, DP = M::DP;
+  constexpr int R = M::R, D = M::D, T = M::T, TL = 32 * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx<real> c = make_ctx<real, STAGED>(A, smem_raw, DP);
-  const int lane = c.lane;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  Ctx<real> c = make_ctx<M, real, STAGED>(A, smem_raw, team_reals);
+  const int tl = c.tl;
+  const int chain = blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL;
   if (chain >= C) return;
+  int own[R];
+  load_own<M, real>(c, own);
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int j = lane + 32 * r;
+    const int j = tl + TL * r;
     th[r] = (j < D) ? theta[(size_t)chain * D + j] : (real)0;
   }
-  const real lp = logp_grad<M, real>(th, g, c);
-  if (lane == 0) lp_out[chain] = lp;
+  const real lp = logp_grad<M, real>(th, g, c, own);
+  if (tl == 0) lp_out[chain] = lp;
   if (grad_out) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int j = lane + 32 * r;
+      const int j = tl + TL * r;
       if (j < D) grad_out[(size_t)chain * D + j] = g[r];
     }
   }
@@ -163,6 +196,7 @@ template <typename real> struct RunParams {
   ModelArgs<real> A;
   int C, t_begin, t_count, B, S, max_depth, num_leapfrog, chain_offset;
   int adapt_enabled, adapt_pooled, num_adapt;
+  int team_reals, n_slots;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -174,6 +208,9 @@ template <typename real> struct RunParams {
   const real* momenta;
   const real* uniforms;
   real* scratch;
+  int32_t* queue;
+  const int32_t* order;
+  int32_t* launch_leaps;
   real* states;
   real* lp_out;
   int32_t* leapfrogs;
@@ -191,6 +228,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.C = r.C; p.t_begin = r.t_begin; p.t_count = r.t_count; p.B = r.B; p.S = r.S;
   p.max_depth = r.max_depth; p.num_leapfrog = r.num_leapfrog; p.chain_offset = r.chain_offset;
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
+  p.team_reals = 0; p.n_slots = 0;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -198,6 +236,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.accept = (real*)r.accept;
   p.step_scale = (const real*)r.step_scale; p.momenta = (const real*)r.momenta;
   p.uniforms = (const real*)r.uniforms; p.scratch = (real*)r.scratch;
+  p.queue = r.queue; p.order = r.order; p.launch_leaps = r.launch_leaps;
   p.states = (real*)r.states; p.lp_out = (real*)r.lp_out; p.leapfrogs = r.leapfrogs;
   p.diverging = r.diverging; p.energy = (real*)r.energy; p.log_accept = (real*)r.log_accept;
   p.depth = r.depth; p.total_leapfrogs = r.total_leapfrogs; p.traj = (real*)r.traj;
@@ -253,28 +292,51 @@ template <typename real> __global__ void export_eps_kernel(RunParams<real> a, re
   if (c < a.C) out[c] = a.da[a.adapt_pooled ? 0 : (size_t)c * 4];
 }
 
+// Scheduling order for the next launch: chains sorted by the leapfrogs they took during the last one,
+// longest first (ties by chain index), so that the persistent teams start the expensive chains first.
+// Rank by counting: O(C^2 / threads), deterministic.
+static __global__ void __launch_bounds__(256) lpt_order_kernel(int C, const int32_t* __restrict__ work, int32_t* __restrict__ order) {
+  __shared__ int32_t tile[1024];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t wi = i < C ? work[i] : 0;
+  int rank = 0;
+  for (int base = 0; base < C; base += 1024) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < 1024; k += blockDim.x) tile[k] = base + k < C ? work[base + k] : -1;
+    __syncthreads();
+    const int n = C - base < 1024 ? C - base : 1024;
+    for (int k = 0; k < n; ++k) {
+      const int32_t wk = tile[k];
+      rank += (wk > wi) || (wk == wi && base + k < i);
+    }
+  }
+  if (i < C) order[rank] = i;
+}
+
 // initial log-density / gradient of every chain (tfp bootstrap_results) + dual-averaging init
 template <class M, typename real, bool STAGED>
-__global__ void __launch_bounds__(128) init_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
-  constexpr int R = M::R, D = M::D, DP = M::DP;
+__global__ void __launch_bounds__(256) init_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
+  constexpr int R = M::R, D = M::D, DP = M::DP, T = M::T, TL = 32 * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
-  const int lane = c.lane;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
+  const int tl = c.tl;
+  const int chain = blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL;
   if (chain >= a.C) return;
+  int own[R];
+  load_own<M, real>(c, own);
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int j = lane + 32 * r;
+    const int j = tl + TL * r;
     th[r] = (j < D) ? theta0[(size_t)chain * D + j] : (real)0;
   }
-  const real lp = logp_grad<M, real>(th, g, c);
+  const real lp = logp_grad<M, real>(th, g, c, own);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    a.th[(size_t)chain * DP + lane + 32 * r] = th[r];
-    a.gr[(size_t)chain * DP + lane + 32 * r] = g[r];
+    a.th[(size_t)chain * DP + tl + TL * r] = th[r];
+    a.gr[(size_t)chain * DP + tl + TL * r] = g[r];
   }
-  if (lane == 0) {
+  if (tl == 0) {
     a.lp[chain] = lp;
     if (a.total_leapfrogs) a.total_leapfrogs[chain] = 0;
     if (!a.adapt_pooled || chain == 0) {
@@ -284,282 +346,318 @@ __global__ void __launch_bounds__(128) init_kernel(RunParams<real> a, const real
   }
 }
 
-// momentum of this chain at transition t: Philox block (q*32 + lane) feeds registers 4q..4q+3
+// momentum of this chain at transition t.  Element j = lane' + 32 r' (lane' = j % 32) is output
+// r' % 4 of Philox block ((r' / 4) * 32 + lane'): the stream does not depend on the team size.
 template <class M, typename real>
-__device__ __forceinline__ void draw_momentum(const RunParams<real>& a, int chain, int t, int lane, real (&p)[M::R]) {
-  constexpr int R = M::R, D = M::D;
+__device__ __forceinline__ void draw_momentum(const RunParams<real>& a, int chain, int t, int tl, real (&p)[M::R]) {
+  constexpr int R = M::R, D = M::D, TL = 32 * M::T;
   if (a.momenta) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int j = lane + 32 * r;
+      const int j = tl + TL * r;
       p[r] = (j < D) ? a.momenta[((size_t)t * a.C + chain) * D + j] : (real)0;
     }
     return;
   }
 #pragma unroll
-  for (int q = 0; q < (R + 3) / 4; ++q) {
-    const U4 u = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, (uint32_t)(q * 32 + lane),
+  for (int r = 0; r < R; ++r) {
+    const int j = tl + TL * r;
+    const int ro = j >> 5, lo = j & 31;
+    const U4 u = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, (uint32_t)((ro >> 2) * 32 + lo),
                                RNG_MOMENTUM, a.seed_lo, a.seed_hi);
-    real n[4];
-    box_muller<real>(u.x, u.y, n[0], n[1]);
-    box_muller<real>(u.z, u.w, n[2], n[3]);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = 4 * q + e;
-      if (r < R) p[r] = (lane + 32 * r < D) ? n[e] : (real)0;
-    }
+    real n0, n1;
+    if (ro & 2) box_muller<real>(u.z, u.w, n0, n1);
+    else box_muller<real>(u.x, u.y, n0, n1);
+    p[r] = (j < D) ? ((ro & 1) ? n1 : n0) : (real)0;
   }
 }
 
 // one leapfrog step: tfp SimpleLeapfrogIntegrator with num_steps = 1:
-// half kick, drift, gradient, full kick, half un-kick.  es[r] = eps * per-dim scale, sgn = +-1.
+// half kick, drift, gradient, full kick, half un-kick.  es[r] = signed eps * per-dim scale.
 template <class M, typename real>
 __device__ __forceinline__ real leapfrog(real (&th)[M::R], real (&p)[M::R], real (&g)[M::R],
-                                         const real (&es)[M::R], real sgn, Ctx<real>& c) {
+                                         const real (&es)[M::R], Ctx<real>& c, const int (&own)[M::R]) {
 #pragma unroll
   for (int r = 0; r < M::R; ++r) {
-    const real e = sgn * es[r];
-    p[r] = p[r] + ((real)0.5 * e) * g[r];
-    th[r] = th[r] + e * p[r];
+    p[r] = p[r] + ((real)0.5 * es[r]) * g[r];
+    th[r] = th[r] + es[r] * p[r];
   }
-  const real lp = logp_grad<M, real>(th, g, c);
+  const real lp = logp_grad<M, real>(th, g, c, own);
 #pragma unroll
   for (int r = 0; r < M::R; ++r) {
-    const real e = sgn * es[r];
-    p[r] = p[r] + e * g[r];
-    p[r] = p[r] - ((real)0.5 * e) * g[r];
+    p[r] = p[r] + es[r] * g[r];
+    p[r] = p[r] - ((real)0.5 * es[r]) * g[r];
   }
   return lp;
 }
 
-template <int R, typename real> __device__ __forceinline__ real dot(const real (&a)[R], const real (&b)[R]) {
-  real s = 0;
-#pragma unroll
-  for (int r = 0; r < R; ++r) s += a[r] * b[r];
-  return warp_sum(s);
+// next chain for this team from the global queue (-1: none left)
+template <int T, typename real> __device__ __forceinline__ int next_chain(const RunParams<real>& a, const Ctx<real>& c) {
+  int qi = 0;
+  if constexpr (T == 1) {
+    if (c.lane == 0) qi = atomicAdd(a.queue, 1);
+    qi = __shfl_sync(FULL, qi, 0);
+  } else {
+    if (c.tl == 0) c.ctl[0] = atomicAdd(a.queue, 1);
+    team_sync<T>(c.bar);
+    qi = c.ctl[0];
+    team_sync<T>(c.bar);
+  }
+  if (qi >= a.C) return -1;
+  return a.order ? a.order[qi] : qi;
 }
-
-// tree scratch lives in global memory (L2-resident: every access is one coalesced line per register)
-template <typename real> __device__ __forceinline__ real ldq(const real* p) { return __ldcg(p); }
-template <typename real> __device__ __forceinline__ void stq(real* p, real v) { __stcg(p, v); }
 
 // ------------------------------------------------------------------------------------------
 // NUTS: tfp NoUTurnSampler.one_step -> _loop_tree_doubling -> _build_sub_tree ->
-// _loop_build_sub_tree in per-chain form, t_count transitions per launch.
+// _loop_build_sub_tree in per-chain form, t_count transitions per chain per launch.
 // ------------------------------------------------------------------------------------------
-template <class M, typename real, int MAXT, bool STAGED>
+template <class M, typename real, int MAXT, bool STAGED, bool SCR_SMEM>
 __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
-  constexpr int R = M::R, D = M::D, DP = M::DP;
+  constexpr int R = M::R, D = M::D, DP = M::DP, DS = M::DS, T = M::T, TL = 32 * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
-  const int lane = c.lane;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chain >= a.C) return;
+  Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
+  const int tl = c.tl, lane = c.lane;
   const real NEG_INF = -m_inf<real>();
   const size_t C = (size_t)a.C;
-  const uint32_t rng_chain = (uint32_t)(a.chain_offset + chain);
-  auto slot = [&](int s) -> real* { return a.scratch + ((size_t)s * C + chain) * DP + lane; };
+  real* const scr = SCR_SMEM ? c.scr
+                             : a.scratch + ((size_t)blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL) * (size_t)a.n_slots * DS;
   const int MEM_P = PM4_SLOT_MEM, MEM_RHO = PM4_SLOT_MEM + a.max_depth + 1;
+  // element tl + TL r exists for every lane when TL (r + 1) <= D, else only for the first lanes
+  auto in = [&](int r) -> bool { return (TL * (r + 1) <= D) || (tl + TL * r < D); };
+  auto ldv = [&](int s, int r) -> real { return in(r) ? scr[s * DS + tl + TL * r] : (real)0; };
+  auto stv = [&](int s, int r, real v) { if (in(r)) scr[s * DS + tl + TL * r] = v; };
 
-  // chain state carried across transitions
-  real cth[R], cg[R], scale[R];
-  real clp = a.lp[chain];
+  int own[R];
+  load_own<M, real>(c, own);
+  real sc[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = lane + 32 * r;
-    cth[r] = a.th[(size_t)chain * DP + j];
-    cg[r] = a.gr[(size_t)chain * DP + j];
-    scale[r] = (a.step_scale && j < D) ? a.step_scale[j] : (real)1;
-  }
-  DualAvg<real> da;
-  da.load(a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4));
-  long long total_leaps = 0;
+  for (int r = 0; r < R; ++r) sc[r] = (a.step_scale && tl + TL * r < D) ? a.step_scale[tl + TL * r] : (real)1;
+  int rb = 0;  // which half of c.red the next team reduction uses
 
-  for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
-    real es[R], th[R], p[R], g[R], rho[R], rho_sub[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) es[r] = da.eps * scale[r];
-    draw_momentum<M, real>(a, chain, t, lane, p);
-    const real H0 = clp - (real)0.5 * dot<R, real>(p, p);
-
-    // merge uniforms (one per doubling, lane d holds depth d) and the direction bits
-    const U4 um = philox4x32_10(rng_chain, (uint32_t)t, (uint32_t)lane, RNG_MERGE, a.seed_lo, a.seed_hi);
-    const U4 ud = philox4x32_10(rng_chain, (uint32_t)t, 0u, RNG_DIRECTION, a.seed_lo, a.seed_hi);
-
-    // both trajectory ends and the candidate start at the current point
+  for (;;) {
+    const int chain = next_chain<T, real>(a, c);
+    if (chain < 0) break;
+    const uint32_t rng_chain = (uint32_t)(a.chain_offset + chain);
+    // the chain's current point lives in the candidate slots between transitions
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      th[r] = cth[r]; g[r] = cg[r]; rho[r] = p[r];
-      stq(slot(PM4_SLOT_OTH_TH) + 32 * r, cth[r]);
-      stq(slot(PM4_SLOT_OTH_P) + 32 * r, p[r]);
-      stq(slot(PM4_SLOT_OTH_G) + 32 * r, cg[r]);
-      stq(slot(PM4_SLOT_CAND_TH) + 32 * r, cth[r]);
-      stq(slot(PM4_SLOT_CAND_G) + 32 * r, cg[r]);
+      stv(PM4_SLOT_CAND_TH, r, a.th[(size_t)chain * DP + tl + TL * r]);
+      stv(PM4_SLOT_CAND_G, r, a.gr[(size_t)chain * DP + tl + TL * r]);
     }
-    real cur_lp = clp, oth_lp = clp;
-    int cur_is_right = 1;
-    real cand_lp = clp, cand_energy = H0, w = 0, ediff_sum = 0;
-    int nleap = 0, depth = 0;
-    bool cont = true, not_div = true;
+    real clp = a.lp[chain];
+    DualAvg<real> da;
+    da.load(a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4));
+    int launch_leaps = 0;
 
-    while (depth < a.max_depth && cont) {
-      const int dir = (int)((ud.x >> depth) & 1u);
-      if (dir != cur_is_right) {  // extend the other end: swap the register-resident end with the stored one
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          real v;
-          v = ldq(slot(PM4_SLOT_OTH_TH) + 32 * r); stq(slot(PM4_SLOT_OTH_TH) + 32 * r, th[r]); th[r] = v;
-          v = ldq(slot(PM4_SLOT_OTH_P) + 32 * r); stq(slot(PM4_SLOT_OTH_P) + 32 * r, p[r]); p[r] = v;
-          v = ldq(slot(PM4_SLOT_OTH_G) + 32 * r); stq(slot(PM4_SLOT_OTH_G) + 32 * r, g[r]); g[r] = v;
-        }
-        const real tl = cur_lp; cur_lp = oth_lp; oth_lp = tl;
-        cur_is_right = dir;
-      }
-      const real sgn = dir ? (real)1 : (real)-1;
-      const int nsteps = 1 << depth;
-#pragma unroll
-      for (int r = 0; r < R; ++r) rho_sub[r] = 0;
-      real w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
-      bool cont_sub = true;
-      int sub_leaps = 0;
-      U4 ul{0u, 0u, 0u, 0u};
-
-      for (int i = 0; i < nsteps && cont_sub; ++i) {
-        // leaf uniforms: two leaves share a Philox block, lane l holds pair-block (base + l)
-        if ((i & 63) == 0)
-          ul = philox4x32_10(rng_chain, (uint32_t)t, ((uint32_t)depth << 20) | (uint32_t)((i >> 1) + lane),
-                             RNG_LEAF, a.seed_lo, a.seed_hi);
-        cur_lp = leapfrog<M, real>(th, p, g, es, sgn, c);
-        sub_leaps += 1;
-
-        bool no_uturn = true;
-        if (i & 1) {
-          // U-turn checks against checkpoints [popcount(i) - trailing_ones(i), popcount(i))
-          const int pc = __popc((unsigned)i), t1 = __ffs(~(unsigned)i) - 1;
-#pragma unroll
-          for (int r = 0; r < R; ++r) rho_sub[r] += p[r];
-          for (int s = pc - t1; s < pc && no_uturn; ++s) {
-            real d1 = 0, d2 = 0;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              const real mp = ldq(slot(MEM_P + s) + 32 * r);
-              const real df = rho_sub[r] - ldq(slot(MEM_RHO + s) + 32 * r);
-              d1 += df * mp;
-              d2 += df * p[r];
-            }
-            d1 = warp_sum(d1);
-            d2 = warp_sum(d2);
-            no_uturn = (d1 > 0) && (d2 > 0);
-          }
-        } else {
-          // even leaves are checkpointed into slot popcount(i): (p_i, rho before this leaf)
-          const int s = __popc((unsigned)i);
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            stq(slot(MEM_P + s) + 32 * r, p[r]);
-            stq(slot(MEM_RHO + s) + 32 * r, rho_sub[r]);
-            rho_sub[r] += p[r];
-          }
-        }
-
-        real energy = cur_lp - (real)0.5 * dot<R, real>(p, p);
-        if (m_isnan(energy)) energy = NEG_INF;
-        const real dH = energy - H0;
-        const bool not_divergent = (-dH < a.max_energy_diff);
-        const real w_new = m_logaddexp(w_sub, dH);
-        const real thresh = dH - w_new;
-        const int src = (i >> 1) & 31;
-        const uint32_t wa = __shfl_sync(FULL, (i & 1) ? ul.z : ul.x, src);
-        const uint32_t wb = __shfl_sync(FULL, (i & 1) ? ul.w : ul.y, src);
-        const real u = m_log1p(-u01<real>(wa, wb));
-        if (u <= thresh) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            stq(slot(PM4_SLOT_SUB_TH) + 32 * r, th[r]);
-            stq(slot(PM4_SLOT_SUB_G) + 32 * r, g[r]);
-          }
-          sub_lp = cur_lp;
-          sub_energy = energy;
-        }
-        w_sub = w_new;
-        not_div = not_div && not_divergent;
-        if (not_divergent) sub_ediff += m_exp(dH < 0 ? dH : (real)0);
-        cont_sub = no_uturn && not_divergent;
-      }
-
-      // merge the subtree into the trajectory (biased progressive sampling)
-      ediff_sum += sub_ediff;
-      nleap += sub_leaps;
-      const real tree_w = cont_sub ? w_sub : NEG_INF;
-      const real thresh = tree_w - w;
-      const uint32_t ma = __shfl_sync(FULL, um.x, depth), mb = __shfl_sync(FULL, um.y, depth);
-      const real umerge = m_log1p(-u01<real>(ma, mb));
-      if ((umerge <= thresh) && cont_sub) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          stq(slot(PM4_SLOT_CAND_TH) + 32 * r, ldq(slot(PM4_SLOT_SUB_TH) + 32 * r));
-          stq(slot(PM4_SLOT_CAND_G) + 32 * r, ldq(slot(PM4_SLOT_SUB_G) + 32 * r));
-        }
-        cand_lp = sub_lp;
-        cand_energy = sub_energy;
-      }
-      w = m_logaddexp(tree_w, w);
-      real d_cur = 0, d_oth = 0;
+    for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
+      real th[R], p[R], g[R], rho[R], rho_sub[R], es[R];
+      const real eps = da.eps;
+      draw_momentum<M, real>(a, chain, t, tl, p);
+      real q[4];
+      q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
+      // both trajectory ends and the candidate start at the current point
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        rho[r] += rho_sub[r];
-        d_cur += rho[r] * p[r];
-        d_oth += rho[r] * ldq(slot(PM4_SLOT_OTH_P) + 32 * r);
+        th[r] = ldv(PM4_SLOT_CAND_TH, r);
+        g[r] = ldv(PM4_SLOT_CAND_G, r);
+        rho[r] = p[r];
+        q[0] += p[r] * p[r];
+        stv(PM4_SLOT_OTH_TH, r, th[r]);
+        stv(PM4_SLOT_OTH_P, r, p[r]);
+        stv(PM4_SLOT_OTH_G, r, g[r]);
       }
-      d_cur = warp_sum(d_cur);
-      d_oth = warp_sum(d_oth);
-      cont = cont_sub && (d_cur > 0) && (d_oth > 0);
-      depth += 1;
-    }
+      team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
+      rb ^= 1;
+      const real H0 = clp - (real)0.5 * q[0];
 
-    // the transition's result is the candidate
+      // merge uniforms (one per doubling, lane d holds depth d) and the direction bits
+      const U4 um = philox4x32_10(rng_chain, (uint32_t)t, (uint32_t)lane, RNG_MERGE, a.seed_lo, a.seed_hi);
+      const U4 ud = philox4x32_10(rng_chain, (uint32_t)t, 0u, RNG_DIRECTION, a.seed_lo, a.seed_hi);
+
+      real cur_lp = clp, oth_lp = clp;
+      int cur_is_right = 1;
+      real cand_lp = clp, cand_energy = H0, w = 0, ediff_sum = 0;
+      int nleap = 0, depth = 0;
+      bool cont = true, not_div = true;
+
+      while (depth < a.max_depth && cont) {
+        const int dir = (int)((ud.x >> depth) & 1u);
+        if (dir != cur_is_right) {  // extend the other end: swap the register-resident end with the stored one
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cth[r] = ldq(slot(PM4_SLOT_CAND_TH) + 32 * r);
-      cg[r] = ldq(slot(PM4_SLOT_CAND_G) + 32 * r);
-    }
-    clp = cand_lp;
-    total_leaps += nleap;
-    const real accept = ediff_sum / (real)nleap;
-    if (a.adapt_enabled) {
-      if (a.adapt_pooled) { if (lane == 0) a.accept[chain] = accept; }
-      else da.update(a, t, accept);
-    }
-    if (t >= a.B) {
-      const size_t k = (size_t)(t - a.B) * C + chain;
-      if (a.states) {
+          for (int r = 0; r < R; ++r) {
+            real v;
+            v = ldv(PM4_SLOT_OTH_TH, r); stv(PM4_SLOT_OTH_TH, r, th[r]); th[r] = v;
+            v = ldv(PM4_SLOT_OTH_P, r); stv(PM4_SLOT_OTH_P, r, p[r]); p[r] = v;
+            v = ldv(PM4_SLOT_OTH_G, r); stv(PM4_SLOT_OTH_G, r, g[r]); g[r] = v;
+          }
+          const real sw = cur_lp; cur_lp = oth_lp; oth_lp = sw;
+          cur_is_right = dir;
+        }
+        const int nsteps = 1 << depth;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int j = lane + 32 * r;
-          if (j < D) __stcs(a.states + k * D + j, cth[r]);
+          rho_sub[r] = 0;
+          es[r] = (dir ? eps : -eps) * sc[r];
+        }
+        real w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
+        bool cont_sub = true;
+        int sub_leaps = 0;
+        U4 ul{0u, 0u, 0u, 0u};
+
+        for (int i = 0; i < nsteps && cont_sub; ++i) {
+          // leaf uniforms: two leaves share a Philox block, lane l holds pair-block (base + l)
+          if ((i & 63) == 0)
+            ul = philox4x32_10(rng_chain, (uint32_t)t, ((uint32_t)depth << 20) | (uint32_t)((i >> 1) + lane),
+                               RNG_LEAF, a.seed_lo, a.seed_hi);
+          cur_lp = leapfrog<M, real>(th, p, g, es, c, own);
+          sub_leaps += 1;
+
+          // one team reduction per leaf: kinetic energy and, on odd leaves, the U-turn test against the
+          // checkpoint of the preceding even leaf
+          const int pc = __popc((unsigned)i), t1 = __ffs(~(unsigned)i) - 1;
+          q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
+          if (i & 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              rho_sub[r] += p[r];
+              const real mp = ldv(MEM_P + pc - 1, r);
+              const real df = rho_sub[r] - ldv(MEM_RHO + pc - 1, r);
+              q[0] += p[r] * p[r];
+              q[1] += df * mp;
+              q[2] += df * p[r];
+            }
+          } else {
+            // even leaves are checkpointed into slot popcount(i): (p_i, rho before this leaf)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              stv(MEM_P + pc, r, p[r]);
+              stv(MEM_RHO + pc, r, rho_sub[r]);
+              rho_sub[r] += p[r];
+              q[0] += p[r] * p[r];
+            }
+          }
+          team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
+          rb ^= 1;
+          bool no_uturn = true;
+          if (i & 1) {
+            no_uturn = (q[1] > 0) && (q[2] > 0);
+            // remaining checkpoints [popcount(i) - trailing_ones(i), popcount(i) - 1), two per reduction
+            for (int s = pc - 2; s >= pc - t1 && no_uturn; s -= 2) {
+              const bool two = s - 1 >= pc - t1;
+              real u4[4];
+              u4[0] = 0; u4[1] = 0; u4[2] = 0; u4[3] = 0;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const real df = rho_sub[r] - ldv(MEM_RHO + s, r);
+                u4[0] += df * ldv(MEM_P + s, r);
+                u4[1] += df * p[r];
+                if (two) {
+                  const real df2 = rho_sub[r] - ldv(MEM_RHO + s - 1, r);
+                  u4[2] += df2 * ldv(MEM_P + s - 1, r);
+                  u4[3] += df2 * p[r];
+                }
+              }
+              team_sum<T, 4, real>(u4, c, c.red + rb * 4 * T);
+              rb ^= 1;
+              no_uturn = (u4[0] > 0) && (u4[1] > 0) && (!two || ((u4[2] > 0) && (u4[3] > 0)));
+            }
+          }
+
+          real energy = cur_lp - (real)0.5 * q[0];
+          if (m_isnan(energy)) energy = NEG_INF;
+          const real dH = energy - H0;
+          const bool not_divergent = (-dH < a.max_energy_diff);
+          const real w_new = m_logaddexp(w_sub, dH);
+          const real thresh = dH - w_new;
+          const int src = (i >> 1) & 31;
+          const uint32_t wa = __shfl_sync(FULL, (i & 1) ? ul.z : ul.x, src);
+          const uint32_t wb = __shfl_sync(FULL, (i & 1) ? ul.w : ul.y, src);
+          const real u = m_log1p(-u01<real>(wa, wb));
+          if (u <= thresh) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              stv(PM4_SLOT_SUB_TH, r, th[r]);
+              stv(PM4_SLOT_SUB_G, r, g[r]);
+            }
+            sub_lp = cur_lp;
+            sub_energy = energy;
+          }
+          w_sub = w_new;
+          not_div = not_div && not_divergent;
+          if (not_divergent) sub_ediff += m_exp(dH < 0 ? dH : (real)0);
+          cont_sub = no_uturn && not_divergent;
+        }
+
+        // merge the subtree into the trajectory (biased progressive sampling)
+        ediff_sum += sub_ediff;
+        nleap += sub_leaps;
+        const real tree_w = cont_sub ? w_sub : NEG_INF;
+        const real thresh = tree_w - w;
+        const uint32_t ma = __shfl_sync(FULL, um.x, depth), mb = __shfl_sync(FULL, um.y, depth);
+        const real umerge = m_log1p(-u01<real>(ma, mb));
+        if ((umerge <= thresh) && cont_sub) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            stv(PM4_SLOT_CAND_TH, r, ldv(PM4_SLOT_SUB_TH, r));
+            stv(PM4_SLOT_CAND_G, r, ldv(PM4_SLOT_SUB_G, r));
+          }
+          cand_lp = sub_lp;
+          cand_energy = sub_energy;
+        }
+        w = m_logaddexp(tree_w, w);
+        q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          rho[r] += rho_sub[r];
+          q[0] += rho[r] * p[r];
+          q[1] += rho[r] * ldv(PM4_SLOT_OTH_P, r);
+        }
+        team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
+        rb ^= 1;
+        cont = cont_sub && (q[0] > 0) && (q[1] > 0);
+        depth += 1;
+      }
+
+      // the transition's result is the candidate
+      clp = cand_lp;
+      launch_leaps += nleap;
+      const real accept = ediff_sum / (real)nleap;
+      if (a.adapt_enabled) {
+        if (a.adapt_pooled) { if (tl == 0) a.accept[chain] = accept; }
+        else da.update(a, t, accept);
+      }
+      if (t >= a.B) {
+        const size_t k = (size_t)(t - a.B) * C + chain;
+        if (a.states) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int j = tl + TL * r;
+            if (j < D) __stcs(a.states + k * D + j, ldv(PM4_SLOT_CAND_TH, r));
+          }
+        }
+        if (tl == 0) {
+          if (a.lp_out) a.lp_out[k] = cand_lp;
+          if (a.leapfrogs) a.leapfrogs[k] = nleap;
+          if (a.diverging) a.diverging[k] = not_div ? 0 : 1;
+          if (a.energy) a.energy[k] = cand_energy;
+          if (a.log_accept) a.log_accept[k] = m_log(accept);
+          if (a.depth) a.depth[k] = depth;
         }
       }
-      if (lane == 0) {
-        if (a.lp_out) a.lp_out[k] = cand_lp;
-        if (a.leapfrogs) a.leapfrogs[k] = nleap;
-        if (a.diverging) a.diverging[k] = not_div ? 0 : 1;
-        if (a.energy) a.energy[k] = cand_energy;
-        if (a.log_accept) a.log_accept[k] = m_log(accept);
-        if (a.depth) a.depth[k] = depth;
-      }
     }
-  }
 
-  // persist the chain for the next launch
+    // persist the chain for the next launch
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    a.th[(size_t)chain * DP + lane + 32 * r] = cth[r];
-    a.gr[(size_t)chain * DP + lane + 32 * r] = cg[r];
-  }
-  if (lane == 0) {
-    a.lp[chain] = clp;
-    if (!a.adapt_pooled) da.store(a.da + (size_t)chain * 4);
-    if (a.total_leapfrogs) a.total_leapfrogs[chain] += total_leaps;
+    for (int r = 0; r < R; ++r) {
+      a.th[(size_t)chain * DP + tl + TL * r] = ldv(PM4_SLOT_CAND_TH, r);
+      a.gr[(size_t)chain * DP + tl + TL * r] = ldv(PM4_SLOT_CAND_G, r);
+    }
+    if (tl == 0) {
+      a.lp[chain] = clp;
+      if (!a.adapt_pooled) da.store(a.da + (size_t)chain * 4);
+      if (a.total_leapfrogs) a.total_leapfrogs[chain] += launch_leaps;
+      if (a.launch_leaps) a.launch_leaps[chain] = launch_leaps;
+    }
   }
 }
 
@@ -568,95 +666,110 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 // ------------------------------------------------------------------------------------------
 template <class M, typename real, int MAXT, bool STAGED>
 __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
-  constexpr int R = M::R, D = M::D, DP = M::DP;
+  constexpr int R = M::R, D = M::D, DP = M::DP, T = M::T, TL = 32 * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx<real> c = make_ctx<real, STAGED>(a.A, smem_raw, DP);
-  const int lane = c.lane;
-  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chain >= a.C) return;
+  Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
+  const int tl = c.tl;
   const size_t C = (size_t)a.C;
-  real cth[R], cg[R], scale[R];
-  real clp = a.lp[chain];
+  int own[R];
+  load_own<M, real>(c, own);
+  real sc[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = lane + 32 * r;
-    cth[r] = a.th[(size_t)chain * DP + j];
-    cg[r] = a.gr[(size_t)chain * DP + j];
-    scale[r] = (a.step_scale && j < D) ? a.step_scale[j] : (real)1;
-  }
-  DualAvg<real> da;
-  da.load(a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4));
+  for (int r = 0; r < R; ++r) sc[r] = (a.step_scale && tl + TL * r < D) ? a.step_scale[tl + TL * r] : (real)1;
+  int rb = 0;
 
-  for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
-    real es[R], th[R], p[R], g[R];
+  for (;;) {
+    const int chain = next_chain<T, real>(a, c);
+    if (chain < 0) break;
+    real cth[R], cg[R];
+    real clp = a.lp[chain];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { es[r] = da.eps * scale[r]; th[r] = cth[r]; g[r] = cg[r]; }
-    draw_momentum<M, real>(a, chain, t, lane, p);
-    const real k0 = (real)0.5 * dot<R, real>(p, p);
-    // half kick, L x (drift, gradient, full kick), half un-kick
-#pragma unroll
-    for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es[r]) * g[r];
-    real plp = clp;
-    for (int l = 0; l < a.num_leapfrog; ++l) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) th[r] = th[r] + es[r] * p[r];
-      plp = logp_grad<M, real>(th, g, c);
-#pragma unroll
-      for (int r = 0; r < R; ++r) p[r] = p[r] + es[r] * g[r];
+    for (int r = 0; r < R; ++r) {
+      cth[r] = a.th[(size_t)chain * DP + tl + TL * r];
+      cg[r] = a.gr[(size_t)chain * DP + tl + TL * r];
     }
-#pragma unroll
-    for (int r = 0; r < R; ++r) p[r] = p[r] - ((real)0.5 * es[r]) * g[r];
-    const real k1 = (real)0.5 * dot<R, real>(p, p);
-    real lar = (plp - clp) + (k0 - k1);
-    if (!(lar == lar) || lar == m_inf<real>() || lar == -m_inf<real>()) lar = -m_inf<real>();
-    real u;
-    if (a.uniforms) u = a.uniforms[(size_t)t * C + chain];
-    else {
-      const U4 uu = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, 0u, RNG_HMC, a.seed_lo, a.seed_hi);
-      u = u01<real>(uu.x, uu.y);
-    }
-    const bool ok = m_log(u) < lar;
-    if (a.traj) {
+    DualAvg<real> da;
+    da.load(a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4));
+
+    for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
+      real es[R], th[R], p[R], g[R], q[4];
+      draw_momentum<M, real>(a, chain, t, tl, p);
+      q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int j = lane + 32 * r;
-        if (j < D) a.traj[((size_t)t * C + chain) * D + j] = th[r];
+        es[r] = da.eps * sc[r]; th[r] = cth[r]; g[r] = cg[r];
+        q[0] += p[r] * p[r];
       }
-    }
-    if (ok) {
+      // half kick, L x (drift, gradient, full kick), half un-kick
 #pragma unroll
-      for (int r = 0; r < R; ++r) { cth[r] = th[r]; cg[r] = g[r]; }
-      clp = plp;
-    }
-    const real accept = m_exp(lar < 0 ? lar : (real)0);
-    if (a.adapt_enabled) {
-      if (a.adapt_pooled) { if (lane == 0) a.accept[chain] = accept; }
-      else da.update(a, t, accept);
-    }
-    if (t >= a.B) {
-      const size_t k = (size_t)(t - a.B) * C + chain;
-      if (a.states) {
+      for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es[r]) * g[r];
+      real plp = clp;
+      for (int l = 0; l < a.num_leapfrog; ++l) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) th[r] = th[r] + es[r] * p[r];
+        plp = logp_grad<M, real>(th, g, c, own);
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = p[r] + es[r] * g[r];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        p[r] = p[r] - ((real)0.5 * es[r]) * g[r];
+        q[1] += p[r] * p[r];
+      }
+      team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
+      rb ^= 1;
+      const real k0 = (real)0.5 * q[0], k1 = (real)0.5 * q[1];
+      real lar = (plp - clp) + (k0 - k1);
+      if (!(lar == lar) || lar == m_inf<real>() || lar == -m_inf<real>()) lar = -m_inf<real>();
+      real u;
+      if (a.uniforms) u = a.uniforms[(size_t)t * C + chain];
+      else {
+        const U4 uu = philox4x32_10((uint32_t)(a.chain_offset + chain), (uint32_t)t, 0u, RNG_HMC, a.seed_lo, a.seed_hi);
+        u = u01<real>(uu.x, uu.y);
+      }
+      const bool ok = m_log(u) < lar;
+      if (a.traj) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int j = lane + 32 * r;
-          if (j < D) a.states[k * D + j] = cth[r];
+          const int j = tl + TL * r;
+          if (j < D) a.traj[((size_t)t * C + chain) * D + j] = th[r];
         }
       }
-      if (lane == 0) {
-        if (a.lp_out) a.lp_out[k] = clp;
-        if (a.log_accept) a.log_accept[k] = lar;
-        if (a.diverging) a.diverging[k] = ok ? 1 : 0;
+      if (ok) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) { cth[r] = th[r]; cg[r] = g[r]; }
+        clp = plp;
+      }
+      const real accept = m_exp(lar < 0 ? lar : (real)0);
+      if (a.adapt_enabled) {
+        if (a.adapt_pooled) { if (tl == 0) a.accept[chain] = accept; }
+        else da.update(a, t, accept);
+      }
+      if (t >= a.B) {
+        const size_t k = (size_t)(t - a.B) * C + chain;
+        if (a.states) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int j = tl + TL * r;
+            if (j < D) a.states[k * D + j] = cth[r];
+          }
+        }
+        if (tl == 0) {
+          if (a.lp_out) a.lp_out[k] = clp;
+          if (a.log_accept) a.log_accept[k] = lar;
+          if (a.diverging) a.diverging[k] = ok ? 1 : 0;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    a.th[(size_t)chain * DP + lane + 32 * r] = cth[r];
-    a.gr[(size_t)chain * DP + lane + 32 * r] = cg[r];
-  }
-  if (lane == 0) {
-    a.lp[chain] = clp;
-    if (!a.adapt_pooled) da.store(a.da + (size_t)chain * 4);
+    for (int r = 0; r < R; ++r) {
+      a.th[(size_t)chain * DP + tl + TL * r] = cth[r];
+      a.gr[(size_t)chain * DP + tl + TL * r] = cg[r];
+    }
+    if (tl == 0) {
+      a.lp[chain] = clp;
+      if (!a.adapt_pooled) da.store(a.da + (size_t)chain * 4);
+    }
   }
 }
 
@@ -667,40 +780,104 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// Launch geometry of the persistent chain kernels: teams per block, whether the tree scratch lives
+// in shared memory, bytes of dynamic shared memory.
+struct Geometry {
+  int teams, grid, team_reals, n_slots, stage, scr_smem;
+  size_t smem;
+};
+
+template <class M, typename real>
+inline Geometry plan_geometry(ModelArgs<real>& A, int C, int wpb, int n_slots, int max_threads) {
+  constexpr int T = M::T;
+  Geometry g{};
+  g.n_slots = n_slots;
+  const int sms = sm_count();
+  int max_teams = max_threads / (32 * T);
+  if (T > 1 && max_teams > 16) max_teams = 16;  // named barriers 0..15
+  if (max_teams < 1) max_teams = 1;
+  int teams = wpb > 0 ? wpb / T : max_teams;
+  if (teams > max_teams) teams = max_teams;
+  if (teams < 1) teams = 1;
+  // do not pack more teams into a block than the chains need to cover every SM
+  const int per_sm = (C + sms - 1) / sms;
+  if (wpb <= 0 && teams > per_sm) teams = per_sm;
+  const size_t base = team_base_reals<M, real>(A), scr = (size_t)n_slots * M::DS;
+  if (A.stage && pool_bytes(A) > SMEM_LIMIT / 2) A.stage = 0;
+  // prefer everything on chip; give up teams before giving up the on-chip tree scratch, but keep at
+  // least a quarter of the team slots busy
+  g.scr_smem = 1;
+  int t_scr = teams;
+  while (t_scr > 1 && pool_bytes(A) + (size_t)t_scr * (base + scr) * sizeof(real) > SMEM_LIMIT) --t_scr;
+  if (pool_bytes(A) + (size_t)t_scr * (base + scr) * sizeof(real) > SMEM_LIMIT || t_scr * 4 < teams) {
+    g.scr_smem = 0;
+    while (teams > 1 && pool_bytes(A) + (size_t)teams * base * sizeof(real) > SMEM_LIMIT) --teams;
+    if (pool_bytes(A) + (size_t)teams * base * sizeof(real) > SMEM_LIMIT) A.stage = 0;
+  } else {
+    teams = t_scr;
+  }
+  g.teams = teams;
+  g.team_reals = (int)(base + (g.scr_smem ? scr : 0));
+  g.stage = A.stage;
+  g.smem = pool_bytes(A) + (size_t)teams * g.team_reals * sizeof(real);
+  int grid = (C + teams - 1) / teams;
+  if (grid > sms) grid = sms;
+  g.grid = grid;
+  return g;
+}
+
 template <class M, typename real, class Kernel>
-inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, int wpb, cudaStream_t st) {
-  const size_t smem = cta_smem_bytes(p.A, M::DP, wpb);
-  if (smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
-  PM4_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (p.C + wpb - 1) / wpb;
-  kernel<<<grid, wpb * 32, smem, st>>>(p);
+inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, const Geometry& g, cudaStream_t st) {
+  if (g.smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
+  PM4_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  PM4_CUDA_OK(cudaMemsetAsync(p.queue, 0, sizeof(int32_t), st));
+  kernel<<<g.grid, g.teams * M::T * 32, g.smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
-// warps per block -> the smallest compiled launch bound that fits (more registers per thread)
+// threads per block of the big single-precision variant: registers per thread = 65536 / PM4_MAXT
+#ifndef PM4_MAXT
+#define PM4_MAXT 1024
+#endif
+template <typename real> constexpr int max_threads_for() { return sizeof(real) == 8 ? 256 : PM4_MAXT; }
+
+// tree-scratch vector slots of a run (HMC keeps its state in registers)
+inline int scratch_slots(bool nuts, int max_depth) { return nuts ? PM4_SLOT_MEM + 2 * (max_depth + 1) : 0; }
+
 template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_mod_run_t& r, int wpb, cudaStream_t st) {
   RunParams<real> p = make_run_params<real>(r);
-  if (wpb <= 0) {  // library default: one block per SM, up to 28 warps (= 28 chains) per block
-    const int per_sm = (r.C + 147) / 148;
-    wpb = per_sm <= 8 ? 8 : 28;
-  }
-  if (wpb > 28) wpb = 28;
-  if (sizeof(real) == 8 && wpb > 8) wpb = 8;  // double precision is only instantiated for 256 threads
-  // shrink the block until the per-chain state (and the staged pools) fit in shared memory
-  while (wpb > 1 && cta_smem_bytes(p.A, M::DP, wpb) > SMEM_LIMIT) {
-    if (p.A.stage && pool_bytes(p.A) > SMEM_LIMIT / 2) p.A.stage = 0;
-    else wpb -= 1;
-  }
-#define PM4_LAUNCH(T)                                                                                       \
-  do {                                                                                                      \
-    if (p.A.stage)                                                                                          \
-      return NUTS ? launch_chain_kernel<M, real>(nuts_kernel<M, real, T, true>, p, wpb, st)                 \
-                  : launch_chain_kernel<M, real>(hmc_kernel<M, real, T, true>, p, wpb, st);                 \
-    return NUTS ? launch_chain_kernel<M, real>(nuts_kernel<M, real, T, false>, p, wpb, st)                  \
-                : launch_chain_kernel<M, real>(hmc_kernel<M, real, T, false>, p, wpb, st);                  \
+  const int n_slots = scratch_slots(NUTS, r.max_depth);
+  Geometry g = plan_geometry<M, real>(p.A, r.C, wpb, n_slots, max_threads_for<real>());
+  p.team_reals = g.team_reals;
+  p.n_slots = n_slots;
+  if (NUTS && !g.scr_smem && !p.scratch) return (int)cudaErrorInvalidValue;
+  const bool small = g.teams * M::T * 32 <= 256;
+#define PM4_LAUNCH(MAXT)                                                                                              \
+  do {                                                                                                                \
+    if constexpr (NUTS) {                                                                                             \
+      if (p.A.stage) {                                                                                                \
+        if (g.scr_smem) return launch_chain_kernel<M, real>(nuts_kernel<M, real, MAXT, true, true>, p, g, st);        \
+        return launch_chain_kernel<M, real>(nuts_kernel<M, real, MAXT, true, false>, p, g, st);                       \
+      }                                                                                                               \
+      if (g.scr_smem) return launch_chain_kernel<M, real>(nuts_kernel<M, real, MAXT, false, true>, p, g, st);         \
+      return launch_chain_kernel<M, real>(nuts_kernel<M, real, MAXT, false, false>, p, g, st);                        \
+    } else {                                                                                                          \
+      if (p.A.stage) return launch_chain_kernel<M, real>(hmc_kernel<M, real, MAXT, true>, p, g, st);                  \
+      return launch_chain_kernel<M, real>(hmc_kernel<M, real, MAXT, false>, p, g, st);                                \
+    }                                                                                                                 \
   } while (0)
-  if (wpb <= 8) PM4_LAUNCH(256);
-  if constexpr (sizeof(real) == 4) PM4_LAUNCH(896);
+  if (small) PM4_LAUNCH(256);
+  if constexpr (sizeof(real) == 4) PM4_LAUNCH(PM4_MAXT);
 #undef PM4_LAUNCH
   return (int)cudaErrorInvalidConfiguration;
 }
@@ -718,8 +895,10 @@ template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_m
 extern "C" int pm4m_info(pm4_mod_info_t* out) {
   out->abi = PM4_MODULE_ABI;
   out->D = PM4_MODEL::D;
+  out->T = PM4_MODEL::T;
   out->R = PM4_MODEL::R;
   out->DP = PM4_MODEL::DP;
+  out->DS = PM4_MODEL::DS;
   out->det_row = PM4_MODEL::DET_ROW;
   out->has_f64 = PM4_HAS_F64;
   out->n_terms = PM4_MODEL::N_TERMS;
@@ -729,20 +908,26 @@ extern "C" int pm4m_info(pm4_mod_info_t* out) {
 }
 
 namespace pm4 {
+// geometry of the stateless kernels: one team per chain, up to 256 threads per block, no tree scratch
+template <class M, typename real> inline Geometry small_geometry(ModelArgs<real>& A, int C) {
+  Geometry g = plan_geometry<M, real>(A, C, 0, 0, 256);
+  g.grid = (C + g.teams - 1) / g.teams;
+  return g;
+}
+
 template <typename real>
 int mod_logp_grad(const pm4_mod_args_t* A, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
   using M = PM4_MODEL;
   ModelArgs<real> ma = make_model_args<real>(*A);
-  const int wpb = 4;
-  if (cta_smem_bytes(ma, M::DP, wpb) > SMEM_LIMIT) ma.stage = 0;
-  const size_t smem = cta_smem_bytes(ma, M::DP, wpb);
-  const unsigned grid = (unsigned)((C + wpb - 1) / wpb);
+  const Geometry g = small_geometry<M, real>(ma, C);
+  if (g.smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
+  const unsigned threads = (unsigned)(g.teams * M::T * 32);
   if (ma.stage) {
-    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    logp_grad_kernel<M, real, true><<<grid, wpb * 32, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    logp_grad_kernel<M, real, true><<<g.grid, threads, g.smem, st>>>(ma, C, g.team_reals, (const real*)theta, (real*)lp, (real*)grad);
   } else {
-    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    logp_grad_kernel<M, real, false><<<grid, wpb * 32, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    logp_grad_kernel<M, real, false><<<g.grid, threads, g.smem, st>>>(ma, C, g.team_reals, (const real*)theta, (real*)lp, (real*)grad);
   }
   return (int)cudaGetLastError();
 }
@@ -757,18 +942,27 @@ int mod_dets(const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, c
 template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0, double eps0, cudaStream_t st) {
   using M = PM4_MODEL;
   RunParams<real> p = make_run_params<real>(*r);
-  const int wpb = 4;
-  if (cta_smem_bytes(p.A, M::DP, wpb) > SMEM_LIMIT) p.A.stage = 0;
-  const size_t smem = cta_smem_bytes(p.A, M::DP, wpb);
-  const unsigned grid = (unsigned)((r->C + wpb - 1) / wpb);
+  const Geometry g = small_geometry<M, real>(p.A, r->C);
+  if (g.smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
+  p.team_reals = g.team_reals;
+  const unsigned threads = (unsigned)(g.teams * M::T * 32);
   if (p.A.stage) {
-    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    init_kernel<M, real, true><<<grid, wpb * 32, smem, st>>>(p, (const real*)theta0, (real)eps0);
+    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    init_kernel<M, real, true><<<g.grid, threads, g.smem, st>>>(p, (const real*)theta0, (real)eps0);
   } else {
-    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    init_kernel<M, real, false><<<grid, wpb * 32, smem, st>>>(p, (const real*)theta0, (real)eps0);
+    PM4_CUDA_OK(cudaFuncSetAttribute(init_kernel<M, real, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    init_kernel<M, real, false><<<g.grid, threads, g.smem, st>>>(p, (const real*)theta0, (real)eps0);
   }
   return (int)cudaGetLastError();
+}
+// bytes of global tree scratch a NUTS run of C chains needs (0 when the scratch fits in shared memory)
+template <typename real> int64_t mod_scratch_bytes(const pm4_mod_args_t* A, int C, int wpb, int max_depth) {
+  using M = PM4_MODEL;
+  ModelArgs<real> ma = make_model_args<real>(*A);
+  const int n_slots = scratch_slots(true, max_depth);
+  const Geometry g = plan_geometry<M, real>(ma, C, wpb, n_slots, max_threads_for<real>());
+  if (g.scr_smem) return 0;
+  return (int64_t)g.grid * g.teams * n_slots * M::DS * (int64_t)sizeof(real);
 }
 }  // namespace pm4
 
@@ -796,6 +990,13 @@ extern "C" int pm4m_init(int dtype, const pm4_mod_run_t* r, const void* theta0, 
   PM4_BY_DTYPE(pm4::mod_init<float>(r, theta0, eps0, (cudaStream_t)stream),
                PM4_F64_CALL(pm4::mod_init<double>(r, theta0, eps0, (cudaStream_t)stream)));
 }
+extern "C" int64_t pm4m_scratch_bytes(int dtype, const pm4_mod_args_t* A, int C, int wpb, int max_depth) {
+  if (dtype == 0) return pm4::mod_scratch_bytes<float>(A, C, wpb, max_depth);
+#if PM4_HAS_F64
+  if (dtype == 1) return pm4::mod_scratch_bytes<double>(A, C, wpb, max_depth);
+#endif
+  return -22;
+}
 extern "C" int pm4m_nuts(int dtype, const pm4_mod_run_t* r, int wpb, void* stream) {
   PM4_BY_DTYPE((pm4::dispatch_run<PM4_MODEL, float, true>(*r, wpb, (cudaStream_t)stream)),
                PM4_F64_CALL((pm4::dispatch_run<PM4_MODEL, double, true>(*r, wpb, (cudaStream_t)stream))));
@@ -814,5 +1015,9 @@ extern "C" int pm4m_export_eps(int dtype, const pm4_mod_run_t* r, void* out, voi
   if (dtype == 0) { pm4::export_eps_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(pm4::make_run_params<float>(*r), (float*)out); return (int)cudaGetLastError(); }
   if (dtype == 1) { pm4::export_eps_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(pm4::make_run_params<double>(*r), (double*)out); return (int)cudaGetLastError(); }
   return -22;
+}
+extern "C" int pm4m_lpt_order(int C, const int32_t* work, int32_t* order, void* stream) {
+  pm4::lpt_order_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(C, work, order);
+  return (int)cudaGetLastError();
 }
 #endif  // PM4_MODEL

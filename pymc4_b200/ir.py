@@ -29,7 +29,7 @@ from . import symbolic as sym
 from .coroutine_model import Model
 from .utils import NameParts
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
 
@@ -103,10 +103,11 @@ class Plan:
     """Device execution plan of a term whose parameters gather from free variables.
 
     The term's elements are regrouped by gather target ("group"), groups are cut into chunks of
-    at most ``chunk_cap`` elements, chunks are sorted by length and dealt 32 at a time to the lanes
-    of the chain's warp (sliced-ELL).  Within a slice every lane walks one chunk, so the gathered
-    values sit in registers and their adjoints accumulate in registers -- no scatter, no atomics,
-    a fixed summation order.  Per-chunk partial sums are combined per group afterwards.
+    at most ``chunk_cap`` elements, chunks are sorted by length and dealt 32*T at a time to the lanes
+    of the chain's team of T warps (sliced-ELL).  Within a slice every lane walks one chunk, so the
+    gathered values sit in registers and their adjoints accumulate in registers -- no scatter, no
+    atomics, a fixed summation order.  Per-chunk sums are parked in the chain's ``part`` array and
+    added up by the lane that owns the gradient element (pymc4_b200/plan.py).
 
     Structure (goes into the struct hash): which ops are planned gathers / record fields.
     Data (run-time pools): everything below.
@@ -122,11 +123,6 @@ class Plan:
     meta_off: int = 0               # offset into plani
     recs_off: int = 0               # offset into planf (reals)
     chunk_cap: int = 0
-    n_part: int = 1                 # scratch reals per gather op (chunks of split groups)
-
-    @property
-    def part_reals(self) -> int:
-        return len(self.gather_ops) * self.n_part
 
 
 @dataclass
@@ -154,6 +150,12 @@ class ModelIR:
     observed: Dict[str, np.ndarray] = field(default_factory=dict)
     planf: np.ndarray = field(default_factory=lambda: np.zeros(0))
     plani: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    # team layout (pymc4_b200/plan.py): warps per chain, scalar-read positions, part-array tables
+    team_warps: int = 1
+    scalar_pos: List[int] = field(default_factory=list)
+    elem_off: int = 0      # offset of elem_tab[DPt] in plani
+    spart_off: int = 0     # offset of spart[n_scalar + 1] in plani
+    part_reals: int = 4
 
     @property
     def plans(self) -> List["Plan"]:
@@ -165,7 +167,7 @@ class ModelIR:
 
     # -- structural hash: everything the generated code depends on ---------
     def struct_key(self) -> bytes:
-        h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<i", self.D)]
+        h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<ii", self.D, self.team_warps)]
         for rv in self.rvs:
             h.append(struct.pack("<iiidd", rv.offset, rv.size, rv.transform, rv.shift, rv.scale))
 
@@ -387,7 +389,8 @@ def _transform_record(dist) -> Tuple[int, float, float]:
     return int(tr.ir_code), float(tr.ir_shift), float(tr.ir_scale)
 
 
-def lower_model(model: Model, observed: Optional[dict] = None, state=None) -> Tuple[ModelIR, Any, List[str]]:
+def lower_model(model: Model, observed: Optional[dict] = None, state=None,
+                team_warps: Optional[int] = None) -> Tuple[ModelIR, Any, List[str]]:
     """Trace ``model`` and return (IR, initial sampling state, deterministic names).
 
     The initial state and the deterministic-name list are exactly what the reference's
@@ -475,7 +478,7 @@ def lower_model(model: Model, observed: Optional[dict] = None, state=None) -> Tu
                  observed=observed_np)
     from .plan import attach_plans
 
-    attach_plans(ir)
+    attach_plans(ir, team_warps)
     return ir, init_state, deterministic_names
 
 
@@ -494,8 +497,8 @@ class CTerm(ctypes.Structure):
 
 
 class CPlan(ctypes.Structure):
-    _fields_ = [("term", ctypes.c_int32), ("n_gather", ctypes.c_int32), ("n_part", ctypes.c_int32),
-                ("width", ctypes.c_int32), ("meta", ctypes.c_int64), ("recs", ctypes.c_int64)]
+    _fields_ = [("term", ctypes.c_int32), ("n_gather", ctypes.c_int32), ("width", ctypes.c_int32),
+                ("_pad", ctypes.c_int32), ("meta", ctypes.c_int64), ("recs", ctypes.c_int64)]
 
 
 class COp(ctypes.Structure):
@@ -520,7 +523,9 @@ class CIR(ctypes.Structure):
                 ("struct_hash", ctypes.c_uint64),
                 ("n_plans", ctypes.c_int32), ("_pad2", ctypes.c_int32), ("plans", ctypes.POINTER(CPlan)),
                 ("n_planf", ctypes.c_int64), ("planf", ctypes.POINTER(ctypes.c_double)),
-                ("n_plani", ctypes.c_int64), ("plani", ctypes.POINTER(ctypes.c_int32))]
+                ("n_plani", ctypes.c_int64), ("plani", ctypes.POINTER(ctypes.c_int32)),
+                ("team_warps", ctypes.c_int32), ("part_reals", ctypes.c_int32),
+                ("elem_off", ctypes.c_int64), ("spart_off", ctypes.c_int64)]
 
 
 class PackedIR:
@@ -556,7 +561,7 @@ class PackedIR:
         self._datai = np.ascontiguousarray(ir.datai, dtype=np.int32)
         cplans = (CPlan * max(len(plans), 1))()
         for k, pl in enumerate(plans):
-            cplans[k] = CPlan(pl.term, len(pl.gather_ops), pl.n_part, pl.width, pl.meta_off, pl.recs_off)
+            cplans[k] = CPlan(pl.term, len(pl.gather_ops), pl.width, 0, pl.meta_off, pl.recs_off)
         self._planf = np.ascontiguousarray(ir.planf, dtype=np.float64)
         self._plani = np.ascontiguousarray(ir.plani, dtype=np.int32)
         self._keep = (cterms, cdets, cops, crvs, cplans)
@@ -570,6 +575,7 @@ class PackedIR:
             len(plans), 0, ctypes.cast(cplans, ctypes.POINTER(CPlan)),
             self._planf.size, self._planf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             self._plani.size, self._plani.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            ir.team_warps, ir.part_reals, ir.elem_off, ir.spart_off,
         )
 
     def byref(self):

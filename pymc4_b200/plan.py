@@ -1,44 +1,74 @@
-"""Device execution plans for terms that gather from free variables (sliced-ELL over groups).
+"""Device execution plans: how one chain's log-density pass is spread over a TEAM of warps.
 
-A likelihood such as ``Normal(y | a[idx] + b[idx] * x, eps)`` (the radon model,
+A chain is owned by a team of ``T`` warps (``TL = 32 T`` lanes; ``ModelIR.team_warps``).  Every
+D-vector of the chain is spread over the team, lane ``tl`` holding elements ``tl, tl + TL, ...``.
+
+Gather terms.  A likelihood such as ``Normal(y | a[idx] + b[idx] * x, eps)`` (the radon model,
 /root/reference/notebooks/radon_hierarchical.ipynb:72-95; the reference evaluates it as
 ``tf.gather`` + broadcasted elementwise ops and differentiates through the gather with a
 scatter-add) needs, per chain and per gradient evaluation, a gather from the chain's state for
-every observation and a segment-sum of adjoints back into it.  With one warp per chain the plan
-below removes both: observations are regrouped by gather target, groups are cut into chunks of at
-most ``cap`` observations, chunks are sorted by length and dealt 32 at a time ("slices") to the
-lanes.  Inside a slice each lane walks ONE chunk: the gathered values live in registers, adjoints
-accumulate in registers, observation records are read with conflict-free shared-memory loads.
-A chunk that is a whole group adds its sums straight into the chain's gradient; the chunks of a
-split group park their partial sums in a small scratch array and are combined per group in a
-fixed order afterwards (deterministic, no atomics).
+every observation and a segment-sum of adjoints back into it.  The plan removes both:
+observations are regrouped by gather target, groups are cut into chunks of at most ``cap``
+observations, chunks are sorted by length and dealt ``TL`` at a time ("slices") to the lanes of
+the team (sliced ELL).  Inside a slice each lane walks ONE chunk: the gathered values live in
+registers, adjoints accumulate in registers, observation records are read with conflict-free
+shared-memory loads.  Every chunk then parks its adjoint sums in the chain's ``part`` array.
+
+The ``part`` array is the single hand-over point between the lanes that *produce* adjoints and the
+lane that *owns* a gradient element: the contributions to element ``j`` (chunk sums of every
+gather op that targets it, and -- for parameters read as scalars -- one warp-level partial sum per
+warp of the team) occupy the consecutive entries ``[first_j, first_j + cnt_j)``; after one team
+barrier the owner adds them in index order.  No atomics, no second pass, a fixed summation order
+(same seed => same trace).  ``elem_tab[j] = first_j << 12 | cnt_j``; ``spart[k]`` is the first entry
+of the k-th scalar parameter's block (``ModelIR.scalar_pos`` order), ``spart[n_scalar]`` that of the
+log-density partials.
 
 The plan depends on the index *values*, so it lives in two run-time pools (``planf`` records,
-``plani`` metadata); the generated code only depends on which ops are planned (``Plan.gather_ops``
-/ ``record_ops`` / ``width``).  The CPU oracle ignores plans and evaluates the original tape, which
-is what makes the parity tests a check of this layout.
+``plani`` metadata); the generated code only depends on which ops are planned and on ``T``.  The CPU
+oracle ignores plans and evaluates the original tape, which is what makes the parity tests a check
+of this layout.
 
-Metadata layout (int32, all offsets relative to the start of the plan's metadata, every table
-16-byte aligned):
-  header[8]   n_slices, n_split_groups, n_part (scratch reals per gather), o_slices, o_slots, o_split, 0, 0
+Per-plan metadata (int32, offsets relative to the start of the plan's metadata, 16-byte aligned):
+  header[4]   n_slices, o_slices, o_slots, SW (int4 words per slot)
   slices      int4 per slice: rows every lane walks unmasked (min length rounded down to a multiple
-              of 4), rows in the slice (max length rounded up to a multiple of 4), first record row, 0
-  slots       int4 per (slice, lane): gather target (-1 = empty lane), chunk length,
-              scratch index for chunks of split groups (-1 = whole group), 0
-  split       int4 per split group: gather target, first scratch index, number of chunks, 0
+              of ROW_UNROLL), rows in the slice (max length rounded up), first record row, 0
+  slots       SW int4 per (slice, lane): gather target (-1 = empty lane), chunk length, then the
+              ``part`` index of the chunk for every gather op of the plan
 Records (reals): row-major [row][lane][width]; row r of slice s is ``first_row + r``.
 """
 from __future__ import annotations
 
+import os
 from collections import Counter
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
 from . import ir as I
 
-HEADER = 8
+HEADER = 4
 ROW_UNROLL = 4
+MAX_GATHER_OPS = 6
+ELEM_CNT_BITS = 12
+TEAM_SIZES = (1, 2, 4, 8, 16, 32)
+
+
+def choose_team_warps(ir: "I.ModelIR") -> int:
+    """Warps per chain: enough lanes that a lane walks only a handful of observations and holds a
+    couple of state elements, as few as possible beyond that (every extra warp repeats the scalar
+    sampler logic).  PM4_TEAM_WARPS overrides (experiments)."""
+    env = os.environ.get("PM4_TEAM_WARPS")
+    if env:
+        t = int(env)
+        if t not in TEAM_SIZES:
+            raise ValueError("PM4_TEAM_WARPS must be one of %s" % (TEAM_SIZES,))
+        return t
+    work = sum(t.n for t in ir.terms)
+    want = max(work / 320.0, ir.D / 128.0)
+    for t in TEAM_SIZES:
+        if t >= want:
+            return min(t, 8)
+    return 8
 
 
 def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
@@ -53,20 +83,32 @@ def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
     return out
 
 
-def _cost(chunks: List[Tuple[int, int]]) -> float:
+def _cost(chunks: List[Tuple[int, int]], TL: int) -> float:
     lens = sorted((l for _, l in chunks), reverse=True)
-    n_slices = -(-len(lens) // 32)
+    n_slices = -(-len(lens) // TL)
     cost = 0.0
     for s in range(n_slices):
-        sl = lens[s * 32:(s + 1) * 32]
-        full = (sl[-1] if len(sl) == 32 else 0) // ROW_UNROLL * ROW_UNROLL
+        sl = lens[s * TL:(s + 1) * TL]
+        full = (sl[-1] if len(sl) == TL else 0) // ROW_UNROLL * ROW_UNROLL
         rows = -(-sl[0] // ROW_UNROLL) * ROW_UNROLL
-        cost += 6.5 * full + 8.5 * (rows - full) + 30.0  # unpredicated rows, masked rows, slice overhead
-    n_groups_split = len({g for g, _ in chunks}) - len({g for g, c in Counter(g for g, _ in chunks).items() if c == 1})
-    return cost + 25.0 * (-(-n_groups_split // 32))
+        cost += 6.5 * full + 8.0 * (rows - full) + 24.0  # unmasked rows, masked rows, slice overhead
+    # every chunk is one more entry its owner lane adds up (worst lane of a warp decides)
+    per_group = Counter(g for g, _ in chunks)
+    return cost + 2.0 * max(per_group.values())
 
 
-def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) -> Optional[Tuple[I.Plan, np.ndarray, np.ndarray]]:
+class _TermPlan:
+    """Chunking of one term before ``part`` indices are known."""
+
+    def __init__(self, plan: I.Plan, chunk_elems, targets, cols, gather_bases):
+        self.plan = plan
+        self.chunk_elems = chunk_elems      # [(group ordinal, element ids)] in slot order
+        self.targets = targets              # group ordinal -> gather target value
+        self.cols = cols                    # record columns (float64 arrays over the term's elements)
+        self.gather_bases = gather_bases    # theta offset of every gather op
+
+
+def _chunk_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray, TL: int) -> Optional[_TermPlan]:
     ld_x, ld_data = I.OP["ld_x"], I.OP["ld_data"]
     gathers = [o for o in term.ops if o.opcode == ld_x and o.mode == I.MODE_GATHER]
     if not gathers or term.n < 64:
@@ -76,6 +118,8 @@ def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) ->
     blob = Counter(o.blob for o in gathers).most_common(1)[0][0]
     if any(o.blob != blob for o in gathers):
         return None  # a second index array: keep the generic path
+    if len(gathers) > MAX_GATHER_OPS:
+        return None
     rec_ops = [o for o in term.ops if o.opcode == ld_data and o.mode == I.MODE_ELEM]
     if len(rec_ops) > 4:
         return None
@@ -90,96 +134,144 @@ def plan_term(t_idx: int, term: I.Term, datai: np.ndarray, dataf: np.ndarray) ->
     starts = np.concatenate([[0], np.cumsum(sizes)])
 
     best = None
-    for cap in sorted({2, 3, 4, 6, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, int(sizes.max())}):
+    max_chunks_per_group = (1 << ELEM_CNT_BITS) - 64
+    caps = sorted({2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 18, 20, 24, 28, 32, 40, 48, 64, 96, 128,
+                   int(sizes.max())})
+    for cap in caps:
+        if -(-int(sizes.max()) // cap) > max_chunks_per_group:
+            continue
         ch = _chunks_for_cap(sizes, cap)
-        c = _cost(ch)
+        c = _cost(ch, TL)
         if best is None or c < best[0]:
             best = (c, cap, ch)
     _, cap, chunks = best
 
     # element ids of every chunk, longest chunks first (ties: by group, so a group's chunks are neighbours)
     chunk_elems: List[Tuple[int, np.ndarray]] = []
-    cursor = {}
+    cursor: Dict[int, int] = {}
     for g, length in chunks:
         off = cursor.get(g, 0)
         chunk_elems.append((g, order[starts[g] + off: starts[g] + off + length]))
         cursor[g] = off + length
     chunk_elems.sort(key=lambda ge: (-len(ge[1]), ge[0]))
-    n_chunks_of = Counter(g for g, _ in chunk_elems)
-
-    n_slices = -(-len(chunk_elems) // 32)
-    n_slots = n_slices * 32
-    slices = np.zeros((n_slices, 4), dtype=np.int32)
-    slots = np.zeros((n_slots, 4), dtype=np.int32)
-    slots[:, 0] = -1
-    slots[:, 2] = -1
-    rec_rows = 0
-    for s in range(n_slices):
-        lens = [len(e) for _, e in chunk_elems[s * 32:(s + 1) * 32]]
-        # both loops of the device walk are unrolled by ROW_UNROLL without remainder: the unmasked
-        # prefix is rounded down, the slice's row count up (padding rows are zero records, masked)
-        full = (lens[-1] if len(lens) == 32 else 0) // ROW_UNROLL * ROW_UNROLL
-        rows = -(-lens[0] // ROW_UNROLL) * ROW_UNROLL
-        slices[s] = (full, rows, rec_rows, 0)
-        rec_rows += rows
-    recs = np.zeros((rec_rows, 32, width), dtype=np.float64)
     cols = [np.asarray(dataf[o.blob: o.blob + n], dtype=np.float64) for o in rec_ops]
-
-    # scratch indices: the chunks of a split group get consecutive slots
-    split_groups = sorted(g for g, c in n_chunks_of.items() if c > 1)
-    part_first, nxt = {}, 0
-    for g in split_groups:
-        part_first[g] = nxt
-        nxt += n_chunks_of[g]
-    n_part = nxt
-    part_used = {g: 0 for g in split_groups}
-    for slot, (g, elems) in enumerate(chunk_elems):
-        s, lane = divmod(slot, 32)
-        pidx = -1
-        if g in part_first:
-            pidx = part_first[g] + part_used[g]
-            part_used[g] += 1
-        slots[slot] = (targets[g], len(elems), pidx, 0)
-        for w, col in enumerate(cols):
-            recs[slices[s, 2]: slices[s, 2] + len(elems), lane, w] = col[elems]
-    split = np.zeros((max(len(split_groups), 1), 4), dtype=np.int32)
-    for q, g in enumerate(split_groups):
-        split[q] = (targets[g], part_first[g], n_chunks_of[g], 0)
-
-    o_slices = HEADER
-    o_slots = o_slices + slices.size
-    o_split = o_slots + slots.size
-    header = np.array([n_slices, len(split_groups), max(n_part, 1), o_slices, o_slots, o_split, 0, 0], dtype=np.int32)
-    meta = np.concatenate([header, slices.reshape(-1), slots.reshape(-1), split.reshape(-1)]).astype(np.int32)
     plan = I.Plan(term=t_idx, index_blob=int(blob), gather_ops=[o.dst for o in gathers],
-                  record_ops=[o.dst for o in rec_ops], width=width, n_slices=n_slices, n_groups=G,
-                  n_chunks=len(chunk_elems), chunk_cap=cap, n_part=max(n_part, 1))
-    return plan, meta, recs.reshape(-1)
+                  record_ops=[o.dst for o in rec_ops], width=width, n_slices=-(-len(chunk_elems) // TL),
+                  n_groups=G, n_chunks=len(chunk_elems), chunk_cap=cap)
+    return _TermPlan(plan, chunk_elems, targets, cols, [o.base for o in gathers])
 
 
-def attach_plans(ir: I.ModelIR) -> I.ModelIR:
-    """Plan every eligible term of ``ir`` in place and fill the plan pools."""
-    fparts, iparts, flen, ilen = [], [], 0, 0
-    for t_idx, term in enumerate(ir.terms):
+def scalar_positions(ir: "I.ModelIR") -> List[int]:
+    """theta positions read as a chain-uniform scalar by any term, in first-use order."""
+    out: List[int] = []
+    for t in ir.terms:
+        for o in t.ops:
+            if o.opcode in (I.OP["ld_x"], I.OP["ld_z"]) and o.mode == I.MODE_SCALAR and o.base not in out:
+                out.append(o.base)
+    return out
+
+
+def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelIR":
+    """Plan every eligible term of ``ir`` in place, lay out the ``part`` array and fill the pools."""
+    for term in ir.terms:
         term.plan = None
-        res = plan_term(t_idx, term, ir.datai, ir.dataf)
-        if res is None:
-            continue
-        plan, meta, recs = res
+    T = int(team_warps) if team_warps else choose_team_warps(ir)
+    if T not in TEAM_SIZES:
+        raise ValueError("team_warps must be one of %s" % (TEAM_SIZES,))
+    TL = 32 * T
+    ir.team_warps = T
+    R = max(1, -(-ir.D // TL))
+    DPt = R * TL
+    ir.scalar_pos = scalar_positions(ir)
+
+    tplans: List[_TermPlan] = []
+    for t_idx, term in enumerate(ir.terms):
+        tp = _chunk_term(t_idx, term, ir.datai, ir.dataf, TL)
+        if tp is not None:
+            tplans.append(tp)
+            term.plan = tp.plan
+
+    # ---- layout of the part array: contributions of element j are consecutive ----
+    n_chunk_contrib = np.zeros(ir.D, dtype=np.int64)
+    for tp in tplans:
+        per_group = Counter(g for g, _ in tp.chunk_elems)
+        for base in tp.gather_bases:
+            for g, c in per_group.items():
+                n_chunk_contrib[base + int(tp.targets[g])] += c
+    cnt = n_chunk_contrib.copy()
+    for pos in ir.scalar_pos:
+        cnt[pos] += T
+    if cnt.max(initial=0) >= (1 << ELEM_CNT_BITS):
+        raise NotImplementedError("an element of theta receives more than %d partial sums" % ((1 << ELEM_CNT_BITS) - 1))
+    first = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    lp_first = int(-(-int(cnt.sum()) // 4) * 4)  # read with one vector load: keep it 16-byte aligned
+    part_reals = lp_first + T
+    if part_reals >= (1 << (31 - ELEM_CNT_BITS)):
+        raise NotImplementedError("part array too large for the packed element table")
+    elem_tab = np.zeros(DPt, dtype=np.int32)
+    elem_tab[: ir.D] = (first << ELEM_CNT_BITS) | cnt
+    # scalar blocks come after the chunk entries of their element
+    spart = [int(first[pos] + n_chunk_contrib[pos]) for pos in ir.scalar_pos] + [lp_first]
+    used = np.zeros(ir.D, dtype=np.int64)  # chunk entries handed out so far, per element
+
+    fparts, iparts, flen, ilen = [], [], 0, 0
+    for tp in tplans:
+        pl = tp.plan
+        n_g = len(tp.gather_bases)
+        SW = -(-(2 + n_g) // 4)
+        n_slices = pl.n_slices
+        slices = np.zeros((n_slices, 4), dtype=np.int32)
+        slots = np.zeros((n_slices * TL, 4 * SW), dtype=np.int32)
+        slots[:, 0] = -1
+        rec_rows = 0
+        for s in range(n_slices):
+            lens = [len(e) for _, e in tp.chunk_elems[s * TL:(s + 1) * TL]]
+            # both loops of the device walk are unrolled by ROW_UNROLL without remainder: the unmasked
+            # prefix is rounded down, the slice's row count up (padding rows are zero records, masked)
+            full = (lens[-1] if len(lens) == TL else 0) // ROW_UNROLL * ROW_UNROLL
+            rows = -(-lens[0] // ROW_UNROLL) * ROW_UNROLL
+            slices[s] = (full, rows, rec_rows, 0)
+            rec_rows += rows
+        recs = np.zeros((rec_rows, TL, pl.width), dtype=np.float64)
+        for slot, (g, elems) in enumerate(tp.chunk_elems):
+            s, lane = divmod(slot, TL)
+            tgt = int(tp.targets[g])
+            row = [tgt, len(elems)]
+            for base in tp.gather_bases:
+                j = base + tgt
+                row.append(int(first[j] + used[j]))
+                used[j] += 1
+            slots[slot, : len(row)] = row
+            for w, col in enumerate(tp.cols):
+                recs[slices[s, 2]: slices[s, 2] + len(elems), lane, w] = col[elems]
+        o_slices = HEADER
+        o_slots = o_slices + slices.size
+        header = np.array([n_slices, o_slices, o_slots, SW], dtype=np.int32)
+        meta = np.concatenate([header, slices.reshape(-1), slots.reshape(-1)]).astype(np.int32)
         fpad, ipad = (-flen) % 4, (-ilen) % 4
         if fpad:
             fparts.append(np.zeros(fpad)); flen += fpad
         if ipad:
             iparts.append(np.zeros(ipad, dtype=np.int32)); ilen += ipad
-        plan.meta_off, plan.recs_off = ilen, flen
-        fparts.append(recs); flen += len(recs)
+        pl.meta_off, pl.recs_off = ilen, flen
+        fparts.append(recs.reshape(-1)); flen += recs.size
         iparts.append(meta); ilen += len(meta)
-        term.plan = plan
+    assert np.array_equal(used, n_chunk_contrib)
+
+    # model-level tables at the end of the metadata pool
+    ipad = (-ilen) % 4
+    if ipad:
+        iparts.append(np.zeros(ipad, dtype=np.int32)); ilen += ipad
+    ir.elem_off = ilen
+    iparts.append(elem_tab); ilen += len(elem_tab)
+    ir.spart_off = ilen
+    sp = np.zeros(-(-len(spart) // 4) * 4, dtype=np.int32)
+    sp[: len(spart)] = spart
+    iparts.append(sp); ilen += len(sp)
+    ir.part_reals = int(-(-part_reals // 4) * 4)
     # pools are copied with 16-byte bulk transfers: pad to a multiple of 4 elements
     if flen % 4:
         fparts.append(np.zeros(4 - flen % 4))
-    if ilen % 4:
-        iparts.append(np.zeros(4 - ilen % 4, dtype=np.int32))
     ir.planf = np.concatenate(fparts) if fparts else np.zeros(0)
-    ir.plani = np.concatenate(iparts).astype(np.int32) if iparts else np.zeros(0, dtype=np.int32)
+    ir.plani = np.concatenate(iparts).astype(np.int32)
     return ir

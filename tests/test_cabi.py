@@ -43,10 +43,11 @@ def test_struct_layouts_match_the_header(tmp_path):
         "pm4_term_t": (I.CTerm, ["kind", "n", "op_begin", "op_end", "n_regs", "value_reg", "param_reg", "plan"]),
         "pm4_op_t": (I.COp, ["opcode", "dst", "a", "b", "mode", "base", "blob", "imm"]),
         "pm4_det_t": (I.CDet, ["n", "op_begin", "op_end", "n_regs", "value_reg", "out_offset"]),
-        "pm4_plan_t": (I.CPlan, ["term", "n_gather", "n_part", "width", "meta", "recs"]),
+        "pm4_plan_t": (I.CPlan, ["term", "n_gather", "width", "meta", "recs"]),
         "pm4_ir_t": (I.CIR, ["abi_version", "D", "n_rv", "n_terms", "n_ops", "n_dets", "det_row", "rvs", "terms",
                              "ops", "dets", "n_dataf", "dataf", "n_datai", "datai", "struct_hash", "n_plans",
-                             "plans", "n_planf", "planf", "n_plani", "plani"]),
+                             "plans", "n_planf", "planf", "n_plani", "plani", "team_warps", "part_reals",
+                             "elem_off", "spart_off"]),
         "pm4_adapt_cfg_t": (_cstructs.AdaptCfg, ["mode", "num_adaptation_steps", "target_accept_prob",
                                                  "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled"]),
         "pm4_hmc_cfg_t": (_cstructs.HMCCfg, ["C", "num_results", "num_burnin", "num_leapfrog_steps", "step_size",
@@ -77,7 +78,7 @@ def test_generated_module_builds_for_sm100a_with_tma_bulk_copy():
     assert os.path.exists(path) and ir.struct_hash_hex in path and codegen.generator_hash() in path
     lib = ctypes.CDLL(path)
     for sym in ("pm4m_info", "pm4m_logp_grad", "pm4m_dets", "pm4m_init", "pm4m_nuts", "pm4m_hmc",
-                "pm4m_da_pooled", "pm4m_export_eps"):
+                "pm4m_da_pooled", "pm4m_export_eps", "pm4m_scratch_bytes", "pm4m_lpt_order"):
         assert hasattr(lib, sym), sym
     elf = subprocess.run(["cuobjdump", "-lelf", path], stdout=subprocess.PIPE, text=True).stdout
     assert "sm_100a" in elf

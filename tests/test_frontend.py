@@ -192,8 +192,8 @@ def test_kwarg_routing_by_signature():
     assert s.stat_names == ["lp", "tree_size", "diverging", "energy", "mean_tree_accept"]
 
 
-@pytest.mark.parametrize("sorted_idx", [True, False])
-def test_execution_plan_is_a_permutation(sorted_idx):
+@pytest.mark.parametrize("sorted_idx,team", [(True, 1), (False, 1), (True, 4), (False, 2)])
+def test_execution_plan_is_a_permutation(sorted_idx, team):
     rng = np.random.default_rng(1)
     n, G = 700, 37
     idx = rng.integers(0, G, n).astype(np.int32)
@@ -201,39 +201,53 @@ def test_execution_plan_is_a_permutation(sorted_idx):
     if sorted_idx:
         idx = np.sort(idx)
     x, y = rng.normal(size=n), rng.normal(size=n)
-    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, G))
+    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, G), team_warps=team)
+    assert ir.team_warps == team
+    TL = 32 * team
     (pl,) = ir.plans
     meta = ir.plani[pl.meta_off:]
-    n_slices, n_split, n_part, o_sl, o_st, o_sp = meta[:6]
+    n_slices, o_sl, o_st, SW = meta[:4]
+    assert SW == 1  # two gather ops (alpha, beta): target, length and two part indices fill one int4
     slices = meta[o_sl:o_sl + 4 * n_slices].reshape(-1, 4)
-    slots = meta[o_st:o_st + 4 * 32 * n_slices].reshape(-1, 4)
-    recs = ir.planf[pl.recs_off:].reshape(-1, 32, pl.width)
+    slots = meta[o_st:o_st + 4 * TL * n_slices].reshape(-1, 4)
+    recs = ir.planf[pl.recs_off:pl.recs_off + int(slices[:, 1].sum()) * TL * pl.width].reshape(-1, TL, pl.width)
     seen = []
     per_target = {}
-    for slot, (tgt, ln, pidx, _) in enumerate(slots):
-        s, lane = divmod(slot, 32)
+    for slot, (tgt, ln, pa, pb) in enumerate(slots):
+        s, lane = divmod(slot, TL)
         full, mx, first, _ = slices[s]
         assert ln <= mx and (tgt < 0) == (ln == 0) and (ln >= full or tgt < 0)
         if tgt >= 0:
             rows = recs[first:first + ln, lane]
             seen.append(rows)
-            per_target.setdefault(int(tgt), []).append((ln, int(pidx)))
+            per_target.setdefault(int(tgt), []).append((ln, int(pa), int(pb)))
             assert np.all(recs[first + ln:first + mx, lane] == 0)  # padding
     got = np.concatenate(seen)
     want = np.stack([y, x], axis=1)  # record order = op order of the data loads: value y first, then x
     assert got.shape == want.shape
     assert np.array_equal(np.sort(got.view([("a", float), ("b", float)]), axis=0),
                           np.sort(want.view([("a", float), ("b", float)]), axis=0))
+    # the part array: every gradient element's contributions are consecutive and nothing overlaps
+    R = -(-ir.D // TL)
+    elem = ir.plani[ir.elem_off:ir.elem_off + TL * R]
+    first_of, cnt_of = elem >> 12, elem & 4095
+    assert np.all(elem[ir.D:] == 0)
+    covered = np.zeros(ir.part_reals, dtype=int)
+    for j in range(ir.D):
+        covered[first_of[j]:first_of[j] + cnt_of[j]] += 1
+    spart = ir.plani[ir.spart_off:ir.spart_off + len(ir.scalar_pos) + 1]
+    covered[spart[-1]:spart[-1] + team] += 1  # log-density partials, one per warp
+    assert covered.max() == 1 and covered[:int(cnt_of.sum())].min() == 1 and spart[-1] % 4 == 0
     sizes = np.bincount(idx, minlength=G)
+    a_off, b_off = ir.rv_by_name("hierarchical_model/alpha").offset, ir.rv_by_name("hierarchical_model/beta").offset
     for tgt, chunks in per_target.items():
-        assert sum(l for l, _ in chunks) == sizes[tgt]
-        if len(chunks) == 1:
-            assert chunks[0][1] == -1
-        else:
-            ps = sorted(p for _, p in chunks)
-            assert ps == list(range(ps[0], ps[0] + len(ps))) and ps[-1] < n_part
-    split = meta[o_sp:o_sp + 4 * n_split].reshape(-1, 4)
-    assert {int(t) for t in split[:, 0]} == {t for t, ch in per_target.items() if len(ch) > 1}
+        assert sum(l for l, _, _ in chunks) == sizes[tgt]
+        for off, col in ((a_off, 1), (b_off, 2)):
+            ps = sorted(c[col] for c in chunks)
+            j = off + tgt
+            assert ps == list(range(first_of[j], first_of[j] + len(ps))) and cnt_of[j] == len(ps)
+    for k, pos in enumerate(ir.scalar_pos):  # scalar parameters: one partial per warp, after any chunk sums
+        assert cnt_of[pos] == team and spart[k] == first_of[pos]
 
 
 def test_step_size_conventions():
