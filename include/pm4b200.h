@@ -173,8 +173,9 @@ typedef struct pm4_ir {
    * per-chain `part` array described by two tables at the end of plani (pymc4_b200/plan.py) */
   int32_t team_warps;   /* 1, 2, 4, 8, 16 or 32; must match the kernel module              */
   int32_t part_reals;   /* length of the per-chain part array (multiple of 4)              */
-  int64_t elem_off;     /* plani offset of elem_tab[32*team_warps*R]: first << 12 | count  */
-  int64_t spart_off;    /* plani offset of spart[n_scalar + 1]                             */
+  int64_t elem_off;     /* plani offset of elem_tab[32*team_warps*R]: overflow first << 12 | count */
+  int64_t spart_off;    /* plani offset of spart[(n_scalar + 1) * team_warps]                */
+  int64_t phdr_off;     /* plani offset of the per-plan int4 headers                         */
 } pm4_ir_t;
 
 typedef struct pm4_model pm4_model_t;

@@ -145,7 +145,17 @@ class _ModuleGen:
                "  static __device__ __forceinline__ void constrain(int r, int tl, real z, real& x, real& dxdz) {",
                "    const int j = tl + %d * r; (void)j;" % self.TL,
                "    x = z; dxdz = (real)1;"]
+        # consecutive variables with the same transform share one range test (one branch, not one each)
+        merged: List[I.RV] = []
         for rv in self.ir.rvs:
+            prev = merged[-1] if merged else None
+            if (prev is not None and prev.offset + prev.size == rv.offset
+                    and (prev.transform, prev.shift, prev.scale) == (rv.transform, rv.shift, rv.scale)):
+                merged[-1] = I.RV(name=prev.name, shape=(prev.size + rv.size,), offset=prev.offset,
+                                  size=prev.size + rv.size, transform=prev.transform, shift=prev.shift, scale=prev.scale)
+            else:
+                merged.append(rv)
+        for rv in merged:
             cond = "j >= %d && j < %d" % (rv.offset, rv.offset + rv.size)
             if rv.transform == I.TR_EXP:
                 out.append("    if (%s) { const real e = pm4::m_exp(z); dxdz = %s * e; x = %s + dxdz; }"
@@ -370,7 +380,6 @@ class _ModuleGen:
             return loop
 
         loop = gen_body(None)
-        loop_masked = gen_body("on") if shape == "planned" else []
 
         for reg in sorted(uacc):
             E("real %s_ua%d = 0;" % (tag, reg), 3)
@@ -399,13 +408,13 @@ class _ModuleGen:
             n_g = len(gather_names)
             SW = -(-(2 + n_g) // 4)
             rec_t = "typename pm4::Rec<real, %d>::type" % plan.width
-            E("const int %s = __ldg(A.term_n + %d);" % (n_expr, k), 3)
-            E("const int32_t* %s_pm = c.pi + __ldg(A.plan_off + %d);" % (tag, 2 * plan_idx), 3)
-            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + __ldg(A.plan_off + %d)) + tl;"
-              % (rec_t, tag, rec_t, 2 * plan_idx + 1), 3)
-            E("const int4 %s_h0 = *reinterpret_cast<const int4*>(%s_pm);      // n_slices, o_slices, o_slots, SW" % (tag, tag), 3)
-            E("const int4* %s_sl = reinterpret_cast<const int4*>(%s_pm + %s_h0.y);" % (tag, tag, tag), 3)
-            E("const int4* %s_st = reinterpret_cast<const int4*>(%s_pm + %s_h0.z) + tl * %d;" % (tag, tag, tag, SW), 3)
+            E("const int4 %s_h0 = *reinterpret_cast<const int4*>(c.pi + A.phdr_off + %d);  // n_slices, slices, records, n"
+              % (tag, 4 * plan_idx), 3)
+            E("const int %s = %s_h0.w;" % (n_expr, tag), 3)
+            E("const int4* %s_sl = reinterpret_cast<const int4*>(c.pi + %s_h0.y);" % (tag, tag), 3)
+            E("const int4* %s_st = %s_sl + %s_h0.x + tl * %d;" % (tag, tag, tag, SW), 3)
+            E("const %s* %s_pr = reinterpret_cast<const %s*>(c.pf + %s_h0.z) + tl;" % (rec_t, tag, rec_t, tag), 3)
+            E("#pragma unroll 1", 3)
             E("for (int s = 0; s < %s_h0.x; ++s) {" % tag, 3)
             E("const int4 sl = %s_sl[s];        // rows all lanes walk, rows in the slice, first record row" % tag, 4)
             E("const int4 st = %s_st[s * %d];   // gather target, chunk length, part index per gather op" % (tag, TL * SW), 4)
@@ -415,23 +424,22 @@ class _ModuleGen:
             for dst, nm in gather_names.items():
                 E("const real %sv = c.xs[%d + tgt]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
             E("const %s* rp = %s_pr + sl.z * %d;" % (rec_t, tag, TL), 4)
-            E("int i0 = 0;", 4)
-            E("for (; i0 < sl.x; i0 += 4) {   // rows every lane has: no mask", 4)
+            E("int i = 0;", 4)
+            E("#pragma unroll 1", 4)
+            E("for (; i + 4 <= len; i += 4) {   // per-lane trip count: lanes with shorter chunks drop out", 4)
+            E("%s %s_rq[4];" % (rec_t, tag), 5)
+            E("#pragma unroll", 5)
+            E("for (int u = 0; u < 4; ++u) %s_rq[u] = rp[(i + u) * %d];" % (tag, TL), 5)
             E("#pragma unroll", 5)
             E("for (int u = 0; u < 4; ++u) {", 5)
-            E("const int i = i0 + u; (void)i;", 5)
-            E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
+            E("const %s %s_rec = %s_rq[u]; (void)%s_rec;" % (rec_t, tag, tag, tag), 5)
             self.lines.extend(loop)
             E("}", 5)
             E("}", 4)
-            E("for (; i0 < sl.y; i0 += 4) {   // ragged rows: branch-free, padded records contribute zero", 4)
-            E("#pragma unroll", 5)
-            E("for (int u = 0; u < 4; ++u) {", 5)
-            E("const int i = i0 + u;", 5)
+            E("#pragma unroll 1", 4)
+            E("for (; i < len; ++i) {", 4)
             E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
-            E("const bool on = i < len;", 5)
-            self.lines.extend(loop_masked)
-            E("}", 5)
+            self.lines.extend(loop)
             E("}", 4)
             E("if (st.x >= 0) {  // park the chunk's adjoint sums where the owner of the element collects them", 4)
             fields = ["x", "y", "z", "w"]

@@ -15,7 +15,7 @@
 namespace pm4 {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int ELEM_CNT_BITS = 12;  // elem_tab entry = first << 12 | count (pymc4_b200/plan.py)
+constexpr int ELEM_CNT_BITS = 12;  // elem_tab entry = overflow first << 12 | count (pymc4_b200/plan.py)
 
 // constant pools and run-time sizes the generated code reads (device pointers)
 template <typename real> struct ModelArgs {
@@ -26,12 +26,12 @@ template <typename real> struct ModelArgs {
   const real* __restrict__ planf;
   const int32_t* __restrict__ plani;
   const int32_t* __restrict__ plan_off;
-  int n_planf, n_plani, part_reals, elem_off, spart_off, stage;
+  int n_planf, n_plani, part_reals, elem_off, spart_off, phdr_off, stage;
 };
 
 template <typename real> __host__ __device__ inline ModelArgs<real> make_model_args(const pm4_mod_args_t& a) {
   return ModelArgs<real>{(const real*)a.dataf, a.datai, a.term_n, a.op_blob, (const real*)a.planf, a.plani,
-                         a.plan_off, a.n_planf, a.n_plani, a.part_reals, a.elem_off, a.spart_off, a.stage};
+                         a.plan_off, a.n_planf, a.n_plani, a.part_reals, a.elem_off, a.spart_off, a.phdr_off, a.stage};
 }
 
 // per-lane evaluation context handed to the generated model code
@@ -106,6 +106,9 @@ template <int T, typename real> __device__ __forceinline__ real sum_consecutive(
   } else if constexpr (sizeof(real) == 8 && T == 2) {
     const double2 v = *reinterpret_cast<const double2*>(p);
     return v.x + v.y;
+  } else if constexpr (sizeof(real) == 8 && T == 4) {
+    const double2 v = *reinterpret_cast<const double2*>(p), w = *reinterpret_cast<const double2*>(p + 2);
+    return ((v.x + v.y) + w.x) + w.y;
   } else {
     real s = p[0];
 #pragma unroll

@@ -66,7 +66,7 @@ struct pm4_model {
   pm4m_export_eps_fn f_eps = nullptr;
   pm4m_scratch_bytes_fn f_scratch = nullptr;
   pm4m_lpt_order_fn f_order = nullptr;
-  int elem_off = 0, spart_off = 0;
+  int elem_off = 0, spart_off = 0, phdr_off = 0;
   float* d_f32 = nullptr;
   double* d_f64 = nullptr;
   int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
@@ -91,6 +91,7 @@ struct pm4_model {
     a.part_reals = part_reals;
     a.elem_off = elem_off;
     a.spart_off = spart_off;
+    a.phdr_off = phdr_off;
     // stage the plan pools in shared memory when they leave room for the per-chain state
     const size_t pool_bytes = (size_t)n_planf * (dtype == PM4_F64 ? 8 : 4) + (size_t)n_plani * 4;
     a.stage = (pool_bytes <= 96 * 1024) ? 1 : 0;
@@ -117,11 +118,13 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   }
   CU(cudaMemcpy(m->d_plan_off, off.data(), sizeof(int32_t) * off.size(), cudaMemcpyHostToDevice));
   if (ir->team_warps != m->info.T) return fail(PM4_EINVAL, "IR is laid out for teams of %d warps, the kernel module for %d", ir->team_warps, m->info.T);
-  if (ir->elem_off < 0 || ir->elem_off + m->info.DP > ni || ir->spart_off < 0 || ir->spart_off >= ni || ir->part_reals <= 0)
+  if (ir->elem_off < 0 || ir->elem_off + m->info.DP > ni || ir->spart_off < 0 || ir->spart_off >= ni ||
+      ir->phdr_off < 0 || ir->phdr_off + 4 * ir->n_plans > ni || ir->part_reals <= 0)
     return fail(PM4_EINVAL, "part-array tables point outside the plan metadata pool");
   m->part_reals = ir->part_reals;
   m->elem_off = (int)ir->elem_off;
   m->spart_off = (int)ir->spart_off;
+  m->phdr_off = (int)ir->phdr_off;
   return PM4_OK;
 }
 

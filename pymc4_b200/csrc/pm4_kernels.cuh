@@ -101,11 +101,14 @@ __device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned
   c.ctl = reinterpret_cast<int32_t*>(w);
   w += 4;
   c.scr = w;
-  // the lane that ends up holding packed-reduction value k parks it at spart[k] + warp
+  // the lane that ends up holding packed-reduction value k parks it at spart[k][warp]
   constexpr int per = 32 / M::P;
   const int k = c.lane / per;
-  c.my_spart = ((c.lane % per) == 0 && k <= M::N_ACC) ? c.pi[A.spart_off + k] + c.warp : -1;
-  c.lp_first = c.pi[A.spart_off + M::N_ACC];
+  c.my_spart = ((c.lane % per) == 0 && k <= M::N_ACC) ? c.pi[A.spart_off + k * T + c.warp] : -1;
+  c.lp_first = c.pi[A.spart_off + M::N_ACC * T];
+  // part entries nobody writes must read as zero for the whole launch
+  for (int i = c.tl; i < A.part_reals; i += TL) c.part[i] = 0;
+  team_sync<T>(c.bar);
   return c;
 }
 
@@ -139,9 +142,14 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
   const real lp = sum_consecutive<T, real>(c.part + c.lp_first);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int first = own[r] >> ELEM_CNT_BITS, cnt = own[r] & ((1 << ELEM_CNT_BITS) - 1);
-    real s = gr[r];
-    for (int k = 0; k < cnt; ++k) s += c.part[first + k];
+    // the element's 4 fixed entries with one vector load, then the (rare) overflow vectors
+    real s = gr[r] + sum_consecutive<4, real>(c.part + 4 * (c.tl + TL * r));
+    if (own[r]) {
+      const real* ov = c.part + (own[r] >> ELEM_CNT_BITS);
+      const int cnt = own[r] & ((1 << ELEM_CNT_BITS) - 1);
+#pragma unroll 1
+      for (int k = 0; k < cnt; ++k) s += sum_consecutive<4, real>(ov + 4 * k);
+    }
     if (M::NEEDS_GX) s += c.gx[c.tl + TL * r];
     g[r] = s * dxdz[r];
   }

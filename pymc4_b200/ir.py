@@ -154,8 +154,10 @@ class ModelIR:
     team_warps: int = 1
     scalar_pos: List[int] = field(default_factory=list)
     elem_off: int = 0      # offset of elem_tab[DPt] in plani
-    spart_off: int = 0     # offset of spart[n_scalar + 1] in plani
+    spart_off: int = 0     # offset of spart[(n_scalar + 1) * T] in plani
+    phdr_off: int = 0      # offset of the per-plan int4 headers in plani
     part_reals: int = 4
+    part_k: int = 2        # fixed part entries per gradient element
 
     @property
     def plans(self) -> List["Plan"]:
@@ -525,7 +527,7 @@ class CIR(ctypes.Structure):
                 ("n_planf", ctypes.c_int64), ("planf", ctypes.POINTER(ctypes.c_double)),
                 ("n_plani", ctypes.c_int64), ("plani", ctypes.POINTER(ctypes.c_int32)),
                 ("team_warps", ctypes.c_int32), ("part_reals", ctypes.c_int32),
-                ("elem_off", ctypes.c_int64), ("spart_off", ctypes.c_int64)]
+                ("elem_off", ctypes.c_int64), ("spart_off", ctypes.c_int64), ("phdr_off", ctypes.c_int64)]
 
 
 class PackedIR:
@@ -575,7 +577,7 @@ class PackedIR:
             len(plans), 0, ctypes.cast(cplans, ctypes.POINTER(CPlan)),
             self._planf.size, self._planf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
             self._plani.size, self._plani.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
-            ir.team_warps, ir.part_reals, ir.elem_off, ir.spart_off,
+            ir.team_warps, ir.part_reals, ir.elem_off, ir.spart_off, ir.phdr_off,
         )
 
     def byref(self):

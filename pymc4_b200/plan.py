@@ -15,26 +15,30 @@ registers, adjoints accumulate in registers, observation records are read with c
 shared-memory loads.  Every chunk then parks its adjoint sums in the chain's ``part`` array.
 
 The ``part`` array is the single hand-over point between the lanes that *produce* adjoints and the
-lane that *owns* a gradient element: the contributions to element ``j`` (chunk sums of every
-gather op that targets it, and -- for parameters read as scalars -- one warp-level partial sum per
-warp of the team) occupy the consecutive entries ``[first_j, first_j + cnt_j)``; after one team
-barrier the owner adds them in index order.  No atomics, no second pass, a fixed summation order
-(same seed => same trace).  ``elem_tab[j] = first_j << 12 | cnt_j``; ``spart[k]`` is the first entry
-of the k-th scalar parameter's block (``ModelIR.scalar_pos`` order), ``spart[n_scalar]`` that of the
-log-density partials.
+lane that *owns* a gradient element.  Element ``j`` owns the K = 4 fixed entries ``part[4 j .. 4 j + 4)``,
+read with ONE vector load after one team barrier; its contributions (chunk sums of every gather op
+that targets it, then -- for parameters read as scalars -- one warp-level partial sum per warp of
+the team) fill them in order, entries nobody writes stay zero (the array is zeroed once per
+launch).  An element with more than 4 contributions (a group cut into many chunks) continues in an
+overflow block of ``ocnt_j`` 4-entry vectors starting at ``ofirst_j`` that its owner adds in a
+loop: ``elem_tab[j] = ofirst_j << 12 | ocnt_j`` (0 for almost every element).  No atomics, no second
+pass, a fixed summation order (same seed => same trace).  ``spart[k * T + w]`` is the entry warp w
+parks the k-th scalar parameter's adjoint at (``ModelIR.scalar_pos`` order); row ``n_scalar`` is the
+log-density (T consecutive entries, 16-byte aligned).
 
 The plan depends on the index *values*, so it lives in two run-time pools (``planf`` records,
 ``plani`` metadata); the generated code only depends on which ops are planned and on ``T``.  The CPU
 oracle ignores plans and evaluates the original tape, which is what makes the parity tests a check
 of this layout.
 
-Per-plan metadata (int32, offsets relative to the start of the plan's metadata, 16-byte aligned):
-  header[4]   n_slices, o_slices, o_slots, SW (int4 words per slot)
-  slices      int4 per slice: rows every lane walks unmasked (min length rounded down to a multiple
-              of ROW_UNROLL), rows in the slice (max length rounded up), first record row, 0
-  slots       SW int4 per (slice, lane): gather target (-1 = empty lane), chunk length, then the
-              ``part`` index of the chunk for every gather op of the plan
+Per-plan metadata (int32, 16-byte aligned):
+  slices      int4 per slice: shortest chunk (0 if a lane is empty), longest chunk = record rows of
+              the slice, first record row, 0
+  slots       SW int4 per (slice, lane), right after the slices: gather target (-1 = empty lane),
+              chunk length, then the ``part`` index of the chunk for every gather op of the plan
 Records (reals): row-major [row][lane][width]; row r of slice s is ``first_row + r``.
+Model tables at the end of the metadata pool: ``elem_tab[DP]``, ``spart[(n_scalar + 1) T]``, and one
+int4 header per plan ``(n_slices, plani offset of the slices, planf offset of the records, n)``.
 """
 from __future__ import annotations
 
@@ -46,7 +50,6 @@ import numpy as np
 
 from . import ir as I
 
-HEADER = 4
 ROW_UNROLL = 4
 MAX_GATHER_OPS = 6
 ELEM_CNT_BITS = 12
@@ -84,17 +87,16 @@ def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
 
 
 def _cost(chunks: List[Tuple[int, int]], TL: int) -> float:
+    """Warp-instructions per warp of one evaluation: every warp pays for the longest chunk of each
+    slice, for the slice bookkeeping, and (the unluckiest owner lane) for overflow vectors."""
     lens = sorted((l for _, l in chunks), reverse=True)
     n_slices = -(-len(lens) // TL)
     cost = 0.0
     for s in range(n_slices):
-        sl = lens[s * TL:(s + 1) * TL]
-        full = (sl[-1] if len(sl) == TL else 0) // ROW_UNROLL * ROW_UNROLL
-        rows = -(-sl[0] // ROW_UNROLL) * ROW_UNROLL
-        cost += 6.5 * full + 8.0 * (rows - full) + 24.0  # unmasked rows, masked rows, slice overhead
-    # every chunk is one more entry its owner lane adds up (worst lane of a warp decides)
+        cost += 7.0 * lens[s * TL] + 10.0 + 30.0
     per_group = Counter(g for g, _ in chunks)
-    return cost + 2.0 * max(per_group.values())
+    over = max(0, -(-(max(per_group.values()) - 4) // 4))
+    return cost + 8.0 * over
 
 
 class _TermPlan:
@@ -191,7 +193,9 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
             tplans.append(tp)
             term.plan = tp.plan
 
-    # ---- layout of the part array: contributions of element j are consecutive ----
+    # ---- layout of the part array: K fixed entries per element, then overflow blocks, then lp ----
+    K = 4
+    ir.part_k = K
     n_chunk_contrib = np.zeros(ir.D, dtype=np.int64)
     for tp in tplans:
         per_group = Counter(g for g, _ in tp.chunk_elems)
@@ -201,17 +205,24 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
     cnt = n_chunk_contrib.copy()
     for pos in ir.scalar_pos:
         cnt[pos] += T
-    if cnt.max(initial=0) >= (1 << ELEM_CNT_BITS):
+    ocnt = -(-np.maximum(cnt - K, 0) // 4)  # overflow vectors of 4 entries
+    if ocnt.max(initial=0) >= (1 << ELEM_CNT_BITS):
         raise NotImplementedError("an element of theta receives more than %d partial sums" % ((1 << ELEM_CNT_BITS) - 1))
-    first = np.concatenate([[0], np.cumsum(cnt)])[:-1]
-    lp_first = int(-(-int(cnt.sum()) // 4) * 4)  # read with one vector load: keep it 16-byte aligned
+    ofirst = K * DPt + 4 * np.concatenate([[0], np.cumsum(ocnt)])[:-1]
+    lp_first = K * DPt + 4 * int(ocnt.sum())  # read with one vector load: 16-byte aligned
     part_reals = lp_first + T
     if part_reals >= (1 << (31 - ELEM_CNT_BITS)):
         raise NotImplementedError("part array too large for the packed element table")
     elem_tab = np.zeros(DPt, dtype=np.int32)
-    elem_tab[: ir.D] = (first << ELEM_CNT_BITS) | cnt
-    # scalar blocks come after the chunk entries of their element
-    spart = [int(first[pos] + n_chunk_contrib[pos]) for pos in ir.scalar_pos] + [lp_first]
+    elem_tab[: ir.D] = np.where(ocnt > 0, (ofirst << ELEM_CNT_BITS) | ocnt, 0)
+
+    def loc(j: int, o: int) -> int:  # part entry of the o-th contribution to element j
+        return K * j + o if o < K else int(ofirst[j]) + (o - K)
+
+    spart = []
+    for pos in ir.scalar_pos:
+        spart.extend(loc(pos, int(n_chunk_contrib[pos]) + w) for w in range(T))
+    spart.extend(lp_first + w for w in range(T))
     used = np.zeros(ir.D, dtype=np.int64)  # chunk entries handed out so far, per element
 
     fparts, iparts, flen, ilen = [], [], 0, 0
@@ -226,10 +237,10 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
         rec_rows = 0
         for s in range(n_slices):
             lens = [len(e) for _, e in tp.chunk_elems[s * TL:(s + 1) * TL]]
-            # both loops of the device walk are unrolled by ROW_UNROLL without remainder: the unmasked
-            # prefix is rounded down, the slice's row count up (padding rows are zero records, masked)
-            full = (lens[-1] if len(lens) == TL else 0) // ROW_UNROLL * ROW_UNROLL
-            rows = -(-lens[0] // ROW_UNROLL) * ROW_UNROLL
+            # every lane walks exactly its own chunk (per-lane trip count, the hardware masks the lanes
+            # that are done): a slice needs as many record rows as its longest chunk
+            full = lens[-1] if len(lens) == TL else 0
+            rows = lens[0]
             slices[s] = (full, rows, rec_rows, 0)
             rec_rows += rows
         recs = np.zeros((rec_rows, TL, pl.width), dtype=np.float64)
@@ -239,15 +250,12 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
             row = [tgt, len(elems)]
             for base in tp.gather_bases:
                 j = base + tgt
-                row.append(int(first[j] + used[j]))
+                row.append(loc(j, int(used[j])))
                 used[j] += 1
             slots[slot, : len(row)] = row
             for w, col in enumerate(tp.cols):
                 recs[slices[s, 2]: slices[s, 2] + len(elems), lane, w] = col[elems]
-        o_slices = HEADER
-        o_slots = o_slices + slices.size
-        header = np.array([n_slices, o_slices, o_slots, SW], dtype=np.int32)
-        meta = np.concatenate([header, slices.reshape(-1), slots.reshape(-1)]).astype(np.int32)
+        meta = np.concatenate([slices.reshape(-1), slots.reshape(-1)]).astype(np.int32)
         fpad, ipad = (-flen) % 4, (-ilen) % 4
         if fpad:
             fparts.append(np.zeros(fpad)); flen += fpad
@@ -268,6 +276,11 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
     sp = np.zeros(-(-len(spart) // 4) * 4, dtype=np.int32)
     sp[: len(spart)] = spart
     iparts.append(sp); ilen += len(sp)
+    ir.phdr_off = ilen
+    hdr = np.zeros((max(len(tplans), 1), 4), dtype=np.int32)
+    for k, tp in enumerate(tplans):
+        hdr[k] = (tp.plan.n_slices, tp.plan.meta_off, tp.plan.recs_off, ir.terms[tp.plan.term].n)
+    iparts.append(hdr.reshape(-1)); ilen += hdr.size
     ir.part_reals = int(-(-part_reals // 4) * 4)
     # pools are copied with 16-byte bulk transfers: pad to a multiple of 4 elements
     if flen % 4:

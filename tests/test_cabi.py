@@ -47,7 +47,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         "pm4_ir_t": (I.CIR, ["abi_version", "D", "n_rv", "n_terms", "n_ops", "n_dets", "det_row", "rvs", "terms",
                              "ops", "dets", "n_dataf", "dataf", "n_datai", "datai", "struct_hash", "n_plans",
                              "plans", "n_planf", "planf", "n_plani", "plani", "team_warps", "part_reals",
-                             "elem_off", "spart_off"]),
+                             "elem_off", "spart_off", "phdr_off"]),
         "pm4_adapt_cfg_t": (_cstructs.AdaptCfg, ["mode", "num_adaptation_steps", "target_accept_prob",
                                                  "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled"]),
         "pm4_hmc_cfg_t": (_cstructs.HMCCfg, ["C", "num_results", "num_burnin", "num_leapfrog_steps", "step_size",

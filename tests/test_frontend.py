@@ -205,18 +205,20 @@ def test_execution_plan_is_a_permutation(sorted_idx, team):
     assert ir.team_warps == team
     TL = 32 * team
     (pl,) = ir.plans
+    n_slices, meta_off, recs_off, n_term = ir.plani[ir.phdr_off:ir.phdr_off + 4]
+    assert (meta_off, recs_off, n_term) == (pl.meta_off, pl.recs_off, n) and n_slices == pl.n_slices
     meta = ir.plani[pl.meta_off:]
-    n_slices, o_sl, o_st, SW = meta[:4]
-    assert SW == 1  # two gather ops (alpha, beta): target, length and two part indices fill one int4
-    slices = meta[o_sl:o_sl + 4 * n_slices].reshape(-1, 4)
-    slots = meta[o_st:o_st + 4 * TL * n_slices].reshape(-1, 4)
+    slices = meta[:4 * n_slices].reshape(-1, 4)
+    # two gather ops (alpha, beta): target, length and two part indices fill one int4 per slot
+    slots = meta[4 * n_slices:4 * n_slices + 4 * TL * n_slices].reshape(-1, 4)
     recs = ir.planf[pl.recs_off:pl.recs_off + int(slices[:, 1].sum()) * TL * pl.width].reshape(-1, TL, pl.width)
+    assert list(slices[:, 2]) == list(np.concatenate([[0], np.cumsum(slices[:, 1])])[:-1])
     seen = []
     per_target = {}
     for slot, (tgt, ln, pa, pb) in enumerate(slots):
         s, lane = divmod(slot, TL)
         full, mx, first, _ = slices[s]
-        assert ln <= mx and (tgt < 0) == (ln == 0) and (ln >= full or tgt < 0)
+        assert ln <= mx and (tgt < 0) == (ln == 0) and ln >= full
         if tgt >= 0:
             rows = recs[first:first + ln, lane]
             seen.append(rows)
@@ -227,27 +229,35 @@ def test_execution_plan_is_a_permutation(sorted_idx, team):
     assert got.shape == want.shape
     assert np.array_equal(np.sort(got.view([("a", float), ("b", float)]), axis=0),
                           np.sort(want.view([("a", float), ("b", float)]), axis=0))
-    # the part array: every gradient element's contributions are consecutive and nothing overlaps
+    # the part array: K fixed entries per gradient element, overflow blocks, log-density partials;
+    # every entry has at most one writer and every contribution is reachable from its owner
+    K = ir.part_k
     R = -(-ir.D // TL)
     elem = ir.plani[ir.elem_off:ir.elem_off + TL * R]
-    first_of, cnt_of = elem >> 12, elem & 4095
+    ofirst, ocnt = elem >> 12, elem & 4095
     assert np.all(elem[ir.D:] == 0)
-    covered = np.zeros(ir.part_reals, dtype=int)
-    for j in range(ir.D):
-        covered[first_of[j]:first_of[j] + cnt_of[j]] += 1
-    spart = ir.plani[ir.spart_off:ir.spart_off + len(ir.scalar_pos) + 1]
-    covered[spart[-1]:spart[-1] + team] += 1  # log-density partials, one per warp
-    assert covered.max() == 1 and covered[:int(cnt_of.sum())].min() == 1 and spart[-1] % 4 == 0
+
+    assert K == 4 and np.all(ofirst[ocnt > 0] % 4 == 0)
+
+    def owned(j):
+        return list(range(K * j, K * j + K)) + list(range(ofirst[j], ofirst[j] + 4 * ocnt[j]))
+
+    spart = ir.plani[ir.spart_off:ir.spart_off + (len(ir.scalar_pos) + 1) * team].reshape(-1, team)
+    writers = np.zeros(ir.part_reals, dtype=int)
     sizes = np.bincount(idx, minlength=G)
     a_off, b_off = ir.rv_by_name("hierarchical_model/alpha").offset, ir.rv_by_name("hierarchical_model/beta").offset
     for tgt, chunks in per_target.items():
         assert sum(l for l, _, _ in chunks) == sizes[tgt]
         for off, col in ((a_off, 1), (b_off, 2)):
-            ps = sorted(c[col] for c in chunks)
-            j = off + tgt
-            assert ps == list(range(first_of[j], first_of[j] + len(ps))) and cnt_of[j] == len(ps)
-    for k, pos in enumerate(ir.scalar_pos):  # scalar parameters: one partial per warp, after any chunk sums
-        assert cnt_of[pos] == team and spart[k] == first_of[pos]
+            ps = [c[col] for c in chunks]
+            assert sorted(ps) == owned(off + tgt)[:len(ps)]  # filled in order: fixed entries first
+            writers[ps] += 1
+    for k, pos in enumerate(ir.scalar_pos):  # scalar parameters: one partial per warp
+        assert set(spart[k]) <= set(owned(pos))
+        writers[spart[k]] += 1
+    writers[spart[-1]] += 1  # log-density partials, one per warp, one aligned vector
+    assert writers.max() == 1 and spart[-1][0] % 4 == 0 and list(spart[-1]) == list(range(spart[-1][0], spart[-1][0] + team))
+    assert ir.part_reals >= spart[-1][-1] + 1  # entries nobody writes are zeroed once per launch
 
 
 def test_step_size_conventions():
