@@ -284,7 +284,7 @@ def run_b200(args):
         sampler.start()
     barrier()
     _cabi.launch_count(reset=True)
-    step_ms, leaps = [], 0
+    step_ms, leaps, detail = [], 0, []
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # evict L2 between timed steps (not timed)
@@ -294,7 +294,12 @@ def run_b200(args):
         e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        leaps += int(out["total_leapfrogs"].sum().item())
+        per_chain = out["total_leapfrogs"]
+        leaps += int(per_chain.sum().item())
+        # a chain is sequential: the longest one bounds the step from below (critical path)
+        detail.append({"ms": step_ms[-1], "leapfrogs": int(per_chain.sum().item()),
+                       "max_chain_leapfrogs": int(per_chain.max().item()),
+                       "mean_chain_leapfrogs": float(per_chain.float().mean().item())})
     barrier()
     wall = time.perf_counter() - wall0
     launches = _cabi.launch_count()
@@ -364,7 +369,8 @@ def run_b200(args):
     roofline = {
         "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": (ach_tflops / fp32_peak) if fp32_peak else None, "traffic": None,
-        "kernel": "pm4::nuts_kernel (one launch per step; bootstrap + export kernels are <0.1% of the step)",
+        "kernel": "pm4::nuts_kernel (persistent blocks, 3 launches per step: transitions [0,20), [20,B], (B,B+S); "
+                  "bootstrap, chain-ordering and export kernels are <0.1% of the step)",
         "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
         "peak_source": "FFMA microbenchmark run by this bench on this GPU (csrc/pm4_peaks.cu); "
                        "MEASURED_PEAKS.json has no FP32-pipe entry",
@@ -386,6 +392,7 @@ def run_b200(args):
                         "mean_accept": mean_accept, "divergent_frac": divergent,
                         "mean_leapfrogs_per_draw": mean_tree},
         "wall_s_timed_region": wall,
+        "steps_detail": detail,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(ir, args)

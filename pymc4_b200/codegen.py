@@ -45,8 +45,9 @@ CSRC = os.path.join(_HERE, "csrc")
 CACHE_DIR = os.environ.get("PM4_KERNEL_CACHE", os.path.join(_HERE, "_kcache"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-# threads per block of the persistent single-precision kernels (registers per thread = 65536 / MAXT)
-MAXT = int(os.environ.get("PM4_MAXT", "1024"))
+# threads per block of the persistent single-precision kernels (registers per thread = 65536 / MAXT):
+# 512 = 128 registers, no spills; measured best on the radon model (1024: 64 registers, 280 B of spills)
+MAXT = int(os.environ.get("PM4_MAXT", "512"))
 _build_lock = threading.Lock()
 
 _UNARY_FWD = {
@@ -135,6 +136,9 @@ class _ModuleGen:
         self.lines: List[str] = []
         self.scalar_pos: List[int] = list(ir.scalar_pos)  # scalar x positions, part-array order
         self.needs_gx = False
+        # element-independent terms run on ONE lane: lane 0 of the team's last warp (chunks are dealt
+        # longest-first, so the first warp is the one with the most rows to walk)
+        self.uni_lane = self.TL - 32
 
     def emit(self, s: str = "", ind: int = 2):
         self.lines.append("  " * ind + s)
@@ -387,7 +391,7 @@ class _ModuleGen:
         # 3. the loop itself
         n_expr = str(t.n)
         if shape == "uniform":
-            E("if (tl == 0) {", 3)
+            E("if (tl == %d) {" % self.uni_lane, 3)
             E("const int i = 0; (void)i;", 5)
             self.lines.extend(loop)
             E("}", 3)
@@ -458,13 +462,13 @@ class _ModuleGen:
         # 4. factored Normal: the sums enter the log-density and the scale adjoint once
         if normal_fast:
             E("lp += (real)-0.5 * %s * %s_S2;" % (K, tag), 3)
-            E("if (tl == 0) lp -= (real)%s * (pm4::K<real>::HALF_LOG_2PI + %s_log_s);" % (n_expr, tag), 3)
+            E("if (tl == %d) lp -= (real)%s * (pm4::K<real>::HALF_LOG_2PI + %s_log_s);" % (self.uni_lane, n_expr, tag), 3)
             if depends[scale_reg]:
                 uacc.setdefault(scale_reg, False)
                 decl = "" if uacc[scale_reg] else "real "
                 # d/d scale = sum (w^2 - 1) / scale = K * S2 / scale - n / scale
-                E("%s%s_ua%d %s %s * %s_S2 * %s_inv_s - (tl == 0 ? (real)%s * %s_inv_s : (real)0);"
-                  % (decl, tag, scale_reg, "+=" if uacc[scale_reg] else "=", K, tag, tag, n_expr, tag), 3)
+                E("%s%s_ua%d %s %s * %s_S2 * %s_inv_s - (tl == %d ? (real)%s * %s_inv_s : (real)0);"
+                  % (decl, tag, scale_reg, "+=" if uacc[scale_reg] else "=", K, tag, tag, self.uni_lane, n_expr, tag), 3)
                 uacc[scale_reg] = True
 
         # 5. epilogue: reverse sweep over the element-independent ops with lane-partial adjoints

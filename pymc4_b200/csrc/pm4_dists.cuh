@@ -24,16 +24,21 @@ template <> struct K<double> {
 };
 
 // ---- math shims (float / double overload sets) ---------------------------------------------
-// FP32 path: MUFU-based exp / log / reciprocal (relative error ~1e-6, two orders below the 1e-5 parity
-// bound); the FP64 path keeps the correctly rounded library functions.
-__device__ __forceinline__ float m_exp(float v) { return __expf(v); }
+// FP32 path: bare MUFU exp2 / log2 / reciprocal (ex2.approx, lg2.approx, rcp.approx with flush-to-zero;
+// relative error ~1e-6, two orders below the 1e-5 parity bound) without the denormal-range fix-ups of
+// __expf / __logf / __fdividef: arguments here are scales, densities and acceptance ratios, never
+// denormal.  The FP64 path keeps the correctly rounded library functions.
+__device__ __forceinline__ float mufu_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float mufu_lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float mufu_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float m_exp(float v) { return mufu_ex2(v * 1.4426950408889634f); }
 __device__ __forceinline__ double m_exp(double v) { return exp(v); }
-__device__ __forceinline__ float m_log(float v) { return __logf(v); }
+__device__ __forceinline__ float m_log(float v) { return mufu_lg2(v) * 0.6931471805599453f; }
 __device__ __forceinline__ double m_log(double v) { return log(v); }
 __device__ __forceinline__ float m_log1p(float v) {
   // log1p only matters near 0, where the series is exact enough and cheaper than the MUFU path's cancellation
   const float a = fabsf(v);
-  return a < 1e-3f ? v * (1.0f - 0.5f * v + 0.33333334f * v * v) : __logf(1.0f + v);
+  return a < 1e-3f ? v * (1.0f - 0.5f * v + 0.33333334f * v * v) : m_log(1.0f + v);
 }
 __device__ __forceinline__ double m_log1p(double v) { return log1p(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
@@ -46,7 +51,7 @@ __device__ __forceinline__ float m_abs(float v) { return fabsf(v); }
 __device__ __forceinline__ double m_abs(double v) { return fabs(v); }
 __device__ __forceinline__ float m_lgamma(float v) { return lgammaf(v); }
 __device__ __forceinline__ double m_lgamma(double v) { return lgamma(v); }
-__device__ __forceinline__ float m_rcp(float v) { return __fdividef(1.0f, v); }
+__device__ __forceinline__ float m_rcp(float v) { return mufu_rcp(v); }
 __device__ __forceinline__ double m_rcp(double v) { return 1.0 / v; }
 __device__ __forceinline__ bool m_isnan(float v) { return isnan(v); }
 __device__ __forceinline__ bool m_isnan(double v) { return isnan(v); }

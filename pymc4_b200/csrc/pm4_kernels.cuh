@@ -855,7 +855,7 @@ inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, const Ge
 
 // threads per block of the big single-precision variant: registers per thread = 65536 / PM4_MAXT
 #ifndef PM4_MAXT
-#define PM4_MAXT 1024
+#define PM4_MAXT 512
 #endif
 template <typename real> constexpr int max_threads_for() { return sizeof(real) == 8 ? 256 : PM4_MAXT; }
 

@@ -67,7 +67,7 @@ def choose_team_warps(ir: "I.ModelIR") -> int:
             raise ValueError("PM4_TEAM_WARPS must be one of %s" % (TEAM_SIZES,))
         return t
     work = sum(t.n for t in ir.terms)
-    want = max(work / 320.0, ir.D / 128.0)
+    want = max(work / 640.0, ir.D / 128.0)
     for t in TEAM_SIZES:
         if t >= want:
             return min(t, 8)
