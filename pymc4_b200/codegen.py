@@ -549,6 +549,7 @@ class _ModuleGen:
                len(ir.plans)),
             "  static constexpr int N_ACC = %d, P = %d;  // scalar adjoints reduced with the log-density, packed width"
             % (len(self.scalar_pos), self.P),
+            "  static constexpr int PK = %d;  // fixed part entries per gradient element" % int(ir.part_k),
             "  static constexpr bool NEEDS_GX = %s;  // some term scatters adjoints with atomics"
             % ("true" if self.needs_gx else "false"),
             "  static constexpr unsigned long long HASH = 0x%sull;" % ir.struct_hash_hex,

@@ -109,6 +109,14 @@ template <int T, typename real> __device__ __forceinline__ real sum_consecutive(
   } else if constexpr (sizeof(real) == 8 && T == 4) {
     const double2 v = *reinterpret_cast<const double2*>(p), w = *reinterpret_cast<const double2*>(p + 2);
     return ((v.x + v.y) + w.x) + w.y;
+  } else if constexpr (sizeof(real) == 4 && T % 4 == 0) {
+    real s = 0;
+#pragma unroll
+    for (int w = 0; w < T; w += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + w);
+      s = (((s + v.x) + v.y) + v.z) + v.w;
+    }
+    return s;
   } else {
     real s = p[0];
 #pragma unroll

@@ -112,11 +112,36 @@ __device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned
   return c;
 }
 
-// gradient-element ownership of this lane: elem_tab entries of elements tl, tl + TL, ...
-template <class M, typename real> __device__ __forceinline__ void load_own(const Ctx<real>& c, int (&own)[M::R]) {
+// Models whose state needs more than LEAN_R registers per lane and vector keep only theta, momentum
+// and gradient in registers: the trajectory momentum sums live in tree-scratch slots and per-element
+// constants (overflow table, step scale) are re-read where they are used.
+constexpr int LEAN_R = 4;
+
+// threads per block: the small variant (double precision, few chains, stateless kernels) and the big
+// single-precision variant; both hold at least one whole team
+#ifndef PM4_MAXT
+#define PM4_MAXT 512
+#endif
+template <class M> constexpr int small_threads() { return 32 * M::T > 256 ? 32 * M::T : 256; }
+template <class M> constexpr int big_threads() { return 32 * M::T > PM4_MAXT ? 32 * M::T : PM4_MAXT; }
+
+// gradient-element ownership of this lane: elem_tab entries of elements tl, tl + TL, ... (overflow
+// vectors of the part array; 0 for almost every element).  Small models hold them in registers.
+template <class M, typename real> struct Own {
+  int reg[M::R > LEAN_R ? 1 : M::R];
+  const int32_t* tab;
+  __device__ __forceinline__ void load(const Ctx<real>& c) {
+    tab = c.pi + c.A.elem_off + c.tl;
+    if constexpr (M::R <= LEAN_R) {
 #pragma unroll
-  for (int r = 0; r < M::R; ++r) own[r] = c.pi[c.A.elem_off + c.tl + 32 * M::T * r];
-}
+      for (int r = 0; r < M::R; ++r) reg[r] = tab[32 * M::T * r];
+    }
+  }
+  __device__ __forceinline__ int operator()(int r) const {
+    if constexpr (M::R <= LEAN_R) return reg[r];
+    else return tab[32 * M::T * r];
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // joint log-density + gradient in unconstrained space for the chain owned by this team.
@@ -125,7 +150,7 @@ template <class M, typename real> __device__ __forceinline__ void load_own(const
 // ------------------------------------------------------------------------------------------
 template <class M, typename real>
 __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R], Ctx<real>& c,
-                                          const int (&own)[M::R]) {
+                                          const Own<M, real>& own) {
   constexpr int R = M::R, T = M::T, TL = 32 * T;
   real x[R], dxdz[R], gr[R];
 #pragma unroll
@@ -142,11 +167,12 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
   const real lp = sum_consecutive<T, real>(c.part + c.lp_first);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    // the element's 4 fixed entries with one vector load, then the (rare) overflow vectors
-    real s = gr[r] + sum_consecutive<4, real>(c.part + 4 * (c.tl + TL * r));
-    if (own[r]) {
-      const real* ov = c.part + (own[r] >> ELEM_CNT_BITS);
-      const int cnt = own[r] & ((1 << ELEM_CNT_BITS) - 1);
+    // the element's PK fixed entries with one (vector) load, then the (rare) overflow vectors
+    real s = gr[r] + sum_consecutive<M::PK, real>(c.part + M::PK * (c.tl + TL * r));
+    const int ow = own(r);
+    if (ow) {
+      const real* ov = c.part + (ow >> ELEM_CNT_BITS);
+      const int cnt = ow & ((1 << ELEM_CNT_BITS) - 1);
 #pragma unroll 1
       for (int k = 0; k < cnt; ++k) s += sum_consecutive<4, real>(ov + 4 * k);
     }
@@ -160,7 +186,7 @@ __device__ __forceinline__ real logp_grad(const real (&th)[M::R], real (&g)[M::R
 // parity kernel (a): log-density and gradient for C independent states
 // ------------------------------------------------------------------------------------------
 template <class M, typename real, bool STAGED>
-__global__ void __launch_bounds__(256) logp_grad_kernel(ModelArgs<real> A, int C, int team_reals,
+__global__ void __launch_bounds__(small_threads<M>()) logp_grad_kernel(ModelArgs<real> A, int C, int team_reals,
                                                         const real* __restrict__ theta,
                                                         real* __restrict__ lp_out, real* __restrict__ grad_out) {
   constexpr int R = M::R, D = M::D, T = M::T, TL = 32 * T;
@@ -169,8 +195,8 @@ __global__ void __launch_bounds__(256) logp_grad_kernel(ModelArgs<real> A, int C
   const int tl = c.tl;
   const int chain = blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL;
   if (chain >= C) return;
-  int own[R];
-  load_own<M, real>(c, own);
+  Own<M, real> own;
+  own.load(c);
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -204,7 +230,7 @@ template <typename real> struct RunParams {
   ModelArgs<real> A;
   int C, t_begin, t_count, B, S, max_depth, num_leapfrog, chain_offset;
   int adapt_enabled, adapt_pooled, num_adapt;
-  int team_reals, n_slots;
+  int team_reals, n_slots, n_fast;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -236,7 +262,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.C = r.C; p.t_begin = r.t_begin; p.t_count = r.t_count; p.B = r.B; p.S = r.S;
   p.max_depth = r.max_depth; p.num_leapfrog = r.num_leapfrog; p.chain_offset = r.chain_offset;
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
-  p.team_reals = 0; p.n_slots = 0;
+  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -323,15 +349,15 @@ static __global__ void __launch_bounds__(256) lpt_order_kernel(int C, const int3
 
 // initial log-density / gradient of every chain (tfp bootstrap_results) + dual-averaging init
 template <class M, typename real, bool STAGED>
-__global__ void __launch_bounds__(256) init_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
+__global__ void __launch_bounds__(small_threads<M>()) init_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
   constexpr int R = M::R, D = M::D, DP = M::DP, T = M::T, TL = 32 * T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
   const int tl = c.tl;
   const int chain = blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL;
   if (chain >= a.C) return;
-  int own[R];
-  load_own<M, real>(c, own);
+  Own<M, real> own;
+  own.load(c);
   real th[R], g[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -382,22 +408,43 @@ __device__ __forceinline__ void draw_momentum(const RunParams<real>& a, int chai
 
 // one leapfrog step: tfp SimpleLeapfrogIntegrator with num_steps = 1:
 // half kick, drift, gradient, full kick, half un-kick.  es[r] = signed eps * per-dim scale.
-template <class M, typename real>
+template <class M, typename real, class Es>
 __device__ __forceinline__ real leapfrog(real (&th)[M::R], real (&p)[M::R], real (&g)[M::R],
-                                         const real (&es)[M::R], Ctx<real>& c, const int (&own)[M::R]) {
+                                         const Es& es, Ctx<real>& c, const Own<M, real>& own) {
 #pragma unroll
   for (int r = 0; r < M::R; ++r) {
-    p[r] = p[r] + ((real)0.5 * es[r]) * g[r];
-    th[r] = th[r] + es[r] * p[r];
+    const real e = es(r);
+    p[r] = p[r] + ((real)0.5 * e) * g[r];
+    th[r] = th[r] + e * p[r];
   }
   const real lp = logp_grad<M, real>(th, g, c, own);
 #pragma unroll
   for (int r = 0; r < M::R; ++r) {
-    p[r] = p[r] + es[r] * g[r];
-    p[r] = p[r] - ((real)0.5 * es[r]) * g[r];
+    const real e = es(r);
+    p[r] = p[r] + e * g[r];
+    p[r] = p[r] - ((real)0.5 * e) * g[r];
   }
   return lp;
 }
+
+// per-dimension step scale of this lane's elements: registers for small models, re-read otherwise
+template <class M, typename real> struct StepScale {
+  real reg[M::R > LEAN_R ? 1 : M::R];
+  const real* tab;  // NULL: every scale is 1
+  int tl;
+  __device__ __forceinline__ void load(const real* scale, int tl_) {
+    tab = scale;
+    tl = tl_;
+    if constexpr (M::R <= LEAN_R) {
+#pragma unroll
+      for (int r = 0; r < M::R; ++r) reg[r] = (scale && tl + 32 * M::T * r < M::D) ? scale[tl + 32 * M::T * r] : (real)1;
+    }
+  }
+  __device__ __forceinline__ real operator()(int r) const {
+    if constexpr (M::R <= LEAN_R) return reg[r];
+    else return (tab && tl + 32 * M::T * r < M::D) ? __ldg(tab + tl + 32 * M::T * r) : (real)1;
+  }
+};
 
 // next chain for this team from the global queue (-1: none left)
 template <int T, typename real> __device__ __forceinline__ int next_chain(const RunParams<real>& a, const Ctx<real>& c) {
@@ -419,27 +466,40 @@ template <int T, typename real> __device__ __forceinline__ int next_chain(const 
 // NUTS: tfp NoUTurnSampler.one_step -> _loop_tree_doubling -> _build_sub_tree ->
 // _loop_build_sub_tree in per-chain form, t_count transitions per chain per launch.
 // ------------------------------------------------------------------------------------------
+// SCR_SMEM: every tree-scratch slot of the team is in shared memory; otherwise the first a.n_fast
+// slots are (the hottest ones come first) and the rest live in global memory (L2).
 template <class M, typename real, int MAXT, bool STAGED, bool SCR_SMEM>
 __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
   constexpr int R = M::R, D = M::D, DP = M::DP, DS = M::DS, T = M::T, TL = 32 * T;
+  constexpr bool LEAN = R > LEAN_R;
+  // slot numbering: lean models keep rho and rho_sub in the two hottest slots
+  constexpr int S0 = LEAN ? 2 : 0;
+  constexpr int SL_RHO = 0, SL_RHO_SUB = 1;
+  constexpr int SL_OTH_TH = S0 + PM4_SLOT_OTH_TH, SL_OTH_P = S0 + PM4_SLOT_OTH_P, SL_OTH_G = S0 + PM4_SLOT_OTH_G;
+  constexpr int SL_CAND_TH = S0 + PM4_SLOT_CAND_TH, SL_CAND_G = S0 + PM4_SLOT_CAND_G;
+  constexpr int SL_SUB_TH = S0 + PM4_SLOT_SUB_TH, SL_SUB_G = S0 + PM4_SLOT_SUB_G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
   const int tl = c.tl, lane = c.lane;
   const real NEG_INF = -m_inf<real>();
   const size_t C = (size_t)a.C;
-  real* const scr = SCR_SMEM ? c.scr
-                             : a.scratch + ((size_t)blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL) * (size_t)a.n_slots * DS;
-  const int MEM_P = PM4_SLOT_MEM, MEM_RHO = PM4_SLOT_MEM + a.max_depth + 1;
+  real* const gscr = SCR_SMEM ? nullptr
+                              : a.scratch + ((size_t)blockIdx.x * (blockDim.x / TL) + threadIdx.x / TL) *
+                                                (size_t)(a.n_slots - a.n_fast) * DS;
+  const int MEM_P = S0 + PM4_SLOT_MEM, MEM_RHO = MEM_P + a.max_depth + 1;
   // element tl + TL r exists for every lane when TL (r + 1) <= D, else only for the first lanes
   auto in = [&](int r) -> bool { return (TL * (r + 1) <= D) || (tl + TL * r < D); };
-  auto ldv = [&](int s, int r) -> real { return in(r) ? scr[s * DS + tl + TL * r] : (real)0; };
-  auto stv = [&](int s, int r, real v) { if (in(r)) scr[s * DS + tl + TL * r] = v; };
+  auto sptr = [&](int s) -> real* {
+    if constexpr (SCR_SMEM) return c.scr + s * DS + tl;
+    else return (s < a.n_fast ? c.scr + s * DS : gscr + (size_t)(s - a.n_fast) * DS) + tl;
+  };
+  auto ldv = [&](int s, int r) -> real { return in(r) ? sptr(s)[TL * r] : (real)0; };
+  auto stv = [&](int s, int r, real v) { if (in(r)) sptr(s)[TL * r] = v; };
 
-  int own[R];
-  load_own<M, real>(c, own);
-  real sc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) sc[r] = (a.step_scale && tl + TL * r < D) ? a.step_scale[tl + TL * r] : (real)1;
+  Own<M, real> own;
+  own.load(c);
+  StepScale<M, real> sc;
+  sc.load(a.step_scale, tl);
   int rb = 0;  // which half of c.red the next team reduction uses
 
   for (;;) {
@@ -449,8 +509,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
     // the chain's current point lives in the candidate slots between transitions
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      stv(PM4_SLOT_CAND_TH, r, a.th[(size_t)chain * DP + tl + TL * r]);
-      stv(PM4_SLOT_CAND_G, r, a.gr[(size_t)chain * DP + tl + TL * r]);
+      stv(SL_CAND_TH, r, a.th[(size_t)chain * DP + tl + TL * r]);
+      stv(SL_CAND_G, r, a.gr[(size_t)chain * DP + tl + TL * r]);
     }
     real clp = a.lp[chain];
     DualAvg<real> da;
@@ -458,7 +518,12 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
     int launch_leaps = 0;
 
     for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
-      real th[R], p[R], g[R], rho[R], rho_sub[R], es[R];
+      real th[R], p[R], g[R];
+      real rho_reg[LEAN ? 1 : R], rho_sub_reg[LEAN ? 1 : R];
+      auto rho = [&](int r) -> real { if constexpr (LEAN) return ldv(SL_RHO, r); else return rho_reg[r]; };
+      auto set_rho = [&](int r, real v) { if constexpr (LEAN) stv(SL_RHO, r, v); else rho_reg[r] = v; };
+      auto rho_sub = [&](int r) -> real { if constexpr (LEAN) return ldv(SL_RHO_SUB, r); else return rho_sub_reg[r]; };
+      auto set_rho_sub = [&](int r, real v) { if constexpr (LEAN) stv(SL_RHO_SUB, r, v); else rho_sub_reg[r] = v; };
       const real eps = da.eps;
       draw_momentum<M, real>(a, chain, t, tl, p);
       real q[4];
@@ -466,13 +531,13 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
       // both trajectory ends and the candidate start at the current point
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        th[r] = ldv(PM4_SLOT_CAND_TH, r);
-        g[r] = ldv(PM4_SLOT_CAND_G, r);
-        rho[r] = p[r];
+        th[r] = ldv(SL_CAND_TH, r);
+        g[r] = ldv(SL_CAND_G, r);
+        set_rho(r, p[r]);
         q[0] += p[r] * p[r];
-        stv(PM4_SLOT_OTH_TH, r, th[r]);
-        stv(PM4_SLOT_OTH_P, r, p[r]);
-        stv(PM4_SLOT_OTH_G, r, g[r]);
+        stv(SL_OTH_TH, r, th[r]);
+        stv(SL_OTH_P, r, p[r]);
+        stv(SL_OTH_G, r, g[r]);
       }
       team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
       rb ^= 1;
@@ -494,19 +559,18 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             real v;
-            v = ldv(PM4_SLOT_OTH_TH, r); stv(PM4_SLOT_OTH_TH, r, th[r]); th[r] = v;
-            v = ldv(PM4_SLOT_OTH_P, r); stv(PM4_SLOT_OTH_P, r, p[r]); p[r] = v;
-            v = ldv(PM4_SLOT_OTH_G, r); stv(PM4_SLOT_OTH_G, r, g[r]); g[r] = v;
+            v = ldv(SL_OTH_TH, r); stv(SL_OTH_TH, r, th[r]); th[r] = v;
+            v = ldv(SL_OTH_P, r); stv(SL_OTH_P, r, p[r]); p[r] = v;
+            v = ldv(SL_OTH_G, r); stv(SL_OTH_G, r, g[r]); g[r] = v;
           }
           const real sw = cur_lp; cur_lp = oth_lp; oth_lp = sw;
           cur_is_right = dir;
         }
         const int nsteps = 1 << depth;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          rho_sub[r] = 0;
-          es[r] = (dir ? eps : -eps) * sc[r];
-        }
+        for (int r = 0; r < R; ++r) set_rho_sub(r, 0);
+        const real eps_s = dir ? eps : -eps;
+        auto es = [&](int r) -> real { return eps_s * sc(r); };
         real w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
         bool cont_sub = true;
         int sub_leaps = 0;
@@ -527,9 +591,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
           if (i & 1) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              rho_sub[r] += p[r];
+              const real rs = rho_sub(r) + p[r];
+              set_rho_sub(r, rs);
               const real mp = ldv(MEM_P + pc - 1, r);
-              const real df = rho_sub[r] - ldv(MEM_RHO + pc - 1, r);
+              const real df = rs - ldv(MEM_RHO + pc - 1, r);
               q[0] += p[r] * p[r];
               q[1] += df * mp;
               q[2] += df * p[r];
@@ -538,9 +603,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
             // even leaves are checkpointed into slot popcount(i): (p_i, rho before this leaf)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
+              const real before = rho_sub(r);
               stv(MEM_P + pc, r, p[r]);
-              stv(MEM_RHO + pc, r, rho_sub[r]);
-              rho_sub[r] += p[r];
+              stv(MEM_RHO + pc, r, before);
+              set_rho_sub(r, before + p[r]);
               q[0] += p[r] * p[r];
             }
           }
@@ -556,11 +622,12 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
               u4[0] = 0; u4[1] = 0; u4[2] = 0; u4[3] = 0;
 #pragma unroll
               for (int r = 0; r < R; ++r) {
-                const real df = rho_sub[r] - ldv(MEM_RHO + s, r);
+                const real rs = rho_sub(r);
+                const real df = rs - ldv(MEM_RHO + s, r);
                 u4[0] += df * ldv(MEM_P + s, r);
                 u4[1] += df * p[r];
                 if (two) {
-                  const real df2 = rho_sub[r] - ldv(MEM_RHO + s - 1, r);
+                  const real df2 = rs - ldv(MEM_RHO + s - 1, r);
                   u4[2] += df2 * ldv(MEM_P + s - 1, r);
                   u4[3] += df2 * p[r];
                 }
@@ -584,8 +651,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
           if (u <= thresh) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-              stv(PM4_SLOT_SUB_TH, r, th[r]);
-              stv(PM4_SLOT_SUB_G, r, g[r]);
+              stv(SL_SUB_TH, r, th[r]);
+              stv(SL_SUB_G, r, g[r]);
             }
             sub_lp = cur_lp;
             sub_energy = energy;
@@ -606,8 +673,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
         if ((umerge <= thresh) && cont_sub) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            stv(PM4_SLOT_CAND_TH, r, ldv(PM4_SLOT_SUB_TH, r));
-            stv(PM4_SLOT_CAND_G, r, ldv(PM4_SLOT_SUB_G, r));
+            stv(SL_CAND_TH, r, ldv(SL_SUB_TH, r));
+            stv(SL_CAND_G, r, ldv(SL_SUB_G, r));
           }
           cand_lp = sub_lp;
           cand_energy = sub_energy;
@@ -616,9 +683,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
         q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          rho[r] += rho_sub[r];
-          q[0] += rho[r] * p[r];
-          q[1] += rho[r] * ldv(PM4_SLOT_OTH_P, r);
+          const real rr = rho(r) + rho_sub(r);
+          set_rho(r, rr);
+          q[0] += rr * p[r];
+          q[1] += rr * ldv(SL_OTH_P, r);
         }
         team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
         rb ^= 1;
@@ -640,7 +708,7 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int j = tl + TL * r;
-            if (j < D) __stcs(a.states + k * D + j, ldv(PM4_SLOT_CAND_TH, r));
+            if (j < D) __stcs(a.states + k * D + j, ldv(SL_CAND_TH, r));
           }
         }
         if (tl == 0) {
@@ -657,8 +725,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
     // persist the chain for the next launch
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      a.th[(size_t)chain * DP + tl + TL * r] = ldv(PM4_SLOT_CAND_TH, r);
-      a.gr[(size_t)chain * DP + tl + TL * r] = ldv(PM4_SLOT_CAND_G, r);
+      a.th[(size_t)chain * DP + tl + TL * r] = ldv(SL_CAND_TH, r);
+      a.gr[(size_t)chain * DP + tl + TL * r] = ldv(SL_CAND_G, r);
     }
     if (tl == 0) {
       a.lp[chain] = clp;
@@ -679,49 +747,48 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
   Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
   const int tl = c.tl;
   const size_t C = (size_t)a.C;
-  int own[R];
-  load_own<M, real>(c, own);
-  real sc[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) sc[r] = (a.step_scale && tl + TL * r < D) ? a.step_scale[tl + TL * r] : (real)1;
+  Own<M, real> own;
+  own.load(c);
+  StepScale<M, real> sc;
+  sc.load(a.step_scale, tl);
   int rb = 0;
 
   for (;;) {
     const int chain = next_chain<T, real>(a, c);
     if (chain < 0) break;
-    real cth[R], cg[R];
+    // the chain's current point stays in global memory (a.th / a.gr): read at the start of a
+    // transition, rewritten when a proposal is accepted
+    real* const cth = a.th + (size_t)chain * DP + tl;
+    real* const cg = a.gr + (size_t)chain * DP + tl;
     real clp = a.lp[chain];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cth[r] = a.th[(size_t)chain * DP + tl + TL * r];
-      cg[r] = a.gr[(size_t)chain * DP + tl + TL * r];
-    }
     DualAvg<real> da;
     da.load(a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4));
 
     for (int t = a.t_begin; t < a.t_begin + a.t_count; ++t) {
-      real es[R], th[R], p[R], g[R], q[4];
+      real th[R], p[R], g[R], q[4];
+      const real eps = da.eps;
+      auto es = [&](int r) -> real { return eps * sc(r); };
       draw_momentum<M, real>(a, chain, t, tl, p);
       q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        es[r] = da.eps * sc[r]; th[r] = cth[r]; g[r] = cg[r];
+        th[r] = cth[TL * r]; g[r] = cg[TL * r];
         q[0] += p[r] * p[r];
       }
       // half kick, L x (drift, gradient, full kick), half un-kick
 #pragma unroll
-      for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es[r]) * g[r];
+      for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es(r)) * g[r];
       real plp = clp;
       for (int l = 0; l < a.num_leapfrog; ++l) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) th[r] = th[r] + es[r] * p[r];
+        for (int r = 0; r < R; ++r) th[r] = th[r] + es(r) * p[r];
         plp = logp_grad<M, real>(th, g, c, own);
 #pragma unroll
-        for (int r = 0; r < R; ++r) p[r] = p[r] + es[r] * g[r];
+        for (int r = 0; r < R; ++r) p[r] = p[r] + es(r) * g[r];
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        p[r] = p[r] - ((real)0.5 * es[r]) * g[r];
+        p[r] = p[r] - ((real)0.5 * es(r)) * g[r];
         q[1] += p[r] * p[r];
       }
       team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
@@ -745,7 +812,7 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
       }
       if (ok) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) { cth[r] = th[r]; cg[r] = g[r]; }
+        for (int r = 0; r < R; ++r) { cth[TL * r] = th[r]; cg[TL * r] = g[r]; }
         clp = plp;
       }
       const real accept = m_exp(lar < 0 ? lar : (real)0);
@@ -759,7 +826,7 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const int j = tl + TL * r;
-            if (j < D) a.states[k * D + j] = cth[r];
+            if (j < D) a.states[k * D + j] = ok ? th[r] : cth[TL * r];
           }
         }
         if (tl == 0) {
@@ -768,11 +835,6 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
           if (a.diverging) a.diverging[k] = ok ? 1 : 0;
         }
       }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      a.th[(size_t)chain * DP + tl + TL * r] = cth[r];
-      a.gr[(size_t)chain * DP + tl + TL * r] = cg[r];
     }
     if (tl == 0) {
       a.lp[chain] = clp;
@@ -801,7 +863,7 @@ inline int sm_count() {
 // Launch geometry of the persistent chain kernels: teams per block, whether the tree scratch lives
 // in shared memory, bytes of dynamic shared memory.
 struct Geometry {
-  int teams, grid, team_reals, n_slots, stage, scr_smem;
+  int teams, grid, team_reals, n_slots, n_fast, stage, scr_smem;
   size_t smem;
 };
 
@@ -827,15 +889,20 @@ inline Geometry plan_geometry(ModelArgs<real>& A, int C, int wpb, int n_slots, i
   g.scr_smem = 1;
   int t_scr = teams;
   while (t_scr > 1 && pool_bytes(A) + (size_t)t_scr * (base + scr) * sizeof(real) > SMEM_LIMIT) --t_scr;
+  g.n_fast = n_slots;
   if (pool_bytes(A) + (size_t)t_scr * (base + scr) * sizeof(real) > SMEM_LIMIT || t_scr * 4 < teams) {
+    // hybrid: as many of the hottest slots on chip as fit beside the per-team arrays, the rest in L2
     g.scr_smem = 0;
     while (teams > 1 && pool_bytes(A) + (size_t)teams * base * sizeof(real) > SMEM_LIMIT) --teams;
     if (pool_bytes(A) + (size_t)teams * base * sizeof(real) > SMEM_LIMIT) A.stage = 0;
+    const size_t used = pool_bytes(A) + (size_t)teams * base * sizeof(real);
+    const size_t room = used < SMEM_LIMIT ? (SMEM_LIMIT - used) / ((size_t)teams * M::DS * sizeof(real)) : 0;
+    g.n_fast = (int)(room < (size_t)n_slots ? room : (size_t)n_slots);
   } else {
     teams = t_scr;
   }
   g.teams = teams;
-  g.team_reals = (int)(base + (g.scr_smem ? scr : 0));
+  g.team_reals = (int)(base + (size_t)g.n_fast * M::DS);
   g.stage = A.stage;
   g.smem = pool_bytes(A) + (size_t)teams * g.team_reals * sizeof(real);
   int grid = (C + teams - 1) / teams;
@@ -853,23 +920,24 @@ inline int launch_chain_kernel(Kernel kernel, const RunParams<real>& p, const Ge
   return (int)cudaGetLastError();
 }
 
-// threads per block of the big single-precision variant: registers per thread = 65536 / PM4_MAXT
-#ifndef PM4_MAXT
-#define PM4_MAXT 512
-#endif
-template <typename real> constexpr int max_threads_for() { return sizeof(real) == 8 ? 256 : PM4_MAXT; }
+template <class M, typename real> constexpr int max_threads_for() {
+  return sizeof(real) == 8 ? small_threads<M>() : big_threads<M>();
+}
 
 // tree-scratch vector slots of a run (HMC keeps its state in registers)
-inline int scratch_slots(bool nuts, int max_depth) { return nuts ? PM4_SLOT_MEM + 2 * (max_depth + 1) : 0; }
+template <class M> inline int scratch_slots(bool nuts, int max_depth) {
+  return nuts ? (M::R > LEAN_R ? 2 : 0) + PM4_SLOT_MEM + 2 * (max_depth + 1) : 0;
+}
 
 template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_mod_run_t& r, int wpb, cudaStream_t st) {
   RunParams<real> p = make_run_params<real>(r);
-  const int n_slots = scratch_slots(NUTS, r.max_depth);
-  Geometry g = plan_geometry<M, real>(p.A, r.C, wpb, n_slots, max_threads_for<real>());
+  const int n_slots = scratch_slots<M>(NUTS, r.max_depth);
+  Geometry g = plan_geometry<M, real>(p.A, r.C, wpb, n_slots, max_threads_for<M, real>());
   p.team_reals = g.team_reals;
   p.n_slots = n_slots;
+  p.n_fast = g.n_fast;
   if (NUTS && !g.scr_smem && !p.scratch) return (int)cudaErrorInvalidValue;
-  const bool small = g.teams * M::T * 32 <= 256;
+  const bool small = g.teams * M::T * 32 <= small_threads<M>();
 #define PM4_LAUNCH(MAXT)                                                                                              \
   do {                                                                                                                \
     if constexpr (NUTS) {                                                                                             \
@@ -884,8 +952,8 @@ template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_m
       return launch_chain_kernel<M, real>(hmc_kernel<M, real, MAXT, false>, p, g, st);                                \
     }                                                                                                                 \
   } while (0)
-  if (small) PM4_LAUNCH(256);
-  if constexpr (sizeof(real) == 4) PM4_LAUNCH(PM4_MAXT);
+  if (small) PM4_LAUNCH(small_threads<M>());
+  if constexpr (sizeof(real) == 4) PM4_LAUNCH(big_threads<M>());
 #undef PM4_LAUNCH
   return (int)cudaErrorInvalidConfiguration;
 }
@@ -918,7 +986,7 @@ extern "C" int pm4m_info(pm4_mod_info_t* out) {
 namespace pm4 {
 // geometry of the stateless kernels: one team per chain, up to 256 threads per block, no tree scratch
 template <class M, typename real> inline Geometry small_geometry(ModelArgs<real>& A, int C) {
-  Geometry g = plan_geometry<M, real>(A, C, 0, 0, 256);
+  Geometry g = plan_geometry<M, real>(A, C, 0, 0, small_threads<M>());
   g.grid = (C + g.teams - 1) / g.teams;
   return g;
 }
@@ -967,10 +1035,10 @@ template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0
 template <typename real> int64_t mod_scratch_bytes(const pm4_mod_args_t* A, int C, int wpb, int max_depth) {
   using M = PM4_MODEL;
   ModelArgs<real> ma = make_model_args<real>(*A);
-  const int n_slots = scratch_slots(true, max_depth);
-  const Geometry g = plan_geometry<M, real>(ma, C, wpb, n_slots, max_threads_for<real>());
+  const int n_slots = scratch_slots<M>(true, max_depth);
+  const Geometry g = plan_geometry<M, real>(ma, C, wpb, n_slots, max_threads_for<M, real>());
   if (g.scr_smem) return 0;
-  return (int64_t)g.grid * g.teams * n_slots * M::DS * (int64_t)sizeof(real);
+  return (int64_t)g.grid * g.teams * (n_slots - g.n_fast) * M::DS * (int64_t)sizeof(real);
 }
 }  // namespace pm4
 

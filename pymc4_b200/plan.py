@@ -15,11 +15,11 @@ registers, adjoints accumulate in registers, observation records are read with c
 shared-memory loads.  Every chunk then parks its adjoint sums in the chain's ``part`` array.
 
 The ``part`` array is the single hand-over point between the lanes that *produce* adjoints and the
-lane that *owns* a gradient element.  Element ``j`` owns the K = 4 fixed entries ``part[4 j .. 4 j + 4)``,
-read with ONE vector load after one team barrier; its contributions (chunk sums of every gather op
+lane that *owns* a gradient element.  Element ``j`` owns the K fixed entries ``part[K j .. K j + K)`` (K = 4;
+1 for very large states), read with ONE (vector) load after one team barrier; its contributions (chunk sums of every gather op
 that targets it, then -- for parameters read as scalars -- one warp-level partial sum per warp of
 the team) fill them in order, entries nobody writes stay zero (the array is zeroed once per
-launch).  An element with more than 4 contributions (a group cut into many chunks) continues in an
+launch).  An element with more than K contributions (a group cut into many chunks) continues in an
 overflow block of ``ocnt_j`` 4-entry vectors starting at ``ofirst_j`` that its owner adds in a
 loop: ``elem_tab[j] = ofirst_j << 12 | ocnt_j`` (0 for almost every element).  No atomics, no second
 pass, a fixed summation order (same seed => same trace).  ``spart[k * T + w]`` is the entry warp w
@@ -67,11 +67,13 @@ def choose_team_warps(ir: "I.ModelIR") -> int:
             raise ValueError("PM4_TEAM_WARPS must be one of %s" % (TEAM_SIZES,))
         return t
     work = sum(t.n for t in ir.terms)
-    want = max(work / 640.0, ir.D / 128.0)
+    # ~640 term elements per warp; at most ~20 state elements per lane (theta, momentum and gradient
+    # stay in registers); never more than 16 warps (512 threads keep 128 registers per thread)
+    want = max(work / 640.0, ir.D / (32.0 * 20.0))
     for t in TEAM_SIZES:
         if t >= want:
-            return min(t, 8)
-    return 8
+            return min(t, 16)
+    return 16 if ir.D <= 32 * 16 * 24 else 32
 
 
 def _chunks_for_cap(sizes: np.ndarray, cap: int) -> List[Tuple[int, int]]:
@@ -194,7 +196,7 @@ def attach_plans(ir: "I.ModelIR", team_warps: Optional[int] = None) -> "I.ModelI
             term.plan = tp.plan
 
     # ---- layout of the part array: K fixed entries per element, then overflow blocks, then lp ----
-    K = 4
+    K = 4 if DPt <= 4096 else 1  # large states cannot afford four shared-memory entries per element
     ir.part_k = K
     n_chunk_contrib = np.zeros(ir.D, dtype=np.int64)
     for tp in tplans:

@@ -59,6 +59,22 @@ def radon_synthetic(n_obs=919, n_groups=85, seed=20261019):
     return idx, x, y, n_groups
 
 
+def radon_large(n_obs=100_000, n_groups=5_000, seed=20261019):
+    """Radon-shaped data scaled up: group sizes ~ Poisson(20) + 1, renormalised
+    to n_obs observations; same generating parameters as radon_synthetic."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.poisson(20.0, n_groups) + 1
+    sizes = np.maximum(1, np.floor(sizes * (n_obs / sizes.sum())).astype(np.int64))
+    sizes[: n_obs - sizes.sum()] += 1
+    idx = np.repeat(np.arange(n_groups, dtype=np.int32), sizes)
+    assert idx.size == n_obs
+    x = (rng.random(n_obs) < 0.17).astype(np.float64)
+    a = rng.normal(1.5, 0.33, n_groups)
+    b = rng.normal(-0.65, 0.35, n_groups)
+    y = a[idx] + b[idx] * x + 0.72 * rng.standard_normal(n_obs)
+    return idx, x, y, n_groups
+
+
 def radon_model(real=False, **kw):
     idx, x, y, g = radon_real() if real else radon_synthetic(**kw)
     return hierarchical_model(idx, x, y, g)
