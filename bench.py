@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k"],
+                    help="radon919 = BASELINE configs[1] (the headline); radon100k = configs[4] shape "
+                         "(100k observations / 5k groups, D = 10 005; pass --chains/--burn-in/--draws to bound the run)")
     return ap.parse_args()
 
 
@@ -60,17 +63,31 @@ def build_model():
     from pymc4_b200.ir import lower_model
     from tests import models as M
 
-    idx, x, y, g = M.radon_synthetic(N_OBS, N_GROUPS)
+    if N_OBS == 919:
+        idx, x, y, g = M.radon_synthetic(N_OBS, N_GROUPS)
+    else:
+        idx, x, y, g = M.radon_large(N_OBS, N_GROUPS)
     model = M.hierarchical_model(idx, x, y, g)
     ir, _, _ = lower_model(model)
     assert ir.D == D_MODEL
     return model, ir
 
 
+def select_workload(name):
+    """Switch the module-level shape constants (the algorithmic cost per unit follows the shape)."""
+    global N_OBS, N_GROUPS, D_MODEL, FLOPS_PER_UNIT, ONCHIP_BYTES_PER_UNIT
+    if name == "radon100k":
+        N_OBS, N_GROUPS = 100_000, 5_000
+    D_MODEL = 2 * N_GROUPS + 5
+    FLOPS_PER_UNIT = 8 * N_OBS + 14 * N_GROUPS + 15 * D_MODEL
+    ONCHIP_BYTES_PER_UNIT = 12 * N_OBS
+
+
 def workload_config(args, n_gpus):
     return {
-        "workload": "radon_hierarchical varying-intercept/slope, synthetic %d obs / %d counties (D=%d), "
-                    "%d chains NUTS per GPU" % (N_OBS, N_GROUPS, D_MODEL, args.chains),
+        "workload": "radon_hierarchical varying-intercept/slope, synthetic %d obs / %d %s (D=%d), "
+                    "%d chains NUTS per GPU" % (N_OBS, N_GROUPS, "counties" if N_OBS == 919 else "groups", D_MODEL,
+                                                args.chains),
         "chains_per_gpu": args.chains,
         "global_chains": args.chains * n_gpus,
         "burn_in": args.burn_in,
@@ -380,6 +397,18 @@ def run_b200(args):
         "hbm": {"peak_gbs": peaks.get("hbm_gbs"), "source": peaks_src,
                 "note": "state and data are on-chip for this shape; HBM carries only the trace writes"},
     }
+    if args.workload == "radon100k":
+        # for the 100k shape the headline fraction is against HBM with 24 D bytes per unit
+        # (theta, momentum, gradient read and written once); this build keeps them in registers, so the
+        # figure says how far the kernel is from the point where HBM would start to matter
+        hbm_peak = peaks.get("hbm_gbs")
+        ach = units_per_step_gpu * 24.0 * D_MODEL / kernel_secs / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (ach / hbm_peak) if hbm_peak else None, "traffic": None,
+                    "kernel": roofline["kernel"], "algorithmic_bytes_per_unit": 24 * D_MODEL,
+                    "fp32": {"achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s"},
+                    "l2_records": {"achieved": ach_smem_tbs, "unit": "TB/s",
+                                   "note": "observation records (12 N bytes per unit) stream from L2, not shared memory"}}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_secs_max / max(args.steps, 1),
@@ -403,6 +432,7 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:
