@@ -4,8 +4,9 @@
 Workload (BASELINE.json configs[1]): synthetic radon hierarchical model, 919 observations /
 85 counties (D = 175), 4096 chains of NUTS per GPU.  One "step" = one complete sampling call of
 the hot path for that batch of chains: bootstrap + `burn_in` adaptive transitions + `draws`
-kept transitions from the common test point (dual averaging with a per-chain step size, i.e.
-`step_size` carrying a leading chain axis -- the reference's no-collective configuration).
+kept transitions from the common test point.  Default step-size policy = pm.sample's own default, a
+scalar `step_size` (one epsilon adapted from the mean acceptance of all chains of the rank);
+`--eps-mode per-chain` = `step_size` with a leading chain axis (independent adaptation).
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (the CPU implementation on the host cores)
@@ -45,14 +46,18 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
-    ap.add_argument("--burn-in", type=int, default=100)
-    ap.add_argument("--draws", type=int, default=100)
+    ap.add_argument("--burn-in", type=int, default=1000)  # S = 1000, B = 1000
+    ap.add_argument("--draws", type=int, default=1000)
     ap.add_argument("--step-size", type=float, default=0.1)
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--cpu-chains", type=int, default=0, help="chains of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--eps-mode", default="pooled", choices=["per-chain", "pooled"],
+                    help="per-chain: step_size with a leading chain axis (independent dual averaging, no coupling); "
+                         "pooled: scalar step_size, the reference default (one epsilon adapted from the mean "
+                         "acceptance of all chains of the rank: lock-step launches during burn-in)")
     ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k"],
                     help="radon919 = BASELINE configs[1] (the headline); radon100k = configs[4] shape "
                          "(100k observations / 5k groups, D = 10 005; pass --chains/--burn-in/--draws to bound the run)")
@@ -93,7 +98,9 @@ def workload_config(args, n_gpus):
         "burn_in": args.burn_in,
         "draws": args.draws,
         "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept NUTS transitions",
-        "step_size": "per-chain dual averaging from %.3g (leading chain axis; no cross-chain coupling)" % args.step_size,
+        "step_size": ("per-chain dual averaging from %.3g (leading chain axis; no cross-chain coupling)" % args.step_size)
+                     if args.eps_mode == "per-chain" else
+                     ("pooled dual averaging from %.3g (scalar step_size, reference default; one epsilon per rank)" % args.step_size),
         "max_tree_depth": 10,
         "parallelism": "chains sharded, %d per GPU; no data-path collective" % args.chains,
         "l2": "L2 flushed (256 MiB write) between timed steps",
@@ -105,11 +112,12 @@ def workload_config(args, n_gpus):
 # ------------------------------------------------------------------------------------------
 def cpu_sample_rate(ir, args, chains, seed):
     from oracle import pm4_oracle
-    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, make_adapt, make_nuts_cfg
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_nuts_cfg
 
     orc = pm4_oracle.Oracle(ir)
+    mode = PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED
     cfg = make_nuts_cfg(chains, args.draws, args.burn_in, step_size=args.step_size, seed=seed,
-                        adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=args.burn_in))
+                        adapt=make_adapt(mode=mode, num_adaptation_steps=args.burn_in))
     t0 = time.perf_counter()
     out = orc.nuts(cfg, np.zeros(ir.D), dtype=np.float32)
     dt = time.perf_counter() - t0
@@ -271,13 +279,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from pymc4_b200 import _cabi, diagnostics
-    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, make_adapt, make_nuts_cfg
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_nuts_cfg
     from pymc4_b200.mcmc.samplers import NUTS
 
     model, ir = build_model()
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
-    adapt = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)
+    adapt = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
+                       num_adaptation_steps=B)
 
     def cfg_for(step):
         return make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + step, adapt=adapt,
@@ -345,13 +354,14 @@ def run_b200(args):
     # ---- end-to-end arm: public sampler API, host buffers in, host trace out --------------
     e2e = None
     if not args.no_e2e:
-        step_arr = np.full((C, 1), args.step_size, dtype=np.float32)
+        step_arr = np.full((C, 1), args.step_size, dtype=np.float32) if args.eps_mode == "per-chain" else args.step_size
         nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C)
         e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
         n_e2e = max(1, min(args.steps, 2))
         for k in range(1 + n_e2e):  # first pass untimed (allocator / pinned-buffer warm-up)
             barrier()
             t0 = time.perf_counter()
+            trace = None  # release the previous trace's pinned host blocks before the next call
             trace = nuts(num_samples=S, num_chains=C, burn_in=B, seed=args.seed + 500 + k)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
@@ -370,7 +380,9 @@ def run_b200(args):
             e2e_secs, e2e_leaps = float(a[0]), float(b[1])
         e2e = {"value": e2e_leaps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_secs / n_e2e,
-               "api": "pymc4_b200.mcmc.samplers.NUTS(model, step_size=[C,1])(num_samples, num_chains, burn_in)"}
+               "api": "pymc4_b200.mcmc.samplers.NUTS(model, step_size=%s)(num_samples, num_chains, burn_in) -> InferenceData "
+                      "on the host (trace copied through pinned memory)"
+                      % ("[C,1]" if args.eps_mode == "per-chain" else "%g" % args.step_size)}
 
     if rank != 0:
         if world > 1:

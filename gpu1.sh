@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py --workload radon100k --chains 592 --burn-in 20 --draws 10 --step-size 0.001 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/t11_big.json 2> gpurun_out/t11_big.err; echo rc=$?
+for cfg in "100 100" "1000 1000"; do set -- $cfg
+timeout 900 python bench.py --eps-mode pooled --burn-in $1 --draws $2 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/t13_pooled_$1.json 2> gpurun_out/t13_pooled_$1.err; echo rc=$?
 python -c "
 import json
-d=json.loads(open('gpurun_out/t11_big.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['steps_detail'])"
-timeout 600 python -m pytest tests -m gpu -q -x -k "large" 2>&1 | tail -3
+d=json.loads(open('gpurun_out/t13_pooled_$1.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['diagnostics'], d['steps_detail'], d['ess_per_sec'])"
+tail -3 gpurun_out/t13_pooled_$1.err
+done

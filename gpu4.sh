@@ -1,6 +1,8 @@
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r1b_bench_n1.json 2> gpurun_out/r1b_bench_n1.err; echo "bench rc=$?"
-tail -c 1500 gpurun_out/r1b_bench_n1.json
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1b_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_l.log 2>&1
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1b_plain2.log 2>&1 && ncu --set full --import-source on --clock-control none -k regex:nuts_kernel -s 4 -c 1 -o gpurun_out/r1b_full -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r1b_ncu_f.log 2>&1
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
+( time python bench.py > gpurun_out/r1c_bench_n1.json 2> gpurun_out/r1c_bench_n1.err ) 2>&1 | tail -3; echo "bench rc=$?"
+python -c "
+import json
+d=json.loads(open('gpurun_out/r1c_bench_n1.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'], d['diagnostics'], d['roofline']['frac'], d['cpu_baseline'], d['ess_per_sec'])"
+( time python bench.py --impl reference > gpurun_out/r1c_ref_n1.json 2> gpurun_out/r1c_ref_n1.err ) 2>&1 | tail -3
+tail -c 400 gpurun_out/r1c_ref_n1.json
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -3

@@ -110,6 +110,36 @@ def _to_numpy(v) -> np.ndarray:
     return np.asarray(v)
 
 
+def _fetch_all(groups):
+    """Device tensors of several dicts -> NumPy arrays with ONE synchronisation: every tensor is
+    copied asynchronously into pinned host memory (torch caches pinned blocks between calls), so a
+    multi-gigabyte trace moves at PCIe speed instead of through pageable staging buffers."""
+    out, pending = [], []
+    for g in groups:
+        if not isinstance(g, dict):
+            out.append(g)
+            continue
+        conv = {}
+        for k, v in g.items():
+            if hasattr(v, "detach") and getattr(v, "is_cuda", False):
+                import torch
+
+                t = v.detach()
+                host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host.copy_(t, non_blocking=True)
+                pending.append(t.device)
+                conv[k] = host
+            else:
+                conv[k] = v
+        out.append(conv)
+    if pending:
+        import torch
+
+        for dev in set(pending):
+            torch.cuda.synchronize(dev)
+    return [({k: _to_numpy(v) for k, v in g.items()} if isinstance(g, dict) else g) for g in out]
+
+
 def trace_to_arviz(
     trace=None,
     sample_stats=None,
@@ -120,6 +150,11 @@ def trace_to_arviz(
     inplace=True,
 ):
     """Convert sampler output (``[draw, chain, ...]`` layout) to an ``InferenceData``."""
+    if isinstance(trace, dict):
+        trace = {k: v for k, v in trace.items() if "/" in k}
+    if isinstance(log_likelihood, dict):
+        log_likelihood = {k: v for k, v in log_likelihood.items() if "/" in k}
+    trace, sample_stats, log_likelihood = _fetch_all([trace, sample_stats, log_likelihood])
     if isinstance(trace, dict):
         trace = {k: np.swapaxes(_to_numpy(v), 1, 0) for k, v in trace.items() if "/" in k}
     if isinstance(sample_stats, dict):
