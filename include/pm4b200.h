@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM4_ABI_VERSION 2
+#define PM4_ABI_VERSION 3
 
 /* error codes */
 #define PM4_OK 0
@@ -83,6 +83,8 @@ typedef struct pm4_term {
   int32_t value_reg;   /* register holding the value                    */
   int32_t param_reg[3];/* registers holding the parameters (-1 unused)  */
   int32_t plan;        /* index into plans, or -1                       */
+  int32_t observed;    /* 1: the term is the density of an observed variable (pointwise log-likelihood) */
+  int32_t ll_offset;   /* position of element 0 inside one state's log-likelihood row (observed terms)  */
 } pm4_term_t;
 
 /* Device execution plan of a term that gathers from free variables: its elements regrouped by
@@ -205,6 +207,14 @@ int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta_dev, void*
 /* Traced outputs for a batch of states: theta_dev [M, D] -> out_dev [M, det_row]. */
 int pm4_deterministics(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev,
                        void* out_dev, void* stream);
+
+/* Pointwise log-likelihood of the observed variables for a batch of states
+ * (calculate_log_likelihood, /root/reference/pymc4/mcmc/samplers.py:832-854: dist.log_prob(observed)
+ * per draw and chain, no reduction): theta_dev [M, D] -> out_dev [M, ll_row], the observed terms'
+ * elements side by side (pm4_term_t.ll_offset).  pm4_model_ll_row gives ll_row. */
+int pm4_log_likelihood(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev,
+                       void* out_dev, void* stream);
+int pm4_model_ll_row(const pm4_model_t* m);
 
 /* Step-size policy (tfp DualAveragingStepSizeAdaptation) */
 #define PM4_EPS_POOLED 0    /* one scalar shared by all chains (reference default, scalar step_size) */

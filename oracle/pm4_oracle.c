@@ -107,6 +107,11 @@ int pm4o_logp_grad(const pm4_ir_t* ir, int dtype, int C, const void* theta, void
                           : pm4o_logp_grad_f32(ir, C, theta, lp, grad);
 }
 
+int pm4o_log_likelihood(const pm4_ir_t* ir, int dtype, int64_t M, int ll_row, const void* theta, void* out) {
+  return dtype == PM4_F64 ? pm4o_log_likelihood_f64(ir, M, ll_row, theta, out)
+                          : pm4o_log_likelihood_f32(ir, M, ll_row, theta, out);
+}
+
 int pm4o_deterministics(const pm4_ir_t* ir, int dtype, int64_t M, const void* theta, void* out) {
   return dtype == PM4_F64 ? pm4o_deterministics_f64(ir, M, theta, out)
                           : pm4o_deterministics_f32(ir, M, theta, out);

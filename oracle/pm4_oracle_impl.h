@@ -221,6 +221,24 @@ static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* the
   return lp;
 }
 
+/* pointwise log-likelihood of ONE state: dist.log_prob(observed) of every observed variable, no
+ * reduction (/root/reference/pymc4/mcmc/samplers.py:832-854) */
+static void NAME(loglik1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta, REAL* out) {
+  REAL* x = ws->x;
+  NAME(constrain)(ir, theta, x);
+  REAL v[PM4O_MAXREG];
+  for (int t = 0; t < ir->n_terms; ++t) {
+    const pm4_term_t* tm = &ir->terms[t];
+    if (!tm->observed) continue;
+    for (int i = 0; i < tm->n; ++i) {
+      NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, theta, v);
+      REAL q[3] = {0, 0, 0}, dq[3], dx;
+      for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+      out[tm->ll_offset + i] = NAME(lpdf)(tm->kind, v[tm->value_reg], q, &dx, dq);
+    }
+  }
+}
+
 static NAME(ws_t) NAME(ws_new)(int D) {
   NAME(ws_t) w;
   w.D = D;
@@ -230,6 +248,15 @@ static NAME(ws_t) NAME(ws_new)(int D) {
   return w;
 }
 static void NAME(ws_free)(NAME(ws_t)* w) { free(w->x); }
+
+int NAME(pm4o_log_likelihood)(const pm4_ir_t* ir, int64_t M, int ll_row, const REAL* theta, REAL* out) {
+  if (!ir || !theta || !out) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  NAME(ws_t) ws = NAME(ws_new)(ir->D);
+  for (int64_t m = 0; m < M; ++m) NAME(loglik1)(ir, &ws, theta + m * ir->D, out + m * ll_row);
+  NAME(ws_free)(&ws);
+  return PM4_OK;
+}
 
 int NAME(pm4o_logp_grad)(const pm4_ir_t* ir, int C, const REAL* theta, REAL* lp, REAL* grad) {
   if (!ir || !theta || !lp) return PM4_EINVAL;

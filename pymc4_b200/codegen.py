@@ -533,6 +533,77 @@ class _ModuleGen:
         out.append("  }")
         return "\n".join(out)
 
+    # -- pointwise log-likelihood -------------------------------------------------
+    def gen_loglik(self) -> str:
+        """One WARP per state: lanes stride over the elements of every observed term, evaluate the
+        forward tape and the log-density (partials are dead code) and store it -- no reduction."""
+        out = ["  template <typename real>",
+               "  static __device__ void loglik(const real* __restrict__ th, real* __restrict__ out, "
+               "const pm4::ModelArgs<real>& A, int lane) {",
+               "    auto c_blob = [&](int op) -> int { return __ldg(A.op_blob + op); }; (void)c_blob;",
+               "    auto X = [&](int j) -> real {  // constrained value of element j",
+               "      const real z = th[j];"]
+        for rv in self.ir.rvs:
+            cond = "j >= %d && j < %d" % (rv.offset, rv.offset + rv.size)
+            if rv.transform == I.TR_EXP:
+                out.append("      if (%s) return %s + %s * pm4::m_exp(z);" % (cond, _lit(rv.shift), _lit(rv.scale)))
+            elif rv.transform == I.TR_SIGMOID:
+                out.append("      if (%s) return %s + %s * pm4::m_sigmoid<real>(z);" % (cond, _lit(rv.shift), _lit(rv.scale)))
+        out += ["      return z;", "    }; (void)X;"]
+        op0 = 0
+        for k, t in enumerate(self.ir.terms):
+            if not t.observed:
+                op0 += len(t.ops)
+                continue
+            tag = "l%d" % k
+            tp = _Tape(t.ops, op0, tag)
+
+            def xread(o: I.Op, idx: str, _op0=op0) -> str:
+                if o.mode == I.MODE_SCALAR:
+                    return "X(%d)" % o.base
+                if o.mode == I.MODE_ELEM:
+                    return "X(%d + %s)" % (o.base, idx)
+                return "X(%d + A.datai[c_blob(%d) + %s])" % (o.base, _op0 + o.dst, idx)
+
+            def dread(o: I.Op, idx: str, _op0=op0) -> str:
+                return "A.dataf[c_blob(%d) + %s]" % (_op0 + o.dst, idx if o.mode == I.MODE_ELEM else "0")
+
+            kind = _KIND[t.kind]
+            n_par = I.TERM_NPARAMS[t.kind]
+            preg = list(t.param_regs[:n_par])
+            out.append("    // ---- observed term %d: %s (%s)" % (k, t.label, kind))
+            out.append("    {")
+            for o in t.ops:
+                if o.uniform:
+                    out.append("      const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "0", xread, dread)))
+            out.append("      const int n = __ldg(A.term_n + %d);" % k)
+            out.append("      for (int i = lane; i < n; i += 32) {")
+            for o in t.ops:
+                if not o.uniform:
+                    out.append("        const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "i", xread, dread)))
+            val = tp.v(t.value_reg)
+            p0 = tp.v(preg[0]) if n_par else ""
+            if kind == "potential":
+                expr = val
+            else:
+                out.append("        real dx_, d0_, d1_; (void)dx_; (void)d0_; (void)d1_;")
+                if kind in ("normal", "halfnormal", "halfcauchy"):
+                    sreg = tp.v(preg[1] if kind == "normal" else preg[0])
+                    out.append("        const real inv_s = pm4::m_rcp(%s), log_s = pm4::m_log(%s);" % (sreg, sreg))
+                expr = {
+                    "normal": "pm4::normal_lpdf<real>(%s, %s, inv_s, log_s, dx_, d0_, d1_)" % (val, p0),
+                    "halfnormal": "pm4::halfnormal_lpdf<real>(%s, inv_s, log_s, dx_, d0_)" % val,
+                    "halfcauchy": "pm4::halfcauchy_lpdf<real>(%s, inv_s, log_s, dx_, d0_)" % val,
+                    "bernoulli": "pm4::bernoulli_lpdf<real>(%s, %s, dx_, d0_)" % (val, p0),
+                    "poisson": "pm4::poisson_lpdf<real>(%s, %s, dx_, d0_)" % (val, p0),
+                }[kind]
+            out.append("        out[%d + i] = %s;" % (t.ll_offset, expr))
+            out.append("      }")
+            out.append("    }")
+            op0 += len(t.ops)
+        out.append("  }")
+        return "\n".join(out)
+
     def source(self) -> str:
         ir = self.ir
         name = "Model_%s" % ir.struct_hash_hex
@@ -556,6 +627,8 @@ class _ModuleGen:
             self.gen_constrain(),
             terms_src,
             self.gen_dets(),
+            "  static constexpr int LL_ROW = %d;  // pointwise log-likelihood scalars per state" % ir.ll_row,
+            self.gen_loglik(),
             "};",
             "#define PM4_MODEL %s" % name,
             "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),

@@ -223,6 +223,17 @@ __global__ void dets_kernel(ModelArgs<real> A, int64_t n_states, const real* __r
   M::template dets<real>(theta + m * M::D, out + m * M::DET_ROW, A);
 }
 
+// pointwise log-likelihood of the observed variables: one warp per state, lanes stride over the
+// observations, coalesced stores; states are taken grid-stride
+template <class M, typename real>
+__global__ void __launch_bounds__(256) loglik_kernel(ModelArgs<real> A, int64_t n_states, const real* __restrict__ theta,
+                                                     real* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < n_states; m += warps)
+    M::template loglik<real>(theta + m * M::D, out + m * M::LL_ROW, A, lane);
+}
+
 // ------------------------------------------------------------------------------------------
 // run-time parameters shared by the HMC and NUTS kernels
 // ------------------------------------------------------------------------------------------
@@ -976,6 +987,7 @@ extern "C" int pm4m_info(pm4_mod_info_t* out) {
   out->DP = PM4_MODEL::DP;
   out->DS = PM4_MODEL::DS;
   out->det_row = PM4_MODEL::DET_ROW;
+  out->ll_row = PM4_MODEL::LL_ROW;
   out->has_f64 = PM4_HAS_F64;
   out->n_terms = PM4_MODEL::N_TERMS;
   out->n_ops = PM4_MODEL::N_OPS;
@@ -1013,6 +1025,16 @@ int mod_dets(const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, c
   if (M::DET_ROW == 0 || n == 0) return 0;
   ModelArgs<real> ma = make_model_args<real>(*A);
   dets_kernel<M, real><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ma, n, (const real*)theta, (real*)out);
+  return (int)cudaGetLastError();
+}
+template <typename real>
+int mod_loglik(const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, cudaStream_t st) {
+  using M = PM4_MODEL;
+  if (M::LL_ROW == 0 || n == 0) return 0;
+  ModelArgs<real> ma = make_model_args<real>(*A);
+  const int64_t blocks = (n + 7) / 8;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+  loglik_kernel<M, real><<<grid, 256, 0, st>>>(ma, n, (const real*)theta, (real*)out);
   return (int)cudaGetLastError();
 }
 template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0, double eps0, cudaStream_t st) {
@@ -1061,6 +1083,10 @@ extern "C" int pm4m_logp_grad(int dtype, const pm4_mod_args_t* A, int C, const v
 extern "C" int pm4m_dets(int dtype, const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, void* stream) {
   PM4_BY_DTYPE(pm4::mod_dets<float>(A, n, theta, out, (cudaStream_t)stream),
                PM4_F64_CALL(pm4::mod_dets<double>(A, n, theta, out, (cudaStream_t)stream)));
+}
+extern "C" int pm4m_loglik(int dtype, const pm4_mod_args_t* A, int64_t n, const void* theta, void* out, void* stream) {
+  PM4_BY_DTYPE(pm4::mod_loglik<float>(A, n, theta, out, (cudaStream_t)stream),
+               PM4_F64_CALL(pm4::mod_loglik<double>(A, n, theta, out, (cudaStream_t)stream)));
 }
 extern "C" int pm4m_init(int dtype, const pm4_mod_run_t* r, const void* theta0, double eps0, void* stream) {
   PM4_BY_DTYPE(pm4::mod_init<float>(r, theta0, eps0, (cudaStream_t)stream),

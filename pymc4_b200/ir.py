@@ -29,7 +29,7 @@ from . import symbolic as sym
 from .coroutine_model import Model
 from .utils import NameParts
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
 
@@ -92,6 +92,9 @@ class Term:
     param_regs: List[int]
     label: str = ""
     plan: Optional["Plan"] = None
+    observed: bool = False          # density of an observed variable (enters the pointwise log-likelihood)
+    ll_offset: int = 0              # position of element 0 in one state's log-likelihood row
+    shape: Tuple[int, ...] = ()     # broadcast shape of the term's elements
 
     @property
     def n_regs(self) -> int:
@@ -167,6 +170,10 @@ class ModelIR:
     def det_row(self) -> int:
         return sum(d.n for d in self.dets)
 
+    @property
+    def ll_row(self) -> int:
+        return sum(t.n for t in self.terms if t.observed)
+
     # -- structural hash: everything the generated code depends on ---------
     def struct_key(self) -> bytes:
         h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<ii", self.D, self.team_warps)]
@@ -182,7 +189,7 @@ class ModelIR:
                 h.append(struct.pack("<i", n))
 
         for t in self.terms:
-            h.append(struct.pack("<iii", t.kind, t.value_reg, len(t.ops)))
+            h.append(struct.pack("<iii?", t.kind, t.value_reg, len(t.ops), t.observed))
             h.append(struct.pack("<%di" % len(t.param_regs), *t.param_regs))
             ops_key(t.ops, t.n)
             if t.plan is not None:
@@ -370,7 +377,8 @@ def _lower_term(kind: str, value, params: List[Any], rvs, pools, label="") -> Te
     n = int(np.prod(shape, dtype=np.int64)) if shape else 1
     tb = _TapeBuilder(n, rvs, pools)
     regs = [tb.lower(e, _broadcast_map(_identity_map(n), shape, e.shape)) for e in exprs]
-    return Term(kind=TERM_KINDS[kind], n=n, ops=tb.ops, value_reg=regs[0], param_regs=regs[1:], label=label)
+    return Term(kind=TERM_KINDS[kind], n=n, ops=tb.ops, value_reg=regs[0], param_regs=regs[1:], label=label,
+                shape=shape)
 
 
 def _lower_det(name: str, value, rvs, pools, out_offset: int) -> Det:
@@ -455,6 +463,7 @@ def lower_model(model: Model, observed: Optional[dict] = None, state=None,
         value = st.all_values[name]
         params = [dist.params[p] for p in dist._param_names]
         terms.append(_lower_term(dist._kind, value, params, rvs, pools, label=name))
+        terms[-1].observed = name in st.observed_values
     for k, pot in enumerate(st.potentials):
         terms.append(_lower_term("potential", pot.value, [], rvs, pools, label="potential_%d" % k))
 
@@ -473,6 +482,11 @@ def lower_model(model: Model, observed: Optional[dict] = None, state=None,
         dets.append(d)
         out_off += d.n
 
+    ll_off = 0
+    for t in terms:
+        if t.observed:
+            t.ll_offset = ll_off
+            ll_off += t.n
     dataf = np.concatenate(pools.f) if pools.f else np.zeros(0)
     datai = np.concatenate(pools.i).astype(np.int32) if pools.i else np.zeros(0, dtype=np.int32)
     observed_np = {k: sym.as_numpy(v) for k, v in st.observed_values.items()}
@@ -495,7 +509,8 @@ class CRV(ctypes.Structure):
 class CTerm(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("n", ctypes.c_int32), ("op_begin", ctypes.c_int32),
                 ("op_end", ctypes.c_int32), ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32),
-                ("param_reg", ctypes.c_int32 * 3), ("plan", ctypes.c_int32)]
+                ("param_reg", ctypes.c_int32 * 3), ("plan", ctypes.c_int32), ("observed", ctypes.c_int32),
+                ("ll_offset", ctypes.c_int32)]
 
 
 class CPlan(ctypes.Structure):
@@ -547,7 +562,7 @@ class PackedIR:
                 plan_idx = len(plans)
                 plans.append(t.plan)
             cterms[k] = CTerm(t.kind, t.n, begin, len(all_ops), t.n_regs, t.value_reg,
-                              (ctypes.c_int32 * 3)(*pr), plan_idx)
+                              (ctypes.c_int32 * 3)(*pr), plan_idx, 1 if t.observed else 0, t.ll_offset)
         cdets = (CDet * max(len(ir.dets), 1))()
         for k, d in enumerate(ir.dets):
             begin = len(all_ops)

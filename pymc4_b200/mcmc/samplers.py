@@ -177,7 +177,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
 
         log_likelihood_dict = dict()
         if include_log_likelihood:
-            log_likelihood_dict = calculate_log_likelihood(self.model, posterior, state_)
+            log_likelihood_dict = _log_likelihood_from_states(self._device_model, self._last_states, self._dtype)
         self.last_run_info = self._run_info
         return trace_to_arviz(
             posterior,
@@ -303,6 +303,7 @@ class HMC(_BaseSampler):
         out = dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale)
         self._run_info = dict(step_size=out["step_size"], kernel="hmc",
                               leapfrogs_per_transition=spec.num_leapfrog_steps)
+        self._last_states = out["states"]
         results = self._unpack_states(out["states"])
         return results, self.trace_fn(out["states"], out)
 
@@ -353,6 +354,7 @@ class NUTS(_BaseSampler):
         out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale)
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
                               depth=out["depth"], kernel="nuts")
+        self._last_states = out["states"]
         results = self._unpack_states(out["states"])
         return results, self.trace_fn(out["states"], out)
 
@@ -489,7 +491,36 @@ def tile_init(init, num_repeats):
     return [np.tile(np.expand_dims(np.asarray(t), 0), [num_repeats] + [1] * np.ndim(t)) for t in init]
 
 
-def calculate_log_likelihood(model: Model, posterior: Dict[str, Any], sampling_state: flow.SamplingState):
-    raise NotImplementedError(
-        "include_log_likelihood is listed under 'next' in SURVEY section 8(f) and is not built yet"
-    )
+def _log_likelihood_from_states(dm, states, dtype) -> Dict[str, Any]:
+    """states [S, C, D] (device) -> {observed name: [S, C, *shape]} device tensors: one kernel evaluates
+    every observed term element-wise for every state (no reduction)."""
+    ir = dm.ir
+    ll = dm.log_likelihood(states, dtype=dtype)
+    lead = tuple(ll.shape[:-1])
+    out = {}
+    for t in ir.terms:
+        if t.observed:
+            out[t.label] = ll[..., t.ll_offset: t.ll_offset + t.n].reshape(lead + tuple(t.shape))
+    return out
+
+
+def calculate_log_likelihood(model: Model, posterior: Dict[str, Any], sampling_state: flow.SamplingState,
+                             dtype="float32", device: Optional[int] = None) -> Dict[str, Any]:
+    """Pointwise log-likelihood ``dist.log_prob(observed)`` of every observed variable for every draw
+    and chain of ``posterior`` (``{sampled name: [draw, chain, *core]}``), on the GPU.
+
+    Reference: pymc4/mcmc/samplers.py:832-854 (two nested ``tf.vectorized_map`` over chains and draws
+    of the transformed executor); here the draws are packed into states ``[S, C, D]`` and one kernel
+    evaluates the observed terms of the lowered model without the reduction."""
+    ir, _, _ = irmod.lower_model(model, observed=dict(sampling_state.observed_values) or None)
+    dm = _get_device_model(ir, np.dtype(dtype), device)
+    torch = dm.torch
+    first = next(iter(posterior.values()))
+    S, C = int(first.shape[0]), int(first.shape[1])
+    theta = torch.empty((S, C, ir.D), dtype=torch.float64 if np.dtype(dtype) == np.float64 else torch.float32,
+                        device=dm._dev())
+    for rv in ir.rvs:
+        part = posterior[rv.name]
+        part = part if isinstance(part, torch.Tensor) else torch.as_tensor(np.asarray(part))
+        theta[:, :, rv.offset: rv.offset + rv.size] = part.to(theta.device, theta.dtype).reshape(S, C, rv.size)
+    return _log_likelihood_from_states(dm, theta, np.dtype(dtype))

@@ -264,3 +264,18 @@ def test_large_state_nuts_against_oracle(large_ir, oracle_mod):
     same = got == want
     assert np.max(np.abs(out["states"].cpu().numpy()[same] - ref["states"][same])) < 5e-2
     assert np.all(np.isfinite(out["states"].cpu().numpy()))
+
+
+@pytest.mark.parametrize("name", ["eight_schools", "radon_synth", "logistic", "poisson"])
+def test_pointwise_log_likelihood_parity(name, oracle_mod):
+    """dist.log_prob(observed) per state on the device against the oracle, FP32 and FP64."""
+    ir, _, _ = lower_model(MODELS[name]())
+    rng = np.random.default_rng(41)
+    theta = rng.normal(0, 0.4, (7, 5, ir.D))
+    ref = oracle_mod.Oracle(ir).log_likelihood(theta, dtype=np.float64)
+    got = _dm(ir).log_likelihood(theta.astype(np.float32), dtype=np.float32).cpu().numpy()
+    assert got.shape == ref.shape == (7, 5, ir.ll_row) and ir.ll_row > 0
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)) < 1e-5
+    if name != "radon_synth":
+        got64 = _dm(ir, f64=True).log_likelihood(theta, dtype=np.float64).cpu().numpy()
+        np.testing.assert_allclose(got64, ref, rtol=1e-12, atol=1e-12)

@@ -260,3 +260,43 @@ def test_deterministics_and_float32_path(oracle_mod):
     np.testing.assert_allclose(out[:, k["outer_model/nested_model/dx"]], x + 1)
     np.testing.assert_allclose(out[:, k["outer_model/ddx"]], x + 1)
     np.testing.assert_allclose(out[:, k["outer_model/cond"]], cond)
+
+
+def test_pointwise_log_likelihood_vs_scipy(oracle_mod):
+    """dist.log_prob(observed) per state, no reduction (/root/reference/pymc4/mcmc/samplers.py:832-854),
+    against scipy for a Normal, a Bernoulli and a Poisson likelihood; the row sums up to the observed
+    terms' share of the joint log-density."""
+    from scipy import stats
+
+    from pymc4_b200.ir import lower_model
+    from tests import models as M
+
+    rng = np.random.default_rng(3)
+    # radon: y ~ Normal(a[idx] + b[idx] x, eps)
+    idx, x, y, g = M.radon_synthetic(200, 11)
+    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, g))
+    (obs,) = [t for t in ir.terms if t.observed]
+    assert obs.label.endswith("y_like") and ir.ll_row == 200 and obs.shape == (200,)
+    theta = rng.normal(0, 0.3, (5, ir.D))
+    ll = oracle_mod.Oracle(ir).log_likelihood(theta)
+    parts = ir.split_theta(theta)
+    a, b = parts["hierarchical_model/alpha"], parts["hierarchical_model/beta"]
+    eps = np.exp(parts["hierarchical_model/__log_eps"])
+    want = stats.norm(a[:, idx] + b[:, idx] * x, eps[:, None]).logpdf(y)
+    np.testing.assert_allclose(ll, want, rtol=1e-12, atol=1e-12)
+    # leading axes are kept: [S, C, D] -> [S, C, ll_row]
+    assert oracle_mod.Oracle(ir).log_likelihood(theta.reshape(5, 1, -1)).shape == (5, 1, 200)
+
+    X, yb = M.logistic_data()
+    ir, _, _ = lower_model(M.logistic_model(X, yb))
+    theta = rng.normal(0, 0.5, (4, ir.D))
+    beta = ir.split_theta(theta)["logistic_model/beta"]
+    p = 1 / (1 + np.exp(-(beta @ X.T)))
+    np.testing.assert_allclose(oracle_mod.Oracle(ir).log_likelihood(theta), stats.bernoulli(p).logpmf(yb), rtol=1e-10)
+
+    idxp, yp, gp = M.poisson_data()
+    ir, _, _ = lower_model(M.poisson_model(idxp, yp, gp))
+    theta = rng.normal(0, 0.5, (4, ir.D))
+    parts = ir.split_theta(theta)
+    rate = np.exp(parts["poisson_model/intercept"][:, None] + parts["poisson_model/eff"][:, idxp])
+    np.testing.assert_allclose(oracle_mod.Oracle(ir).log_likelihood(theta), stats.poisson(rate).logpmf(yp), rtol=1e-10)

@@ -118,3 +118,24 @@ def test_float64_mode_and_chain_offset():
     full = pm.sample(M.schools_pm4(), num_chains=4, num_samples=15, burn_in=15, seed=9, step_size=step)
     part = pm.sample(M.schools_pm4(), num_chains=2, num_samples=15, burn_in=15, seed=9, step_size=step[:2], chain_offset=2)
     np.testing.assert_array_equal(full.posterior["schools_pm4/eta"][2:], part.posterior["schools_pm4/eta"])
+
+
+def test_include_log_likelihood():
+    """pm.sample(..., include_log_likelihood=True): a log_likelihood group with one [chain, draw, *obs] array per
+    observed variable (reference sampling.py:52-184 -> samplers.py:832-854, mcmc/utils.py:95-144)."""
+    from scipy import stats
+
+    chains, samples = 3, 20
+    trace = pm.sample(M.schools_pm4(), step_size=0.28, num_chains=chains, num_samples=samples, burn_in=20,
+                      seed=5, include_log_likelihood=True)
+    assert "log_likelihood" in trace.groups()
+    ll = trace.log_likelihood["schools_pm4/obs"]
+    assert ll.shape == (chains, samples, 8)
+    post = trace.posterior
+    theta = post["schools_pm4/mu"][..., None] + post["schools_pm4/tau"][..., None] * post["schools_pm4/eta"]
+    np.testing.assert_allclose(ll, stats.norm(theta, M.SIGMA8).logpdf(M.Y8), rtol=2e-4, atol=2e-4)
+    # the free function takes the posterior in sampler layout [draw, chain, ...]
+    logp, init, _, _, state = pm.mcmc.samplers.build_logp_and_deterministic_functions(M.schools_pm4())
+    posterior = {k: np.swapaxes(post[k], 0, 1) for k in init}
+    ll2 = pm.mcmc.samplers.calculate_log_likelihood(M.schools_pm4(), posterior, state)
+    np.testing.assert_allclose(np.swapaxes(ll2["schools_pm4/obs"].cpu().numpy(), 0, 1), ll, rtol=1e-5, atol=1e-5)
