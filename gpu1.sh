@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | cut -c1-300
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 | cut -c1-400

@@ -216,6 +216,14 @@ int pm4_log_likelihood(pm4_model_t* m, int dtype, int64_t M, const void* theta_d
                        void* out_dev, void* stream);
 int pm4_model_ll_row(const pm4_model_t* m);
 
+/* Posterior predictive: one draw of every observed variable from its distribution for every state
+ * (sample_posterior_predictive, /root/reference/pymc4/forward_sampling.py:230-427: the model is
+ * re-evaluated with the posterior values and the observed variables are sampled).
+ * theta_dev [M, D] -> out_dev [M, ll_row] (row layout of pm4_log_likelihood).  Philox counters are
+ * (state, element), key = seed: the same seed gives the same draws whatever the launch geometry. */
+int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, uint64_t seed,
+                             void* out_dev, void* stream);
+
 /* Step-size policy (tfp DualAveragingStepSizeAdaptation) */
 #define PM4_EPS_POOLED 0    /* one scalar shared by all chains (reference default, scalar step_size) */
 #define PM4_EPS_PER_CHAIN 1 /* step_size carries a leading chain axis: independent adaptation       */

@@ -39,6 +39,7 @@
 #define PM4_RNG_LEAF 2u
 #define PM4_RNG_MERGE 3u
 #define PM4_RNG_HMC 4u
+#define PM4_RNG_PREDICTIVE 5u
 
 void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint32_t out[4]) {
   uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
@@ -70,6 +71,8 @@ void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint
 #define RLGAMMA lgammaf
 #define RCOS cosf
 #define RSIN sinf
+#define RTAN tanf
+#define RFLOOR floorf
 #include "pm4_oracle_impl.h"
 #undef REAL
 #undef REAL_IS_DOUBLE
@@ -84,6 +87,8 @@ void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint
 #undef RLGAMMA
 #undef RCOS
 #undef RSIN
+#undef RTAN
+#undef RFLOOR
 
 /* ---- double instantiation ---- */
 #define REAL double
@@ -99,6 +104,8 @@ void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint
 #define RLGAMMA lgamma
 #define RCOS cos
 #define RSIN sin
+#define RTAN tan
+#define RFLOOR floor
 #include "pm4_oracle_impl.h"
 
 /* ---- dtype-dispatching entry points (signatures mirror include/pm4b200.h, host pointers) ---- */
@@ -110,6 +117,12 @@ int pm4o_logp_grad(const pm4_ir_t* ir, int dtype, int C, const void* theta, void
 int pm4o_log_likelihood(const pm4_ir_t* ir, int dtype, int64_t M, int ll_row, const void* theta, void* out) {
   return dtype == PM4_F64 ? pm4o_log_likelihood_f64(ir, M, ll_row, theta, out)
                           : pm4o_log_likelihood_f32(ir, M, ll_row, theta, out);
+}
+
+int pm4o_posterior_predictive(const pm4_ir_t* ir, int dtype, int64_t M, int ll_row, uint64_t seed,
+                              const void* theta, void* out) {
+  return dtype == PM4_F64 ? pm4o_posterior_predictive_f64(ir, M, ll_row, seed, theta, out)
+                          : pm4o_posterior_predictive_f32(ir, M, ll_row, seed, theta, out);
 }
 
 int pm4o_deterministics(const pm4_ir_t* ir, int dtype, int64_t M, const void* theta, void* out) {

@@ -41,6 +41,7 @@ def lib():
         L.pm4o_logp_grad.argtypes = [irp, i32, i32, vp, vp, vp]
         L.pm4o_deterministics.argtypes = [irp, i32, i64, vp, vp]
         L.pm4o_log_likelihood.argtypes = [irp, i32, i64, i32, vp, vp]
+        L.pm4o_posterior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
         L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 12
         L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
         L.pm4o_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
@@ -114,6 +115,16 @@ class Oracle:
         out = np.empty((flat.shape[0], self.ir.ll_row), dtype=dtype)
         _check(lib().pm4o_log_likelihood(self.packed.byref(), _code(dtype), flat.shape[0], self.ir.ll_row,
                                          _ptr(flat), _ptr(out)), "log_likelihood")
+        return out.reshape(lead + (self.ir.ll_row,))
+
+    def posterior_predictive(self, theta, seed=0, dtype=np.float64):
+        """theta [..., D] -> [..., ll_row]: one draw of every observed variable per state."""
+        theta = np.ascontiguousarray(theta, dtype=dtype)
+        lead = theta.shape[:-1]
+        flat = theta.reshape(-1, self.ir.D)
+        out = np.empty((flat.shape[0], self.ir.ll_row), dtype=dtype)
+        _check(lib().pm4o_posterior_predictive(self.packed.byref(), _code(dtype), flat.shape[0], self.ir.ll_row,
+                                               int(seed) & (2**64 - 1), _ptr(flat), _ptr(out)), "posterior_predictive")
         return out.reshape(lead + (self.ir.ll_row,))
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None):

@@ -326,6 +326,75 @@ static inline void NAME(box_muller)(uint32_t xa, uint32_t xb, REAL* n0, REAL* n1
   *n1 = rad * RSIN(ang);
 }
 
+/* one draw of a variable given its parameters: posterior predictive
+ * (/root/reference/pymc4/forward_sampling.py:230-427).  Same algorithm and Philox counters as
+ * csrc/pm4_philox.cuh: draw_value. */
+static REAL NAME(draw_value)(int kind, REAL p0, REAL p1, uint32_t c0, uint32_t c1, uint32_t c2, uint64_t seed) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t ctr[4] = {c0, c1, c2, PM4_RNG_PREDICTIVE}, u[4];
+  pm4o_philox4x32_10(ctr, k0, k1, u);
+  if (kind == PM4_T_NORMAL || kind == PM4_T_HALFNORMAL) {
+    REAL n0, n1;
+    NAME(box_muller)(u[0], u[1], &n0, &n1);
+    return kind == PM4_T_NORMAL ? p0 + p1 * n0 : RABS(p0 * n0);
+  }
+  if (kind == PM4_T_HALFCAUCHY) return p0 * RTAN((REAL)1.57079632679489661923 * NAME(u01)(u));
+  if (kind == PM4_T_BERNOULLI) return NAME(u01)(u) < p0 ? (REAL)1 : (REAL)0;
+  if (kind == PM4_T_POISSON) {
+    const REAL lam = p0;
+    if (lam < (REAL)10) {
+      const REAL uu = NAME(u01)(u);
+      REAL p = REXP(-lam), F = p;
+      int k = 0;
+      while (uu > F && k < 1000) { k += 1; p *= lam / (REAL)k; F += p; }
+      return (REAL)k;
+    }
+    const REAL slam = RSQRT(lam), loglam = RLOG(lam), b = (REAL)0.931 + (REAL)2.53 * slam;
+    const REAL a = (REAL)-0.059 + (REAL)0.02483 * b, inv_alpha = (REAL)1.1239 + (REAL)1.1328 / (b - (REAL)3.4);
+    const REAL vr = (REAL)0.9277 - (REAL)3.6224 / (b - (REAL)2);
+    for (uint32_t it = 0; it < 64u; ++it) {
+      uint32_t w[4];
+      if (it == 0) memcpy(w, u, sizeof w);
+      else { ctr[3] = PM4_RNG_PREDICTIVE | (it << 8); pm4o_philox4x32_10(ctr, k0, k1, w); }
+      const REAL U = NAME(u01)(w) - (REAL)0.5, V = NAME(u01)(w + 2);
+      const REAL us = (REAL)0.5 - RABS(U);
+      const REAL k = RFLOOR(((REAL)2 * a / us + b) * U + lam + (REAL)0.43);
+      if (us >= (REAL)0.07 && V <= vr) return k;
+      if (k < 0 || (us < (REAL)0.013 && V > us)) continue;
+      if (RLOG(V) + RLOG(inv_alpha) - RLOG(a / (us * us) + b) <= -lam + k * loglam - RLGAMMA(k + 1)) return k;
+    }
+    return RFLOOR(lam + (REAL)0.5);
+  }
+  return (REAL)NAN;
+}
+
+int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint64_t seed, const REAL* theta,
+                                    REAL* out) {
+  if (!ir || !theta || !out) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  const int D = ir->D;
+  REAL* x = (REAL*)malloc(sizeof(REAL) * (size_t)(D + 1));
+  REAL v[PM4O_MAXREG];
+  for (int64_t m = 0; m < M; ++m) {
+    const REAL* th = theta + (size_t)m * D;
+    NAME(constrain)(ir, th, x);
+    for (int t = 0; t < ir->n_terms; ++t) {
+      const pm4_term_t* tm = &ir->terms[t];
+      if (!tm->observed) continue;
+      for (int i = 0; i < tm->n; ++i) {
+        NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, th, v);
+        REAL q[3] = {0, 0, 0};
+        for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+        out[(size_t)m * ll_row + tm->ll_offset + i] =
+            NAME(draw_value)(tm->kind, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
+                             (uint32_t)(tm->ll_offset + i), seed);
+      }
+    }
+  }
+  free(x);
+  return PM4_OK;
+}
+
 /* momentum for every dimension of one chain at one transition; dimension j is owned by
  * lane j%32, register j/32 of the chain's warp and four registers share one Philox call */
 static void NAME(draw_momentum)(uint64_t seed, uint32_t chain, uint32_t t, int D, REAL* p) {

@@ -13,5 +13,6 @@ from . import inference
 from .mcmc.utils import initialize_sampling_state, trace_to_arviz
 from .mcmc.samplers import *  # noqa: F401,F403
 from .inference.sampling import sample
+from .forward_sampling import sample_posterior_predictive, sample_prior_predictive
 
 __version__ = "0.1.0"

@@ -29,7 +29,7 @@ _lib = None
 EXPORTS = [
     "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_model_set_plans",
     "pm4_logp_grad",
-    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
+    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
 ]
 
@@ -75,6 +75,7 @@ def load_library():
     L.pm4_deterministics.argtypes = [vp, i32, i64, vp, vp, vp]
     L.pm4_log_likelihood.argtypes = [vp, i32, i64, vp, vp, vp]
     L.pm4_model_ll_row.argtypes = [vp]
+    L.pm4_posterior_predictive.argtypes = [vp, i32, i64, vp, ctypes.c_uint64, vp, vp]
     L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
     L.pm4_nuts_run.argtypes = [vp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
     L.pm4_scratch_bytes.argtypes = [vp, i32, i32, i32]
@@ -215,6 +216,19 @@ class DeviceModel:
         with torch.cuda.device(self._dev()):
             self._check(self.lib.pm4_log_likelihood(self.handle, _code(dtype), flat.shape[0], self._p(flat),
                                                     self._p(out), self._stream()))
+        return out.reshape(lead + (self.ir.ll_row,))
+
+    def posterior_predictive(self, theta, seed: int = 0, dtype=np.float32):
+        """theta [..., D] device/host -> [..., ll_row] device tensor: one draw of every observed variable."""
+        torch = self.torch
+        th = self.to_device(theta, dtype)
+        lead = tuple(th.shape[:-1])
+        flat = th.reshape(-1, self.ir.D)
+        out = self.empty((flat.shape[0], self.ir.ll_row), _tdtype(torch, dtype))
+        with torch.cuda.device(self._dev()):
+            self._check(self.lib.pm4_posterior_predictive(self.handle, _code(dtype), flat.shape[0], self._p(flat),
+                                                          ctypes.c_uint64(int(seed) & (2**64 - 1)), self._p(out),
+                                                          self._stream()))
         return out.reshape(lead + (self.ir.ll_row,))
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None,

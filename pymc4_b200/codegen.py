@@ -534,12 +534,16 @@ class _ModuleGen:
         return "\n".join(out)
 
     # -- pointwise log-likelihood -------------------------------------------------
-    def gen_loglik(self) -> str:
+    def gen_loglik(self, predictive: bool = False) -> str:
         """One WARP per state: lanes stride over the elements of every observed term, evaluate the
-        forward tape and the log-density (partials are dead code) and store it -- no reduction."""
+        forward tape and either the log-density (partials are dead code) or -- ``predictive`` -- one
+        draw from the distribution with those parameters, and store it -- no reduction."""
         out = ["  template <typename real>",
-               "  static __device__ void loglik(const real* __restrict__ th, real* __restrict__ out, "
-               "const pm4::ModelArgs<real>& A, int lane) {",
+               ("  static __device__ void predict(const real* __restrict__ th, real* __restrict__ out, "
+                "const pm4::ModelArgs<real>& A, int lane, uint32_t m_lo, uint32_t m_hi, uint32_t k0, uint32_t k1) {")
+               if predictive else
+               ("  static __device__ void loglik(const real* __restrict__ th, real* __restrict__ out, "
+                "const pm4::ModelArgs<real>& A, int lane) {"),
                "    auto c_blob = [&](int op) -> int { return __ldg(A.op_blob + op); }; (void)c_blob;",
                "    auto X = [&](int j) -> real {  // constrained value of element j",
                "      const real z = th[j];"]
@@ -583,7 +587,11 @@ class _ModuleGen:
                     out.append("        const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "i", xread, dread)))
             val = tp.v(t.value_reg)
             p0 = tp.v(preg[0]) if n_par else ""
-            if kind == "potential":
+            if predictive:
+                p1 = tp.v(preg[1]) if n_par > 1 else "(real)0"
+                expr = ("pm4::draw_value<real>(%d, %s, %s, m_lo, m_hi, (uint32_t)(%d + i), k0, k1)"
+                        % (t.kind, p0 if n_par else "(real)0", p1, t.ll_offset))
+            elif kind == "potential":
                 expr = val
             else:
                 out.append("        real dx_, d0_, d1_; (void)dx_; (void)d0_; (void)d1_;")
@@ -629,6 +637,7 @@ class _ModuleGen:
             self.gen_dets(),
             "  static constexpr int LL_ROW = %d;  // pointwise log-likelihood scalars per state" % ir.ll_row,
             self.gen_loglik(),
+            self.gen_loglik(predictive=True),
             "};",
             "#define PM4_MODEL %s" % name,
             "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),

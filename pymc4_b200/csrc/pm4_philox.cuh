@@ -8,7 +8,7 @@
 
 namespace pm4 {
 
-enum : uint32_t { RNG_MOMENTUM = 0u, RNG_DIRECTION = 1u, RNG_LEAF = 2u, RNG_MERGE = 3u, RNG_HMC = 4u };
+enum : uint32_t { RNG_MOMENTUM = 0u, RNG_DIRECTION = 1u, RNG_LEAF = 2u, RNG_MERGE = 3u, RNG_HMC = 4u, RNG_PREDICTIVE = 5u };
 
 struct U4 { uint32_t x, y, z, w; };
 
@@ -52,6 +52,49 @@ template <> __device__ __forceinline__ void box_muller<double>(uint32_t xa, uint
   sincos(6.283185307179586476925 * u2, &s, &c);
   n0 = rad * c;
   n1 = rad * s;
+}
+
+// One draw of a variable from its distribution given the parameters (posterior predictive,
+// /root/reference/pymc4/forward_sampling.py:230-427: the observed variables are re-sampled for every
+// posterior draw).  Counter = (state lo, state hi, element of the row, purpose | attempt << 8), key =
+// seed; the CPU oracle (oracle/pm4_oracle_impl.h: draw_value) runs the identical algorithm on the
+// identical stream.  kinds: include/pm4b200.h PM4_T_*.
+template <typename real>
+__device__ __forceinline__ real draw_value(int kind, real p0, real p1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                           uint32_t k0, uint32_t k1) {
+  const U4 u = philox4x32_10(c0, c1, c2, RNG_PREDICTIVE, k0, k1);
+  if (kind == 1 || kind == 2) {  // Normal(loc, scale), HalfNormal(scale)
+    real n0, n1;
+    box_muller<real>(u.x, u.y, n0, n1);
+    return kind == 1 ? p0 + p1 * n0 : fabs(p0 * n0);
+  }
+  if (kind == 3) return p0 * tan((real)1.57079632679489661923 * u01<real>(u.x, u.y));  // HalfCauchy(scale)
+  if (kind == 4) return u01<real>(u.x, u.y) < p0 ? (real)1 : (real)0;                  // Bernoulli(probs)
+  if (kind == 5) {                                                                       // Poisson(rate)
+    const real lam = p0;
+    if (lam < (real)10) {  // inversion by sequential search
+      const real uu = u01<real>(u.x, u.y);
+      real p = exp(-lam), F = p;
+      int k = 0;
+      while (uu > F && k < 1000) { k += 1; p *= lam / (real)k; F += p; }
+      return (real)k;
+    }
+    // PTRS (Hoermann 1993), two uniforms per attempt
+    const real slam = sqrt(lam), loglam = log(lam), b = (real)0.931 + (real)2.53 * slam;
+    const real a = (real)-0.059 + (real)0.02483 * b, inv_alpha = (real)1.1239 + (real)1.1328 / (b - (real)3.4);
+    const real vr = (real)0.9277 - (real)3.6224 / (b - (real)2);
+    for (uint32_t it = 0; it < 64u; ++it) {
+      const U4 w = it == 0 ? u : philox4x32_10(c0, c1, c2, RNG_PREDICTIVE | (it << 8), k0, k1);
+      const real U = u01<real>(w.x, w.y) - (real)0.5, V = u01<real>(w.z, w.w);
+      const real us = (real)0.5 - fabs(U);
+      const real k = floor(((real)2 * a / us + b) * U + lam + (real)0.43);
+      if (us >= (real)0.07 && V <= vr) return k;
+      if (k < 0 || (us < (real)0.013 && V > us)) continue;
+      if (log(V) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + (real)1)) return k;
+    }
+    return floor(lam + (real)0.5);
+  }
+  return (real)NAN;  // potentials are not distributions
 }
 
 }  // namespace pm4

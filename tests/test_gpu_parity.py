@@ -279,3 +279,29 @@ def test_pointwise_log_likelihood_parity(name, oracle_mod):
     if name != "radon_synth":
         got64 = _dm(ir, f64=True).log_likelihood(theta, dtype=np.float64).cpu().numpy()
         np.testing.assert_allclose(got64, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["eight_schools", "radon_synth", "logistic", "poisson"])
+def test_posterior_predictive_matches_oracle_stream(name, oracle_mod):
+    """device draws of the observed variables against the oracle on the same Philox stream:
+    continuous draws agree to rounding, integer draws are identical except where rounding flips a comparison."""
+    ir, _, _ = lower_model(MODELS[name]())
+    rng = np.random.default_rng(43)
+    theta = rng.normal(0, 0.4, (6, 50, ir.D))
+    if name == "poisson":
+        theta[3:, :, ir.rv_by_name("poisson_model/intercept").offset] += 3.0  # rates above 10: the PTRS branch
+    ref = oracle_mod.Oracle(ir).posterior_predictive(theta, seed=77, dtype=np.float64)
+    # FP32 draws use 24-bit uniforms, FP64 draws 32/53-bit ones: compare each precision with its own oracle
+    ref32 = oracle_mod.Oracle(ir).posterior_predictive(theta.astype(np.float32), seed=77, dtype=np.float32)
+    got = _dm(ir).posterior_predictive(theta.astype(np.float32), seed=77, dtype=np.float32).cpu().numpy()
+    assert got.shape == ref.shape
+    if name in ("eight_schools", "radon_synth"):
+        assert np.max(np.abs(got - ref32) / np.maximum(np.abs(ref32), 1.0)) < 2e-5
+    else:
+        assert np.mean(got == ref32) > 0.995 and np.all(got == np.round(got)) and got.min() >= 0
+    if name != "radon_synth":
+        got64 = _dm(ir, f64=True).posterior_predictive(theta, seed=77, dtype=np.float64).cpu().numpy()
+        if name == "eight_schools":
+            np.testing.assert_allclose(got64, ref, rtol=1e-11, atol=1e-11)
+        else:
+            assert np.mean(got64 == ref) > 0.9999

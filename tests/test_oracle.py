@@ -300,3 +300,43 @@ def test_pointwise_log_likelihood_vs_scipy(oracle_mod):
     parts = ir.split_theta(theta)
     rate = np.exp(parts["poisson_model/intercept"][:, None] + parts["poisson_model/eff"][:, idxp])
     np.testing.assert_allclose(oracle_mod.Oracle(ir).log_likelihood(theta), stats.poisson(rate).logpmf(yp), rtol=1e-10)
+
+
+def test_posterior_predictive_draws_have_the_right_moments(oracle_mod):
+    """One draw of every observed variable per state (forward_sampling.py:230-427): the oracle's Philox-driven
+    samplers against the analytic moments of Normal / Bernoulli / Poisson (inversion below rate 10, PTRS above)."""
+    from pymc4_b200.ir import lower_model
+    from tests import models as M
+
+    rng = np.random.default_rng(9)
+    idx, x, y, g = M.radon_synthetic(400, 7)
+    ir, _, _ = lower_model(M.hierarchical_model(idx, x, y, g))
+    theta = np.tile(rng.normal(0, 0.3, ir.D), (3000, 1))
+    d = oracle_mod.Oracle(ir).posterior_predictive(theta, seed=11)
+    parts = ir.split_theta(theta[0])
+    mu = parts["hierarchical_model/alpha"][idx] + parts["hierarchical_model/beta"][idx] * x
+    eps = float(np.exp(parts["hierarchical_model/__log_eps"]))
+    assert d.shape == (3000, 400)
+    assert np.max(np.abs(d.mean(0) - mu)) < 5 * eps / np.sqrt(3000)
+    assert abs(d.std() ** 2 / (eps ** 2 + mu.var()) - 1) < 0.02
+    # same seed, same draws; another seed, other draws; states are independent streams
+    assert np.array_equal(d, oracle_mod.Oracle(ir).posterior_predictive(theta, seed=11))
+    assert not np.array_equal(d, oracle_mod.Oracle(ir).posterior_predictive(theta, seed=12))
+    assert abs(np.corrcoef(d[0], d[1])[0, 1] - np.corrcoef(mu, mu + 0)[0, 1] * mu.var() / (mu.var() + eps ** 2)) < 0.15
+
+    X, yb = M.logistic_data()
+    ir, _, _ = lower_model(M.logistic_model(X, yb))
+    theta = np.tile(rng.normal(0, 0.5, ir.D), (4000, 1))
+    d = oracle_mod.Oracle(ir).posterior_predictive(theta, seed=3)
+    p = 1 / (1 + np.exp(-(ir.split_theta(theta[0])["logistic_model/beta"] @ X.T)))
+    assert set(np.unique(d)) <= {0.0, 1.0} and np.max(np.abs(d.mean(0) - p)) < 5 * 0.5 / np.sqrt(4000)
+
+    idxp, yp, gp = M.poisson_data()
+    ir, _, _ = lower_model(M.poisson_model(idxp, yp, gp))
+    for intercept in (0.5, 3.5):  # rates ~1.6 (inversion) and ~33 (PTRS)
+        th = np.zeros(ir.D)
+        th[ir.rv_by_name("poisson_model/intercept").offset] = intercept
+        d = oracle_mod.Oracle(ir).posterior_predictive(np.tile(th, (4000, 1)), seed=5)
+        lam = np.exp(intercept)
+        assert np.all(d >= 0) and np.all(d == np.round(d))
+        assert abs(d.mean() / lam - 1) < 0.01 and abs(d.var() / lam - 1) < 0.03

@@ -139,3 +139,25 @@ def test_include_log_likelihood():
     posterior = {k: np.swapaxes(post[k], 0, 1) for k in init}
     ll2 = pm.mcmc.samplers.calculate_log_likelihood(M.schools_pm4(), posterior, state)
     np.testing.assert_allclose(np.swapaxes(ll2["schools_pm4/obs"].cpu().numpy(), 0, 1), ll, rtol=1e-5, atol=1e-5)
+
+
+def test_sample_posterior_predictive():
+    """pm.sample_posterior_predictive(model, trace): a posterior_predictive group with one
+    [chain, draw, *observed shape] array per observed variable (reference forward_sampling.py:230-427)."""
+    chains, samples = 4, 200
+    trace = pm.sample(M.schools_pm4(), step_size=0.28, num_chains=chains, num_samples=samples, burn_in=100, seed=7)
+    out = pm.sample_posterior_predictive(M.schools_pm4(), trace, seed=1)
+    assert out is not trace and "posterior_predictive" in out.groups() and "posterior" in out.groups()
+    ppc = out.posterior_predictive
+    assert sorted(ppc) == ["schools_pm4/obs"] and ppc["schools_pm4/obs"].shape == (chains, samples, 8)
+    post = trace.posterior
+    theta = post["schools_pm4/mu"][..., None] + post["schools_pm4/tau"][..., None] * post["schools_pm4/eta"]
+    z = (ppc["schools_pm4/obs"] - theta) / M.SIGMA8
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05
+    again = pm.sample_posterior_predictive(M.schools_pm4(), trace, seed=1, inplace=False)
+    assert again.groups() == ["posterior_predictive"]
+    assert np.array_equal(again.posterior_predictive["schools_pm4/obs"], ppc["schools_pm4/obs"])
+    with pytest.raises(KeyError):
+        pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=["schools_pm4/nope"])
+    with pytest.raises(ValueError):
+        pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=[])
