@@ -100,9 +100,13 @@ def workload_config(args, n_gpus):
         "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept NUTS transitions",
         "step_size": ("per-chain dual averaging from %.3g (leading chain axis; no cross-chain coupling)" % args.step_size)
                      if args.eps_mode == "per-chain" else
-                     ("pooled dual averaging from %.3g (scalar step_size, reference default; one epsilon per rank)" % args.step_size),
+                     ("pooled dual averaging from %.3g (scalar step_size, reference default; ONE epsilon for the chains "
+                      "of all ranks: per-transition exchange over NVLink peer memory inside the adaptation kernel)"
+                      % args.step_size),
         "max_tree_depth": 10,
-        "parallelism": "chains sharded, %d per GPU; no data-path collective" % args.chains,
+        "parallelism": ("chains sharded, %d per GPU; " % args.chains)
+                       + ("no data-path collective" if (n_gpus == 1 or args.eps_mode == "per-chain") else
+                          "one 16-byte all-reduce per burn-in transition (pooled step size), none afterwards"),
         "l2": "L2 flushed (256 MiB write) between timed steps",
     }
 
@@ -285,6 +289,12 @@ def run_b200(args):
     model, ir = build_model()
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
+    comm = None
+    if world > 1 and args.eps_mode == "pooled":
+        # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
+        # of the chains of ALL ranks (mailboxes in peer memory, read over NVLink by the dual-averaging kernel)
+        comm = _cabi.Communicator(local_rank, rank, world)
+        dm.attach_comm(comm)
     adapt = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
                        num_adaptation_steps=B)
 
@@ -355,7 +365,8 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         step_arr = np.full((C, 1), args.step_size, dtype=np.float32) if args.eps_mode == "per-chain" else args.step_size
-        nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C)
+        extra = {"comm": comm} if comm is not None else {}
+        nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C, **extra)
         e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
         n_e2e = max(1, min(args.steps, 2))
         for k in range(1 + n_e2e):  # first pass untimed (allocator / pinned-buffer warm-up)

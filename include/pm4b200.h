@@ -291,6 +291,23 @@ int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const voi
                  void* log_accept_dev, int32_t* depth_dev, void* step_size_dev,
                  int64_t* total_leapfrogs_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU: chains of one pm.sample call sharded over the GPUs of one box, one process per GPU.
+ * The sampler has ONE exchange step: with a scalar step_size (PM4_EPS_POOLED) tfp's
+ * DualAveragingStepSizeAdaptation adapts one epsilon from the mean acceptance of ALL chains
+ * (SURVEY App. A.3), i.e. one all-reduce of (sum, count) per burn-in transition.  It is fused into the
+ * dual-averaging kernel: every rank owns a small mailbox in device memory, exported with CUDA IPC and
+ * read by its peers over NVLink.  Protocol: pm4_comm_create on every rank -> exchange the 64-byte
+ * handles (e.g. torch.distributed.all_gather) -> pm4_comm_connect -> pm4_model_attach_comm.
+ * All ranks must then issue the same sequence of pm4_nuts_run / pm4_hmc_run calls.
+ * ------------------------------------------------------------------------------------------ */
+#define PM4_IPC_HANDLE_BYTES 64
+typedef struct pm4_comm pm4_comm_t;
+int pm4_comm_create(int device, int rank, int world, pm4_comm_t** out, unsigned char handle_out[PM4_IPC_HANDLE_BYTES]);
+int pm4_comm_connect(pm4_comm_t* comm, const unsigned char* handles /* [world][PM4_IPC_HANDLE_BYTES] */);
+int pm4_comm_destroy(pm4_comm_t* comm);
+int pm4_model_attach_comm(pm4_model_t* m, pm4_comm_t* comm /* NULL detaches */);
+
 /* Bytes of device scratch pm4_nuts_run / pm4_hmc_run allocate internally for C chains. */
 int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth);
 

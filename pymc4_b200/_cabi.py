@@ -31,6 +31,7 @@ EXPORTS = [
     "pm4_logp_grad",
     "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
+    "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm",
 ]
 
 
@@ -83,6 +84,10 @@ def load_library():
     L.pm4_launch_count.argtypes = [i32]
     L.pm4_launch_count.restype = i64
     L.pm4_last_error.restype = ctypes.c_char_p
+    L.pm4_comm_create.argtypes = [i32, i32, i32, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.pm4_comm_connect.argtypes = [vp, ctypes.c_char_p]
+    L.pm4_comm_destroy.argtypes = [vp]
+    L.pm4_model_attach_comm.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -167,6 +172,11 @@ class DeviceModel:
         return self.torch.empty(shape, dtype=dtype, device=self._dev())
 
     # -- API ---------------------------------------------------------------------
+    def attach_comm(self, comm: Optional["Communicator"]):
+        """Couple the pooled step size of this model's runs with the other ranks of ``comm`` (None detaches)."""
+        self._check(self.lib.pm4_model_attach_comm(self.handle, comm.handle if comm is not None else None))
+        self._comm = comm
+
     def set_data(self, ir: ModelIR):
         """New constant pools for the same structure (new observed values)."""
         if ir.struct_hash != self.ir.struct_hash:
@@ -285,3 +295,38 @@ class DeviceModel:
         self._check(rc)
         out["_keepalive"] = (th0, sc, mom, uni)
         return out
+
+
+class Communicator:
+    """The box-wide exchange the sampler needs: one mailbox per rank in device memory, mapped into every peer
+    with CUDA IPC and read over NVLink by the pooled dual-averaging kernel (include/pm4b200.h: pm4_comm_*).
+    ``torch.distributed`` only carries the 64-byte IPC handles at set-up."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, device: int, rank: int, world: int, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+
+        self.lib = load_library()
+        self.rank, self.world = int(rank), int(world)
+        self.handle = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        rc = self.lib.pm4_comm_create(int(device), self.rank, self.world, ctypes.byref(self.handle), buf)
+        if rc != 0:
+            raise RuntimeError("libpm4b200: %s (code %d)" % (self.lib.pm4_last_error().decode(), rc))
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend(group) == "nccl":
+            mine = mine.to(torch.device("cuda", int(device)))
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=group)
+        handles = b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts)
+        rc = self.lib.pm4_comm_connect(self.handle, handles)
+        if rc != 0:
+            raise RuntimeError("libpm4b200: %s (code %d)" % (self.lib.pm4_last_error().decode(), rc))
+        dist.barrier(group=group)
+
+    def close(self):
+        if self.handle and self.handle.value:
+            self.lib.pm4_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()

@@ -51,8 +51,17 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace
 
+struct pm4_comm {
+  int device = 0, rank = 0, world = 1;
+  void* box[PM4_MAX_RANKS] = {nullptr};  // box[rank] is ours (cudaMalloc), the others are IPC mappings
+  int32_t* d_error = nullptr;
+  uint32_t epoch = 0;                    // one per sampling call: stale mailbox entries never match
+  bool connected = false;
+};
+
 struct pm4_model {
   int device = 0;
+  pm4_comm* comm = nullptr;
   int D = 0, n_terms = 0, n_ops = 0, n_dets = 0, det_row = 0;
   int64_t n_dataf = 0, n_datai = 0;
   std::vector<double> dataf;
@@ -100,6 +109,9 @@ struct pm4_model {
     return a;
   }
 };
+
+static void fill_comm(pm4_model* m, pm4_mod_run_t& r);
+static int check_comm(pm4_model* m, cudaStream_t st);
 
 static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   const int64_t nf = ir->n_planf, ni = ir->n_plani;
@@ -446,9 +458,11 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   r.energy = energy_dev; r.log_accept = log_accept_dev; r.depth = depth_dev;
   r.total_leapfrogs = total_leapfrogs_dev;
 
+  fill_comm(m, r);
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
   if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, (int32_t*)order, st))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  if (r.adapt_enabled && r.adapt_pooled) return check_comm(m, st);
   return PM4_OK;
 }
 
@@ -488,9 +502,92 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   r.states = states_dev; r.lp_out = lp_dev; r.log_accept = log_accept_dev; r.diverging = accepted_dev;
   r.traj = traj_dev;
 
+  fill_comm(m, r);
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
   if ((rc = drive(m, dtype, r, false, cfg->warps_per_block, T, nullptr, st))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  if (r.adapt_enabled && r.adapt_pooled) return check_comm(m, st);
+  return PM4_OK;
+}
+
+extern "C" int pm4_comm_create(int device, int rank, int world, pm4_comm_t** out, unsigned char* handle_out) {
+  if (!out || !handle_out || world < 1 || world > PM4_MAX_RANKS || rank < 0 || rank >= world)
+    return fail(PM4_EINVAL, "pm4_comm_create: bad argument (at most %d ranks)", PM4_MAX_RANKS);
+  static_assert(sizeof(cudaIpcMemHandle_t) == PM4_IPC_HANDLE_BYTES, "IPC handle size");
+  CU(cudaSetDevice(device));
+  pm4_comm* c = new pm4_comm();
+  c->device = device; c->rank = rank; c->world = world;
+  const size_t bytes = 32 * PM4_COMM_SLOTS + 64;
+  cudaError_t e = cudaMalloc(&c->box[rank], bytes);
+  if (e == cudaSuccess) e = cudaMemset(c->box[rank], 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_error, sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(c->d_error, 0, sizeof(int32_t));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->box[rank]);
+  if (e != cudaSuccess) {
+    int rc = fail(PM4_ECUDA, "pm4_comm_create: %s", cudaGetErrorString(e));
+    pm4_comm_destroy(c);
+    return rc;
+  }
+  memcpy(handle_out, &h, sizeof h);
+  *out = c;
+  return PM4_OK;
+}
+
+extern "C" int pm4_comm_connect(pm4_comm_t* c, const unsigned char* handles) {
+  if (!c || !handles) return fail(PM4_EINVAL, "pm4_comm_connect: null argument");
+  CU(cudaSetDevice(c->device));
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank || c->box[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * PM4_IPC_HANDLE_BYTES, sizeof h);
+    cudaError_t e = cudaIpcOpenMemHandle(&c->box[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(PM4_ECUDA, "pm4_comm_connect: cannot map the mailbox of rank %d: %s", r, cudaGetErrorString(e));
+  }
+  c->connected = true;
+  return PM4_OK;
+}
+
+extern "C" int pm4_comm_destroy(pm4_comm_t* c) {
+  if (!c) return PM4_OK;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->world; ++r) {
+    if (!c->box[r]) continue;
+    if (r == c->rank) cudaFree(c->box[r]);
+    else cudaIpcCloseMemHandle(c->box[r]);
+  }
+  cudaFree(c->d_error);
+  delete c;
+  return PM4_OK;
+}
+
+extern "C" int pm4_model_attach_comm(pm4_model_t* m, pm4_comm_t* c) {
+  if (!m) return fail(PM4_EINVAL, "null model");
+  if (c && (!c->connected || c->device != m->device)) return fail(PM4_EINVAL, "communicator is not connected or lives on another device");
+  m->comm = c;
+  return PM4_OK;
+}
+
+// fill the coupling fields of a run; a new epoch per sampling call
+static void fill_comm(pm4_model* m, pm4_mod_run_t& r) {
+  for (int k = 0; k < PM4_MAX_RANKS; ++k) r.comm_box[k] = nullptr;
+  r.comm_rank = 0; r.comm_world = 1; r.comm_epoch = 0; r.comm_error = nullptr;
+  if (!m->comm || m->comm->world < 2) return;
+  pm4_comm* c = m->comm;
+  for (int k = 0; k < c->world; ++k) r.comm_box[k] = c->box[k];
+  r.comm_rank = c->rank; r.comm_world = c->world; r.comm_epoch = ++c->epoch; r.comm_error = c->d_error;
+}
+
+// after a run with a communicator: did a peer time out?  (synchronises the stream)
+static int check_comm(pm4_model* m, cudaStream_t st) {
+  if (!m->comm || m->comm->world < 2) return PM4_OK;
+  int32_t err = 0;
+  CU(cudaMemcpyAsync(&err, m->comm->d_error, sizeof err, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (err) {
+    cudaMemsetAsync(m->comm->d_error, 0, sizeof(int32_t), st);
+    return fail(PM4_ECUDA, "pooled step-size exchange timed out waiting for rank %d", err - 1);
+  }
   return PM4_OK;
 }
 

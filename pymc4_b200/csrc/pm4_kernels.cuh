@@ -266,6 +266,10 @@ template <typename real> struct RunParams {
   int32_t* queue;
   const int32_t* order;
   int32_t* launch_leaps;
+  void* comm_box[PM4_MAX_RANKS];
+  int comm_rank, comm_world;
+  uint32_t comm_epoch;
+  int32_t* comm_error;
   real* states;
   real* lp_out;
   int32_t* leapfrogs;
@@ -292,6 +296,8 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.step_scale = (const real*)r.step_scale; p.momenta = (const real*)r.momenta;
   p.uniforms = (const real*)r.uniforms; p.scratch = (real*)r.scratch;
   p.queue = r.queue; p.order = r.order; p.launch_leaps = r.launch_leaps;
+  for (int k = 0; k < PM4_MAX_RANKS; ++k) p.comm_box[k] = r.comm_box[k];
+  p.comm_rank = r.comm_rank; p.comm_world = r.comm_world; p.comm_epoch = r.comm_epoch; p.comm_error = r.comm_error;
   p.states = (real*)r.states; p.lp_out = (real*)r.lp_out; p.leapfrogs = r.leapfrogs;
   p.diverging = r.diverging; p.energy = (real*)r.energy; p.log_accept = (real*)r.log_accept;
   p.depth = r.depth; p.total_leapfrogs = r.total_leapfrogs; p.traj = (real*)r.traj;
@@ -320,8 +326,20 @@ template <typename real> struct DualAvg {
   }
 };
 
+// mailbox slot a rank publishes per lock-step transition (32 bytes; peers read it over NVLink)
+struct CommSlot {
+  double sum, count;
+  unsigned long long seq;
+  unsigned long long pad;
+};
+
 // one-block kernel: pooled (cross-chain) dual-averaging update after a lock-step transition.
 // reduce_logmeanexp over chains followed by exp = arithmetic mean of the acceptance probabilities.
+// With a communicator attached (chains of one pm.sample call sharded over the GPUs of the box, scalar
+// step_size) the mean is over the chains of ALL ranks: the reduction and the exchange are one kernel --
+// every rank writes (sum, count) into its own mailbox, reads its peers' mailboxes through NVLink peer
+// memory, and adds them in rank order, so all ranks compute the bit-identical epsilon.  A peer that
+// does not show up within ~4 s raises the device error word instead of hanging the GPU.
 template <typename real>
 __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int t) {
   __shared__ double part[32];
@@ -333,10 +351,42 @@ __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int 
   if (threadIdx.x < 32) {
     double v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
     v = warp_sum(v);
+    double total = v, count = (double)a.C;
+    if (a.comm_world > 1) {
+      const unsigned long long seq = ((unsigned long long)a.comm_epoch << 32) | (unsigned long long)(t + 1);
+      const int slot = t % PM4_COMM_SLOTS;
+      if (threadIdx.x == 0) {
+        volatile CommSlot* mine = reinterpret_cast<volatile CommSlot*>(a.comm_box[a.comm_rank]) + slot;
+        mine->sum = v;
+        mine->count = (double)a.C;
+        __threadfence_system();
+        mine->seq = seq;
+        __threadfence_system();
+      }
+      // lane r waits for rank r, then the sums are added in rank order
+      double ps = 0, pc = 0;
+      if ((int)threadIdx.x < a.comm_world) {
+        volatile CommSlot* box = reinterpret_cast<volatile CommSlot*>(a.comm_box[threadIdx.x]) + slot;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (box->seq != seq) {
+          if (clock64() - t0 > 8000000000ll) { ok = false; break; }
+          __nanosleep(200);
+        }
+        __threadfence_system();
+        if (ok) { ps = box->sum; pc = box->count; }
+        else if (a.comm_error) atomicExch(a.comm_error, 1 + (int)threadIdx.x);
+      }
+      total = 0; count = 0;
+      for (int r = 0; r < a.comm_world; ++r) {
+        total += __shfl_sync(FULL, ps, r);
+        count += __shfl_sync(FULL, pc, r);
+      }
+    }
     if (threadIdx.x == 0) {
       DualAvg<real> d;
       d.load(a.da);
-      d.update(a, t, (real)(v / (double)a.C));
+      d.update(a, t, (real)(total / count));
       d.store(a.da);
     }
   }

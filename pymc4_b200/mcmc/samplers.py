@@ -39,7 +39,7 @@ if not _log.handlers:
 _log.setLevel(logging.INFO)
 
 # keyword arguments of this backend that the reference does not have
-_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block")
+_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block", "comm")
 
 
 def register_sampler(cls):
@@ -300,6 +300,8 @@ class HMC(_BaseSampler):
                            num_leapfrog_steps=spec.num_leapfrog_steps, seed=self._seed_value(), adapt=adapt,
                            warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
                            chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        if "comm" in self.backend_kwargs:
+            dm.attach_comm(self.backend_kwargs["comm"])
         out = dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale)
         self._run_info = dict(step_size=out["step_size"], kernel="hmc",
                               leapfrogs_per_transition=spec.num_leapfrog_steps)
@@ -351,6 +353,8 @@ class NUTS(_BaseSampler):
                             adapt=self._adapt_cfg(mode),
                             warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
                             chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        if "comm" in self.backend_kwargs:  # chains of this call are one shard of a box-wide run
+            dm.attach_comm(self.backend_kwargs["comm"])
         out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale)
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
                               depth=out["depth"], kernel="nuts")
