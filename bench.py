@@ -324,6 +324,8 @@ def run_b200(args):
     wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)  # evict L2 between timed steps (not timed)
+        if comm is not None:
+            barrier()  # coupled ranks start a step together (a rank waits for its peers inside the step)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = dm.nuts(cfg_for(k), theta0, dtype=np.float32)

@@ -339,7 +339,7 @@ struct CommSlot {
 // step_size) the mean is over the chains of ALL ranks: the reduction and the exchange are one kernel --
 // every rank writes (sum, count) into its own mailbox, reads its peers' mailboxes through NVLink peer
 // memory, and adds them in rank order, so all ranks compute the bit-identical epsilon.  A peer that
-// does not show up within ~4 s raises the device error word instead of hanging the GPU.
+// does not show up within ~30 s raises the device error word (once per run) instead of hanging the GPU.
 template <typename real>
 __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int t) {
   __shared__ double part[32];
@@ -352,7 +352,9 @@ __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int 
     double v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
     v = warp_sum(v);
     double total = v, count = (double)a.C;
-    if (a.comm_world > 1) {
+    // a peer already timed out in this run: keep going with the local chains instead of waiting again
+    const bool comm_ok = a.comm_world > 1 && !(a.comm_error && *reinterpret_cast<volatile int32_t*>(a.comm_error) != 0);
+    if (comm_ok) {
       const unsigned long long seq = ((unsigned long long)a.comm_epoch << 32) | (unsigned long long)(t + 1);
       const int slot = t % PM4_COMM_SLOTS;
       if (threadIdx.x == 0) {
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int 
         const long long t0 = clock64();
         bool ok = true;
         while (box->seq != seq) {
-          if (clock64() - t0 > 8000000000ll) { ok = false; break; }
+          if (clock64() - t0 > 60000000000ll) { ok = false; break; }  // ~30 s at 2 GHz
           __nanosleep(200);
         }
         __threadfence_system();
