@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM4_ABI_VERSION 3
+#define PM4_ABI_VERSION 4
 
 /* error codes */
 #define PM4_OK 0
@@ -228,6 +228,12 @@ int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, const void* t
 #define PM4_EPS_POOLED 0    /* one scalar shared by all chains (reference default, scalar step_size) */
 #define PM4_EPS_PER_CHAIN 1 /* step_size carries a leading chain axis: independent adaptation       */
 
+/* adaptation scheme: tfp DualAveragingStepSizeAdaptation (samplers "hmc", "nuts") or
+ * tfp SimpleStepSizeAdaptation (samplers "hmc_simple", "nuts_simple", samplers.py:318-339, 422-447):
+ * step *= (1 + adaptation_rate) when the mean acceptance exceeds the target, else /= (1 + rate) */
+#define PM4_ADAPT_DUAL_AVERAGING 0
+#define PM4_ADAPT_SIMPLE 1
+
 typedef struct pm4_adapt_cfg {
   int32_t mode;                 /* PM4_EPS_*                                  */
   int32_t num_adaptation_steps; /* = burn_in (inference/sampling.py:155-156)  */
@@ -236,8 +242,15 @@ typedef struct pm4_adapt_cfg {
   double step_count_smoothing;  /* 10                                         */
   double decay_rate;            /* 0.75                                       */
   int32_t enabled;              /* 0: fixed step size                         */
-  int32_t _pad;
+  int32_t kind;                 /* PM4_ADAPT_*                                */
+  double adaptation_rate;       /* 0.01 (PM4_ADAPT_SIMPLE)                    */
 } pm4_adapt_cfg_t;
+
+/* proposals of the Metropolis-Hastings kernel run by pm4_hmc_run */
+#define PM4_PROPOSAL_LEAPFROG 0     /* Hamiltonian Monte Carlo (samplers "hmc", "hmc_simple")                    */
+#define PM4_PROPOSAL_RANDOM_WALK 1  /* tfp RandomWalkMetropolis with random_walk_normal_fn (sampler "rwm",
+                                       samplers.py:450-478): state + scale * N(0, 1), gradient-free; the
+                                       `momenta` argument then injects the perturbations               */
 
 typedef struct pm4_hmc_cfg {
   int32_t C;                  /* chains                                                    */
@@ -249,6 +262,9 @@ typedef struct pm4_hmc_cfg {
   pm4_adapt_cfg_t adapt;
   int32_t warps_per_block;    /* warps per thread block (a multiple of the model's team size); 0 = library default */
   int32_t chain_offset;       /* global index of chain 0 (RNG stream id) when chains are sharded */
+  int32_t proposal;           /* PM4_PROPOSAL_*                                            */
+  int32_t _pad;
+  double rw_scale;            /* PM4_PROPOSAL_RANDOM_WALK: standard deviation of the normal perturbation (1.0) */
 } pm4_hmc_cfg_t;
 
 /* Fixed-L HMC (tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC); App. A.4).

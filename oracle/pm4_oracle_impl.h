@@ -488,6 +488,11 @@ static void NAME(da_init)(NAME(da_t)* s, REAL eps0) {
 /* called after transition t (0-based) with the (cross-chain or per-chain) mean accept prob */
 static void NAME(da_update)(NAME(da_t)* s, const pm4_adapt_cfg_t* a, int t, REAL accept) {
   if (!a->enabled) return;
+  if (a->kind == PM4_ADAPT_SIMPLE) { /* tfp SimpleStepSizeAdaptation.one_step: multiplicative, no averaging */
+    const REAL f = 1 + (REAL)a->adaptation_rate;
+    if (t < a->num_adaptation_steps) s->eps = accept > (REAL)a->target_accept_prob ? s->eps * f : s->eps / f;
+    return;
+  }
   REAL step = (REAL)(t + 1);
   s->error_sum += (REAL)a->target_accept_prob - accept;
   REAL log_eps = s->log_shrink_target -
@@ -756,10 +761,18 @@ int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL*
       const REAL k0 = (REAL)0.5 * NAME(dot)(pp, pp, D);
       memcpy(pth, cth, sizeof(REAL) * (size_t)D);
       memcpy(pg, cgr, sizeof(REAL) * (size_t)D);
-      REAL plp = lp[c];
-      NAME(leapfrog)(ir, &ws, L, eps, step_scale, pth, pp, pg, &plp);
-      const REAL k1 = (REAL)0.5 * NAME(dot)(pp, pp, D);
-      REAL lar = (plp - lp[c]) + (k0 - k1);
+      REAL plp = lp[c], lar;
+      if (cfg->proposal == PM4_PROPOSAL_RANDOM_WALK) {
+        /* tfp RandomWalkMetropolis with random_walk_normal_fn(scale): symmetric proposal, gradient-free
+         * (/root/reference/pymc4/mcmc/samplers.py:450-478) */
+        for (int j = 0; j < D; ++j) pth[j] = pth[j] + (REAL)cfg->rw_scale * pp[j];
+        plp = NAME(logp_grad1)(ir, &ws, pth, pg);
+        lar = plp - lp[c];
+      } else {
+        NAME(leapfrog)(ir, &ws, L, eps, step_scale, pth, pp, pg, &plp);
+        const REAL k1 = (REAL)0.5 * NAME(dot)(pp, pp, D);
+        lar = (plp - lp[c]) + (k0 - k1);
+      }
       if (!isfinite(lar)) lar = -(REAL)INFINITY;
       REAL u = uniforms ? uniforms[(size_t)t * C + c]
                         : NAME(draw_u)(cfg->seed, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, 0, PM4_RNG_HMC, 0);

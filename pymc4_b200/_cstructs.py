@@ -3,6 +3,8 @@ import ctypes
 
 PM4_F32, PM4_F64 = 0, 1
 PM4_EPS_POOLED, PM4_EPS_PER_CHAIN = 0, 1
+PM4_ADAPT_DUAL_AVERAGING, PM4_ADAPT_SIMPLE = 0, 1
+PM4_PROPOSAL_LEAPFROG, PM4_PROPOSAL_RANDOM_WALK = 0, 1
 
 
 class AdaptCfg(ctypes.Structure):
@@ -14,7 +16,8 @@ class AdaptCfg(ctypes.Structure):
         ("step_count_smoothing", ctypes.c_double),
         ("decay_rate", ctypes.c_double),
         ("enabled", ctypes.c_int32),
-        ("_pad", ctypes.c_int32),
+        ("kind", ctypes.c_int32),
+        ("adaptation_rate", ctypes.c_double),
     ]
 
 
@@ -29,6 +32,9 @@ class HMCCfg(ctypes.Structure):
         ("adapt", AdaptCfg),
         ("warps_per_block", ctypes.c_int32),
         ("chain_offset", ctypes.c_int32),
+        ("proposal", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("rw_scale", ctypes.c_double),
     ]
 
 
@@ -49,10 +55,10 @@ class NUTSCfg(ctypes.Structure):
 
 def make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=0, target_accept_prob=0.75,
                exploration_shrinkage=0.05, step_count_smoothing=10.0, decay_rate=0.75,
-               enabled=True) -> AdaptCfg:
+               enabled=True, kind=PM4_ADAPT_DUAL_AVERAGING, adaptation_rate=0.01) -> AdaptCfg:
     return AdaptCfg(int(mode), int(num_adaptation_steps), float(target_accept_prob),
                     float(exploration_shrinkage), float(step_count_smoothing), float(decay_rate),
-                    int(bool(enabled)), 0)
+                    int(bool(enabled)), int(kind), float(adaptation_rate))
 
 
 def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_depth=10,
@@ -64,8 +70,9 @@ def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_de
 
 
 def make_hmc_cfg(C, num_results, num_burnin, step_size=0.1, num_leapfrog_steps=3, seed=0,
-                 adapt=None, warps_per_block=0, chain_offset=0) -> HMCCfg:
+                 adapt=None, warps_per_block=0, chain_offset=0, proposal=PM4_PROPOSAL_LEAPFROG,
+                 rw_scale=1.0) -> HMCCfg:
     adapt = adapt if adapt is not None else make_adapt(num_adaptation_steps=num_burnin)
     return HMCCfg(int(C), int(num_results), int(num_burnin), int(num_leapfrog_steps),
                   float(step_size), int(seed) & (2**64 - 1), adapt, int(warps_per_block),
-                  int(chain_offset))
+                  int(chain_offset), int(proposal), 0, float(rw_scale))

@@ -362,6 +362,9 @@ struct RunBuffers {
 
 int fill_adapt(pm4_mod_run_t& r, const pm4_adapt_cfg_t& a) {
   if (a.mode != PM4_EPS_POOLED && a.mode != PM4_EPS_PER_CHAIN) return fail(PM4_EINVAL, "unknown step-size mode %d", a.mode);
+  if (a.kind != PM4_ADAPT_DUAL_AVERAGING && a.kind != PM4_ADAPT_SIMPLE) return fail(PM4_EINVAL, "unknown adaptation kind %d", a.kind);
+  r.adapt_kind = a.kind;
+  r.adapt_rate = a.adaptation_rate;
   r.adapt_enabled = a.enabled ? 1 : 0;
   r.adapt_pooled = a.mode == PM4_EPS_POOLED ? 1 : 0;
   r.num_adapt = a.num_adaptation_steps;
@@ -473,9 +476,12 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_hmc_run: null argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
-  if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0 || cfg->num_leapfrog_steps < 1)
+  const bool rw = cfg->proposal == PM4_PROPOSAL_RANDOM_WALK;
+  if (cfg->proposal != PM4_PROPOSAL_LEAPFROG && !rw) return fail(PM4_EINVAL, "unknown proposal %d", cfg->proposal);
+  if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0 || (!rw && cfg->num_leapfrog_steps < 1))
     return fail(PM4_EINVAL, "pm4_hmc_run: bad chain/draw/leapfrog counts");
   if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
+  if (rw && !(cfg->rw_scale > 0)) return fail(PM4_EINVAL, "rw_scale must be positive");
   CU(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
@@ -486,6 +492,8 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   r.A = m->args(dtype);
   r.C = cfg->C; r.B = cfg->num_burnin; r.S = cfg->num_results;
   r.num_leapfrog = cfg->num_leapfrog_steps;
+  r.random_walk = rw ? 1 : 0;
+  r.rw_scale = cfg->rw_scale;
   r.chain_offset = cfg->chain_offset;
   r.seed_lo = (uint32_t)cfg->seed; r.seed_hi = (uint32_t)(cfg->seed >> 32);
   if ((rc = fill_adapt(r, cfg->adapt))) return rc;

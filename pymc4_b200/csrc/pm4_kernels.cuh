@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(256) predict_kernel(ModelArgs<real> A, int64_t
 template <typename real> struct RunParams {
   ModelArgs<real> A;
   int C, t_begin, t_count, B, S, max_depth, num_leapfrog, chain_offset;
-  int adapt_enabled, adapt_pooled, num_adapt;
+  int adapt_enabled, adapt_pooled, num_adapt, adapt_kind, random_walk;
   int team_reals, n_slots, n_fast;
-  real max_energy_diff, target_accept, shrinkage, smoothing, decay;
+  real max_energy_diff, target_accept, shrinkage, smoothing, decay, adapt_rate, rw_scale;
   uint32_t seed_lo, seed_hi;
   real* th;
   real* gr;
@@ -287,6 +287,8 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.C = r.C; p.t_begin = r.t_begin; p.t_count = r.t_count; p.B = r.B; p.S = r.S;
   p.max_depth = r.max_depth; p.num_leapfrog = r.num_leapfrog; p.chain_offset = r.chain_offset;
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
+  p.adapt_kind = r.adapt_kind; p.random_walk = r.random_walk;
+  p.adapt_rate = (real)r.adapt_rate; p.rw_scale = (real)r.rw_scale;
   p.team_reals = 0; p.n_slots = 0; p.n_fast = 0;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
@@ -316,6 +318,10 @@ template <typename real> struct DualAvg {
   }
   // called after transition t (0-based) with the mean acceptance probability
   template <class P> __device__ __forceinline__ void update(const P& a, int t, real accept) {
+    if (a.adapt_kind == 1) {  // tfp SimpleStepSizeAdaptation: multiplicative, no averaging
+      if (t < a.num_adapt) eps = accept > a.target_accept ? eps * ((real)1 + a.adapt_rate) : eps / ((real)1 + a.adapt_rate);
+      return;
+    }
     const real step = (real)(t + 1);
     error_sum += a.target_accept - accept;
     const real log_eps = log_shrink_target - error_sum * m_sqrt(step) / ((a.smoothing + step) * a.shrinkage);
@@ -848,26 +854,34 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
         th[r] = cth[TL * r]; g[r] = cg[TL * r];
         q[0] += p[r] * p[r];
       }
-      // half kick, L x (drift, gradient, full kick), half un-kick
+      real plp = clp, lar;
+      if (a.random_walk) {
+        // tfp RandomWalkMetropolis, random_walk_normal_fn: symmetric proposal state + scale * N(0, 1)
 #pragma unroll
-      for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es(r)) * g[r];
-      real plp = clp;
-      for (int l = 0; l < a.num_leapfrog; ++l) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) th[r] = th[r] + es(r) * p[r];
+        for (int r = 0; r < R; ++r) th[r] = th[r] + a.rw_scale * p[r];
         plp = logp_grad<M, real>(th, g, c, own);
+        lar = plp - clp;
+      } else {
+        // half kick, L x (drift, gradient, full kick), half un-kick
 #pragma unroll
-        for (int r = 0; r < R; ++r) p[r] = p[r] + es(r) * g[r];
-      }
+        for (int r = 0; r < R; ++r) p[r] = p[r] + ((real)0.5 * es(r)) * g[r];
+        for (int l = 0; l < a.num_leapfrog; ++l) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        p[r] = p[r] - ((real)0.5 * es(r)) * g[r];
-        q[1] += p[r] * p[r];
+          for (int r = 0; r < R; ++r) th[r] = th[r] + es(r) * p[r];
+          plp = logp_grad<M, real>(th, g, c, own);
+#pragma unroll
+          for (int r = 0; r < R; ++r) p[r] = p[r] + es(r) * g[r];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          p[r] = p[r] - ((real)0.5 * es(r)) * g[r];
+          q[1] += p[r] * p[r];
+        }
+        team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
+        rb ^= 1;
+        const real k0 = (real)0.5 * q[0], k1 = (real)0.5 * q[1];
+        lar = (plp - clp) + (k0 - k1);
       }
-      team_sum<T, 4, real>(q, c, c.red + rb * 4 * T);
-      rb ^= 1;
-      const real k0 = (real)0.5 * q[0], k1 = (real)0.5 * q[1];
-      real lar = (plp - clp) + (k0 - k1);
       if (!(lar == lar) || lar == m_inf<real>() || lar == -m_inf<real>()) lar = -m_inf<real>();
       real u;
       if (a.uniforms) u = a.uniforms[(size_t)t * C + chain];

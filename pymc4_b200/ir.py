@@ -29,7 +29,7 @@ from . import symbolic as sym
 from .coroutine_model import Model
 from .utils import NameParts
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
 

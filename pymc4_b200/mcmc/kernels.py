@@ -70,6 +70,44 @@ class DualAveragingStepSizeAdaptation:
     is_calibrated = True
 
 
+class SimpleStepSizeAdaptation:
+    """tfp.mcmc.SimpleStepSizeAdaptation: step *= (1 + adaptation_rate) when the (mean) acceptance
+    probability exceeds the target, /= otherwise, for the first ``num_adaptation_steps`` transitions."""
+
+    def __init__(self, inner_kernel, num_adaptation_steps, target_accept_prob=0.75, adaptation_rate=0.01,
+                 step_size_setter_fn: Optional[Callable] = None, step_size_getter_fn: Optional[Callable] = None,
+                 log_accept_prob_getter_fn: Optional[Callable] = None, reduce_fn: Any = None,
+                 validate_args=False, name=None):
+        self.inner_kernel = inner_kernel
+        self.num_adaptation_steps = int(num_adaptation_steps)
+        self.target_accept_prob = float(target_accept_prob)
+        self.adaptation_rate = float(adaptation_rate)
+        self.name = name
+
+    is_calibrated = True
+
+
+class RandomWalkMetropolis:
+    """tfp.mcmc.RandomWalkMetropolis: proposal = state + perturbation, Metropolis-Hastings accept.  Only the
+    default ``new_state_fn`` (``random_walk_normal_fn(scale=1.0)``) runs on the device; ``scale`` (a backend
+    extension) sets its standard deviation."""
+
+    def __init__(self, target_log_prob_fn, new_state_fn=None, seed=None, name=None, scale=1.0):
+        if new_state_fn is not None:
+            raise NotImplementedError("custom new_state_fn is not supported; the device proposal is "
+                                      "state + scale * Normal(0, 1) (tfp random_walk_normal_fn)")
+        self.target_log_prob_fn = target_log_prob_fn
+        self.scale = float(scale)
+        self.seed = seed
+        self.name = name
+
+    is_calibrated = True
+
+    @property
+    def parameters(self):
+        return dict(scale=self.scale)
+
+
 def sample_chain(num_results, current_state, previous_kernel_results=None, kernel=None, num_burnin_steps=0,
                  num_steps_between_results=0, trace_fn=None, return_final_kernel_results=False,
                  parallel_iterations=10, seed=None, name=None):

@@ -5,8 +5,9 @@ Class protocol, kwarg routing and return layout follow the reference
 :729-829 ``build_logp_and_deterministic_functions`` / ``vectorize_logp_function`` /
 ``tile_init``).  The one call that changes is ``_run_chains`` (:172-189): instead of
 ``tfp.mcmc.sample_chain`` it calls ``pm4_nuts_run`` / ``pm4_hmc_run`` of libpm4b200 through
-ctypes, with torch tensors as device buffers.  Out of scope for this backend:
-``hmc_simple`` / ``nuts_simple`` / ``rwm`` / ``compound`` (gradient-free or discrete-latent kernels).
+ctypes, with torch tensors as device buffers.  ``hmc_simple`` / ``nuts_simple`` (:318-339, :422-447:
+``SimpleStepSizeAdaptation``) and ``rwm`` (:450-478: random-walk Metropolis) run on the same kernels;
+``compound`` (discrete latents, :481-726) is out of scope for this backend.
 """
 import abc
 import inspect
@@ -18,7 +19,8 @@ import numpy as np
 
 from .. import flow
 from .. import ir as irmod
-from .._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt, make_hmc_cfg, make_nuts_cfg
+from .._cstructs import (PM4_ADAPT_SIMPLE, PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, PM4_PROPOSAL_RANDOM_WALK, make_adapt,
+                         make_hmc_cfg, make_nuts_cfg)
 from ..coroutine_model import Model
 from ..utils import NameParts
 from . import kernels as mcmc
@@ -30,7 +32,7 @@ from .utils import (
     trace_to_arviz,
 )
 
-__all__ = ["HMC", "NUTS"]
+__all__ = ["HMC", "HMCSimple", "NUTS", "NUTSSimple", "RandomWalkM"]
 reg_samplers: Dict[str, type] = {}
 
 _log = logging.getLogger("pymc4.sampling")
@@ -243,6 +245,10 @@ class _BaseSampler(metaclass=abc.ABCMeta):
         if self._adaptation is None or "num_adaptation_steps" not in a:
             return make_adapt(mode=mode, enabled=False)
         spec = self._adaptation(inner_kernel=None, **{k: v for k, v in a.items() if not callable(v)})
+        if isinstance(spec, mcmc.SimpleStepSizeAdaptation):
+            return make_adapt(mode=mode, num_adaptation_steps=spec.num_adaptation_steps,
+                              target_accept_prob=spec.target_accept_prob, kind=PM4_ADAPT_SIMPLE,
+                              adaptation_rate=spec.adaptation_rate, enabled=True)
         return make_adapt(mode=mode, num_adaptation_steps=spec.num_adaptation_steps,
                           target_accept_prob=spec.target_accept_prob,
                           exploration_shrinkage=spec.exploration_shrinkage,
@@ -311,6 +317,14 @@ class HMC(_BaseSampler):
 
 
 @register_sampler
+class HMCSimple(HMC):
+    """HMC under ``SimpleStepSizeAdaptation`` (multiplicative step-size updates; reference :318-339)."""
+
+    _name = "hmc_simple"
+    _adaptation = mcmc.SimpleStepSizeAdaptation
+
+
+@register_sampler
 class NUTS(_BaseSampler):
     """No-U-Turn sampler under dual-averaging step-size adaptation (default ``step_size=0.1``;
     stats ``lp, tree_size, diverging, energy, mean_tree_accept``; reference :342-419)."""
@@ -358,6 +372,54 @@ class NUTS(_BaseSampler):
         out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale)
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
                               depth=out["depth"], kernel="nuts")
+        self._last_states = out["states"]
+        results = self._unpack_states(out["states"])
+        return results, self.trace_fn(out["states"], out)
+
+
+@register_sampler
+class NUTSSimple(NUTS):
+    """NUTS under ``SimpleStepSizeAdaptation`` (reference :422-447)."""
+
+    _name = "nuts_simple"
+    _adaptation = mcmc.SimpleStepSizeAdaptation
+    default_adapter_kwargs: dict = {k: v for k, v in NUTS.default_adapter_kwargs.items()}
+
+
+@register_sampler
+class RandomWalkM(_BaseSampler):
+    """Random-walk Metropolis (gradient-free): proposal = state + Normal(0, 1) perturbation, MH accept
+    (tfp RandomWalkMetropolis with its default ``random_walk_normal_fn``; reference :450-478).
+    ``stat_names = ["mean_accept"]``; ``trace_fn`` returns ``(log_accept_ratio, *deterministics)``."""
+
+    _name = "rwm"
+    _adaptation = None
+    _kernel = mcmc.RandomWalkMetropolis
+    _grad = False
+
+    default_kernel_kwargs: dict = {}
+    default_adapter_kwargs: dict = {}
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.stat_names = ["mean_accept"]
+
+    def trace_fn(self, current_state, pkr):
+        return (pkr["log_accept"],) + tuple(self._deterministic_values(current_state))
+
+    def _run_chains(self, init, burn_in):
+        self._check_chain_kwargs()
+        dm = self._device_model
+        theta0 = self._pack_init(init)
+        C = theta0.shape[0]
+        spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
+        cfg = make_hmc_cfg(C, self._num_samples, burn_in, step_size=1.0, num_leapfrog_steps=0,
+                           seed=self._seed_value(), adapt=make_adapt(enabled=False),
+                           warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
+                           chain_offset=self.backend_kwargs.get("chain_offset", 0),
+                           proposal=PM4_PROPOSAL_RANDOM_WALK, rw_scale=spec.scale)
+        out = dm.hmc(cfg, theta0, dtype=self._dtype)
+        self._run_info = dict(kernel="rwm", accepted=out["accepted"])
         self._last_states = out["states"]
         results = self._unpack_states(out["states"])
         return results, self.trace_fn(out["states"], out)

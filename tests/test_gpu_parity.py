@@ -305,3 +305,43 @@ def test_posterior_predictive_matches_oracle_stream(name, oracle_mod):
             np.testing.assert_allclose(got64, ref, rtol=1e-11, atol=1e-11)
         else:
             assert np.mean(got64 == ref) > 0.9999
+
+
+def test_simple_adaptation_and_random_walk_replay(oracle_mod):
+    """hmc_simple / nuts_simple (tfp SimpleStepSizeAdaptation) and rwm (RandomWalkMetropolis),
+    FP64 replay from injected randomness against the oracle."""
+    from pymc4_b200._cstructs import PM4_ADAPT_SIMPLE, PM4_PROPOSAL_RANDOM_WALK
+
+    ir, _, _ = lower_model(M.schools_pm4())
+    C, D, B, S = 8, ir.D, 20, 10
+    rng = np.random.default_rng(51)
+    momenta = rng.standard_normal((B + S, C, D))
+    uniforms = rng.random((B + S, C))
+    orc, dm = oracle_mod.Oracle(ir), _dm(ir, f64=True)
+    for mode in (PM4_EPS_POOLED, PM4_EPS_PER_CHAIN):
+        adapt = make_adapt(mode=mode, num_adaptation_steps=B, kind=PM4_ADAPT_SIMPLE, adaptation_rate=0.05)
+        cfg = make_hmc_cfg(C, S, B, step_size=0.1, num_leapfrog_steps=3, seed=3, adapt=adapt)
+        ref = orc.hmc(cfg, np.zeros(D), dtype=np.float64, momenta=momenta, uniforms=uniforms)
+        out = dm.hmc(cfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta, uniforms=uniforms)
+        assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+        np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-9)
+        np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-12)
+        assert len(np.unique(ref["step_size"])) == (1 if mode == PM4_EPS_POOLED else len(np.unique(ref["step_size"])))
+        # the step size moved by whole powers of (1 + rate)
+        k = np.log(ref["step_size"] / 0.1) / np.log(1.05)
+        np.testing.assert_allclose(k, np.round(k), atol=1e-9)
+        ncfg = make_nuts_cfg(C, S, B, step_size=0.1, seed=3, adapt=adapt)
+        nref = orc.nuts(ncfg, np.zeros(D), dtype=np.float64, momenta=momenta)
+        nout = dm.nuts(ncfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta)
+        for key in ("leapfrogs", "depth", "diverging"):
+            assert np.array_equal(nout[key].cpu().numpy(), nref[key]), key
+        np.testing.assert_allclose(nout["step_size"].cpu().numpy(), nref["step_size"], rtol=1e-12)
+    # random-walk Metropolis: `momenta` injects the perturbations
+    cfg = make_hmc_cfg(C, S, B, step_size=1.0, num_leapfrog_steps=0, seed=3, adapt=make_adapt(enabled=False),
+                       proposal=PM4_PROPOSAL_RANDOM_WALK, rw_scale=0.3)
+    ref = orc.hmc(cfg, np.zeros(D), dtype=np.float64, momenta=momenta, uniforms=uniforms)
+    out = dm.hmc(cfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta, uniforms=uniforms, want_traj=True)
+    assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"]) and 0 < ref["accepted"].mean() < 1
+    np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-12)
+    np.testing.assert_allclose(out["log_accept"].cpu().numpy(), ref["log_accept"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out["traj"].cpu().numpy(), ref["traj"], atol=1e-12)

@@ -340,3 +340,32 @@ def test_posterior_predictive_draws_have_the_right_moments(oracle_mod):
         lam = np.exp(intercept)
         assert np.all(d >= 0) and np.all(d == np.round(d))
         assert abs(d.mean() / lam - 1) < 0.01 and abs(d.var() / lam - 1) < 0.03
+
+
+def test_simple_adaptation_and_random_walk_metropolis(oracle_mod):
+    """tfp SimpleStepSizeAdaptation (step *= or /= 1 + rate by the sign of accept - target) and
+    RandomWalkMetropolis (state + scale * N(0, 1), symmetric MH) as the oracle restates them."""
+    from pymc4_b200._cstructs import (PM4_ADAPT_SIMPLE, PM4_EPS_PER_CHAIN, PM4_PROPOSAL_RANDOM_WALK, make_adapt,
+                                      make_hmc_cfg)
+    from pymc4_b200.ir import lower_model
+    from tests import models as M
+
+    ir, _, _ = lower_model(M.simple_model())
+    orc = oracle_mod.Oracle(ir)
+    C, B, S = 64, 200, 400
+    cfg = make_hmc_cfg(C, S, B, step_size=0.3, num_leapfrog_steps=3, seed=2,
+                       adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B, kind=PM4_ADAPT_SIMPLE,
+                                        adaptation_rate=0.01, target_accept_prob=0.75))
+    out = orc.hmc(cfg, np.zeros(ir.D), dtype=np.float64)
+    k = np.log(out["step_size"] / 0.3) / np.log(1.01)
+    np.testing.assert_allclose(k, np.round(k), atol=1e-8)  # whole powers of (1 + rate)
+    assert np.all(np.abs(k) <= B) and np.all((np.round(k) - B) % 2 == 0)  # B moves of +-1
+    x = out["states"][..., 0]
+    assert abs(x.mean()) < 0.1 and abs(x.std() - 1) < 0.1
+    cfg = make_hmc_cfg(256, 2000, 500, step_size=1.0, num_leapfrog_steps=0, seed=4, adapt=make_adapt(enabled=False),
+                       proposal=PM4_PROPOSAL_RANDOM_WALK, rw_scale=1.0)
+    out = orc.hmc(cfg, np.zeros(ir.D), dtype=np.float64)
+    x = out["states"][..., 0]
+    assert abs(x.mean()) < 0.05 and abs(x.std() - 1) < 0.05
+    acc = out["accepted"].mean()
+    assert 0.6 < acc < 0.8  # theory for N(0,1) target with unit normal proposals: 2/pi * atan(2) = 0.705

@@ -76,12 +76,14 @@ def test_sample_shapes_unvectorized_model():
     assert trace.posterior["model/mu"].shape == (4, 10, 4) and trace.posterior["model/__log_scale"].shape == (4, 10)
 
 
-@pytest.mark.parametrize("sampler", ["nuts", "hmc"])
+@pytest.mark.parametrize("sampler", ["nuts", "hmc", "nuts_simple", "hmc_simple", "rwm"])
 def test_samplers_on_standard_normal_and_seed_determinism(sampler):
     """tests/test_compound.py:124-146: |posterior mean| < 0.1; the same seed gives the same trace."""
     kw = dict(sampler_type=sampler, num_chains=50, num_samples=300, burn_in=200, seed=5)
-    if sampler == "hmc":
+    if sampler.startswith("hmc"):
         kw.update(step_size=0.5, num_leapfrog_steps=5)
+    if sampler == "rwm":
+        kw.update(num_chains=200, num_samples=500)  # random walk: high autocorrelation
     t1 = pm.sample(M.simple_model(), **kw)
     t2 = pm.sample(M.simple_model(), **kw)
     x1, x2 = t1.posterior["simple_model/norm"], t2.posterior["simple_model/norm"]
@@ -89,7 +91,7 @@ def test_samplers_on_standard_normal_and_seed_determinism(sampler):
     assert np.array_equal(x1, x2)
     t3 = pm.sample(M.simple_model(), **dict(kw, seed=6))
     assert not np.array_equal(x1, t3.posterior["simple_model/norm"])
-    assert "mean_tree_accept" in t1.sample_stats
+    assert ("mean_accept" if sampler == "rwm" else "mean_tree_accept") in t1.sample_stats
 
 
 def test_per_part_step_sizes_like_the_radon_notebook():
