@@ -224,6 +224,13 @@ int pm4_model_ll_row(const pm4_model_t* m);
 int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, uint64_t seed,
                              void* out_dev, void* stream);
 
+/* Prior predictive: M ancestral samples of the whole model (sample_prior_predictive,
+ * /root/reference/pymc4/forward_sampling.py:26-227: the model evaluated with nothing given).
+ * x_dev [M, D]: CONSTRAINED values of the free variables (theta layout); obs_dev [M, ll_row] or NULL:
+ * draws of the observed variables (sample_from_observed). */
+int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64_t seed, void* x_dev, void* obs_dev,
+                         void* stream);
+
 /* Step-size policy (tfp DualAveragingStepSizeAdaptation) */
 #define PM4_EPS_POOLED 0    /* one scalar shared by all chains (reference default, scalar step_size) */
 #define PM4_EPS_PER_CHAIN 1 /* step_size carries a leading chain axis: independent adaptation       */

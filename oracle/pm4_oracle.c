@@ -125,6 +125,12 @@ int pm4o_posterior_predictive(const pm4_ir_t* ir, int dtype, int64_t M, int ll_r
                           : pm4o_posterior_predictive_f32(ir, M, ll_row, seed, theta, out);
 }
 
+int pm4o_prior_predictive(const pm4_ir_t* ir, int dtype, int64_t M, int ll_row, uint64_t seed, void* x_out,
+                          void* obs_out) {
+  return dtype == PM4_F64 ? pm4o_prior_predictive_f64(ir, M, ll_row, seed, x_out, obs_out)
+                          : pm4o_prior_predictive_f32(ir, M, ll_row, seed, x_out, obs_out);
+}
+
 int pm4o_deterministics(const pm4_ir_t* ir, int dtype, int64_t M, const void* theta, void* out) {
   return dtype == PM4_F64 ? pm4o_deterministics_f64(ir, M, theta, out)
                           : pm4o_deterministics_f32(ir, M, theta, out);

@@ -42,6 +42,7 @@ def lib():
         L.pm4o_deterministics.argtypes = [irp, i32, i64, vp, vp]
         L.pm4o_log_likelihood.argtypes = [irp, i32, i64, i32, vp, vp]
         L.pm4o_posterior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
+        L.pm4o_prior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
         L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 12
         L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
         L.pm4o_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
@@ -126,6 +127,15 @@ class Oracle:
         _check(lib().pm4o_posterior_predictive(self.packed.byref(), _code(dtype), flat.shape[0], self.ir.ll_row,
                                                int(seed) & (2**64 - 1), _ptr(flat), _ptr(out)), "posterior_predictive")
         return out.reshape(lead + (self.ir.ll_row,))
+
+    def prior_predictive(self, M, seed=0, dtype=np.float64):
+        """M ancestral samples of the model: (x [M, D] constrained values of the free variables,
+        obs [M, ll_row] draws of the observed variables)."""
+        x = np.empty((int(M), self.ir.D), dtype=dtype)
+        obs = np.empty((int(M), self.ir.ll_row), dtype=dtype)
+        _check(lib().pm4o_prior_predictive(self.packed.byref(), _code(dtype), int(M), self.ir.ll_row,
+                                           int(seed) & (2**64 - 1), _ptr(x), _ptr(obs)), "prior_predictive")
+        return x, obs
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None):
         C, S, D = cfg.C, cfg.num_results, self.ir.D

@@ -395,6 +395,51 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
   return PM4_OK;
 }
 
+/* Prior predictive: ancestral sampling of the whole model
+ * (/root/reference/pymc4/forward_sampling.py:26-227: evaluate_model with no values given, once per
+ * sample).  Free variables are drawn in model order from their distributions given the already
+ * drawn ones (x holds CONSTRAINED values), then the observed variables; Philox element ids:
+ * ll_row + position for free variables, row position for observed ones. */
+static int NAME(term_defines)(const pm4_ir_t* ir, const pm4_term_t* tm) {
+  if (tm->observed || tm->kind == PM4_T_POTENTIAL) return 0;
+  const pm4_op_t* o = &ir->ops[tm->op_begin + tm->value_reg];
+  return o->opcode == PM4_OP_LD_X && (o->mode == PM4_MODE_ELEM || o->mode == PM4_MODE_SCALAR);
+}
+
+int NAME(pm4o_prior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint64_t seed, REAL* x_out, REAL* obs_out) {
+  if (!ir || !x_out) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  const int D = ir->D;
+  REAL v[PM4O_MAXREG];
+  for (int64_t m = 0; m < M; ++m) {
+    REAL* x = x_out + (size_t)m * D;
+    for (int j = 0; j < D; ++j) x[j] = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < ir->n_terms; ++t) {
+        const pm4_term_t* tm = &ir->terms[t];
+        const int defines = NAME(term_defines)(ir, tm);
+        if (pass == 0 ? !defines : !(tm->observed && obs_out)) continue;
+        const pm4_op_t* vo = &ir->ops[tm->op_begin + tm->value_reg];
+        for (int i = 0; i < tm->n; ++i) {
+          NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, x, v);
+          REAL q[3] = {0, 0, 0};
+          for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+          if (pass == 0) {
+            const int pos = vo->base + (vo->mode == PM4_MODE_ELEM ? i : 0);
+            x[pos] = NAME(draw_value)(tm->kind, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
+                                      (uint32_t)(ll_row + pos), seed);
+          } else {
+            obs_out[(size_t)m * ll_row + tm->ll_offset + i] =
+                NAME(draw_value)(tm->kind, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
+                                 (uint32_t)(tm->ll_offset + i), seed);
+          }
+        }
+      }
+    }
+  }
+  return PM4_OK;
+}
+
 /* momentum for every dimension of one chain at one transition; dimension j is owned by
  * lane j%32, register j/32 of the chain's warp and four registers share one Philox call */
 static void NAME(draw_momentum)(uint64_t seed, uint32_t chain, uint32_t t, int D, REAL* p) {

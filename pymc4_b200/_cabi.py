@@ -29,7 +29,7 @@ _lib = None
 EXPORTS = [
     "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_model_set_plans",
     "pm4_logp_grad",
-    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
+    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_prior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
     "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm",
 ]
@@ -77,6 +77,7 @@ def load_library():
     L.pm4_log_likelihood.argtypes = [vp, i32, i64, vp, vp, vp]
     L.pm4_model_ll_row.argtypes = [vp]
     L.pm4_posterior_predictive.argtypes = [vp, i32, i64, vp, ctypes.c_uint64, vp, vp]
+    L.pm4_prior_predictive.argtypes = [vp, i32, i64, ctypes.c_uint64, vp, vp, vp]
     L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
     L.pm4_nuts_run.argtypes = [vp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
     L.pm4_scratch_bytes.argtypes = [vp, i32, i32, i32]
@@ -240,6 +241,18 @@ class DeviceModel:
                                                           ctypes.c_uint64(int(seed) & (2**64 - 1)), self._p(out),
                                                           self._stream()))
         return out.reshape(lead + (self.ir.ll_row,))
+
+    def prior_predictive(self, M: int, seed: int = 0, dtype=np.float32, sample_observed: bool = True):
+        """M ancestral samples: (x [M, D] constrained free variables, obs [M, ll_row] or None), device tensors."""
+        torch = self.torch
+        td = _tdtype(torch, dtype)
+        x = self.empty((int(M), self.ir.D), td)
+        obs = self.empty((int(M), self.ir.ll_row), td) if sample_observed else None
+        with torch.cuda.device(self._dev()):
+            self._check(self.lib.pm4_prior_predictive(self.handle, _code(dtype), int(M),
+                                                      ctypes.c_uint64(int(seed) & (2**64 - 1)), self._p(x),
+                                                      self._p(obs), self._stream()))
+        return x, obs
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None,
              want_states: bool = True) -> Dict[str, "object"]:

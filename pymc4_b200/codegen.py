@@ -612,6 +612,87 @@ class _ModuleGen:
         out.append("  }")
         return "\n".join(out)
 
+    # -- prior predictive ----------------------------------------------------------
+    def gen_prior(self) -> str:
+        """One WARP per sample: ancestral sampling.  Free variables are drawn in model order (lanes stride
+        over the elements of a variable; parameters read the already drawn CONSTRAINED values from the
+        sample's row ``x``), then the observed variables.  Philox element ids: LL_ROW + position for free
+        variables, row position for observed ones (oracle: pm4o_prior_predictive)."""
+        ld_x = I.OP["ld_x"]
+        out = ["  template <typename real>",
+               "  static __device__ void prior(real* __restrict__ x, real* __restrict__ obs, const pm4::ModelArgs<real>& A, "
+               "int lane, uint32_t m_lo, uint32_t m_hi, uint32_t k0, uint32_t k1) {",
+               "    auto c_blob = [&](int op) -> int { return __ldg(A.op_blob + op); }; (void)c_blob;",
+               "    auto X = [&](int j) -> real { return x[j]; }; (void)X;",
+               "    for (int j = lane; j < D; j += 32) x[j] = 0;",
+               "    __syncwarp();"]
+        op_of = {}
+        op0 = 0
+        for k, t in enumerate(self.ir.terms):
+            op_of[k] = op0
+            op0 += len(t.ops)
+
+        def emit(k, t, target):
+            base0 = op_of[k]
+            tp = _Tape(t.ops, base0, "p%d" % k)
+
+            def xread(o: I.Op, idx: str) -> str:
+                if o.mode == I.MODE_SCALAR:
+                    return "X(%d)" % o.base
+                if o.mode == I.MODE_ELEM:
+                    return "X(%d + %s)" % (o.base, idx)
+                return "X(%d + A.datai[c_blob(%d) + %s])" % (o.base, base0 + o.dst, idx)
+
+            def dread(o: I.Op, idx: str) -> str:
+                return "A.dataf[c_blob(%d) + %s]" % (base0 + o.dst, idx if o.mode == I.MODE_ELEM else "0")
+
+            n_par = I.TERM_NPARAMS[t.kind]
+            preg = list(t.param_regs[:n_par])
+            needed = set()  # only the ops the parameters depend on (the value itself is what we draw)
+            stack = list(preg)
+            while stack:
+                r = stack.pop()
+                if r in needed or r < 0:
+                    continue
+                needed.add(r)
+                o = t.ops[r]
+                if I.OP_NAME[o.opcode] not in ("ld_const", "ld_data", "ld_x", "ld_z"):
+                    stack.extend([o.a, o.b])
+            out.append("    // ---- %s term %d: %s (%s)" % ("free" if target == "x" else "observed", k, t.label, _KIND[t.kind]))
+            out.append("    {")
+            for o in t.ops:
+                if o.uniform and o.dst in needed:
+                    out.append("      const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "0", xread, dread)))
+            out.append("      const int n = __ldg(A.term_n + %d);" % k)
+            out.append("      for (int i = lane; i < n; i += 32) {")
+            for o in t.ops:
+                if not o.uniform and o.dst in needed:
+                    out.append("        const real %s = %s;" % (tp.v(o.dst), tp.fwd(o, "i", xread, dread)))
+            p0 = tp.v(preg[0]) if n_par else "(real)0"
+            p1 = tp.v(preg[1]) if n_par > 1 else "(real)0"
+            if target == "x":
+                vo = t.ops[t.value_reg]
+                pos = "%d + i" % vo.base if vo.mode == I.MODE_ELEM else "%d" % vo.base
+                out.append("        x[%s] = pm4::draw_value<real>(%d, %s, %s, m_lo, m_hi, (uint32_t)(LL_ROW + %s), k0, k1);"
+                           % (pos, t.kind, p0, p1, pos))
+            else:
+                out.append("        if (obs) obs[%d + i] = pm4::draw_value<real>(%d, %s, %s, m_lo, m_hi, (uint32_t)(%d + i), k0, k1);"
+                           % (t.ll_offset, t.kind, p0, p1, t.ll_offset))
+            out.append("      }")
+            out.append("      __syncwarp();")
+            out.append("    }")
+
+        for k, t in enumerate(self.ir.terms):
+            vo = t.ops[t.value_reg]
+            if (not t.observed and t.kind != I.TERM_KINDS["potential"] and vo.opcode == ld_x
+                    and vo.mode in (I.MODE_ELEM, I.MODE_SCALAR)):
+                emit(k, t, "x")
+        for k, t in enumerate(self.ir.terms):
+            if t.observed:
+                emit(k, t, "obs")
+        out.append("  }")
+        return "\n".join(out)
+
     def source(self) -> str:
         ir = self.ir
         name = "Model_%s" % ir.struct_hash_hex
@@ -638,6 +719,7 @@ class _ModuleGen:
             "  static constexpr int LL_ROW = %d;  // pointwise log-likelihood scalars per state" % ir.ll_row,
             self.gen_loglik(),
             self.gen_loglik(predictive=True),
+            self.gen_prior(),
             "};",
             "#define PM4_MODEL %s" % name,
             "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),

@@ -71,6 +71,7 @@ struct pm4_model {
   pm4m_dets_fn f_dets = nullptr;
   pm4m_loglik_fn f_loglik = nullptr;
   pm4m_predict_fn f_predict = nullptr;
+  pm4m_prior_fn f_prior = nullptr;
   pm4m_init_fn f_init = nullptr;
   pm4m_run_fn f_nuts = nullptr, f_hmc = nullptr;
   pm4m_da_pooled_fn f_da = nullptr;
@@ -186,6 +187,7 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
   m->f_dets = (pm4m_dets_fn)dlsym(m->module, "pm4m_dets");
   m->f_loglik = (pm4m_loglik_fn)dlsym(m->module, "pm4m_loglik");
   m->f_predict = (pm4m_predict_fn)dlsym(m->module, "pm4m_predict");
+  m->f_prior = (pm4m_prior_fn)dlsym(m->module, "pm4m_prior");
   m->f_init = (pm4m_init_fn)dlsym(m->module, "pm4m_init");
   m->f_nuts = (pm4m_run_fn)dlsym(m->module, "pm4m_nuts");
   m->f_hmc = (pm4m_run_fn)dlsym(m->module, "pm4m_hmc");
@@ -194,7 +196,7 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
   m->f_scratch = (pm4m_scratch_bytes_fn)dlsym(m->module, "pm4m_scratch_bytes");
   m->f_order = (pm4m_lpt_order_fn)dlsym(m->module, "pm4m_lpt_order");
   if (!f_info || !m->f_logp || !m->f_dets || !m->f_init || !m->f_nuts || !m->f_hmc || !m->f_da || !m->f_eps ||
-      !m->f_scratch || !m->f_order || !m->f_loglik || !m->f_predict) {
+      !m->f_scratch || !m->f_order || !m->f_loglik || !m->f_predict || !m->f_prior) {
     int rc = fail(PM4_ENOMOD, "kernel module %s lacks a required entry point", module_path);
     pm4_model_destroy(m);
     return rc;
@@ -329,6 +331,19 @@ extern "C" int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, co
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_predict(dtype, &a, M, theta_dev, out_dev, seed, stream), "posterior_predictive");
+  return PM4_OK;
+}
+
+extern "C" int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64_t seed, void* x_dev, void* obs_dev,
+                                    void* stream) {
+  if (!m || M < 0) return fail(PM4_EINVAL, "pm4_prior_predictive: bad argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (M == 0) return PM4_OK;
+  if (!x_dev) return fail(PM4_EINVAL, "pm4_prior_predictive: null buffer");
+  CU(cudaSetDevice(m->device));
+  pm4_mod_args_t a = m->args(dtype);
+  MOD(m->f_prior(dtype, &a, M, x_dev, obs_dev, seed, stream), "prior_predictive");
   return PM4_OK;
 }
 

@@ -244,6 +244,17 @@ __global__ void __launch_bounds__(256) predict_kernel(ModelArgs<real> A, int64_t
     M::template predict<real>(theta + m * M::D, out + m * M::LL_ROW, A, lane, (uint32_t)m, (uint32_t)((uint64_t)m >> 32), k0, k1);
 }
 
+// prior predictive: one ancestral sample of the whole model per warp
+template <class M, typename real>
+__global__ void __launch_bounds__(256) prior_kernel(ModelArgs<real> A, int64_t n_samples, real* __restrict__ x_out,
+                                                    real* __restrict__ obs_out, uint32_t k0, uint32_t k1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); m < n_samples; m += warps)
+    M::template prior<real>(x_out + m * M::D, obs_out ? obs_out + m * M::LL_ROW : nullptr, A, lane, (uint32_t)m,
+                            (uint32_t)((uint64_t)m >> 32), k0, k1);
+}
+
 // ------------------------------------------------------------------------------------------
 // run-time parameters shared by the HMC and NUTS kernels
 // ------------------------------------------------------------------------------------------
@@ -1123,6 +1134,16 @@ int mod_predict(const pm4_mod_args_t* A, int64_t n, const void* theta, void* out
   predict_kernel<M, real><<<grid, 256, 0, st>>>(ma, n, (const real*)theta, (real*)out, (uint32_t)seed, (uint32_t)(seed >> 32));
   return (int)cudaGetLastError();
 }
+template <typename real>
+int mod_prior(const pm4_mod_args_t* A, int64_t n, void* x_out, void* obs_out, uint64_t seed, cudaStream_t st) {
+  using M = PM4_MODEL;
+  if (n == 0) return 0;
+  ModelArgs<real> ma = make_model_args<real>(*A);
+  const int64_t blocks = (n + 7) / 8;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+  prior_kernel<M, real><<<grid, 256, 0, st>>>(ma, n, (real*)x_out, (real*)obs_out, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (int)cudaGetLastError();
+}
 template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0, double eps0, cudaStream_t st) {
   using M = PM4_MODEL;
   RunParams<real> p = make_run_params<real>(*r);
@@ -1178,6 +1199,11 @@ extern "C" int pm4m_predict(int dtype, const pm4_mod_args_t* A, int64_t n, const
                             void* stream) {
   PM4_BY_DTYPE(pm4::mod_predict<float>(A, n, theta, out, seed, (cudaStream_t)stream),
                PM4_F64_CALL(pm4::mod_predict<double>(A, n, theta, out, seed, (cudaStream_t)stream)));
+}
+extern "C" int pm4m_prior(int dtype, const pm4_mod_args_t* A, int64_t n, void* x_out, void* obs_out, uint64_t seed,
+                          void* stream) {
+  PM4_BY_DTYPE(pm4::mod_prior<float>(A, n, x_out, obs_out, seed, (cudaStream_t)stream),
+               PM4_F64_CALL(pm4::mod_prior<double>(A, n, x_out, obs_out, seed, (cudaStream_t)stream)));
 }
 extern "C" int pm4m_init(int dtype, const pm4_mod_run_t* r, const void* theta0, double eps0, void* stream) {
   PM4_BY_DTYPE(pm4::mod_init<float>(r, theta0, eps0, (cudaStream_t)stream),

@@ -1,4 +1,4 @@
-"""Posterior predictive sampling on the device.
+"""Prior and posterior predictive sampling on the device.
 
 Reference: ``sample_posterior_predictive`` (/root/reference/pymc4/forward_sampling.py:230-427) re-evaluates
 the model once per posterior draw (``tf.vectorized_map`` over the flattened chain x draw axes) with the
@@ -8,9 +8,9 @@ posterior is packed into states ``[chain, draw, D]`` and one kernel (generated p
 HalfNormal / HalfCauchy / Bernoulli / Poisson with a counter-based Philox stream keyed by
 (state, element), so the same ``seed`` reproduces the same draws.
 
-Not built (SURVEY section 8(f)1 is only half done): ``sample_prior_predictive`` and posterior predictive
-draws of variables other than the observed ones (free variables are taken from the trace,
-deterministics are already in it).
+``sample_prior_predictive`` (forward_sampling.py:26-227) is ancestral sampling of the whole model, one warp
+per sample (``Model::prior``).  Not built: posterior predictive draws of variables other than the observed
+ones (free variables are taken from the trace, deterministics are already in it).
 """
 from __future__ import annotations
 
@@ -26,10 +26,85 @@ from .mcmc.utils import InferenceData, trace_to_arviz
 __all__ = ["sample_posterior_predictive", "sample_prior_predictive"]
 
 
-def sample_prior_predictive(*args, **kwargs):
-    raise NotImplementedError(
-        "sample_prior_predictive is listed under 'next' in SURVEY section 8(f) and is not built yet"
-    )
+def sample_prior_predictive(
+    model: Model,
+    sample_shape: Union[int, tuple] = 1000,
+    sample_from_observed: bool = True,
+    var_names: Optional[Union[str, List[str]]] = None,
+    state=None,
+    use_auto_batching: bool = True,
+    seed: Optional[int] = None,
+    dtype="float32",
+    device: Optional[int] = None,
+) -> InferenceData:
+    """Draw ``sample_shape`` ancestral samples of the model (reference forward_sampling.py:26-227): every
+    free variable from its distribution given the ones drawn before it, the deterministics, and -- with
+    ``sample_from_observed`` -- the observed variables.  Returns an ``InferenceData`` with a
+    ``prior_predictive`` group ``{name: [1, *sample_shape, *core]}`` keyed by the untransformed names.
+
+    Limitation: observed values enter the lowered model as constants, so a free variable that depends on
+    an observed one still sees the observed data when ``sample_from_observed`` is set."""
+    from .mcmc.samplers import _get_device_model
+
+    if not isinstance(model, Model):
+        raise TypeError("`sample_prior_predictive` only supports `pymc4.Model` objects, but you've passed `{}`"
+                        .format(type(model)))
+    if state is not None:
+        raise NotImplementedError("sample_prior_predictive(state=...) is not supported")
+    if isinstance(sample_shape, int):
+        sample_shape = (sample_shape,)
+    sample_shape = tuple(int(s) for s in sample_shape)
+    if isinstance(var_names, str):
+        var_names = [var_names]
+    ir, _, _ = irmod.lower_model(model)
+    obs_terms = {t.label: t for t in ir.terms if t.observed}
+    dist_names = [rv.untransformed_name or rv.name for rv in ir.rvs]
+    if sample_from_observed:
+        dist_names = dist_names + list(obs_terms)
+    back_transformed = {rv.untransformed_name for rv in ir.rvs if rv.untransformed_name}
+    # the model's own return value is traced under the bare model name: like trace_to_arviz, keep scoped names only
+    det_names = [d.name for d in ir.dets if d.name not in back_transformed and "/" in d.name]
+    traced_observeds = set()
+    if var_names is None:
+        var_names = dist_names + det_names
+    else:
+        traced_observeds = {v for v in var_names if v in obs_terms}
+    if not set(var_names) <= (set(dist_names + det_names) | traced_observeds):
+        raise ValueError("Some of the supplied var_names are not defined in the supplied model {}.\n"
+                         "List of unknown var_names: {}".format(model, sorted(set(var_names) - set(dist_names + det_names))))
+    dm = _get_device_model(ir, np.dtype(dtype), device)
+    torch = dm.torch
+    M = int(np.prod(sample_shape)) if sample_shape else 1
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    x, obs = dm.prior_predictive(M, seed=seed, dtype=np.dtype(dtype),
+                                 sample_observed=sample_from_observed)
+    output: Dict[str, Any] = {}
+    lead = sample_shape
+    for rv in ir.rvs:
+        name = rv.untransformed_name or rv.name
+        if name in var_names:
+            output[name] = x[:, rv.offset: rv.offset + rv.size].reshape(lead + rv.shape).cpu().numpy()
+    if any(n in var_names for n in det_names):
+        theta = x.clone()  # deterministics are tapes over the unconstrained state: undo the transforms
+        for rv in ir.rvs:
+            sl = slice(rv.offset, rv.offset + rv.size)
+            if rv.transform == irmod.TR_EXP:
+                theta[:, sl] = torch.log((x[:, sl] - rv.shift) / rv.scale)
+            elif rv.transform == irmod.TR_SIGMOID:
+                u = (x[:, sl] - rv.shift) / rv.scale
+                theta[:, sl] = torch.log(u) - torch.log1p(-u)
+        dets = dm.deterministics(theta, dtype=np.dtype(dtype)).cpu().numpy()
+        for d in ir.dets:
+            if d.name in var_names and d.name in det_names:
+                output[d.name] = dets[:, d.out_offset: d.out_offset + d.n].reshape(lead + tuple(d.shape))
+    for name, t in obs_terms.items():
+        if name in var_names:
+            if obs is not None:
+                output[name] = obs[:, t.ll_offset: t.ll_offset + t.n].reshape(lead + tuple(t.shape)).cpu().numpy()
+            else:  # explicitly requested but not resampled: the observed data itself
+                output[name] = np.broadcast_to(np.asarray(ir.observed[name]), lead + np.shape(ir.observed[name])).copy()
+    return trace_to_arviz(prior_predictive=output)
 
 
 def sample_posterior_predictive(

@@ -369,3 +369,33 @@ def test_simple_adaptation_and_random_walk_metropolis(oracle_mod):
     assert abs(x.mean()) < 0.05 and abs(x.std() - 1) < 0.05
     acc = out["accepted"].mean()
     assert 0.6 < acc < 0.8  # theory for N(0,1) target with unit normal proposals: 2/pi * atan(2) = 0.705
+
+
+def test_prior_predictive_ancestral_sampling(oracle_mod):
+    """forward_sampling.py:26-227 restated: free variables in model order given the ones before, then the
+    observed variables -- eight schools (eta ~ N(0,1), mu ~ N(1,10), tau ~ HalfNormal(2), obs ~ N(mu + tau eta, sigma))
+    and the radon hierarchy (alpha[g] ~ N(mu_alpha, sigma_alpha))."""
+    from pymc4_b200.ir import lower_model
+    from tests import models as M
+
+    ir, _, _ = lower_model(M.schools_pm4())
+    x, obs = oracle_mod.Oracle(ir).prior_predictive(40000, seed=1)
+    eta, mu, tau = x[:, :8], x[:, 8], x[:, 9]  # constrained values: tau itself, not log tau
+    assert np.max(np.abs(eta.mean(0))) < 0.03 and np.max(np.abs(eta.std(0) - 1)) < 0.03
+    assert abs(mu.mean() - 1) < 0.2 and abs(mu.std() / 10 - 1) < 0.03
+    assert tau.min() > 0 and abs(tau.mean() / (2 * np.sqrt(2 / np.pi)) - 1) < 0.03
+    want_var = 100 + 4 + M.SIGMA8 ** 2  # var(mu) + E[tau^2] var(eta) + sigma^2
+    assert np.max(np.abs(obs.var(0) / want_var - 1)) < 0.06
+    # conditional structure: obs - (mu + tau eta) is N(0, sigma)
+    z = (obs - (mu[:, None] + tau[:, None] * eta)) / M.SIGMA8
+    assert np.max(np.abs(z.std(0) - 1)) < 0.03 and np.max(np.abs(z.mean(0))) < 0.03
+
+    idx, xx, y, g = M.radon_synthetic(120, 5)
+    ir, _, _ = lower_model(M.hierarchical_model(idx, xx, y, g))
+    x, obs = oracle_mod.Oracle(ir).prior_predictive(20000, seed=2)
+    p = ir.split_theta(x)  # slices of the CONSTRAINED vector, named after the sampled (transformed) names
+    mu_a, sig_a, alpha = p["hierarchical_model/mu_alpha"], p["hierarchical_model/__log_sigma_alpha"], p["hierarchical_model/alpha"]
+    assert np.all(sig_a > 0) and abs(np.median(sig_a) - 1) < 0.05  # HalfCauchy(1): median 1
+    z = (alpha - mu_a[:, None]) / sig_a[:, None]
+    assert np.max(np.abs(z.mean(0))) < 0.03 and np.max(np.abs(z.std(0) - 1)) < 0.03
+    assert obs.shape == (20000, 120) and np.all(np.isfinite(obs))

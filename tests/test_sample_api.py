@@ -163,3 +163,27 @@ def test_sample_posterior_predictive():
         pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=["schools_pm4/nope"])
     with pytest.raises(ValueError):
         pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=[])
+
+
+def test_sample_prior_predictive():
+    """pm.sample_prior_predictive(model, sample_shape): a prior_predictive group [1, *sample_shape, *core] keyed by
+    the untransformed names, deterministics included (reference forward_sampling.py:26-227 and its doctest)."""
+    out = pm.sample_prior_predictive(M.schools_pm4(), sample_shape=(50, 40), seed=3)
+    pp = out.prior_predictive
+    assert out.groups() == ["prior_predictive"]
+    assert sorted(pp) == ["schools_pm4/eta", "schools_pm4/mu", "schools_pm4/obs", "schools_pm4/tau"]
+    assert pp["schools_pm4/eta"].shape == (1, 50, 40, 8) and pp["schools_pm4/tau"].shape == (1, 50, 40)
+    assert pp["schools_pm4/tau"].min() > 0 and abs(pp["schools_pm4/eta"].std() - 1) < 0.05
+    z = (pp["schools_pm4/obs"] - (pp["schools_pm4/mu"][..., None] + pp["schools_pm4/tau"][..., None] * pp["schools_pm4/eta"])) / M.SIGMA8
+    assert abs(z.std() - 1) < 0.05
+    again = pm.sample_prior_predictive(M.schools_pm4(), sample_shape=(50, 40), seed=3).prior_predictive
+    assert all(np.array_equal(again[k], pp[k]) for k in pp)
+    only = pm.sample_prior_predictive(M.schools_pm4(), sample_shape=7, sample_from_observed=False).prior_predictive
+    assert sorted(only) == ["schools_pm4/eta", "schools_pm4/mu", "schools_pm4/tau"] and only["schools_pm4/mu"].shape == (1, 7)
+    det = pm.sample_prior_predictive(M.outer_model(), sample_shape=100, seed=1).prior_predictive
+    assert {"outer_model/cond", "outer_model/dcond", "outer_model/nested_model/x", "outer_model/nested_model/dx",
+            "outer_model/ddx"} <= set(det)
+    np.testing.assert_allclose(det["outer_model/dcond"], 2 * det["outer_model/cond"], rtol=1e-5)
+    np.testing.assert_allclose(det["outer_model/nested_model/dx"], det["outer_model/nested_model/x"] + 1, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        pm.sample_prior_predictive(M.schools_pm4(), var_names=["schools_pm4/nope"])
