@@ -429,22 +429,48 @@ class _ModuleGen:
                 E("const real %sv = c.xs[%d + tgt]; real %sa = 0;" % (nm, by_dst[dst].base, nm), 4)
             E("const %s* rp = %s_pr + sl.z * %d;" % (rec_t, tag, TL), 4)
             E("int i = 0;", 4)
-            E("#pragma unroll 1", 4)
-            E("for (; i + 4 <= len; i += 4) {   // per-lane trip count: lanes with shorter chunks drop out", 4)
-            E("%s %s_rq[4];" % (rec_t, tag), 5)
-            E("#pragma unroll", 5)
-            E("for (int u = 0; u < 4; ++u) %s_rq[u] = rp[(i + u) * %d];" % (tag, TL), 5)
-            E("#pragma unroll", 5)
-            E("for (int u = 0; u < 4; ++u) {", 5)
-            E("const %s %s_rec = %s_rq[u]; (void)%s_rec;" % (rec_t, tag, tag, tag), 5)
-            self.lines.extend(loop)
-            E("}", 5)
-            E("}", 4)
-            E("#pragma unroll 1", 4)
-            E("for (; i < len; ++i) {", 4)
-            E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
-            self.lines.extend(loop)
-            E("}", 4)
+            if self.ir.streamed:
+                # records stream from L2 (pools too large to stage): keep the NEXT four rows in flight while
+                # the current four are consumed (rows up to the slice's longest chunk exist, zero padded)
+                E("%s %s_nx[4];" % (rec_t, tag), 4)
+                E("#pragma unroll", 4)
+                E("for (int u = 0; u < 4; ++u) %s_nx[u] = rp[(u < sl.y ? u : 0) * %d];" % (tag, TL), 4)
+                E("#pragma unroll 1", 4)
+                E("for (; i + 4 <= len; i += 4) {   // per-lane trip count: lanes with shorter chunks drop out", 4)
+                E("%s %s_rq[4];" % (rec_t, tag), 5)
+                E("#pragma unroll", 5)
+                E("for (int u = 0; u < 4; ++u) { %s_rq[u] = %s_nx[u]; %s_nx[u] = rp[(i + 4 + u < sl.y ? i + 4 + u : 0) * %d]; }"
+                  % (tag, tag, tag, TL), 5)
+                E("#pragma unroll", 5)
+                E("for (int u = 0; u < 4; ++u) {", 5)
+                E("const %s %s_rec = %s_rq[u]; (void)%s_rec;" % (rec_t, tag, tag, tag), 5)
+                self.lines.extend(loop)
+                E("}", 5)
+                E("}", 4)
+                E("#pragma unroll", 4)
+                E("for (int u = 0; u < 3; ++u) {   // the last rows of the chunk are already in registers", 4)
+                E("if (i + u < len) {", 5)
+                E("const %s %s_rec = %s_nx[u]; (void)%s_rec;" % (rec_t, tag, tag, tag), 5)
+                self.lines.extend(loop)
+                E("}", 5)
+                E("}", 4)
+            else:
+                E("#pragma unroll 1", 4)
+                E("for (; i + 4 <= len; i += 4) {   // per-lane trip count: lanes with shorter chunks drop out", 4)
+                E("%s %s_rq[4];" % (rec_t, tag), 5)
+                E("#pragma unroll", 5)
+                E("for (int u = 0; u < 4; ++u) %s_rq[u] = rp[(i + u) * %d];" % (tag, TL), 5)
+                E("#pragma unroll", 5)
+                E("for (int u = 0; u < 4; ++u) {", 5)
+                E("const %s %s_rec = %s_rq[u]; (void)%s_rec;" % (rec_t, tag, tag, tag), 5)
+                self.lines.extend(loop)
+                E("}", 5)
+                E("}", 4)
+                E("#pragma unroll 1", 4)
+                E("for (; i < len; ++i) {", 4)
+                E("const %s %s_rec = rp[i * %d]; (void)%s_rec;" % (rec_t, tag, TL, tag), 5)
+                self.lines.extend(loop)
+                E("}", 4)
             E("if (st.x >= 0) {  // park the chunk's adjoint sums where the owner of the element collects them", 4)
             fields = ["x", "y", "z", "w"]
             for j, (dst, nm) in enumerate(gather_names.items()):

@@ -171,12 +171,18 @@ class ModelIR:
         return sum(d.n for d in self.dets)
 
     @property
+    def streamed(self) -> bool:
+        """Plan pools too large to stage in shared memory (the device reads them from L2): the generated row
+        loops prefetch."""
+        return self.planf.size * 4 + self.plani.size * 4 > 96 * 1024
+
+    @property
     def ll_row(self) -> int:
         return sum(t.n for t in self.terms if t.observed)
 
     # -- structural hash: everything the generated code depends on ---------
     def struct_key(self) -> bytes:
-        h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<ii", self.D, self.team_warps)]
+        h = [b"pm4ir-v%d" % ABI_VERSION, struct.pack("<ii?", self.D, self.team_warps, self.streamed)]
         for rv in self.rvs:
             h.append(struct.pack("<iiidd", rv.offset, rv.size, rv.transform, rv.shift, rv.scale))
 
