@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--max-tree-depth", type=int, default=10)
     ap.add_argument("--eps-mode", default="pooled", choices=["per-chain", "pooled"],
                     help="per-chain: step_size with a leading chain axis (independent dual averaging, no coupling); "
                          "pooled: scalar step_size, the reference default (one epsilon adapted from the mean "
@@ -103,7 +104,7 @@ def workload_config(args, n_gpus):
                      ("pooled dual averaging from %.3g (scalar step_size, reference default; ONE epsilon for the chains "
                       "of all ranks: per-transition exchange over NVLink peer memory inside the adaptation kernel)"
                       % args.step_size),
-        "max_tree_depth": 10,
+        "max_tree_depth": args.max_tree_depth,
         "parallelism": ("chains sharded, %d per GPU; " % args.chains)
                        + ("no data-path collective" if (n_gpus == 1 or args.eps_mode == "per-chain") else
                           "one 16-byte all-reduce per burn-in transition (pooled step size), none afterwards"),
@@ -300,6 +301,7 @@ def run_b200(args):
 
     def cfg_for(step):
         return make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + step, adapt=adapt,
+                             max_tree_depth=args.max_tree_depth,
                              warps_per_block=args.warps_per_block, chain_offset=rank * C)
 
     theta0 = torch.zeros((C, ir.D), dtype=torch.float32, device=dev)

@@ -1,6 +1,8 @@
-mkdir -p gpurun_out
-timeout 600 python bench.py --workload radon100k --eps-mode per-chain --chains 592 --burn-in 20 --draws 10 --step-size 0.001 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/t14_big.json 2> gpurun_out/t14_big.err; echo rc=$?
-python -c "
-import json
-d=json.loads(open('gpurun_out/t14_big.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['steps_detail'])"
-timeout 600 python -m pytest tests -m gpu -q -x -k "large" 2>&1 | tail -3
+for m in 512 576 640; do
+echo "MAXT=$m depth 7"
+PM4_MAXT=$m python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --max-tree-depth 7 | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d=json.loads(l); print(d['value'], d['ms_per_step'])
+    except Exception: pass"
+done
