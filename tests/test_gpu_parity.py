@@ -366,3 +366,41 @@ def test_prior_predictive_matches_oracle_stream(name, oracle_mod):
     elif ir.ll_row:
         rows = np.all(np.abs(xr) < 50, axis=1)
         assert np.max(np.abs(ob - obr)[rows] / np.maximum(np.abs(obr[rows]), 1.0)) < 1e-3
+
+
+def test_full_size_invariants_radon_4096_chains():
+    """BASELINE configs[1] at full size (919 observations / 85 counties, 4096 chains) through size-independent
+    properties: the log-density the sampler tracks equals an independent evaluation of the traced states, tree
+    sizes are consistent with tree depths, the run is reproducible, and a sharded run equals the unsharded one."""
+    import torch
+
+    ir, _, _ = lower_model(M.radon_model(real=False))
+    dm = _dm(ir)
+    C, B, S = 4096, 30, 8
+    adapt = make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B)
+    cfg = make_nuts_cfg(C, S, B, step_size=0.1, seed=123, adapt=adapt)
+    out = dm.nuts(cfg, np.zeros((C, ir.D), np.float32), dtype=np.float32)
+    states, lp = out["states"], out["lp"]
+    assert tuple(states.shape) == (S, C, ir.D) and bool(torch.isfinite(states).all())
+    lp2, _ = dm.logp_grad(states.reshape(-1, ir.D), dtype=np.float32, want_grad=False)
+    rel = (lp2.reshape(S, C) - lp).abs() / lp.abs().clamp_min(1.0)
+    assert float(rel.max()) < 1e-5
+    leaps, depth = out["leapfrogs"], out["depth"]
+    assert int(leaps.min()) >= 1 and int(depth.max()) <= 10
+    assert bool((leaps <= (2 ** depth.long() - 1)).all()) and bool((leaps >= 2 ** (depth.long() - 1)).all())
+    eps = out["step_size"]
+    assert bool((eps == eps[0]).all()) and 1e-3 < float(eps[0]) < 1.0  # one pooled epsilon
+    assert 0.3 < float(torch.exp(out["log_accept"]).mean()) <= 1.0
+    # same seed, same trace (scheduling order does not enter any result)
+    again = dm.nuts(cfg, np.zeros((C, ir.D), np.float32), dtype=np.float32)
+    assert torch.equal(again["states"], states) and torch.equal(again["leapfrogs"], leaps)
+    # per-chain step sizes: chains are independent, so a shard of the chains reproduces its slice exactly
+    adapt_pc = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)
+    full = dm.nuts(make_nuts_cfg(C, S, B, step_size=0.1, seed=7, adapt=adapt_pc), np.zeros((C, ir.D), np.float32),
+                   dtype=np.float32)
+    n, off = 1000, 2048
+    shard = dm.nuts(make_nuts_cfg(n, S, B, step_size=0.1, seed=7, adapt=adapt_pc, chain_offset=off),
+                    np.zeros((n, ir.D), np.float32), dtype=np.float32)
+    assert torch.equal(shard["states"], full["states"][:, off:off + n])
+    assert torch.equal(shard["leapfrogs"], full["leapfrogs"][:, off:off + n])
+    assert int(full["total_leapfrogs"].sum()) > C * (B + S)
