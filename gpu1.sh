@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -q -x -k "full_size" 2>&1 | tail -15 | cut -c1-300
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 | cut -c1-500

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM4_ABI_VERSION 4
+#define PM4_ABI_VERSION 5
 
 /* error codes */
 #define PM4_OK 0
@@ -73,6 +73,9 @@ typedef struct pm4_rv {
 #define PM4_T_HALFCAUCHY 3 /* value, scale  (loc = 0)                 */
 #define PM4_T_BERNOULLI 4  /* value, probs                            */
 #define PM4_T_POISSON 5    /* value, rate                             */
+#define PM4_T_BERNOULLI_LOGIT_GLM 6 /* Bernoulli(probs = sigmoid(X beta)) observed: a dense term with no tape;
+                                       X [n, glm_p] row-major at dataf[glm_x], y at dataf[glm_y], beta = x[glm_base ..]
+                                       (evaluated for all chains at once on the tensor cores, csrc/pm4_glm.cu) */
 
 typedef struct pm4_term {
   int32_t kind;        /* PM4_T_*                                       */
@@ -85,6 +88,10 @@ typedef struct pm4_term {
   int32_t plan;        /* index into plans, or -1                       */
   int32_t observed;    /* 1: the term is the density of an observed variable (pointwise log-likelihood) */
   int32_t ll_offset;   /* position of element 0 inside one state's log-likelihood row (observed terms)  */
+  int32_t glm_base;    /* PM4_T_BERNOULLI_LOGIT_GLM: theta offset of beta[0]                            */
+  int32_t glm_p;       /*   number of covariates                                                        */
+  int64_t glm_x;       /*   dataf offset of X [n, glm_p]                                                */
+  int64_t glm_y;       /*   dataf offset of y [n]                                                       */
 } pm4_term_t;
 
 /* Device execution plan of a term that gathers from free variables: its elements regrouped by
@@ -330,6 +337,22 @@ int pm4_comm_create(int device, int rank, int world, pm4_comm_t** out, unsigned 
 int pm4_comm_connect(pm4_comm_t* comm, const unsigned char* handles /* [world][PM4_IPC_HANDLE_BYTES] */);
 int pm4_comm_destroy(pm4_comm_t* comm);
 int pm4_model_attach_comm(pm4_model_t* m, pm4_comm_t* comm /* NULL detaches */);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense Bernoulli-logit likelihood (PM4_T_BERNOULLI_LOGIT_GLM) for C chains at once, the building block
+ * pm4_logp_grad and pm4_hmc_run call for such terms (csrc/pm4_glm.cu): two GEMMs on the tcgen05
+ * tensor cores in 3xTF32, eta = X beta with the Bernoulli epilogue and g = X^T (y - sigmoid(eta)).
+ *   X [n, P] row-major, Xt [P, ldxt] its transpose (ldxt >= n, multiple of 4), y [n] as float,
+ *   theta [C, ldt] with beta at columns base .. base+P-1; adds into lp [C] and grad [C, ldg] (NULL: skip).
+ *   P must be a multiple of 4, at most 104.  work: pm4_glm_work_bytes(n, P, C) bytes of device memory.
+ *   *error_dev (device int, zeroed by the caller) is set when a tensor-core step timed out.
+ * pm4_glm_gemm_tile: one 128 x 128 tile C = A B^T of the same MMA path (kernel-level test). */
+int64_t pm4_glm_work_bytes(int n, int P, int C);
+int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P, const float* theta,
+                      int ldt, int base, int C, float* lp, float* grad, int ldg, void* work, int* error_dev,
+                      void* stream);
+int pm4_glm_gemm_tile(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int K, int passes,
+                      void* stream);
 
 /* Bytes of device scratch pm4_nuts_run / pm4_hmc_run allocate internally for C chains. */
 int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth);

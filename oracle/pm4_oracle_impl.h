@@ -179,6 +179,19 @@ static void NAME(constrain)(const pm4_ir_t* ir, const REAL* theta, REAL* x) {
   }
 }
 
+/* element i of a dense Bernoulli-logit term: eta = X[i, :] . beta, p = sigmoid(eta), returns log_prob(y_i) */
+static REAL NAME(glm_elem)(const pm4_ir_t* ir, const pm4_term_t* tm, const REAL* x, int i, REAL* eta_out, REAL* p_out) {
+  REAL eta = 0;
+  for (int q = 0; q < tm->glm_p; ++q) eta += (REAL)ir->dataf[tm->glm_x + (int64_t)i * tm->glm_p + q] * x[tm->glm_base + q];
+  const REAL p = NAME(sigmoid)(eta);
+  const REAL yv = (REAL)ir->dataf[tm->glm_y + i];
+  REAL dx, dq[3];
+  const REAL q1[3] = {p, 0, 0};
+  *eta_out = eta;
+  *p_out = p;
+  return NAME(lpdf)(PM4_T_BERNOULLI, yv, q1, &dx, dq);
+}
+
 /* joint log-density and gradient in unconstrained space for ONE chain */
 static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta, REAL* grad) {
   const int D = ir->D;
@@ -190,6 +203,20 @@ static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* the
   for (int t = 0; t < ir->n_terms; ++t) {
     const pm4_term_t* tm = &ir->terms[t];
     REAL term_sum = 0;
+    if (tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) {
+      /* tfd.Bernoulli(probs=sigmoid(X beta)).log_prob(y), summed: xlogy(y, p) + xlog1py(1 - y, -p) */
+      for (int i = 0; i < tm->n; ++i) {
+        REAL eta, p;
+        term_sum += NAME(glm_elem)(ir, tm, x, i, &eta, &p);
+        if (grad) {
+          const REAL yv = (REAL)ir->dataf[tm->glm_y + i];
+          const REAL r = yv - p; /* d/d eta of the Bernoulli-logit log-likelihood */
+          for (int q = 0; q < tm->glm_p; ++q) gx[tm->glm_base + q] += r * (REAL)ir->dataf[tm->glm_x + (int64_t)i * tm->glm_p + q];
+        }
+      }
+      lp += term_sum;
+      continue;
+    }
     for (int i = 0; i < tm->n; ++i) {
       NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, theta, v);
       REAL q[3] = {0, 0, 0}, dq[3], dx;
@@ -231,6 +258,11 @@ static void NAME(loglik1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta,
     const pm4_term_t* tm = &ir->terms[t];
     if (!tm->observed) continue;
     for (int i = 0; i < tm->n; ++i) {
+      if (tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) {
+        REAL eta, p;
+        out[tm->ll_offset + i] = NAME(glm_elem)(ir, tm, x, i, &eta, &p);
+        continue;
+      }
       NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, theta, v);
       REAL q[3] = {0, 0, 0}, dq[3], dx;
       for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
@@ -382,11 +414,18 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
       const pm4_term_t* tm = &ir->terms[t];
       if (!tm->observed) continue;
       for (int i = 0; i < tm->n; ++i) {
-        NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, th, v);
         REAL q[3] = {0, 0, 0};
-        for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+        int kind = tm->kind;
+        if (kind == PM4_T_BERNOULLI_LOGIT_GLM) {
+          REAL eta;
+          NAME(glm_elem)(ir, tm, x, i, &eta, &q[0]);
+          kind = PM4_T_BERNOULLI;
+        } else {
+          NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, th, v);
+          for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
+        }
         out[(size_t)m * ll_row + tm->ll_offset + i] =
-            NAME(draw_value)(tm->kind, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
+            NAME(draw_value)(kind, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
                              (uint32_t)(tm->ll_offset + i), seed);
       }
     }
@@ -401,7 +440,7 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
  * drawn ones (x holds CONSTRAINED values), then the observed variables; Philox element ids:
  * ll_row + position for free variables, row position for observed ones. */
 static int NAME(term_defines)(const pm4_ir_t* ir, const pm4_term_t* tm) {
-  if (tm->observed || tm->kind == PM4_T_POTENTIAL) return 0;
+  if (tm->observed || tm->kind == PM4_T_POTENTIAL || tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) return 0;
   const pm4_op_t* o = &ir->ops[tm->op_begin + tm->value_reg];
   return o->opcode == PM4_OP_LD_X && (o->mode == PM4_MODE_ELEM || o->mode == PM4_MODE_SCALAR);
 }
@@ -419,10 +458,18 @@ int NAME(pm4o_prior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint6
         const pm4_term_t* tm = &ir->terms[t];
         const int defines = NAME(term_defines)(ir, tm);
         if (pass == 0 ? !defines : !(tm->observed && obs_out)) continue;
-        const pm4_op_t* vo = &ir->ops[tm->op_begin + tm->value_reg];
+        const pm4_op_t* vo = &ir->ops[tm->op_begin + (tm->value_reg >= 0 ? tm->value_reg : 0)];
         for (int i = 0; i < tm->n; ++i) {
-          NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, x, v);
           REAL q[3] = {0, 0, 0};
+          if (tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) {
+            REAL eta;
+            NAME(glm_elem)(ir, tm, x, i, &eta, &q[0]);
+            obs_out[(size_t)m * ll_row + tm->ll_offset + i] =
+                NAME(draw_value)(PM4_T_BERNOULLI, q[0], q[1], (uint32_t)m, (uint32_t)((uint64_t)m >> 32),
+                                 (uint32_t)(tm->ll_offset + i), seed);
+            continue;
+          }
+          NAME(tape_forward)(ir, tm->op_begin, tm->op_end, i, x, x, v);
           for (int k = 0; k < 3; ++k) if (tm->param_reg[k] >= 0) q[k] = v[tm->param_reg[k]];
           if (pass == 0) {
             const int pos = vo->base + (vo->mode == PM4_MODE_ELEM ? i : 0);

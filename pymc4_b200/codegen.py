@@ -181,6 +181,11 @@ class _ModuleGen:
         self.lines = body
         op0, plan_idx = 0, 0
         for k, t in enumerate(self.ir.terms):
+            if t.glm is not None:
+                # dense Bernoulli-logit term: evaluated for all chains at once on the tensor cores
+                # (csrc/pm4_glm.cu, added by libpm4b200 after this per-chain pass); nothing to emit here
+                body.append("    // ---- term %d: %s (bernoulli_logit_glm) -- batched tensor-core path" % (k, t.label))
+                continue
             self.gen_one_term(k, t, op0, plan_idx)
             op0 += len(t.ops)
             if t.plan is not None:
@@ -585,6 +590,25 @@ class _ModuleGen:
             if not t.observed:
                 op0 += len(t.ops)
                 continue
+            if t.glm is not None:
+                g = t.glm
+                out.append("    // ---- observed term %d: %s (bernoulli_logit_glm): eta = X[i, :] . beta" % (k, t.label))
+                out.append("    {")
+                out.append("      const int n = __ldg(A.term_n + %d);" % k)
+                out.append("      for (int i = lane; i < n; i += 32) {")
+                out.append("        real eta = 0;")
+                out.append("        for (int q = 0; q < %d; ++q) eta += A.dataf[%d + (size_t)i * %d + q] * X(%d + q);"
+                           % (g.P, g.x_blob, g.P, g.base))
+                out.append("        const real prob = pm4::m_sigmoid<real>(eta), yv = A.dataf[%d + i];" % g.y_blob)
+                if predictive:
+                    out.append("        out[%d + i] = pm4::draw_value<real>(4, prob, (real)0, m_lo, m_hi, (uint32_t)(%d + i), k0, k1);"
+                               % (t.ll_offset, t.ll_offset))
+                else:
+                    # log Bernoulli(y | sigmoid(eta)) in the cancellation-free form y eta - softplus(eta)
+                    out.append("        out[%d + i] = yv * eta - pm4::m_softplus<real>(eta); (void)prob;" % t.ll_offset)
+                out.append("      }")
+                out.append("    }")
+                continue
             tag = "l%d" % k
             tp = _Tape(t.ops, op0, tag)
 
@@ -708,13 +732,31 @@ class _ModuleGen:
             out.append("      __syncwarp();")
             out.append("    }")
 
+        def emit_glm(k, t):
+            g = t.glm
+            out.append("    // ---- observed term %d: %s (bernoulli_logit_glm)" % (k, t.label))
+            out.append("    {")
+            out.append("      const int n = __ldg(A.term_n + %d);" % k)
+            out.append("      for (int i = lane; i < n; i += 32) {")
+            out.append("        real eta = 0;")
+            out.append("        for (int q = 0; q < %d; ++q) eta += A.dataf[%d + (size_t)i * %d + q] * X(%d + q);"
+                       % (g.P, g.x_blob, g.P, g.base))
+            out.append("        if (obs) obs[%d + i] = pm4::draw_value<real>(4, pm4::m_sigmoid<real>(eta), (real)0, m_lo, m_hi, "
+                       "(uint32_t)(%d + i), k0, k1);" % (t.ll_offset, t.ll_offset))
+            out.append("      }")
+            out.append("    }")
+
         for k, t in enumerate(self.ir.terms):
+            if t.glm is not None:
+                continue
             vo = t.ops[t.value_reg]
             if (not t.observed and t.kind != I.TERM_KINDS["potential"] and vo.opcode == ld_x
                     and vo.mode in (I.MODE_ELEM, I.MODE_SCALAR)):
                 emit(k, t, "x")
         for k, t in enumerate(self.ir.terms):
-            if t.observed:
+            if t.observed and t.glm is not None:
+                emit_glm(k, t)
+            elif t.observed:
                 emit(k, t, "obs")
         out.append("  }")
         return "\n".join(out)

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/pm4b200.h"
+#include "pm4_lockstep.cuh"
 #include "pm4_module.h"
 
 namespace {
@@ -59,9 +60,20 @@ struct pm4_comm {
   bool connected = false;
 };
 
+// a dense Bernoulli-logit term (PM4_T_BERNOULLI_LOGIT_GLM): pool offsets + the transposed covariates
+struct GlmTerm {
+  int n = 0, P = 0, base = 0, ldxt = 0;
+  int64_t x_off = 0, y_off = 0;
+  float* d_xt = nullptr;  // [P, ldxt]
+};
+
 struct pm4_model {
   int device = 0;
   pm4_comm* comm = nullptr;
+  std::vector<GlmTerm> glm;
+  void* glm_work = nullptr;
+  size_t glm_work_bytes = 0;
+  int* d_glm_err = nullptr;
   int D = 0, n_terms = 0, n_ops = 0, n_dets = 0, det_row = 0;
   int64_t n_dataf = 0, n_datai = 0;
   std::vector<double> dataf;
@@ -140,6 +152,53 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   m->elem_off = (int)ir->elem_off;
   m->spart_off = (int)ir->spart_off;
   m->phdr_off = (int)ir->phdr_off;
+  return PM4_OK;
+}
+
+// transposed single-precision copy of every GLM term's covariates (the gradient GEMM contracts over observations)
+static int upload_glm(pm4_model* m, const double* dataf) {
+  for (GlmTerm& g : m->glm) {
+    std::vector<float> xt((size_t)g.P * g.ldxt, 0.0f);
+    for (int i = 0; i < g.n; ++i)
+      for (int q = 0; q < g.P; ++q) xt[(size_t)q * g.ldxt + i] = (float)dataf[g.x_off + (int64_t)i * g.P + q];
+    if (!g.d_xt) CU(cudaMalloc(&g.d_xt, sizeof(float) * xt.size()));
+    CU(cudaMemcpy(g.d_xt, xt.data(), sizeof(float) * xt.size(), cudaMemcpyHostToDevice));
+  }
+  return PM4_OK;
+}
+
+// add the dense terms' log-likelihood and gradient for C chains (theta [C, D] -> lp [C], grad [C, D] or NULL)
+static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
+  if (m->glm.empty()) return PM4_OK;
+  if (dtype != PM4_F32) return fail(PM4_ENOSYS, "dense GLM terms are evaluated in 3xTF32 on the tensor cores: float32 only");
+  for (const GlmTerm& g : m->glm) {
+    const size_t need = (size_t)pm4_glm_work_bytes(g.n, g.P, C);
+    if (need > m->glm_work_bytes) {
+      CU(cudaStreamSynchronize(st));
+      if (m->glm_work) CU(cudaFree(m->glm_work));
+      m->glm_work = nullptr; m->glm_work_bytes = 0;
+      cudaError_t e = cudaMalloc(&m->glm_work, need);
+      if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GLM residuals: %s", need, cudaGetErrorString(e));
+      m->glm_work_bytes = need;
+    }
+    int rc = pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
+                               g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
+    g_launches += grad ? 3 : 2;
+    if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GLM kernels: %s", rc < 0 ? "unsupported shape (P must be a multiple of 4, at most 104)" : cudaGetErrorString((cudaError_t)rc));
+  }
+  return PM4_OK;
+}
+
+// did a tensor-core step time out?  (synchronises the stream)
+static int check_glm(pm4_model* m, cudaStream_t st) {
+  if (m->glm.empty()) return PM4_OK;
+  int err = 0;
+  CU(cudaMemcpyAsync(&err, m->d_glm_err, sizeof err, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (err) {
+    cudaMemsetAsync(m->d_glm_err, 0, sizeof(int), st);
+    return fail(PM4_ECUDA, "a tcgen05 step of the GLM kernels timed out (code %d)", err);
+  }
   return PM4_OK;
 }
 
@@ -235,7 +294,25 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
     CU(cudaMalloc(&m->d_plan_off, sizeof(int32_t) * (size_t)(2 * ir->n_plans + 2)));
     int rcp = upload_plans(m, ir);
     if (rcp != PM4_OK) return rcp;
-    return upload_pools(m, ir->dataf, ir->n_dataf, ir->datai, ir->n_datai);
+    for (int t = 0; t < ir->n_terms; ++t) {
+      const pm4_term_t& tm = ir->terms[t];
+      if (tm.kind != PM4_T_BERNOULLI_LOGIT_GLM) continue;
+      if (tm.glm_p <= 0 || tm.glm_p % 4 || tm.glm_p > 104) return fail(PM4_ENOSYS, "GLM term %d: the covariate count must be a multiple of 4, at most 104 (got %d)", t, tm.glm_p);
+      if (tm.glm_base < 0 || tm.glm_base + tm.glm_p > ir->D || tm.glm_x < 0 || tm.glm_x + (int64_t)tm.n * tm.glm_p > ir->n_dataf ||
+          tm.glm_y < 0 || tm.glm_y + tm.n > ir->n_dataf)
+        return fail(PM4_EINVAL, "GLM term %d points outside theta or the data pool", t);
+      GlmTerm g;
+      g.n = tm.n; g.P = tm.glm_p; g.base = tm.glm_base; g.x_off = tm.glm_x; g.y_off = tm.glm_y;
+      g.ldxt = (tm.n + 3) / 4 * 4;
+      m->glm.push_back(g);
+    }
+    if (!m->glm.empty()) {
+      CU(cudaMalloc((void**)&m->d_glm_err, sizeof(int)));
+      CU(cudaMemset(m->d_glm_err, 0, sizeof(int)));
+    }
+    rcp = upload_pools(m, ir->dataf, ir->n_dataf, ir->datai, ir->n_datai);
+    if (rcp != PM4_OK) return rcp;
+    return upload_glm(m, ir->dataf);
   };
   int rc = alloc();
   if (rc != PM4_OK) {
@@ -252,6 +329,8 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
   if (!m) return PM4_OK;
   cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_datai); cudaFree(m->d_term_n); cudaFree(m->d_op_blob);
   cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
+  for (GlmTerm& g : m->glm) cudaFree(g.d_xt);
+  cudaFree(m->glm_work); cudaFree(m->d_glm_err);
   if (m->module) dlclose(m->module);
   delete m;
   return PM4_OK;
@@ -266,7 +345,8 @@ extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n
                 (long long)n_datai, (long long)m->n_dataf, (long long)m->n_datai);
   CU(cudaSetDevice(m->device));
   CU(cudaDeviceSynchronize());
-  return upload_pools(m, dataf, n_dataf, datai, n_datai);
+  int rc = upload_pools(m, dataf, n_dataf, datai, n_datai);
+  return rc != PM4_OK ? rc : upload_glm(m, dataf);
 }
 
 extern "C" int pm4_model_set_plans(pm4_model_t* m, const pm4_ir_t* ir) {
@@ -292,6 +372,10 @@ extern "C" int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_logp(dtype, &a, C, theta_dev, lp_dev, grad_dev, stream), "logp_grad");
+  if (!m->glm.empty()) {
+    if ((rc = add_glm(m, dtype, C, theta_dev, lp_dev, grad_dev, (cudaStream_t)stream))) return rc;
+    return check_glm(m, (cudaStream_t)stream);
+  }
   return PM4_OK;
 }
 
@@ -439,6 +523,9 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_nuts_run: null argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
+  if (!m->glm.empty())
+    return fail(PM4_ENOSYS, "models with a dense GLM likelihood run on the lock-step path: use pm4_hmc_run "
+                            "(sampler_type=\"hmc\"); a lock-step NUTS is not built");
   if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0) return fail(PM4_EINVAL, "pm4_nuts_run: bad chain/draw counts");
   if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 20) return fail(PM4_EINVAL, "max_tree_depth must be in [1, 20]");
   if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
@@ -484,6 +571,75 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   return PM4_OK;
 }
 
+// Lock-step HMC for models with dense GLM terms (csrc/pm4_lockstep.cuh): every leapfrog is one batched
+// gradient -- the generated module's per-chain pass over the other terms + the tensor-core GLM pass.
+static int hmc_lockstep(pm4_model* m, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0_dev,
+                        const void* step_scale_dev, const void* momenta_dev, const void* uniforms_dev, void* states_dev,
+                        void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev, void* step_size_dev, void* traj_dev,
+                        cudaStream_t st) {
+  if (dtype != PM4_F32) return fail(PM4_ENOSYS, "the lock-step GLM path is float32 only");
+  if (cfg->proposal != PM4_PROPOSAL_LEAPFROG) return fail(PM4_ENOSYS, "random-walk proposals are not built for GLM models");
+  if (m->comm && m->comm->world > 1) return fail(PM4_ENOSYS, "cross-GPU pooled step sizes are not built for the lock-step path");
+  const int C = cfg->C, D = m->D, T = cfg->num_burnin + cfg->num_results;
+  const size_t CD = (size_t)C * D;
+  int rc;
+  pm4_mod_run_t r;  // only what fill_adapt and the pooled dual-averaging kernel read
+  memset(&r, 0, sizeof r);
+  r.C = C;
+  if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  RunBuffers buf(st);
+  pm4ls::Params p;
+  memset(&p, 0, sizeof p);
+  void* q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.th = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.g = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.thp = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.gp = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.p = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.lp = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.lpp = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.k0 = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 16))) return rc; p.da = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.accept = (float*)q;
+  p.C = C; p.D = D; p.B = cfg->num_burnin; p.S = cfg->num_results; p.L = cfg->num_leapfrog_steps;
+  p.chain_offset = cfg->chain_offset;
+  p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.adapt_kind = r.adapt_kind; p.num_adapt = r.num_adapt;
+  p.target_accept = (float)r.target_accept; p.shrinkage = (float)r.shrinkage; p.smoothing = (float)r.smoothing;
+  p.decay = (float)r.decay; p.adapt_rate = (float)r.adapt_rate;
+  p.seed_lo = (uint32_t)cfg->seed; p.seed_hi = (uint32_t)(cfg->seed >> 32);
+  p.step_scale = (const float*)step_scale_dev; p.momenta = (const float*)momenta_dev; p.uniforms = (const float*)uniforms_dev;
+  p.states = (float*)states_dev; p.lp_out = (float*)lp_dev; p.log_accept = (float*)log_accept_dev;
+  p.accepted = accepted_dev; p.traj = (float*)traj_dev;
+  r.da = p.da; r.accept = p.accept;
+  pm4_mod_args_t a = m->args(dtype);
+  auto full_grad = [&](const float* th, float* lp, float* g) -> int {
+    MOD(m->f_logp(dtype, &a, C, th, lp, g, st), "logp_grad (lock-step)");
+    return add_glm(m, dtype, C, th, lp, g, st);
+  };
+  const unsigned warp_grid = (unsigned)((C + 7) / 8), elem_grid = (unsigned)((CD + 255) / 256);
+  CU(cudaMemcpyAsync(p.th, theta0_dev, CD * 4, cudaMemcpyDeviceToDevice, st));
+  if ((rc = full_grad(p.th, p.lp, p.g))) return rc;
+  pm4ls::init_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(p, (float)cfg->step_size);
+  for (int t = 0; t < T; ++t) {
+    p.t = t;
+    pm4ls::begin_kernel<<<warp_grid, 256, 0, st>>>(p);
+    for (int l = 0; l < p.L; ++l) {
+      pm4ls::drift_kernel<<<elem_grid, 256, 0, st>>>(p);
+      if ((rc = full_grad(p.thp, p.lpp, p.gp))) return rc;
+      pm4ls::kick_kernel<<<elem_grid, 256, 0, st>>>(p);
+    }
+    pm4ls::finish_kernel<<<warp_grid, 256, 0, st>>>(p);
+    g_launches += 2 + 2 * p.L;
+    if (p.adapt_enabled && p.adapt_pooled) MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");
+  }
+  CU(cudaGetLastError());
+  if (step_size_dev) {
+    r.adapt_pooled = p.adapt_pooled;
+    MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  }
+  return check_glm(m, st);
+}
+
 extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0_dev,
                            const void* step_scale_dev, const void* momenta_dev, const void* uniforms_dev,
                            void* states_dev, void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev,
@@ -499,6 +655,9 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   if (rw && !(cfg->rw_scale > 0)) return fail(PM4_EINVAL, "rw_scale must be positive");
   CU(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (!m->glm.empty())
+    return hmc_lockstep(m, dtype, cfg, theta0_dev, step_scale_dev, momenta_dev, uniforms_dev, states_dev, lp_dev,
+                        log_accept_dev, accepted_dev, step_size_dev, traj_dev, st);
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
   const int T = cfg->num_burnin + cfg->num_results;
 

@@ -1,0 +1,494 @@
+// pm4_glm.cu -- dense-GLM building block: C[M x N] = A[M x K] * B[N x K]^T on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, accumulator in tensor memory), FP32 inputs split into two
+// TF32 terms each ("3xTF32": hi*hi + lo*hi + hi*lo) so that the product keeps FP32-level accuracy --
+// the X*beta contraction of the hierarchical logistic regression (BASELINE configs[2]; the
+// reference evaluates it as a broadcasted tf.tensordot inside tfd.Bernoulli's log_prob,
+// /root/reference/pymc4/distributions/discrete.py:75-78).
+//
+// Called by libpm4b200 (pm4_core.cu) for PM4_T_BERNOULLI_LOGIT_GLM terms: pm4_logp_grad adds it to the per-chain
+// pass of the generated module, pm4_hmc_run drives it once per lock-step leapfrog (pm4_lockstep.cuh).
+//
+// Test kernel: one CTA computes one 128 x 128 output tile.  Operands are staged by the CTA's threads into shared
+// memory in the canonical K-major "interleave" (no-swizzle) layout the UMMA descriptors describe:
+// 8-row x 16-byte core matrices, LBO between the two core matrices of one K-step, SBO between
+// 8-row groups.  One thread issues the MMAs and commits them to an mbarrier; the four warps read
+// the accumulator back with tcgen05.ld (warp w owns TMEM lanes 32w .. 32w+31).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pm4b200.h"
+
+namespace {
+
+constexpr int TILE = 128;     // M and N of one MMA tile
+constexpr int UMMA_K = 8;     // tf32 elements per tcgen05.mma (32 bytes)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 in bits
+// [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M x N
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (row, k) in the staged operand: core matrix = 8 rows x 4 tf32
+__device__ __forceinline__ uint32_t op_offset(int row, int k, int K) {
+  const uint32_t sbo = (uint32_t)(K / 4) * 128u;
+  return (uint32_t)(row >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
+}
+
+// C[128 x 128] (row-major, ldc) = A[128 x K] (row-major, lda) * B[128 x K]^T (row-major, ldb); K % 8 == 0
+__global__ void __launch_bounds__(128, 1) gemm_nt_3xtf32_kernel(const float* __restrict__ A, int lda,
+                                                                const float* __restrict__ B, int ldb,
+                                                                float* __restrict__ C, int ldc, int K, int passes,
+                                                                int* __restrict__ error) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t op_bytes = (uint32_t)TILE * (uint32_t)K * 4u;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + op_bytes;
+  unsigned char* b_hi = a_lo + op_bytes;
+  unsigned char* b_lo = b_hi + op_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + op_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TILE));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // stage the operands: split every FP32 value into two TF32 terms
+  for (int idx = tid; idx < TILE * K; idx += blockDim.x) {
+    const int row = idx / K, k = idx - row * K;
+    const float a = A[(size_t)row * lda + k], b = B[(size_t)row * ldb + k];
+    const float ah = to_tf32(a), bh = to_tf32(b);
+    const uint32_t off = op_offset(row, k, K);
+    *reinterpret_cast<float*>(a_hi + off) = ah;
+    *reinterpret_cast<float*>(a_lo + off) = to_tf32(a - ah);
+    *reinterpret_cast<float*>(b_hi + off) = bh;
+    *reinterpret_cast<float*>(b_lo + off) = to_tf32(b - bh);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(TILE, TILE);
+    const uint32_t sbo = (uint32_t)(K / 4) * 128u, lbo = 128u;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < passes; ++pass) {  // hi*hi, lo*hi, hi*lo
+      const unsigned char* ap = pass == 1 ? a_lo : a_hi;
+      const unsigned char* bp = pass == 2 ? b_lo : b_hi;
+      for (int ks = 0; ks < K / UMMA_K; ++ks) {
+        const uint64_t da = make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo);
+        const uint64_t db = make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+            "l"(da), "l"(db), "r"(idesc), "r"(acc)
+            : "memory");
+        acc = 1;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+  }
+  // wait for the accumulator (bounded: a malformed descriptor must not hang the GPU)
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
+    if (!done && clock64() - t0 > 2000000000ll) break;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!done) {
+    if (tid == 0 && error) *error = 1;
+  } else {
+    // warp w reads TMEM lanes 32w .. 32w+31 (= output rows), 32 columns at a time
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < TILE; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) C[(size_t)row * ldc + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE));
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Bernoulli-logit GLM likelihood for C chains in lock-step:
+//   eta[n, c] = sum_p X[n, p] beta[c, p]
+//   lp[c]    += sum_n y_n eta - softplus(eta)            (Bernoulli(probs = sigmoid(eta)).log_prob(y))
+//   g[c, p]  += sum_n (y_n - sigmoid(eta[n, c])) X[n, p]
+// Kernel 1 (eta): one CTA per (128 observations) x (128 chains): X tile and beta tile staged K-major,
+//   3xTF32 MMAs into TMEM, epilogue from TMEM: residuals r = y - sigmoid(eta) to global, TRANSPOSED
+//   (Rt[Cp, Np]: a lane owns an observation, so the stores of one chain are coalesced), the tile's column
+//   sums of the log-likelihood to LP[tile, Cp] (deterministic: no atomics).
+// Kernel 2 (grad): one CTA per (observation split) x (128 chains), looping over 64-observation tiles:
+//   Rt tile and Xt tile (the covariates transposed once at model creation) staged K-major -- the
+//   contraction runs over observations -- with 16-byte loads and stores, 3xTF32 MMAs accumulating
+//   G[chain, p] in TMEM over all tiles of the split, then G to GP[split, Cp, Pp].
+//   (MN-major TF32 operands in the no-swizzle layout produced zeros on this part; transposing the
+//   operands in memory keeps both GEMMs on the K-major path.)
+// Kernel 3: fixed-order reductions of LP and GP in double precision into lp[C] and grad[C, D].
+// ------------------------------------------------------------------------------------------
+constexpr int KT2 = 64;  // observations per tile of the gradient kernel
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+// bounded wait on an mbarrier phase; false on time-out
+__device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// sum of 32 per-lane values over the warp, transposed: lane j ends up with the total of v[j]
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int h = 32; h > 1; h >>= 1) {
+    const int half = h >> 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float send = up ? v[k] : v[k + half];
+      const float keep = up ? v[k + half] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  // value index held by lane l after the butterfly: bit-reversed interleave -> lane l holds column brev5(l)? no:
+  // the step with offset `off` sends the upper half of the live values to the lanes with that bit set, so lane l
+  // holds value ((l>>4)&1)*16 + ((l>>3)&1)*8 + ((l>>2)&1)*4 + ((l>>1)&1)*2 + (l&1) = l
+  return v[0];
+}
+
+__global__ void __launch_bounds__(128, 1) glm_eta_kernel(const float* __restrict__ X, const float* __restrict__ y, int n,
+                                                         int P, const float* __restrict__ theta, int ldt, int base, int C,
+                                                         float* __restrict__ Rt, int Np, int Cp,
+                                                         float* __restrict__ LP, int* __restrict__ error) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int K = (P + 7) & ~7;
+  const uint32_t op_bytes = (uint32_t)TILE * (uint32_t)K * 4u;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + op_bytes;
+  unsigned char* b_hi = a_lo + op_bytes;
+  unsigned char* b_lo = b_hi + op_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + op_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  float* colsum = reinterpret_cast<float*>(mbar + 2);  // [4][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TILE));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // stage X[n0 .. n0+127, :] and beta[c0 .. c0+127, :] (zero padded), split into two TF32 terms
+  for (int idx = tid; idx < TILE * K; idx += blockDim.x) {
+    const int row = idx / K, k = idx - row * K;
+    const float a = (n0 + row < n && k < P) ? X[(size_t)(n0 + row) * P + k] : 0.0f;
+    const float b = (c0 + row < C && k < P) ? theta[(size_t)(c0 + row) * ldt + base + k] : 0.0f;
+    const float ah = to_tf32(a), bh = to_tf32(b);
+    const uint32_t off = op_offset(row, k, K);
+    *reinterpret_cast<float*>(a_hi + off) = ah;
+    *reinterpret_cast<float*>(a_lo + off) = to_tf32(a - ah);
+    *reinterpret_cast<float*>(b_hi + off) = bh;
+    *reinterpret_cast<float*>(b_lo + off) = to_tf32(b - bh);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(TILE, TILE);
+    const uint32_t sbo = (uint32_t)(K / 4) * 128u, lbo = 128u;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < 3; ++pass) {  // hi*hi, lo*hi, hi*lo
+      const unsigned char* ap = pass == 1 ? a_lo : a_hi;
+      const unsigned char* bp = pass == 2 ? b_lo : b_hi;
+      for (int ks = 0; ks < K / UMMA_K; ++ks) {
+        mma_tf32(tmem, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
+                 make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, acc);
+        acc = 1;
+      }
+    }
+    mma_commit(mbar);
+  }
+  const bool ok = mbar_wait(mbar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok) {
+    if (tid == 0 && error) *error = 1;
+  } else {
+    const int row = warp * 32 + lane;
+    const bool live = n0 + row < n;
+    const float yv = live ? y[n0 + row] : 0.0f;
+    for (int cc = 0; cc < TILE; cc += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
+      float ll[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float eta = __uint_as_float(v[j]);
+        // softplus(eta) = max(eta, 0) + log1p(exp(-|eta|)); sigmoid from the same exponential
+        const float e = __expf(-fabsf(eta));
+        const float sp = fmaxf(eta, 0.0f) + log1pf(e);
+        const float sg = eta >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+        ll[j] = live ? yv * eta - sp : 0.0f;
+        v[j] = __float_as_uint(live ? yv - sg : 0.0f);
+      }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) Rt[(size_t)(c0 + cc + j) * Np + n0 + row] = __uint_as_float(v[j]);
+      }
+      const float cs = warp_colsum32(ll, lane);
+      colsum[warp * TILE + cc + lane] = cs;
+    }
+    __syncthreads();
+    LP[(size_t)blockIdx.x * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE));
+}
+
+// G[chain, p] = sum over the observations of this split of Rt[chain, n] * Xt[p, n]
+__global__ void __launch_bounds__(128, 1) glm_grad_kernel(const float* __restrict__ Xt, int ldx, int n, int P,
+                                                          const float* __restrict__ Rt, int Np, int Cp,
+                                                          float* __restrict__ GP, int Pp, int n_splits,
+                                                          int* __restrict__ error) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t a_bytes = (uint32_t)TILE * KT2 * 4u, b_bytes = (uint32_t)Pp * KT2 * 4u;
+  unsigned char* a_hi = smem;
+  unsigned char* a_lo = a_hi + a_bytes;
+  unsigned char* b_hi = a_lo + a_bytes;
+  unsigned char* b_lo = b_hi + b_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + b_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, c0 = blockIdx.y * TILE;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TILE));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const int n_tiles = (n + KT2 - 1) / KT2;
+  uint32_t acc = 0, parity = 0;
+  bool ok = true;
+  // stage `rows` rows of a [rows, ld] matrix, columns nb .. nb+63, K-major, split into two TF32 terms
+  auto stage = [&](const float* __restrict__ src, int ld, int rows, int rows_valid, int nb, unsigned char* hi, unsigned char* lo) {
+    for (int idx = tid; idx < rows * (KT2 / 4); idx += blockDim.x) {
+      const int row = idx / (KT2 / 4), k4 = idx - row * (KT2 / 4);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < rows_valid) {
+        const float* p = src + (size_t)row * ld + nb + 4 * k4;
+        if (nb + 4 * k4 + 3 < n) {
+          const float4 q = *reinterpret_cast<const float4*>(p);
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (nb + 4 * k4 + j < n) v[j] = p[j];
+        }
+      }
+      const float4 h = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+      const float4 l = make_float4(to_tf32(v[0] - h.x), to_tf32(v[1] - h.y), to_tf32(v[2] - h.z), to_tf32(v[3] - h.w));
+      const uint32_t off = op_offset(row, 4 * k4, KT2);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  };
+  for (int t = split; t < n_tiles && ok; t += n_splits) {
+    const int nb = t * KT2;
+    stage(Rt + (size_t)c0 * Np, Np, TILE, TILE, nb, a_hi, a_lo);
+    stage(Xt, ldx, Pp, P, nb, b_hi, b_lo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc(TILE, Pp);
+      const uint32_t sbo = (uint32_t)(KT2 / 4) * 128u, lbo = 128u;
+      for (int pass = 0; pass < 3; ++pass) {
+        const unsigned char* ap = pass == 1 ? a_lo : a_hi;
+        const unsigned char* bp = pass == 2 ? b_lo : b_hi;
+        for (int ks = 0; ks < KT2 / UMMA_K; ++ks)
+          mma_tf32(tmem, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
+                   make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, (pass | ks) ? 1u : acc);
+      }
+      mma_commit(mbar);
+    }
+    acc = 1;  // CTA-uniform: the accumulator holds at least one tile from here on
+    // the operand buffers are reused by the next tile: wait until the tensor core has consumed them
+    ok = mbar_wait(mbar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (!ok) {
+    if (tid == 0 && error) *error = 2;
+  } else {
+    const int row = warp * 32 + lane;  // chain within the tile
+    float* dst = GP + ((size_t)split * Cp + c0 + row) * Pp;
+    for (int cc = 0; cc < Pp; cc += 32) {
+      uint32_t v[32];
+      if (acc) tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cc + j < Pp) dst[cc + j] = acc ? __uint_as_float(v[j]) : 0.0f;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE));
+}
+
+// fixed-order reductions in double precision: lp[c] += sum_tiles LP[tile, c]; grad[c, base + p] += sum_splits GP[s, c, p]
+__global__ void glm_reduce_kernel(const float* __restrict__ LP, int n_tiles, const float* __restrict__ GP, int n_splits,
+                                  int Cp, int Pp, int C, int P, float* __restrict__ lp, float* __restrict__ grad, int ldg,
+                                  int base) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < C) {
+    double s = 0;
+    for (int t = 0; t < n_tiles; ++t) s += (double)LP[(size_t)t * Cp + idx];
+    lp[idx] += (float)s;
+  }
+  if (grad && idx < C * P) {
+    const int c = idx / P, p = idx - c * P;
+    double s = 0;
+    for (int k = 0; k < n_splits; ++k) s += (double)GP[((size_t)k * Cp + c) * Pp + p];
+    grad[(size_t)c * ldg + base + p] += (float)s;
+  }
+}
+
+}  // namespace
+
+// test entry: one 128 x 128 tile; passes = 1 (plain TF32) or 3 (3xTF32); returns 0, a CUDA error code, or
+// -62 (ETIME) when the MMA never completed
+extern "C" int pm4_glm_gemm_tile(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int K, int passes,
+                                 void* stream) {
+  if (K <= 0 || K % UMMA_K != 0 || K > 104 || passes < 1 || passes > 3) return -22;
+  const size_t smem = 4 * (size_t)TILE * K * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int* d_err = nullptr;
+  if ((e = cudaMalloc(&d_err, sizeof(int))) != cudaSuccess) return (int)e;
+  cudaMemsetAsync(d_err, 0, sizeof(int), (cudaStream_t)stream);
+  gemm_nt_3xtf32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, K, passes, d_err);
+  int err = 0;
+  e = cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(d_err);
+  if (e != cudaSuccess) return (int)e;
+  return err ? -62 : 0;
+}
+
+
+// Adds the Bernoulli-logit GLM likelihood of C chains to lp[C] and grad[C, ldg] (grad may be NULL).
+// X [n, P] row-major and its transpose Xt [P, ldxt] (ldxt >= n, a multiple of 4), y [n] (0/1 as float),
+// theta [C, ldt] with beta at columns base .. base+P-1.  work: device scratch of pm4_glm_work_bytes(n, P, C)
+// bytes.  Asynchronous on `stream`; *error_dev (device int, zeroed by the caller) becomes non-zero when a
+// tensor-core step timed out.
+static int glm_splits(int Cp) {
+  int splits = 296 / (Cp / TILE);
+  return splits < 1 ? 1 : splits;
+}
+static int64_t glm_np(int n) { return ((int64_t)n + KT2 - 1) / KT2 * KT2; }
+
+extern "C" int64_t pm4_glm_work_bytes(int n, int P, int C) {
+  const int64_t Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16;
+  const int64_t n_tiles = (n + TILE - 1) / TILE;
+  return 4 * (glm_np(n) * Cp + n_tiles * Cp + (int64_t)glm_splits((int)Cp) * Cp * Pp) + 256;
+}
+
+extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P,
+                                 const float* theta, int ldt, int base, int C, float* lp, float* grad, int ldg,
+                                 void* work, int* error_dev, void* stream) {
+  if (n <= 0 || P <= 0 || P > 104 || P % 4 != 0 || C <= 0 || ldxt < n || ldxt % 4 != 0) return -22;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16, K = (P + 7) & ~7;
+  const int n_tiles = (n + TILE - 1) / TILE;
+  const int Np = (int)glm_np(n);
+  const int splits = glm_splits(Cp);
+  float* Rt = (float*)work;
+  float* LP = Rt + (size_t)Np * Cp;
+  float* GP = LP + (size_t)n_tiles * Cp;
+  const size_t smem1 = 4 * (size_t)TILE * K * 4 + 16 + 4 * TILE * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(glm_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  if (e != cudaSuccess) return (int)e;
+  glm_eta_kernel<<<dim3(n_tiles, Cp / TILE), 128, smem1, st>>>(X, y, n, P, theta, ldt, base, C, Rt, Np, Cp, LP, error_dev);
+  if (grad) {
+    const size_t smem2 = 2 * (size_t)TILE * KT2 * 4 + 2 * (size_t)Pp * KT2 * 4 + 64;
+    e = cudaFuncSetAttribute(glm_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    glm_grad_kernel<<<dim3(splits, Cp / TILE), 128, smem2, st>>>(Xt, ldxt, n, P, Rt, Np, Cp, GP, Pp, splits, error_dev);
+  }
+  const int work_items = grad ? C * P : C;
+  glm_reduce_kernel<<<(work_items + 255) / 256, 256, 0, st>>>(LP, n_tiles, GP, splits, Cp, Pp, C, P, lp, grad, ldg, base);
+  return (int)cudaGetLastError();
+}

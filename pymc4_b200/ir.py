@@ -29,7 +29,7 @@ from . import symbolic as sym
 from .coroutine_model import Model
 from .utils import NameParts
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
 
@@ -40,8 +40,9 @@ TERM_KINDS = {
     "halfcauchy": 3,
     "bernoulli": 4,
     "poisson": 5,
+    "bernoulli_logit_glm": 6,
 }
-TERM_NPARAMS = {0: 0, 1: 2, 2: 1, 3: 1, 4: 1, 5: 1}
+TERM_NPARAMS = {0: 0, 1: 2, 2: 1, 3: 1, 4: 1, 5: 1, 6: 0}
 
 OP = {
     "ld_const": 0, "ld_data": 1, "ld_x": 2, "ld_z": 3,
@@ -92,6 +93,7 @@ class Term:
     param_regs: List[int]
     label: str = ""
     plan: Optional["Plan"] = None
+    glm: Optional["GLM"] = None     # dense Bernoulli-logit term (no tape): see GLM
     observed: bool = False          # density of an observed variable (enters the pointwise log-likelihood)
     ll_offset: int = 0              # position of element 0 in one state's log-likelihood row
     shape: Tuple[int, ...] = ()     # broadcast shape of the term's elements
@@ -99,6 +101,18 @@ class Term:
     @property
     def n_regs(self) -> int:
         return max([o.dst for o in self.ops] + [-1]) + 1
+
+
+@dataclass
+class GLM:
+    """``Bernoulli(probs=sigmoid(X @ beta))`` with a constant matrix X [n, P] and a free vector beta: the dense
+    likelihood of the hierarchical logistic regression (BASELINE configs[2]).  It has no element-wise tape: the
+    device evaluates it for all chains at once as two tensor-core GEMMs (csrc/pm4_glm.cu), the oracle with
+    plain loops."""
+    x_blob: int      # dataf offset of X, row-major [n, P]
+    y_blob: int      # dataf offset of y [n]
+    base: int        # theta offset of beta[0]
+    P: int
 
 
 @dataclass
@@ -171,6 +185,10 @@ class ModelIR:
         return sum(d.n for d in self.dets)
 
     @property
+    def glm_terms(self) -> List["Term"]:
+        return [t for t in self.terms if t.glm is not None]
+
+    @property
     def streamed(self) -> bool:
         """Plan pools too large to stage in shared memory (the device reads them from L2): the generated row
         loops prefetch."""
@@ -196,6 +214,8 @@ class ModelIR:
 
         for t in self.terms:
             h.append(struct.pack("<iii?", t.kind, t.value_reg, len(t.ops), t.observed))
+            if t.glm is not None:
+                h.append(struct.pack("<qqii", t.glm.x_blob, t.glm.y_blob, t.glm.base, t.glm.P))
             h.append(struct.pack("<%di" % len(t.param_regs), *t.param_regs))
             ops_key(t.ops, t.n)
             if t.plan is not None:
@@ -377,7 +397,33 @@ def _identity_map(n: int) -> np.ndarray:
     return np.arange(n, dtype=np.int64)
 
 
+def _match_glm(kind: str, value, params: List[Any], rvs, pools, label: str) -> Optional[Term]:
+    """Bernoulli(probs=sigmoid(X @ beta)) observed, with constant X and beta a whole free vector -> GLM term."""
+    if kind != "bernoulli" or len(params) != 1:
+        return None
+    p, v = sym.as_expr(params[0]), sym.as_expr(value)
+    if p.op != "sigmoid" or p.args[0].op != "matvec" or v.op != "const":
+        return None
+    X, b = p.args[0].args
+    if X.op != "const" or b.op != "view" or b.space != "x":
+        return None
+    rv = rvs[b.rv]
+    idx = np.asarray(b.index).reshape(-1)
+    if rv.transform != TR_IDENTITY or idx.size != rv.size or not np.array_equal(idx, np.arange(rv.size)):
+        return None
+    n, P = X.shape
+    if v.shape != (n,):
+        return None
+    x_blob = pools.add_f(np.asarray(X.data, dtype=np.float64).reshape(-1))
+    y_blob = pools.add_f(np.asarray(v.data, dtype=np.float64).reshape(-1))
+    return Term(kind=TERM_KINDS["bernoulli_logit_glm"], n=int(n), ops=[], value_reg=-1, param_regs=[], label=label,
+                shape=(int(n),), glm=GLM(x_blob=x_blob, y_blob=y_blob, base=rv.offset, P=int(P)))
+
+
 def _lower_term(kind: str, value, params: List[Any], rvs, pools, label="") -> Term:
+    glm = _match_glm(kind, value, params, rvs, pools, label)
+    if glm is not None:
+        return glm
     exprs = [sym.as_expr(value)] + [sym.as_expr(p) for p in params]
     shape = tuple(np.broadcast_shapes(*[e.shape for e in exprs]))
     n = int(np.prod(shape, dtype=np.int64)) if shape else 1
@@ -516,7 +562,8 @@ class CTerm(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("n", ctypes.c_int32), ("op_begin", ctypes.c_int32),
                 ("op_end", ctypes.c_int32), ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32),
                 ("param_reg", ctypes.c_int32 * 3), ("plan", ctypes.c_int32), ("observed", ctypes.c_int32),
-                ("ll_offset", ctypes.c_int32)]
+                ("ll_offset", ctypes.c_int32), ("glm_base", ctypes.c_int32), ("glm_p", ctypes.c_int32),
+                ("glm_x", ctypes.c_int64), ("glm_y", ctypes.c_int64)]
 
 
 class CPlan(ctypes.Structure):
@@ -567,8 +614,10 @@ class PackedIR:
             if t.plan is not None:
                 plan_idx = len(plans)
                 plans.append(t.plan)
+            g = t.glm
             cterms[k] = CTerm(t.kind, t.n, begin, len(all_ops), t.n_regs, t.value_reg,
-                              (ctypes.c_int32 * 3)(*pr), plan_idx, 1 if t.observed else 0, t.ll_offset)
+                              (ctypes.c_int32 * 3)(*pr), plan_idx, 1 if t.observed else 0, t.ll_offset,
+                              g.base if g else 0, g.P if g else 0, g.x_blob if g else 0, g.y_blob if g else 0)
         cdets = (CDet * max(len(ir.dets), 1))()
         for k, d in enumerate(ir.dets):
             begin = len(all_ops)

@@ -66,7 +66,7 @@ def choose_team_warps(ir: "I.ModelIR") -> int:
         if t not in TEAM_SIZES:
             raise ValueError("PM4_TEAM_WARPS must be one of %s" % (TEAM_SIZES,))
         return t
-    work = sum(t.n for t in ir.terms)
+    work = sum(t.n for t in ir.terms if t.glm is None)  # dense GLM terms are not evaluated by the teams
     # ~640 term elements per warp; at most ~20 state elements per lane (theta, momentum and gradient
     # stay in registers); never more than 16 warps (512 threads keep 128 registers per thread)
     want = max(work / 640.0, ir.D / (32.0 * 20.0))

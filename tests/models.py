@@ -151,3 +151,21 @@ def outer_model():
     dx = yield nested_model(dcond)
     ddx = yield pm.Deterministic("ddx", dx)
     return ddx
+
+
+@pm.model
+def logistic_glm_model(X, y):
+    """Hierarchical logistic regression with a dense linear predictor X @ beta (BASELINE configs[2] shape;
+    SURVEY section 8(d) item 3): beta_p ~ N(mu, tau), mu ~ N(0, 1), tau ~ HalfNormal(1), y ~ Bernoulli(sigmoid(X beta))."""
+    mu = yield pm.Normal("mu", 0.0, 1.0)
+    tau = yield pm.HalfNormal("tau", 1.0)
+    beta = yield pm.Normal("beta", mu, tau, batch_stack=X.shape[1])
+    obs = yield pm.Bernoulli("obs", pm.math.sigmoid(X @ beta), observed=y)
+
+
+def logistic_glm_data(n=3000, p=20, seed=11):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, p))
+    beta = rng.normal(0, 0.5, p)
+    y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
+    return X, y

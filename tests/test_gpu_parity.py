@@ -404,3 +404,81 @@ def test_full_size_invariants_radon_4096_chains():
     assert torch.equal(shard["states"], full["states"][:, off:off + n])
     assert torch.equal(shard["leapfrogs"], full["leapfrogs"][:, off:off + n])
     assert int(full["total_leapfrogs"].sum()) > C * (B + S)
+
+
+# ------------------------------------------------------------------------------------------
+# dense GLM likelihood (BASELINE configs[2] shape: hierarchical logistic regression, X @ beta): the likelihood
+# and its gradient for all chains at once on the tcgen05 tensor cores in 3xTF32 (csrc/pm4_glm.cu), HMC in
+# lock-step over the chains (csrc/pm4_lockstep.cuh)
+# ------------------------------------------------------------------------------------------
+def test_tcgen05_gemm_tile_3xtf32():
+    """The MMA building block alone: one 128 x 128 tile, plain TF32 (1e-3) against 3xTF32 (1e-6)."""
+    import ctypes
+
+    import torch
+
+    from pymc4_b200 import _cabi
+
+    L = _cabi.load_library()
+    torch.manual_seed(0)
+    for K in (8, 40, 104):
+        A, B = torch.randn(128, K, device="cuda"), torch.randn(128, K, device="cuda")
+        ref = A.double() @ B.double().T
+        errs = []
+        for passes in (1, 3):
+            C = torch.zeros(128, 128, device="cuda")
+            rc = L.pm4_glm_gemm_tile(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), 128, K, passes, None)
+            assert rc == 0
+            errs.append(float((C.double() - ref).abs().max() / ref.abs().max()))
+        assert 1e-5 < errs[0] < 2e-3 and errs[1] < 5e-6, errs
+
+
+@pytest.mark.parametrize("n,p,C", [(3000, 20, 96), (700, 100, 300)])
+def test_dense_glm_logp_grad_parity(n, p, C, oracle_mod):
+    X, y = M.logistic_glm_data(n=n, p=p)
+    ir, _, _ = lower_model(M.logistic_glm_model(X, y))
+    rng = np.random.default_rng(61)
+    theta = rng.normal(0, 0.4, (C, ir.D))
+    theta[0] = 0.0
+    lp_ref, g_ref = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    lp, g = _dm(ir).logp_grad(theta.astype(np.float32), dtype=np.float32)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    assert np.max(np.abs(lp - lp_ref) / np.abs(lp_ref)) < 1e-5
+    for c in range(C):
+        assert _rel(g[c], g_ref[c]) < 1e-5, c
+    lp_only, _ = _dm(ir).logp_grad(theta.astype(np.float32), dtype=np.float32, want_grad=False)
+    np.testing.assert_allclose(lp_only.cpu().numpy(), lp, rtol=1e-6)
+    # post-processing kernels know the dense term too
+    ll = _dm(ir).log_likelihood(theta[:8].astype(np.float32), dtype=np.float32).cpu().numpy()
+    np.testing.assert_allclose(ll, oracle_mod.Oracle(ir).log_likelihood(theta[:8]), rtol=1e-4, atol=1e-5)
+
+
+def test_dense_glm_lockstep_hmc_parity(oracle_mod):
+    """(b) for the GLM path: a 30-leapfrog trajectory from injected momenta, then an adaptive chain."""
+    X, y = M.logistic_glm_data(n=2000, p=20)
+    ir, _, _ = lower_model(M.logistic_glm_model(X, y))
+    C, D, L = 40, ir.D, 30
+    rng = np.random.default_rng(62)
+    theta0 = rng.normal(0, 0.2, (C, D))
+    momenta = rng.standard_normal((1, C, D))
+    uniforms = rng.random((1, C))
+    cfg = make_hmc_cfg(C, 1, 0, step_size=0.01, num_leapfrog_steps=L, seed=1, adapt=make_adapt(enabled=False))
+    ref = oracle_mod.Oracle(ir).hmc(cfg, theta0, dtype=np.float64, momenta=momenta, uniforms=uniforms)
+    out = _dm(ir).hmc(cfg, theta0.astype(np.float32), dtype=np.float32, momenta=momenta, uniforms=uniforms, want_traj=True)
+    assert np.max(np.abs(out["traj"].cpu().numpy() - ref["traj"])) < 1e-4
+    assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+    # adaptive run (per-chain and pooled dual averaging): same Philox stream as the oracle's FP32 run
+    B, S = 30, 20
+    for mode in (PM4_EPS_POOLED, PM4_EPS_PER_CHAIN):
+        cfg = make_hmc_cfg(C, S, B, step_size=0.02, num_leapfrog_steps=5, seed=9,
+                           adapt=make_adapt(mode=mode, num_adaptation_steps=B))
+        ref = oracle_mod.Oracle(ir).hmc(cfg, np.zeros(D), dtype=np.float32)
+        out = _dm(ir).hmc(cfg, np.zeros((C, D), np.float32), dtype=np.float32)
+        # a single accept decision that rounding flips sends that chain (pooled: every chain, through epsilon) on
+        # another path, so the runs are compared statistically: first transitions identical, then the same regime
+        acc, racc = out["accepted"].cpu().numpy(), ref["accepted"]
+        assert np.mean(acc == racc) > 0.8 and abs(acc.mean() - racc.mean()) < 0.1
+        np.testing.assert_allclose(np.median(out["step_size"].cpu().numpy()), np.median(ref["step_size"]), rtol=0.25)
+        np.testing.assert_allclose(out["states"].cpu().numpy().mean((0, 1)), ref["states"].mean((0, 1)), atol=0.15)
+    with pytest.raises(RuntimeError, match="lock-step"):
+        _dm(ir).nuts(make_nuts_cfg(C, 2, 2), np.zeros((C, D), np.float32), dtype=np.float32)

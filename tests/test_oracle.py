@@ -399,3 +399,46 @@ def test_prior_predictive_ancestral_sampling(oracle_mod):
     z = (alpha - mu_a[:, None]) / sig_a[:, None]
     assert np.max(np.abs(z.mean(0))) < 0.03 and np.max(np.abs(z.std(0) - 1)) < 0.03
     assert obs.shape == (20000, 120) and np.all(np.isfinite(obs))
+
+
+def test_dense_glm_term_lowering_and_oracle(oracle_mod):
+    """Bernoulli(sigmoid(X @ beta)) lowers to ONE dense term (no tape) and the oracle evaluates it like the
+    explicit-sum model and like scipy (the reference: tfd.Bernoulli(probs=...).log_prob, discrete.py:75-78)."""
+    from scipy import stats
+
+    from pymc4_b200.ir import TERM_KINDS, lower_model
+    from tests import models as M
+
+    X, y = M.logistic_glm_data(n=500, p=12)
+    ir, _, _ = lower_model(M.logistic_glm_model(X, y))
+    (g,) = ir.glm_terms
+    assert g.kind == TERM_KINDS["bernoulli_logit_glm"] and g.n == 500 and g.glm.P == 12 and not g.ops and g.observed
+    assert g.glm.base == ir.rv_by_name("logistic_glm_model/beta").offset and ir.ll_row == 500
+    assert ir.team_warps == 1  # the dense term is not the teams' work
+    rng = np.random.default_rng(2)
+    theta = rng.normal(0, 0.5, (6, ir.D))
+    lp, grad = oracle_mod.Oracle(ir).logp_grad(theta)
+    parts = ir.split_theta(theta)
+    mu, beta, tau = parts["logistic_glm_model/mu"], parts["logistic_glm_model/beta"], np.exp(parts["logistic_glm_model/__log_tau"])
+    p = 1 / (1 + np.exp(-(beta @ X.T)))
+    want = (stats.norm(0, 1).logpdf(mu) + stats.halfnorm(scale=1).logpdf(tau) + parts["logistic_glm_model/__log_tau"]
+            + stats.norm(mu[:, None], tau[:, None]).logpdf(beta).sum(1) + stats.bernoulli(p).logpmf(y).sum(1))
+    np.testing.assert_allclose(lp, want, rtol=1e-12)
+    eps = 1e-6
+    for j in (0, 3, ir.D - 1):
+        d = np.zeros(ir.D); d[j] = eps
+        fd = (oracle_mod.Oracle(ir).logp_grad(theta + d)[0] - oracle_mod.Oracle(ir).logp_grad(theta - d)[0]) / (2 * eps)
+        np.testing.assert_allclose(grad[:, j], fd, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(oracle_mod.Oracle(ir).log_likelihood(theta), stats.bernoulli(p).logpmf(y), rtol=1e-10)
+    d = oracle_mod.Oracle(ir).posterior_predictive(np.tile(theta[0], (3000, 1)), seed=4)
+    assert np.max(np.abs(d.mean(0) - p[0])) < 5 * 0.5 / np.sqrt(3000)
+    # anything that is not exactly that pattern still needs the tape (and matvec has no tape op)
+    import pymc4_b200 as pm
+
+    @pm.model
+    def shifted(X, y):
+        beta = yield pm.Normal("beta", 0.0, 1.0, batch_stack=X.shape[1])
+        yield pm.Bernoulli("obs", pm.math.sigmoid(X @ beta + 1.0), observed=y)
+
+    with pytest.raises(NotImplementedError):
+        lower_model(shifted(X, y))

@@ -187,3 +187,19 @@ def test_sample_prior_predictive():
     np.testing.assert_allclose(det["outer_model/nested_model/dx"], det["outer_model/nested_model/x"] + 1, rtol=1e-5, atol=1e-5)
     with pytest.raises(ValueError):
         pm.sample_prior_predictive(M.schools_pm4(), var_names=["schools_pm4/nope"])
+
+
+def test_sample_dense_logistic_regression_with_hmc():
+    """pm.sample(..., sampler_type="hmc") on the hierarchical logistic regression with X @ beta: the posterior mean
+    of beta recovers the generating coefficients."""
+    X, y = M.logistic_glm_data(n=3000, p=20)
+    rng = np.random.default_rng(11)
+    rng.standard_normal((3000, 20))
+    beta_true = rng.normal(0, 0.5, 20)  # the generator of logistic_glm_data draws X first, then beta
+    trace = pm.sample(M.logistic_glm_model(X, y), sampler_type="hmc", num_chains=64, num_samples=150, burn_in=150,
+                      step_size=0.02, num_leapfrog_steps=10, seed=2)
+    beta = trace.posterior["logistic_glm_model/beta"]
+    assert beta.shape == (64, 150, 20)
+    err = np.abs(beta.mean((0, 1)) - beta_true)
+    assert np.max(err) < 0.25 and np.mean(err) < 0.1
+    assert 0.5 < np.exp(np.minimum(trace.sample_stats["mean_tree_accept"], 0)).mean() <= 1.0
