@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_3xtf32_kernel(const float* __r
 // Kernel 3: fixed-order reductions of LP and GP in double precision into lp[C] and grad[C, D].
 // ------------------------------------------------------------------------------------------
 constexpr int KT2 = 64;  // observations per tile of the gradient kernel
+constexpr int NT = 512;  // threads per CTA of the GLM kernels: 16 warps stage the operands and share the epilogue
+                         // (warp w reads TMEM lanes 32 (w % 4) .. + 31, column block w / 4)
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -218,7 +220,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(128, 1) glm_eta_kernel(const float* __restrict__ X, const float* __restrict__ y, int n,
+__global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict__ X, const float* __restrict__ y, int n,
                                                          int P, const float* __restrict__ theta, int ldt, int base, int C,
                                                          float* __restrict__ Rt, int Np, int Cp,
                                                          float* __restrict__ LP, int* __restrict__ error) {
@@ -280,12 +282,12 @@ __global__ void __launch_bounds__(128, 1) glm_eta_kernel(const float* __restrict
   if (!ok) {
     if (tid == 0 && error) *error = 1;
   } else {
-    const int row = warp * 32 + lane;
+    const int lg = warp & 3, row = lg * 32 + lane;
     const bool live = n0 + row < n;
     const float yv = live ? y[n0 + row] : 0.0f;
-    for (int cc = 0; cc < TILE; cc += 32) {
+    for (int cc = (warp >> 2) * 32; cc < TILE; cc += (NT / 128) * 32) {
       uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
+      tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)cc, v);
       float ll[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -302,10 +304,11 @@ __global__ void __launch_bounds__(128, 1) glm_eta_kernel(const float* __restrict
         for (int j = 0; j < 32; ++j) Rt[(size_t)(c0 + cc + j) * Np + n0 + row] = __uint_as_float(v[j]);
       }
       const float cs = warp_colsum32(ll, lane);
-      colsum[warp * TILE + cc + lane] = cs;
+      colsum[lg * TILE + cc + lane] = cs;
     }
     __syncthreads();
-    LP[(size_t)blockIdx.x * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
+    if (tid < TILE)
+      LP[(size_t)blockIdx.x * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(128, 1) glm_eta_kernel(const float* __restrict
 }
 
 // G[chain, p] = sum over the observations of this split of Rt[chain, n] * Xt[p, n]
-__global__ void __launch_bounds__(128, 1) glm_grad_kernel(const float* __restrict__ Xt, int ldx, int n, int P,
+__global__ void __launch_bounds__(NT, 1) glm_grad_kernel(const float* __restrict__ Xt, int ldx, int n, int P,
                                                           const float* __restrict__ Rt, int Np, int Cp,
                                                           float* __restrict__ GP, int Pp, int n_splits,
                                                           int* __restrict__ error) {
@@ -393,11 +396,11 @@ __global__ void __launch_bounds__(128, 1) glm_grad_kernel(const float* __restric
   if (!ok) {
     if (tid == 0 && error) *error = 2;
   } else {
-    const int row = warp * 32 + lane;  // chain within the tile
+    const int lg = warp & 3, row = lg * 32 + lane;  // chain within the tile
     float* dst = GP + ((size_t)split * Cp + c0 + row) * Pp;
-    for (int cc = 0; cc < Pp; cc += 32) {
+    for (int cc = (warp >> 2) * 32; cc < Pp; cc += (NT / 128) * 32) {
       uint32_t v[32];
-      if (acc) tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
+      if (acc) tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)cc, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (cc + j < Pp) dst[cc + j] = acc ? __uint_as_float(v[j]) : 0.0f;
@@ -481,12 +484,12 @@ extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, cons
   const size_t smem1 = 4 * (size_t)TILE * K * 4 + 16 + 4 * TILE * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(glm_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return (int)e;
-  glm_eta_kernel<<<dim3(n_tiles, Cp / TILE), 128, smem1, st>>>(X, y, n, P, theta, ldt, base, C, Rt, Np, Cp, LP, error_dev);
+  glm_eta_kernel<<<dim3(n_tiles, Cp / TILE), NT, smem1, st>>>(X, y, n, P, theta, ldt, base, C, Rt, Np, Cp, LP, error_dev);
   if (grad) {
     const size_t smem2 = 2 * (size_t)TILE * KT2 * 4 + 2 * (size_t)Pp * KT2 * 4 + 64;
     e = cudaFuncSetAttribute(glm_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return (int)e;
-    glm_grad_kernel<<<dim3(splits, Cp / TILE), 128, smem2, st>>>(Xt, ldxt, n, P, Rt, Np, Cp, GP, Pp, splits, error_dev);
+    glm_grad_kernel<<<dim3(splits, Cp / TILE), NT, smem2, st>>>(Xt, ldxt, n, P, Rt, Np, Cp, GP, Pp, splits, error_dev);
   }
   const int work_items = grad ? C * P : C;
   glm_reduce_kernel<<<(work_items + 255) / 256, 256, 0, st>>>(LP, n_tiles, GP, splits, Cp, Pp, C, P, lp, grad, ldg, base);
