@@ -59,9 +59,13 @@ def parse_args():
                     help="per-chain: step_size with a leading chain axis (independent dual averaging, no coupling); "
                          "pooled: scalar step_size, the reference default (one epsilon adapted from the mean "
                          "acceptance of all chains of the rank: lock-step launches during burn-in)")
-    ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k"],
+    ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k", "logit"],
                     help="radon919 = BASELINE configs[1] (the headline); radon100k = configs[4] shape "
-                         "(100k observations / 5k groups, D = 10 005; pass --chains/--burn-in/--draws to bound the run)")
+                         "(100k observations / 5k groups, D = 10 005; pass --chains/--burn-in/--draws to bound the run); "
+                         "logit = configs[2]: hierarchical logistic regression, N = 1M x P = 100, 1024 chains of HMC "
+                         "(3 leapfrogs), X beta on the tcgen05 tensor cores in 3xTF32")
+    ap.add_argument("--logit-n", type=int, default=1_000_000)
+    ap.add_argument("--leapfrogs", type=int, default=3, help="HMC leapfrog steps (logit workload; reference default 3)")
     return ap.parse_args()
 
 
@@ -69,6 +73,12 @@ def build_model():
     from pymc4_b200.ir import lower_model
     from tests import models as M
 
+    if WORKLOAD == "logit":
+        X, y = M.logistic_glm_data(n=N_OBS, p=LOGIT_P, seed=20261019)
+        model = M.logistic_glm_model(X, y)
+        ir, _, _ = lower_model(model)
+        assert ir.D == D_MODEL and len(ir.glm_terms) == 1
+        return model, ir
     if N_OBS == 919:
         idx, x, y, g = M.radon_synthetic(N_OBS, N_GROUPS)
     else:
@@ -79,9 +89,20 @@ def build_model():
     return model, ir
 
 
-def select_workload(name):
+WORKLOAD, LOGIT_P = "radon919", 100
+
+
+def select_workload(name, logit_n=1_000_000):
     """Switch the module-level shape constants (the algorithmic cost per unit follows the shape)."""
-    global N_OBS, N_GROUPS, D_MODEL, FLOPS_PER_UNIT, ONCHIP_BYTES_PER_UNIT
+    global N_OBS, N_GROUPS, D_MODEL, FLOPS_PER_UNIT, ONCHIP_BYTES_PER_UNIT, WORKLOAD
+    WORKLOAD = name
+    if name == "logit":
+        # SURVEY 8(d): F = 4 N P flops per unit (X beta and X^T r), X read once per lock-step leapfrog for all chains
+        N_OBS, N_GROUPS = int(logit_n), 0
+        D_MODEL = LOGIT_P + 2
+        FLOPS_PER_UNIT = 4 * N_OBS * LOGIT_P
+        ONCHIP_BYTES_PER_UNIT = 0
+        return
     if name == "radon100k":
         N_OBS, N_GROUPS = 100_000, 5_000
     D_MODEL = 2 * N_GROUPS + 5
@@ -90,6 +111,18 @@ def select_workload(name):
 
 
 def workload_config(args, n_gpus):
+    if WORKLOAD == "logit":
+        return {
+            "workload": "hierarchical logistic regression, synthetic N=%d x P=%d Bernoulli likelihood (D=%d), %d chains "
+                        "HMC (%d leapfrogs) per GPU, X.beta as 3xTF32 tcgen05 tiles" % (N_OBS, LOGIT_P, D_MODEL, args.chains,
+                                                                                          args.leapfrogs),
+            "chains_per_gpu": args.chains, "global_chains": args.chains * n_gpus, "burn_in": args.burn_in,
+            "draws": args.draws, "num_leapfrog_steps": args.leapfrogs,
+            "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept HMC transitions, lock-step over chains",
+            "step_size": "%s dual averaging from %.3g" % (args.eps_mode, args.step_size),
+            "parallelism": "chains sharded, %d per GPU; every GPU holds the full X" % args.chains,
+            "l2": "L2 flushed (256 MiB write) between timed steps; X (400 MB) exceeds L2",
+        }
     return {
         "workload": "radon_hierarchical varying-intercept/slope, synthetic %d obs / %d %s (D=%d), "
                     "%d chains NUTS per GPU" % (N_OBS, N_GROUPS, "counties" if N_OBS == 919 else "groups", D_MODEL,
@@ -121,8 +154,21 @@ def cpu_sample_rate(ir, args, chains, seed):
 
     orc = pm4_oracle.Oracle(ir)
     mode = PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED
-    cfg = make_nuts_cfg(chains, args.draws, args.burn_in, step_size=args.step_size, seed=seed,
-                        adapt=make_adapt(mode=mode, num_adaptation_steps=args.burn_in))
+    adapt = make_adapt(mode=mode, num_adaptation_steps=args.burn_in)
+    if WORKLOAD == "logit":
+        from pymc4_b200._cstructs import make_hmc_cfg
+
+        # a scalar gradient evaluation over N = 1M rows takes ~0.2 s: bound the sample to 2 + 2 transitions
+        # (the cost per gradient evaluation does not depend on the transition count)
+        b, s_ = min(args.burn_in, 2), min(args.draws, 2)
+        adapt = make_adapt(mode=mode, num_adaptation_steps=b)
+        cfg = make_hmc_cfg(chains, s_, b, step_size=args.step_size, num_leapfrog_steps=args.leapfrogs,
+                           seed=seed, adapt=adapt)
+        t0 = time.perf_counter()
+        orc.hmc(cfg, np.zeros(ir.D), dtype=np.float32)
+        dt = time.perf_counter() - t0
+        return float(chains * (b + s_) * args.leapfrogs), dt
+    cfg = make_nuts_cfg(chains, args.draws, args.burn_in, step_size=args.step_size, seed=seed, adapt=adapt)
     t0 = time.perf_counter()
     out = orc.nuts(cfg, np.zeros(ir.D), dtype=np.float32)
     dt = time.perf_counter() - t0
@@ -136,14 +182,16 @@ def cpu_baseline(ir, args):
     # calibrate so the sample costs roughly 10-30 s of CPU work
     evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
     rate = evals / dt
-    if dt < 8.0 and not args.cpu_chains:
+    if dt < 8.0 and not args.cpu_chains and WORKLOAD != "logit":
         chains = int(min(args.chains, max(chains, chains * 15.0 / max(dt, 1e-3)) // cores * cores))
         evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
         rate = evals / dt
     return {
         "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": "%d of the %d chains, same burn_in/draws, float32, OpenMP over chains (%d threads); "
-                  "%.3g grad-evals in %.1f s" % (chains, args.chains, cores, evals, dt),
+        "sample": "%d of the %d chains, %s, float32, OpenMP over chains (%d threads); "
+                  "%.3g grad-evals in %.1f s" % (chains, args.chains,
+                                                 "2 + 2 transitions" if WORKLOAD == "logit" else "same burn_in/draws",
+                                                 cores, evals, dt),
     }
 
 
@@ -157,8 +205,8 @@ def run_reference(args):
     pm4_oracle.build()
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    chains = args.cpu_chains or 2 * cores
-    for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU code
+    chains = args.cpu_chains or (cores if WORKLOAD == "logit" else 2 * cores)
+    for _ in range((max(args.warmup, 0) and 1) if WORKLOAD != "logit" else 0):  # one short warm-up pass is enough for a CPU code
         cpu_sample_rate(ir, args, cores, args.seed + 1)
     evals, secs = 0.0, 0.0
     for k in range(args.steps):
@@ -173,9 +221,9 @@ def run_reference(args):
         "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "each step = %d of the %d chains per GPU, same burn_in/draws; TFP-semantics CPU oracle "
+            "sample": "each step = %d of the %d chains per GPU, %s; TFP-semantics CPU oracle "
                       "(the reference's TF/TFP stack is not installable in this image), OpenMP over chains" %
-                      (chains, args.chains),
+                      (chains, args.chains, "2 + 2 transitions" if WORKLOAD == "logit" else "same burn_in/draws"),
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -291,7 +339,7 @@ def run_b200(args):
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
     comm = None
-    if world > 1 and args.eps_mode == "pooled":
+    if world > 1 and args.eps_mode == "pooled" and args.workload != "logit":
         # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
         # of the chains of ALL ranks (mailboxes in peer memory, read over NVLink by the dual-averaging kernel)
         comm = _cabi.Communicator(local_rank, rank, world)
@@ -299,10 +347,28 @@ def run_b200(args):
     adapt = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
                        num_adaptation_steps=B)
 
+    is_logit = args.workload == "logit"
+
     def cfg_for(step):
+        if is_logit:
+            from pymc4_b200._cstructs import make_hmc_cfg
+
+            return make_hmc_cfg(C, S, B, step_size=args.step_size, num_leapfrog_steps=args.leapfrogs,
+                                seed=args.seed + step, adapt=adapt, chain_offset=rank * C)
         return make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + step, adapt=adapt,
                              max_tree_depth=args.max_tree_depth,
                              warps_per_block=args.warps_per_block, chain_offset=rank * C)
+
+    def run_step(cfg):
+        if not is_logit:
+            return dm.nuts(cfg, theta0, dtype=np.float32)
+        o = dm.hmc(cfg, theta0, dtype=np.float32)
+        # every chain takes exactly L gradient evaluations per transition
+        o["total_leapfrogs"] = torch.full((C,), (B + S) * args.leapfrogs, dtype=torch.int64, device=dev)
+        o["leapfrogs"] = torch.full((S, C), args.leapfrogs, dtype=torch.int32, device=dev)
+        o["diverging"] = torch.zeros((S, C), dtype=torch.uint8, device=dev)
+        o["log_accept"] = o["log_accept"].clamp(max=0.0)
+        return o
 
     theta0 = torch.zeros((C, ir.D), dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -314,7 +380,7 @@ def run_b200(args):
 
     # ---- device-resident arm: inputs already in HBM ------------------------------------
     for w in range(args.warmup):
-        out = dm.nuts(cfg_for(1000 + w), theta0, dtype=np.float32)
+        out = run_step(cfg_for(1000 + w))
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -330,7 +396,7 @@ def run_b200(args):
             barrier()  # coupled ranks start a step together (a rank waits for its peers inside the step)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = dm.nuts(cfg_for(k), theta0, dtype=np.float32)
+        out = run_step(cfg_for(k))
         e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -359,6 +425,8 @@ def run_b200(args):
 
     # ---- diagnostics on the last step (all-gather of the monitored columns over NCCL) ---
     cols = [0, 1, 2, 2 + N_GROUPS, ir.D - 3, ir.D - 2, ir.D - 1]  # mu_a, mu_b, alpha[0], beta[0], log sigmas, log eps
+    if is_logit:
+        cols = [0, 1, 2, ir.D // 2, ir.D - 2, ir.D - 1]  # mu, beta[0], beta[1], beta[mid], beta[last], log tau
     summ = diagnostics.summarize(out["states"], columns=cols)
     ess_per_sec = summ["min_ess"] / (dev_secs_max / max(args.steps, 1))
     mean_accept = float(torch.exp(out["log_accept"]).mean().item())
@@ -370,7 +438,14 @@ def run_b200(args):
     if not args.no_e2e:
         step_arr = np.full((C, 1), args.step_size, dtype=np.float32) if args.eps_mode == "per-chain" else args.step_size
         extra = {"comm": comm} if comm is not None else {}
-        nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C, **extra)
+        if is_logit:
+            from pymc4_b200.mcmc.samplers import HMC
+
+            nuts = HMC(model, step_size=step_arr, num_leapfrog_steps=args.leapfrogs, num_adaptation_steps=B,
+                       device=local_rank, chain_offset=rank * C)
+        else:
+            nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C,
+                        **extra)
         e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
         n_e2e = max(1, min(args.steps, 2))
         for k in range(1 + n_e2e):  # first pass untimed (allocator / pinned-buffer warm-up)
@@ -383,7 +458,8 @@ def run_b200(args):
             if k == 0:
                 continue
             e2e_secs += dt
-            e2e_leaps += float(nuts.last_run_info["total_leapfrogs"].sum().item())
+            e2e_leaps += (float(C * (B + S) * args.leapfrogs) if is_logit
+                          else float(nuts.last_run_info["total_leapfrogs"].sum().item()))
             h2d = C * ir.D * 4 + ir.dataf.size * 4 + ir.datai.size * 4
             d2h = sum(v.nbytes for v in trace.posterior.values()) + sum(v.nbytes for v in trace.sample_stats.values())
         te = torch.tensor([e2e_secs, e2e_leaps], dtype=torch.float64, device=dev)
@@ -436,6 +512,37 @@ def run_b200(args):
                     "fp32": {"achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s"},
                     "l2_records": {"achieved": ach_smem_tbs, "unit": "TB/s",
                                    "note": "observation records (12 N bytes per unit) stream from L2, not shared memory"}}
+    if is_logit:
+        # the dense likelihood is GEMM-shaped: 4 N P useful flops per gradient evaluation (X beta and
+        # X^T r).  The kernels issue them as 3xTF32 (three tensor-core passes per product, TF32 at half the bf16
+        # rate), so the fraction against the measured bf16 peak is bounded by 1/6 for FP32-accurate results.
+        tpeak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ma = torch.randn(8192, 8192, device=dev)
+        mb = torch.randn(8192, 8192, device=dev)
+        for _ in range(2):
+            ma @ mb
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ma @ mb
+        e1.record()
+        torch.cuda.synchronize()
+        tf32_peak = 10 * 2 * 8192.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "achieved": ach_tflops, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": (ach_tflops / tpeak) if tpeak else None, "traffic": None,
+            "kernel": "glm_eta_kernel + glm_grad_kernel (tcgen05.mma kind::tf32, TMEM accumulators), 2 launches per "
+                      "lock-step gradient evaluation of all chains; time base = the whole step",
+            "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
+            "peak_source": peaks_src + " bf16 sustained",
+            "tf32": {"issued_tflops": 3.0 * ach_tflops, "cublas_tf32_peak_tflops": tf32_peak,
+                     "frac_of_tf32_issued": 3.0 * ach_tflops / tf32_peak,
+                     "note": "3xTF32 split: hi*hi + lo*hi + hi*lo keeps ~22 mantissa bits; cuBLAS TF32 8192^3 timed live"},
+            "hbm": {"achieved_gbs": units_per_step_gpu / C * 2.0 * 4.0 * N_OBS * LOGIT_P / kernel_secs / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"),
+                    "note": "X read twice per lock-step leapfrog for all chains together"},
+        }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_secs_max / max(args.steps, 1),
@@ -459,7 +566,15 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    select_workload(args.workload)
+    select_workload(args.workload, args.logit_n)
+    if args.workload == "logit":
+        # bounded defaults for the dense workload (one batched leapfrog of 1024 chains reads the 400 MB matrix twice)
+        if args.chains == CHAINS_PER_GPU:
+            args.chains = 1024
+        if args.burn_in == 1000 and args.draws == 1000:
+            args.burn_in, args.draws = 10, 10
+        if args.step_size == 0.1:
+            args.step_size = 0.002
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -74,6 +74,7 @@ struct pm4_model {
   void* glm_work = nullptr;
   size_t glm_work_bytes = 0;
   int* d_glm_err = nullptr;
+  int* h_flag = nullptr;  // pinned: chains still growing their tree (lock-step NUTS)
   int D = 0, n_terms = 0, n_ops = 0, n_dets = 0, det_row = 0;
   int64_t n_dataf = 0, n_datai = 0;
   std::vector<double> dataf;
@@ -331,6 +332,7 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
   cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
   for (GlmTerm& g : m->glm) cudaFree(g.d_xt);
   cudaFree(m->glm_work); cudaFree(m->d_glm_err);
+  if (m->h_flag) cudaFreeHost(m->h_flag);
   if (m->module) dlclose(m->module);
   delete m;
   return PM4_OK;
@@ -516,6 +518,83 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
 }
 }  // namespace
 
+// Lock-step NUTS for models with dense GLM terms (csrc/pm4_lockstep.cuh): one batched gradient per
+// lock-step leapfrog for every chain whose tree is still growing -- the reference's execution model
+// (tfp NoUTurnSampler under tf.vectorized_map: every chain pays for the deepest tree of the transition).
+static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
+                         const void* step_scale_dev, const void* momenta_dev, void* states_dev, void* lp_dev,
+                         int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev, void* log_accept_dev,
+                         int32_t* depth_dev, void* step_size_dev, int64_t* total_leapfrogs_dev, cudaStream_t st) {
+  if (dtype != PM4_F32) return fail(PM4_ENOSYS, "the lock-step GLM path is float32 only");
+  if (m->comm && m->comm->world > 1) return fail(PM4_ENOSYS, "cross-GPU pooled step sizes are not built for the lock-step path");
+  const int C = cfg->C, D = m->D, T = cfg->num_burnin + cfg->num_results;
+  const size_t CD = (size_t)C * D;
+  int rc;
+  pm4_mod_run_t r;  // only what fill_adapt and the pooled dual-averaging kernel read
+  memset(&r, 0, sizeof r);
+  r.C = C;
+  if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  RunBuffers buf(st);
+  pm4ls::NutsParams p;
+  memset(&p, 0, sizeof p);
+  p.max_depth = cfg->max_tree_depth;
+  p.ns = pm4ls::NS_MEM + 2 * (cfg->max_tree_depth + 1);
+  p.max_energy_diff = (float)cfg->max_energy_diff;
+  void* q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.h.th = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.h.g = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.thb = (float*)q;
+  if ((rc = buf.get(&q, CD * 4))) return rc; p.gb = (float*)q;
+  if ((rc = buf.get(&q, CD * 4 * (size_t)p.ns))) return rc; p.slots = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * sizeof(pm4ls::NutsChain)))) return rc; p.cs = (pm4ls::NutsChain*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.h.lp = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.lpb = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 16))) return rc; p.h.da = (float*)q;
+  if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.h.accept = (float*)q;
+  if ((rc = buf.get(&q, 16))) return rc; p.active = (int*)q;
+  p.h.C = C; p.h.D = D; p.h.B = cfg->num_burnin; p.h.S = cfg->num_results;
+  p.h.chain_offset = cfg->chain_offset;
+  p.h.adapt_enabled = r.adapt_enabled; p.h.adapt_pooled = r.adapt_pooled; p.h.adapt_kind = r.adapt_kind; p.h.num_adapt = r.num_adapt;
+  p.h.target_accept = (float)r.target_accept; p.h.shrinkage = (float)r.shrinkage; p.h.smoothing = (float)r.smoothing;
+  p.h.decay = (float)r.decay; p.h.adapt_rate = (float)r.adapt_rate;
+  p.h.seed_lo = (uint32_t)cfg->seed; p.h.seed_hi = (uint32_t)(cfg->seed >> 32);
+  p.h.step_scale = (const float*)step_scale_dev; p.h.momenta = (const float*)momenta_dev;
+  p.h.states = (float*)states_dev; p.h.lp_out = (float*)lp_dev; p.h.log_accept = (float*)log_accept_dev;
+  p.leapfrogs = leapfrogs_dev; p.diverging = diverging_dev; p.energy = (float*)energy_dev; p.depth_out = depth_dev;
+  p.total_leapfrogs = (long long*)total_leapfrogs_dev;
+  r.da = p.h.da; r.accept = p.h.accept;
+  if (!m->h_flag) CU(cudaMallocHost((void**)&m->h_flag, sizeof(int)));
+  pm4_mod_args_t a = m->args(dtype);
+  auto full_grad = [&](const float* th, float* lp, float* g) -> int {
+    MOD(m->f_logp(dtype, &a, C, th, lp, g, st), "logp_grad (lock-step)");
+    return add_glm(m, dtype, C, th, lp, g, st);
+  };
+  const unsigned warp_grid = (unsigned)((C + 7) / 8);
+  CU(cudaMemcpyAsync(p.h.th, theta0_dev, CD * 4, cudaMemcpyDeviceToDevice, st));
+  if (total_leapfrogs_dev) CU(cudaMemsetAsync(total_leapfrogs_dev, 0, sizeof(int64_t) * (size_t)C, st));
+  if ((rc = full_grad(p.h.th, p.h.lp, p.h.g))) return rc;
+  pm4ls::init_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(p.h, (float)cfg->step_size);
+  for (int t = 0; t < T; ++t) {
+    p.h.t = t;
+    pm4ls::nuts_begin_kernel<<<warp_grid, 256, 0, st>>>(p);
+    g_launches += 2;
+    for (;;) {
+      if ((rc = full_grad(p.thb, p.lpb, p.gb))) return rc;
+      CU(cudaMemsetAsync(p.active, 0, sizeof(int), st));
+      pm4ls::nuts_advance_kernel<<<warp_grid, 256, 0, st>>>(p);
+      g_launches += 1;
+      CU(cudaMemcpyAsync(m->h_flag, p.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (*m->h_flag == 0) break;
+    }
+    pm4ls::nuts_finish_kernel<<<warp_grid, 256, 0, st>>>(p);
+    if (p.h.adapt_enabled && p.h.adapt_pooled) MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");
+  }
+  CU(cudaGetLastError());
+  if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
+  return check_glm(m, st);
+}
+
 extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
                             const void* step_scale_dev, const void* momenta_dev, void* states_dev, void* lp_dev,
                             int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev, void* log_accept_dev,
@@ -523,14 +602,14 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_nuts_run: null argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
-  if (!m->glm.empty())
-    return fail(PM4_ENOSYS, "models with a dense GLM likelihood run on the lock-step path: use pm4_hmc_run "
-                            "(sampler_type=\"hmc\"); a lock-step NUTS is not built");
   if (cfg->C <= 0 || cfg->num_results < 0 || cfg->num_burnin < 0) return fail(PM4_EINVAL, "pm4_nuts_run: bad chain/draw counts");
   if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 20) return fail(PM4_EINVAL, "max_tree_depth must be in [1, 20]");
   if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
   CU(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (!m->glm.empty())
+    return nuts_lockstep(m, dtype, cfg, theta0_dev, step_scale_dev, momenta_dev, states_dev, lp_dev, leapfrogs_dev,
+                         diverging_dev, energy_dev, log_accept_dev, depth_dev, step_size_dev, total_leapfrogs_dev, st);
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
   const int T = cfg->num_burnin + cfg->num_results;
 

@@ -480,5 +480,39 @@ def test_dense_glm_lockstep_hmc_parity(oracle_mod):
         assert np.mean(acc == racc) > 0.8 and abs(acc.mean() - racc.mean()) < 0.1
         np.testing.assert_allclose(np.median(out["step_size"].cpu().numpy()), np.median(ref["step_size"]), rtol=0.25)
         np.testing.assert_allclose(out["states"].cpu().numpy().mean((0, 1)), ref["states"].mean((0, 1)), atol=0.15)
-    with pytest.raises(RuntimeError, match="lock-step"):
-        _dm(ir).nuts(make_nuts_cfg(C, 2, 2), np.zeros((C, D), np.float32), dtype=np.float32)
+
+
+def test_dense_glm_lockstep_nuts_parity(oracle_mod):
+    """NUTS on the GLM path runs in lock-step over the chains (one batched gradient per leapfrog); same Philox
+    streams and the same tree arithmetic as the oracle: the first transitions replay exactly (integer tree
+    statistics), later ones agree in distribution (one flipped comparison sends a chain down another path)."""
+    X, y = M.logistic_glm_data(n=2000, p=20)
+    ir, _, _ = lower_model(M.logistic_glm_model(X, y))
+    C, D = 48, ir.D
+    rng = np.random.default_rng(63)
+    theta0 = rng.normal(0, 0.2, (C, D))
+    # fixed step size, two transitions: trees are replayed leaf for leaf
+    cfg = make_nuts_cfg(C, 2, 0, step_size=0.02, seed=5, adapt=make_adapt(enabled=False), max_tree_depth=6)
+    ref = oracle_mod.Oracle(ir).nuts(cfg, theta0, dtype=np.float32)
+    out = _dm(ir).nuts(cfg, theta0.astype(np.float32), dtype=np.float32)
+    lf, rlf = out["leapfrogs"].cpu().numpy(), ref["leapfrogs"]
+    assert np.mean(lf[0] == rlf[0]) > 0.9 and np.mean(lf == rlf) > 0.8
+    same = lf[0] == rlf[0]
+    assert np.array_equal(out["depth"].cpu().numpy()[0][same], ref["depth"][0][same])
+    assert np.array_equal(out["diverging"].cpu().numpy()[0][same], ref["diverging"][0][same])
+    d0 = np.abs(out["states"].cpu().numpy()[0] - ref["states"][0]).max(axis=1)
+    assert np.median(d0[same]) < 1e-4
+    np.testing.assert_allclose(out["energy"].cpu().numpy()[0][same], ref["energy"][0][same], rtol=1e-3, atol=1e-2)
+    assert np.array_equal(out["total_leapfrogs"].cpu().numpy(), lf.sum(0))
+    # adaptive runs, pooled and per-chain: same regime as the oracle
+    B, S = 40, 30
+    for mode in (PM4_EPS_POOLED, PM4_EPS_PER_CHAIN):
+        cfg = make_nuts_cfg(C, S, B, step_size=0.02, seed=9, adapt=make_adapt(mode=mode, num_adaptation_steps=B),
+                            max_tree_depth=6)
+        ref = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(D), dtype=np.float32)
+        out = _dm(ir).nuts(cfg, np.zeros((C, D), np.float32), dtype=np.float32)
+        np.testing.assert_allclose(np.median(out["step_size"].cpu().numpy()), np.median(ref["step_size"]), rtol=0.25)
+        np.testing.assert_allclose(out["leapfrogs"].cpu().numpy().mean(), ref["leapfrogs"].mean(), rtol=0.25)
+        np.testing.assert_allclose(np.exp(out["log_accept"].cpu().numpy()).mean(), np.exp(ref["log_accept"]).mean(), atol=0.08)
+        np.testing.assert_allclose(out["states"].cpu().numpy().mean((0, 1)), ref["states"].mean((0, 1)), atol=0.15)
+        assert out["diverging"].cpu().numpy().mean() < 0.05

@@ -189,6 +189,21 @@ def test_sample_prior_predictive():
         pm.sample_prior_predictive(M.schools_pm4(), var_names=["schools_pm4/nope"])
 
 
+def test_sample_dense_logistic_regression_default_nuts():
+    """pm.sample with the default sampler (NUTS) on the dense logistic regression: lock-step trees, every leapfrog
+    one batched tensor-core gradient."""
+    X, y = M.logistic_glm_data(n=3000, p=20)
+    rng = np.random.default_rng(11)
+    rng.standard_normal((3000, 20))
+    beta_true = rng.normal(0, 0.5, 20)
+    trace = pm.sample(M.logistic_glm_model(X, y), num_chains=64, num_samples=100, burn_in=100, step_size=0.02, seed=3)
+    beta = trace.posterior["logistic_glm_model/beta"]
+    assert beta.shape == (64, 100, 20)
+    err = np.abs(beta.mean((0, 1)) - beta_true)
+    assert np.max(err) < 0.25 and np.mean(err) < 0.1
+    assert trace.sample_stats["tree_size"].min() >= 1 and trace.sample_stats["diverging"].mean() < 0.05
+
+
 def test_sample_dense_logistic_regression_with_hmc():
     """pm.sample(..., sampler_type="hmc") on the hierarchical logistic regression with X @ beta: the posterior mean
     of beta recovers the generating coefficients."""
