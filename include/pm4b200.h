@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM4_ABI_VERSION 5
+#define PM4_ABI_VERSION 6
 
 /* error codes */
 #define PM4_OK 0
@@ -77,6 +77,17 @@ typedef struct pm4_rv {
                                        X [n, glm_p] row-major at dataf[glm_x], y at dataf[glm_y], beta = x[glm_base ..]
                                        (evaluated for all chains at once on the tensor cores, csrc/pm4_glm.cu) */
 
+#define PM4_T_MVN_EXPQUAD 7 /* y ~ MvNormal(loc, K) observed, K_ij = a^2 exp(-|X_i - X_j|^2 / (2 l^2)) + (noise + jitter) [i == j]:
+                               the marginal likelihood of GP regression (/root/reference/pymc4/gp/cov.py:399-475,
+                               distributions/multivariate.py:159-199), a dense term with no tape and n = 1 (one density
+                               value per state).  The dense-term fields are reused: glm_base = number of points,
+                               glm_p = feature dimension d, X [points, d] row-major at dataf[glm_x], y - loc at
+                               dataf[glm_y]; dataf[gp_par .. gp_par + 8) = (l_elem, a_elem, noise_elem, l_const, a_const,
+                               noise_const, noise_squared, jitter): *_elem is the position in x (constrained space) of
+                               the scalar free variable, or -1 to use the constant; the diagonal term is
+                               (noise_squared ? v * v : v) + jitter.  Evaluated for all chains at once by batched
+                               float64 Cholesky kernels (csrc/pm4_gp.cu). */
+
 typedef struct pm4_term {
   int32_t kind;        /* PM4_T_*                                       */
   int32_t n;           /* number of elements                            */
@@ -92,6 +103,7 @@ typedef struct pm4_term {
   int32_t glm_p;       /*   number of covariates                                                        */
   int64_t glm_x;       /*   dataf offset of X [n, glm_p]                                                */
   int64_t glm_y;       /*   dataf offset of y [n]                                                       */
+  int64_t gp_par;      /* PM4_T_MVN_EXPQUAD: dataf offset of the 8-double parameter record                */
 } pm4_term_t;
 
 /* Device execution plan of a term that gathers from free variables: its elements regrouped by
@@ -348,6 +360,21 @@ int pm4_model_attach_comm(pm4_model_t* m, pm4_comm_t* comm /* NULL detaches */);
  *   *error_dev (device int, zeroed by the caller) is set when a tensor-core step timed out.
  * pm4_glm_gemm_tile: one 128 x 128 tile C = A B^T of the same MMA path (kernel-level test). */
 int64_t pm4_glm_work_bytes(int n, int P, int C);
+
+/* The marginal GP likelihood (PM4_T_MVN_EXPQUAD; /root/reference/pymc4/gp/cov.py:227-272,399-475, gp/util.py:15-21,
+ * distributions/multivariate.py:159-199) for C chains at once, the building block pm4_logp_grad / pm4_hmc_run /
+ * pm4_nuts_run / pm4_log_likelihood call for such terms (csrc/pm4_gp.cu): per chain the n x n kernel matrix, a
+ * blocked Cholesky factorisation, the inverse factor and the contraction of (alpha alpha^T - K^-1) with dK, all in
+ * float64.  X [n, d] and y [n] (y - loc) are DEVICE doubles; par is the HOST 8-double record described at
+ * PM4_T_MVN_EXPQUAD; tr / shift / scale (HOST, 3 each, may be NULL = identity) are the transforms of the free
+ * variables behind (l, a, noise).  dtype is the type of theta [C, ldt], lp and grad [C, ldg].  lp[c * lp_stride] is
+ * overwritten (accumulate = 0) or added to; grad (may be NULL) is added to.  work: pm4_gp_work_bytes(n, C) bytes.
+ * Returns 0, PM4_EINVAL or a cudaError_t. */
+int64_t pm4_gp_work_bytes(int n, int C);
+int pm4_gp_logp_grad(const double* X, const double* y, int n, int d, const double* par, const int* tr,
+                     const double* shift, const double* scale, int dtype, const void* theta, int ldt, int C, void* lp,
+                     int lp_stride, int accumulate, void* grad, int ldg, void* work, void* stream);
+int pm4_gp_launches(int n, int want_grad);
 int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P, const float* theta,
                       int ldt, int base, int C, float* lp, float* grad, int ldg, void* work, int* error_dev,
                       void* stream);

@@ -192,6 +192,88 @@ static REAL NAME(glm_elem)(const pm4_ir_t* ir, const pm4_term_t* tm, const REAL*
   return NAME(lpdf)(PM4_T_BERNOULLI, yv, q1, &dx, dq);
 }
 
+/* Marginal GP likelihood (PM4_T_MVN_EXPQUAD): y ~ MvNormal(0, K), K_ij = a^2 exp(-|X_i - X_j|^2 / (2 l^2)) +
+ * (noise + jitter) [i == j]  (/root/reference/pymc4/gp/cov.py:399-475 -> tfp ExponentiatedQuadratic.matrix;
+ * distributions/multivariate.py:159-199 -> tfd.MultivariateNormalFullCovariance.log_prob =
+ * -1/2 y^T K^-1 y - sum log diag chol(K) - n/2 log 2 pi).  The gradient with respect to the three scalars is the
+ * reverse-mode result of that expression, 1/2 tr((alpha alpha^T - K^-1) dK/dp) with alpha = K^-1 y.  The term is
+ * factorised in float64 whatever REAL is (as on the device); gx may be NULL.  Returns NAN when K is not
+ * positive definite. */
+static double NAME(gp_term)(const pm4_ir_t* ir, const pm4_term_t* tm, const REAL* x, REAL* gx) {
+  const int n = tm->glm_base, d = tm->glm_p;
+  const double *X = ir->dataf + tm->glm_x, *y = ir->dataf + tm->glm_y, *par = ir->dataf + tm->gp_par;
+  const int el = (int)par[0], ea = (int)par[1], en = (int)par[2], sq = par[6] != 0.0;
+  const double l = el >= 0 ? (double)x[el] : par[3], a = ea >= 0 ? (double)x[ea] : par[4];
+  const double v = en >= 0 ? (double)x[en] : par[5];
+  const double dg = (sq ? v * v : v) + par[7];
+  double* K = (double*)malloc(sizeof(double) * (size_t)n * n);
+  double* Z = gx ? (double*)calloc((size_t)n * n, sizeof(double)) : NULL;
+  double* w = (double*)malloc(sizeof(double) * (size_t)n * 2);
+  double* alpha = w + n;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double d2 = 0;
+      for (int f = 0; f < d; ++f) { const double df = X[(size_t)i * d + f] - X[(size_t)j * d + f]; d2 += df * df; }
+      K[(size_t)i * n + j] = a * a * exp(-d2 / (2.0 * l * l)) + (i == j ? dg : 0.0);
+    }
+  double lp = NAN, logdet = 0;
+  int ok = 1;
+  for (int j = 0; j < n && ok; ++j) { /* Cholesky, lower, in place */
+    double s = K[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) s -= K[(size_t)j * n + k] * K[(size_t)j * n + k];
+    if (!(s > 0)) { ok = 0; break; }
+    const double ljj = sqrt(s);
+    K[(size_t)j * n + j] = ljj;
+    logdet += log(ljj);
+    for (int i = j + 1; i < n; ++i) {
+      double t = K[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) t -= K[(size_t)i * n + k] * K[(size_t)j * n + k];
+      K[(size_t)i * n + j] = t / ljj;
+    }
+  }
+  if (ok) {
+    double quad = 0;
+    for (int i = 0; i < n; ++i) { /* w = L^-1 y */
+      double t = y[i];
+      for (int k = 0; k < i; ++k) t -= K[(size_t)i * n + k] * w[k];
+      w[i] = t / K[(size_t)i * n + i];
+      quad += w[i] * w[i];
+    }
+    lp = -0.5 * quad - logdet - 0.5 * n * 1.8378770664093454835606594728112;
+    if (gx) {
+      for (int j = 0; j < n; ++j) /* Z = L^-1, column by column */
+        for (int i = j; i < n; ++i) {
+          double t = i == j ? 1.0 : 0.0;
+          for (int k = j; k < i; ++k) t -= K[(size_t)i * n + k] * Z[(size_t)k * n + j];
+          Z[(size_t)i * n + j] = t / K[(size_t)i * n + i];
+        }
+      for (int i = 0; i < n; ++i) { /* alpha = L^-T w */
+        double t = 0;
+        for (int k = i; k < n; ++k) t += Z[(size_t)k * n + i] * w[k];
+        alpha[i] = t;
+      }
+      double s1 = 0, s2 = 0, s3 = 0;
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) {
+          double kinv = 0;
+          for (int k = i; k < n; ++k) kinv += Z[(size_t)k * n + i] * Z[(size_t)k * n + j];
+          const double W = alpha[i] * alpha[j] - kinv;
+          double d2 = 0;
+          for (int f = 0; f < d; ++f) { const double df = X[(size_t)i * d + f] - X[(size_t)j * d + f]; d2 += df * df; }
+          const double kse = a * a * exp(-d2 / (2.0 * l * l)), wt = i == j ? 1.0 : 2.0;
+          s1 += wt * W * kse;
+          s2 += wt * W * kse * d2;
+          if (i == j) s3 += W;
+        }
+      if (el >= 0) gx[el] += (REAL)(0.5 * s2 / (l * l * l));
+      if (ea >= 0) gx[ea] += (REAL)(s1 / a);
+      if (en >= 0) gx[en] += (REAL)(0.5 * s3 * (sq ? 2.0 * v : 1.0));
+    }
+  }
+  free(K); free(Z); free(w);
+  return lp;
+}
+
 /* joint log-density and gradient in unconstrained space for ONE chain */
 static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta, REAL* grad) {
   const int D = ir->D;
@@ -203,6 +285,10 @@ static REAL NAME(logp_grad1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* the
   for (int t = 0; t < ir->n_terms; ++t) {
     const pm4_term_t* tm = &ir->terms[t];
     REAL term_sum = 0;
+    if (tm->kind == PM4_T_MVN_EXPQUAD) {
+      lp += (REAL)NAME(gp_term)(ir, tm, x, grad ? gx : NULL);
+      continue;
+    }
     if (tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) {
       /* tfd.Bernoulli(probs=sigmoid(X beta)).log_prob(y), summed: xlogy(y, p) + xlog1py(1 - y, -p) */
       for (int i = 0; i < tm->n; ++i) {
@@ -257,6 +343,10 @@ static void NAME(loglik1)(const pm4_ir_t* ir, NAME(ws_t)* ws, const REAL* theta,
   for (int t = 0; t < ir->n_terms; ++t) {
     const pm4_term_t* tm = &ir->terms[t];
     if (!tm->observed) continue;
+    if (tm->kind == PM4_T_MVN_EXPQUAD) { /* one density value per state */
+      out[tm->ll_offset] = (REAL)NAME(gp_term)(ir, tm, x, NULL);
+      continue;
+    }
     for (int i = 0; i < tm->n; ++i) {
       if (tm->kind == PM4_T_BERNOULLI_LOGIT_GLM) {
         REAL eta, p;
@@ -404,6 +494,7 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
                                     REAL* out) {
   if (!ir || !theta || !out) return PM4_EINVAL;
   for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].kind == PM4_T_MVN_EXPQUAD) return PM4_ENOSYS;
   const int D = ir->D;
   REAL* x = (REAL*)malloc(sizeof(REAL) * (size_t)(D + 1));
   REAL v[PM4O_MAXREG];
@@ -448,6 +539,7 @@ static int NAME(term_defines)(const pm4_ir_t* ir, const pm4_term_t* tm) {
 int NAME(pm4o_prior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint64_t seed, REAL* x_out, REAL* obs_out) {
   if (!ir || !x_out) return PM4_EINVAL;
   for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
+  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].kind == PM4_T_MVN_EXPQUAD) return PM4_ENOSYS;
   const int D = ir->D;
   REAL v[PM4O_MAXREG];
   for (int64_t m = 0; m < M; ++m) {

@@ -8,6 +8,7 @@ from . import distributions
 from . import flow
 from .flow import evaluate_model_transformed, evaluate_model, evaluate_meta_model
 from .distributions import *  # noqa: F401,F403
+from . import gp
 from . import mcmc
 from . import inference
 from .mcmc.utils import initialize_sampling_state, trace_to_arviz

@@ -23,6 +23,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpm4b200.so")
 _CORE_SRC = os.path.join(_HERE, "csrc", "pm4_core.cu")
 _GLM_SRC = os.path.join(_HERE, "csrc", "pm4_glm.cu")
+_GP_SRC = os.path.join(_HERE, "csrc", "pm4_gp.cu")
 _HEADER = os.path.join(_HERE, "..", "include", "pm4b200.h")
 _lock = threading.Lock()
 _lib = None
@@ -34,6 +35,7 @@ EXPORTS = [
     "pm4_last_error", "pm4_abi_version",
     "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
+    "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches",
 ]
 
 
@@ -43,13 +45,13 @@ class BackendUnavailable(RuntimeError):
 
 def build_core(force: bool = False) -> str:
     """Compile libpm4b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
-    deps = [_CORE_SRC, _GLM_SRC, _HEADER, os.path.join(_HERE, "csrc", "pm4_module.h"),
+    deps = [_CORE_SRC, _GLM_SRC, _GP_SRC, _HEADER, os.path.join(_HERE, "csrc", "pm4_module.h"),
             os.path.join(_HERE, "csrc", "pm4_lockstep.cuh"), os.path.join(_HERE, "csrc", "pm4_philox.cuh")]
     with _lock:
         fresh = os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps)
         if fresh and not force:
             return LIB_PATH
-        cmd = [codegen.find_nvcc()] + codegen.NVCC_FLAGS + ["-shared", "-o", LIB_PATH + ".tmp", _CORE_SRC, _GLM_SRC, "-ldl"]
+        cmd = [codegen.find_nvcc()] + codegen.NVCC_FLAGS + ["-shared", "-o", LIB_PATH + ".tmp", _CORE_SRC, _GLM_SRC, _GP_SRC, "-ldl"]
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if proc.returncode != 0:
             raise BackendUnavailable("nvcc failed building libpm4b200.so:\n" + proc.stdout[-4000:])

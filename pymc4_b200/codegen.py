@@ -181,6 +181,10 @@ class _ModuleGen:
         self.lines = body
         op0, plan_idx = 0, 0
         for k, t in enumerate(self.ir.terms):
+            if t.gp is not None:
+                # marginal GP likelihood: batched float64 Cholesky kernels (csrc/pm4_gp.cu) after this per-chain pass
+                body.append("    // ---- term %d: %s (mvn_expquad) -- batched dense path" % (k, t.label))
+                continue
             if t.glm is not None:
                 # dense Bernoulli-logit term: evaluated for all chains at once on the tensor cores
                 # (csrc/pm4_glm.cu, added by libpm4b200 after this per-chain pass); nothing to emit here
@@ -590,6 +594,11 @@ class _ModuleGen:
             if not t.observed:
                 op0 += len(t.ops)
                 continue
+            if t.gp is not None:
+                # one density value per state, produced by the batched path (libpm4b200 refuses these entry points
+                # for GP models until it routes them there)
+                out.append("    // ---- observed term %d: %s (mvn_expquad): not evaluated per state" % (k, t.label))
+                continue
             if t.glm is not None:
                 g = t.glm
                 out.append("    // ---- observed term %d: %s (bernoulli_logit_glm): eta = X[i, :] . beta" % (k, t.label))
@@ -747,7 +756,7 @@ class _ModuleGen:
             out.append("    }")
 
         for k, t in enumerate(self.ir.terms):
-            if t.glm is not None:
+            if t.glm is not None or t.gp is not None:
                 continue
             vo = t.ops[t.value_reg]
             if (not t.observed and t.kind != I.TERM_KINDS["potential"] and vo.opcode == ld_x
@@ -756,6 +765,8 @@ class _ModuleGen:
         for k, t in enumerate(self.ir.terms):
             if t.observed and t.glm is not None:
                 emit_glm(k, t)
+            elif t.gp is not None:
+                continue
             elif t.observed:
                 emit(k, t, "obs")
         out.append("  }")

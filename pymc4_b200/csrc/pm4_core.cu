@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -67,10 +68,23 @@ struct GlmTerm {
   float* d_xt = nullptr;  // [P, ldxt]
 };
 
+// a marginal GP likelihood term (PM4_T_MVN_EXPQUAD): pool offsets + how its three scalars are read from theta
+struct GpTerm {
+  int n = 0, d = 0, ll_offset = 0;
+  int64_t x_off = 0, y_off = 0;
+  double par[8] = {0};
+  int tr[3] = {0, 0, 0};
+  double shift[3] = {0, 0, 0}, scale[3] = {1, 1, 1};
+};
+
 struct pm4_model {
   int device = 0;
   pm4_comm* comm = nullptr;
   std::vector<GlmTerm> glm;
+  std::vector<GpTerm> gp;
+  void* gp_work = nullptr;
+  size_t gp_work_bytes = 0;
+  bool lockstep() const { return !glm.empty() || !gp.empty(); }
   void* glm_work = nullptr;
   size_t glm_work_bytes = 0;
   int* d_glm_err = nullptr;
@@ -168,8 +182,48 @@ static int upload_glm(pm4_model* m, const double* dataf) {
   return PM4_OK;
 }
 
+// add the GP terms for C chains: batched float64 Cholesky kernels (csrc/pm4_gp.cu), chains in chunks that fit
+// the workspace (2 n^2 doubles per chain)
+static int add_gp(pm4_model* m, int dtype, int C, const void* theta, void* lp, int lp_stride, bool accumulate, void* grad,
+                  cudaStream_t st) {
+  const size_t rs = dtype == PM4_F64 ? 8 : 4;
+  for (const GpTerm& g : m->gp) {
+    const size_t per_chain = (size_t)pm4_gp_work_bytes(g.n, 1);
+    if (m->gp_work_bytes < per_chain * (size_t)std::min(C, 8)) {
+      CU(cudaStreamSynchronize(st));
+      if (m->gp_work) CU(cudaFree(m->gp_work));
+      m->gp_work = nullptr; m->gp_work_bytes = 0;
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      size_t want = per_chain * (size_t)C, cap = free_b / 10 * 6;
+      if (const char* e = getenv("PM4_GP_WORK_MB")) cap = (size_t)atoll(e) << 20;
+      if (want > cap) want = cap / per_chain * per_chain;
+      if (want < per_chain) return fail(PM4_ENOMEM, "GP term with %d points needs %zu bytes of workspace per chain, %zu are free", g.n, per_chain, free_b);
+      cudaError_t e = cudaMalloc(&m->gp_work, want);
+      if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GP factorisations: %s", want, cudaGetErrorString(e));
+      m->gp_work_bytes = want;
+    }
+    const int chunk = (int)std::min<size_t>((size_t)C, m->gp_work_bytes / per_chain);
+    for (int c0 = 0; c0 < C; c0 += chunk) {
+      const int cc = std::min(chunk, C - c0);
+      int rc = pm4_gp_logp_grad(m->d_f64 + g.x_off, m->d_f64 + g.y_off, g.n, g.d, g.par, g.tr, g.shift, g.scale, dtype,
+                                (const char*)theta + (size_t)c0 * m->D * rs, m->D, cc,
+                                (char*)lp + ((size_t)c0 * lp_stride + (accumulate ? 0 : (size_t)g.ll_offset)) * rs, lp_stride,
+                                accumulate ? 1 : 0,
+                                grad ? (char*)grad + (size_t)c0 * m->D * rs : nullptr, m->D, m->gp_work, st);
+      g_launches += pm4_gp_launches(g.n, grad ? 1 : 0);
+      if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GP kernels: %s", rc < 0 ? "bad argument" : cudaGetErrorString((cudaError_t)rc));
+    }
+  }
+  return PM4_OK;
+}
+
 // add the dense terms' log-likelihood and gradient for C chains (theta [C, D] -> lp [C], grad [C, D] or NULL)
 static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
+  if (!m->gp.empty()) {
+    int rc = add_gp(m, dtype, C, theta, lp, 1, true, grad, st);
+    if (rc) return rc;
+  }
   if (m->glm.empty()) return PM4_OK;
   if (dtype != PM4_F32) return fail(PM4_ENOSYS, "dense GLM terms are evaluated in 3xTF32 on the tensor cores: float32 only");
   for (const GlmTerm& g : m->glm) {
@@ -307,6 +361,31 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
       g.ldxt = (tm.n + 3) / 4 * 4;
       m->glm.push_back(g);
     }
+    for (int t = 0; t < ir->n_terms; ++t) {
+      const pm4_term_t& tm = ir->terms[t];
+      if (tm.kind != PM4_T_MVN_EXPQUAD) continue;
+      const int n = tm.glm_base, d = tm.glm_p;
+      if (n <= 0 || d <= 0 || tm.glm_x < 0 || tm.glm_x + (int64_t)n * d > ir->n_dataf || tm.glm_y < 0 ||
+          tm.glm_y + n > ir->n_dataf || tm.gp_par < 0 || tm.gp_par + 8 > ir->n_dataf)
+        return fail(PM4_EINVAL, "GP term %d points outside the data pool", t);
+      GpTerm g;
+      g.n = n; g.d = d; g.ll_offset = tm.ll_offset; g.x_off = tm.glm_x; g.y_off = tm.glm_y;
+      for (int k = 0; k < 8; ++k) g.par[k] = ir->dataf[tm.gp_par + k];
+      for (int k = 0; k < 3; ++k) {
+        const int e = (int)g.par[k];
+        if (e < 0) continue;
+        bool found = false;
+        for (int r = 0; r < ir->n_rv && !found; ++r) {
+          const pm4_rv_t& rv = ir->rvs[r];
+          if (e >= rv.offset && e < rv.offset + rv.size) {
+            g.tr[k] = rv.transform; g.shift[k] = rv.shift; g.scale[k] = rv.scale;
+            found = true;
+          }
+        }
+        if (!found) return fail(PM4_EINVAL, "GP term %d: parameter %d is not a position of theta", t, k);
+      }
+      m->gp.push_back(g);
+    }
     if (!m->glm.empty()) {
       CU(cudaMalloc((void**)&m->d_glm_err, sizeof(int)));
       CU(cudaMemset(m->d_glm_err, 0, sizeof(int)));
@@ -331,7 +410,7 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
   cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_datai); cudaFree(m->d_term_n); cudaFree(m->d_op_blob);
   cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
   for (GlmTerm& g : m->glm) cudaFree(g.d_xt);
-  cudaFree(m->glm_work); cudaFree(m->d_glm_err);
+  cudaFree(m->glm_work); cudaFree(m->d_glm_err); cudaFree(m->gp_work);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   if (m->module) dlclose(m->module);
   delete m;
@@ -374,7 +453,7 @@ extern "C" int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_logp(dtype, &a, C, theta_dev, lp_dev, grad_dev, stream), "logp_grad");
-  if (!m->glm.empty()) {
+  if (m->lockstep()) {
     if ((rc = add_glm(m, dtype, C, theta_dev, lp_dev, grad_dev, (cudaStream_t)stream))) return rc;
     return check_glm(m, (cudaStream_t)stream);
   }
@@ -404,6 +483,10 @@ extern "C" int pm4_log_likelihood(pm4_model_t* m, int dtype, int64_t M, const vo
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_loglik(dtype, &a, M, theta_dev, out_dev, stream), "log_likelihood");
+  if (!m->gp.empty()) {  // one density value per state, written at the term's position of the row
+    if (M > 0x7fffffff) return fail(PM4_EINVAL, "pm4_log_likelihood: too many states for a GP model");
+    return add_gp(m, dtype, (int)M, theta_dev, out_dev, m->info.ll_row, false, nullptr, (cudaStream_t)stream);
+  }
   return PM4_OK;
 }
 
@@ -414,6 +497,7 @@ extern "C" int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, co
   if (rc) return rc;
   if (M == 0 || m->info.ll_row == 0) return PM4_OK;
   if (!theta_dev || !out_dev) return fail(PM4_EINVAL, "pm4_posterior_predictive: null buffer");
+  if (!m->gp.empty()) return fail(PM4_ENOSYS, "forward sampling of MvNormal (GP) observations is not built");
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_predict(dtype, &a, M, theta_dev, out_dev, seed, stream), "posterior_predictive");
@@ -427,6 +511,7 @@ extern "C" int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64
   if (rc) return rc;
   if (M == 0) return PM4_OK;
   if (!x_dev) return fail(PM4_EINVAL, "pm4_prior_predictive: null buffer");
+  if (!m->gp.empty() && obs_dev) return fail(PM4_ENOSYS, "forward sampling of MvNormal (GP) observations is not built");
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_prior(dtype, &a, M, x_dev, obs_dev, seed, stream), "prior_predictive");
@@ -607,7 +692,7 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   if (!(cfg->step_size > 0)) return fail(PM4_EINVAL, "step_size must be positive");
   CU(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!m->glm.empty())
+  if (m->lockstep())
     return nuts_lockstep(m, dtype, cfg, theta0_dev, step_scale_dev, momenta_dev, states_dev, lp_dev, leapfrogs_dev,
                          diverging_dev, energy_dev, log_accept_dev, depth_dev, step_size_dev, total_leapfrogs_dev, st);
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;
@@ -734,7 +819,7 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   if (rw && !(cfg->rw_scale > 0)) return fail(PM4_EINVAL, "rw_scale must be positive");
   CU(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!m->glm.empty())
+  if (m->lockstep())
     return hmc_lockstep(m, dtype, cfg, theta0_dev, step_scale_dev, momenta_dev, uniforms_dev, states_dev, lp_dev,
                         log_accept_dev, accepted_dev, step_size_dev, traj_dev, st);
   const size_t rs = real_size(dtype), C = (size_t)cfg->C, DP = (size_t)m->info.DP;

@@ -29,7 +29,7 @@ from . import symbolic as sym
 from .coroutine_model import Model
 from .utils import NameParts
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 TR_IDENTITY, TR_EXP, TR_SIGMOID = 0, 1, 2
 
@@ -41,6 +41,7 @@ TERM_KINDS = {
     "bernoulli": 4,
     "poisson": 5,
     "bernoulli_logit_glm": 6,
+    "mvn_expquad": 7,
 }
 TERM_NPARAMS = {0: 0, 1: 2, 2: 1, 3: 1, 4: 1, 5: 1, 6: 0}
 
@@ -94,6 +95,7 @@ class Term:
     label: str = ""
     plan: Optional["Plan"] = None
     glm: Optional["GLM"] = None     # dense Bernoulli-logit term (no tape): see GLM
+    gp: Optional["GP"] = None       # marginal GP likelihood (no tape): see GP
     observed: bool = False          # density of an observed variable (enters the pointwise log-likelihood)
     ll_offset: int = 0              # position of element 0 in one state's log-likelihood row
     shape: Tuple[int, ...] = ()     # broadcast shape of the term's elements
@@ -113,6 +115,24 @@ class GLM:
     y_blob: int      # dataf offset of y [n]
     base: int        # theta offset of beta[0]
     P: int
+
+
+@dataclass
+class GP:
+    """``MvNormal(loc, ExpQuad(l, a)(X, X) + noise I)`` observed: the marginal likelihood of GP regression
+    (BASELINE configs[3]).  Like the GLM term it has no element-wise tape; the device evaluates it for all
+    chains at once with batched float64 Cholesky kernels (csrc/pm4_gp.cu), the oracle with plain loops.
+
+    ``par_blob`` points at 8 doubles in dataf: (l_elem, a_elem, noise_elem, l_const, a_const, noise_const,
+    noise_squared, jitter).  ``*_elem`` is the position in x (constrained space) of the scalar free variable
+    the parameter is, or -1 when it is the constant next to it; the diagonal added to the kernel matrix is
+    ``(noise_squared ? v * v : v) + jitter`` with v the noise parameter."""
+    x_blob: int      # dataf offset of X, row-major [n, d]
+    y_blob: int      # dataf offset of y - loc [n]
+    par_blob: int
+    n: int
+    d: int
+    elems: Tuple[int, int, int] = (-1, -1, -1)
 
 
 @dataclass
@@ -189,6 +209,15 @@ class ModelIR:
         return [t for t in self.terms if t.glm is not None]
 
     @property
+    def gp_terms(self) -> List["Term"]:
+        return [t for t in self.terms if t.gp is not None]
+
+    @property
+    def lockstep(self) -> bool:
+        """Models with a dense term run in lock-step over the chain axis (csrc/pm4_lockstep.cuh)."""
+        return any(t.glm is not None or t.gp is not None for t in self.terms)
+
+    @property
     def streamed(self) -> bool:
         """Plan pools too large to stage in shared memory (the device reads them from L2): the generated row
         loops prefetch."""
@@ -216,6 +245,8 @@ class ModelIR:
             h.append(struct.pack("<iii?", t.kind, t.value_reg, len(t.ops), t.observed))
             if t.glm is not None:
                 h.append(struct.pack("<qqii", t.glm.x_blob, t.glm.y_blob, t.glm.base, t.glm.P))
+            if t.gp is not None:
+                h.append(struct.pack("<qqqii", t.gp.x_blob, t.gp.y_blob, t.gp.par_blob, t.gp.n, t.gp.d))
             h.append(struct.pack("<%di" % len(t.param_regs), *t.param_regs))
             ops_key(t.ops, t.n)
             if t.plan is not None:
@@ -420,10 +451,97 @@ def _match_glm(kind: str, value, params: List[Any], rvs, pools, label: str) -> O
                 shape=(int(n),), glm=GLM(x_blob=x_blob, y_blob=y_blob, base=rv.offset, P=int(P)))
 
 
+def _scalar_param(e: "sym.Expr", rvs) -> Optional[Tuple[int, float]]:
+    """(position in x, 0) for a scalar view of a free variable, (-1, value) for a constant, else None."""
+    if e.op == "reshape" and e.size == 1:
+        e = e.args[0]
+    if e.size != 1:
+        return None
+    if e.op == "const":
+        return -1, float(np.asarray(e.data).reshape(-1)[0])
+    if e.op == "view" and e.space == "x":
+        return int(rvs[e.rv].offset + int(np.asarray(e.index).reshape(-1)[0])), 0.0
+    return None
+
+
+def _match_gp(kind: str, value, params: List[Any], rvs, pools, label: str) -> Optional[Term]:
+    """MvNormal(loc, expquad(l, a; X, X) + noise * I [+ jitter * I]) with a constant value and loc -> GP term."""
+    if kind != "mvn":
+        return None
+    why = ("MvNormal runs on the device as the marginal likelihood of GP regression: an observed vector, a constant "
+           "loc, covariance_matrix = ExpQuad(l, a)(X, X) + noise * np.eye(n) with l, a, noise scalars (free variables "
+           "or constants; noise may be sigma or sigma ** 2)")
+    loc, cov, v = sym.as_expr(params[0]), sym.as_expr(params[1]), sym.as_expr(value)
+    if v.op != "const" or loc.op != "const":
+        raise NotImplementedError(why)
+    # flatten the sum
+    addends, stack = [], [cov]
+    while stack:
+        e = stack.pop()
+        if e.op == "add":
+            stack.extend(e.args)
+        else:
+            addends.append(e)
+    kern = [e for e in addends if e.op == "expquad"]
+    rest = [e for e in addends if e.op != "expquad"]
+    if len(kern) != 1 or not np.array_equal(kern[0].data[0], kern[0].data[1]):
+        raise NotImplementedError(why)
+    n = kern[0].shape[0]
+    eye = None
+
+    def is_eye_times(e):  # const c * I -> c
+        nonlocal eye
+        if e.op != "const" or e.shape != (n, n):
+            return None
+        dg = np.diag(e.data)
+        if not np.all(dg == dg[0]) or np.count_nonzero(e.data) != (n if dg[0] != 0 else 0):
+            return None
+        return float(dg[0])
+
+    jitter, noise = 0.0, None
+    for e in rest:
+        c = is_eye_times(e)
+        if c is not None:
+            jitter += c
+            continue
+        if e.op == "mul" and noise is None:
+            a, b = e.args
+            if is_eye_times(b) is None:
+                a, b = b, a
+            c = is_eye_times(b)
+            squared = False
+            if c == 1.0:
+                if a.op == "square" or (a.op == "pow" and a.args[1].op == "const" and float(a.args[1].data) == 2.0):
+                    a, squared = a.args[0], True
+                sp = _scalar_param(a, rvs)
+                if sp is not None:
+                    noise = (sp, squared)
+                    continue
+        raise NotImplementedError(why)
+    ls, amp = _scalar_param(kern[0].args[0], rvs), _scalar_param(kern[0].args[1], rvs)
+    if ls is None or amp is None:
+        raise NotImplementedError(why)
+    if noise is None:
+        noise = ((-1, 0.0), False)
+    (ne, nc), squared = noise
+    X = np.asarray(kern[0].data[0], dtype=np.float64)
+    y = np.asarray(v.data, dtype=np.float64).reshape(-1) - np.broadcast_to(np.asarray(loc.data, dtype=np.float64), (n,))
+    if y.shape != (n,):
+        raise ValueError("observed value of shape {} does not match the {} x {} covariance".format(v.shape, n, n))
+    par = np.array([ls[0], amp[0], ne, ls[1], amp[1], nc, 1.0 if squared else 0.0, jitter], dtype=np.float64)
+    x_blob, y_blob, par_blob = pools.add_f(X.reshape(-1)), pools.add_f(y), pools.add_f(par)
+    return Term(kind=TERM_KINDS["mvn_expquad"], n=1, ops=[], value_reg=-1, param_regs=[], label=label, shape=(),
+                gp=GP(x_blob=x_blob, y_blob=y_blob, par_blob=par_blob, n=int(n), d=int(X.shape[1]),
+                      elems=(ls[0], amp[0], ne)))
+
+
 def _lower_term(kind: str, value, params: List[Any], rvs, pools, label="") -> Term:
     glm = _match_glm(kind, value, params, rvs, pools, label)
     if glm is not None:
         return glm
+    gp = _match_gp(kind, value, params, rvs, pools, label)
+    if gp is not None:
+        return gp
     exprs = [sym.as_expr(value)] + [sym.as_expr(p) for p in params]
     shape = tuple(np.broadcast_shapes(*[e.shape for e in exprs]))
     n = int(np.prod(shape, dtype=np.int64)) if shape else 1
@@ -563,7 +681,7 @@ class CTerm(ctypes.Structure):
                 ("op_end", ctypes.c_int32), ("n_regs", ctypes.c_int32), ("value_reg", ctypes.c_int32),
                 ("param_reg", ctypes.c_int32 * 3), ("plan", ctypes.c_int32), ("observed", ctypes.c_int32),
                 ("ll_offset", ctypes.c_int32), ("glm_base", ctypes.c_int32), ("glm_p", ctypes.c_int32),
-                ("glm_x", ctypes.c_int64), ("glm_y", ctypes.c_int64)]
+                ("glm_x", ctypes.c_int64), ("glm_y", ctypes.c_int64), ("gp_par", ctypes.c_int64)]
 
 
 class CPlan(ctypes.Structure):
@@ -614,10 +732,13 @@ class PackedIR:
             if t.plan is not None:
                 plan_idx = len(plans)
                 plans.append(t.plan)
-            g = t.glm
+            g, gp = t.glm, t.gp
+            if gp is not None:  # the dense-term fields are shared: (n points, d features, X, y - loc, parameter record)
+                dense = (gp.n, gp.d, gp.x_blob, gp.y_blob, gp.par_blob)
+            else:
+                dense = (g.base if g else 0, g.P if g else 0, g.x_blob if g else 0, g.y_blob if g else 0, 0)
             cterms[k] = CTerm(t.kind, t.n, begin, len(all_ops), t.n_regs, t.value_reg,
-                              (ctypes.c_int32 * 3)(*pr), plan_idx, 1 if t.observed else 0, t.ll_offset,
-                              g.base if g else 0, g.P if g else 0, g.x_blob if g else 0, g.y_blob if g else 0)
+                              (ctypes.c_int32 * 3)(*pr), plan_idx, 1 if t.observed else 0, t.ll_offset, *dense)
         cdets = (CDet * max(len(ir.dets), 1))()
         for k, d in enumerate(ir.dets):
             begin = len(all_ops)

@@ -186,6 +186,8 @@ class Expr:
             out = np.reshape(self.args[0].eval(env, memo), -1)[self.index]
         elif self.op == "matvec":
             out = self.args[0].eval(env, memo) @ self.args[1].eval(env, memo)
+        elif self.op == "expquad":
+            out = expquad_numpy(self.data[0], self.data[1], self.args[0].eval(env, memo), self.args[1].eval(env, memo))
         else:  # pragma: no cover - guarded by constructors
             raise NotImplementedError(self.op)
         out = np.asarray(out, dtype=np.float64)
@@ -414,6 +416,23 @@ def matvec(a, b) -> Expr:
     if a.op != "const":
         raise NotImplementedError("matvec with a symbolic matrix is not part of the model IR")
     return _maybe_fold(Expr("matvec", (a, b), (a.shape[0],)))
+
+
+def expquad_numpy(X1: np.ndarray, X2: np.ndarray, length_scale, amplitude) -> np.ndarray:
+    """``amplitude^2 exp(-|x - x'|^2 / (2 length_scale^2))`` between the rows of X1 [n1, d] and X2 [n2, d]
+    (tfp ExponentiatedQuadratic.matrix, which /root/reference/pymc4/gp/cov.py:463-469 wraps)."""
+    X1, X2 = np.asarray(X1, dtype=np.float64), np.asarray(X2, dtype=np.float64)
+    d2 = np.sum(np.square(X1[:, None, :] - X2[None, :, :]), axis=-1)
+    return np.square(amplitude) * np.exp(-d2 / (2.0 * np.square(length_scale)))
+
+
+def expquad(X1, X2, length_scale, amplitude) -> Expr:
+    """Covariance-matrix node: constant points, scalar (possibly free) length scale and amplitude."""
+    X1, X2 = as_numpy(X1), as_numpy(X2)
+    ls, amp = as_expr(length_scale), as_expr(amplitude)
+    if ls.size != 1 or amp.size != 1:
+        raise NotImplementedError("ExpQuad on the device takes a scalar length_scale and amplitude")
+    return _maybe_fold(Expr("expquad", (reshape(ls, ()), reshape(amp, ())), (X1.shape[0], X2.shape[0]), data=(X1, X2)))
 
 
 def zeros(shape):

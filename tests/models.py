@@ -169,3 +169,28 @@ def logistic_glm_data(n=3000, p=20, seed=11):
     beta = rng.normal(0, 0.5, p)
     y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
     return X, y
+
+
+def gp_data(n=64, d=1, seed=20261019, ls=1.0, amp=1.0, sigma=0.1):
+    """BASELINE configs[3] shape: X ~ U(0, 10), y ~ MVN(0, ExpQuad(ls, amp)(X, X) + sigma^2 I)."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0.0, 10.0, (n, d))
+    d2 = np.sum(np.square(X[:, None, :] - X[None, :, :]), axis=-1)
+    K = amp ** 2 * np.exp(-d2 / (2 * ls ** 2)) + sigma ** 2 * np.eye(n)
+    y = np.linalg.cholesky(K) @ rng.standard_normal(n)
+    return X, y
+
+
+def gp_model(X, y):
+    """Marginal GP regression spelled the way the reference allows (no marginal_likelihood, gp/gp.py:51-60)."""
+    n = X.shape[0]
+
+    @pm.model
+    def gp_regression():
+        ls = yield pm.HalfCauchy("ls", 5.0)
+        amp = yield pm.HalfCauchy("amp", 5.0)
+        sigma = yield pm.HalfNormal("sigma", 1.0)
+        cov = pm.gp.cov.ExpQuad(length_scale=ls, amplitude=amp)(X, X) + sigma ** 2 * np.eye(n)
+        yield pm.MvNormal("y", loc=0.0, covariance_matrix=pm.gp.util.stabilize(cov, 1e-6), observed=y)
+
+    return gp_regression()

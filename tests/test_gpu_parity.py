@@ -516,3 +516,54 @@ def test_dense_glm_lockstep_nuts_parity(oracle_mod):
         np.testing.assert_allclose(np.exp(out["log_accept"].cpu().numpy()).mean(), np.exp(ref["log_accept"]).mean(), atol=0.08)
         np.testing.assert_allclose(out["states"].cpu().numpy().mean((0, 1)), ref["states"].mean((0, 1)), atol=0.15)
         assert out["diverging"].cpu().numpy().mean() < 0.05
+
+
+@pytest.mark.parametrize("n,d", [(40, 1), (200, 2), (256, 1)])
+def test_gp_marginal_likelihood_logp_grad_parity(n, d, oracle_mod):
+    """MvNormal(0, ExpQuad(l, a)(X, X) + sigma^2 I) observed.  The device factorises K per chain in
+    float64 (blocked Cholesky, inverse factor, contraction with dK); compared with the oracle's plain loops."""
+    X, y = M.gp_data(n=n, d=d)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    assert len(ir.gp_terms) == 1 and ir.lockstep
+    C = 12
+    rng = np.random.default_rng(71)
+    theta = rng.normal(0, 0.4, (C, ir.D))
+    theta[:, 2] -= 1.5
+    theta[0] = 0.0
+    lp_ref, g_ref = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    dm64 = _dm(ir, f64=True)
+    lp, g = dm64.logp_grad(theta, dtype=np.float64)
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-8, atol=1e-7)
+    # float32 sampling dtype: theta, lp and grad are float32, the factorisation stays float64
+    lp32, g32 = _dm(ir).logp_grad(theta.astype(np.float32), dtype=np.float32)
+    lp_r32, g_r32 = oracle_mod.Oracle(ir).logp_grad(theta.astype(np.float32).astype(np.float64), dtype=np.float64)
+    np.testing.assert_allclose(lp32.cpu().numpy(), lp_r32, rtol=2e-6)
+    for c in range(C):
+        assert _rel(g32[c].cpu().numpy(), g_r32[c]) < 1e-5
+    lp_only, _ = dm64.logp_grad(theta, dtype=np.float64, want_grad=False)
+    np.testing.assert_allclose(lp_only.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-8)
+    ll = dm64.log_likelihood(theta[:5], dtype=np.float64).cpu().numpy()
+    np.testing.assert_allclose(ll, oracle_mod.Oracle(ir).log_likelihood(theta[:5]), rtol=1e-10, atol=1e-8)
+    assert ll.shape == (5, 1)
+
+
+def test_gp_lockstep_hmc_and_nuts_against_oracle(oracle_mod):
+    X, y = M.gp_data(n=96, d=1)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    C, D = 24, ir.D
+    rng = np.random.default_rng(72)
+    theta0 = rng.normal(0, 0.1, (C, D))
+    theta0[:, 2] -= 1.0
+    momenta = rng.standard_normal((1, C, D))
+    uniforms = rng.random((1, C))
+    cfg = make_hmc_cfg(C, 1, 0, step_size=0.01, num_leapfrog_steps=10, seed=1, adapt=make_adapt(enabled=False))
+    ref = oracle_mod.Oracle(ir).hmc(cfg, theta0, dtype=np.float64, momenta=momenta, uniforms=uniforms)
+    out = _dm(ir).hmc(cfg, theta0.astype(np.float32), dtype=np.float32, momenta=momenta, uniforms=uniforms, want_traj=True)
+    assert np.max(np.abs(out["traj"].cpu().numpy() - ref["traj"])) < 1e-4
+    assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+    cfg = make_nuts_cfg(C, 30, 40, step_size=0.05, seed=4, adapt=make_adapt(num_adaptation_steps=40), max_tree_depth=5)
+    ref = oracle_mod.Oracle(ir).nuts(cfg, theta0[0] * 0, dtype=np.float32)
+    out = _dm(ir).nuts(cfg, np.zeros((C, D), np.float32), dtype=np.float32)
+    np.testing.assert_allclose(out["leapfrogs"].cpu().numpy().mean(), ref["leapfrogs"].mean(), rtol=0.3)
+    np.testing.assert_allclose(out["states"].cpu().numpy().mean((0, 1)), ref["states"].mean((0, 1)), atol=0.25)

@@ -3,6 +3,7 @@ torch autograd and published known-answer vectors.  No GPU needed."""
 import math
 
 import numpy as np
+import pymc4_b200 as pm
 import pytest
 import torch
 from scipy import stats
@@ -442,3 +443,49 @@ def test_dense_glm_term_lowering_and_oracle(oracle_mod):
 
     with pytest.raises(NotImplementedError):
         lower_model(shifted(X, y))
+
+
+def test_gp_marginal_likelihood_oracle_against_scipy(oracle_mod):
+    """The GP term of the oracle: tfd.MultivariateNormalFullCovariance.log_prob of an ExpQuad + noise covariance
+    (/root/reference/pymc4/gp/cov.py:399-475; the class docstring's 3-point example is the golden vector for the kernel
+    matrix), against scipy's MVN density and central differences."""
+    from scipy.stats import halfcauchy, halfnorm, multivariate_normal
+
+    k = pm.gp.cov.ExpQuad(amplitude=1.0, length_scale=1.0, feature_ndims=1)
+    K = k(np.array([[1.0], [2.0], [3.0]]), np.array([[3.0], [2.0], [1.0]]))
+    np.testing.assert_allclose(K, [[0.13533528, 0.60653067, 1.0], [0.60653067, 1.0, 0.60653067], [1.0, 0.60653067, 0.13533528]],
+                               rtol=1e-7)
+    np.testing.assert_allclose(k.evaluate_kernel(np.array([[1.0], [2.0], [3.0]]), np.array([[3.0], [2.0], [1.0]])),
+                               [0.13533528, 1.0, 0.13533528], rtol=1e-7)
+    np.testing.assert_allclose(pm.gp.util.stabilize(np.eye(3)), 1.0001 * np.eye(3))
+    X, y = M.gp_data(n=40, d=2)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    t = ir.gp_terms[0]
+    assert t.kind == 7 and t.n == 1 and t.observed and t.gp.elems == (0, 1, 2) and ir.ll_row == 1
+    np.testing.assert_allclose(ir.dataf[t.gp.par_blob:t.gp.par_blob + 8], [0, 1, 2, 0, 0, 0, 1, 1e-6])
+    rng = np.random.default_rng(5)
+    theta = rng.normal(0, 0.3, (4, 3))
+    theta[:, 2] -= 1.5
+
+    def ref(th):
+        ls, amp, sg = np.exp(th)
+        d2 = np.sum(np.square(X[:, None] - X[None]), -1)
+        Kc = amp ** 2 * np.exp(-d2 / (2 * ls ** 2)) + (sg ** 2 + 1e-6) * np.eye(len(y))
+        return (multivariate_normal(np.zeros(len(y)), Kc).logpdf(y) + halfcauchy(scale=5).logpdf(ls)
+                + halfcauchy(scale=5).logpdf(amp) + halfnorm(scale=1).logpdf(sg) + th.sum())
+
+    lp, g = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    np.testing.assert_allclose(lp, [ref(th) for th in theta], rtol=1e-11)
+    eps = 1e-6
+    num = np.array([[(ref(th + eps * e) - ref(th - eps * e)) / (2 * eps) for e in np.eye(3)] for th in theta])
+    np.testing.assert_allclose(g, num, rtol=1e-5, atol=1e-5)
+    ll = oracle_mod.Oracle(ir).log_likelihood(theta)
+    assert ll.shape == (4, 1)
+    # unsupported spellings fail loudly at lowering time
+    @pm.model
+    def latent():
+        f = yield pm.MvNormal("f", loc=0.0, covariance_matrix=np.eye(3))
+        yield pm.Normal("y", f, 1.0, observed=np.zeros(3))
+
+    with pytest.raises(NotImplementedError, match="marginal likelihood"):
+        lower_model(latent())

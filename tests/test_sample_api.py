@@ -218,3 +218,17 @@ def test_sample_dense_logistic_regression_with_hmc():
     err = np.abs(beta.mean((0, 1)) - beta_true)
     assert np.max(err) < 0.25 and np.mean(err) < 0.1
     assert 0.5 < np.exp(np.minimum(trace.sample_stats["mean_tree_accept"], 0)).mean() <= 1.0
+
+
+def test_sample_gp_regression_recovers_hyperparameters():
+    """BASELINE configs[3] at test size: marginal GP regression spelled with ExpQuad + MvNormal (the reference has no
+    marginal_likelihood), sampled with the default NUTS; the posterior covers the generating (l, a, sigma) = (1, 1, 0.1)."""
+    X, y = M.gp_data(n=128, d=1)
+    trace = pm.sample(M.gp_model(X, y), num_chains=32, num_samples=100, burn_in=150, step_size=0.05, seed=5)
+    post = trace.posterior
+    ls, amp, sg = (post["gp_regression/" + k] for k in ("ls", "amp", "sigma"))
+    assert ls.shape == (32, 100)
+    assert 0.6 < np.median(ls) < 1.6 and 0.4 < np.median(amp) < 2.5 and 0.07 < np.median(sg) < 0.14
+    assert trace.sample_stats["diverging"].mean() < 0.1
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        pm.sample_posterior_predictive(M.gp_model(X, y), trace)
