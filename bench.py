@@ -59,11 +59,14 @@ def parse_args():
                     help="per-chain: step_size with a leading chain axis (independent dual averaging, no coupling); "
                          "pooled: scalar step_size, the reference default (one epsilon adapted from the mean "
                          "acceptance of all chains of the rank: lock-step launches during burn-in)")
-    ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k", "logit"],
+    ap.add_argument("--workload", default="radon919", choices=["radon919", "radon100k", "logit", "gp"],
                     help="radon919 = BASELINE configs[1] (the headline); radon100k = configs[4] shape "
                          "(100k observations / 5k groups, D = 10 005; pass --chains/--burn-in/--draws to bound the run); "
                          "logit = configs[2]: hierarchical logistic regression, N = 1M x P = 100, 1024 chains of HMC "
-                         "(3 leapfrogs), X beta on the tcgen05 tensor cores in 3xTF32")
+                         "(3 leapfrogs), X beta on the tcgen05 tensor cores in 3xTF32; "
+                         "gp = configs[3]: marginal GP regression, n = 4096 points, 256 chains of HMC (3 leapfrogs), "
+                         "float64 batched Cholesky")
+    ap.add_argument("--gp-n", type=int, default=4096)
     ap.add_argument("--logit-n", type=int, default=1_000_000)
     ap.add_argument("--leapfrogs", type=int, default=3, help="HMC leapfrog steps (logit workload; reference default 3)")
     return ap.parse_args()
@@ -73,6 +76,12 @@ def build_model():
     from pymc4_b200.ir import lower_model
     from tests import models as M
 
+    if WORKLOAD == "gp":
+        X, y = M.gp_data(n=N_OBS, d=1, seed=20261019)
+        model = M.gp_model(X, y)
+        ir, _, _ = lower_model(model)
+        assert ir.D == D_MODEL and len(ir.gp_terms) == 1
+        return model, ir
     if WORKLOAD == "logit":
         X, y = M.logistic_glm_data(n=N_OBS, p=LOGIT_P, seed=20261019)
         model = M.logistic_glm_model(X, y)
@@ -92,10 +101,17 @@ def build_model():
 WORKLOAD, LOGIT_P = "radon919", 100
 
 
-def select_workload(name, logit_n=1_000_000):
+def select_workload(name, logit_n=1_000_000, gp_n=4096):
     """Switch the module-level shape constants (the algorithmic cost per unit follows the shape)."""
     global N_OBS, N_GROUPS, D_MODEL, FLOPS_PER_UNIT, ONCHIP_BYTES_PER_UNIT, WORKLOAD
     WORKLOAD = name
+    if name == "gp":
+        # SURVEY 8(d): F ~ n^3 flops per unit (Cholesky n^3/3 + inverse factor n^3/3 + contraction with dK n^3/3)
+        N_OBS, N_GROUPS = int(gp_n), 0
+        D_MODEL = 3
+        FLOPS_PER_UNIT = float(N_OBS) ** 3
+        ONCHIP_BYTES_PER_UNIT = 0
+        return
     if name == "logit":
         # SURVEY 8(d): F = 4 N P flops per unit (X beta and X^T r), X read once per lock-step leapfrog for all chains
         N_OBS, N_GROUPS = int(logit_n), 0
@@ -111,6 +127,19 @@ def select_workload(name, logit_n=1_000_000):
 
 
 def workload_config(args, n_gpus):
+    if WORKLOAD == "gp":
+        return {
+            "workload": "marginal GP regression, synthetic n=%d points (1-D), ExpQuad + noise covariance, MvNormal "
+                        "likelihood (D=3 hyper-parameters), %d chains HMC (%d leapfrogs) per GPU, float64 batched blocked "
+                        "Cholesky" % (N_OBS, args.chains, args.leapfrogs),
+            "chains_per_gpu": args.chains, "global_chains": args.chains * n_gpus, "burn_in": args.burn_in,
+            "draws": args.draws, "num_leapfrog_steps": args.leapfrogs,
+            "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept HMC transitions, lock-step over chains",
+            "step_size": "%s dual averaging from %.3g" % (args.eps_mode, args.step_size),
+            "parallelism": "chains sharded, %d per GPU; every GPU holds X and y" % args.chains,
+            "l2": "L2 flushed (256 MiB write) between timed steps; the per-chain factors (%.0f GB) exceed L2"
+                  % (args.chains * 2 * N_OBS * N_OBS * 8 / 1e9),
+        }
     if WORKLOAD == "logit":
         return {
             "workload": "hierarchical logistic regression, synthetic N=%d x P=%d Bernoulli likelihood (D=%d), %d chains "
@@ -155,6 +184,15 @@ def cpu_sample_rate(ir, args, chains, seed):
     orc = pm4_oracle.Oracle(ir)
     mode = PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED
     adapt = make_adapt(mode=mode, num_adaptation_steps=args.burn_in)
+    if WORKLOAD == "gp":
+        # one scalar gradient evaluation at n = 4096 is ~7e10 flops: the sample is one evaluation per chain
+        rng = np.random.default_rng(seed)
+        th = rng.normal(0, 0.1, (chains, ir.D))
+        th[:, 2] -= 2.0
+        t0 = time.perf_counter()
+        orc.logp_grad(th, dtype=np.float64)
+        dt = time.perf_counter() - t0
+        return float(chains), dt
     if WORKLOAD == "logit":
         from pymc4_b200._cstructs import make_hmc_cfg
 
@@ -182,7 +220,7 @@ def cpu_baseline(ir, args):
     # calibrate so the sample costs roughly 10-30 s of CPU work
     evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
     rate = evals / dt
-    if dt < 8.0 and not args.cpu_chains and WORKLOAD != "logit":
+    if dt < 8.0 and not args.cpu_chains and WORKLOAD not in ("logit", "gp"):
         chains = int(min(args.chains, max(chains, chains * 15.0 / max(dt, 1e-3)) // cores * cores))
         evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
         rate = evals / dt
@@ -190,7 +228,8 @@ def cpu_baseline(ir, args):
         "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": "%d of the %d chains, %s, float32, OpenMP over chains (%d threads); "
                   "%.3g grad-evals in %.1f s" % (chains, args.chains,
-                                                 "2 + 2 transitions" if WORKLOAD == "logit" else "same burn_in/draws",
+                                                 {"logit": "2 + 2 transitions", "gp": "one gradient evaluation each"}.get(
+                                                     WORKLOAD, "same burn_in/draws"),
                                                  cores, evals, dt),
     }
 
@@ -205,8 +244,8 @@ def run_reference(args):
     pm4_oracle.build()
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    chains = args.cpu_chains or (cores if WORKLOAD == "logit" else 2 * cores)
-    for _ in range((max(args.warmup, 0) and 1) if WORKLOAD != "logit" else 0):  # one short warm-up pass is enough for a CPU code
+    chains = args.cpu_chains or (cores if WORKLOAD in ("logit", "gp") else 2 * cores)
+    for _ in range((max(args.warmup, 0) and 1) if WORKLOAD not in ("logit", "gp") else 0):  # one short warm-up pass is enough for a CPU code
         cpu_sample_rate(ir, args, cores, args.seed + 1)
     evals, secs = 0.0, 0.0
     for k in range(args.steps):
@@ -217,13 +256,14 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if WORKLOAD == "gp" else "f32",
         "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "each step = %d of the %d chains per GPU, %s; TFP-semantics CPU oracle "
                       "(the reference's TF/TFP stack is not installable in this image), OpenMP over chains" %
-                      (chains, args.chains, "2 + 2 transitions" if WORKLOAD == "logit" else "same burn_in/draws"),
+                      (chains, args.chains, {"logit": "2 + 2 transitions", "gp": "one gradient evaluation each"}.get(
+                          WORKLOAD, "same burn_in/draws")),
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -339,7 +379,7 @@ def run_b200(args):
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
     comm = None
-    if world > 1 and args.eps_mode == "pooled" and args.workload != "logit":
+    if world > 1 and args.eps_mode == "pooled" and args.workload not in ("logit", "gp"):
         # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
         # of the chains of ALL ranks (mailboxes in peer memory, read over NVLink by the dual-averaging kernel)
         comm = _cabi.Communicator(local_rank, rank, world)
@@ -347,7 +387,7 @@ def run_b200(args):
     adapt = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
                        num_adaptation_steps=B)
 
-    is_logit = args.workload == "logit"
+    is_logit = args.workload in ("logit", "gp")  # the lock-step HMC workloads
 
     def cfg_for(step):
         if is_logit:
@@ -427,6 +467,8 @@ def run_b200(args):
     cols = [0, 1, 2, 2 + N_GROUPS, ir.D - 3, ir.D - 2, ir.D - 1]  # mu_a, mu_b, alpha[0], beta[0], log sigmas, log eps
     if is_logit:
         cols = [0, 1, 2, ir.D // 2, ir.D - 2, ir.D - 1]  # mu, beta[0], beta[1], beta[mid], beta[last], log tau
+    if args.workload == "gp":
+        cols = [0, 1, 2]  # log l, log a, log sigma
     summ = diagnostics.summarize(out["states"], columns=cols)
     ess_per_sec = summ["min_ess"] / (dev_secs_max / max(args.steps, 1))
     mean_accept = float(torch.exp(out["log_accept"]).mean().item())
@@ -471,9 +513,9 @@ def run_b200(args):
             e2e_secs, e2e_leaps = float(a[0]), float(b[1])
         e2e = {"value": e2e_leaps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_secs / n_e2e,
-               "api": "pymc4_b200.mcmc.samplers.NUTS(model, step_size=%s)(num_samples, num_chains, burn_in) -> InferenceData "
+               "api": "pymc4_b200.mcmc.samplers.%s(model, step_size=%s)(num_samples, num_chains, burn_in) -> InferenceData "
                       "on the host (trace copied through pinned memory)"
-                      % ("[C,1]" if args.eps_mode == "per-chain" else "%g" % args.step_size)}
+                      % ("HMC" if is_logit else "NUTS", "[C,1]" if args.eps_mode == "per-chain" else "%g" % args.step_size)}
 
     if rank != 0:
         if world > 1:
@@ -512,7 +554,28 @@ def run_b200(args):
                     "fp32": {"achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s"},
                     "l2_records": {"achieved": ach_smem_tbs, "unit": "TB/s",
                                    "note": "observation records (12 N bytes per unit) stream from L2, not shared memory"}}
-    if is_logit:
+    if args.workload == "gp":
+        # ~n^3 float64 flops per unit; yardstick = cuBLAS DGEMM timed live on this GPU
+        ma = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        mb = torch.randn(4096, 4096, device=dev, dtype=torch.float64)
+        for _ in range(2):
+            ma @ mb
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ma @ mb
+        e1.record()
+        torch.cuda.synchronize()
+        f64_peak = 10 * 2 * 4096.0 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "achieved": ach_tflops, "peak": f64_peak, "unit": "TFLOP/s",
+            "frac": ach_tflops / f64_peak, "traffic": None,
+            "kernel": "gp_nt_kernel<CHOL|ZT|DOT> (64 x 64 float64 tiles, DFMA): blocked Cholesky, inverse factor and the "
+                      "contraction with dK; time base = the whole step",
+            "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
+            "peak_source": "cuBLAS float64 matmul 4096^3 timed live by this bench (MEASURED_PEAKS.json has no float64 entry)",
+        }
+    elif is_logit:
         # the dense likelihood is GEMM-shaped: 4 N P useful flops per gradient evaluation (X beta and
         # X^T r).  The kernels issue them as 3xTF32 (three tensor-core passes per product, TF32 at half the bf16
         # rate), so the fraction against the measured bf16 peak is bounded by 1/6 for FP32-accurate results.
@@ -546,7 +609,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_secs_max / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if WORKLOAD == "gp" else "f32",
         "data": "synthetic", "config": workload_config(args, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "ess_per_sec": ess_per_sec,
@@ -566,7 +629,15 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    select_workload(args.workload, args.logit_n)
+    select_workload(args.workload, args.logit_n, args.gp_n)
+    if args.workload == "gp":
+        # one batched gradient evaluation of 256 chains is 1.8e13 float64 flops: bounded defaults
+        if args.chains == CHAINS_PER_GPU:
+            args.chains = 256
+        if args.burn_in == 1000 and args.draws == 1000:
+            args.burn_in, args.draws = 2, 2
+        if args.step_size == 0.1:
+            args.step_size = 0.005
     if args.workload == "logit":
         # bounded defaults for the dense workload (one batched leapfrog of 1024 chains reads the 400 MB matrix twice)
         if args.chains == CHAINS_PER_GPU:

@@ -241,23 +241,36 @@ static double NAME(gp_term)(const pm4_ir_t* ir, const pm4_term_t* tm, const REAL
     }
     lp = -0.5 * quad - logdet - 0.5 * n * 1.8378770664093454835606594728112;
     if (gx) {
-      for (int j = 0; j < n; ++j) /* Z = L^-1, column by column */
-        for (int i = j; i < n; ++i) {
-          double t = i == j ? 1.0 : 0.0;
-          for (int k = j; k < i; ++k) t -= K[(size_t)i * n + k] * Z[(size_t)k * n + j];
-          Z[(size_t)i * n + j] = t / K[(size_t)i * n + i];
+      /* Z = L^-1 row by row (contiguous inner loops): z_i = (e_i - sum_{k < i} L[i, k] z_k) / L[i, i] */
+      for (int i = 0; i < n; ++i) {
+        double* zi = Z + (size_t)i * n;
+        zi[i] = 1.0;
+        for (int k = 0; k < i; ++k) {
+          const double lik = K[(size_t)i * n + k];
+          const double* zk = Z + (size_t)k * n;
+          for (int j = 0; j <= k; ++j) zi[j] -= lik * zk[j];
         }
-      for (int i = 0; i < n; ++i) { /* alpha = L^-T w */
-        double t = 0;
-        for (int k = i; k < n; ++k) t += Z[(size_t)k * n + i] * w[k];
-        alpha[i] = t;
+        const double r = 1.0 / K[(size_t)i * n + i];
+        for (int j = 0; j <= i; ++j) zi[j] *= r;
+      }
+      for (int i = 0; i < n; ++i) alpha[i] = 0; /* alpha = L^-T w */
+      for (int k = 0; k < n; ++k)
+        for (int i = 0; i <= k; ++i) alpha[i] += Z[(size_t)k * n + i] * w[k];
+      /* K^-1 = Z^T Z accumulated into the (now free) lower triangle of K, one rank-1 update per row of Z */
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j) K[(size_t)i * n + j] = 0;
+      for (int k = 0; k < n; ++k) {
+        const double* zk = Z + (size_t)k * n;
+        for (int i = 0; i <= k; ++i) {
+          const double zki = zk[i];
+          double* gi = K + (size_t)i * n;
+          for (int j = 0; j <= i; ++j) gi[j] += zki * zk[j];
+        }
       }
       double s1 = 0, s2 = 0, s3 = 0;
       for (int i = 0; i < n; ++i)
         for (int j = 0; j <= i; ++j) {
-          double kinv = 0;
-          for (int k = i; k < n; ++k) kinv += Z[(size_t)k * n + i] * Z[(size_t)k * n + j];
-          const double W = alpha[i] * alpha[j] - kinv;
+          const double W = alpha[i] * alpha[j] - K[(size_t)i * n + j];
           double d2 = 0;
           for (int f = 0; f < d; ++f) { const double df = X[(size_t)i * d + f] - X[(size_t)j * d + f]; d2 += df * df; }
           const double kse = a * a * exp(-d2 / (2.0 * l * l)), wt = i == j ? 1.0 : 2.0;

@@ -16,7 +16,7 @@
 // All of it in float64 on the FP64 pipe (B200: 64 DFMA/clk/SM), whatever the sampling dtype: the kernel matrix
 // of a smooth covariance function has a condition number ~ a^2 n / noise, out of reach of float32 or of
 // split-TF32 tensor-core arithmetic.  The O(n^3) work is three passes of ONE tile kernel, C[I, J] -= sum_k
-// A[I, k] B[J, k] on 64 x 64 tiles with 4 x 4 register blocking: n^3/3 flops each for the factor, the inverse
+// A[I, k] B[J, k] on 64 x 64 tiles with 8 x 8 register blocking: n^3/3 flops each for the factor, the inverse
 // factor and the contraction with dK.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int NB = 64;   // block size of the factorisation
-constexpr int KS = 16;   // k-slab of the tile kernel
+constexpr int KS = 8;    // k-slab of the tile kernel
 
 struct GpShape {
   int n, np, nt, d, C;             // points, padded points (multiple of NB), tiles per side, features, chains in this chunk
@@ -92,36 +92,56 @@ __global__ void __launch_bounds__(256) gp_build_kernel(GpShape s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// the tile kernel: acc[I, J] = sum_{k in [k0, k1)} A[I, k] B[J, k], 64 x 64 per block, 256 threads x (4 x 4)
+// the tile kernel: acc[I, J] = sum_{k in [k0, k1)} A[I, k] B[J, k], 64 x 64 per block, 64 threads x (8 x 8)
 // ------------------------------------------------------------------------------------------
 enum { MODE_CHOL = 0, MODE_ZT = 1, MODE_DOT = 2 };
 
+// 64 threads per 64 x 64 tile, 8 x 8 results per thread: thread (tx, ty) of the 8 x 8 grid owns rows
+// {ty 4 .. + 3} and {32 + ty 4 .. + 3} and the column pairs 16 m + 2 tx + {0, 1}, m = 0 .. 3.  Per slab row that is
+// 8 LDS.128 (one shared-memory wavefront each: the lanes of a warp read 4 distinct 16-byte row pieces or 128
+// contiguous column bytes) for 64 DFMA -- the FP64 pipe, not shared memory, is the limiter.  The next slab is
+// fetched into registers while the current one is multiplied.
+constexpr int NT_THREADS = 64;
+__device__ __forceinline__ int tile_row(int ty, int i) { return (i >> 2) * 32 + ty * 4 + (i & 3); }
+__device__ __forceinline__ int tile_col(int tx, int j) { return (j >> 1) * 16 + tx * 2 + (j & 1); }
+
 __device__ __forceinline__ void tile_nt(const double* __restrict__ A, const double* __restrict__ B, int ld, int k0, int k1,
-                                        double (&acc)[4][4], double (*As)[NB + 2], double (*Bs)[NB + 2]) {
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  const int lr = t >> 2, lk = (t & 3) * 4;  // this thread stages row lr, slab columns lk .. lk + 3
+                                        double (&acc)[8][8], double (*As)[NB + 2], double (*Bs)[NB + 2]) {
+  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  if (k0 >= k1) return;
+  const double* ap = A + (size_t)t * ld;  // this thread stages row t of both slabs
+  const double* bp = B + (size_t)t * ld;
+  double4 a0 = *reinterpret_cast<const double4*>(ap + k0), a1 = *reinterpret_cast<const double4*>(ap + k0 + 4);
+  double4 b0 = *reinterpret_cast<const double4*>(bp + k0), b1 = *reinterpret_cast<const double4*>(bp + k0 + 4);
   for (int k = k0; k < k1; k += KS) {
-    const double4 av = *reinterpret_cast<const double4*>(A + (size_t)lr * ld + k + lk);
-    const double4 bv = *reinterpret_cast<const double4*>(B + (size_t)lr * ld + k + lk);
     __syncthreads();
-    As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
-    Bs[lk + 0][lr] = bv.x; Bs[lk + 1][lr] = bv.y; Bs[lk + 2][lr] = bv.z; Bs[lk + 3][lr] = bv.w;
+    As[0][t] = a0.x; As[1][t] = a0.y; As[2][t] = a0.z; As[3][t] = a0.w;
+    As[4][t] = a1.x; As[5][t] = a1.y; As[6][t] = a1.z; As[7][t] = a1.w;
+    Bs[0][t] = b0.x; Bs[1][t] = b0.y; Bs[2][t] = b0.z; Bs[3][t] = b0.w;
+    Bs[4][t] = b1.x; Bs[5][t] = b1.y; Bs[6][t] = b1.z; Bs[7][t] = b1.w;
     __syncthreads();
+    if (k + KS < k1) {
+      a0 = *reinterpret_cast<const double4*>(ap + k + KS); a1 = *reinterpret_cast<const double4*>(ap + k + KS + 4);
+      b0 = *reinterpret_cast<const double4*>(bp + k + KS); b1 = *reinterpret_cast<const double4*>(bp + k + KS + 4);
+    }
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk) {
-      const double2 a01 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]);
-      const double2 a23 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
-      const double2 b01 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
-      const double2 b23 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
-      const double a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+      double a[8], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int h = 0; h < 4; ++h) {
+        const double2 av = *reinterpret_cast<const double2*>(&As[kk][(h >> 1) * 32 + ty * 4 + (h & 1) * 2]);
+        const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][h * 16 + tx * 2]);
+        a[2 * h] = av.x; a[2 * h + 1] = av.y;
+        b[2 * h] = bv.x; b[2 * h + 1] = bv.y;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
   }
 }
@@ -130,38 +150,42 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, const doub
 // MODE_ZT,   block ib:        tile (J = blockIdx.x <= ib, ib) of Zt = [J == ib] I - Zt[J, J NB : ib NB] L[ib, J NB : ib NB]^T
 // MODE_DOT:  tile (I, J <= I) from the linear index blockIdx.x: G = Zt[I, I NB :] Zt[J, I NB :]^T, then the sums
 template <int MODE>
-__global__ void __launch_bounds__(256) gp_nt_kernel(GpShape s, int blk) {
+__global__ void __launch_bounds__(NT_THREADS) gp_nt_kernel(GpShape s, int blk) {
   __shared__ __align__(16) double As[KS][NB + 2];
   __shared__ __align__(16) double Bs[KS][NB + 2];
   const int c = blockIdx.y, np = s.np;
   double* L = s.Kb + (size_t)c * np * np;
   double* Zt = s.Zt + (size_t)c * np * np;
-  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-  double acc[4][4];
+  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+  double acc[8][8];
   if (MODE == MODE_CHOL) {
     const int I = blk + blockIdx.x;
     tile_nt(L + (size_t)I * NB * np, L + (size_t)blk * NB * np, np, 0, blk * NB, acc, As, Bs);
     double* Ct = L + (size_t)I * NB * np + (size_t)blk * NB;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double4* p = reinterpret_cast<double4*>(Ct + (size_t)(ty * 4 + i) * np + tx * 4);
-      double4 v = *p;
-      v.x -= acc[i][0]; v.y -= acc[i][1]; v.z -= acc[i][2]; v.w -= acc[i][3];
-      *p = v;
-    }
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        double2* p = reinterpret_cast<double2*>(Ct + (size_t)tile_row(ty, i) * np + tile_col(tx, 2 * h));
+        double2 v = *p;
+        v.x -= acc[i][2 * h]; v.y -= acc[i][2 * h + 1];
+        *p = v;
+      }
   } else if (MODE == MODE_ZT) {
     const int J = blockIdx.x;
     tile_nt(Zt + (size_t)J * NB * np, L + (size_t)blk * NB * np, np, J * NB, blk * NB, acc, As, Bs);
     double* Ct = Zt + (size_t)J * NB * np + (size_t)blk * NB;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = ty * 4 + i;
-      double4 v;
-      v.x = ((J == blk && r == tx * 4 + 0) ? 1.0 : 0.0) - acc[i][0];
-      v.y = ((J == blk && r == tx * 4 + 1) ? 1.0 : 0.0) - acc[i][1];
-      v.z = ((J == blk && r == tx * 4 + 2) ? 1.0 : 0.0) - acc[i][2];
-      v.w = ((J == blk && r == tx * 4 + 3) ? 1.0 : 0.0) - acc[i][3];
-      *reinterpret_cast<double4*>(Ct + (size_t)r * np + tx * 4) = v;
+    for (int i = 0; i < 8; ++i) {
+      const int r = tile_row(ty, i);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int col = tile_col(tx, 2 * h);
+        double2 v;
+        v.x = ((J == blk && r == col) ? 1.0 : 0.0) - acc[i][2 * h];
+        v.y = ((J == blk && r == col + 1) ? 1.0 : 0.0) - acc[i][2 * h + 1];
+        *reinterpret_cast<double2*>(Ct + (size_t)r * np + col) = v;
+      }
     }
   } else {
     // linear index -> (I, J <= I)
@@ -176,11 +200,11 @@ __global__ void __launch_bounds__(256) gp_nt_kernel(GpShape s, int blk) {
     const double wt = (I == J) ? 1.0 : 2.0;
     double s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gi = I * NB + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+      const int gi = I * NB + tile_row(ty, i);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int gj = J * NB + tx * 4 + j;
+      for (int j = 0; j < 8; ++j) {
+        const int gj = J * NB + tile_col(tx, j);
         if (gi < s.n && gj < s.n) {
           const double W = alpha[gi] * alpha[gj] - acc[i][j];
           const double d2 = dist2(s.X, s.d, gi, gj);
@@ -192,11 +216,11 @@ __global__ void __launch_bounds__(256) gp_nt_kernel(GpShape s, int blk) {
       }
     }
     // block reduction in a fixed order
-    __shared__ double red[3][256];
+    __shared__ double red[3][NT_THREADS];
     __syncthreads();
     red[0][t] = s1; red[1][t] = s2; red[2][t] = s3;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = NT_THREADS / 2; o > 0; o >>= 1) {
       if (t < o) { red[0][t] += red[0][t + o]; red[1][t] += red[1][t + o]; red[2][t] += red[2][t + o]; }
       __syncthreads();
     }
@@ -365,21 +389,21 @@ extern "C" int pm4_gp_logp_grad(const double* X, const double* y, int n, int d, 
   gp_build_kernel<<<dim3((unsigned)s.nt, (unsigned)s.nt, (unsigned)C), 256, 0, st>>>(s);
   // Cholesky, left-looking over block columns
   for (int jb = 0; jb < s.nt; ++jb) {
-    if (jb > 0) gp_nt_kernel<MODE_CHOL><<<dim3((unsigned)(s.nt - jb), (unsigned)C), 256, 0, st>>>(s, jb);
+    if (jb > 0) gp_nt_kernel<MODE_CHOL><<<dim3((unsigned)(s.nt - jb), (unsigned)C), NT_THREADS, 0, st>>>(s, jb);
     gp_potrf_kernel<<<(unsigned)C, NB, 0, st>>>(s, jb);
     const int r0 = (jb + 1) * NB;
     if (r0 < s.np) gp_trsm_kernel<<<dim3((unsigned)((s.np - r0 + 127) / 128), (unsigned)C), 128, 0, st>>>(s, jb, 0, r0, s.np);
   }
   // Zt = L^-T, block column by block column
   for (int ib = 0; ib < s.nt; ++ib) {
-    gp_nt_kernel<MODE_ZT><<<dim3((unsigned)(ib + 1), (unsigned)C), 256, 0, st>>>(s, ib);
+    gp_nt_kernel<MODE_ZT><<<dim3((unsigned)(ib + 1), (unsigned)C), NT_THREADS, 0, st>>>(s, ib);
     const int r1 = (ib + 1) * NB;
     gp_trsm_kernel<<<dim3((unsigned)((r1 + 127) / 128), (unsigned)C), 128, 0, st>>>(s, ib, 1, 0, r1);
   }
   gp_v_kernel<<<dim3((unsigned)((s.np + 255) / 256), (unsigned)C), 256, 0, st>>>(s);
   if (grad) {
     gp_alpha_kernel<<<dim3((unsigned)((s.np + 7) / 8), (unsigned)C), 256, 0, st>>>(s);
-    gp_nt_kernel<MODE_DOT><<<dim3((unsigned)ntile, (unsigned)C), 256, 0, st>>>(s, 0);
+    gp_nt_kernel<MODE_DOT><<<dim3((unsigned)ntile, (unsigned)C), NT_THREADS, 0, st>>>(s, 0);
   }
   const unsigned fb = (unsigned)((C + 7) / 8);
   if (dtype == PM4_F64) gp_finish_kernel<double><<<fb, 256, 0, st>>>(s, p, (double*)lp, lp_stride, accumulate, (double*)grad, ldg);

@@ -85,6 +85,10 @@ def summarize(states: torch.Tensor, columns: Optional[list] = None, group=None, 
     sel = states[:, :, cols].contiguous()
     if gather:
         sel = gather_chains(sel, group=group)
+    if sel.shape[0] < 4:  # split chains need two draws per half
+        nan = float("nan")
+        return dict(min_ess=nan, max_rhat=nan, columns=cols, ess=[nan] * len(cols), rhat=[nan] * len(cols),
+                    n_draws=int(sel.shape[0]), n_chains=int(sel.shape[1]))
     ess = [ess_bulk(sel[:, :, k]) for k in range(len(cols))]
     rhat = [split_rhat(sel[:, :, k]) for k in range(len(cols))]
     return dict(min_ess=min(ess), max_rhat=max(rhat), columns=cols, ess=ess, rhat=rhat,
