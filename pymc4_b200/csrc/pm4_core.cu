@@ -170,15 +170,31 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   return PM4_OK;
 }
 
-// transposed single-precision copy of every GLM term's covariates (the gradient GEMM contracts over observations)
-static int upload_glm(pm4_model* m, const double* dataf) {
-  for (GlmTerm& g : m->glm) {
-    std::vector<float> xt((size_t)g.P * g.ldxt, 0.0f);
-    for (int i = 0; i < g.n; ++i)
-      for (int q = 0; q < g.P; ++q) xt[(size_t)q * g.ldxt + i] = (float)dataf[g.x_off + (int64_t)i * g.P + q];
-    if (!g.d_xt) CU(cudaMalloc(&g.d_xt, sizeof(float) * xt.size()));
-    CU(cudaMemcpy(g.d_xt, xt.data(), sizeof(float) * xt.size(), cudaMemcpyHostToDevice));
+// Xt[q, i] = X[i, q] through a 32 x 33 shared-memory tile (both sides coalesced); columns i >= n stay zero
+__global__ void transpose_kernel(const float* __restrict__ X, int n, int P, float* __restrict__ Xt, int ldxt) {
+  __shared__ float tile[32][33];
+  const int i0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r, q = q0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && q < P) ? X[(size_t)i * P + q] : 0.0f;
   }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int q = q0 + r, i = i0 + threadIdx.x;
+    if (q < P && i < ldxt) Xt[(size_t)q * ldxt + i] = tile[threadIdx.x][r];
+  }
+}
+
+// transposed single-precision copy of every GLM term's covariates (the gradient GEMM contracts over observations),
+// made on the device from the pool upload_pools has just written
+static int upload_glm(pm4_model* m, const double*) {
+  for (GlmTerm& g : m->glm) {
+    if (!g.d_xt) CU(cudaMalloc(&g.d_xt, sizeof(float) * (size_t)g.P * g.ldxt));
+    transpose_kernel<<<dim3((unsigned)((g.ldxt + 31) / 32), (unsigned)((g.P + 31) / 32)), dim3(32, 8)>>>(
+        m->d_f32 + g.x_off, g.n, g.P, g.d_xt, g.ldxt);
+    CU(cudaGetLastError());
+  }
+  CU(cudaDeviceSynchronize());
   return PM4_OK;
 }
 

@@ -40,7 +40,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     """Compile a C probe against the public header and compare sizeof/offsetof with ctypes."""
     structs = {
         "pm4_rv_t": (I.CRV, ["offset", "size", "transform", "shift", "scale"]),
-        "pm4_term_t": (I.CTerm, ["kind", "n", "op_begin", "op_end", "n_regs", "value_reg", "param_reg", "plan"]),
+        "pm4_term_t": (I.CTerm, ["kind", "n", "op_begin", "op_end", "n_regs", "value_reg", "param_reg", "plan", "observed",
+                                 "ll_offset", "glm_base", "glm_p", "glm_x", "glm_y", "gp_par"]),
         "pm4_op_t": (I.COp, ["opcode", "dst", "a", "b", "mode", "base", "blob", "imm"]),
         "pm4_det_t": (I.CDet, ["n", "op_begin", "op_end", "n_regs", "value_reg", "out_offset"]),
         "pm4_plan_t": (I.CPlan, ["term", "n_gather", "width", "meta", "recs"]),
