@@ -254,7 +254,7 @@ static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, 
     }
     int rc = pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
                                g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
-    g_launches += grad ? 3 : 2;
+    g_launches += grad ? 4 : 3;
     if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GLM kernels: %s", rc < 0 ? "unsupported shape (P must be a multiple of 4, at most 104)" : cudaGetErrorString((cudaError_t)rc));
   }
   return PM4_OK;

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_3xtf32_kernel(const float* __r
 //   3xTF32 MMAs into TMEM, epilogue from TMEM: residuals r = y - sigmoid(eta) to global, TRANSPOSED
 //   (Rt[Cp, Np]: a lane owns an observation, so the stores of one chain are coalesced), the tile's column
 //   sums of the log-likelihood to LP[tile, Cp] (deterministic: no atomics).
-// Kernel 2 (grad): one CTA per (observation split) x (128 chains), looping over 64-observation tiles:
+// Kernel 2 (grad): one CTA per (observation split) x (128 chains), looping over 32-observation tiles:
 //   Rt tile and Xt tile (the covariates transposed once at model creation) staged K-major -- the
 //   contraction runs over observations -- with 16-byte loads and stores, 3xTF32 MMAs accumulating
 //   G[chain, p] in TMEM over all tiles of the split, then G to GP[split, Cp, Pp].
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_3xtf32_kernel(const float* __r
 //   operands in memory keeps both GEMMs on the K-major path.)
 // Kernel 3: fixed-order reductions of LP and GP in double precision into lp[C] and grad[C, D].
 // ------------------------------------------------------------------------------------------
-constexpr int KT2 = 64;  // observations per tile of the gradient kernel
+constexpr int KT2 = 32;  // observations per tile of the gradient kernel (60 KB of operands: two CTAs per SM overlap staging and MMA)
 constexpr int NT = 512;  // threads per CTA of the GLM kernels: 16 warps stage the operands and share the epilogue
                          // (warp w reads TMEM lanes 32 (w % 4) .. + 31, column block w / 4)
 
@@ -245,17 +245,25 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // stage X[n0 .. n0+127, :] and beta[c0 .. c0+127, :] (zero padded), split into two TF32 terms
-  for (int idx = tid; idx < TILE * K; idx += blockDim.x) {
-    const int row = idx / K, k = idx - row * K;
-    const float a = (n0 + row < n && k < P) ? X[(size_t)(n0 + row) * P + k] : 0.0f;
-    const float b = (c0 + row < C && k < P) ? theta[(size_t)(c0 + row) * ldt + base + k] : 0.0f;
-    const float ah = to_tf32(a), bh = to_tf32(b);
+  // stage X[n0 .. n0+127, :] and beta[c0 .. c0+127, :] (zero padded), split into two TF32 terms; 16 bytes at a
+  // time (P is a multiple of 4, so a group of 4 covariates is whole or absent; rows of X are 16-byte aligned)
+  const int K4 = K >> 2;
+#pragma unroll 2
+  for (int idx = tid; idx < TILE * K4; idx += NT) {
+    const int row = idx / K4, k = (idx - row * K4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (n0 + row < n && k < P) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + row) * P + k));
+    if (c0 + row < C && k < P) {
+      const float* tp = theta + (size_t)(c0 + row) * ldt + base + k;
+      b = make_float4(tp[0], tp[1], tp[2], tp[3]);
+    }
+    const float4 ah = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
+    const float4 bh = make_float4(to_tf32(b.x), to_tf32(b.y), to_tf32(b.z), to_tf32(b.w));
     const uint32_t off = op_offset(row, k, K);
-    *reinterpret_cast<float*>(a_hi + off) = ah;
-    *reinterpret_cast<float*>(a_lo + off) = to_tf32(a - ah);
-    *reinterpret_cast<float*>(b_hi + off) = bh;
-    *reinterpret_cast<float*>(b_lo + off) = to_tf32(b - bh);
+    *reinterpret_cast<float4*>(a_hi + off) = ah;
+    *reinterpret_cast<float4*>(a_lo + off) = make_float4(to_tf32(a.x - ah.x), to_tf32(a.y - ah.y), to_tf32(a.z - ah.z), to_tf32(a.w - ah.w));
+    *reinterpret_cast<float4*>(b_hi + off) = bh;
+    *reinterpret_cast<float4*>(b_lo + off) = make_float4(to_tf32(b.x - bh.x), to_tf32(b.y - bh.y), to_tf32(b.z - bh.z), to_tf32(b.w - bh.w));
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -293,9 +301,11 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
       for (int j = 0; j < 32; ++j) {
         const float eta = __uint_as_float(v[j]);
         // softplus(eta) = max(eta, 0) + log1p(exp(-|eta|)); sigmoid from the same exponential
+        // (MUFU ex2 / lg2 / rcp: 1 + e lies in (1, 2], so the absolute error of each term stays ~1e-7)
         const float e = __expf(-fabsf(eta));
-        const float sp = fmaxf(eta, 0.0f) + log1pf(e);
-        const float sg = eta >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+        const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + e);
+        const float rc = __fdividef(1.0f, 1.0f + e);
+        const float sg = eta >= 0.0f ? rc : e * rc;
         ll[j] = live ? yv * eta - sp : 0.0f;
         v[j] = __float_as_uint(live ? yv - sg : 0.0f);
       }
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
 }
 
 // G[chain, p] = sum over the observations of this split of Rt[chain, n] * Xt[p, n]
-__global__ void __launch_bounds__(NT, 1) glm_grad_kernel(const float* __restrict__ Xt, int ldx, int n, int P,
+__global__ void __launch_bounds__(NT, 2) glm_grad_kernel(const float* __restrict__ Xt, int ldx, int n, int P,
                                                           const float* __restrict__ Rt, int Np, int Cp,
                                                           float* __restrict__ GP, int Pp, int n_splits,
                                                           int* __restrict__ error) {
@@ -345,39 +355,66 @@ __global__ void __launch_bounds__(NT, 1) glm_grad_kernel(const float* __restrict
   const int n_tiles = (n + KT2 - 1) / KT2;
   uint32_t acc = 0, parity = 0;
   bool ok = true;
-  // stage `rows` rows of a [rows, ld] matrix, columns nb .. nb+63, K-major, split into two TF32 terms
-  auto stage = [&](const float* __restrict__ src, int ld, int rows, int rows_valid, int nb, unsigned char* hi, unsigned char* lo) {
-    for (int idx = tid; idx < rows * (KT2 / 4); idx += blockDim.x) {
-      const int row = idx / (KT2 / 4), k4 = idx - row * (KT2 / 4);
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (row < rows_valid) {
-        const float* p = src + (size_t)row * ld + nb + 4 * k4;
-        if (nb + 4 * k4 + 3 < n) {
-          const float4 q = *reinterpret_cast<const float4*>(p);
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
+  // Each thread carries one tile's share of the operands in registers: 2 x 16 bytes of Rt (128 rows x 32
+  // observations) and up to 2 x 16 bytes of Xt (Pp rows).  The loads of tile t + 1 are issued right after the
+  // MMAs of tile t, so the memory latency overlaps the tensor core (and the co-resident CTA).
+  constexpr int Q = KT2 / 4;  // 16-byte groups per row
+  float4 ra[2], rb[2];
+  auto fetch = [&](int nb) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) if (nb + 4 * k4 + j < n) v[j] = p[j];
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * NT, row = idx / Q, k = (idx - row * Q) * 4;
+      ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[u] = ra[u];
+      const bool whole = nb + k + 3 < n;  // observations >= n: Rt is not written there, both operands read as zero
+      if (row < TILE) {
+        const float* p = Rt + (size_t)(c0 + row) * Np + nb + k;
+        if (whole) ra[u] = *reinterpret_cast<const float4*>(p);
+        else {
+          if (nb + k < n) ra[u].x = p[0];
+          if (nb + k + 1 < n) ra[u].y = p[1];
+          if (nb + k + 2 < n) ra[u].z = p[2];
         }
       }
-      const float4 h = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-      const float4 l = make_float4(to_tf32(v[0] - h.x), to_tf32(v[1] - h.y), to_tf32(v[2] - h.z), to_tf32(v[3] - h.w));
-      const uint32_t off = op_offset(row, 4 * k4, KT2);
-      *reinterpret_cast<float4*>(hi + off) = h;
-      *reinterpret_cast<float4*>(lo + off) = l;
+      if (row < P) {
+        const float* p = Xt + (size_t)row * ldx + nb + k;
+        if (whole) rb[u] = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+          if (nb + k < n) rb[u].x = p[0];
+          if (nb + k + 1 < n) rb[u].y = p[1];
+          if (nb + k + 2 < n) rb[u].z = p[2];
+        }
+      }
     }
   };
+  auto split_store = [&](const float4& v, unsigned char* hi, unsigned char* lo, uint32_t off) {
+    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+  };
+  if (split < n_tiles) fetch(split * KT2);
   for (int t = split; t < n_tiles && ok; t += n_splits) {
-    const int nb = t * KT2;
-    stage(Rt + (size_t)c0 * Np, Np, TILE, TILE, nb, a_hi, a_lo);
-    stage(Xt, ldx, Pp, P, nb, b_hi, b_lo);
+    // the operand buffers are reused: wait until the tensor core has consumed the previous tile
+    if (acc) {
+      ok = mbar_wait(mbar, parity);
+      parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!ok) break;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * NT, row = idx / Q, k = (idx - row * Q) * 4;
+      const uint32_t off = op_offset(row, k, KT2);
+      if (row < TILE) split_store(ra[u], a_hi, a_lo, off);
+      if (row < Pp) split_store(rb[u], b_hi, b_lo, off);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {
       const uint32_t idesc = make_idesc(TILE, Pp);
-      const uint32_t sbo = (uint32_t)(KT2 / 4) * 128u, lbo = 128u;
+      const uint32_t sbo = (uint32_t)Q * 128u, lbo = 128u;
       for (int pass = 0; pass < 3; ++pass) {
         const unsigned char* ap = pass == 1 ? a_lo : a_hi;
         const unsigned char* bp = pass == 2 ? b_lo : b_hi;
@@ -388,9 +425,10 @@ __global__ void __launch_bounds__(NT, 1) glm_grad_kernel(const float* __restrict
       mma_commit(mbar);
     }
     acc = 1;  // CTA-uniform: the accumulator holds at least one tile from here on
-    // the operand buffers are reused by the next tile: wait until the tensor core has consumed them
+    if (t + n_splits < n_tiles) fetch((t + n_splits) * KT2);
+  }
+  if (ok && acc) {  // the last tile's MMAs
     ok = mbar_wait(mbar, parity);
-    parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   if (!ok) {
@@ -411,14 +449,31 @@ __global__ void __launch_bounds__(NT, 1) glm_grad_kernel(const float* __restrict
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE));
 }
 
-// fixed-order reductions in double precision: lp[c] += sum_tiles LP[tile, c]; grad[c, base + p] += sum_splits GP[s, c, p]
-__global__ void glm_reduce_kernel(const float* __restrict__ LP, int n_tiles, const float* __restrict__ GP, int n_splits,
+// first level of the log-likelihood reduction: group g of the observation tiles, 32 chains x 8 tile lanes per block,
+// fixed order (LP2[g, c] = sum over the group's tiles, double)
+constexpr int LP_GROUPS = 64;
+__global__ void __launch_bounds__(256) glm_lp_kernel(const float* __restrict__ LP, int n_tiles, int Cp, double* __restrict__ LP2) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + cx, g = blockIdx.y;
+  const int per = (n_tiles + LP_GROUPS - 1) / LP_GROUPS, t0 = g * per, t1 = min(n_tiles, t0 + per);
+  double s = 0;
+  for (int t = t0 + ty; t < t1; t += 8) s += (double)LP[(size_t)t * Cp + c];
+  red[ty][cx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    for (int k = 1; k < 8; ++k) s += red[k][cx];
+    LP2[(size_t)g * Cp + c] = s;
+  }
+}
+
+// fixed-order reductions in double precision: lp[c] += sum_groups LP2[g, c]; grad[c, base + p] += sum_splits GP[s, c, p]
+__global__ void glm_reduce_kernel(const double* __restrict__ LP2, const float* __restrict__ GP, int n_splits,
                                   int Cp, int Pp, int C, int P, float* __restrict__ lp, float* __restrict__ grad, int ldg,
                                   int base) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C) {
     double s = 0;
-    for (int t = 0; t < n_tiles; ++t) s += (double)LP[(size_t)t * Cp + idx];
+    for (int g = 0; g < LP_GROUPS; ++g) s += LP2[(size_t)g * Cp + idx];
     lp[idx] += (float)s;
   }
   if (grad && idx < C * P) {
@@ -466,7 +521,7 @@ static int64_t glm_np(int n) { return ((int64_t)n + KT2 - 1) / KT2 * KT2; }
 extern "C" int64_t pm4_glm_work_bytes(int n, int P, int C) {
   const int64_t Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16;
   const int64_t n_tiles = (n + TILE - 1) / TILE;
-  return 4 * (glm_np(n) * Cp + n_tiles * Cp + (int64_t)glm_splits((int)Cp) * Cp * Pp) + 256;
+  return 4 * (glm_np(n) * Cp + n_tiles * Cp + (int64_t)glm_splits((int)Cp) * Cp * Pp) + 8 * LP_GROUPS * Cp + 256;
 }
 
 extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P,
@@ -481,6 +536,7 @@ extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, cons
   float* Rt = (float*)work;
   float* LP = Rt + (size_t)Np * Cp;
   float* GP = LP + (size_t)n_tiles * Cp;
+  double* LP2 = (double*)(((uintptr_t)(GP + (size_t)splits * Cp * Pp) + 15) & ~(uintptr_t)15);
   const size_t smem1 = 4 * (size_t)TILE * K * 4 + 16 + 4 * TILE * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(glm_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return (int)e;
@@ -492,6 +548,7 @@ extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, cons
     glm_grad_kernel<<<dim3(splits, Cp / TILE), NT, smem2, st>>>(Xt, ldxt, n, P, Rt, Np, Cp, GP, Pp, splits, error_dev);
   }
   const int work_items = grad ? C * P : C;
-  glm_reduce_kernel<<<(work_items + 255) / 256, 256, 0, st>>>(LP, n_tiles, GP, splits, Cp, Pp, C, P, lp, grad, ldg, base);
+  glm_lp_kernel<<<dim3(Cp / 32, LP_GROUPS), 256, 0, st>>>(LP, n_tiles, Cp, LP2);
+  glm_reduce_kernel<<<(work_items + 255) / 256, 256, 0, st>>>(LP2, GP, splits, Cp, Pp, C, P, lp, grad, ldg, base);
   return (int)cudaGetLastError();
 }
