@@ -14,6 +14,7 @@
 // 8-row groups.  One thread issues the MMAs and commits them to an mbarrier; the four warps read
 // the accumulator back with tcgen05.ld (warp w owns TMEM lanes 32w .. 32w+31).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 
 #include "../../include/pm4b200.h"
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
                                                          float* __restrict__ Rt, int Np, int Cp,
                                                          float* __restrict__ LP, int* __restrict__ error) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int K = (P + 7) & ~7;
+  const int K = (P + 7) & ~7, K4 = K >> 2;
   const uint32_t op_bytes = (uint32_t)TILE * (uint32_t)K * 4u;
   unsigned char* a_hi = smem;
   unsigned char* a_lo = a_hi + op_bytes;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   float* colsum = reinterpret_cast<float*>(mbar + 2);  // [4][128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * TILE, c0 = blockIdx.y * TILE;
+  const int c0 = blockIdx.y * TILE, n_tiles = (n + TILE - 1) / TILE;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TILE));
@@ -245,52 +246,65 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // stage X[n0 .. n0+127, :] and beta[c0 .. c0+127, :] (zero padded), split into two TF32 terms; 16 bytes at a
-  // time (P is a multiple of 4, so a group of 4 covariates is whole or absent; rows of X are 16-byte aligned)
-  const int K4 = K >> 2;
-#pragma unroll 2
+  auto split_store = [&](const float4& v, unsigned char* hi, unsigned char* lo, uint32_t off) {
+    const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+  };
+  // the CTA's chain tile beta[c0 .. c0+127, :] is staged ONCE (zero padded, split into two TF32 terms); the CTA then
+  // walks over observation tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   for (int idx = tid; idx < TILE * K4; idx += NT) {
     const int row = idx / K4, k = (idx - row * K4) * 4;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (n0 + row < n && k < P) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + row) * P + k));
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c0 + row < C && k < P) {
       const float* tp = theta + (size_t)(c0 + row) * ldt + base + k;
       b = make_float4(tp[0], tp[1], tp[2], tp[3]);
     }
-    const float4 ah = make_float4(to_tf32(a.x), to_tf32(a.y), to_tf32(a.z), to_tf32(a.w));
-    const float4 bh = make_float4(to_tf32(b.x), to_tf32(b.y), to_tf32(b.z), to_tf32(b.w));
-    const uint32_t off = op_offset(row, k, K);
-    *reinterpret_cast<float4*>(a_hi + off) = ah;
-    *reinterpret_cast<float4*>(a_lo + off) = make_float4(to_tf32(a.x - ah.x), to_tf32(a.y - ah.y), to_tf32(a.z - ah.z), to_tf32(a.w - ah.w));
-    *reinterpret_cast<float4*>(b_hi + off) = bh;
-    *reinterpret_cast<float4*>(b_lo + off) = make_float4(to_tf32(b.x - bh.x), to_tf32(b.y - bh.y), to_tf32(b.z - bh.z), to_tf32(b.w - bh.w));
+    split_store(b, b_hi, b_lo, op_offset(row, k, K));
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {
-    const uint32_t idesc = make_idesc(TILE, TILE);
-    const uint32_t sbo = (uint32_t)(K / 4) * 128u, lbo = 128u;
-    uint32_t acc = 0;
-    for (int pass = 0; pass < 3; ++pass) {  // hi*hi, lo*hi, hi*lo
-      const unsigned char* ap = pass == 1 ? a_lo : a_hi;
-      const unsigned char* bp = pass == 2 ? b_lo : b_hi;
-      for (int ks = 0; ks < K / UMMA_K; ++ks) {
-        mma_tf32(tmem, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
-                 make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, acc);
-        acc = 1;
-      }
+  const int lg = warp & 3, row = lg * 32 + lane;
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n0 = tile * TILE;
+    // stage X[n0 .. n0+127, :], 16 bytes at a time (P is a multiple of 4: a group of 4 covariates is whole or
+    // absent; rows of X are 16-byte aligned)
+#pragma unroll 2
+    for (int idx = tid; idx < TILE * K4; idx += NT) {
+      const int r = idx / K4, k = (idx - r * K4) * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + r < n && k < P) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * P + k));
+      split_store(a, a_hi, a_lo, op_offset(r, k, K));
     }
-    mma_commit(mbar);
-  }
-  const bool ok = mbar_wait(mbar, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (!ok) {
-    if (tid == 0 && error) *error = 1;
-  } else {
-    const int lg = warp & 3, row = lg * 32 + lane;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+      const uint32_t idesc = make_idesc(TILE, TILE);
+      const uint32_t sbo = (uint32_t)(K / 4) * 128u, lbo = 128u;
+      uint32_t acc = 0;
+      for (int pass = 0; pass < 3; ++pass) {  // hi*hi, lo*hi, hi*lo
+        const unsigned char* ap = pass == 1 ? a_lo : a_hi;
+        const unsigned char* bp = pass == 2 ? b_lo : b_hi;
+        for (int ks = 0; ks < K / UMMA_K; ++ks) {
+          mma_tf32(tmem, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
+                   make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, acc);
+          acc = 1;
+        }
+      }
+      mma_commit(mbar);
+    }
+    const bool ok = mbar_wait(mbar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok) {  // CTA-uniform (every thread waits on the same phase)
+      if (tid == 0 && error) *error = 1;
+      break;
+    }
     const bool live = n0 + row < n;
     const float yv = live ? y[n0 + row] : 0.0f;
     for (int cc = (warp >> 2) * 32; cc < TILE; cc += (NT / 128) * 32) {
@@ -318,7 +332,11 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     }
     __syncthreads();
     if (tid < TILE)
-      LP[(size_t)blockIdx.x * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
+      LP[(size_t)tile * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
+    // the accumulator, the X buffers and colsum are reused by the next tile
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -540,7 +558,9 @@ extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, cons
   const size_t smem1 = 4 * (size_t)TILE * K * 4 + 16 + 4 * TILE * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(glm_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   if (e != cudaSuccess) return (int)e;
-  glm_eta_kernel<<<dim3(n_tiles, Cp / TILE), NT, smem1, st>>>(X, y, n, P, theta, ldt, base, C, Rt, Np, Cp, LP, error_dev);
+  // one CTA per SM (213 KB of operands): two waves of 148 CTAs, each walking its share of the observation tiles
+  const int eta_groups = std::max(1, std::min(n_tiles, splits));
+  glm_eta_kernel<<<dim3(eta_groups, Cp / TILE), NT, smem1, st>>>(X, y, n, P, theta, ldt, base, C, Rt, Np, Cp, LP, error_dev);
   if (grad) {
     const size_t smem2 = 2 * (size_t)TILE * KT2 * 4 + 2 * (size_t)Pp * KT2 * 4 + 64;
     e = cudaFuncSetAttribute(glm_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
