@@ -13,10 +13,10 @@
 //   v = L^-1 y, alpha = K^-1 y                                               gp_v_kernel, gp_alpha_kernel
 //   S     = sum_ij (alpha_i alpha_j - (Zt Zt^T)_ij) {K_se, K_se d^2, I}_ij   gp_nt_kernel<DOT>  (K^-1 is never stored)
 //   lp    = -1/2 |v|^2 - sum log L_ii - n/2 log 2 pi,  d lp / d(l, a, noise) from S       gp_finish_kernel
-// All of it in float64 on the FP64 pipe (B200: 64 DFMA/clk/SM), whatever the sampling dtype: the kernel matrix
+// All of it in float64 (B200: 64 FP64 FMA/clk/SM, through DFMA or the FP64 tensor-core MMA), whatever the sampling dtype: the kernel matrix
 // of a smooth covariance function has a condition number ~ a^2 n / noise, out of reach of float32 or of
 // split-TF32 tensor-core arithmetic.  The O(n^3) work is three passes of ONE tile kernel, C[I, J] -= sum_k
-// A[I, k] B[J, k] on 64 x 64 tiles with 8 x 8 register blocking: n^3/3 flops each for the factor, the inverse
+// A[I, k] B[J, k] on 64 x 64 tiles of FP64 tensor-core MMAs (mma.sync m8n8k4): n^3/3 flops each for the factor, the inverse
 // factor and the contraction with dK.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int NB = 64;   // block size of the factorisation
-constexpr int KS = 8;    // k-slab of the tile kernel
+constexpr int KS = 16;   // k-slab of the tile kernel
 
 struct GpShape {
   int n, np, nt, d, C;             // points, padded points (multiple of NB), tiles per side, features, chains in this chunk
@@ -92,56 +92,66 @@ __global__ void __launch_bounds__(256) gp_build_kernel(GpShape s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// the tile kernel: acc[I, J] = sum_{k in [k0, k1)} A[I, k] B[J, k], 64 x 64 per block, 64 threads x (8 x 8)
+// the tile kernel: acc[I, J] = sum_{k in [k0, k1)} A[I, k] B[J, k], 64 x 64 per block, 4 warps x (4 x 4 MMA tiles)
 // ------------------------------------------------------------------------------------------
 enum { MODE_CHOL = 0, MODE_ZT = 1, MODE_DOT = 2 };
 
-// 64 threads per 64 x 64 tile, 8 x 8 results per thread: thread (tx, ty) of the 8 x 8 grid owns rows
-// {ty 4 .. + 3} and {32 + ty 4 .. + 3} and the column pairs 16 m + 2 tx + {0, 1}, m = 0 .. 3.  Per slab row that is
-// 8 LDS.128 (one shared-memory wavefront each: the lanes of a warp read 4 distinct 16-byte row pieces or 128
-// contiguous column bytes) for 64 DFMA -- the FP64 pipe, not shared memory, is the limiter.  The next slab is
-// fetched into registers while the current one is multiplied.
-constexpr int NT_THREADS = 64;
-__device__ __forceinline__ int tile_row(int ty, int i) { return (i >> 2) * 32 + ty * 4 + (i & 3); }
-__device__ __forceinline__ int tile_col(int tx, int j) { return (j >> 1) * 16 + tx * 2 + (j & 1); }
+// 128 threads (4 warps) per 64 x 64 tile; warp (wr, wc) owns the 32 x 32 quadrant as 4 x 4 FP64 tensor-core tiles
+// (mma.sync m8n8k4: the form cuBLAS DGEMM uses on this part).  Per k4 step a thread reads 8 doubles from shared
+// memory for 16 MMAs = 4096 FMAs per warp: a quarter of the shared-memory traffic per flop of an 8 x 8 register
+// tile on the DFMA pipe, which is what limited the previous version (LSU data pipe 69 % busy at 44 % FP64).
+// Fragments (PTX ISA, mma.m8n8k4.f64): A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4],
+// C[row = lane / 4][col = 2 (lane % 4) + {0, 1}].  Slabs are stored k-major with a row stride of 68 doubles:
+// the 16 lanes of a half-warp then hit 16 distinct 8-byte banks.  The next slab is fetched into registers while
+// the current one is multiplied.
+constexpr int NT_THREADS = 128;
+constexpr int SLD = NB + 4;  // slab row stride in doubles
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// element (mi, ni, e) of a thread's accumulators inside the 64 x 64 tile
+__device__ __forceinline__ int tile_row(int wr, int lane, int mi) { return wr * 32 + mi * 8 + (lane >> 2); }
+__device__ __forceinline__ int tile_col(int wc, int lane, int ni) { return wc * 32 + ni * 8 + (lane & 3) * 2; }
 
 __device__ __forceinline__ void tile_nt(const double* __restrict__ A, const double* __restrict__ B, int ld, int k0, int k1,
-                                        double (&acc)[8][8], double (*As)[NB + 2], double (*Bs)[NB + 2]) {
-  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
+                                        double (&acc)[4][4][2], double (*As)[SLD], double (*Bs)[SLD]) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, wr = warp >> 1, wc = warp & 1;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
   if (k0 >= k1) return;
-  const double* ap = A + (size_t)t * ld;  // this thread stages row t of both slabs
-  const double* bp = B + (size_t)t * ld;
+  const int sr = t & 63, sk = (t >> 6) * 8;  // this thread stages row sr, slab columns sk .. sk + 7 of both slabs
+  const double* ap = A + (size_t)sr * ld + sk;
+  const double* bp = B + (size_t)sr * ld + sk;
   double4 a0 = *reinterpret_cast<const double4*>(ap + k0), a1 = *reinterpret_cast<const double4*>(ap + k0 + 4);
   double4 b0 = *reinterpret_cast<const double4*>(bp + k0), b1 = *reinterpret_cast<const double4*>(bp + k0 + 4);
+  const int fr = lane >> 2, fk = lane & 3;
   for (int k = k0; k < k1; k += KS) {
     __syncthreads();
-    As[0][t] = a0.x; As[1][t] = a0.y; As[2][t] = a0.z; As[3][t] = a0.w;
-    As[4][t] = a1.x; As[5][t] = a1.y; As[6][t] = a1.z; As[7][t] = a1.w;
-    Bs[0][t] = b0.x; Bs[1][t] = b0.y; Bs[2][t] = b0.z; Bs[3][t] = b0.w;
-    Bs[4][t] = b1.x; Bs[5][t] = b1.y; Bs[6][t] = b1.z; Bs[7][t] = b1.w;
+    As[sk + 0][sr] = a0.x; As[sk + 1][sr] = a0.y; As[sk + 2][sr] = a0.z; As[sk + 3][sr] = a0.w;
+    As[sk + 4][sr] = a1.x; As[sk + 5][sr] = a1.y; As[sk + 6][sr] = a1.z; As[sk + 7][sr] = a1.w;
+    Bs[sk + 0][sr] = b0.x; Bs[sk + 1][sr] = b0.y; Bs[sk + 2][sr] = b0.z; Bs[sk + 3][sr] = b0.w;
+    Bs[sk + 4][sr] = b1.x; Bs[sk + 5][sr] = b1.y; Bs[sk + 6][sr] = b1.z; Bs[sk + 7][sr] = b1.w;
     __syncthreads();
     if (k + KS < k1) {
       a0 = *reinterpret_cast<const double4*>(ap + k + KS); a1 = *reinterpret_cast<const double4*>(ap + k + KS + 4);
       b0 = *reinterpret_cast<const double4*>(bp + k + KS); b1 = *reinterpret_cast<const double4*>(bp + k + KS + 4);
     }
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      double a[8], b[8];
+    for (int k4 = 0; k4 < KS; k4 += 4) {
+      double a[4], b[4];
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
-        const double2 av = *reinterpret_cast<const double2*>(&As[kk][(h >> 1) * 32 + ty * 4 + (h & 1) * 2]);
-        const double2 bv = *reinterpret_cast<const double2*>(&Bs[kk][h * 16 + tx * 2]);
-        a[2 * h] = av.x; a[2 * h + 1] = av.y;
-        b[2 * h] = bv.x; b[2 * h + 1] = bv.y;
+        a[h] = As[k4 + fk][wr * 32 + h * 8 + fr];
+        b[h] = Bs[k4 + fk][wc * 32 + h * 8 + fr];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
     }
   }
 }
@@ -151,24 +161,24 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, const doub
 // MODE_DOT:  tile (I, J <= I) from the linear index blockIdx.x: G = Zt[I, I NB :] Zt[J, I NB :]^T, then the sums
 template <int MODE>
 __global__ void __launch_bounds__(NT_THREADS) gp_nt_kernel(GpShape s, int blk) {
-  __shared__ __align__(16) double As[KS][NB + 2];
-  __shared__ __align__(16) double Bs[KS][NB + 2];
+  __shared__ __align__(16) double As[KS][SLD];
+  __shared__ __align__(16) double Bs[KS][SLD];
   const int c = blockIdx.y, np = s.np;
   double* L = s.Kb + (size_t)c * np * np;
   double* Zt = s.Zt + (size_t)c * np * np;
-  const int t = threadIdx.x, tx = t & 7, ty = t >> 3;
-  double acc[8][8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, wr = warp >> 1, wc = warp & 1;
+  double acc[4][4][2];
   if (MODE == MODE_CHOL) {
     const int I = blk + blockIdx.x;
     tile_nt(L + (size_t)I * NB * np, L + (size_t)blk * NB * np, np, 0, blk * NB, acc, As, Bs);
     double* Ct = L + (size_t)I * NB * np + (size_t)blk * NB;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        double2* p = reinterpret_cast<double2*>(Ct + (size_t)tile_row(ty, i) * np + tile_col(tx, 2 * h));
+      for (int j = 0; j < 4; ++j) {
+        double2* p = reinterpret_cast<double2*>(Ct + (size_t)tile_row(wr, lane, i) * np + tile_col(wc, lane, j));
         double2 v = *p;
-        v.x -= acc[i][2 * h]; v.y -= acc[i][2 * h + 1];
+        v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
         *p = v;
       }
   } else if (MODE == MODE_ZT) {
@@ -176,14 +186,14 @@ __global__ void __launch_bounds__(NT_THREADS) gp_nt_kernel(GpShape s, int blk) {
     tile_nt(Zt + (size_t)J * NB * np, L + (size_t)blk * NB * np, np, J * NB, blk * NB, acc, As, Bs);
     double* Ct = Zt + (size_t)J * NB * np + (size_t)blk * NB;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = tile_row(ty, i);
+    for (int i = 0; i < 4; ++i) {
+      const int r = tile_row(wr, lane, i);
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int col = tile_col(tx, 2 * h);
+      for (int j = 0; j < 4; ++j) {
+        const int col = tile_col(wc, lane, j);
         double2 v;
-        v.x = ((J == blk && r == col) ? 1.0 : 0.0) - acc[i][2 * h];
-        v.y = ((J == blk && r == col + 1) ? 1.0 : 0.0) - acc[i][2 * h + 1];
+        v.x = ((J == blk && r == col) ? 1.0 : 0.0) - acc[i][j][0];
+        v.y = ((J == blk && r == col + 1) ? 1.0 : 0.0) - acc[i][j][1];
         *reinterpret_cast<double2*>(Ct + (size_t)r * np + col) = v;
       }
     }
@@ -200,20 +210,22 @@ __global__ void __launch_bounds__(NT_THREADS) gp_nt_kernel(GpShape s, int blk) {
     const double wt = (I == J) ? 1.0 : 2.0;
     double s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gi = I * NB + tile_row(ty, i);
+    for (int i = 0; i < 4; ++i) {
+      const int gi = I * NB + tile_row(wr, lane, i);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int gj = J * NB + tile_col(tx, j);
-        if (gi < s.n && gj < s.n) {
-          const double W = alpha[gi] * alpha[gj] - acc[i][j];
-          const double d2 = dist2(s.X, s.d, gi, gj);
-          const double kse = a2 * exp(inv * d2);
-          s1 += wt * W * kse;
-          s2 += wt * W * kse * d2;
-          if (gi == gj) s3 += W;
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gj = J * NB + tile_col(wc, lane, j) + e;
+          if (gi < s.n && gj < s.n) {
+            const double W = alpha[gi] * alpha[gj] - acc[i][j][e];
+            const double d2 = dist2(s.X, s.d, gi, gj);
+            const double kse = a2 * exp(inv * d2);
+            s1 += wt * W * kse;
+            s2 += wt * W * kse * d2;
+            if (gi == gj) s3 += W;
+          }
         }
-      }
     }
     // block reduction in a fixed order
     __shared__ double red[3][NT_THREADS];
