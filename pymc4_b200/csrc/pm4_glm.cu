@@ -253,8 +253,10 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
   };
   // the CTA's chain tile beta[c0 .. c0+127, :] is staged ONCE (zero padded, split into two TF32 terms); the CTA then
   // walks over observation tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  // (index map: 8 consecutive lanes take the 8 rows of one core matrix at the same k -- 128 contiguous bytes of
+  //  shared memory, no bank conflicts -- and the next 8 lanes the next 4 covariates of the same rows)
   for (int idx = tid; idx < TILE * K4; idx += NT) {
-    const int row = idx / K4, k = (idx - row * K4) * 4;
+    const int q = idx >> 3, row = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c0 + row < C && k < P) {
       const float* tp = theta + (size_t)(c0 + row) * ldt + base + k;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     // absent; rows of X are 16-byte aligned)
 #pragma unroll 2
     for (int idx = tid; idx < TILE * K4; idx += NT) {
-      const int r = idx / K4, k = (idx - r * K4) * 4;
+      const int q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (n0 + r < n && k < P) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * P + k));
       split_store(a, a_hi, a_lo, op_offset(r, k, K));
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(NT, 2) glm_grad_kernel(const float* __restrict
   auto fetch = [&](int nb) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int idx = tid + u * NT, row = idx / Q, k = (idx - row * Q) * 4;
+      const int idx = tid + u * NT, q = idx >> 3, row = (q / Q) * 8 + (idx & 7), k = (q % Q) * 4;
       ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       rb[u] = ra[u];
       const bool whole = nb + k + 3 < n;  // observations >= n: Rt is not written there, both operands read as zero
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(NT, 2) glm_grad_kernel(const float* __restrict
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int idx = tid + u * NT, row = idx / Q, k = (idx - row * Q) * 4;
+      const int idx = tid + u * NT, q = idx >> 3, row = (q / Q) * 8 + (idx & 7), k = (q % Q) * 4;
       const uint32_t off = op_offset(row, k, KT2);
       if (row < TILE) split_store(ra[u], a_hi, a_lo, off);
       if (row < Pp) split_store(rb[u], b_hi, b_lo, off);
