@@ -270,16 +270,26 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
   const uint32_t tmem = *tmem_slot;
   const int lg = warp & 3, row = lg * 32 + lane;
   uint32_t parity = 0;
+  // X[n0 .. n0+127, :] travels through registers, 16 bytes at a time (P is a multiple of 4: a group of 4 covariates
+  // is whole or absent; rows of X are 16-byte aligned): the loads of the NEXT tile are issued before the MMAs of this
+  // one complete, so their latency hides behind the tensor core and the epilogue
+  constexpr int AU = (TILE * 26 + NT - 1) / NT;  // K <= 104: at most 7 groups per thread
+  float4 ra[AU];
+  auto fetch = [&](int n0) {
+#pragma unroll
+    for (int u = 0; u < AU; ++u) {
+      const int idx = tid + u * NT, q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
+      ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < TILE * K4 && n0 + r < n && k < P) ra[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * P + k));
+    }
+  };
+  if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x * TILE);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int n0 = tile * TILE;
-    // stage X[n0 .. n0+127, :], 16 bytes at a time (P is a multiple of 4: a group of 4 covariates is whole or
-    // absent; rows of X are 16-byte aligned)
-#pragma unroll 2
-    for (int idx = tid; idx < TILE * K4; idx += NT) {
-      const int q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + r < n && k < P) a = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * P + k));
-      split_store(a, a_hi, a_lo, op_offset(r, k, K));
+#pragma unroll
+    for (int u = 0; u < AU; ++u) {
+      const int idx = tid + u * NT, q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
+      if (idx < TILE * K4) split_store(ra[u], a_hi, a_lo, op_offset(r, k, K));
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -300,6 +310,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
       }
       mma_commit(mbar);
     }
+    if (tile + (int)gridDim.x < n_tiles) fetch((tile + (int)gridDim.x) * TILE);
     const bool ok = mbar_wait(mbar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
