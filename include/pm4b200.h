@@ -356,7 +356,7 @@ int pm4_model_attach_comm(pm4_model_t* m, pm4_comm_t* comm /* NULL detaches */);
  * tensor cores in 3xTF32, eta = X beta with the Bernoulli epilogue and g = X^T (y - sigmoid(eta)).
  *   X [n, P] row-major, Xt [P, ldxt] its transpose (ldxt >= n, multiple of 4), y [n] as float,
  *   theta [C, ldt] with beta at columns base .. base+P-1; adds into lp [C] and grad [C, ldg] (NULL: skip).
- *   P must be a multiple of 4, at most 104.  work: pm4_glm_work_bytes(n, P, C) bytes of device memory.
+ *   P at most 104 (multiples of 4 take the 16-byte load path).  work: pm4_glm_work_bytes(n, P, C) bytes of device memory.
  *   *error_dev (device int, zeroed by the caller) is set when a tensor-core step timed out.
  * pm4_glm_gemm_tile: one 128 x 128 tile C = A B^T of the same MMA path (kernel-level test). */
 int64_t pm4_glm_work_bytes(int n, int P, int C);

@@ -255,7 +255,7 @@ static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, 
     int rc = pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
                                g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
     g_launches += grad ? 4 : 3;
-    if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GLM kernels: %s", rc < 0 ? "unsupported shape (P must be a multiple of 4, at most 104)" : cudaGetErrorString((cudaError_t)rc));
+    if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GLM kernels: %s", rc < 0 ? "unsupported shape (at most 104 covariates)" : cudaGetErrorString((cudaError_t)rc));
   }
   return PM4_OK;
 }
@@ -368,7 +368,7 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
     for (int t = 0; t < ir->n_terms; ++t) {
       const pm4_term_t& tm = ir->terms[t];
       if (tm.kind != PM4_T_BERNOULLI_LOGIT_GLM) continue;
-      if (tm.glm_p <= 0 || tm.glm_p % 4 || tm.glm_p > 104) return fail(PM4_ENOSYS, "GLM term %d: the covariate count must be a multiple of 4, at most 104 (got %d)", t, tm.glm_p);
+      if (tm.glm_p <= 0 || tm.glm_p > 104) return fail(PM4_ENOSYS, "GLM term %d: at most 104 covariates fit the shared-memory operand tiles (got %d)", t, tm.glm_p);
       if (tm.glm_base < 0 || tm.glm_base + tm.glm_p > ir->D || tm.glm_x < 0 || tm.glm_x + (int64_t)tm.n * tm.glm_p > ir->n_dataf ||
           tm.glm_y < 0 || tm.glm_y + tm.n > ir->n_dataf)
         return fail(PM4_EINVAL, "GLM term %d points outside theta or the data pool", t);

@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c0 + row < C && k < P) {
       const float* tp = theta + (size_t)(c0 + row) * ldt + base + k;
-      b = make_float4(tp[0], tp[1], tp[2], tp[3]);
+      b.x = tp[0];
+      if (k + 1 < P) b.y = tp[1];
+      if (k + 2 < P) b.z = tp[2];
+      if (k + 3 < P) b.w = tp[3];
     }
     split_store(b, b_hi, b_lo, op_offset(row, k, K));
   }
@@ -275,12 +278,22 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
   // one complete, so their latency hides behind the tensor core and the epilogue
   constexpr int AU = (TILE * 26 + NT - 1) / NT;  // K <= 104: at most 7 groups per thread
   float4 ra[AU];
+  const bool vec4 = (P & 3) == 0;
   auto fetch = [&](int n0) {
 #pragma unroll
     for (int u = 0; u < AU; ++u) {
       const int idx = tid + u * NT, q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
       ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < TILE * K4 && n0 + r < n && k < P) ra[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)(n0 + r) * P + k));
+      if (idx < TILE * K4 && n0 + r < n && k < P) {
+        const float* xp = X + (size_t)(n0 + r) * P + k;
+        if (vec4) ra[u] = __ldg(reinterpret_cast<const float4*>(xp));  // P % 4 == 0: rows are 16-byte aligned
+        else {
+          ra[u].x = xp[0];
+          if (k + 1 < P) ra[u].y = xp[1];
+          if (k + 2 < P) ra[u].z = xp[2];
+          if (k + 3 < P) ra[u].w = xp[3];
+        }
+      }
     }
   };
   if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x * TILE);
@@ -558,7 +571,7 @@ extern "C" int64_t pm4_glm_work_bytes(int n, int P, int C) {
 extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P,
                                  const float* theta, int ldt, int base, int C, float* lp, float* grad, int ldg,
                                  void* work, int* error_dev, void* stream) {
-  if (n <= 0 || P <= 0 || P > 104 || P % 4 != 0 || C <= 0 || ldxt < n || ldxt % 4 != 0) return -22;
+  if (n <= 0 || P <= 0 || P > 104 || C <= 0 || ldxt < n || ldxt % 4 != 0) return -22;
   cudaStream_t st = (cudaStream_t)stream;
   const int Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16, K = (P + 7) & ~7;
   const int n_tiles = (n + TILE - 1) / TILE;

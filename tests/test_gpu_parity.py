@@ -433,7 +433,7 @@ def test_tcgen05_gemm_tile_3xtf32():
         assert 1e-5 < errs[0] < 2e-3 and errs[1] < 5e-6, errs
 
 
-@pytest.mark.parametrize("n,p,C", [(3000, 20, 96), (700, 100, 300)])
+@pytest.mark.parametrize("n,p,C", [(3000, 20, 96), (700, 100, 300), (500, 10, 40), (333, 7, 5)])
 def test_dense_glm_logp_grad_parity(n, p, C, oracle_mod):
     X, y = M.logistic_glm_data(n=n, p=p)
     ir, _, _ = lower_model(M.logistic_glm_model(X, y))
