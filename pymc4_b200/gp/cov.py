@@ -19,16 +19,42 @@ class Covariance:
     """Base class of the covariance functions (cov.py:84-298)."""
 
     def __init__(self, feature_ndims=1, active_dims=None, scale_diag=None, **kwargs):
+        if not isinstance(feature_ndims, (int, np.integer)) or feature_ndims <= 0:
+            raise ValueError(
+                "expected 'feature_ndims' to be an integer greater or equal to 1"
+                " but found {}.".format(feature_ndims)
+            )
         if feature_ndims != 1:
             raise NotImplementedError("feature_ndims > 1 is not built; flatten the feature axes")
+        kwargs.pop("ARD", None)
         if kwargs:
             raise TypeError("unexpected keyword arguments {}".format(sorted(kwargs)))
         self._feature_ndims = int(feature_ndims)
-        if active_dims is not None and not isinstance(active_dims, (int, np.integer)):
-            active_dims = tuple(int(a) for a in np.atleast_1d(active_dims).tolist())
+        # reference semantics (cov.py:115-146): an int k (or [k]) keeps the first k features, a nested list
+        # [[i, j, ...]] keeps those feature columns
+        self._columns = None
+        if active_dims is not None:
+            if isinstance(active_dims, (int, np.integer)):
+                active_dims = (int(active_dims),)
+            else:
+                active_dims = tuple(active_dims)
+            if len(active_dims) > self._feature_ndims:
+                raise ValueError(
+                    "'active_dims' contain more entries than number of feature dimensions."
+                    " Consider increasing the 'feature_ndims' or decreasing the entries"
+                    " in 'active_dims'. expected len(active_dims) < feature_ndims but got"
+                    " {} > {}".format(len(active_dims), self._feature_ndims)
+                )
+            dim = active_dims[0]
+            if isinstance(dim, slice):
+                self._columns = dim
+            elif isinstance(dim, (int, np.integer)):
+                self._columns = slice(0, int(dim))
+            else:
+                self._columns = [int(i) for i in dim]
         self._active_dims = active_dims
         self._scale_diag = scale_diag
-        self._ard = scale_diag is not None
+        self._ard = True
 
     @property
     def feature_ndims(self) -> int:
@@ -55,10 +81,8 @@ class Covariance:
             X2 = X2[:, None]
         if X1.ndim != 2 or X2.ndim != 2 or X1.shape[1] != X2.shape[1]:
             raise ValueError("expected points of shape [n, d], got {} and {}".format(X1.shape, X2.shape))
-        ad = self._active_dims
-        if ad is not None:
-            cols = list(range(ad)) if isinstance(ad, (int, np.integer)) else list(ad)
-            X1, X2 = X1[:, cols], X2[:, cols]
+        if self._columns is not None:
+            X1, X2 = X1[:, self._columns], X2[:, self._columns]
         if self._scale_diag is not None:
             sd = np.asarray(sym.as_numpy(self._scale_diag), dtype=np.float64)
             X1, X2 = X1 / sd, X2 / sd
@@ -75,10 +99,12 @@ class Covariance:
     def __call__(self, X1, X2, diag=False, to_dense=True):
         """Covariance matrix between the points ``X1`` and ``X2`` (cov.py:227-272)."""
         X1, X2 = self._slice(X1, X2)
-        if diag:
-            d = self._pointwise(X1, X2)
-            return np.diag(d) if to_dense else d
-        return self._matrix(X1, X2)
+        cov = self._matrix(X1, X2)
+        if diag and not to_dense:  # the reference's _diag (cov.py:182-187) returns the full matrix when to_dense
+            if isinstance(cov, sym.Expr):
+                raise NotImplementedError("diag=True needs concrete kernel parameters")
+            return np.diag(cov).copy()
+        return cov
 
 
 class Stationary(Covariance):

@@ -287,3 +287,41 @@ def test_trace_to_arviz_layout():
     assert tr.posterior["m/x"].shape == (4, 3, 2) and tr.sample_stats["lp"].shape == (4, 3)
     assert tr.posterior["m/x"][1, 2, 0] == post["m/x"][2, 1, 0]
     assert tr.groups() == ["posterior", "sample_stats", "observed_data"]
+
+
+def test_expquad_covariance_function_mirrors_the_reference():
+    """pm.gp.cov.ExpQuad against the reference's own expectations (/root/reference/tests/test_gp_cov.py:306-391,
+    pymc4/gp/cov.py:430-438): docstring matrix, the 2-point value behind test_scaled_cov (2 x 0.01831564 = 0.03663128),
+    active_dims slicing, argument validation, stabilize."""
+    import pymc4_b200 as pm
+
+    k = pm.gp.cov.ExpQuad(1.0)
+    x = np.array([[1.0, 2.0], [3.0, 4.0]])
+    np.testing.assert_allclose(2 * k(x, x), [[2.0, 0.03663128], [0.03663128, 2.0]], rtol=1e-6)
+    np.testing.assert_allclose(k(x[:, :1], x[:, :1]), pm.gp.cov.ExpQuad(1.0, 1.0, 1, 1)(x, x))       # first feature only
+    np.testing.assert_allclose(pm.gp.cov.ExpQuad(1.0, 1.0, 1, [[1]])(x, x), k(x[:, 1:], x[:, 1:]))  # listed column
+    rng = np.random.default_rng(0)
+    X1, X2 = rng.normal(size=(20, 5)), rng.normal(size=(7, 5))
+    ref = pm.gp.cov.ExpQuad(2.0, 1.5)
+    cov = pm.gp.cov.ExpQuad(2.0, 1.5, 1, 3)(X1, X2)
+    assert cov.shape == (20, 7)
+    np.testing.assert_allclose(cov, ref(X1[:, :3], X2[:, :3]))
+    np.testing.assert_allclose(pm.gp.cov.ExpQuad(2.0, 1.5, 1, [[0, 4]])(X1, X2), ref(X1[:, [0, 4]], X2[:, [0, 4]]))
+    np.testing.assert_allclose(ref(X1, X1, diag=True, to_dense=False), np.full(20, 1.5 ** 2))
+    np.testing.assert_allclose(ref.evaluate_kernel(X1[:7], X2), np.diag(ref(X1[:7], X2)))
+    assert np.all(np.linalg.eigvalsh(pm.gp.util.stabilize(ref(X1, X1))) > 0)
+    sd = np.array([1.0, 2.0, 0.5, 1.0, 4.0])
+    np.testing.assert_allclose(pm.gp.cov.ExpQuad(1.0, scale_diag=sd)(X1, X2), k(X1 / sd, X2 / sd))
+    with pytest.raises(ValueError, match=r"expected 'feature_ndims' to be an integer"):
+        pm.gp.cov.ExpQuad(1.0, 1.0, 0)
+    with pytest.raises(ValueError, match=r"active_dims' contain more entries than number of feature dimensions"):
+        pm.gp.cov.ExpQuad(1.0, 1.0, 1, [1, 2, 3, 4, 5])
+    # MvNormal on the host: scipy's density, shapes
+    from scipy.stats import multivariate_normal
+
+    K = pm.gp.util.stabilize(ref(X1, X1), 1e-6)
+    y = rng.normal(size=20)
+    d = pm.MvNormal("y", loc=0.5, covariance_matrix=K)
+    assert d.event_shape == (20,) and d.batch_shape == ()
+    np.testing.assert_allclose(d.log_prob(y), multivariate_normal(np.full(20, 0.5), K).logpdf(y), rtol=1e-9)
+    assert d.sample(seed=1).shape == (20,)
