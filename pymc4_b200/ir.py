@@ -306,13 +306,23 @@ class _Pools:
         self.f_len = 0
         self.i_len = 0
         self._fkey: Dict[bytes, int] = {}
+        self._fbig: Dict[Any, List[Tuple[int, np.ndarray]]] = {}
         self._ikey: Dict[bytes, int] = {}
 
     def add_f(self, arr: np.ndarray) -> int:
         arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
-        key = arr.tobytes()
-        if key in self._fkey:
-            return self._fkey[key]
+        big = arr.size > (1 << 20)
+        if big:
+            # large blobs (a 10^6 x 100 design matrix): a sampled fingerprint finds the candidates, an exact
+            # comparison confirms a duplicate -- hashing 800 MB per lowering would cost more than the upload
+            key = (arr.size, arr[:64].tobytes(), arr[-64:].tobytes(), arr[:: arr.size // 4096].tobytes())
+            for off, ref in self._fbig.get(key, ()):
+                if np.array_equal(ref, arr):
+                    return off
+        else:
+            key = arr.tobytes()
+            if key in self._fkey:
+                return self._fkey[key]
         # keep every blob 4-element aligned so 128-bit loads stay legal
         pad = (-self.f_len) % 4
         if pad:
@@ -321,7 +331,10 @@ class _Pools:
         off = self.f_len
         self.f.append(arr)
         self.f_len += arr.size
-        self._fkey[key] = off
+        if big:
+            self._fbig.setdefault(key, []).append((off, arr))
+        else:
+            self._fkey[key] = off
         return off
 
     def add_i(self, arr: np.ndarray) -> int:
