@@ -379,7 +379,7 @@ def run_b200(args):
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
     comm = None
-    if world > 1 and args.eps_mode == "pooled" and args.workload not in ("logit", "gp"):
+    if world > 1 and args.eps_mode == "pooled":
         # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
         # of the chains of ALL ranks (mailboxes in peer memory, read over NVLink by the dual-averaging kernel)
         comm = _cabi.Communicator(local_rank, rank, world)
@@ -484,7 +484,7 @@ def run_b200(args):
             from pymc4_b200.mcmc.samplers import HMC
 
             nuts = HMC(model, step_size=step_arr, num_leapfrog_steps=args.leapfrogs, num_adaptation_steps=B,
-                       device=local_rank, chain_offset=rank * C)
+                       device=local_rank, chain_offset=rank * C, **extra)
         else:
             nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C,
                         **extra)

@@ -627,7 +627,6 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
                          int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev, void* log_accept_dev,
                          int32_t* depth_dev, void* step_size_dev, int64_t* total_leapfrogs_dev, cudaStream_t st) {
   if (dtype != PM4_F32) return fail(PM4_ENOSYS, "the lock-step GLM path is float32 only");
-  if (m->comm && m->comm->world > 1) return fail(PM4_ENOSYS, "cross-GPU pooled step sizes are not built for the lock-step path");
   const int C = cfg->C, D = m->D, T = cfg->num_burnin + cfg->num_results;
   const size_t CD = (size_t)C * D;
   int rc;
@@ -635,6 +634,7 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
   memset(&r, 0, sizeof r);
   r.C = C;
   if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  fill_comm(m, r);  // chains sharded over the GPUs of the box: the pooled adaptation kernel exchanges over NVLink
   RunBuffers buf(st);
   pm4ls::NutsParams p;
   memset(&p, 0, sizeof p);
@@ -693,7 +693,8 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
   }
   CU(cudaGetLastError());
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
-  return check_glm(m, st);
+  if ((rc = check_glm(m, st))) return rc;
+  return (r.adapt_enabled && r.adapt_pooled) ? check_comm(m, st) : PM4_OK;
 }
 
 extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
@@ -759,7 +760,6 @@ static int hmc_lockstep(pm4_model* m, int dtype, const pm4_hmc_cfg_t* cfg, const
                         cudaStream_t st) {
   if (dtype != PM4_F32) return fail(PM4_ENOSYS, "the lock-step GLM path is float32 only");
   if (cfg->proposal != PM4_PROPOSAL_LEAPFROG) return fail(PM4_ENOSYS, "random-walk proposals are not built for GLM models");
-  if (m->comm && m->comm->world > 1) return fail(PM4_ENOSYS, "cross-GPU pooled step sizes are not built for the lock-step path");
   const int C = cfg->C, D = m->D, T = cfg->num_burnin + cfg->num_results;
   const size_t CD = (size_t)C * D;
   int rc;
@@ -767,6 +767,7 @@ static int hmc_lockstep(pm4_model* m, int dtype, const pm4_hmc_cfg_t* cfg, const
   memset(&r, 0, sizeof r);
   r.C = C;
   if ((rc = fill_adapt(r, cfg->adapt))) return rc;
+  fill_comm(m, r);  // chains sharded over the GPUs of the box: the pooled adaptation kernel exchanges over NVLink
   RunBuffers buf(st);
   pm4ls::Params p;
   memset(&p, 0, sizeof p);
@@ -817,7 +818,8 @@ static int hmc_lockstep(pm4_model* m, int dtype, const pm4_hmc_cfg_t* cfg, const
     r.adapt_pooled = p.adapt_pooled;
     MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   }
-  return check_glm(m, st);
+  if ((rc = check_glm(m, st))) return rc;
+  return (r.adapt_enabled && r.adapt_pooled) ? check_comm(m, st) : PM4_OK;
 }
 
 extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0_dev,
