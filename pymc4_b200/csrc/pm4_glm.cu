@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
   const int c0 = blockIdx.y * TILE, n_tiles = (n + TILE - 1) / TILE;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TILE));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * TILE));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
@@ -296,9 +296,10 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
       }
     }
   };
-  if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x * TILE);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * TILE;
+  // The accumulator is double-buffered in TMEM (2 x 128 columns): the MMAs of tile t + 1 are issued BEFORE the
+  // epilogue of tile t, so the tensor core works while the CUDA cores do the Bernoulli arithmetic and the stores.
+  // One X buffer is enough: it is rewritten only after the MMAs that read it have completed.
+  auto stage_and_issue = [&](uint32_t buf) {   // registers -> shared memory (split), then the 3 x K/8 MMAs
 #pragma unroll
     for (int u = 0; u < AU; ++u) {
       const int idx = tid + u * NT, q = idx >> 3, r = (q / K4) * 8 + (idx & 7), k = (q % K4) * 4;
@@ -316,26 +317,39 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
         const unsigned char* ap = pass == 1 ? a_lo : a_hi;
         const unsigned char* bp = pass == 2 ? b_lo : b_hi;
         for (int ks = 0; ks < K / UMMA_K; ++ks) {
-          mma_tf32(tmem, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
+          mma_tf32(tmem + buf * (uint32_t)TILE, make_desc(smem_u32(ap) + (uint32_t)ks * 256u, lbo, sbo),
                    make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, acc);
           acc = 1;
         }
       }
       mma_commit(mbar);
     }
-    if (tile + (int)gridDim.x < n_tiles) fetch((tile + (int)gridDim.x) * TILE);
-    const bool ok = mbar_wait(mbar, parity);
+  };
+  const int stride = (int)gridDim.x;
+  uint32_t buf = 0;
+  if ((int)blockIdx.x < n_tiles) {
+    fetch(blockIdx.x * TILE);
+    stage_and_issue(0);
+    if ((int)blockIdx.x + stride < n_tiles) fetch(((int)blockIdx.x + stride) * TILE);
+  }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += stride, buf ^= 1u) {
+    const int n0 = tile * TILE;
+    const bool ok = mbar_wait(mbar, parity);  // the MMAs of this tile
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (!ok) {  // CTA-uniform (every thread waits on the same phase)
       if (tid == 0 && error) *error = 1;
       break;
     }
+    if (tile + stride < n_tiles) {  // next tile: its X rows are in registers, its MMAs go to the other accumulator
+      stage_and_issue(buf ^ 1u);
+      if (tile + 2 * stride < n_tiles) fetch((tile + 2 * stride) * TILE);
+    }
     const bool live = n0 + row < n;
     const float yv = live ? y[n0 + row] : 0.0f;
     for (int cc = (warp >> 2) * 32; cc < TILE; cc += (NT / 128) * 32) {
       uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)cc, v);
+      tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + buf * (uint32_t)TILE + (uint32_t)cc, v);
       float ll[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -359,14 +373,14 @@ __global__ void __launch_bounds__(NT, 1) glm_eta_kernel(const float* __restrict_
     __syncthreads();
     if (tid < TILE)
       LP[(size_t)tile * Cp + c0 + tid] = ((colsum[tid] + colsum[TILE + tid]) + colsum[2 * TILE + tid]) + colsum[3 * TILE + tid];
-    // the accumulator, the X buffers and colsum are reused by the next tile
+    // this accumulator and colsum are reused two / one tiles from now
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TILE));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TILE));
 }
 
 // G[chain, p] = sum over the observations of this split of Rt[chain, n] * Xt[p, n]
