@@ -205,20 +205,25 @@ static int add_gp(pm4_model* m, int dtype, int C, const void* theta, void* lp, i
   const size_t rs = dtype == PM4_F64 ? 8 : 4;
   for (const GpTerm& g : m->gp) {
     const size_t per_chain = (size_t)pm4_gp_work_bytes(g.n, 1);
-    if (m->gp_work_bytes < per_chain * (size_t)std::min(C, 8)) {
-      CU(cudaStreamSynchronize(st));
-      if (m->gp_work) CU(cudaFree(m->gp_work));
-      m->gp_work = nullptr; m->gp_work_bytes = 0;
+    // grow the workspace to hold all C chains when it can (60 % of what is free, or PM4_GP_WORK_MB); otherwise
+    // the chains go through it in chunks
+    if (m->gp_work_bytes < per_chain * (size_t)C) {
       size_t free_b = 0, total_b = 0;
       CU(cudaMemGetInfo(&free_b, &total_b));
-      size_t want = per_chain * (size_t)C, cap = free_b / 10 * 6;
+      size_t cap = (free_b + m->gp_work_bytes) / 10 * 6;
       if (const char* e = getenv("PM4_GP_WORK_MB")) cap = (size_t)atoll(e) << 20;
-      if (want > cap) want = cap / per_chain * per_chain;
-      if (want < per_chain) return fail(PM4_ENOMEM, "GP term with %d points needs %zu bytes of workspace per chain, %zu are free", g.n, per_chain, free_b);
-      cudaError_t e = cudaMalloc(&m->gp_work, want);
-      if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GP factorisations: %s", want, cudaGetErrorString(e));
-      m->gp_work_bytes = want;
+      size_t want = std::min(per_chain * (size_t)C, cap / per_chain * per_chain);
+      if (want > m->gp_work_bytes) {
+        CU(cudaStreamSynchronize(st));
+        if (m->gp_work) CU(cudaFree(m->gp_work));
+        m->gp_work = nullptr; m->gp_work_bytes = 0;
+        if (want < per_chain) return fail(PM4_ENOMEM, "GP term with %d points needs %zu bytes of workspace per chain, %zu are free", g.n, per_chain, free_b);
+        cudaError_t e = cudaMalloc(&m->gp_work, want);
+        if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GP factorisations: %s", want, cudaGetErrorString(e));
+        m->gp_work_bytes = want;
+      }
     }
+    if (m->gp_work_bytes < per_chain) return fail(PM4_ENOMEM, "no workspace for a GP term with %d points", g.n);
     const int chunk = (int)std::min<size_t>((size_t)C, m->gp_work_bytes / per_chain);
     for (int c0 = 0; c0 < C; c0 += chunk) {
       const int cc = std::min(chunk, C - c0);

@@ -548,6 +548,23 @@ def test_gp_marginal_likelihood_logp_grad_parity(n, d, oracle_mod):
     assert ll.shape == (5, 1)
 
 
+def test_gp_chains_go_through_a_small_workspace_in_chunks(oracle_mod, monkeypatch):
+    """2 n^2 doubles of workspace per chain: when not all chains fit, they are processed in chunks."""
+    X, y = M.gp_data(n=200, d=1)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    rng = np.random.default_rng(73)
+    theta = rng.normal(0, 0.3, (13, ir.D))
+    theta[:, 2] -= 1.5
+    lp_ref, g_ref = oracle_mod.Oracle(ir).logp_grad(theta, dtype=np.float64)
+    monkeypatch.setenv("PM4_GP_WORK_MB", "6")  # 1.06 MB per chain at n = 200 (padded to 256): 5 chains per chunk
+    lp, g = _dm(ir, f64=True).logp_grad(theta, dtype=np.float64)
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref, rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-8, atol=1e-7)
+    monkeypatch.setenv("PM4_GP_WORK_MB", "0")
+    with pytest.raises(RuntimeError, match="workspace"):
+        _dm(ir, f64=True).logp_grad(theta, dtype=np.float64)
+
+
 def test_gp_lockstep_hmc_and_nuts_against_oracle(oracle_mod):
     X, y = M.gp_data(n=96, d=1)
     ir, _, _ = lower_model(M.gp_model(X, y))
