@@ -82,10 +82,10 @@ typedef struct pm4_rv {
                                distributions/multivariate.py:159-199), a dense term with no tape and n = 1 (one density
                                value per state).  The dense-term fields are reused: glm_base = number of points,
                                glm_p = feature dimension d, X [points, d] row-major at dataf[glm_x], y - loc at
-                               dataf[glm_y]; dataf[gp_par .. gp_par + 8) = (l_elem, a_elem, noise_elem, l_const, a_const,
-                               noise_const, noise_squared, jitter): *_elem is the position in x (constrained space) of
-                               the scalar free variable, or -1 to use the constant; the diagonal term is
-                               (noise_squared ? v * v : v) + jitter.  Evaluated for all chains at once by batched
+                               dataf[glm_y]; dataf[gp_par .. gp_par + 9) = (l_elem, a_elem, noise_elem, l_const, a_const,
+                               noise_const, noise_squared, jitter, loc_off): *_elem is the position in x (constrained
+                               space) of the scalar free variable, or -1 to use the constant; the diagonal term is
+                               (noise_squared ? v * v : v) + jitter; loc [points] at dataf[loc_off] (forward sampling).  Evaluated for all chains at once by batched
                                float64 Cholesky kernels (csrc/pm4_gp.cu). */
 
 typedef struct pm4_term {
@@ -103,7 +103,7 @@ typedef struct pm4_term {
   int32_t glm_p;       /*   number of covariates                                                        */
   int64_t glm_x;       /*   dataf offset of X [n, glm_p]                                                */
   int64_t glm_y;       /*   dataf offset of y [n]                                                       */
-  int64_t gp_par;      /* PM4_T_MVN_EXPQUAD: dataf offset of the 8-double parameter record                */
+  int64_t gp_par;      /* PM4_T_MVN_EXPQUAD: dataf offset of the 9-double parameter record                */
 } pm4_term_t;
 
 /* Device execution plan of a term that gathers from free variables: its elements regrouped by
@@ -375,6 +375,19 @@ int pm4_gp_logp_grad(const double* X, const double* y, int n, int d, const doubl
                      const double* shift, const double* scale, int dtype, const void* theta, int ldt, int C, void* lp,
                      int lp_stride, int accumulate, void* grad, int ldg, void* work, void* stream);
 int pm4_gp_launches(int n, int want_grad);
+/* Forward sampling of the GP term's observed vector: out[c, :] = loc + chol(K_c) z_c, z_c from the Philox stream of
+ * (state0 + c, elem0 + i, seed).  loc [n]: DEVICE doubles; out [C, ldo] of `dtype`; other arguments as above. */
+int pm4_gp_sample(const double* X, const double* loc, int n, int d, const double* par, const int* tr, const double* shift,
+                  const double* scale, int dtype, const void* theta, int ldt, int C, int64_t state0, uint32_t elem0,
+                  uint64_t seed, void* out, int ldo, void* work, void* stream);
+
+/* Model-level wrapper: one draw of the observed vector of GP term `which` (0-based among the model's GP terms) for each
+ * of the M states theta_dev [M, D] (unconstrained); out_dev [M, n_points].  Replaces, for MvNormal observations, the
+ * resampling step of sample_posterior_predictive / sample_prior_predictive (/root/reference/pymc4/forward_sampling.py:
+ * 26-427).  pm4_gp_points returns n_points of that term (or PM4_EINVAL). */
+int pm4_gp_predictive(pm4_model_t* m, int dtype, int which, int64_t M, const void* theta_dev, uint64_t seed, void* out_dev,
+                      void* stream);
+int pm4_gp_points(const pm4_model_t* m, int which);
 int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, const float* y, int n, int P, const float* theta,
                       int ldt, int base, int C, float* lp, float* grad, int ldg, void* work, int* error_dev,
                       void* stream);

@@ -125,6 +125,62 @@ int pm4o_posterior_predictive(const pm4_ir_t* ir, int dtype, int64_t M, int ll_r
                           : pm4o_posterior_predictive_f32(ir, M, ll_row, seed, theta, out);
 }
 
+/* One draw of the observed vector of GP term `which` per state: out[m, :] = loc + chol(K(theta_m)) z_m with
+ * z_m[i] = the first Box-Muller normal of Philox(state m, element 0x40000000 + (which << 24) + i, PM4_RNG_PREDICTIVE; seed)
+ * (MvNormal.sample of /root/reference/pymc4/distributions/multivariate.py:159-199 inside sample_posterior_predictive,
+ * forward_sampling.py:230-427; TF's own RNG stream is not reproduced).  theta [M, D] and out [M, n] are doubles. */
+int pm4o_gp_predictive(const pm4_ir_t* ir, int which, int64_t M, uint64_t seed, const double* theta, double* out) {
+  if (!ir || !theta || !out || which < 0) return PM4_EINVAL;
+  const pm4_term_t* tm = NULL;
+  int seen = 0;
+  for (int t = 0; t < ir->n_terms; ++t)
+    if (ir->terms[t].kind == PM4_T_MVN_EXPQUAD && seen++ == which) { tm = &ir->terms[t]; break; }
+  if (!tm) return PM4_EINVAL;
+  const int n = tm->glm_base, d = tm->glm_p, D = ir->D;
+  const double *X = ir->dataf + tm->glm_x, *par = ir->dataf + tm->gp_par, *loc = ir->dataf + (int64_t)par[8];
+  const int el = (int)par[0], ea = (int)par[1], en = (int)par[2], sq = par[6] != 0.0;
+  double* x = (double*)malloc(sizeof(double) * (size_t)(D + 1));
+  double* K = (double*)malloc(sizeof(double) * (size_t)n * n);
+  double* z = (double*)malloc(sizeof(double) * (size_t)n);
+  int rc = PM4_OK;
+  for (int64_t m = 0; m < M; ++m) {
+    constrain_f64(ir, theta + (size_t)m * D, x);
+    const double l = el >= 0 ? x[el] : par[3], a = ea >= 0 ? x[ea] : par[4], v = en >= 0 ? x[en] : par[5];
+    const double dg = (sq ? v * v : v) + par[7];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double d2 = 0;
+        for (int f = 0; f < d; ++f) { const double df = X[(size_t)i * d + f] - X[(size_t)j * d + f]; d2 += df * df; }
+        K[(size_t)i * n + j] = a * a * exp(-d2 / (2.0 * l * l)) + (i == j ? dg : 0.0);
+      }
+    for (int j = 0; j < n; ++j) {
+      double s = K[(size_t)j * n + j];
+      for (int k = 0; k < j; ++k) s -= K[(size_t)j * n + k] * K[(size_t)j * n + k];
+      const double ljj = sqrt(s); /* NaN when K is not positive definite: propagates into the draws */
+      K[(size_t)j * n + j] = ljj;
+      for (int i = j + 1; i < n; ++i) {
+        double t = K[(size_t)i * n + j];
+        for (int k = 0; k < j; ++k) t -= K[(size_t)i * n + k] * K[(size_t)j * n + k];
+        K[(size_t)i * n + j] = t / ljj;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      uint32_t ctr[4] = {(uint32_t)m, (uint32_t)((uint64_t)m >> 32), 0x40000000u + ((uint32_t)which << 24) + (uint32_t)i,
+                         PM4_RNG_PREDICTIVE}, u[4];
+      double n1;
+      pm4o_philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32), u);
+      box_muller_f64(u[0], u[1], &z[i], &n1);
+    }
+    for (int i = 0; i < n; ++i) {
+      double t = 0;
+      for (int k = 0; k <= i; ++k) t += K[(size_t)i * n + k] * z[k];
+      out[(size_t)m * n + i] = loc[i] + t;
+    }
+  }
+  free(x); free(K); free(z);
+  return rc;
+}
+
 int pm4o_prior_predictive(const pm4_ir_t* ir, int dtype, int64_t M, int ll_row, uint64_t seed, void* x_out,
                           void* obs_out) {
   return dtype == PM4_F64 ? pm4o_prior_predictive_f64(ir, M, ll_row, seed, x_out, obs_out)

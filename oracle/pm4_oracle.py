@@ -42,6 +42,7 @@ def lib():
         L.pm4o_deterministics.argtypes = [irp, i32, i64, vp, vp]
         L.pm4o_log_likelihood.argtypes = [irp, i32, i64, i32, vp, vp]
         L.pm4o_posterior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
+        L.pm4o_gp_predictive.argtypes = [irp, i32, i64, ctypes.c_uint64, vp, vp]
         L.pm4o_prior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
         L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 12
         L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
@@ -127,6 +128,17 @@ class Oracle:
         _check(lib().pm4o_posterior_predictive(self.packed.byref(), _code(dtype), flat.shape[0], self.ir.ll_row,
                                                int(seed) & (2**64 - 1), _ptr(flat), _ptr(out)), "posterior_predictive")
         return out.reshape(lead + (self.ir.ll_row,))
+
+    def gp_predictive(self, theta, seed=0, which=0):
+        """theta [..., D] -> [..., n_points]: one draw of the observed vector of GP term ``which`` per state."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        lead = theta.shape[:-1]
+        flat = theta.reshape(-1, self.ir.D)
+        n = self.ir.gp_terms[which].gp.n
+        out = np.empty((flat.shape[0], n), dtype=np.float64)
+        _check(lib().pm4o_gp_predictive(self.packed.byref(), int(which), flat.shape[0], int(seed) & (2**64 - 1),
+                                        _ptr(flat), _ptr(out)), "gp_predictive")
+        return out.reshape(lead + (n,))
 
     def prior_predictive(self, M, seed=0, dtype=np.float64):
         """M ancestral samples of the model: (x [M, D] constrained values of the free variables,

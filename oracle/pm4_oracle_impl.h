@@ -507,7 +507,6 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
                                     REAL* out) {
   if (!ir || !theta || !out) return PM4_EINVAL;
   for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
-  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].kind == PM4_T_MVN_EXPQUAD) return PM4_ENOSYS;
   const int D = ir->D;
   REAL* x = (REAL*)malloc(sizeof(REAL) * (size_t)(D + 1));
   REAL v[PM4O_MAXREG];
@@ -517,6 +516,7 @@ int NAME(pm4o_posterior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, u
     for (int t = 0; t < ir->n_terms; ++t) {
       const pm4_term_t* tm = &ir->terms[t];
       if (!tm->observed) continue;
+      if (tm->kind == PM4_T_MVN_EXPQUAD) continue; /* a vector per state: pm4o_gp_predictive */
       for (int i = 0; i < tm->n; ++i) {
         REAL q[3] = {0, 0, 0};
         int kind = tm->kind;
@@ -552,7 +552,6 @@ static int NAME(term_defines)(const pm4_ir_t* ir, const pm4_term_t* tm) {
 int NAME(pm4o_prior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint64_t seed, REAL* x_out, REAL* obs_out) {
   if (!ir || !x_out) return PM4_EINVAL;
   for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].n_regs > PM4O_MAXREG) return PM4_EINVAL;
-  for (int t = 0; t < ir->n_terms; ++t) if (ir->terms[t].kind == PM4_T_MVN_EXPQUAD) return PM4_ENOSYS;
   const int D = ir->D;
   REAL v[PM4O_MAXREG];
   for (int64_t m = 0; m < M; ++m) {
@@ -561,6 +560,7 @@ int NAME(pm4o_prior_predictive)(const pm4_ir_t* ir, int64_t M, int ll_row, uint6
     for (int pass = 0; pass < 2; ++pass) {
       for (int t = 0; t < ir->n_terms; ++t) {
         const pm4_term_t* tm = &ir->terms[t];
+        if (tm->kind == PM4_T_MVN_EXPQUAD) continue; /* a vector per sample: pm4o_gp_predictive */
         const int defines = NAME(term_defines)(ir, tm);
         if (pass == 0 ? !defines : !(tm->observed && obs_out)) continue;
         const pm4_op_t* vo = &ir->ops[tm->op_begin + (tm->value_reg >= 0 ? tm->value_reg : 0)];

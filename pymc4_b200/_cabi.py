@@ -35,7 +35,7 @@ EXPORTS = [
     "pm4_last_error", "pm4_abi_version",
     "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
-    "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches",
+    "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches", "pm4_gp_sample", "pm4_gp_predictive", "pm4_gp_points",
 ]
 
 
@@ -83,6 +83,8 @@ def load_library():
     L.pm4_model_ll_row.argtypes = [vp]
     L.pm4_posterior_predictive.argtypes = [vp, i32, i64, vp, ctypes.c_uint64, vp, vp]
     L.pm4_prior_predictive.argtypes = [vp, i32, i64, ctypes.c_uint64, vp, vp, vp]
+    L.pm4_gp_predictive.argtypes = [vp, i32, i32, i64, vp, ctypes.c_uint64, vp, vp]
+    L.pm4_gp_points.argtypes = [vp, i32]
     L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
     L.pm4_nuts_run.argtypes = [vp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
     L.pm4_scratch_bytes.argtypes = [vp, i32, i32, i32]
@@ -250,6 +252,22 @@ class DeviceModel:
                                                           ctypes.c_uint64(int(seed) & (2**64 - 1)), self._p(out),
                                                           self._stream()))
         return out.reshape(lead + (self.ir.ll_row,))
+
+    def gp_predictive(self, theta, seed: int = 0, dtype=np.float32, which: int = 0):
+        """theta [..., D] (unconstrained) -> [..., n_points] device tensor: one draw of the observed vector of the
+        model's GP term ``which`` per state (loc + chol(K(theta)) z, float64 factorisation)."""
+        torch = self.torch
+        th = self.to_device(theta, dtype)
+        lead = tuple(th.shape[:-1])
+        flat = th.reshape(-1, self.ir.D)
+        n = self.lib.pm4_gp_points(self.handle, int(which))
+        if n <= 0:
+            raise ValueError("the model has no GP term %d" % which)
+        out = self.empty((flat.shape[0], n), _tdtype(torch, dtype))
+        with torch.cuda.device(self._dev()):
+            self._check(self.lib.pm4_gp_predictive(self.handle, _code(dtype), int(which), flat.shape[0], self._p(flat),
+                                                   ctypes.c_uint64(int(seed) & (2**64 - 1)), self._p(out), self._stream()))
+        return out.reshape(lead + (n,))
 
     def prior_predictive(self, M: int, seed: int = 0, dtype=np.float32, sample_observed: bool = True):
         """M ancestral samples: (x [M, D] constrained free variables, obs [M, ll_row] or None), device tensors."""

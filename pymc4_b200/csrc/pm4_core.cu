@@ -71,7 +71,7 @@ struct GlmTerm {
 // a marginal GP likelihood term (PM4_T_MVN_EXPQUAD): pool offsets + how its three scalars are read from theta
 struct GpTerm {
   int n = 0, d = 0, ll_offset = 0;
-  int64_t x_off = 0, y_off = 0;
+  int64_t x_off = 0, y_off = 0, loc_off = 0;
   double par[8] = {0};
   int tr[3] = {0, 0, 0};
   double shift[3] = {0, 0, 0}, scale[3] = {1, 1, 1};
@@ -198,6 +198,30 @@ static int upload_glm(pm4_model* m, const double*) {
   return PM4_OK;
 }
 
+// grow the GP workspace to hold all C chains when it can (60 % of what is free, or PM4_GP_WORK_MB); otherwise the
+// chains go through it in chunks
+static int gp_workspace(pm4_model* m, const GpTerm& g, int C, cudaStream_t st) {
+  const size_t per_chain = (size_t)pm4_gp_work_bytes(g.n, 1);
+  if (m->gp_work_bytes < per_chain * (size_t)C) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t cap = (free_b + m->gp_work_bytes) / 10 * 6;
+    if (const char* e = getenv("PM4_GP_WORK_MB")) cap = (size_t)atoll(e) << 20;
+    size_t want = std::min(per_chain * (size_t)C, cap / per_chain * per_chain);
+    if (want > m->gp_work_bytes) {
+      CU(cudaStreamSynchronize(st));
+      if (m->gp_work) CU(cudaFree(m->gp_work));
+      m->gp_work = nullptr; m->gp_work_bytes = 0;
+      if (want < per_chain) return fail(PM4_ENOMEM, "GP term with %d points needs %zu bytes of workspace per chain, %zu are free", g.n, per_chain, free_b);
+      cudaError_t e = cudaMalloc(&m->gp_work, want);
+      if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GP factorisations: %s", want, cudaGetErrorString(e));
+      m->gp_work_bytes = want;
+    }
+  }
+  if (m->gp_work_bytes < per_chain) return fail(PM4_ENOMEM, "no workspace for a GP term with %d points", g.n);
+  return PM4_OK;
+}
+
 // add the GP terms for C chains: batched float64 Cholesky kernels (csrc/pm4_gp.cu), chains in chunks that fit
 // the workspace (2 n^2 doubles per chain)
 static int add_gp(pm4_model* m, int dtype, int C, const void* theta, void* lp, int lp_stride, bool accumulate, void* grad,
@@ -205,25 +229,7 @@ static int add_gp(pm4_model* m, int dtype, int C, const void* theta, void* lp, i
   const size_t rs = dtype == PM4_F64 ? 8 : 4;
   for (const GpTerm& g : m->gp) {
     const size_t per_chain = (size_t)pm4_gp_work_bytes(g.n, 1);
-    // grow the workspace to hold all C chains when it can (60 % of what is free, or PM4_GP_WORK_MB); otherwise
-    // the chains go through it in chunks
-    if (m->gp_work_bytes < per_chain * (size_t)C) {
-      size_t free_b = 0, total_b = 0;
-      CU(cudaMemGetInfo(&free_b, &total_b));
-      size_t cap = (free_b + m->gp_work_bytes) / 10 * 6;
-      if (const char* e = getenv("PM4_GP_WORK_MB")) cap = (size_t)atoll(e) << 20;
-      size_t want = std::min(per_chain * (size_t)C, cap / per_chain * per_chain);
-      if (want > m->gp_work_bytes) {
-        CU(cudaStreamSynchronize(st));
-        if (m->gp_work) CU(cudaFree(m->gp_work));
-        m->gp_work = nullptr; m->gp_work_bytes = 0;
-        if (want < per_chain) return fail(PM4_ENOMEM, "GP term with %d points needs %zu bytes of workspace per chain, %zu are free", g.n, per_chain, free_b);
-        cudaError_t e = cudaMalloc(&m->gp_work, want);
-        if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GP factorisations: %s", want, cudaGetErrorString(e));
-        m->gp_work_bytes = want;
-      }
-    }
-    if (m->gp_work_bytes < per_chain) return fail(PM4_ENOMEM, "no workspace for a GP term with %d points", g.n);
+    if (int rcw = gp_workspace(m, g, C, st)) return rcw;
     const int chunk = (int)std::min<size_t>((size_t)C, m->gp_work_bytes / per_chain);
     for (int c0 = 0; c0 < C; c0 += chunk) {
       const int cc = std::min(chunk, C - c0);
@@ -387,10 +393,12 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
       if (tm.kind != PM4_T_MVN_EXPQUAD) continue;
       const int n = tm.glm_base, d = tm.glm_p;
       if (n <= 0 || d <= 0 || tm.glm_x < 0 || tm.glm_x + (int64_t)n * d > ir->n_dataf || tm.glm_y < 0 ||
-          tm.glm_y + n > ir->n_dataf || tm.gp_par < 0 || tm.gp_par + 8 > ir->n_dataf)
+          tm.glm_y + n > ir->n_dataf || tm.gp_par < 0 || tm.gp_par + 9 > ir->n_dataf)
         return fail(PM4_EINVAL, "GP term %d points outside the data pool", t);
+      const int64_t loc_off = (int64_t)ir->dataf[tm.gp_par + 8];
+      if (loc_off < 0 || loc_off + n > ir->n_dataf) return fail(PM4_EINVAL, "GP term %d: loc points outside the data pool", t);
       GpTerm g;
-      g.n = n; g.d = d; g.ll_offset = tm.ll_offset; g.x_off = tm.glm_x; g.y_off = tm.glm_y;
+      g.n = n; g.d = d; g.ll_offset = tm.ll_offset; g.x_off = tm.glm_x; g.y_off = tm.glm_y; g.loc_off = loc_off;
       for (int k = 0; k < 8; ++k) g.par[k] = ir->dataf[tm.gp_par + k];
       for (int k = 0; k < 3; ++k) {
         const int e = (int)g.par[k];
@@ -518,10 +526,40 @@ extern "C" int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, co
   if (rc) return rc;
   if (M == 0 || m->info.ll_row == 0) return PM4_OK;
   if (!theta_dev || !out_dev) return fail(PM4_EINVAL, "pm4_posterior_predictive: null buffer");
-  if (!m->gp.empty()) return fail(PM4_ENOSYS, "forward sampling of MvNormal (GP) observations is not built");
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_predict(dtype, &a, M, theta_dev, out_dev, seed, stream), "posterior_predictive");
+  return PM4_OK;
+}
+
+extern "C" int pm4_gp_points(const pm4_model_t* m, int which) {
+  if (!m || which < 0 || which >= (int)m->gp.size()) return PM4_EINVAL;
+  return m->gp[(size_t)which].n;
+}
+
+extern "C" int pm4_gp_predictive(pm4_model_t* m, int dtype, int which, int64_t M, const void* theta_dev, uint64_t seed,
+                                 void* out_dev, void* stream) {
+  if (!m || M < 0 || which < 0 || which >= (int)m->gp.size()) return fail(PM4_EINVAL, "pm4_gp_predictive: bad argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (M == 0) return PM4_OK;
+  if (!theta_dev || !out_dev) return fail(PM4_EINVAL, "pm4_gp_predictive: null buffer");
+  if (M > 0x7fffffff) return fail(PM4_EINVAL, "pm4_gp_predictive: too many states");
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const GpTerm& g = m->gp[(size_t)which];
+  if ((rc = gp_workspace(m, g, (int)M, st))) return rc;
+  const size_t rs = dtype == PM4_F64 ? 8 : 4, per_chain = (size_t)pm4_gp_work_bytes(g.n, 1);
+  const int chunk = (int)std::min<size_t>((size_t)M, m->gp_work_bytes / per_chain);
+  for (int c0 = 0; c0 < (int)M; c0 += chunk) {
+    const int cc = std::min(chunk, (int)M - c0);
+    // element ids of the draws live in their own range: they never coincide with those of another observed term
+    rc = pm4_gp_sample(m->d_f64 + g.x_off, m->d_f64 + g.loc_off, g.n, g.d, g.par, g.tr, g.shift, g.scale, dtype,
+                       (const char*)theta_dev + (size_t)c0 * m->D * rs, m->D, cc, (int64_t)c0,
+                       0x40000000u + ((uint32_t)which << 24), seed, (char*)out_dev + (size_t)c0 * g.n * rs, g.n, m->gp_work, st);
+    g_launches += pm4_gp_launches(g.n, 0);
+    if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GP kernels: %s", rc < 0 ? "bad argument" : cudaGetErrorString((cudaError_t)rc));
+  }
   return PM4_OK;
 }
 
@@ -532,7 +570,6 @@ extern "C" int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64
   if (rc) return rc;
   if (M == 0) return PM4_OK;
   if (!x_dev) return fail(PM4_EINVAL, "pm4_prior_predictive: null buffer");
-  if (!m->gp.empty() && obs_dev) return fail(PM4_ENOSYS, "forward sampling of MvNormal (GP) observations is not built");
   CU(cudaSetDevice(m->device));
   pm4_mod_args_t a = m->args(dtype);
   MOD(m->f_prior(dtype, &a, M, x_dev, obs_dev, seed, stream), "prior_predictive");

@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "../../include/pm4b200.h"
+#include "pm4_philox.cuh"
 
 namespace {
 
@@ -355,9 +356,72 @@ __global__ void __launch_bounds__(256) gp_finish_kernel(GpShape s, GpParams p, r
   }
 }
 
+// forward sampling: z ~ N(0, I) from the Philox stream of (state, element), then y = loc + L z
+__global__ void __launch_bounds__(256) gp_z_kernel(GpShape s, long long state0, uint32_t elem0, uint32_t k0, uint32_t k1) {
+  const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.np) return;
+  double z = 0.0;
+  if (i < s.n) {
+    const unsigned long long m = (unsigned long long)(state0 + c);
+    const pm4::U4 u = pm4::philox4x32_10((uint32_t)m, (uint32_t)(m >> 32), elem0 + (uint32_t)i, pm4::RNG_PREDICTIVE, k0, k1);
+    double n1;
+    pm4::box_muller<double>(u.x, u.y, z, n1);
+  }
+  s.vec[(size_t)c * 2 * s.np + i] = z;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) gp_draw_kernel(GpShape s, const double* __restrict__ loc, real* __restrict__ out, int ldo) {
+  const int c = blockIdx.y, i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= s.n) return;
+  const double* Lr = s.Kb + (size_t)c * s.np * s.np + (size_t)i * s.np;
+  const double* z = s.vec + (size_t)c * 2 * s.np;
+  double acc = 0;
+  for (int k = lane; k <= i; k += 32) acc = fma(Lr[k], z[k], acc);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[(size_t)c * ldo + i] = (real)(loc[i] + acc);
+}
+
 }  // namespace
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// workspace layout + how the scalars are read; hyper-parameters, kernel matrix and its Cholesky factor for C chains
+static void gp_setup(GpShape& s, GpParams& p, const double* X, const double* y, int n, int d, const double* par,
+                     const int* tr, const double* shift, const double* scale, int C, void* work) {
+  s.n = n; s.np = round_up(n, NB); s.nt = s.np / NB; s.d = d; s.C = C; s.X = X; s.y = y;
+  const size_t np = (size_t)s.np;
+  double* w = (double*)work;
+  s.Kb = w; w += (size_t)C * np * np;
+  s.Zt = w; w += (size_t)C * np * np;
+  s.hyp = w; w += (size_t)C * 8;
+  s.vec = w; w += (size_t)C * 2 * np;
+  s.part = w;
+  for (int k = 0; k < 3; ++k) {
+    p.elem[k] = (int)par[k];
+    p.cst[k] = par[3 + k];
+    p.tr[k] = tr ? tr[k] : PM4_TR_IDENTITY;
+    p.shift[k] = shift ? shift[k] : 0.0;
+    p.scale[k] = scale ? scale[k] : 1.0;
+  }
+  p.noise_squared = par[6] != 0.0;
+  p.jitter = par[7];
+}
+
+static void gp_factorize(const GpShape& s, const GpParams& p, int dtype, const void* theta, int ldt, cudaStream_t st) {
+  const int C = s.C;
+  const unsigned cb = (unsigned)((C + 127) / 128);
+  if (dtype == PM4_F64) gp_hyp_kernel<double><<<cb, 128, 0, st>>>(s, p, (const double*)theta, ldt);
+  else gp_hyp_kernel<float><<<cb, 128, 0, st>>>(s, p, (const float*)theta, ldt);
+  gp_build_kernel<<<dim3((unsigned)s.nt, (unsigned)s.nt, (unsigned)C), 256, 0, st>>>(s);
+  // Cholesky, left-looking over block columns
+  for (int jb = 0; jb < s.nt; ++jb) {
+    if (jb > 0) gp_nt_kernel<MODE_CHOL><<<dim3((unsigned)(s.nt - jb), (unsigned)C), NT_THREADS, 0, st>>>(s, jb);
+    gp_potrf_kernel<<<(unsigned)C, NB, 0, st>>>(s, jb);
+    const int r0 = (jb + 1) * NB;
+    if (r0 < s.np) gp_trsm_kernel<<<dim3((unsigned)((s.np - r0 + 127) / 128), (unsigned)C), 128, 0, st>>>(s, jb, 0, r0, s.np);
+  }
+}
 
 extern "C" int64_t pm4_gp_work_bytes(int n, int C) {
   if (n <= 0 || C <= 0) return PM4_EINVAL;
@@ -376,36 +440,10 @@ extern "C" int pm4_gp_logp_grad(const double* X, const double* y, int n, int d, 
   if (!X || !y || !par || !theta || !lp || !work || n <= 0 || d <= 0 || C <= 0) return PM4_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   GpShape s;
-  s.n = n; s.np = round_up(n, NB); s.nt = s.np / NB; s.d = d; s.C = C; s.X = X; s.y = y;
-  const size_t np = (size_t)s.np, ntile = (size_t)s.nt * (s.nt + 1) / 2;
-  double* w = (double*)work;
-  s.Kb = w; w += (size_t)C * np * np;
-  s.Zt = w; w += (size_t)C * np * np;
-  s.hyp = w; w += (size_t)C * 8;
-  s.vec = w; w += (size_t)C * 2 * np;
-  s.part = w;
-  (void)ntile;
   GpParams p;
-  for (int k = 0; k < 3; ++k) {
-    p.elem[k] = (int)par[k];
-    p.cst[k] = par[3 + k];
-    p.tr[k] = tr ? tr[k] : PM4_TR_IDENTITY;
-    p.shift[k] = shift ? shift[k] : 0.0;
-    p.scale[k] = scale ? scale[k] : 1.0;
-  }
-  p.noise_squared = par[6] != 0.0;
-  p.jitter = par[7];
-  const unsigned cb = (unsigned)((C + 127) / 128);
-  if (dtype == PM4_F64) gp_hyp_kernel<double><<<cb, 128, 0, st>>>(s, p, (const double*)theta, ldt);
-  else gp_hyp_kernel<float><<<cb, 128, 0, st>>>(s, p, (const float*)theta, ldt);
-  gp_build_kernel<<<dim3((unsigned)s.nt, (unsigned)s.nt, (unsigned)C), 256, 0, st>>>(s);
-  // Cholesky, left-looking over block columns
-  for (int jb = 0; jb < s.nt; ++jb) {
-    if (jb > 0) gp_nt_kernel<MODE_CHOL><<<dim3((unsigned)(s.nt - jb), (unsigned)C), NT_THREADS, 0, st>>>(s, jb);
-    gp_potrf_kernel<<<(unsigned)C, NB, 0, st>>>(s, jb);
-    const int r0 = (jb + 1) * NB;
-    if (r0 < s.np) gp_trsm_kernel<<<dim3((unsigned)((s.np - r0 + 127) / 128), (unsigned)C), 128, 0, st>>>(s, jb, 0, r0, s.np);
-  }
+  gp_setup(s, p, X, y, n, d, par, tr, shift, scale, C, work);
+  const size_t ntile = (size_t)s.nt * (s.nt + 1) / 2;
+  gp_factorize(s, p, dtype, theta, ldt, st);
   // Zt = L^-T, block column by block column
   for (int ib = 0; ib < s.nt; ++ib) {
     gp_nt_kernel<MODE_ZT><<<dim3((unsigned)(ib + 1), (unsigned)C), NT_THREADS, 0, st>>>(s, ib);
@@ -420,6 +458,27 @@ extern "C" int pm4_gp_logp_grad(const double* X, const double* y, int n, int d, 
   const unsigned fb = (unsigned)((C + 7) / 8);
   if (dtype == PM4_F64) gp_finish_kernel<double><<<fb, 256, 0, st>>>(s, p, (double*)lp, lp_stride, accumulate, (double*)grad, ldg);
   else gp_finish_kernel<float><<<fb, 256, 0, st>>>(s, p, (float*)lp, lp_stride, accumulate, (float*)grad, ldg);
+  return (int)cudaGetLastError();
+}
+
+// Forward sampling of the observed vector (sample_posterior_predictive / sample_prior_predictive for an MvNormal with
+// the ExpQuad + noise covariance, /root/reference/pymc4/forward_sampling.py:26-427): for each of the C states
+// out[c, :] = loc + chol(K_c) z_c with z_c ~ N(0, I) drawn from the Philox stream of (state0 + c, elem0 + i, seed) -- the
+// oracle draws the identical stream.  loc [n] device doubles; out [C, ldo] of `dtype`; the other arguments as above.
+extern "C" int pm4_gp_sample(const double* X, const double* loc, int n, int d, const double* par, const int* tr,
+                             const double* shift, const double* scale, int dtype, const void* theta, int ldt, int C,
+                             int64_t state0, uint32_t elem0, uint64_t seed, void* out, int ldo, void* work, void* stream) {
+  if (!X || !loc || !par || !theta || !out || !work || n <= 0 || d <= 0 || C <= 0) return PM4_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  GpShape s;
+  GpParams p;
+  gp_setup(s, p, X, loc, n, d, par, tr, shift, scale, C, work);
+  gp_factorize(s, p, dtype, theta, ldt, st);
+  gp_z_kernel<<<dim3((unsigned)((s.np + 255) / 256), (unsigned)C), 256, 0, st>>>(s, (long long)state0, elem0, (uint32_t)seed,
+                                                                                 (uint32_t)(seed >> 32));
+  const dim3 g((unsigned)((n + 7) / 8), (unsigned)C);
+  if (dtype == PM4_F64) gp_draw_kernel<double><<<g, 256, 0, st>>>(s, loc, (double*)out, ldo);
+  else gp_draw_kernel<float><<<g, 256, 0, st>>>(s, loc, (float*)out, ldo);
   return (int)cudaGetLastError();
 }
 

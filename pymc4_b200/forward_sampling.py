@@ -86,25 +86,37 @@ def sample_prior_predictive(
         if name in var_names:
             output[name] = x[:, rv.offset: rv.offset + rv.size].reshape(lead + rv.shape).cpu().numpy()
     if any(n in var_names for n in det_names):
-        theta = x.clone()  # deterministics are tapes over the unconstrained state: undo the transforms
-        for rv in ir.rvs:
-            sl = slice(rv.offset, rv.offset + rv.size)
-            if rv.transform == irmod.TR_EXP:
-                theta[:, sl] = torch.log((x[:, sl] - rv.shift) / rv.scale)
-            elif rv.transform == irmod.TR_SIGMOID:
-                u = (x[:, sl] - rv.shift) / rv.scale
-                theta[:, sl] = torch.log(u) - torch.log1p(-u)
+        theta = _unconstrain(ir, x, torch)  # deterministics are tapes over the unconstrained state
         dets = dm.deterministics(theta, dtype=np.dtype(dtype)).cpu().numpy()
         for d in ir.dets:
             if d.name in var_names and d.name in det_names:
                 output[d.name] = dets[:, d.out_offset: d.out_offset + d.n].reshape(lead + tuple(d.shape))
+    gp_index = {t.label: k for k, t in enumerate(ir.gp_terms)}
     for name, t in obs_terms.items():
         if name in var_names:
-            if obs is not None:
+            if obs is not None and name in gp_index:
+                # MvNormal observation of a GP model: a vector per sample, loc + chol(K(x)) z on the device
+                theta = _unconstrain(ir, x, torch)
+                output[name] = dm.gp_predictive(theta, seed=seed, dtype=np.dtype(dtype), which=gp_index[name]) \
+                    .reshape(lead + (t.gp.n,)).cpu().numpy()
+            elif obs is not None:
                 output[name] = obs[:, t.ll_offset: t.ll_offset + t.n].reshape(lead + tuple(t.shape)).cpu().numpy()
             else:  # explicitly requested but not resampled: the observed data itself
                 output[name] = np.broadcast_to(np.asarray(ir.observed[name]), lead + np.shape(ir.observed[name])).copy()
     return trace_to_arviz(prior_predictive=output)
+
+
+def _unconstrain(ir, x, torch):
+    """Constrained values x [M, D] of the free variables -> unconstrained state (undo the transforms)."""
+    theta = x.clone()
+    for rv in ir.rvs:
+        sl = slice(rv.offset, rv.offset + rv.size)
+        if rv.transform == irmod.TR_EXP:
+            theta[:, sl] = torch.log((x[:, sl] - rv.shift) / rv.scale)
+        elif rv.transform == irmod.TR_SIGMOID:
+            u = (x[:, sl] - rv.shift) / rv.scale
+            theta[:, sl] = torch.log(u) - torch.log1p(-u)
+    return theta
 
 
 def sample_posterior_predictive(
@@ -159,8 +171,12 @@ def sample_posterior_predictive(
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
     draws = dm.posterior_predictive(theta, seed=seed, dtype=np.dtype(dtype)).cpu().numpy()
+    gp_index = {t.label: k for k, t in enumerate(ir.gp_terms)}
     output = {}
     for name in var_names:
         t = obs_terms[name]
-        output[name] = draws[..., t.ll_offset: t.ll_offset + t.n].reshape(tuple(lead) + tuple(t.shape))
+        if name in gp_index:  # MvNormal observation of a GP model: a vector per draw, loc + chol(K(theta)) z
+            output[name] = dm.gp_predictive(theta, seed=seed, dtype=np.dtype(dtype), which=gp_index[name]).cpu().numpy()
+        else:
+            output[name] = draws[..., t.ll_offset: t.ll_offset + t.n].reshape(tuple(lead) + tuple(t.shape))
     return trace_to_arviz(trace=trace, posterior_predictive=output, inplace=inplace)

@@ -123,8 +123,8 @@ class GP:
     (BASELINE configs[3]).  Like the GLM term it has no element-wise tape; the device evaluates it for all
     chains at once with batched float64 Cholesky kernels (csrc/pm4_gp.cu), the oracle with plain loops.
 
-    ``par_blob`` points at 8 doubles in dataf: (l_elem, a_elem, noise_elem, l_const, a_const, noise_const,
-    noise_squared, jitter).  ``*_elem`` is the position in x (constrained space) of the scalar free variable
+    ``par_blob`` points at 9 doubles in dataf: (l_elem, a_elem, noise_elem, l_const, a_const, noise_const,
+    noise_squared, jitter, loc_blob) -- loc_blob is the dataf offset of loc [n] (forward sampling adds it back).  ``*_elem`` is the position in x (constrained space) of the scalar free variable
     the parameter is, or -1 when it is the constant next to it; the diagonal added to the kernel matrix is
     ``(noise_squared ? v * v : v) + jitter`` with v the noise parameter."""
     x_blob: int      # dataf offset of X, row-major [n, d]
@@ -538,11 +538,13 @@ def _match_gp(kind: str, value, params: List[Any], rvs, pools, label: str) -> Op
         noise = ((-1, 0.0), False)
     (ne, nc), squared = noise
     X = np.asarray(kern[0].data[0], dtype=np.float64)
-    y = np.asarray(v.data, dtype=np.float64).reshape(-1) - np.broadcast_to(np.asarray(loc.data, dtype=np.float64), (n,))
+    loc_vec = np.broadcast_to(np.asarray(loc.data, dtype=np.float64), (n,)).copy()
+    y = np.asarray(v.data, dtype=np.float64).reshape(-1) - loc_vec
     if y.shape != (n,):
         raise ValueError("observed value of shape {} does not match the {} x {} covariance".format(v.shape, n, n))
-    par = np.array([ls[0], amp[0], ne, ls[1], amp[1], nc, 1.0 if squared else 0.0, jitter], dtype=np.float64)
-    x_blob, y_blob, par_blob = pools.add_f(X.reshape(-1)), pools.add_f(y), pools.add_f(par)
+    x_blob, y_blob, loc_blob = pools.add_f(X.reshape(-1)), pools.add_f(y), pools.add_f(loc_vec)
+    par = np.array([ls[0], amp[0], ne, ls[1], amp[1], nc, 1.0 if squared else 0.0, jitter, float(loc_blob)], dtype=np.float64)
+    par_blob = pools.add_f(par)
     return Term(kind=TERM_KINDS["mvn_expquad"], n=1, ops=[], value_reg=-1, param_regs=[], label=label, shape=(),
                 gp=GP(x_blob=x_blob, y_blob=y_blob, par_blob=par_blob, n=int(n), d=int(X.shape[1]),
                       elems=(ls[0], amp[0], ne)))

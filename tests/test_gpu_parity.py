@@ -565,6 +565,24 @@ def test_gp_chains_go_through_a_small_workspace_in_chunks(oracle_mod, monkeypatc
         _dm(ir, f64=True).logp_grad(theta, dtype=np.float64)
 
 
+def test_gp_forward_sampling_matches_the_oracle_stream(oracle_mod):
+    """sample_posterior_predictive for the MvNormal observation of a GP model: loc + chol(K(theta)) z per state, z from
+    the Philox stream the oracle draws too."""
+    X, y = M.gp_data(n=150, d=2)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    rng = np.random.default_rng(74)
+    theta = rng.normal(0, 0.3, (9, ir.D))
+    theta[:, 2] -= 1.0
+    ref = oracle_mod.Oracle(ir).gp_predictive(theta, seed=5)
+    out = _dm(ir, f64=True).gp_predictive(theta, seed=5, dtype=np.float64).cpu().numpy()
+    assert out.shape == (9, 150)
+    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-9)
+    out32 = _dm(ir).gp_predictive(theta.astype(np.float32), seed=5, dtype=np.float32).cpu().numpy()
+    ref32 = oracle_mod.Oracle(ir).gp_predictive(theta.astype(np.float32).astype(np.float64), seed=5)
+    np.testing.assert_allclose(out32, ref32, rtol=1e-4, atol=1e-5)
+    assert not np.allclose(out, _dm(ir, f64=True).gp_predictive(theta, seed=6, dtype=np.float64).cpu().numpy())
+
+
 def test_gp_lockstep_hmc_and_nuts_against_oracle(oracle_mod):
     X, y = M.gp_data(n=96, d=1)
     ir, _, _ = lower_model(M.gp_model(X, y))

@@ -481,6 +481,17 @@ def test_gp_marginal_likelihood_oracle_against_scipy(oracle_mod):
     np.testing.assert_allclose(g, num, rtol=1e-5, atol=1e-5)
     ll = oracle_mod.Oracle(ir).log_likelihood(theta)
     assert ll.shape == (4, 1)
+    # forward sampling of the observed vector: loc + chol(K) z -- the sample covariance over many states is K
+    Xs, ys = M.gp_data(n=10, d=1)
+    irs, _, _ = lower_model(M.gp_model(Xs, ys))
+    th = np.tile(np.log([1.3, 0.8, 0.3]), (6000, 1))
+    draws = oracle_mod.Oracle(irs).gp_predictive(th, seed=11)
+    assert draws.shape == (6000, 10)
+    d2 = np.square(Xs - Xs.T)
+    Ks = 0.8 ** 2 * np.exp(-d2 / (2 * 1.3 ** 2)) + (0.3 ** 2 + 1e-6) * np.eye(10)
+    np.testing.assert_allclose(np.cov(draws.T), Ks, atol=0.06)
+    assert np.all(np.abs(draws.mean(0)) < 0.06)
+    np.testing.assert_array_equal(draws[:5], oracle_mod.Oracle(irs).gp_predictive(th[:5], seed=11))  # keyed by (state, element)
     # unsupported spellings fail loudly at lowering time
     @pm.model
     def latent():

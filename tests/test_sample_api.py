@@ -230,5 +230,9 @@ def test_sample_gp_regression_recovers_hyperparameters():
     assert ls.shape == (32, 100)
     assert 0.6 < np.median(ls) < 1.6 and 0.4 < np.median(amp) < 2.5 and 0.07 < np.median(sg) < 0.14
     assert trace.sample_stats["diverging"].mean() < 0.1
-    with pytest.raises((RuntimeError, NotImplementedError)):
-        pm.sample_posterior_predictive(M.gp_model(X, y), trace)
+    # forward sampling: the observed vector is redrawn from MvNormal(0, K(theta)) for every posterior draw
+    ppc = pm.sample_posterior_predictive(M.gp_model(X, y), trace, seed=1).posterior_predictive["gp_regression/y"]
+    assert ppc.shape == (32, 100, 128) and np.all(np.isfinite(ppc))
+    assert 0.3 < ppc.var() < 4.0 and abs(ppc.mean()) < 0.3
+    prior = pm.sample_prior_predictive(M.gp_model(X, y), sample_shape=50, seed=2).prior_predictive
+    assert prior["gp_regression/y"].shape == (1, 50, 128) and prior["gp_regression/ls"].shape == (1, 50)
