@@ -406,6 +406,65 @@ def test_full_size_invariants_radon_4096_chains():
     assert int(full["total_leapfrogs"].sum()) > C * (B + S)
 
 
+def test_full_size_invariants_logit_1m_observations():
+    """BASELINE configs[2] at full size (N = 10^6, P = 100) through a size-independent property, additivity over
+    observations: log-density and gradient of the full model minus those of the model holding the first half of the
+    data are the likelihood terms of the second half, computed here in float64 NumPy."""
+    n, p, C = 1_000_000, 100, 128
+    X, y = M.logistic_glm_data(n=n, p=p, seed=20261019)
+    ir, _, _ = lower_model(M.logistic_glm_model(X, y))
+    ir_a, _, _ = lower_model(M.logistic_glm_model(X[: n // 2], y[: n // 2]))
+    rng = np.random.default_rng(81)
+    theta = rng.normal(0, 0.3, (C, ir.D)).astype(np.float32)
+    lp, g = _dm(ir).logp_grad(theta, dtype=np.float32)
+    lp_a, g_a = _dm(ir_a).logp_grad(theta, dtype=np.float32)
+    base = ir.glm_terms[0].glm.base
+    beta = theta[:, base: base + p].astype(np.float64)
+    eta = X[n // 2:] @ beta.T                                     # [n/2, C]
+    yb = y[n // 2:, None]
+    ll_b = np.sum(yb * eta - np.logaddexp(0.0, eta), axis=0)
+    gr_b = (yb - 1.0 / (1.0 + np.exp(-eta))).T @ X[n // 2:]       # [C, P]
+    d_lp = lp.cpu().numpy().astype(np.float64) - lp_a.cpu().numpy().astype(np.float64)
+    scale = np.abs(lp.cpu().numpy()).astype(np.float64)
+    assert np.max(np.abs(d_lp - ll_b) / scale) < 1e-5
+    d_g = (g.cpu().numpy().astype(np.float64) - g_a.cpu().numpy().astype(np.float64))[:, base: base + p]
+    for c in range(C):
+        assert _rel(d_g[c], gr_b[c]) < 2e-4, c   # 3xTF32 keeps ~22 bits of beta: 3.4e-5 at this size
+    # nothing else of the gradient depends on the data
+    other = np.ones(ir.D, bool)
+    other[base: base + p] = False
+    np.testing.assert_allclose(g.cpu().numpy()[:, other], g_a.cpu().numpy()[:, other], rtol=1e-5, atol=1e-5)
+
+
+def test_full_size_invariants_gp_4096_points():
+    """BASELINE configs[3] at full size (n = 4096): the log-density against LAPACK's Cholesky for one chain, and
+    the gradient against central differences of the device log-density."""
+    X, y = M.gp_data(n=4096, d=1, seed=20261019)
+    ir, _, _ = lower_model(M.gp_model(X, y))
+    dm = _dm(ir, f64=True)
+    theta = np.array([[0.05, -0.1, -2.2], [0.3, 0.2, -1.8]])
+    lp, g = dm.logp_grad(theta, dtype=np.float64)
+    lp, g = lp.cpu().numpy(), g.cpu().numpy()
+    ls, amp, sg = np.exp(theta[0])
+    d2 = np.square(X - X.T)
+    K = amp ** 2 * np.exp(-d2 / (2 * ls ** 2)) + (sg ** 2 + 1e-6) * np.eye(4096)
+    L = np.linalg.cholesky(K)
+    w = np.linalg.solve(L, y)
+    from scipy.stats import halfcauchy, halfnorm
+
+    ref = (-0.5 * w @ w - np.log(np.diag(L)).sum() - 0.5 * 4096 * np.log(2 * np.pi) + halfcauchy(scale=5).logpdf(ls)
+           + halfcauchy(scale=5).logpdf(amp) + halfnorm(scale=1).logpdf(sg) + theta[0].sum())
+    np.testing.assert_allclose(lp[0], ref, rtol=1e-9)
+    eps = 1e-5
+    for k in range(3):
+        e = np.zeros(3)
+        e[k] = eps
+        up, _ = dm.logp_grad(theta + e, dtype=np.float64, want_grad=False)
+        dn, _ = dm.logp_grad(theta - e, dtype=np.float64, want_grad=False)
+        num = (up.cpu().numpy() - dn.cpu().numpy()) / (2 * eps)
+        np.testing.assert_allclose(g[:, k], num, rtol=2e-5, atol=1e-3)
+
+
 # ------------------------------------------------------------------------------------------
 # dense GLM likelihood (BASELINE configs[2] shape: hierarchical logistic regression, X @ beta): the likelihood
 # and its gradient for all chains at once on the tcgen05 tensor cores in 3xTF32 (csrc/pm4_glm.cu), HMC in
