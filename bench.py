@@ -226,11 +226,10 @@ def cpu_baseline(ir, args):
         rate = evals / dt
     return {
         "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": "%d of the %d chains, %s, " + ("float64" if WORKLOAD == "gp" else "float32") + ", OpenMP over chains (%d threads); "
-                  "%.3g grad-evals in %.1f s" % (chains, args.chains,
-                                                 {"logit": "2 + 2 transitions", "gp": "one gradient evaluation each"}.get(
-                                                     WORKLOAD, "same burn_in/draws"),
-                                                 cores, evals, dt),
+        "sample": "%d of the %d chains, %s, %s, OpenMP over chains (%d threads); %.3g grad-evals in %.1f s"
+                  % (chains, args.chains,
+                     {"logit": "2 + 2 transitions", "gp": "one gradient evaluation each"}.get(WORKLOAD, "same burn_in/draws"),
+                     "float64" if WORKLOAD == "gp" else "float32", cores, evals, dt),
     }
 
 
