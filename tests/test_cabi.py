@@ -141,3 +141,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.parametrize("extra", [["--workload", "logit", "--logit-n", "4000"], ["--workload", "gp", "--gp-n", "128"]])
+def test_bench_reference_arm_of_the_dense_workloads(extra):
+    """The CPU arm of the LOGIT and GP workloads (reduced sizes here): same contract line, bounded samples."""
+    import json
+    import sys
+
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                           "--warmup", "0", "--cpu-chains", "2"] + extra,
+                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "leapfrog_grad_evals_per_sec" and d["value"] > 0
+    assert d["dtype"] == ("f64" if "gp" in extra else "f32")
+    assert d["cpu_baseline"]["kind"] == "port" and d["config"]["num_leapfrog_steps"] == 3
