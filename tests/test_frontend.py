@@ -325,3 +325,34 @@ def test_expquad_covariance_function_mirrors_the_reference():
     assert d.event_shape == (20,) and d.batch_shape == ()
     np.testing.assert_allclose(d.log_prob(y), multivariate_normal(np.full(20, 0.5), K).logpdf(y), rtol=1e-9)
     assert d.sample(seed=1).shape == (20,)
+
+
+def test_forward_sampling_argument_errors_mirror_the_reference():
+    """The validations of sample_prior_predictive / sample_posterior_predictive the reference tests
+    (/root/reference/tests/test_forward_sampling.py:242-248, 324-335); they run before any device work."""
+    import re
+
+    from pymc4_b200 import forward_sampling
+    from pymc4_b200.mcmc.utils import trace_to_arviz
+
+    @pm.model
+    def model():
+        sd = yield pm.HalfNormal("sd", 1.0)
+        yield pm.Normal("y", 0.0, sd, observed=np.zeros(3))
+
+    model_func = model()
+    expected = ("Some of the supplied var_names are not defined in the supplied model {}.\nList of unknown var_names: {}"
+                .format(model_func, ["X"]))
+    with pytest.raises(ValueError, match=re.escape(expected)):
+        pm.sample_prior_predictive(model_func, var_names=["X", "model/y"], sample_shape=())
+    trace = trace_to_arviz({"model/__log_sd": np.zeros((1, 10)), "model/sd": np.ones((1, 10))})
+    with pytest.raises(ValueError):
+        forward_sampling.sample_posterior_predictive(model(), trace, var_names=[])
+    with pytest.raises(KeyError):
+        forward_sampling.sample_posterior_predictive(model(), trace, var_names=["name not in model!"])
+    with pytest.raises(TypeError):
+        pm.sample_posterior_predictive("not a model", trace)
+    with pytest.raises(TypeError):
+        pm.sample_prior_predictive("not a model")
+    with pytest.raises(TypeError, match="only supports `pymc4.Model` objects"):
+        pm.sample("not a model", sampler_type="nuts")
