@@ -220,8 +220,11 @@ def cpu_sample_rate(ir, args, chains, seed):
 
 
 def cpu_baseline(ir, args):
+    from oracle import pm4_oracle
+
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    pm4_oracle.build()
+    cores = pm4_oracle.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host thread
     chains = args.cpu_chains or cores
     # calibrate so the sample costs roughly 10-30 s of CPU work
     evals, dt = cpu_sample_rate(ir, args, chains, args.seed)
@@ -248,8 +251,7 @@ def run_reference(args):
     from oracle import pm4_oracle
 
     pm4_oracle.build()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = pm4_oracle.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use every host thread
     chains = args.cpu_chains or (cores if WORKLOAD in ("logit", "gp") else 2 * cores)
     for _ in range((max(args.warmup, 0) and 1) if WORKLOAD not in ("logit", "gp") else 0):  # one short warm-up pass is enough for a CPU code
         cpu_sample_rate(ir, args, cores, args.seed + 1)

@@ -108,6 +108,16 @@ void pm4o_philox4x32_10(const uint32_t ctr_in[4], uint32_t k0, uint32_t k1, uint
 #define RFLOOR floor
 #include "pm4_oracle_impl.h"
 
+/* number of OpenMP threads of the chain loops (a launcher such as torchrun exports OMP_NUM_THREADS=1) */
+#ifdef _OPENMP
+#include <omp.h>
+void pm4o_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int pm4o_max_threads(void) { return omp_get_max_threads(); }
+#else
+void pm4o_set_num_threads(int n) { (void)n; }
+int pm4o_max_threads(void) { return 1; }
+#endif
+
 /* ---- dtype-dispatching entry points (signatures mirror include/pm4b200.h, host pointers) ---- */
 int pm4o_logp_grad(const pm4_ir_t* ir, int dtype, int C, const void* theta, void* lp, void* grad) {
   return dtype == PM4_F64 ? pm4o_logp_grad_f64(ir, C, theta, lp, grad)

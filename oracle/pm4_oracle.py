@@ -72,6 +72,16 @@ def _check(rc, what):
         raise RuntimeError("oracle {} failed with code {}".format(what, rc))
 
 
+def set_threads(n: int) -> int:
+    """OpenMP threads of the chain loops (overrides an inherited OMP_NUM_THREADS); returns the count in effect."""
+    try:  # a BLAS initialised under OMP_NUM_THREADS=1 may have pinned the process to one core: undo it, the
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))  # OpenMP workers inherit the mask when they are created
+    except (AttributeError, OSError):
+        pass
+    lib().pm4o_set_num_threads(int(n))
+    return int(lib().pm4o_max_threads())
+
+
 def philox4x32_10(ctr, key):
     c = (ctypes.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
     out = (ctypes.c_uint32 * 4)()
