@@ -13,7 +13,7 @@ import abc
 import inspect
 import logging
 import os
-from typing import Any, Dict, List, Optional, Union
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 
@@ -22,7 +22,6 @@ from .. import ir as irmod
 from .._cstructs import (PM4_ADAPT_SIMPLE, PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, PM4_PROPOSAL_RANDOM_WALK, make_adapt,
                          make_hmc_cfg, make_nuts_cfg)
 from ..coroutine_model import Model
-from ..utils import NameParts
 from . import kernels as mcmc
 from .utils import (
     KERNEL_KWARGS_SET,
