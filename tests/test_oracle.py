@@ -500,3 +500,69 @@ def test_gp_marginal_likelihood_oracle_against_scipy(oracle_mod):
 
     with pytest.raises(NotImplementedError, match="marginal likelihood"):
         lower_model(latent())
+
+
+def test_gp_term_spellings_lower_to_the_same_term(oracle_mod):
+    """Variants of the marginal-GP spelling the lowering accepts: noise as a variance (not squared), constant kernel
+    parameters, a vector loc, several jitter terms, square() instead of ** 2 -- each checked against scipy."""
+    from scipy.stats import halfnorm, multivariate_normal
+
+    X, y = M.gp_data(n=24, d=1)
+    n = len(y)
+    loc = np.linspace(-0.5, 0.5, n)
+    d2 = np.square(X - X.T)
+
+    @pm.model
+    def variance_noise():  # noise enters as a variance; the length scale is a constant
+        amp = yield pm.HalfNormal("amp", 2.0)
+        s2 = yield pm.HalfNormal("s2", 1.0)
+        cov = pm.gp.cov.ExpQuad(1.7, amp)(X, X) + s2 * np.eye(n) + 1e-6 * np.eye(n) + 2e-6 * np.eye(n)
+        yield pm.MvNormal("y", loc=loc, covariance_matrix=cov, observed=y)
+
+    @pm.model
+    def squared_noise():  # pm.math.square spelling, constant amplitude
+        ls = yield pm.HalfNormal("ls", 2.0)
+        sg = yield pm.HalfNormal("sg", 1.0)
+        cov = pm.math.square(sg) * np.eye(n) + pm.gp.cov.ExpQuad(ls, 0.9)(X, X)
+        yield pm.MvNormal("y", loc=0.0, covariance_matrix=cov, observed=y)
+
+    ir1, _, _ = lower_model(variance_noise())
+    g1 = ir1.gp_terms[0].gp
+    par1 = ir1.dataf[g1.par_blob:g1.par_blob + 8]
+    assert g1.elems == (-1, 0, 1) and par1[3] == 1.7 and par1[6] == 0.0 and abs(par1[7] - 3e-6) < 1e-18
+    ir2, _, _ = lower_model(squared_noise())
+    g2 = ir2.gp_terms[0].gp
+    par2 = ir2.dataf[g2.par_blob:g2.par_blob + 8]
+    assert g2.elems == (0, -1, 1) and par2[4] == 0.9 and par2[6] == 1.0 and par2[7] == 0.0
+    th = np.array([[0.2, -1.1], [-0.3, -0.4]])
+    lp1, gr1 = oracle_mod.Oracle(ir1).logp_grad(th, dtype=np.float64)
+    lp2, gr2 = oracle_mod.Oracle(ir2).logp_grad(th, dtype=np.float64)
+
+    def ref1(t):
+        amp, s2 = np.exp(t)
+        K = amp ** 2 * np.exp(-d2 / (2 * 1.7 ** 2)) + (s2 + 3e-6) * np.eye(n)
+        return (multivariate_normal(loc, K).logpdf(y) + halfnorm(scale=2).logpdf(amp) + halfnorm(scale=1).logpdf(s2) + t.sum())
+
+    def ref2(t):
+        ls, sg = np.exp(t)
+        K = 0.81 * np.exp(-d2 / (2 * ls ** 2)) + sg ** 2 * np.eye(n)
+        return (multivariate_normal(np.zeros(n), K).logpdf(y) + halfnorm(scale=2).logpdf(ls) + halfnorm(scale=1).logpdf(sg) + t.sum())
+
+    np.testing.assert_allclose(lp1, [ref1(t) for t in th], rtol=1e-11)
+    np.testing.assert_allclose(lp2, [ref2(t) for t in th], rtol=1e-11)
+    eps = 1e-6
+    for ref, gr in ((ref1, gr1), (ref2, gr2)):
+        num = np.array([[(ref(t + eps * e) - ref(t - eps * e)) / (2 * eps) for e in np.eye(2)] for t in th])
+        np.testing.assert_allclose(gr, num, rtol=2e-5, atol=2e-5)
+    # forward sampling adds the vector loc back
+    draws = oracle_mod.Oracle(ir1).gp_predictive(np.tile(th[0], (4000, 1)), seed=3)
+    np.testing.assert_allclose(draws.mean(0), loc, atol=0.12)
+
+    @pm.model
+    def two_kernels():
+        ls = yield pm.HalfNormal("ls", 2.0)
+        cov = pm.gp.cov.ExpQuad(ls, 1.0)(X, X) + pm.gp.cov.ExpQuad(2 * ls, 1.0)(X, X) + 0.1 * np.eye(n)
+        yield pm.MvNormal("y", loc=0.0, covariance_matrix=cov, observed=y)
+
+    with pytest.raises(NotImplementedError, match="marginal likelihood"):
+        lower_model(two_kernels())
