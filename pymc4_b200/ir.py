@@ -419,10 +419,18 @@ class _TapeBuilder:
             return self.lower(node.args[0], emap)
         if op == "take":
             return self.lower(node.args[0], node.index.reshape(-1).astype(np.int64)[emap])
+        hint = ""
+        if op == "matvec":
+            hint = (".  A dense linear predictor runs on the device only as the whole likelihood "
+                    "pm.Bernoulli(name, probs=pm.math.sigmoid(pm.math.matvec(X, beta)), observed=y) with a constant X and a "
+                    "free vector beta (for an intercept, append a column of ones to X)")
+        elif op == "expquad":
+            hint = (".  A covariance matrix with free parameters runs on the device only inside an observed "
+                    "pm.MvNormal(name, loc, covariance_matrix=ExpQuad(l, a)(X, X) + noise * np.eye(n), observed=y)")
         raise NotImplementedError(
             "op {!r} on random variables cannot be lowered to the element-wise model IR yet "
-            "(supported: arithmetic, exp/log/sigmoid/..., static indexing, gather, broadcasting)"
-            .format(op)
+            "(supported: arithmetic, exp/log/sigmoid/..., static indexing, gather, broadcasting){}"
+            .format(op, hint)
         )
 
 

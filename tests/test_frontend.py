@@ -356,3 +356,34 @@ def test_forward_sampling_argument_errors_mirror_the_reference():
         pm.sample_prior_predictive("not a model")
     with pytest.raises(TypeError, match="only supports `pymc4.Model` objects"):
         pm.sample("not a model", sampler_type="nuts")
+
+
+def test_dense_predictor_spellings_and_the_intercept_hint():
+    """`X @ beta` and `pm.math.matvec(X, beta)` both lower to the dense GLM term; a linear predictor that is not the whole
+    sigmoid argument is refused with the work-around in the message."""
+    X, y = M.logistic_glm_data(n=50, p=4)
+
+    @pm.model
+    def with_matmul():
+        beta = yield pm.Normal("beta", 0.0, 1.0, batch_stack=4)
+        yield pm.Bernoulli("y", probs=pm.math.sigmoid(X @ beta), observed=y)
+
+    @pm.model
+    def with_intercept():
+        beta = yield pm.Normal("beta", 0.0, 1.0, batch_stack=4)
+        b0 = yield pm.Normal("b0", 0.0, 1.0)
+        yield pm.Bernoulli("y", probs=pm.math.sigmoid(pm.math.matvec(X, beta) + b0), observed=y)
+
+    ir, _, _ = lower_model(with_matmul())
+    assert len(ir.glm_terms) == 1 and ir.glm_terms[0].glm.P == 4 and ir.lockstep
+    with pytest.raises(NotImplementedError, match="append a column of ones"):
+        lower_model(with_intercept())
+    Xi = np.concatenate([X, np.ones((50, 1))], axis=1)
+
+    @pm.model
+    def intercept_as_a_column():
+        beta = yield pm.Normal("beta", 0.0, 1.0, batch_stack=5)
+        yield pm.Bernoulli("y", probs=pm.math.sigmoid(Xi @ beta), observed=y)
+
+    ir2, _, _ = lower_model(intercept_as_a_column())
+    assert ir2.glm_terms[0].glm.P == 5
