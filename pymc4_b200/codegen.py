@@ -45,10 +45,13 @@ CSRC = os.path.join(_HERE, "csrc")
 CACHE_DIR = os.environ.get("PM4_KERNEL_CACHE", os.path.join(_HERE, "_kcache"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# experiments: extra nvcc flags for the model modules (part of the module hash)
+NVCC_FLAGS += os.environ.get("PM4_EXTRA_NVCC_FLAGS", "").split()
 # threads per block of the persistent single-precision kernels (registers per thread = 65536 / MAXT):
 # 512 = 128 registers, no spills; measured best on the radon model (1024: 64 registers, 280 B of spills)
 MAXT = int(os.environ.get("PM4_MAXT", "512"))
 _build_lock = threading.Lock()
+_path_locks: Dict[str, threading.Lock] = {}
 
 _UNARY_FWD = {
     "neg": "-{a}", "exp": "pm4::m_exp({a})", "log": "pm4::m_log({a})", "log1p": "pm4::m_log1p({a})",
@@ -860,7 +863,9 @@ def build_module(ir: I.ModelIR, has_f64: bool = False, force: bool = False, verb
     """Return the path of the compiled module for this IR structure, building it if needed."""
     path = module_path(ir, has_f64)
     alt = module_path(ir, True)  # a module with double precision also serves float requests
-    with _build_lock:
+    with _build_lock:  # one lock per module file: different models compile concurrently
+        lock = _path_locks.setdefault(path, threading.Lock())
+    with lock:
         for cand in (path, alt):
             if not force and os.path.exists(cand):
                 return cand

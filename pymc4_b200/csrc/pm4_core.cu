@@ -627,6 +627,13 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
   pm4m_run_fn f = nuts ? m->f_nuts : m->f_hmc;
   int t = 0;
   r.order = nullptr;
+  // PM4_PHASE_TIMES=1 (diagnostics): device time of the lock-step phase and of the persistent launches on stderr
+  static const bool phase_times = getenv("PM4_PHASE_TIMES") != nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  if (phase_times) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+  }
   if (r.adapt_enabled && r.adapt_pooled) {
     const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
     for (; t < coupled; ++t) {
@@ -636,6 +643,8 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
       MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");
     }
   }
+  const int t_coupled = t;
+  if (phase_times) cudaEventRecord(ev[1], st);
   // phase boundaries: a short first phase (step sizes settle within ~20 transitions), the end of
   // adaptation, the end of the run
   std::vector<int> ends;
@@ -646,6 +655,9 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
     if (freeze > (ends.empty() ? t : ends.back()) + 10 && freeze < T - 10) ends.push_back(freeze);
   }
   ends.push_back(T);
+  // persistent launches of the warp-per-chain path hand out (chain, block of tb transitions) items
+  static const int tb_env = getenv("PM4_TB") ? atoi(getenv("PM4_TB")) : 25;
+  r.tb = nuts && r.progress ? tb_env : 0;
   for (size_t k = 0; k < ends.size(); ++k) {
     if (ends[k] <= t) continue;
     r.t_begin = t;
@@ -656,6 +668,16 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
       MOD(m->f_order(r.C, r.launch_leaps, order_buf, st), "longest-first chain order");
       r.order = order_buf;
     }
+  }
+  if (phase_times) {
+    cudaEventRecord(ev[2], st);
+    cudaEventSynchronize(ev[2]);
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[1], ev[2]);
+    fprintf(stderr, "[pm4 phases] lock-step %d transitions %.3f ms (%.1f us each); persistent %d transitions %.3f ms\n",
+            t_coupled, a, t_coupled ? 1e3 * a / t_coupled : 0.0, T - t_coupled, b);
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   return PM4_OK;
 }
@@ -775,12 +797,14 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   const int64_t tree_bytes = m->f_scratch(dtype, &r.A, cfg->C, cfg->warps_per_block, cfg->max_tree_depth);
   if (tree_bytes < 0) return fail(PM4_EINVAL, "kernel module cannot size its tree scratch");
   if (tree_bytes > 0 && (rc = buf.get(&r.scratch, (size_t)tree_bytes))) return rc;
-  void *queue = nullptr, *order = nullptr, *leaps = nullptr;
+  void *queue = nullptr, *order = nullptr, *leaps = nullptr, *progress = nullptr;
   if ((rc = buf.get(&queue, 16))) return rc;
   if ((rc = buf.get(&order, C * sizeof(int32_t)))) return rc;
   if ((rc = buf.get(&leaps, C * sizeof(int32_t)))) return rc;
+  if ((rc = buf.get(&progress, C * sizeof(int32_t)))) return rc;
   r.queue = (int32_t*)queue;
   r.launch_leaps = (int32_t*)leaps;
+  r.progress = (int32_t*)progress;
   r.step_scale = step_scale_dev; r.momenta = momenta_dev;
   r.states = states_dev; r.lp_out = lp_dev; r.leapfrogs = leapfrogs_dev; r.diverging = diverging_dev;
   r.energy = energy_dev; r.log_accept = log_accept_dev; r.depth = depth_dev;

@@ -115,7 +115,10 @@ __device__ __forceinline__ Ctx<real> make_ctx(const ModelArgs<real>& A, unsigned
 // Models whose state needs more than LEAN_R registers per lane and vector keep only theta, momentum
 // and gradient in registers: the trajectory momentum sums live in tree-scratch slots and per-element
 // constants (overflow table, step scale) are re-read where they are used.
-constexpr int LEAN_R = 4;
+#ifndef PM4_LEAN_R
+#define PM4_LEAN_R 4
+#endif
+constexpr int LEAN_R = PM4_LEAN_R;
 
 // threads per block: the small variant (double precision, few chains, stateless kernels) and the big
 // single-precision variant; both hold at least one whole team
@@ -262,7 +265,8 @@ template <typename real> struct RunParams {
   ModelArgs<real> A;
   int C, t_begin, t_count, B, S, max_depth, num_leapfrog, chain_offset;
   int adapt_enabled, adapt_pooled, num_adapt, adapt_kind, random_walk;
-  int team_reals, n_slots, n_fast;
+  int team_reals, n_slots, n_fast, tb;
+  int32_t* progress;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay, adapt_rate, rw_scale;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -300,7 +304,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
   p.adapt_kind = r.adapt_kind; p.random_walk = r.random_walk;
   p.adapt_rate = (real)r.adapt_rate; p.rw_scale = (real)r.rw_scale;
-  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0;
+  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -1058,6 +1062,8 @@ template <class M, typename real, bool NUTS> inline int dispatch_run(const pm4_m
 
 }  // namespace pm4
 
+#include "pm4_warp.cuh"
+
 // ------------------------------------------------------------------------------------------
 // module entry points (csrc/pm4_module.h).  PM4_MODEL is the generated model struct.
 // ------------------------------------------------------------------------------------------
@@ -1164,6 +1170,7 @@ template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0
 template <typename real> int64_t mod_scratch_bytes(const pm4_mod_args_t* A, int C, int wpb, int max_depth) {
   using M = PM4_MODEL;
   ModelArgs<real> ma = make_model_args<real>(*A);
+  if constexpr (use_warp_path<M>()) return warp_scratch_bytes<M, real>(ma, C, wpb, max_depth);
   const int n_slots = scratch_slots<M>(true, max_depth);
   const Geometry g = plan_geometry<M, real>(ma, C, wpb, n_slots, max_threads_for<M, real>());
   if (g.scr_smem) return 0;
@@ -1216,9 +1223,15 @@ extern "C" int64_t pm4m_scratch_bytes(int dtype, const pm4_mod_args_t* A, int C,
 #endif
   return -22;
 }
+namespace pm4 {
+template <typename real> int mod_nuts(const pm4_mod_run_t* r, int wpb, cudaStream_t st) {
+  if constexpr (use_warp_path<PM4_MODEL>()) return dispatch_warp_nuts<PM4_MODEL, real>(*r, wpb, st);
+  else return dispatch_run<PM4_MODEL, real, true>(*r, wpb, st);
+}
+}  // namespace pm4
 extern "C" int pm4m_nuts(int dtype, const pm4_mod_run_t* r, int wpb, void* stream) {
-  PM4_BY_DTYPE((pm4::dispatch_run<PM4_MODEL, float, true>(*r, wpb, (cudaStream_t)stream)),
-               PM4_F64_CALL((pm4::dispatch_run<PM4_MODEL, double, true>(*r, wpb, (cudaStream_t)stream))));
+  PM4_BY_DTYPE((pm4::mod_nuts<float>(r, wpb, (cudaStream_t)stream)),
+               PM4_F64_CALL((pm4::mod_nuts<double>(r, wpb, (cudaStream_t)stream))));
 }
 extern "C" int pm4m_hmc(int dtype, const pm4_mod_run_t* r, int wpb, void* stream) {
   PM4_BY_DTYPE((pm4::dispatch_run<PM4_MODEL, float, false>(*r, wpb, (cudaStream_t)stream)),

@@ -67,6 +67,10 @@ def choose_team_warps(ir: "I.ModelIR") -> int:
             raise ValueError("PM4_TEAM_WARPS must be one of %s" % (TEAM_SIZES,))
         return t
     work = sum(t.n for t in ir.terms if t.glm is None)  # dense GLM terms are not evaluated by the teams
+    # small models: ONE warp per chain (csrc/pm4_warp.cuh) -- the state fits in 8 registers per lane and vector,
+    # reductions are warp shuffles, and nothing of the sampler's scalar logic is repeated by a second warp
+    if ir.D <= 32 * 8 and work <= 4096:
+        return 1
     # ~640 term elements per warp; at most ~20 state elements per lane (theta, momentum and gradient
     # stay in registers); never more than 16 warps (512 threads keep 128 registers per thread)
     want = max(work / 640.0, ir.D / (32.0 * 20.0))
