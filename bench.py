@@ -74,7 +74,7 @@ def parse_args():
 
 def build_model():
     from pymc4_b200.ir import lower_model
-    from tests import models as M
+    from pymc4_b200 import benchmodels as M
 
     if WORKLOAD == "gp":
         X, y = M.gp_data(n=N_OBS, d=1, seed=20261019)

@@ -775,6 +775,13 @@ class _ModuleGen:
         out.append("  }")
         return "\n".join(out)
 
+    def gen_owned(self) -> str:
+        from .codegen_owned import OwnedGen, not_owned_members
+
+        if self.ir.owned is None:
+            return not_owned_members()
+        return OwnedGen(self.ir, self.ir.owned).members()
+
     def source(self) -> str:
         ir = self.ir
         name = "Model_%s" % ir.struct_hash_hex
@@ -802,6 +809,7 @@ class _ModuleGen:
             self.gen_loglik(),
             self.gen_loglik(predictive=True),
             self.gen_prior(),
+            self.gen_owned(),
             "};",
             "#define PM4_MODEL %s" % name,
             "#define PM4_HAS_F64 %d" % (1 if self.has_f64 else 0),
@@ -829,7 +837,7 @@ def generator_hash() -> str:
 
         h = hashlib.sha256()
         deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
-        deps += [os.path.join(_HERE, f) for f in ("codegen.py", "plan.py", "ir.py")]
+        deps += [os.path.join(_HERE, f) for f in ("codegen.py", "codegen_owned.py", "owned.py", "plan.py", "ir.py")]
         for d in deps:
             with open(d, "rb") as f:
                 h.update(f.read())
@@ -854,7 +862,7 @@ def _csrc_mtime() -> float:
     """Newest modification time of anything a built module depends on (device headers and the
     generator itself: a module built by an older generator may read plans in an older layout)."""
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps += [os.path.join(_HERE, f) for f in ("codegen.py", "plan.py", "ir.py")]
+    deps += [os.path.join(_HERE, f) for f in ("codegen.py", "codegen_owned.py", "owned.py", "plan.py", "ir.py")]
     return max(os.path.getmtime(d) for d in deps)
 
 

@@ -8,14 +8,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "pm4_dists.cuh"
 #include "pm4_module.h"
+#include "pm4_pair.cuh"
 #include "pm4_philox.cuh"
 
 namespace pm4 {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int ELEM_CNT_BITS = 12;  // elem_tab entry = overflow first << 12 | count (pymc4_b200/plan.py)
+
+// header of the owner-computes plan (8 ints behind the per-plan headers of plani)
+struct OwnedHeader { int enabled, i_off, i_len, f_off, f_len, NF, Q, n; };
 
 // constant pools and run-time sizes the generated code reads (device pointers)
 template <typename real> struct ModelArgs {
@@ -27,11 +33,13 @@ template <typename real> struct ModelArgs {
   const int32_t* __restrict__ plani;
   const int32_t* __restrict__ plan_off;
   int n_planf, n_plani, part_reals, elem_off, spart_off, phdr_off, stage;
+  OwnedHeader oh;  // owner-computes plan of the warp-per-chain path (pymc4_b200/owned.py): host copy of its header
 };
 
 template <typename real> __host__ __device__ inline ModelArgs<real> make_model_args(const pm4_mod_args_t& a) {
   return ModelArgs<real>{(const real*)a.dataf, a.datai, a.term_n, a.op_blob, (const real*)a.planf, a.plani,
-                         a.plan_off, a.n_planf, a.n_plani, a.part_reals, a.elem_off, a.spart_off, a.phdr_off, a.stage};
+                         a.plan_off, a.n_planf, a.n_plani, a.part_reals, a.elem_off, a.spart_off, a.phdr_off, a.stage,
+                         OwnedHeader{a.owned[0], a.owned[1], a.owned[2], a.owned[3], a.owned[4], a.owned[5], a.owned[6], a.owned[7]}};
 }
 
 // per-lane evaluation context handed to the generated model code

@@ -106,6 +106,7 @@ struct pm4_model {
   pm4m_scratch_bytes_fn f_scratch = nullptr;
   pm4m_lpt_order_fn f_order = nullptr;
   int elem_off = 0, spart_off = 0, phdr_off = 0;
+  int32_t owned_hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float* d_f32 = nullptr;
   double* d_f64 = nullptr;
   int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
@@ -134,6 +135,7 @@ struct pm4_model {
     // stage the plan pools in shared memory when they leave room for the per-chain state
     const size_t pool_bytes = (size_t)n_planf * (dtype == PM4_F64 ? 8 : 4) + (size_t)n_plani * 4;
     a.stage = (pool_bytes <= 96 * 1024) ? 1 : 0;
+    memcpy(a.owned, owned_hdr, sizeof a.owned);
     return a;
   }
 };
@@ -167,6 +169,18 @@ static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   m->elem_off = (int)ir->elem_off;
   m->spart_off = (int)ir->spart_off;
   m->phdr_off = (int)ir->phdr_off;
+  // owner-computes plan of the warp-per-chain path (pymc4_b200/owned.py): 8 ints behind the per-plan headers
+  memset(m->owned_hdr, 0, sizeof m->owned_hdr);
+  const int64_t oh = ir->phdr_off + 4 * (ir->n_plans > 0 ? ir->n_plans : 1);
+  if (oh + 8 <= ni) {
+    const int32_t* h = ir->plani + oh;
+    if (h[0] == 1) {
+      if (h[1] < 0 || h[2] < 0 || h[1] + (int64_t)h[2] > ni || h[3] < 0 || h[4] < 0 || h[3] + (int64_t)h[4] > nf || (h[2] % 4) || (h[4] % 4) ||
+          (h[1] % 4) || (h[3] % 4))
+        return fail(PM4_EINVAL, "owned plan sections point outside the plan pools");
+      memcpy(m->owned_hdr, h, sizeof m->owned_hdr);
+    }
+  }
   return PM4_OK;
 }
 

@@ -1100,6 +1100,14 @@ template <typename real>
 int mod_logp_grad(const pm4_mod_args_t* A, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
   using M = PM4_MODEL;
   ModelArgs<real> ma = make_model_args<real>(*A);
+  if constexpr (M::OWNED) {  // the sampler's own arithmetic: owner-computes layout, one warp per chain
+    if (!ma.oh.enabled) return (int)cudaErrorInvalidValue;
+    const size_t smem = owned_pool_bytes(ma.oh, sizeof(real));
+    if (smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
+    PM4_CUDA_OK(cudaFuncSetAttribute(logp_grad_o_kernel<M, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    logp_grad_o_kernel<M, real><<<(unsigned)((C + 7) / 8), 256, smem, st>>>(ma, C, (const real*)theta, (real*)lp, (real*)grad);
+    return (int)cudaGetLastError();
+  }
   const Geometry g = small_geometry<M, real>(ma, C);
   if (g.smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
   const unsigned threads = (unsigned)(g.teams * M::T * 32);
@@ -1153,6 +1161,14 @@ int mod_prior(const pm4_mod_args_t* A, int64_t n, void* x_out, void* obs_out, ui
 template <typename real> int mod_init(const pm4_mod_run_t* r, const void* theta0, double eps0, cudaStream_t st) {
   using M = PM4_MODEL;
   RunParams<real> p = make_run_params<real>(*r);
+  if constexpr (M::OWNED) {
+    if (!p.A.oh.enabled) return (int)cudaErrorInvalidValue;
+    const size_t smem = owned_pool_bytes(p.A.oh, sizeof(real));
+    if (smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
+    PM4_CUDA_OK(cudaFuncSetAttribute(init_o_kernel<M, real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    init_o_kernel<M, real><<<(unsigned)((r->C + 7) / 8), 256, smem, st>>>(p, (const real*)theta0, (real)eps0);
+    return (int)cudaGetLastError();
+  }
   const Geometry g = small_geometry<M, real>(p.A, r->C);
   if (g.smem > SMEM_LIMIT) return (int)cudaErrorInvalidConfiguration;
   p.team_reals = g.team_reals;

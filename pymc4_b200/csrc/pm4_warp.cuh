@@ -60,19 +60,157 @@ __device__ __forceinline__ void st_release(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------
+// owner-computes layout (pymc4_b200/owned.py, Model::OWNED): the chain's state sits in RI registers per
+// lane in the plan's internal order; element perm[reg * 32 + lane] of theta (or none).  The plan's pools
+// (records as pairs of observations, slice tables) are staged once per CTA with a TMA bulk copy.
+// ------------------------------------------------------------------------------------------
+template <typename real, int RI> struct OCtx {
+  int lane;
+  int pj[RI];           // theta element held by register r of this lane, or -1
+  const real* rec;      // shared memory: pair records
+  const int32_t* oi;    // shared memory: owned int section (perm | own_len | slice bases + sentinel | foreign meta int4)
+  int len_off, slb_off, fm_off, NF, Q, n_term;
+  ModelArgs<real> A;
+};
+
+// bytes of the staged owned pools (+ the mbarrier); the host reads the header from its own copy
+__host__ __device__ inline size_t owned_pool_bytes(const OwnedHeader& h, size_t real_size) {
+  return 16 + (size_t)h.f_len * real_size + (size_t)h.i_len * sizeof(int32_t);
+}
+
+// Must be called by ALL threads of the CTA.  Returns the context; *scratch_base = first byte after the pools.
+template <class M, typename real>
+__device__ __forceinline__ OCtx<real, M::RI> make_octx(const ModelArgs<real>& A, unsigned char* smem_raw, size_t* pool_bytes_out) {
+  OCtx<real, M::RI> c;
+  c.lane = threadIdx.x & 31;
+  c.A = A;
+  const OwnedHeader h = A.oh;
+  const uint32_t fbytes = (uint32_t)h.f_len * (uint32_t)sizeof(real), ibytes = (uint32_t)h.i_len * 4u;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+  unsigned char* sf = smem_raw + 16;
+  unsigned char* si = sf + fbytes;
+  const uint32_t bar = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(fbytes + ibytes) : "memory");
+    const unsigned char* gf = reinterpret_cast<const unsigned char*>(A.planf + h.f_off);
+    const unsigned char* gi = reinterpret_cast<const unsigned char*>(A.plani + h.i_off);
+    for (uint32_t off = 0; off < fbytes; off += 32768u) {
+      const uint32_t nb = fbytes - off < 32768u ? fbytes - off : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sf + off)), "l"(gf + off), "r"(nb), "r"(bar) : "memory");
+    }
+    for (uint32_t off = 0; off < ibytes; off += 32768u) {
+      const uint32_t nb = ibytes - off < 32768u ? ibytes - off : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(si + off)), "l"(gi + off), "r"(nb), "r"(bar) : "memory");
+    }
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+  }
+  c.rec = reinterpret_cast<const real*>(sf);
+  c.oi = reinterpret_cast<const int32_t*>(si);
+  constexpr int KS1 = M::KS > 0 ? M::KS : 1;
+  const int n_sl = M::KS + h.NF + 1;  // slice bases + sentinel
+  c.len_off = M::RI * 32;
+  c.slb_off = c.len_off + KS1 * 32;
+  c.fm_off = c.slb_off + ((n_sl + 3) & ~3);
+  c.NF = h.NF; c.Q = h.Q; c.n_term = h.n;
+#pragma unroll
+  for (int r = 0; r < M::RI; ++r) c.pj[r] = c.oi[r * 32 + c.lane];
+  *pool_bytes_out = 16 + (size_t)fbytes + ibytes;
+  return c;
+}
+
+// joint log-density + gradient in unconstrained space on the internal layout: shuffles only, no barrier
+template <class M, typename real, class OC>
+__device__ __forceinline__ real logp_grad_o(const real (&th)[M::RI], real (&g)[M::RI], const OC& c) {
+  constexpr int RI = M::RI;
+  real x[RI], dxdz[RI], gr[RI];
+  M::template constrain_o<real>(th, x, dxdz, c.lane);
+#pragma unroll
+  for (int r = 0; r < RI; ++r) gr[r] = 0;
+  const real lp = M::template terms_o<real>(x, gr, c);
+#pragma unroll
+  for (int r = 0; r < RI; ++r) g[r] = ((M::ID_REGS >> r) & 1u) ? gr[r] : gr[r] * dxdz[r];
+  return lp;
+}
+
+// ------------------------------------------------------------------------------------------
+// what the warp kernel needs from a layout: RV registers per vector, elem(r) = theta element of register r
+// of this lane (or -1), the gradient, the momentum draw, this warp's shared-memory scratch
+// ------------------------------------------------------------------------------------------
+template <class M, typename real, bool STAGED> struct StripedWarp {  // theta order, xs / part hand-over (plan.py)
+  static constexpr int RV = M::R;
+  Ctx<real> c;
+  Own<M, real> own;
+  __device__ __forceinline__ void init(const RunParams<real>& a, unsigned char* smem_raw) {
+    c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
+    own.load(c);
+  }
+  __device__ __forceinline__ int lane() const { return c.lane; }
+  __device__ __forceinline__ real* scratch() const { return c.scr; }
+  __device__ __forceinline__ int elem(int r) const { const int j = c.lane + 32 * r; return j < M::D ? j : -1; }
+  __device__ __forceinline__ real grad(const real (&th)[RV], real (&g)[RV]) { return logp_grad<M, real>(th, g, c, own); }
+  __device__ __forceinline__ void momentum(const RunParams<real>& a, int chain, int t, real (&p)[RV]) {
+    draw_momentum<M, real>(a, chain, t, c.lane, p);
+  }
+};
+
+template <class M, typename real> struct OwnedWarp {  // owner-computes layout (owned.py)
+  static constexpr int RV = M::RI;
+  OCtx<real, M::RI> c;
+  real* scr;
+  __device__ __forceinline__ void init(const RunParams<real>& a, unsigned char* smem_raw) {
+    size_t pool = 0;
+    c = make_octx<M, real>(a.A, smem_raw, &pool);
+    scr = reinterpret_cast<real*>(smem_raw + pool) + (size_t)(threadIdx.x >> 5) * (size_t)a.team_reals;
+  }
+  __device__ __forceinline__ int lane() const { return c.lane; }
+  __device__ __forceinline__ real* scratch() const { return scr; }
+  __device__ __forceinline__ int elem(int r) const { return c.pj[r]; }
+  __device__ __forceinline__ real grad(const real (&th)[RV], real (&g)[RV]) { return logp_grad_o<M, real>(th, g, c); }
+  // the Philox stream is keyed by theta element in blocks of four: draw in theta order (two blocks per lane
+  // for D <= 256), then permute through this warp's scratch (free at the start of a transition)
+  __device__ __forceinline__ void momentum(const RunParams<real>& a, int chain, int t, real (&p)[RV]) {
+    if (a.momenta) {
+#pragma unroll
+      for (int r = 0; r < RV; ++r) p[r] = c.pj[r] >= 0 ? a.momenta[((size_t)t * a.C + chain) * M::D + c.pj[r]] : (real)0;
+      return;
+    }
+    real ps[M::R];
+    draw_momentum<M, real>(a, chain, t, c.lane, ps);
+#pragma unroll
+    for (int r = 0; r < M::R; ++r) scr[c.lane + 32 * r] = ps[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < RV; ++r) p[r] = c.pj[r] >= 0 ? scr[c.pj[r]] : (real)0;
+    __syncwarp();
+  }
+};
+
 template <class M, typename real, int MAXT, bool STAGED>
 __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
   static_assert(M::T == 1, "one warp per chain");
-  constexpr int R = M::R, D = M::D, DP = M::DP, DS = M::DS;
-  static_assert(DS == DP, "scratch vectors of the warp path are as long as the padded state");
+  using L = typename std::conditional<M::OWNED, OwnedWarp<M, real>, StripedWarp<M, real, STAGED>>::type;
+  constexpr int R = L::RV, D = M::D, DP = M::DP, DS = 32 * R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Ctx<real> c = make_ctx<M, real, STAGED>(a.A, smem_raw, a.team_reals);
-  const int lane = c.lane;
+  L lay;
+  lay.init(a, smem_raw);
+  const int lane = lay.lane();
   const real NEG_INF = -m_inf<real>();
   const size_t C = (size_t)a.C;
   const int NL = a.n_fast;  // checkpoint levels on chip
   // shared-memory slots of this warp (lane-private columns: no synchronisation needed)
-  real* const s_sub_th = c.scr + lane;
+  real* const s_sub_th = lay.scratch() + lane;
   real* const s_sub_g = s_sub_th + DS;
   real* const s_oth_p = s_sub_g + DS;
   real* const s_mem = s_oth_p + DS;  // level l: momentum at 2 l DS, rho at (2 l + 1) DS
@@ -87,11 +225,14 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
     if (l < NL) f(s_mem + 2 * l * DS);
     else f(g_mem + 2 * (l - NL) * DS);
   };
-
-  Own<M, real> own;
-  own.load(c);
-  StepScale<M, real> sc;
-  sc.load(a.step_scale, lane);
+  // theta element of every register of this lane, and its step scale
+  int ej[R];
+  real scl[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ej[r] = lay.elem(r);
+    scl[r] = (a.step_scale && ej[r] >= 0) ? a.step_scale[ej[r]] : (real)1;
+  }
   const int tb = a.tb > 0 ? a.tb : a.t_count;
   const int n_blocks = (a.t_count + tb - 1) / tb;
   const int n_items = n_blocks * a.C;
@@ -112,8 +253,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
       __syncwarp();
     }
     const uint32_t rng_chain = (uint32_t)(a.chain_offset + chain);
-    real* const cth = a.th + (size_t)chain * DP + lane;  // the chain's current point = the transition's candidate
-    real* const cg = a.gr + (size_t)chain * DP + lane;
+    real* const cth = a.th + (size_t)chain * DP;  // the chain's current point = the transition's candidate (theta order)
+    real* const cg = a.gr + (size_t)chain * DP;
     real clp = __ldcg(a.lp + chain);
     DualAvg<real> da;
     {
@@ -125,12 +266,12 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
     for (int t = t0; t < t1; ++t) {
       real th[R], p[R], g[R], rho[R], rho_sub[R];
       const real eps = da.eps;
-      draw_momentum<M, real>(a, chain, t, lane, p);
+      lay.momentum(a, chain, t, p);
       real q0 = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        th[r] = __ldcg(cth + 32 * r);
-        g[r] = __ldcg(cg + 32 * r);
+        th[r] = ej[r] >= 0 ? __ldcg(cth + ej[r]) : (real)0;
+        g[r] = ej[r] >= 0 ? __ldcg(cg + ej[r]) : (real)0;
         rho[r] = p[r];
         q0 += p[r] * p[r];
         g_oth_th[32 * r] = th[r];
@@ -168,8 +309,7 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
         const real eps_s = dir ? eps : -eps;
         real es_r[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) es_r[r] = eps_s * sc(r);
-        auto es = [&](int r) -> real { return es_r[r]; };
+        for (int r = 0; r < R; ++r) es_r[r] = eps_s * scl[r];
         real w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
         bool cont_sub = true;
         int sub_leaps = 0;
@@ -180,7 +320,18 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
           if ((i & 63) == 0)
             ul = philox4x32_10(rng_chain, (uint32_t)t, ((uint32_t)depth << 20) | (uint32_t)((i >> 1) + lane),
                                RNG_LEAF, a.seed_lo, a.seed_hi);
-          cur_lp = leapfrog<M, real>(th, p, g, es, c, own);
+          // one leapfrog step: tfp SimpleLeapfrogIntegrator with num_steps = 1
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            p[r] = p[r] + ((real)0.5 * es_r[r]) * g[r];
+            th[r] = th[r] + es_r[r] * p[r];
+          }
+          cur_lp = lay.grad(th, g);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            p[r] = p[r] + es_r[r] * g[r];
+            p[r] = p[r] - ((real)0.5 * es_r[r]) * g[r];
+          }
           sub_leaps += 1;
 
           // one reduction per leaf: kinetic energy and, on odd leaves, the U-turn test against the
@@ -282,8 +433,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
         if ((umerge <= thresh) && cont_sub) {
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            cth[32 * r] = s_sub_th[32 * r];
-            cg[32 * r] = s_sub_g[32 * r];
+            if (ej[r] >= 0) {
+              cth[ej[r]] = s_sub_th[32 * r];
+              cg[ej[r]] = s_sub_g[32 * r];
+            }
           }
           cand_lp = sub_lp;
           cand_energy = sub_energy;
@@ -314,10 +467,8 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
         const size_t k = (size_t)(t - a.B) * C + chain;
         if (a.states) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int j = lane + 32 * r;
-            if (j < D) __stcs(a.states + k * D + j, __ldcg(cth + 32 * r));
-          }
+          for (int r = 0; r < R; ++r)
+            if (ej[r] >= 0) __stcs(a.states + k * D + ej[r], __ldcg(cth + ej[r]));
         }
         if (lane == 0) {
           if (a.lp_out) a.lp_out[k] = cand_lp;
@@ -337,10 +488,61 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
       if (a.total_leapfrogs) a.total_leapfrogs[chain] = __ldcg(a.total_leapfrogs + chain) + launch_leaps;
       if (a.launch_leaps) a.launch_leaps[chain] = (blk == 0 ? 0 : __ldcg(a.launch_leaps + chain)) + launch_leaps;
     }
-    if (n_blocks > 1) {
-      __syncwarp();
+    if (n_blocks > 1) {  // every lane's stores are fenced before lane 0 publishes the block
       __threadfence();
+      __syncwarp();
       if (lane == 0) st_release(a.progress + chain, blk + 1);
+    }
+  }
+}
+
+// parity kernel (a) and bootstrap on the owner-computes layout: one warp per chain
+template <class M, typename real>
+__global__ void __launch_bounds__(256) logp_grad_o_kernel(ModelArgs<real> A, int C, const real* __restrict__ theta,
+                                                         real* __restrict__ lp_out, real* __restrict__ grad_out) {
+  constexpr int RI = M::RI, D = M::D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  size_t pool = 0;
+  const OCtx<real, RI> c = make_octx<M, real>(A, smem_raw, &pool);
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chain >= C) return;
+  real th[RI], g[RI];
+#pragma unroll
+  for (int r = 0; r < RI; ++r) th[r] = c.pj[r] >= 0 ? theta[(size_t)chain * D + c.pj[r]] : (real)0;
+  const real lp = logp_grad_o<M, real>(th, g, c);
+  if (c.lane == 0) lp_out[chain] = lp;
+  if (grad_out) {
+#pragma unroll
+    for (int r = 0; r < RI; ++r)
+      if (c.pj[r] >= 0) grad_out[(size_t)chain * D + c.pj[r]] = g[r];
+  }
+}
+
+template <class M, typename real>
+__global__ void __launch_bounds__(256) init_o_kernel(RunParams<real> a, const real* __restrict__ theta0, real eps0) {
+  constexpr int RI = M::RI, D = M::D, DP = M::DP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  size_t pool = 0;
+  const OCtx<real, RI> c = make_octx<M, real>(a.A, smem_raw, &pool);
+  const int chain = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chain >= a.C) return;
+  real th[RI], g[RI];
+#pragma unroll
+  for (int r = 0; r < RI; ++r) th[r] = c.pj[r] >= 0 ? theta0[(size_t)chain * D + c.pj[r]] : (real)0;
+  const real lp = logp_grad_o<M, real>(th, g, c);
+#pragma unroll
+  for (int r = 0; r < RI; ++r) {
+    if (c.pj[r] >= 0) {
+      a.th[(size_t)chain * DP + c.pj[r]] = th[r];
+      a.gr[(size_t)chain * DP + c.pj[r]] = g[r];
+    }
+  }
+  if (c.lane == 0) {
+    a.lp[chain] = lp;
+    if (a.total_leapfrogs) a.total_leapfrogs[chain] = 0;
+    if (!a.adapt_pooled || chain == 0) {
+      real* d = a.da + (a.adapt_pooled ? 0 : (size_t)chain * 4);
+      d[0] = eps0; d[1] = 0; d[2] = 0; d[3] = m_log((real)10 * eps0);
     }
   }
 }
@@ -351,8 +553,14 @@ struct WarpGeometry {
   size_t smem;
 };
 
+template <class M, typename real> inline size_t warp_pool_bytes(const ModelArgs<real>& A) {
+  if constexpr (M::OWNED) return owned_pool_bytes(A.oh, sizeof(real));
+  else return pool_bytes(A);
+}
+
 template <class M, typename real>
 inline WarpGeometry plan_warp_geometry(ModelArgs<real>& A, int C, int wpb, int max_depth, int max_threads) {
+  constexpr int DSV = M::OWNED ? 32 * M::RI : M::DS;
   WarpGeometry g{};
   const int sms = sm_count();
   int warps = max_threads / 32;
@@ -360,26 +568,29 @@ inline WarpGeometry plan_warp_geometry(ModelArgs<real>& A, int C, int wpb, int m
   const int per_sm = (C + sms - 1) / sms;
   if (wpb <= 0 && warps > per_sm) warps = per_sm;
   if (warps < 1) warps = 1;
-  const size_t base = team_base_reals<M, real>(A);
-  if (A.stage && pool_bytes(A) > SMEM_LIMIT / 2) A.stage = 0;
+  const size_t base = M::OWNED ? 0 : team_base_reals<M, real>(A);
+  if (!M::OWNED && A.stage && pool_bytes(A) > SMEM_LIMIT / 2) A.stage = 0;
   const int want = max_depth + 1;
   int lvl = 0;
   for (;;) {
-    const size_t fixed = pool_bytes(A) + (size_t)warps * (base + (size_t)WARP_FIXED_SLOTS * M::DS) * sizeof(real);
-    const size_t per_lvl = (size_t)warps * 2 * M::DS * sizeof(real);
+    const size_t fixed = warp_pool_bytes<M, real>(A) + (size_t)warps * (base + (size_t)WARP_FIXED_SLOTS * DSV) * sizeof(real);
+    const size_t per_lvl = (size_t)warps * 2 * DSV * sizeof(real);
     lvl = fixed < SMEM_LIMIT ? (int)((SMEM_LIMIT - fixed) / per_lvl) : -1;
     if (lvl > want) lvl = want;
     // four levels serve every tree of up to 31 leapfrogs: give up warps before going below that
     if (lvl >= (want < 4 ? want : 4) || warps == 1) break;
     --warps;
   }
-  if (lvl < 0) { A.stage = 0; lvl = 0; }
+  if (lvl < 0) {
+    if (!M::OWNED) A.stage = 0;
+    lvl = 0;
+  }
   g.warps = warps;
   g.n_lvl = lvl;
   g.n_gslots = WARP_GLOBAL_FIXED + 2 * (want - lvl);
-  g.team_reals = (int)(base + (size_t)(WARP_FIXED_SLOTS + 2 * lvl) * M::DS);
+  g.team_reals = (int)(base + (size_t)(WARP_FIXED_SLOTS + 2 * lvl) * DSV);
   g.stage = A.stage;
-  g.smem = pool_bytes(A) + (size_t)warps * g.team_reals * sizeof(real);
+  g.smem = warp_pool_bytes<M, real>(A) + (size_t)warps * g.team_reals * sizeof(real);
   int grid = (C + warps - 1) / warps;
   if (grid > sms) grid = sms;
   g.grid = grid;
@@ -403,12 +614,12 @@ template <class M, typename real> inline int dispatch_warp_nuts(const pm4_mod_ru
     return (int)cudaGetLastError();                                                                              \
   } while (0)
   if (g.warps * 32 <= small_threads<M>()) {
-    if (g.stage) PM4_WLAUNCH(small_threads<M>(), true);
-    PM4_WLAUNCH(small_threads<M>(), false);
+    if (M::OWNED || g.stage) PM4_WLAUNCH(small_threads<M>(), true);
+    if constexpr (!M::OWNED) PM4_WLAUNCH(small_threads<M>(), false);
   }
   if constexpr (sizeof(real) == 4) {
-    if (g.stage) PM4_WLAUNCH(big_threads<M>(), true);
-    PM4_WLAUNCH(big_threads<M>(), false);
+    if (M::OWNED || g.stage) PM4_WLAUNCH(big_threads<M>(), true);
+    if constexpr (!M::OWNED) PM4_WLAUNCH(big_threads<M>(), false);
   }
 #undef PM4_WLAUNCH
   return (int)cudaErrorInvalidConfiguration;
@@ -416,7 +627,7 @@ template <class M, typename real> inline int dispatch_warp_nuts(const pm4_mod_ru
 
 template <class M, typename real> inline int64_t warp_scratch_bytes(ModelArgs<real>& A, int C, int wpb, int max_depth) {
   const WarpGeometry g = plan_warp_geometry<M, real>(A, C, wpb, max_depth, max_threads_for<M, real>());
-  return (int64_t)g.grid * g.warps * g.n_gslots * M::DS * (int64_t)sizeof(real);
+  return (int64_t)g.grid * g.warps * g.n_gslots * (M::OWNED ? 32 * M::RI : M::DS) * (int64_t)sizeof(real);
 }
 
 }  // namespace pm4

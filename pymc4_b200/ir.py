@@ -195,6 +195,7 @@ class ModelIR:
     phdr_off: int = 0      # offset of the per-plan int4 headers in plani
     part_reals: int = 4
     part_k: int = 2        # fixed part entries per gradient element
+    owned: Any = None      # owner-computes layout of the warp-per-chain path (pymc4_b200/owned.py), or None
 
     @property
     def plans(self) -> List["Plan"]:
@@ -255,6 +256,8 @@ class ModelIR:
         for d in self.dets:
             h.append(struct.pack("<iii", d.value_reg, len(d.ops), d.n))
             ops_key(d.ops, d.n)
+        if self.owned is not None:
+            h.append(self.owned.key())
         return b"".join(h)
 
     @property
@@ -685,9 +688,11 @@ def lower_model(model: Model, observed: Optional[dict] = None, state=None,
     observed_np = {k: sym.as_numpy(v) for k, v in st.observed_values.items()}
     ir = ModelIR(D=D, rvs=list(rvs.values()), terms=terms, dets=dets, dataf=dataf, datai=datai,
                  observed=observed_np)
+    from .owned import attach_owned
     from .plan import attach_plans
 
     attach_plans(ir, team_warps)
+    attach_owned(ir)
     return ir, init_state, deterministic_names
 
 
