@@ -633,91 +633,97 @@ class OwnedGen:
                     st = st.replace("%sa += " % nm, "%ss += " % nm)
                 E(st, indent)
 
-        E("const int n_sl = %d + c.NF;" % KS, 3)
-        E("#pragma unroll 1", 3)
-        E("for (int s = 0; s < n_sl; ++s) {  // owned slices, then the foreign pieces of the groups capped in slice 0", 3)
-        E("const bool own = s < %d;  // warp-uniform" % KS, 4)
-        E("const int sb0 = c.oi[c.slb_off + s], npr = c.oi[c.slb_off + s + 1] - sb0;  // first pair row, pair rows of the slice", 4)
-        E("int4 fm = make_int4(0, 0, 0, -1);  // foreign: rows, owner lane, segment mask, head lane of this owner's segment", 4)
-        E("if (!own) fm = *reinterpret_cast<const int4*>(c.oi + c.fm_off + ((s - %d) * 32 + lane) * 4);" % KS, 4)
-        E("const int len = own ? c.oi[c.len_off + s * 32 + lane] : fm.x, npl = len >> 1;", 4)
-        for nm in vecs:
-            v = vidx[nm]
-            regs = [v * KS + k for k in range(KS)]
-            E("real %sv = %s;" % (nm, sel(regs)), 4)
-            E("if (!own) %sv = __shfl_sync(pm4::FULL, x[%d], fm.y);  // the owner's slot is in slice 0" % (nm, v * KS), 4)
+        def walk_slice(s_expr: str, own_slice: Optional[int]) -> None:
+            """rows of slice s_expr; own_slice = compile-time owned slice index, None for a foreign slice (run-time)"""
+            ind = 4
+            E("const int sb0 = c.oi[c.slb_off + %s], npr = c.oi[c.slb_off + %s + 1] - sb0;  // first pair row, pair rows (uniform)"
+              % (s_expr, s_expr), ind)
+            if own_slice is None:
+                E("const int4 fm = *reinterpret_cast<const int4*>(c.oi + c.fm_off + (f * 32 + lane) * 4);  // rows, owner lane, segment mask, head lane of this owner's segment", ind)
+                E("const int len = fm.x, npl = len >> 1;", ind)
+            else:
+                E("const int len = c.oi[c.len_off + %d + lane], npl = len >> 1;" % (32 * own_slice), ind)
+            for nm in vecs:
+                v = vidx[nm]
+                if own_slice is None:
+                    E("const real %sv = __shfl_sync(pm4::FULL, x[%d], fm.y);  // the owner's slot is in slice 0" % (nm, v * KS), ind)
+                else:
+                    E("const real %sv = x[%d];" % (nm, v * KS + own_slice), ind)
+                if pair:
+                    E("const P2 %svp = pm4::pk_bcast<real>(%sv);" % (nm, nm), ind)
+            E("const %s* rp = %s_rec + sb0 * 32;" % (rec_t, tag), ind)
             if pair:
-                E("const P2 %svp = pm4::pk_bcast<real>(%sv);" % (nm, nm), 4)
-        E("const %s* rp = %s_rec + sb0 * 32;" % (rec_t, tag), 4)
-        if pair:
-            for nm in vecs:
-                E("P2 %sa = pm4::pk_bcast<real>((real)0);" % nm, 4)
-            # rows beyond this lane's chunk are predicated off by a bit test on an opaque per-lane mask (a comparison
-            # against the row index would be turned into a chain of divergent branches); blocks of 4, 2, 1 pair rows
-            E("unsigned mk = npl >= 32 ? 0xffffffffu : ((1u << npl) - 1u);  // bit k: pair row k belongs to this lane", 4)
+                for nm in vecs:
+                    E("P2 %sa = pm4::pk_bcast<real>((real)0);" % nm, ind)
+                # rows beyond this lane's chunk are predicated off by a bit test on an opaque per-lane mask (a comparison
+                # against the row index would be turned into a chain of divergent branches); blocks of 4, 2, 1 pair rows
+                E("unsigned mk = npl >= 32 ? 0xffffffffu : ((1u << npl) - 1u);  // bit k: pair row k belongs to this lane", ind)
 
-            def body(kk: int, ind: int) -> None:
-                E("if ((mk >> %d) & 1u) {" % kk, ind)
-                E("const %s rq = rp[%d * 32];" % (rec_t, kk), ind + 1)
-                for j in range(W):
-                    E("const P2 %s_c%d = pm4::rec_col<real, %d>(rq, %d);" % (tag, j, W, j), ind + 1)
-                for ln in pair_lines:
-                    E(ln, ind + 1)
+                def body(kk: int, i2: int) -> None:
+                    E("if ((mk >> %d) & 1u) {" % kk, i2)
+                    E("const %s rq = rp[%d * 32];" % (rec_t, kk), i2 + 1)
+                    for j in range(W):
+                        E("const P2 %s_c%d = pm4::rec_col<real, %d>(rq, %d);" % (tag, j, W, j), i2 + 1)
+                    for ln in pair_lines:
+                        E(ln, i2 + 1)
+                    E("}", i2)
+
+                E("int k = 0;", ind)
+                E("#pragma unroll 1", ind)
+                E("for (; k + 4 <= npr; k += 4, rp += 4 * 32, mk >>= 4) {  // uniform trip count", ind)
+                for kk in range(4):
+                    body(kk, ind + 1)
                 E("}", ind)
+                E("if (npr & 2) {", ind)
+                for kk in range(2):
+                    body(kk, ind + 1)
+                E("rp += 2 * 32; mk >>= 2;", ind + 1)
+                E("}", ind)
+                E("if (npr & 1) {", ind)
+                body(0, ind + 1)
+                E("}", ind)
+                for nm in vecs:
+                    E("real %ss = pm4::pk_hsum(%sa);" % (nm, nm), ind)
+                E("if (len & 1) {  // odd last observation: first half of the zero-padded pair", ind)
+                E("const %s rq = %s_rec[(sb0 + npl) * 32];" % (rec_t, tag), ind + 2)
+                for j in range(W):
+                    E("const real %s_c%d = pm4::rec_col<real, %d>(rq, %d).x;" % (tag, j, W, j), ind + 2)
+                E("const int i = 0; (void)i;", ind + 2)
+                scalar_row(ind + 2)
+                E("}", ind)
+            else:
+                for nm in vecs:
+                    E("real %ss = 0;" % nm, ind)
+                E("#pragma unroll 1", ind)
+                E("for (int i2 = 0; i2 < 2 * npr; ++i2) {  // uniform trip count, rows beyond the lane's chunk predicated off", ind)
+                E("if (i2 < len) {", ind + 1)
+                E("const %s rq = rp[(i2 >> 1) * 32];" % rec_t, ind + 2)
+                E("const int i = 0; (void)i;", ind + 2)
+                for j in range(W):
+                    E("const pm4::Pk<real> %s_cp%d = pm4::rec_col<real, %d>(rq, %d);" % (tag, j, W, j), ind + 2)
+                    E("const real %s_c%d = (i2 & 1) ? %s_cp%d.y : %s_cp%d.x;" % (tag, j, tag, j, tag, j), ind + 2)
+                scalar_row(ind + 2)
+                E("}", ind + 1)
+                E("}", ind)
+            if own_slice is not None:
+                for nm in vecs:
+                    E("gr[%d] += %s;" % (vidx[nm] * KS + own_slice, sink("%ss" % nm)), ind)
+            else:
+                E("for (int q = 0; q < c.Q; ++q) {  // segmented shuffle reduction over the pieces of one group ...", ind)
+                for nm in vecs:
+                    E("{ const real tq = __shfl_down_sync(pm4::FULL, %ss, 1u << q); if ((fm.z >> q) & 1) %ss += tq; }" % (nm, nm), ind + 2)
+                E("}", ind)
+                for nm in vecs:
+                    E("{ const real tq = __shfl_sync(pm4::FULL, %ss, fm.w < 0 ? lane : fm.w); if (fm.w >= 0) gr[%d] += %s; }  // ... then the owner pulls the total"
+                      % (nm, vidx[nm] * KS, sink("tq")), ind)
 
-            E("int k = 0;", 4)
-            E("#pragma unroll 1", 4)
-            E("for (; k + 4 <= npr; k += 4, rp += 4 * 32, mk >>= 4) {  // uniform trip count", 4)
-            for kk in range(4):
-                body(kk, 5)
-            E("}", 4)
-            E("if (npr & 2) {", 4)
-            for kk in range(2):
-                body(kk, 5)
-            E("rp += 2 * 32; mk >>= 2;", 5)
-            E("}", 4)
-            E("if (npr & 1) {", 4)
-            body(0, 5)
-            E("}", 4)
-            for nm in vecs:
-                E("real %ss = pm4::pk_hsum(%sa);" % (nm, nm), 4)
-            E("if (len & 1) {  // odd last observation: first half of the zero-padded pair", 4)
-            E("const %s rq = %s_rec[(sb0 + npl) * 32];" % (rec_t, tag), 6)
-            for j in range(W):
-                E("const real %s_c%d = pm4::rec_col<real, %d>(rq, %d).x;" % (tag, j, W, j), 6)
-            E("const int i = 0; (void)i;", 6)
-            scalar_row(6)
-            E("}", 4)
-        else:
-            for nm in vecs:
-                E("real %ss = 0;" % nm, 4)
-            E("#pragma unroll 1", 4)
-            E("for (int i2 = 0; i2 < 2 * npr; ++i2) {  // uniform trip count, rows beyond the lane's chunk predicated off", 4)
-            E("if (i2 < len) {", 5)
-            E("const %s rq = rp[(i2 >> 1) * 32];" % rec_t, 6)
-            E("const int i = 0; (void)i;", 6)
-            for j in range(W):
-                E("const pm4::Pk<real> %s_cp%d = pm4::rec_col<real, %d>(rq, %d);" % (tag, j, W, j), 6)
-                E("const real %s_c%d = (i2 & 1) ? %s_cp%d.y : %s_cp%d.x;" % (tag, j, tag, j, tag, j), 6)
-            scalar_row(6)
-            E("}", 5)
-            E("}", 4)
-        # flush: owned slices add into this lane's gradient registers; foreign pieces return their sums
-        E("if (own) {", 4)
-        for nm in vecs:
-            v = vidx[nm]
-            for k in range(KS):
-                E("if (s == %d) gr[%d] += %s;" % (k, v * KS + k, sink("%ss" % nm)), 5)
-        E("} else {  // segmented shuffle reduction over the pieces of one group, then the owner pulls the total", 4)
-        E("for (int q = 0; q < c.Q; ++q) {", 5)
-        for nm in vecs:
-            E("{ const real tq = __shfl_down_sync(pm4::FULL, %ss, 1u << q); if ((fm.z >> q) & 1) %ss += tq; }" % (nm, nm), 6)
-        E("}", 5)
-        for nm in vecs:
-            v = vidx[nm]
-            E("{ const real tq = __shfl_sync(pm4::FULL, %ss, fm.w < 0 ? lane : fm.w); if (fm.w >= 0) gr[%d] += %s; }"
-              % (nm, v * KS, sink("tq")), 5)
-        E("}", 4)
+        for s_own in range(KS):
+            E("{  // owned slice %d: this lane's group, parameters and gradient accumulators in its registers" % s_own, 3)
+            walk_slice(str(s_own), s_own)
+            E("}", 3)
+        E("#pragma unroll 1", 3)
+        E("for (int f = 0; f < c.NF; ++f) {  // foreign pieces of the groups capped in owned slice 0", 3)
+        walk_slice("%d + f" % KS, None)
         E("}", 3)
         if pair:
             E("%s_S2 += pm4::pk_hsum(%s_S2p);" % (tag, tag), 3)

@@ -197,7 +197,9 @@ template <class M, typename real> struct OwnedWarp {  // owner-computes layout (
   }
 };
 
-template <class M, typename real, int MAXT, bool STAGED>
+// SCALED: a per-dimension step scale is attached (step_size given per element / diagonal mass matrix); without
+// it the signed step size is one uniform scalar and costs no registers
+template <class M, typename real, int MAXT, bool STAGED, bool SCALED>
 __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
   static_assert(M::T == 1, "one warp per chain");
   using L = typename std::conditional<M::OWNED, OwnedWarp<M, real>, StripedWarp<M, real, STAGED>>::type;
@@ -227,11 +229,11 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
   };
   // theta element of every register of this lane, and its step scale
   int ej[R];
-  real scl[R];
+  real scl[SCALED ? R : 1];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     ej[r] = lay.elem(r);
-    scl[r] = (a.step_scale && ej[r] >= 0) ? a.step_scale[ej[r]] : (real)1;
+    if constexpr (SCALED) scl[r] = ej[r] >= 0 ? a.step_scale[ej[r]] : (real)1;
   }
   const int tb = a.tb > 0 ? a.tb : a.t_count;
   const int n_blocks = (a.t_count + tb - 1) / tb;
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) rho_sub[r] = 0;
         const real eps_s = dir ? eps : -eps;
-        real es_r[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) es_r[r] = eps_s * scl[r];
+        const real heps_s = (real)0.5 * eps_s;
+        auto es = [&](int r) -> real { if constexpr (SCALED) return eps_s * scl[r]; else return eps_s; };
+        auto hes = [&](int r) -> real { if constexpr (SCALED) return (real)0.5 * (eps_s * scl[r]); else return heps_s; };
         real w_sub = NEG_INF, sub_lp = cur_lp, sub_energy = cur_lp, sub_ediff = 0;
         bool cont_sub = true;
         int sub_leaps = 0;
@@ -323,14 +325,14 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
           // one leapfrog step: tfp SimpleLeapfrogIntegrator with num_steps = 1
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            p[r] = p[r] + ((real)0.5 * es_r[r]) * g[r];
-            th[r] = th[r] + es_r[r] * p[r];
+            p[r] = p[r] + hes(r) * g[r];
+            th[r] = th[r] + es(r) * p[r];
           }
           cur_lp = lay.grad(th, g);
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            p[r] = p[r] + es_r[r] * g[r];
-            p[r] = p[r] - ((real)0.5 * es_r[r]) * g[r];
+            p[r] = p[r] + es(r) * g[r];
+            p[r] = p[r] - hes(r) * g[r];
           }
           sub_leaps += 1;
 
@@ -608,7 +610,7 @@ template <class M, typename real> inline int dispatch_warp_nuts(const pm4_mod_ru
   if (p.tb > 0 && p.tb < p.t_count) PM4_CUDA_OK(cudaMemsetAsync(p.progress, 0, sizeof(int32_t) * (size_t)r.C, st));
 #define PM4_WLAUNCH(MAXT, STG)                                                                                   \
   do {                                                                                                           \
-    auto k = nuts_warp_kernel<M, real, MAXT, STG>;                                                               \
+    auto k = p.step_scale ? nuts_warp_kernel<M, real, MAXT, STG, true> : nuts_warp_kernel<M, real, MAXT, STG, false>; \
     PM4_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));             \
     k<<<g.grid, g.warps * 32, g.smem, st>>>(p);                                                                  \
     return (int)cudaGetLastError();                                                                              \
