@@ -648,7 +648,18 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
     for (auto& e : ev) cudaEventCreate(&e);
     cudaEventRecord(ev[0], st);
   }
-  if (r.adapt_enabled && r.adapt_pooled) {
+  static const bool no_persistent = getenv("PM4_NO_PERSISTENT_LOCKSTEP") != nullptr;
+  if (r.adapt_enabled && r.adapt_pooled && nuts && (m->info.caps & PM4_CAP_PERSISTENT_LOCKSTEP) && r.sync && !no_persistent) {
+    // the module runs the lock-step transitions in one cooperative launch (grid barrier + pooled update in the kernel)
+    const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
+    r.t_begin = 0;
+    r.t_count = coupled;
+    r.rounds = coupled;
+    r.tb = 0;
+    MOD(f(dtype, &r, wpb, st), "nuts (lock-step rounds)");
+    r.rounds = 0;
+    t = coupled;
+  } else if (r.adapt_enabled && r.adapt_pooled) {
     const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
     for (; t < coupled; ++t) {
       r.t_begin = t;
@@ -811,8 +822,10 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   const int64_t tree_bytes = m->f_scratch(dtype, &r.A, cfg->C, cfg->warps_per_block, cfg->max_tree_depth);
   if (tree_bytes < 0) return fail(PM4_EINVAL, "kernel module cannot size its tree scratch");
   if (tree_bytes > 0 && (rc = buf.get(&r.scratch, (size_t)tree_bytes))) return rc;
-  void *queue = nullptr, *order = nullptr, *leaps = nullptr, *progress = nullptr;
-  if ((rc = buf.get(&queue, 16))) return rc;
+  void *queue = nullptr, *order = nullptr, *leaps = nullptr, *progress = nullptr, *sync = nullptr;
+  if ((rc = buf.get(&queue, sizeof(int32_t) * (size_t)(T + 4)))) return rc;  // one counter per lock-step round
+  if ((rc = buf.get(&sync, 16))) return rc;
+  r.sync = (int32_t*)sync;
   if ((rc = buf.get(&order, C * sizeof(int32_t)))) return rc;
   if ((rc = buf.get(&leaps, C * sizeof(int32_t)))) return rc;
   if ((rc = buf.get(&progress, C * sizeof(int32_t)))) return rc;

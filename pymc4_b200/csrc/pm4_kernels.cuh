@@ -265,8 +265,9 @@ template <typename real> struct RunParams {
   ModelArgs<real> A;
   int C, t_begin, t_count, B, S, max_depth, num_leapfrog, chain_offset;
   int adapt_enabled, adapt_pooled, num_adapt, adapt_kind, random_walk;
-  int team_reals, n_slots, n_fast, tb;
+  int team_reals, n_slots, n_fast, tb, rounds;
   int32_t* progress;
+  int32_t* sync;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay, adapt_rate, rw_scale;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -304,7 +305,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
   p.adapt_kind = r.adapt_kind; p.random_walk = r.random_walk;
   p.adapt_rate = (real)r.adapt_rate; p.rw_scale = (real)r.rw_scale;
-  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress;
+  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress; p.rounds = r.rounds; p.sync = r.sync;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -362,10 +363,9 @@ struct CommSlot {
 // memory, and adds them in rank order, so all ranks compute the bit-identical epsilon.  A peer that
 // does not show up within ~30 s raises the device error word (once per run) instead of hanging the GPU.
 template <typename real>
-__global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int t) {
-  __shared__ double part[32];
-  double s = 0;  // fixed-order, deterministic reduction
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) s += (double)a.accept[c];
+__device__ __forceinline__ void pooled_update(const RunParams<real>& a, int t, double* part /* shared, 32 doubles */) {
+  double s = 0;  // fixed-order, deterministic reduction (the chains' accept words may come from other SMs: L2 loads)
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) s += (double)__ldcg(a.accept + c);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -408,11 +408,18 @@ __global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int 
     }
     if (threadIdx.x == 0) {
       DualAvg<real> d;
-      d.load(a.da);
+      d.eps = __ldcg(a.da); d.error_sum = __ldcg(a.da + 1); d.log_avg = __ldcg(a.da + 2); d.log_shrink_target = __ldcg(a.da + 3);
       d.update(a, t, (real)(total / count));
       d.store(a.da);
     }
   }
+  __syncthreads();
+}
+
+template <typename real>
+__global__ void __launch_bounds__(1024) da_pooled_kernel(RunParams<real> a, int t) {
+  __shared__ double part[32];
+  pooled_update<real>(a, t, part);
 }
 
 template <typename real> __global__ void export_eps_kernel(RunParams<real> a, real* __restrict__ out) {
@@ -1085,6 +1092,7 @@ extern "C" int pm4m_info(pm4_mod_info_t* out) {
   out->n_terms = PM4_MODEL::N_TERMS;
   out->n_ops = PM4_MODEL::N_OPS;
   out->struct_hash = PM4_MODEL::HASH;
+  out->caps = pm4::use_warp_path<PM4_MODEL>() ? PM4_CAP_PERSISTENT_LOCKSTEP : 0;
   return 0;
 }
 

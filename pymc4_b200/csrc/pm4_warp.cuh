@@ -199,7 +199,8 @@ template <class M, typename real> struct OwnedWarp {  // owner-computes layout (
 
 // SCALED: a per-dimension step scale is attached (step_size given per element / diagonal mass matrix); without
 // it the signed step size is one uniform scalar and costs no registers
-template <class M, typename real, int MAXT, bool STAGED, bool SCALED>
+// ROUNDS: lock-step instantiation (a.rounds transitions, grid barrier + pooled update after each)
+template <class M, typename real, int MAXT, bool STAGED, bool SCALED, bool ROUNDS>
 __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
   static_assert(M::T == 1, "one warp per chain");
   using L = typename std::conditional<M::OWNED, OwnedWarp<M, real>, StripedWarp<M, real, STAGED>>::type;
@@ -235,19 +236,28 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
     ej[r] = lay.elem(r);
     if constexpr (SCALED) scl[r] = ej[r] >= 0 ? a.step_scale[ej[r]] : (real)1;
   }
-  const int tb = a.tb > 0 ? a.tb : a.t_count;
-  const int n_blocks = (a.t_count + tb - 1) / tb;
+  // lock-step rounds (pooled step size still adapting): one transition per round, every chain, then a grid
+  // barrier whose last arrival runs the pooled dual-averaging update -- all in this one (cooperative) launch
+  const int rounds = ROUNDS ? a.rounds : 1;
+  __shared__ double s_part[ROUNDS ? 32 : 1];
+  __shared__ int s_last;
+  for (int rd = 0; rd < rounds; ++rd) {
+  const int rt_begin = ROUNDS ? a.t_begin + rd : a.t_begin;
+  const int rt_count = ROUNDS ? 1 : a.t_count;
+  int32_t* const queue = ROUNDS ? a.queue + rd : a.queue;
+  const int tb = (a.tb > 0 && !ROUNDS) ? a.tb : rt_count;
+  const int n_blocks = (rt_count + tb - 1) / tb;
   const int n_items = n_blocks * a.C;
 
   for (;;) {
     int qi = 0;
-    if (lane == 0) qi = atomicAdd(a.queue, 1);
+    if (lane == 0) qi = atomicAdd(queue, 1);
     qi = __shfl_sync(FULL, qi, 0);
     if (qi >= n_items) break;
     const int blk = qi / a.C, slot = qi - blk * a.C;
     const int chain = a.order ? a.order[slot] : slot;
-    const int t0 = a.t_begin + blk * tb;
-    const int t1 = t0 + tb < a.t_begin + a.t_count ? t0 + tb : a.t_begin + a.t_count;
+    const int t0 = rt_begin + blk * tb;
+    const int t1 = t0 + tb < rt_begin + rt_count ? t0 + tb : rt_begin + rt_count;
     if (n_blocks > 1 && blk > 0) {  // the previous block of this chain is running on another warp (or done)
       if (lane == 0) {
         while (ld_acquire(a.progress + chain) < blk) __nanosleep(100);
@@ -496,6 +506,22 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
       if (lane == 0) st_release(a.progress + chain, blk + 1);
     }
   }
+  if constexpr (ROUNDS) {
+    __threadfence();  // this CTA's accept words and chain rows are visible before it arrives
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.sync, 1) == (int)gridDim.x * (rd + 1) - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (a.adapt_enabled && a.adapt_pooled) pooled_update<real>(a, rt_begin, s_part);
+      __threadfence();
+      if (threadIdx.x == 0) st_release(a.sync + 1, rd + 1);
+    } else if (threadIdx.x == 0) {
+      while (ld_acquire(a.sync + 1) < rd + 1) __nanosleep(64);
+    }
+    __syncthreads();
+  }
+  }
 }
 
 // parity kernel (a) and bootstrap on the owner-computes layout: one warp per chain
@@ -606,12 +632,23 @@ template <class M, typename real> inline int dispatch_warp_nuts(const pm4_mod_ru
   p.team_reals = g.team_reals;
   p.n_fast = g.n_lvl;
   p.n_slots = g.n_gslots;
-  PM4_CUDA_OK(cudaMemsetAsync(p.queue, 0, sizeof(int32_t), st));
-  if (p.tb > 0 && p.tb < p.t_count) PM4_CUDA_OK(cudaMemsetAsync(p.progress, 0, sizeof(int32_t) * (size_t)r.C, st));
+  PM4_CUDA_OK(cudaMemsetAsync(p.queue, 0, sizeof(int32_t) * (size_t)(p.rounds > 0 ? p.rounds : 1), st));
+  if (p.rounds > 0) {
+    if (!p.sync) return (int)cudaErrorInvalidValue;
+    PM4_CUDA_OK(cudaMemsetAsync(p.sync, 0, 2 * sizeof(int32_t), st));
+  }
+  if (p.rounds == 0 && p.tb > 0 && p.tb < p.t_count) PM4_CUDA_OK(cudaMemsetAsync(p.progress, 0, sizeof(int32_t) * (size_t)r.C, st));
 #define PM4_WLAUNCH(MAXT, STG)                                                                                   \
   do {                                                                                                           \
-    auto k = p.step_scale ? nuts_warp_kernel<M, real, MAXT, STG, true> : nuts_warp_kernel<M, real, MAXT, STG, false>; \
+    auto k = p.rounds > 0 ? (p.step_scale ? nuts_warp_kernel<M, real, MAXT, STG, true, true>                      \
+                                          : nuts_warp_kernel<M, real, MAXT, STG, false, true>)                    \
+                          : (p.step_scale ? nuts_warp_kernel<M, real, MAXT, STG, true, false>                     \
+                                          : nuts_warp_kernel<M, real, MAXT, STG, false, false>);                  \
     PM4_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));             \
+    if (p.rounds > 0) { /* the blocks wait on one another: co-residency must be guaranteed */                    \
+      void* args[] = {(void*)&p};                                                                                \
+      return (int)cudaLaunchCooperativeKernel((const void*)k, dim3(g.grid), dim3(g.warps * 32), args, g.smem, st); \
+    }                                                                                                            \
     k<<<g.grid, g.warps * 32, g.smem, st>>>(p);                                                                  \
     return (int)cudaGetLastError();                                                                              \
   } while (0)
