@@ -193,11 +193,17 @@ class DeviceModel:
         """New constant pools for the same structure (new observed values)."""
         if ir.struct_hash != self.ir.struct_hash:
             raise ValueError("set_data needs an IR with the same structure")
-        self.packed = PackedIR(ir)
-        self.ir = ir
-        c = self.packed.c
+        if ir.layout_key() != self.ir.layout_key():
+            raise ValueError("set_data needs an IR with the same pool sizes, element counts and blob offsets "
+                             "(build a new DeviceModel for data of a different shape)")
+        packed = PackedIR(ir)
+        c = packed.c
+        # plans first (the library validates them before it uploads anything), then the data pools; the Python
+        # side switches to the new IR only when both calls went through
+        self._check(self.lib.pm4_model_set_plans(self.handle, packed.byref()))
         self._check(self.lib.pm4_model_set_data(self.handle, c.dataf, c.n_dataf, c.datai, c.n_datai))
-        self._check(self.lib.pm4_model_set_plans(self.handle, self.packed.byref()))
+        self.packed = packed
+        self.ir = ir
 
     def logp_grad(self, theta, dtype=np.float32, want_grad: bool = True):
         """theta [C, D] (host or device) -> (lp [C], grad [C, D]) device tensors."""

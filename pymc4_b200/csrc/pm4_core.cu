@@ -146,6 +146,24 @@ static int check_comm(pm4_model* m, cudaStream_t st);
 static int upload_plans(pm4_model* m, const pm4_ir_t* ir) {
   const int64_t nf = ir->n_planf, ni = ir->n_plani;
   if (nf % 4 || ni % 4) return fail(PM4_EINVAL, "plan pools must be padded to multiples of 4 elements");
+  // validate everything before the first byte is copied: a rejected IR leaves the model untouched
+  for (int k = 0; k < ir->n_plans; ++k) {
+    const pm4_plan_t& pl = ir->plans[k];
+    if (pl.meta < 0 || pl.meta >= ni || pl.recs < 0 || pl.recs > nf) return fail(PM4_EINVAL, "plan %d points outside the plan pools", k);
+  }
+  if (ir->team_warps != m->info.T) return fail(PM4_EINVAL, "IR is laid out for teams of %d warps, the kernel module for %d", ir->team_warps, m->info.T);
+  if (ir->elem_off < 0 || ir->elem_off + m->info.DP > ni || ir->spart_off < 0 || ir->spart_off >= ni ||
+      ir->phdr_off < 0 || ir->phdr_off + 4 * ir->n_plans > ni || ir->part_reals <= 0)
+    return fail(PM4_EINVAL, "part-array tables point outside the plan metadata pool");
+  {
+    const int64_t oh = ir->phdr_off + 4 * (ir->n_plans > 0 ? ir->n_plans : 1);
+    if (oh + 8 <= ni && ir->plani[oh] == 1) {
+      const int32_t* h = ir->plani + oh;
+      if (h[1] < 0 || h[2] < 0 || h[1] + (int64_t)h[2] > ni || h[3] < 0 || h[4] < 0 || h[3] + (int64_t)h[4] > nf || (h[2] % 4) || (h[4] % 4) ||
+          (h[1] % 4) || (h[3] % 4))
+        return fail(PM4_EINVAL, "owned plan sections point outside the plan pools");
+    }
+  }
   std::vector<float> f32((size_t)nf);
   for (int64_t k = 0; k < nf; ++k) f32[(size_t)k] = (float)ir->planf[k];
   if (nf) {
@@ -357,8 +375,12 @@ extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int
     return rc;
   }
   f_info(&m->info);
+  int64_t ir_ll_row = 0;  // the module bakes the pointwise log-likelihood row layout in: it must be the IR's
+  for (int k = 0; k < ir->n_terms; ++k)
+    if (ir->terms[k].observed) ir_ll_row += ir->terms[k].n;
   if (m->info.abi != PM4_MODULE_ABI || m->info.struct_hash != ir->struct_hash || m->info.D != ir->D ||
-      m->info.n_terms != ir->n_terms || m->info.n_ops != ir->n_ops || m->info.det_row != ir->det_row) {
+      m->info.n_terms != ir->n_terms || m->info.n_ops != ir->n_ops || m->info.det_row != ir->det_row ||
+      (int64_t)m->info.ll_row != ir_ll_row) {
     int rc = fail(PM4_ENOMOD, "kernel module %s was built for another model structure (hash %016llx, IR %016llx)",
                   module_path, (unsigned long long)m->info.struct_hash, (unsigned long long)ir->struct_hash);
     pm4_model_destroy(m);

@@ -36,9 +36,14 @@ __device__ __forceinline__ double m_exp(double v) { return exp(v); }
 __device__ __forceinline__ float m_log(float v) { return mufu_lg2(v) * 0.6931471805599453f; }
 __device__ __forceinline__ double m_log(double v) { return log(v); }
 __device__ __forceinline__ float m_log1p(float v) {
-  // log1p only matters near 0, where the series is exact enough and cheaper than the MUFU path's cancellation
+  // lg2.approx(1 + v) has an ABSOLUTE error of ~1e-7, i.e. a relative error of 1e-7 / |log1p v|: compensate the
+  // rounding of 1 + v (the classic log(u) * v / (u - 1) form) so the relative error stays ~1e-6 for every v; the
+  // series takes over below 2^-12, where u - 1 loses its last bits
   const float a = fabsf(v);
-  return a < 1e-3f ? v * (1.0f - 0.5f * v + 0.33333334f * v * v) : m_log(1.0f + v);
+  if (a < 2.44140625e-4f) return v * (1.0f - 0.5f * v + 0.33333334f * v * v);
+  const float u = 1.0f + v;
+  const float d = u - 1.0f;
+  return a < 0.5f ? m_log(u) * (v * mufu_rcp(d)) : m_log(u);
 }
 __device__ __forceinline__ double m_log1p(double v) { return log1p(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }
@@ -62,8 +67,12 @@ template <typename real> __device__ __forceinline__ real m_softplus(real v) {
   return v > 0 ? v + m_log1p(m_exp(-v)) : m_log1p(m_exp(v));
 }
 template <typename real> __device__ __forceinline__ real m_digamma(real x) {
+  // d/dx lgamma on user expressions: only positive finite arguments are meaningful here; anything else is a bad
+  // proposal and gets NaN (a divergent transition) instead of a recurrence that never terminates
+  if (!(x > 0) || x == m_inf<real>()) return (real)NAN;
   real r = 0;
-  while (x < 6) { r -= m_rcp(x); x += 1; }
+#pragma unroll 1
+  for (int k = 0; k < 6 && x < 6; ++k) { r -= m_rcp(x); x += 1; }
   const real f = m_rcp(x * x);
   return r + m_log(x) - (real)0.5 / x -
          f * ((real)(1.0 / 12) - f * ((real)(1.0 / 120) - f * ((real)(1.0 / 252) - f * (real)(1.0 / 240))));

@@ -244,6 +244,9 @@ class ModelIR:
 
         for t in self.terms:
             h.append(struct.pack("<iii?", t.kind, t.value_reg, len(t.ops), t.observed))
+            if t.observed:
+                # the generated pointwise log-likelihood / predictive kernels bake the row layout in (LL_ROW, ll_offset)
+                h.append(struct.pack("<ii", t.n, t.ll_offset))
             if t.glm is not None:
                 h.append(struct.pack("<qqii", t.glm.x_blob, t.glm.y_blob, t.glm.base, t.glm.P))
             if t.gp is not None:
@@ -259,6 +262,13 @@ class ModelIR:
         if self.owned is not None:
             h.append(self.owned.key())
         return b"".join(h)
+
+    def layout_key(self) -> tuple:
+        """Everything a device model keeps besides the data VALUES: pool sizes, element counts, blob offsets.
+        Two IRs of one structure whose layout keys agree can share a DeviceModel through ``set_data``."""
+        return (self.struct_hash, self.dataf.shape, self.datai.shape, np.asarray(self.planf).shape,
+                np.asarray(self.plani).shape, tuple(t.n for t in self.terms), tuple(d.n for d in self.dets),
+                tuple(o.blob for t in self.terms for o in t.ops), tuple(o.blob for d in self.dets for o in d.ops))
 
     @property
     def struct_hash(self) -> int:

@@ -15,6 +15,8 @@ import logging
 import os
 from typing import Any, Dict, List, Optional
 
+from collections import OrderedDict
+
 import numpy as np
 
 from .. import flow
@@ -427,7 +429,15 @@ class RandomWalkM(_BaseSampler):
 # ---------------------------------------------------------------------------
 # log-density builder (reference :729-829)
 # ---------------------------------------------------------------------------
-_device_models: Dict[Any, Any] = {}
+_device_models: "OrderedDict[Any, Any]" = OrderedDict()
+MAX_DEVICE_MODELS = 4  # every entry holds device copies of the data pools (and GLM / GP workspaces)
+
+
+def clear_device_models():
+    """Release the device copies (data pools, workspaces) of every cached model."""
+    while _device_models:
+        _, dm = _device_models.popitem(last=False)
+        dm.close()
 
 
 def _get_device_model(ir: irmod.ModelIR, dtype, device):
@@ -437,16 +447,26 @@ def _get_device_model(ir: irmod.ModelIR, dtype, device):
     dev = 0 if device is None else int(device)
     key = (ir.struct_hash, dev, f64)
     dm = _device_models.get(key)
-    if dm is None:
-        dm = _device_models[key] = DeviceModel(ir, device=dev, f64=f64)
-    else:
-        same = (dm.ir.dataf.shape == ir.dataf.shape and dm.ir.datai.shape == ir.datai.shape
-                and np.array_equal(dm.ir.dataf, ir.dataf) and np.array_equal(dm.ir.datai, ir.datai))
-        if not same:
-            if dm.ir.dataf.shape == ir.dataf.shape and dm.ir.datai.shape == ir.datai.shape:
+    if dm is not None:
+        if dm.ir.layout_key() != ir.layout_key():
+            # same model structure, data of another shape (or other blob offsets / plan sizes): a fresh device model
+            del _device_models[key]
+            dm.close()
+            dm = None
+        elif not (np.array_equal(dm.ir.dataf, ir.dataf) and np.array_equal(dm.ir.datai, ir.datai)):
+            try:
                 dm.set_data(ir)
-            else:
-                dm = _device_models[key] = DeviceModel(ir, device=dev, f64=f64)
+            except Exception:
+                del _device_models[key]
+                dm.close()
+                dm = None
+    if dm is None:
+        dm = DeviceModel(ir, device=dev, f64=f64)
+    _device_models[key] = dm
+    _device_models.move_to_end(key)
+    while len(_device_models) > MAX_DEVICE_MODELS:  # least recently used first
+        _, old = _device_models.popitem(last=False)
+        old.close()
     return dm
 
 

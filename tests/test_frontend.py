@@ -387,3 +387,46 @@ def test_dense_predictor_spellings_and_the_intercept_hint():
 
     ir2, _, _ = lower_model(intercept_as_a_column())
     assert ir2.glm_terms[0].glm.P == 5
+
+
+def test_struct_hash_covers_the_observed_row_layout():
+    """Two data sets of different length for one model must not share a kernel module: the generated pointwise
+    log-likelihood / predictive kernels bake LL_ROW and every observed term's row offset in."""
+    import pymc4_b200 as pm
+    from pymc4_b200 import codegen
+    from pymc4_b200.ir import lower_model
+
+    def make(n):
+        y = np.linspace(-1.0, 1.0, n)
+
+        @pm.model
+        def m():
+            mu = yield pm.Normal("mu", 0.0, 1.0)
+            s = yield pm.HalfNormal("s", 1.0)
+            yield pm.Normal("y", mu, s, observed=y)
+
+        return lower_model(m())[0]
+
+    a, b, a2 = make(100), make(200), make(100)
+    assert a.struct_hash != b.struct_hash
+    assert codegen.module_path(a) != codegen.module_path(b)
+    assert a.struct_hash == a2.struct_hash and a.layout_key() == a2.layout_key()
+    assert "LL_ROW = 100" in codegen.generate_source(a) and "LL_ROW = 200" in codegen.generate_source(b)
+
+
+def test_layout_key_separates_data_of_another_shape_or_plan():
+    """Same structure, same shapes, other gather indices: the plan pools may differ in size, and then the cached device
+    model must be rebuilt, not patched."""
+    from pymc4_b200.ir import lower_model
+
+    rng = np.random.default_rng(0)
+    n, g = 400, 12
+    x = rng.standard_normal(n)
+    y = rng.standard_normal(n)
+    idx_a = np.sort(rng.integers(0, g, n)).astype(np.int32)
+    idx_b = np.sort(np.minimum(rng.geometric(0.4, n) - 1, g - 1)).astype(np.int32)  # very different group sizes
+    ir_a = lower_model(M.hierarchical_model(idx_a, x, y, g))[0]
+    ir_b = lower_model(M.hierarchical_model(idx_b, x, y, g))[0]
+    assert ir_a.struct_hash == ir_b.struct_hash
+    same_pools = np.asarray(ir_a.plani).shape == np.asarray(ir_b.plani).shape and np.asarray(ir_a.planf).shape == np.asarray(ir_b.planf).shape
+    assert (ir_a.layout_key() == ir_b.layout_key()) == same_pools

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 
 import pymc4_b200 as pm
+from oracle import pm4_oracle
+from pymc4_b200 import ir as I
 from tests import models as M
 
 pytestmark = pytest.mark.gpu
@@ -236,3 +238,42 @@ def test_sample_gp_regression_recovers_hyperparameters():
     assert 0.3 < ppc.var() < 4.0 and abs(ppc.mean()) < 0.3
     prior = pm.sample_prior_predictive(M.gp_model(X, y), sample_shape=50, seed=2).prior_predictive
     assert prior["gp_regression/y"].shape == (1, 50, 128) and prior["gp_regression/ls"].shape == (1, 50)
+
+
+def test_refit_on_data_of_another_length_and_on_other_indices():
+    """One model fitted on data sets of different length (a cross-validation fold), then on same-shaped data with
+    other group indices: every fit gets its own row layout / plans -- no stale module, no half-updated device model
+    (struct hash without the row layout; set_data committing before validation)."""
+    from scipy import stats
+
+    def fit(n, seed):
+        y = np.random.default_rng(seed).normal(0.5, 1.0, n)
+
+        @pm.model
+        def m():
+            mu = yield pm.Normal("mu", 0.0, 1.0)
+            s = yield pm.HalfNormal("s", 1.0)
+            yield pm.Normal("y", mu, s, observed=y)
+
+        tr = pm.sample(m(), step_size=0.2, num_chains=4, num_samples=30, burn_in=30, seed=3, include_log_likelihood=True)
+        ll = tr.log_likelihood["m/y"]
+        assert ll.shape == (4, 30, n)
+        mu, s = tr.posterior["m/mu"][..., None], tr.posterior["m/s"][..., None]
+        np.testing.assert_allclose(ll, stats.norm(mu, s).logpdf(y), rtol=2e-4, atol=2e-4)
+
+    fit(100, 0)
+    fit(200, 1)
+    fit(100, 2)  # same layout as the first fit, new values: the cached device model takes them through set_data
+
+    rng = np.random.default_rng(0)
+    n, g = 400, 12
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    for idx in (np.sort(rng.integers(0, g, n)), np.sort(np.minimum(rng.geometric(0.4, n) - 1, g - 1))):
+        model = M.hierarchical_model(idx.astype(np.int32), x, y, g)
+        ir, _, _ = I.lower_model(model)
+        dm = pm.mcmc.samplers._get_device_model(ir, np.float32, 0)
+        th = rng.normal(0, 0.3, (16, ir.D))
+        lp, gr = dm.logp_grad(th.astype(np.float32), dtype=np.float32)
+        lp_ref, g_ref = pm4_oracle.Oracle(ir).logp_grad(th, dtype=np.float64)
+        np.testing.assert_allclose(lp.cpu().numpy(), lp_ref, rtol=2e-5)
+        assert np.max(np.abs(gr.cpu().numpy() - g_ref)) / np.max(np.abs(g_ref)) < 2e-5
