@@ -69,6 +69,12 @@ def parse_args():
     ap.add_argument("--gp-n", type=int, default=4096)
     ap.add_argument("--logit-n", type=int, default=1_000_000)
     ap.add_argument("--leapfrogs", type=int, default=3, help="HMC leapfrog steps (logit workload; reference default 3)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="radon919 only: do not append the bounded runs of the other BASELINE configurations "
+                         "(logit, gp, radon100k) as the line's \"secondary\" object")
+    ap.add_argument("--shard-rank", type=int, default=-1,
+                    help="(secondary runs) this single-GPU process is shard R of a box-wide run: chains get the "
+                         "global offsets R * chains")
     return ap.parse_args()
 
 
@@ -359,6 +365,82 @@ def onchip_peaks(torch):
 
 
 # ------------------------------------------------------------------------------------------
+# the other BASELINE configurations, bounded, as the default line's "secondary" object
+# ------------------------------------------------------------------------------------------
+SECONDARY = {
+    # configs[2]: hierarchical logistic regression, N = 1M x P = 100, 1024 chains per GPU (HMC, 3 leapfrogs)
+    "logit": ["--workload", "logit", "--steps", "2", "--warmup", "1"],
+    # configs[3]: marginal GP regression, n = 4096, 256 chains per GPU (HMC, 3 leapfrogs); one batched gradient
+    # evaluation of 256 chains is 1.8e13 float64 flops, so the run is 1 + 1 transitions
+    "gp": ["--workload", "gp", "--burn-in", "1", "--draws", "1", "--steps", "1", "--warmup", "1"],
+    # configs[4]: radon-shaped, 100k observations / 5k groups, 8192 chains per GPU (65 536 chains at 8 GPUs)
+    "radon100k": ["--workload", "radon100k", "--chains", "8192", "--burn-in", "20", "--draws", "10", "--steps", "1",
+                  "--warmup", "1"],
+}
+
+
+def run_secondaries(args, rank, local_rank):
+    """Every rank runs the bounded secondary workloads as single-GPU child processes on ITS GPU (shard `rank` of the
+    box-wide run: global chain offsets, no data-path collective; the scalar step size is pooled over the rank's
+    chains).  Returns {name: parsed JSON line or {"error": ...}}."""
+    env = dict(os.environ)
+    for k in list(env):
+        if k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "MASTER_ADDR",
+                 "MASTER_PORT") or k.startswith("TORCHELASTIC"):
+            env.pop(k)
+    visible = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    env["CUDA_VISIBLE_DEVICES"] = visible[local_rank] if local_rank < len(visible) else str(local_rank)
+    env.pop("PM4_PHASE_TIMES", None)
+    out = {}
+    for name, argv in SECONDARY.items():
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--no-cpu-baseline", "--no-secondary",
+               "--shard-rank", str(rank), "--seed", str(args.seed)] + argv
+        t0 = time.perf_counter()
+        try:
+            proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            lines = [ln for ln in proc.stdout.strip().splitlines() if ln.startswith("{")]
+            if proc.returncode != 0 or not lines:
+                out[name] = {"error": "exit %d: %s" % (proc.returncode, proc.stderr.strip()[-300:])}
+            else:
+                out[name] = json.loads(lines[-1])
+                out[name]["child_wall_s"] = time.perf_counter() - t0
+        except subprocess.TimeoutExpired:
+            out[name] = {"error": "timed out after 600 s"}
+    return out
+
+
+def merge_secondaries(per_rank):
+    """Whole-job figures of the secondary workloads: units of all ranks over the slowest rank's device time."""
+    merged = {}
+    for name in SECONDARY:
+        rows = [r.get(name) for r in per_rank if r]
+        bad = [r for r in rows if not r or "error" in r]
+        if bad:
+            merged[name] = {"error": (bad[0] or {}).get("error", "missing")}
+            continue
+        secs = [r["ms_per_step"] * r["steps"] / 1e3 for r in rows]
+        units = sum(r["value"] * t for r, t in zip(rows, secs))
+        e_secs = [r["e2e"]["ms_per_step"] / 1e3 for r in rows if r.get("e2e")]
+        e_units = sum(r["e2e"]["value"] * t for r, t in zip(rows, e_secs)) if e_secs else None
+        first = rows[0]
+        merged[name] = {
+            "metric": first["metric"], "value": units / max(secs), "unit": first["unit"], "n_gpus": len(rows),
+            "ms_per_step": 1e3 * max(secs) / first["steps"], "steps": first["steps"], "warmup": first["warmup"],
+            "dtype": first["dtype"], "scaling": "weak", "config": first["config"],
+            "parallelism": "one single-GPU process per rank on its own GPU (chains sharded by global offset, every GPU "
+                           "holds the data, no data-path collective; scalar step size pooled over the rank's chains)",
+            "e2e": ({"value": e_units / max(e_secs), "unit": first["unit"],
+                     "h2d_bytes_per_step": first["e2e"]["h2d_bytes_per_step"],
+                     "d2h_bytes_per_step": first["e2e"]["d2h_bytes_per_step"], "api": first["e2e"].get("api")}
+                    if e_secs else None),
+            "roofline": first["roofline"], "gpu_launches": first.get("gpu_launches"), "clocks": first.get("clocks"),
+            "ess_per_sec": first.get("ess_per_sec"), "diagnostics": first.get("diagnostics"),
+            "per_rank_values": [r["value"] for r in rows],
+        }
+    return merged
+
+
+# ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_b200(args):
@@ -386,6 +468,7 @@ def run_b200(args):
     model, ir = build_model()
     dm = _cabi.DeviceModel(ir, device=local_rank)
     C, B, S = args.chains, args.burn_in, args.draws
+    shard = args.shard_rank if (world == 1 and args.shard_rank >= 0) else rank  # global chain offsets of this process
     comm = None
     if world > 1 and args.eps_mode == "pooled":
         # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
@@ -402,10 +485,10 @@ def run_b200(args):
             from pymc4_b200._cstructs import make_hmc_cfg
 
             return make_hmc_cfg(C, S, B, step_size=args.step_size, num_leapfrog_steps=args.leapfrogs,
-                                seed=args.seed + step, adapt=adapt, chain_offset=rank * C)
+                                seed=args.seed + step, adapt=adapt, chain_offset=shard * C)
         return make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + step, adapt=adapt,
                              max_tree_depth=args.max_tree_depth,
-                             warps_per_block=args.warps_per_block, chain_offset=rank * C)
+                             warps_per_block=args.warps_per_block, chain_offset=shard * C)
 
     def run_step(cfg):
         if not is_logit:
@@ -492,9 +575,9 @@ def run_b200(args):
             from pymc4_b200.mcmc.samplers import HMC
 
             nuts = HMC(model, step_size=step_arr, num_leapfrog_steps=args.leapfrogs, num_adaptation_steps=B,
-                       device=local_rank, chain_offset=rank * C, **extra)
+                       device=local_rank, chain_offset=shard * C, **extra)
         else:
-            nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=rank * C,
+            nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=shard * C,
                         **extra)
         e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
         n_e2e = max(1, min(args.steps, 2))
@@ -525,6 +608,15 @@ def run_b200(args):
                       "on the host (trace copied through pinned memory)"
                       % ("HMC" if is_logit else "NUTS", "[C,1]" if args.eps_mode == "per-chain" else "%g" % args.step_size)}
 
+    secondary = None
+    if args.workload == "radon919" and not args.no_secondary:
+        mine = run_secondaries(args, rank, local_rank)
+        gathered = [mine]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+        secondary = merge_secondaries(gathered)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,8 +634,12 @@ def run_b200(args):
     roofline = {
         "bound": "smem", "achieved": ach_smem_tbs * 1e3, "peak": (smem_peak * 1e3) if smem_peak else None, "unit": "GB/s",
         "frac": (ach_smem_tbs / smem_peak) if smem_peak else None, "traffic": None,
-        "kernel": "pm4::nuts_kernel (persistent blocks, 3 launches per step: transitions [0,20), [20,B], (B,B+S); "
-                  "bootstrap, chain-ordering and export kernels are <0.1% of the step)",
+        "kernel": ("pm4::nuts_warp_kernel (one warp per chain, owner-computes layout; per step: ONE cooperative launch for the "
+                   "burn_in + 1 lock-step transitions while the pooled step size adapts -- grid barrier + dual-averaging "
+                   "update inside the kernel -- then one persistent launch for the draws; bootstrap and export kernels are "
+                   "<0.1% of the step)") if WORKLOAD == "radon919" and args.eps_mode == "pooled" else
+                  "pm4::nuts_warp_kernel / pm4::nuts_kernel (persistent blocks; bootstrap, chain-ordering and export "
+                  "kernels are <0.1% of the step)",
         "algorithmic_bytes_per_unit": ONCHIP_BYTES_PER_UNIT,
         "peak_source": "LDS.128 microbenchmark run by this bench on this GPU (csrc/pm4_peaks.cu); "
                        "MEASURED_PEAKS.json has no shared-memory entry",
@@ -582,7 +678,7 @@ def run_b200(args):
         roofline = {
             "bound": "tensor", "achieved": ach_tflops, "peak": f64_peak, "unit": "TFLOP/s",
             "frac": ach_tflops / f64_peak, "traffic": None,
-            "kernel": "gp_nt_kernel<CHOL|ZT|DOT> (64 x 64 float64 tiles, DFMA): blocked Cholesky, inverse factor and the "
+            "kernel": "gp_nt_kernel<CHOL|ZT|DOT> (64 x 64 float64 tiles on the FP64 tensor cores, DMMA m8n8k4): blocked Cholesky, inverse factor and the "
                       "contraction with dK; time base = the whole step",
             "algorithmic_flops_per_unit": FLOPS_PER_UNIT,
             "peak_source": "cuBLAS float64 matmul 4096^3 timed live by this bench (MEASURED_PEAKS.json has no float64 entry)",
@@ -632,7 +728,9 @@ def run_b200(args):
         "wall_s_timed_region": wall,
         "steps_detail": detail,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if secondary is not None:
+        line["secondary"] = secondary
+    if not args.no_cpu_baseline:  # rank 0's host cores, a bounded sample of the per-GPU workload (also on N > 1 lines)
         line["cpu_baseline"] = cpu_baseline(ir, args)
     print(json.dumps(line))
     if world > 1:

@@ -206,6 +206,70 @@ def test_nuts_posterior_matches_oracle(oracle_mod):
     assert out["diverging"].float().mean().item() < 0.02
 
 
+def test_radon_pooled_step_size_matches_the_oracle_regime(oracle_mod):
+    """(c) on the HEADLINE configuration: radon-919, the reference-default scalar step size (one epsilon adapted from
+    the mean acceptance of all chains), GPU FP32 (2048 chains) against the oracle's FP64 NUTS (128 chains).
+
+    The reference-default policy does NOT converge on this model (one shared epsilon sticks ~1 % of the chains in the
+    sigma_beta funnel: split R-hat ~1.2-1.3, ~9 % divergent transitions -- the oracle says the same, and the
+    reference's own notebook works around it with per-dimension step sizes, radon_hierarchical.ipynb:123-146), so this
+    test compares the REGIME, chain means as the independent unit: posterior means and second moments of the seven
+    monitored columns within 3 standard errors, divergent fraction, mean acceptance, leapfrogs per draw, adapted step
+    size and the fraction of chains that diverge on (almost) every transition."""
+    ir, _, _ = lower_model(M.radon_model(real=False))
+    D = ir.D
+    B, S = 300, 300
+    Cg, Co = 2048, 128
+    adapt = make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B)
+    out = _dm(ir).nuts(make_nuts_cfg(Cg, S, B, step_size=0.1, seed=2026, adapt=adapt), np.zeros((Cg, D), np.float32),
+                       dtype=np.float32)
+    ref = oracle_mod.Oracle(ir).nuts(make_nuts_cfg(Co, S, B, step_size=0.1, seed=77, adapt=adapt), np.zeros(D),
+                                     dtype=np.float64)
+    cols = [0, 1, 2, 87, 172, 173, 174]  # mu_a, mu_b, alpha[0], beta[0], log sigma_a, log sigma_b, log eps
+    xs = out["states"].cpu().numpy().astype(np.float64)[:, :, cols]
+    xr = ref["states"][:, :, cols]
+    assert np.all(np.isfinite(xs))
+    for fn in (lambda v: v, lambda v: v * v):
+        mg, mo = fn(xs).mean(axis=0), fn(xr).mean(axis=0)  # per-chain means [C, 7]
+        se = np.sqrt(mg.var(axis=0, ddof=1) / Cg + mo.var(axis=0, ddof=1) / Co)
+        z = np.abs(mg.mean(axis=0) - mo.mean(axis=0)) / se
+        assert np.all(z < 3.0), z
+    dg, do = out["diverging"].cpu().numpy().astype(np.float64), ref["diverging"].astype(np.float64)
+    # per-chain divergence rates are the independent unit (a stuck chain diverges on every transition)
+    se_div = np.sqrt(dg.mean(axis=0).var(ddof=1) / Cg + do.mean(axis=0).var(ddof=1) / Co)
+    assert abs(dg.mean() - do.mean()) < 3.0 * se_div + 0.01, (dg.mean(), do.mean())
+    stuck_g, stuck_o = (dg.mean(axis=0) > 0.9).mean(), (do.mean(axis=0) > 0.9).mean()
+    assert abs(stuck_g - stuck_o) < 3.0 * np.sqrt(max(stuck_o, 1.0 / Co) / Co) + 0.01, (stuck_g, stuck_o)
+    ag, ao = np.exp(out["log_accept"].cpu().numpy()).mean(), np.exp(ref["log_accept"]).mean()
+    assert abs(ag - ao) < 0.03, (ag, ao)
+    lg, lo = out["leapfrogs"].float().mean().item(), ref["leapfrogs"].mean()
+    assert abs(lg - lo) / lo < 0.08, (lg, lo)
+    eg, eo = float(out["step_size"][0]), float(ref["step_size"][0])
+    assert abs(eg - eo) / eo < 0.15, (eg, eo)
+
+
+def test_radon_fp32_replay_reports_exact_match_rate(oracle_mod):
+    """(d) in FP32 on radon-919 with injected momenta: the integer tree statistics replay bit-exactly until a rounding
+    difference flips a comparison (device FMA contraction, MUFU vs libm, another summation order); from there a chain
+    runs its own valid trajectory.  The first transitions must match for (almost) every chain and the match rate is
+    reported."""
+    ir, _, _ = lower_model(M.radon_model(real=False))
+    C, D, T = 64, ir.D, 6
+    rng = np.random.default_rng(5)
+    momenta = rng.standard_normal((T, C, D))
+    cfg = make_nuts_cfg(C, T, 0, step_size=0.02, seed=4, adapt=make_adapt(enabled=False))
+    ref = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(D), dtype=np.float32, momenta=momenta)
+    out = _dm(ir).nuts(cfg, np.zeros((C, D), np.float32), dtype=np.float32, momenta=momenta.astype(np.float32))
+    same = out["leapfrogs"].cpu().numpy() == ref["leapfrogs"]  # [T, C]
+    alive = np.cumprod(same, axis=0).astype(bool)  # still on the oracle's trajectory
+    rate = alive.mean(axis=1)
+    print("FP32 replay, radon-919: chains on the oracle's trajectory after transition 1..%d: %s" % (T, np.round(rate, 3)))
+    assert rate[0] >= 0.95 and rate[1] >= 0.85, rate
+    first = alive[0]
+    np.testing.assert_allclose(out["states"].cpu().numpy()[0][first], ref["states"][0][first], atol=5e-4)
+    assert np.array_equal(out["diverging"].cpu().numpy()[0][first], ref["diverging"][0][first])
+
+
 # ------------------------------------------------------------------------------------------
 # large-state path (BASELINE configs[4]: radon-shaped, 100k observations / 5k groups, D = 10 005):
 # 16 warps per chain, 20 state elements per lane, hybrid tree scratch (hot slots on chip, rest in L2),

@@ -566,3 +566,95 @@ def test_gp_term_spellings_lower_to_the_same_term(oracle_mod):
 
     with pytest.raises(NotImplementedError, match="marginal likelihood"):
         lower_model(two_kernels())
+
+
+# ------------------------------------------------------------------------------------------
+# invariants that pin the restated sampler WITHOUT TensorFlow Probability (the reference holds no golden
+# chains and TF/TFP cannot be installed here): properties any correct NUTS / HMC / dual averaging has
+# ------------------------------------------------------------------------------------------
+def test_nuts_is_stationary_on_the_standard_normal(oracle_mod):
+    """NUTS must leave N(0, I) invariant: per-dimension Kolmogorov-Smirnov test of thinned draws, moments, and the
+    chi-square law of |x|^2 (a wrong multinomial weight, U-turn test or leapfrog shows up here)."""
+    @pm.model
+    def m():
+        yield pm.Normal("x", 0.0, 1.0, batch_stack=4)
+
+    ir, _, _ = lower_model(m())
+    C, B, S = 64, 150, 400
+    out = oracle_mod.Oracle(ir).nuts(make_nuts_cfg(C, S, B, step_size=0.3, seed=3,
+                                                   adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B)),
+                                     np.zeros(4), dtype=np.float64)
+    x = out["states"][::8]  # thin: NUTS draws on a Gaussian are nearly independent after a few transitions
+    flat = x.reshape(-1, 4)
+    for d in range(4):
+        assert stats.kstest(flat[:, d], "norm").pvalue > 1e-3
+    np.testing.assert_allclose(flat.mean(axis=0), 0.0, atol=5.0 / math.sqrt(flat.shape[0]))
+    np.testing.assert_allclose(flat.var(axis=0), 1.0, atol=0.08)
+    assert stats.kstest((flat ** 2).sum(axis=1), "chi2", args=(4,)).pvalue > 1e-3
+    assert out["diverging"].mean() == 0.0
+    assert 0.6 < np.exp(out["log_accept"]).mean() < 0.95  # dual averaging steers towards 0.75
+
+
+def test_hmc_leapfrog_is_reversible_and_volume_preserving(oracle_mod):
+    """Run L leapfrogs from (q, p), flip the momentum, run L more: the integrator must come back to q; the energy
+    error of a short trajectory must shrink like eps^2 (second-order symplectic integrator)."""
+    ir, _, _ = lower_model(M.radon_model(real=True))
+    D, L = ir.D, 7
+    rng = np.random.default_rng(1)
+    q0 = rng.normal(0, 0.1, D)
+    p0 = rng.standard_normal(D)
+    orc = oracle_mod.Oracle(ir)
+
+    def run(q, p, eps, L=L):
+        cfg = make_hmc_cfg(1, 1, 0, step_size=eps, num_leapfrog_steps=L, seed=0, adapt=make_adapt(enabled=False))
+        o = orc.hmc(cfg, q, dtype=np.float64, momenta=p[None, None, :], uniforms=np.full((1, 1), 1e-300))
+        return o["traj"][0, 0], o["log_accept"][0, 0]
+
+    def final_momentum(q, p, eps):  # restate the integrator for the momentum the ABI does not return
+        lp, g = orc.logp_grad(q[None], dtype=np.float64)
+        g = g[0]
+        p = p + 0.5 * eps * g
+        for _ in range(L):
+            q = q + eps * p
+            g = orc.logp_grad(q[None], dtype=np.float64)[1][0]
+            p = p + eps * g
+        return q, p - 0.5 * eps * g
+
+    eps = 0.01
+    q1, _ = run(q0, p0, eps)
+    q1_ref, p1 = final_momentum(q0, p0, eps)
+    np.testing.assert_allclose(q1, q1_ref, atol=1e-10)  # the C integrator is the restated one
+    q2, _ = run(q1, -p1, eps)
+    np.testing.assert_allclose(q2, q0, atol=1e-9)      # time reversal
+    # same trajectory length, step halved twice: the energy error of a second-order integrator falls ~4x each time
+    errs = [abs(run(q0, p0, e, n)[1]) for e, n in ((0.004, 5), (0.002, 10), (0.001, 20))]
+    assert 3.0 < errs[0] / errs[1] < 5.5 and 3.0 < errs[1] / errs[2] < 5.5, errs
+
+
+def test_sample_chain_step_accounting_and_averaged_step_size(oracle_mod):
+    """tfp sample_chain / DualAveragingStepSizeAdaptation accounting: with
+    num_adaptation_steps = A the update after transition t = A (0-based) installs exp(log_avg); every transition is
+    traced when burn_in = 0, so the recursion can be replayed from the traced acceptance ratios."""
+    @pm.model
+    def m():
+        yield pm.Normal("x", 0.0, 1.0, batch_stack=5)
+
+    ir, _, _ = lower_model(m())
+    A, S = 12, 20
+    cfg = make_nuts_cfg(1, S, 0, step_size=0.1, seed=9, adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=A))
+    out = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(5), dtype=np.float64)
+    acc = np.exp(out["log_accept"][:, 0])
+    assert out["log_accept"].shape == (S, 1)
+    eps0, err, log_avg, eps = 0.1, 0.0, 0.0, 0.1
+    for t in range(S):
+        step = t + 1.0
+        err += 0.75 - acc[t]
+        log_eps = math.log(10 * eps0) - err * math.sqrt(step) / ((10 + step) * 0.05)
+        eta = step ** -0.75
+        log_avg = eta * log_eps + (1 - eta) * log_avg
+        if t < A:
+            eps = math.exp(log_eps)
+        elif t == A:
+            eps = math.exp(log_avg)
+    np.testing.assert_allclose(out["step_size"][0], eps, rtol=1e-10)
+    assert out["total_leapfrogs"][0] == out["leapfrogs"].sum()  # every transition of the call is accounted for
