@@ -580,6 +580,7 @@ def run_b200(args):
             nuts = NUTS(model, step_size=step_arr, num_adaptation_steps=B, device=local_rank, chain_offset=shard * C,
                         **extra)
         e2e_leaps, e2e_secs, h2d, d2h = 0.0, 0.0, 0, 0
+        e2e_pass_ms = []
         n_e2e = max(1, min(args.steps, 2))
         for k in range(1 + n_e2e):  # first pass untimed (allocator / pinned-buffer warm-up)
             barrier()
@@ -588,6 +589,7 @@ def run_b200(args):
             trace = nuts(num_samples=S, num_chains=C, burn_in=B, seed=args.seed + 500 + k)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            e2e_pass_ms.append(1e3 * dt)
             if k == 0:
                 continue
             e2e_secs += dt
@@ -604,6 +606,7 @@ def run_b200(args):
             e2e_secs, e2e_leaps = float(a[0]), float(b[1])
         e2e = {"value": e2e_leaps / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_secs / n_e2e,
+               "passes_ms": [round(v, 1) for v in e2e_pass_ms],  # the first pass (allocator / pinned-buffer warm-up) is not timed
                "api": "pymc4_b200.mcmc.samplers.%s(model, step_size=%s)(num_samples, num_chains, burn_in) -> InferenceData "
                       "on the host (trace copied through pinned memory)"
                       % ("HMC" if is_logit else "NUTS", "[C,1]" if args.eps_mode == "per-chain" else "%g" % args.step_size)}

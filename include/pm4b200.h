@@ -333,6 +333,14 @@ int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const voi
                  void* log_accept_dev, int32_t* depth_dev, void* step_size_dev,
                  int64_t* total_leapfrogs_dev, void* stream);
 
+/* Trace streaming (one-shot, consumed by the next pm4_nuts_run of a model without dense terms): the kept draws
+ * are produced in `n_slabs` launches and every finished slab of `states` [S, C, D] is copied to `states_host`
+ * (pinned host memory, same layout and dtype) on `copy_stream` while the next slab is sampled.  The reference's
+ * _sample pulls the whole trace to the host at the end (`.numpy()`, samplers.py:155-160; trace_to_arviz,
+ * mcmc/utils.py:95-144): for the radon shape that is 2.9 GB per call.  The caller synchronises `copy_stream`
+ * before it reads the buffer.  states_host == NULL detaches. */
+int pm4_model_set_trace_sink(pm4_model_t* m, void* states_host, int n_slabs, void* copy_stream);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU: chains of one pm.sample call sharded over the GPUs of one box, one process per GPU.
  * The sampler has ONE exchange step: with a scalar step_size (PM4_EPS_POOLED) tfp's

@@ -33,7 +33,7 @@ EXPORTS = [
     "pm4_logp_grad",
     "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_prior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
-    "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm",
+    "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm", "pm4_model_set_trace_sink",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
     "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches", "pm4_gp_sample", "pm4_gp_predictive", "pm4_gp_points",
 ]
@@ -100,6 +100,7 @@ def load_library():
     L.pm4_comm_connect.argtypes = [vp, ctypes.c_char_p]
     L.pm4_comm_destroy.argtypes = [vp]
     L.pm4_model_attach_comm.argtypes = [vp, vp]
+    L.pm4_model_set_trace_sink.argtypes = [vp, vp, i32, vp]
     _lib = L
     return L
 
@@ -288,8 +289,11 @@ class DeviceModel:
         return x, obs
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None,
-             want_states: bool = True) -> Dict[str, "object"]:
-        """Run NUTS; every result is a device tensor in the reference layout [S, C, ...]."""
+             want_states: bool = True, stream_trace: int = 0) -> Dict[str, "object"]:
+        """Run NUTS; every result is a device tensor in the reference layout [S, C, ...].
+
+        ``stream_trace = n > 0``: the kept draws also travel to a pinned host tensor ``out["states_host"]`` in n slabs
+        on a copy stream while the sampler keeps running; ``out["states_host_ready"]()`` waits for the last slab."""
         torch = self.torch
         td = _tdtype(torch, dtype)
         C, S, D = cfg.C, cfg.num_results, self.ir.D
@@ -308,13 +312,26 @@ class DeviceModel:
             step_size=self.empty((C,), td),
             total_leapfrogs=self.empty((C,), torch.int64),
         )
+        host = copy_stream = None
+        if stream_trace > 0 and want_states and S > 0 and not self.ir.lockstep:
+            host = torch.empty((S, C, D), dtype=td, pin_memory=True)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self._dev())
+            copy_stream = self._copy_stream
+            self._check(self.lib.pm4_model_set_trace_sink(self.handle, ctypes.c_void_p(host.data_ptr()), int(stream_trace),
+                                                          ctypes.c_void_p(copy_stream.cuda_stream)))
         with torch.cuda.device(self._dev()):
             rc = self.lib.pm4_nuts_run(
                 self.handle, _code(dtype), ctypes.byref(cfg), self._p(th0), self._p(sc), self._p(mom),
                 self._p(out["states"]), self._p(out["lp"]), self._p(out["leapfrogs"]), self._p(out["diverging"]),
                 self._p(out["energy"]), self._p(out["log_accept"]), self._p(out["depth"]),
                 self._p(out["step_size"]), self._p(out["total_leapfrogs"]), self._stream())
+        if host is not None:
+            self.lib.pm4_model_set_trace_sink(self.handle, None, 0, None)  # one-shot even when the run failed
         self._check(rc)
+        if host is not None:
+            out["states_host"] = host
+            out["states_host_ready"] = copy_stream.synchronize
         out["_keepalive"] = (th0, sc, mom)
         return out
 

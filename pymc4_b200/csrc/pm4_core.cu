@@ -107,6 +107,12 @@ struct pm4_model {
   pm4m_lpt_order_fn f_order = nullptr;
   int elem_off = 0, spart_off = 0, phdr_off = 0;
   int32_t owned_hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // one-shot trace sink of the next NUTS run (pm4_model_set_trace_sink): the draws leave the device in slabs
+  // on a copy stream while the persistent kernel keeps sampling
+  void* sink_host = nullptr;
+  int sink_slabs = 0;
+  cudaStream_t sink_stream = nullptr;
+  cudaEvent_t sink_event = nullptr;
   float* d_f32 = nullptr;
   double* d_f64 = nullptr;
   int32_t *d_datai = nullptr, *d_term_n = nullptr, *d_op_blob = nullptr;
@@ -495,6 +501,22 @@ extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n
   return rc != PM4_OK ? rc : upload_glm(m, dataf);
 }
 
+extern "C" int pm4_model_set_trace_sink(pm4_model_t* m, void* states_host, int n_slabs, void* copy_stream) {
+  if (!m) return fail(PM4_EINVAL, "null model");
+  if (!states_host || n_slabs <= 0) {  // detach
+    m->sink_host = nullptr;
+    m->sink_slabs = 0;
+    return PM4_OK;
+  }
+  if (!copy_stream) return fail(PM4_EINVAL, "pm4_model_set_trace_sink: the copies need their own stream");
+  CU(cudaSetDevice(m->device));
+  if (!m->sink_event) CU(cudaEventCreateWithFlags(&m->sink_event, cudaEventDisableTiming));
+  m->sink_host = states_host;
+  m->sink_slabs = n_slabs > 64 ? 64 : n_slabs;
+  m->sink_stream = (cudaStream_t)copy_stream;
+  return PM4_OK;
+}
+
 extern "C" int pm4_model_set_plans(pm4_model_t* m, const pm4_ir_t* ir) {
   if (!m || !ir) return fail(PM4_EINVAL, "null argument");
   if (ir->n_plans != m->n_plans || ir->n_planf != m->n_planf || ir->n_plani != m->n_plani)
@@ -703,18 +725,49 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
   }
   ends.push_back(T);
   // persistent launches of the warp-per-chain path hand out (chain, block of tb transitions) items
-  static const int tb_env = getenv("PM4_TB") ? atoi(getenv("PM4_TB")) : 25;
+  static const int tb_env = getenv("PM4_TB") ? atoi(getenv("PM4_TB")) : 10;
   r.tb = nuts && r.progress ? tb_env : 0;
+  // trace sink: the kept draws of the last segment are produced in `sink_slabs` launches; the states of a finished
+  // slab travel to the (pinned) host buffer on the copy stream while the next slab is sampled
+  const bool sink = nuts && m->sink_host && m->sink_slabs > 0 && r.states && r.S > 0;
+  if (sink) {
+    const int last_begin = ends.size() > 1 ? ends[ends.size() - 2] : t;
+    const int first = last_begin > r.B ? last_begin : r.B;  // the slabs cover draws only
+    ends.pop_back();
+    if (first > t && (ends.empty() || ends.back() < first)) ends.push_back(first);
+    for (int k = 1; k <= m->sink_slabs; ++k) {
+      const int e = first + (int)(((int64_t)(T - first) * k) / m->sink_slabs);
+      if (e > (ends.empty() ? t : ends.back())) ends.push_back(e);
+    }
+    if (ends.empty() || ends.back() != T) ends.push_back(T);
+  }
+  const size_t row_bytes = (size_t)r.C * (size_t)m->D * (dtype == PM4_F64 ? 8 : 4);  // one draw of all chains
+  int copied_to = 0;  // draws already handed to the copy stream
+  auto flush_sink = [&](int t_done) -> int {
+    const int k1 = t_done - r.B;  // draws [0, k1) are complete
+    if (!sink || k1 <= copied_to) return PM4_OK;
+    CU(cudaEventRecord(m->sink_event, st));
+    CU(cudaStreamWaitEvent(m->sink_stream, m->sink_event, 0));
+    CU(cudaMemcpyAsync((char*)m->sink_host + (size_t)copied_to * row_bytes, (const char*)r.states + (size_t)copied_to * row_bytes,
+                       (size_t)(k1 - copied_to) * row_bytes, cudaMemcpyDeviceToHost, m->sink_stream));
+    copied_to = k1;
+    return PM4_OK;
+  };
   for (size_t k = 0; k < ends.size(); ++k) {
     if (ends[k] <= t) continue;
     r.t_begin = t;
     r.t_count = ends[k] - t;
     MOD(f(dtype, &r, wpb, st), nuts ? "nuts" : "hmc");
     t = ends[k];
-    if (phased && t < T) {
+    if (int rc2 = flush_sink(t)) return rc2;
+    if (phased && t < T && !sink) {
       MOD(m->f_order(r.C, r.launch_leaps, order_buf, st), "longest-first chain order");
       r.order = order_buf;
     }
+  }
+  if (sink) {  // one-shot
+    m->sink_host = nullptr;
+    m->sink_slabs = 0;
   }
   if (phase_times) {
     cudaEventRecord(ev[2], st);

@@ -36,14 +36,11 @@ __device__ __forceinline__ double m_exp(double v) { return exp(v); }
 __device__ __forceinline__ float m_log(float v) { return mufu_lg2(v) * 0.6931471805599453f; }
 __device__ __forceinline__ double m_log(double v) { return log(v); }
 __device__ __forceinline__ float m_log1p(float v) {
-  // lg2.approx(1 + v) has an ABSOLUTE error of ~1e-7, i.e. a relative error of 1e-7 / |log1p v|: compensate the
-  // rounding of 1 + v (the classic log(u) * v / (u - 1) form) so the relative error stays ~1e-6 for every v; the
-  // series takes over below 2^-12, where u - 1 loses its last bits
-  const float a = fabsf(v);
-  if (a < 2.44140625e-4f) return v * (1.0f - 0.5f * v + 0.33333334f * v * v);
-  const float u = 1.0f + v;
-  const float d = u - 1.0f;
-  return a < 0.5f ? m_log(u) * (v * mufu_rcp(d)) : m_log(u);
+  // lg2.approx(1 + v) has an ABSOLUTE error of ~1e-7, i.e. a relative error of 1e-7 / |log1p v|: below 0.02 the
+  // alternating series takes over (four terms: truncation < v^4 / 5 = 3e-8 relative), above it the MUFU form is
+  // within 5e-6 relative -- both inside the 1e-5 parity bound, and no slower than the bare MUFU form
+  const float s = v * (1.0f + v * (-0.5f + v * (0.33333334f - 0.25f * v)));
+  return fabsf(v) < 0.02f ? s : m_log(1.0f + v);
 }
 __device__ __forceinline__ double m_log1p(double v) { return log1p(v); }
 __device__ __forceinline__ float m_sqrt(float v) { return sqrtf(v); }

@@ -42,7 +42,7 @@ if not _log.handlers:
 _log.setLevel(logging.INFO)
 
 # keyword arguments of this backend that the reference does not have
-_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block", "comm")
+_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block", "comm", "trace_slabs")
 
 
 def register_sampler(cls):
@@ -167,7 +167,8 @@ class _BaseSampler(metaclass=abc.ABCMeta):
             init_keys_ = [scope_remove_transformed_part_if_required(k, state_.transformed_values)[1] for k in init_keys]
             for name in trace_discrete:
                 key = init_keys[init_keys_.index(name)]
-                posterior[key] = posterior[key].to(dtype=self._device_model.torch.int32)
+                v = posterior[key]
+                posterior[key] = v.astype(np.int32) if isinstance(v, np.ndarray) else v.to(dtype=self._device_model.torch.int32)
 
         deterministic_values = ()
         if len(sample_stats) > len(self.stat_names):
@@ -370,12 +371,23 @@ class NUTS(_BaseSampler):
                             chain_offset=self.backend_kwargs.get("chain_offset", 0))
         if "comm" in self.backend_kwargs:  # chains of this call are one shard of a box-wide run
             dm.attach_comm(self.backend_kwargs["comm"])
-        out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale)
+        # a large trace leaves the device in slabs while the sampler keeps running (pm4_model_set_trace_sink): the
+        # posterior arrays are then views of one pinned host buffer instead of per-variable copies made afterwards
+        trace_bytes = self._num_samples * C * dm.ir.D * np.dtype(self._dtype).itemsize
+        slabs = int(self.backend_kwargs.get("trace_slabs", 8 if trace_bytes >= (64 << 20) else 0))
+        out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale, stream_trace=slabs)
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
                               depth=out["depth"], kernel="nuts")
         self._last_states = out["states"]
-        results = self._unpack_states(out["states"])
-        return results, self.trace_fn(out["states"], out)
+        stats = self.trace_fn(out["states"], out)
+        if "states_host" in out:
+            out["states_host_ready"]()
+            host = out["states_host"].numpy()
+            S = host.shape[0]
+            results = [host[:, :, rv.offset: rv.offset + rv.size].reshape((S, C) + rv.shape) for rv in dm.ir.rvs]
+        else:
+            results = self._unpack_states(out["states"])
+        return results, stats
 
 
 @register_sampler

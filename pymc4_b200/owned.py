@@ -169,31 +169,29 @@ def _pieces(left: int, cap: int) -> List[int]:
 
 def _choose_caps(sizes_desc: np.ndarray) -> Tuple[int, int]:
     """(L0, Lf): row cap of owned slice 0 and of a foreign piece, minimising the rows every lane walks
-    (plus a per-slice and per-round overhead, in row units of ~3 instructions)."""
-    top = sizes_desc[:32]
+    (plus a per-slice and per-step overhead, in row units of ~3 instructions)."""
+    top = np.asarray(sizes_desc[:32], dtype=np.int64)
     rest_cost = sum(int(sizes_desc[s]) for s in range(32, len(sizes_desc), 32))
     best = None
-    for L0 in range(1, int(top.max(initial=0)) + 1):
-        if L0 <= 0:
-            continue
-        left = [int(s) - L0 for s in top if s > L0]
-        if not left:
+    hi = int(top.max(initial=0))
+    cands = sorted({int(v) for v in top if v > 0} | {max(1, hi // k) for k in range(1, 17)})
+    for L0 in cands:
+        left = top[top > L0] - L0
+        if left.size == 0:
             cost = L0 + rest_cost
             if best is None or cost < best[0]:
                 best = (cost, L0, max(L0, 1))
             continue
-        for Lf in range(2, 65):
-            lens: List[int] = []
-            qmax = 0
-            for l in left:
-                ps = _pieces(l, Lf)
-                lens.extend(ps)
-                qmax = max(qmax, len(ps))
-            lens.sort(reverse=True)
-            nf = -(-len(lens) // 32)
-            f_rows = sum(lens[k * 32] for k in range(nf))
-            # a group's pieces spread over the foreign slices: rounds per slice ~ ceil(qmax / nf)
-            cost = L0 + rest_cost + f_rows + 7.0 * nf + 1.5 * qmax
+        for Lf in range(2, 49):
+            k = -(-left // Lf)                       # pieces per group, near-equal lengths
+            longest = -(-left // k)
+            n_pieces = int(k.sum())
+            nf = -(-n_pieces // 32)
+            # the pieces are dealt longest-first, 32 per foreign slice: slice f is as long as its longest piece
+            lens = np.sort(np.repeat(longest, k))[::-1]
+            f_rows = int(lens[::32].sum())
+            steps = int(np.ceil(np.log2(max(int(k.max()), 1)))) if k.max() > 1 else 0
+            cost = L0 + rest_cost + f_rows + 7.0 * nf + 2.0 * steps * nf + 0.0 * int(longest.max())
             if best is None or cost < best[0]:
                 best = (cost, L0, Lf)
     return best[1], best[2]

@@ -277,3 +277,16 @@ def test_refit_on_data_of_another_length_and_on_other_indices():
         lp_ref, g_ref = pm4_oracle.Oracle(ir).logp_grad(th, dtype=np.float64)
         np.testing.assert_allclose(lp.cpu().numpy(), lp_ref, rtol=2e-5)
         assert np.max(np.abs(gr.cpu().numpy() - g_ref)) / np.max(np.abs(g_ref)) < 2e-5
+
+
+def test_streamed_trace_equals_the_plain_trace():
+    """pm4_model_set_trace_sink: the draws copied to the host in slabs while the sampler keeps running are the draws
+    the device holds at the end (same seed, streamed vs fetched afterwards)."""
+    model = M.radon_model(real=False)
+    kw = dict(step_size=0.05, num_chains=96, num_samples=40, burn_in=30, seed=11)
+    plain = pm.sample(model, trace_slabs=0, **kw)
+    streamed = pm.sample(model, trace_slabs=5, **kw)
+    for k, v in plain.posterior.items():
+        np.testing.assert_array_equal(streamed.posterior[k], v)
+    for k, v in plain.sample_stats.items():
+        np.testing.assert_array_equal(streamed.sample_stats[k], v)
