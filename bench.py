@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--gp-n", type=int, default=4096)
     ap.add_argument("--logit-n", type=int, default=1_000_000)
     ap.add_argument("--leapfrogs", type=int, default=3, help="HMC leapfrog steps (logit workload; reference default 3)")
+    ap.add_argument("--mass-windows", type=int, default=0,
+                    help="diagonal mass-matrix windows during burn-in (backend extension; 0 = the reference behaviour)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="radon919 only: do not append the bounded runs of the other BASELINE configurations "
                          "(logit, gp, radon100k) as the line's \"secondary\" object")
@@ -476,7 +478,7 @@ def run_b200(args):
         comm = _cabi.Communicator(local_rank, rank, world)
         dm.attach_comm(comm)
     adapt = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
-                       num_adaptation_steps=B)
+                       num_adaptation_steps=B, mass_windows=args.mass_windows)
 
     is_logit = args.workload in ("logit", "gp")  # the lock-step HMC workloads
 
@@ -564,7 +566,39 @@ def run_b200(args):
     ess_per_sec = summ["min_ess"] / (dev_secs_max / max(args.steps, 1))
     mean_accept = float(torch.exp(out["log_accept"]).mean().item())
     divergent = float(out["diverging"].float().mean().item())
+    stuck_frac = float((out["diverging"].float().mean(dim=0) > 0.9).float().mean().item())  # chains diverging on ~every transition
     mean_tree = float(out["leapfrogs"].float().mean().item())
+
+    # ---- the same workload with diagonal mass-matrix windows (one extra step, reported beside the headline) -------
+    mass_adapted = None
+    if args.workload == "radon919" and args.mass_windows == 0 and not is_logit:
+        adapt_m = make_adapt(mode=PM4_EPS_PER_CHAIN if args.eps_mode == "per-chain" else PM4_EPS_POOLED,
+                             num_adaptation_steps=B, mass_windows=4)
+        cfg_m = make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + 77, adapt=adapt_m,
+                              max_tree_depth=args.max_tree_depth, warps_per_block=args.warps_per_block, chain_offset=shard * C)
+        dm.nuts(cfg_m, theta0, dtype=np.float32)  # warm-up of the scaled kernel variant
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        om = dm.nuts(cfg_m, theta0, dtype=np.float32)
+        e1.record()
+        e1.synchronize()
+        ms_m = e0.elapsed_time(e1)
+        sm = diagnostics.summarize(om["states"], columns=cols)
+        lm = float(om["total_leapfrogs"].sum().item())
+        dvm = om["diverging"].float()
+        mass_adapted = {
+            "what": "same workload, one step, 4 diagonal mass-matrix windows during burn-in (pm.sample(..., mass_windows=4); "
+                    "not in the reference API: its radon notebook hand-feeds per-dimension step sizes instead)",
+            "value_this_rank": lm / (ms_m / 1e3), "unit": UNIT, "ms_per_step": ms_m,
+            "ess_per_sec_this_rank": sm["min_ess"] / (ms_m / 1e3),
+            "diagnostics": {"min_bulk_ess": sm["min_ess"], "max_split_rhat": sm["max_rhat"],
+                            "divergent_frac": float(dvm.mean().item()),
+                            "stuck_chain_frac": float((dvm.mean(dim=0) > 0.9).float().mean().item()),
+                            "mean_leapfrogs_per_draw": float(om["leapfrogs"].float().mean().item()),
+                            "step_size": float(om["step_size"][0].item())},
+        }
+        del om
 
     # ---- end-to-end arm: public sampler API, host buffers in, host trace out --------------
     e2e = None
@@ -731,6 +765,9 @@ def run_b200(args):
         "wall_s_timed_region": wall,
         "steps_detail": detail,
     }
+    if mass_adapted is not None:
+        line["mass_adapted"] = mass_adapted
+    line["diagnostics"]["stuck_chain_frac"] = stuck_frac
     if secondary is not None:
         line["secondary"] = secondary
     if not args.no_cpu_baseline:  # rank 0's host cores, a bounded sample of the per-GPU workload (also on N > 1 lines)

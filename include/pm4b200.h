@@ -270,6 +270,14 @@ typedef struct pm4_adapt_cfg {
   int32_t enabled;              /* 0: fixed step size                         */
   int32_t kind;                 /* PM4_ADAPT_*                                */
   double adaptation_rate;       /* 0.01 (PM4_ADAPT_SIMPLE)                    */
+  /* Diagonal mass-matrix adaptation (NUTS; SURVEY 8(f) item 4 -- NOT in the reference API: its radon notebook feeds
+   * the posterior standard deviations in by hand as per-dimension step sizes, radon_hierarchical.ipynb:123-146).
+   * K = mass_windows > 0: before transition w_k = num_adaptation_steps * k / (K + 1), k = 1 .. K, the per-dimension
+   * step scale becomes the CROSS-CHAIN standard deviation of the unconstrained states (divided by its geometric mean)
+   * and dual averaging restarts from the current epsilon.  A step scale s_d with unit-Gaussian momenta is the diagonal
+   * mass matrix diag(1 / s_d^2).  0 = off (the reference behaviour). */
+  int32_t mass_windows;
+  int32_t _pad;
 } pm4_adapt_cfg_t;
 
 /* proposals of the Metropolis-Hastings kernel run by pm4_hmc_run */
@@ -332,6 +340,10 @@ int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const voi
                  void* lp_dev, int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev,
                  void* log_accept_dev, int32_t* depth_dev, void* step_size_dev,
                  int64_t* total_leapfrogs_dev, void* stream);
+
+/* Per-dimension step scale [D] (unconstrained order) the last pm4_nuts_run with mass_windows > 0 ended with,
+ * copied to out_dev (dtype real); PM4_EINVAL when no such run has happened. */
+int pm4_model_get_mass_scale(pm4_model_t* m, int dtype, void* out_dev, void* stream);
 
 /* Trace streaming (one-shot, consumed by the next pm4_nuts_run of a model without dense terms): the kept draws
  * are produced in `n_slabs` launches and every finished slab of `states` [S, C, D] is copied to `states_host`

@@ -205,12 +205,12 @@ int pm4o_deterministics(const pm4_ir_t* ir, int dtype, int64_t M, const void* th
 int pm4o_nuts_run(const pm4_ir_t* ir, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0,
                   const void* step_scale, const void* momenta, void* states, void* lp,
                   int32_t* leapfrogs, uint8_t* diverging, void* energy, void* log_accept,
-                  int32_t* depth, void* step_size_out, int64_t* total_leapfrogs) {
+                  int32_t* depth, void* step_size_out, int64_t* total_leapfrogs, void* mass_scale_out) {
   return dtype == PM4_F64
              ? pm4o_nuts_run_f64(ir, cfg, theta0, step_scale, momenta, states, lp, leapfrogs,
-                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs)
+                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs, mass_scale_out)
              : pm4o_nuts_run_f32(ir, cfg, theta0, step_scale, momenta, states, lp, leapfrogs,
-                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs);
+                                 diverging, energy, log_accept, depth, step_size_out, total_leapfrogs, mass_scale_out);
 }
 
 int pm4o_hmc_run(const pm4_ir_t* ir, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0,

@@ -44,7 +44,7 @@ def lib():
         L.pm4o_posterior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
         L.pm4o_gp_predictive.argtypes = [irp, i32, i64, ctypes.c_uint64, vp, vp]
         L.pm4o_prior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
-        L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 12
+        L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
         L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
         L.pm4o_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
                                          ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
@@ -170,12 +170,13 @@ class Oracle:
             energy=np.empty((S, C), dtype=dtype), log_accept=np.empty((S, C), dtype=dtype),
             depth=np.empty((S, C), dtype=np.int32), step_size=np.empty(C, dtype=dtype),
             total_leapfrogs=np.empty(C, dtype=np.int64),
+            mass_scale=np.ones(D, dtype=dtype),
         )
         rc = lib().pm4o_nuts_run(
             self.packed.byref(), _code(dtype), ctypes.byref(cfg), _ptr(theta0), _ptr(step_scale), _ptr(momenta),
             _ptr(out["states"]), _ptr(out["lp"]), _ptr(out["leapfrogs"]), _ptr(out["diverging"]),
             _ptr(out["energy"]), _ptr(out["log_accept"]), _ptr(out["depth"]), _ptr(out["step_size"]),
-            _ptr(out["total_leapfrogs"]))
+            _ptr(out["total_leapfrogs"]), _ptr(out["mass_scale"]))
         _check(rc, "nuts_run")
         return out
 

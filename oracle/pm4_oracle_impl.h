@@ -672,6 +672,7 @@ static inline REAL NAME(logaddexp)(REAL a, REAL b) {
  * -------------------------------------------------------------------------------------- */
 typedef struct NAME(da) {
   REAL eps0, eps, error_sum, log_avg, log_shrink_target;
+  int t0; /* first transition of the current adaptation window (mass-matrix windows restart the recursion) */
 } NAME(da_t);
 
 static void NAME(da_init)(NAME(da_t)* s, REAL eps0) {
@@ -680,6 +681,47 @@ static void NAME(da_init)(NAME(da_t)* s, REAL eps0) {
   s->error_sum = 0;
   s->log_avg = 0;
   s->log_shrink_target = RLOG((REAL)10 * eps0);
+  s->t0 = 0;
+}
+
+/* restart of the recursion at transition t0 from the current step size (after a mass-matrix update) */
+static void NAME(da_restart)(NAME(da_t)* s, int t0) {
+  s->error_sum = 0;
+  s->log_avg = 0;
+  s->log_shrink_target = RLOG((REAL)10 * s->eps);
+  s->t0 = t0;
+}
+
+/* Diagonal mass-matrix window (include/pm4b200.h: pm4_adapt_cfg_t.mass_windows): the step scale becomes the
+ * cross-chain standard deviation of the unconstrained states divided by its geometric mean.  Returns 0 (and leaves
+ * `scale` alone) when some dimension has no finite positive spread yet. */
+static int NAME(mass_update)(const REAL* th, int C, int D, REAL* scale) {
+  double* ls = (double*)malloc(sizeof(double) * (size_t)D);
+  double mean_ls = 0;
+  int ok = 1;
+  for (int d = 0; d < D && ok; ++d) {
+    double m = 0, v = 0;
+    for (int c = 0; c < C; ++c) m += (double)th[(size_t)c * D + d];
+    m /= C;
+    for (int c = 0; c < C; ++c) { const double e = (double)th[(size_t)c * D + d] - m; v += e * e; }
+    v /= C;
+    if (!(v > 0) || !isfinite(v)) ok = 0;
+    else { ls[d] = 0.5 * log(v); mean_ls += ls[d]; }
+  }
+  if (ok) {
+    mean_ls /= D;
+    for (int d = 0; d < D; ++d) scale[d] = (REAL)exp(ls[d] - mean_ls);
+  }
+  free(ls);
+  return ok;
+}
+
+/* is transition t the first of a mass-matrix window?  w_k = num_adapt * k / (K + 1), k = 1 .. K */
+static int NAME(mass_window_start)(const pm4_adapt_cfg_t* a, int t) {
+  if (!a->enabled || a->mass_windows <= 0 || t <= 0 || t >= a->num_adaptation_steps) return 0;
+  for (int k = 1; k <= a->mass_windows; ++k)
+    if ((int)(((int64_t)a->num_adaptation_steps * k) / (a->mass_windows + 1)) == t) return 1;
+  return 0;
 }
 
 /* called after transition t (0-based) with the (cross-chain or per-chain) mean accept prob */
@@ -690,7 +732,7 @@ static void NAME(da_update)(NAME(da_t)* s, const pm4_adapt_cfg_t* a, int t, REAL
     if (t < a->num_adaptation_steps) s->eps = accept > (REAL)a->target_accept_prob ? s->eps * f : s->eps / f;
     return;
   }
-  REAL step = (REAL)(t + 1);
+  REAL step = (REAL)(t - s->t0 + 1);
   s->error_sum += (REAL)a->target_accept_prob - accept;
   REAL log_eps = s->log_shrink_target -
                  s->error_sum * RSQRT(step) / (((REAL)a->step_count_smoothing + step) * (REAL)a->exploration_shrinkage);
@@ -844,7 +886,7 @@ static void NAME(nuts_buf_free)(NAME(nuts_buf_t)* b) { free(b->p0); }
 int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REAL* theta0,
                         const REAL* step_scale, const REAL* momenta, REAL* states, REAL* lp_out,
                         int32_t* leapfrogs, uint8_t* diverging, REAL* energy, REAL* log_accept,
-                        int32_t* depth_out, REAL* step_size_out, int64_t* total_leapfrogs) {
+                        int32_t* depth_out, REAL* step_size_out, int64_t* total_leapfrogs, REAL* mass_scale_out) {
   const int D = ir->D, C = cfg->C, B = cfg->num_burnin, S = cfg->num_results, T = B + S;
   if (cfg->max_tree_depth < 1 || cfg->max_tree_depth > 20) return PM4_EINVAL;
   REAL* th = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
@@ -857,6 +899,21 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
   NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)(pooled ? 1 : C));
   for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init)(&da[c], (REAL)cfg->step_size);
 
+  /* the step scale in effect: the caller's (or ones when mass windows will write it), updated at window starts */
+  REAL* scale_buf = NULL;
+  if (cfg->adapt.enabled && cfg->adapt.mass_windows > 0) {
+    scale_buf = (REAL*)malloc(sizeof(REAL) * (size_t)D);
+    for (int d = 0; d < D; ++d) scale_buf[d] = step_scale ? step_scale[d] : (REAL)1;
+    step_scale = scale_buf;
+  }
+  /* segments between mass-matrix window starts: inside a segment the chains only couple through a pooled step size */
+  int* seg = (int*)malloc(sizeof(int) * (size_t)(cfg->adapt.mass_windows > 0 ? cfg->adapt.mass_windows + 3 : 3));
+  int n_seg = 0;
+  seg[n_seg++] = 0;
+  for (int t = 1; t < T; ++t)
+    if (NAME(mass_window_start)(&cfg->adapt, t)) seg[n_seg++] = t;
+  seg[n_seg] = T;
+
 #pragma omp parallel
   {
     NAME(ws_t) ws = NAME(ws_new)(D);
@@ -866,54 +923,64 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
 #pragma omp for schedule(static)
     for (int c = 0; c < C; ++c) lp[c] = NAME(logp_grad1)(ir, &ws, th + (size_t)c * D, gr + (size_t)c * D);
 
-    if (pooled) {
-      for (int t = 0; t < T; ++t) {
-#pragma omp for schedule(dynamic, 1)
-        for (int c = 0; c < C; ++c) {
-          NAME(nuts_out_t) o;
-          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[0].eps, step_scale,
-                                momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
-                                gr + (size_t)c * D, &lp[c], &o);
-          acc[c] = REXP(o.log_accept);
-          tot[c] += o.leapfrogs;
-          if (t >= B) {
-            size_t k = (size_t)(t - B) * C + c;
-            if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
-            if (lp_out) lp_out[k] = o.lp;
-            if (leapfrogs) leapfrogs[k] = o.leapfrogs;
-            if (diverging) diverging[k] = (uint8_t)o.diverging;
-            if (energy) energy[k] = o.energy;
-            if (log_accept) log_accept[k] = o.log_accept;
-            if (depth_out) depth_out[k] = o.depth;
-          }
-        }
+    for (int sg = 0; sg < n_seg; ++sg) {
+      const int ta = seg[sg], tb = seg[sg + 1];
+      if (sg > 0) {
 #pragma omp single
         {
-          /* reduce_logmeanexp over all chains, then exp: the arithmetic mean accept prob */
-          REAL s = 0;
-          for (int c = 0; c < C; ++c) s += acc[c];
-          NAME(da_update)(&da[0], &cfg->adapt, t, s / (REAL)C);
+          if (NAME(mass_update)(th, C, D, scale_buf))
+            for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_restart)(&da[c], ta);
         }
       }
-    } else {
+      if (pooled) {
+        for (int t = ta; t < tb; ++t) {
 #pragma omp for schedule(dynamic, 1)
-      for (int c = 0; c < C; ++c) {
-        for (int t = 0; t < T; ++t) {
-          NAME(nuts_out_t) o;
-          NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[c].eps, step_scale,
-                                momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
-                                gr + (size_t)c * D, &lp[c], &o);
-          NAME(da_update)(&da[c], &cfg->adapt, t, REXP(o.log_accept));
-          tot[c] += o.leapfrogs;
-          if (t >= B) {
-            size_t k = (size_t)(t - B) * C + c;
-            if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
-            if (lp_out) lp_out[k] = o.lp;
-            if (leapfrogs) leapfrogs[k] = o.leapfrogs;
-            if (diverging) diverging[k] = (uint8_t)o.diverging;
-            if (energy) energy[k] = o.energy;
-            if (log_accept) log_accept[k] = o.log_accept;
-            if (depth_out) depth_out[k] = o.depth;
+          for (int c = 0; c < C; ++c) {
+            NAME(nuts_out_t) o;
+            NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[0].eps, step_scale,
+                                  momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
+                                  gr + (size_t)c * D, &lp[c], &o);
+            acc[c] = REXP(o.log_accept);
+            tot[c] += o.leapfrogs;
+            if (t >= B) {
+              size_t k = (size_t)(t - B) * C + c;
+              if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
+              if (lp_out) lp_out[k] = o.lp;
+              if (leapfrogs) leapfrogs[k] = o.leapfrogs;
+              if (diverging) diverging[k] = (uint8_t)o.diverging;
+              if (energy) energy[k] = o.energy;
+              if (log_accept) log_accept[k] = o.log_accept;
+              if (depth_out) depth_out[k] = o.depth;
+            }
+          }
+#pragma omp single
+          {
+            /* reduce_logmeanexp over all chains, then exp: the arithmetic mean accept prob */
+            REAL s = 0;
+            for (int c = 0; c < C; ++c) s += acc[c];
+            NAME(da_update)(&da[0], &cfg->adapt, t, s / (REAL)C);
+          }
+        }
+      } else {
+#pragma omp for schedule(dynamic, 1)
+        for (int c = 0; c < C; ++c) {
+          for (int t = ta; t < tb; ++t) {
+            NAME(nuts_out_t) o;
+            NAME(nuts_transition)(ir, &ws, &nb, cfg, (uint32_t)(cfg->chain_offset + c), (uint32_t)t, da[c].eps, step_scale,
+                                  momenta ? momenta + ((size_t)t * C + c) * D : NULL, th + (size_t)c * D,
+                                  gr + (size_t)c * D, &lp[c], &o);
+            NAME(da_update)(&da[c], &cfg->adapt, t, REXP(o.log_accept));
+            tot[c] += o.leapfrogs;
+            if (t >= B) {
+              size_t k = (size_t)(t - B) * C + c;
+              if (states) memcpy(states + k * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
+              if (lp_out) lp_out[k] = o.lp;
+              if (leapfrogs) leapfrogs[k] = o.leapfrogs;
+              if (diverging) diverging[k] = (uint8_t)o.diverging;
+              if (energy) energy[k] = o.energy;
+              if (log_accept) log_accept[k] = o.log_accept;
+              if (depth_out) depth_out[k] = o.depth;
+            }
           }
         }
       }
@@ -922,6 +989,9 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
     NAME(nuts_buf_free)(&nb);
     NAME(ws_free)(&ws);
   }
+  free(seg);
+  if (mass_scale_out && scale_buf) memcpy(mass_scale_out, scale_buf, sizeof(REAL) * (size_t)D);
+  free(scale_buf);
   for (int c = 0; c < C; ++c) {
     if (step_size_out) step_size_out[c] = da[pooled ? 0 : c].eps;
     if (total_leapfrogs) total_leapfrogs[c] = tot[c];

@@ -33,7 +33,7 @@ EXPORTS = [
     "pm4_logp_grad",
     "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_prior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
-    "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm", "pm4_model_set_trace_sink",
+    "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm", "pm4_model_set_trace_sink", "pm4_model_get_mass_scale",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
     "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches", "pm4_gp_sample", "pm4_gp_predictive", "pm4_gp_points",
 ]
@@ -101,6 +101,7 @@ def load_library():
     L.pm4_comm_destroy.argtypes = [vp]
     L.pm4_model_attach_comm.argtypes = [vp, vp]
     L.pm4_model_set_trace_sink.argtypes = [vp, vp, i32, vp]
+    L.pm4_model_get_mass_scale.argtypes = [vp, i32, vp, vp]
     _lib = L
     return L
 
@@ -332,6 +333,11 @@ class DeviceModel:
         if host is not None:
             out["states_host"] = host
             out["states_host_ready"] = copy_stream.synchronize
+        if cfg.adapt.enabled and cfg.adapt.mass_windows > 0:  # the per-dimension step scale the run ended with
+            out["mass_scale"] = self.empty((D,), td)
+            with torch.cuda.device(self._dev()):
+                self._check(self.lib.pm4_model_get_mass_scale(self.handle, _code(dtype), self._p(out["mass_scale"]),
+                                                              self._stream()))
         out["_keepalive"] = (th0, sc, mom)
         return out
 

@@ -18,6 +18,8 @@ class AdaptCfg(ctypes.Structure):
         ("enabled", ctypes.c_int32),
         ("kind", ctypes.c_int32),
         ("adaptation_rate", ctypes.c_double),
+        ("mass_windows", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
     ]
 
 
@@ -55,10 +57,10 @@ class NUTSCfg(ctypes.Structure):
 
 def make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=0, target_accept_prob=0.75,
                exploration_shrinkage=0.05, step_count_smoothing=10.0, decay_rate=0.75,
-               enabled=True, kind=PM4_ADAPT_DUAL_AVERAGING, adaptation_rate=0.01) -> AdaptCfg:
+               enabled=True, kind=PM4_ADAPT_DUAL_AVERAGING, adaptation_rate=0.01, mass_windows=0) -> AdaptCfg:
     return AdaptCfg(int(mode), int(num_adaptation_steps), float(target_accept_prob),
                     float(exploration_shrinkage), float(step_count_smoothing), float(decay_rate),
-                    int(bool(enabled)), int(kind), float(adaptation_rate))
+                    int(bool(enabled)), int(kind), float(adaptation_rate), int(mass_windows), 0)
 
 
 def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_depth=10,

@@ -109,6 +109,8 @@ struct pm4_model {
   int32_t owned_hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // one-shot trace sink of the next NUTS run (pm4_model_set_trace_sink): the draws leave the device in slabs
   // on a copy stream while the persistent kernel keeps sampling
+  void* mass_scale = nullptr;  // [D] reals: step scale the last run with mass windows ended with
+  int mass_scale_dtype = -1;
   void* sink_host = nullptr;
   int sink_slabs = 0;
   cudaStream_t sink_stream = nullptr;
@@ -482,6 +484,8 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
   cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
   for (GlmTerm& g : m->glm) cudaFree(g.d_xt);
   cudaFree(m->glm_work); cudaFree(m->d_glm_err); cudaFree(m->gp_work);
+  cudaFree(m->mass_scale);
+  if (m->sink_event) cudaEventDestroy(m->sink_event);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   if (m->module) dlclose(m->module);
   delete m;
@@ -499,6 +503,14 @@ extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n
   CU(cudaDeviceSynchronize());
   int rc = upload_pools(m, dataf, n_dataf, datai, n_datai);
   return rc != PM4_OK ? rc : upload_glm(m, dataf);
+}
+
+extern "C" int pm4_model_get_mass_scale(pm4_model_t* m, int dtype, void* out_dev, void* stream) {
+  if (!m || !out_dev) return fail(PM4_EINVAL, "pm4_model_get_mass_scale: null argument");
+  if (!m->mass_scale || m->mass_scale_dtype != dtype) return fail(PM4_EINVAL, "no NUTS run with mass_windows > 0 in this dtype yet");
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(out_dev, m->mass_scale, (dtype == PM4_F64 ? 8 : 4) * (size_t)m->D, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return PM4_OK;
 }
 
 extern "C" int pm4_model_set_trace_sink(pm4_model_t* m, void* states_host, int n_slabs, void* copy_stream) {
@@ -634,6 +646,70 @@ extern "C" int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64
   return PM4_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// diagonal mass-matrix windows (pm4_adapt_cfg_t.mass_windows): cross-chain standard deviation of the
+// unconstrained states -> per-dimension step scale, dual averaging restarted from the current epsilon
+// ------------------------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) mass_logsd_kernel(const real* __restrict__ th, int C, int DP, double* __restrict__ logsd,
+                                                          int* __restrict__ bad) {
+  __shared__ double red[256];
+  const int d = blockIdx.x;
+  double s = 0;
+  for (int c = threadIdx.x; c < C; c += 256) s += (double)th[(size_t)c * DP + d];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double mean = red[0] / C;
+  __syncthreads();
+  double v = 0;
+  for (int c = threadIdx.x; c < C; c += 256) { const double e = (double)th[(size_t)c * DP + d] - mean; v += e * e; }
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double var = red[0] / C;
+    if (!(var > 0) || isinf(var) || isnan(var)) atomicExch(bad, 1);
+    else logsd[d] = 0.5 * log(var);
+  }
+}
+
+// one block: geometric-mean normalisation, new scale, restart of every dual-averaging state, window start word
+template <typename real>
+__global__ void __launch_bounds__(256) mass_finish_kernel(const double* __restrict__ logsd, int* __restrict__ bad, int D,
+                                                           real* __restrict__ scale, real* __restrict__ da, int n_da,
+                                                           int32_t* __restrict__ da_t0, int t0) {
+  __shared__ double red[256];
+  if (*bad) {  // some dimension has no finite positive spread yet: keep the scale and the recursion
+    __syncthreads();
+    if (threadIdx.x == 0) *bad = 0;
+    return;
+  }
+  double s = 0;
+  for (int d = threadIdx.x; d < D; d += 256) s += logsd[d];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double mean = red[0] / D;
+  for (int d = threadIdx.x; d < D; d += 256) scale[d] = (real)exp(logsd[d] - mean);
+  for (int c = threadIdx.x; c < n_da; c += 256) {
+    real* p = da + (size_t)c * 4;
+    p[1] = 0;
+    p[2] = 0;
+    p[3] = (real)log(10.0 * (double)p[0]);
+  }
+  if (threadIdx.x == 0) *da_t0 = t0;
+}
+
 static size_t real_size(int dtype) { return dtype == PM4_F64 ? 8 : 4; }
 
 extern "C" int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth) {
@@ -681,7 +757,39 @@ int fill_adapt(pm4_mod_run_t& r, const pm4_adapt_cfg_t& a) {
 // (transitions 0..num_adapt), then a few persistent launches for the rest.  NUTS chains differ a lot
 // in cost (per-chain step sizes): after each phase the chains are ranked by the leapfrogs they took
 // and the next launch hands them out longest-first (`order_buf`: int32[C], `r.launch_leaps` set).
-int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, int32_t* order_buf, cudaStream_t st) {
+struct MassCtx {  // device buffers of the mass-matrix windows of one run (null when off)
+  int windows = 0, num_adapt = 0;
+  double* logsd = nullptr;
+  int* bad = nullptr;
+  void* scale = nullptr;
+};
+
+// window starts in (lo, hi): w_k = num_adapt * k / (K + 1), k = 1 .. K
+static std::vector<int> mass_cuts(const MassCtx& mc, int lo, int hi) {
+  std::vector<int> out;
+  for (int k = 1; k <= mc.windows; ++k) {
+    const int w = (int)(((int64_t)mc.num_adapt * k) / (mc.windows + 1));
+    if (w > 0 && w < mc.num_adapt && w > lo && w < hi && (out.empty() || out.back() != w)) out.push_back(w);
+  }
+  return out;
+}
+
+static int mass_window(pm4_model* m, int dtype, const pm4_mod_run_t& r, const MassCtx& mc, int t0, cudaStream_t st) {
+  const int n_da = r.adapt_pooled ? 1 : r.C;
+  if (dtype == PM4_F64) {
+    mass_logsd_kernel<double><<<m->D, 256, 0, st>>>((const double*)r.th, r.C, m->info.DP, mc.logsd, mc.bad);
+    mass_finish_kernel<double><<<1, 256, 0, st>>>(mc.logsd, mc.bad, m->D, (double*)mc.scale, (double*)r.da, n_da, (int32_t*)r.da_t0, t0);
+  } else {
+    mass_logsd_kernel<float><<<m->D, 256, 0, st>>>((const float*)r.th, r.C, m->info.DP, mc.logsd, mc.bad);
+    mass_finish_kernel<float><<<1, 256, 0, st>>>(mc.logsd, mc.bad, m->D, (float*)mc.scale, (float*)r.da, n_da, (int32_t*)r.da_t0, t0);
+  }
+  g_launches += 2;
+  CU(cudaGetLastError());
+  return PM4_OK;
+}
+
+int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, int32_t* order_buf, cudaStream_t st,
+          const MassCtx& mc = MassCtx()) {
   pm4m_run_fn f = nuts ? m->f_nuts : m->f_hmc;
   int t = 0;
   r.order = nullptr;
@@ -696,16 +804,25 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
   if (r.adapt_enabled && r.adapt_pooled && nuts && (m->info.caps & PM4_CAP_PERSISTENT_LOCKSTEP) && r.sync && !no_persistent) {
     // the module runs the lock-step transitions in one cooperative launch (grid barrier + pooled update in the kernel)
     const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
-    r.t_begin = 0;
-    r.t_count = coupled;
-    r.rounds = coupled;
-    r.tb = 0;
-    MOD(f(dtype, &r, wpb, st), "nuts (lock-step rounds)");
+    std::vector<int> cuts = mass_cuts(mc, 0, coupled);  // a mass-matrix window starts a new launch
+    cuts.push_back(coupled);
+    for (int cut : cuts) {
+      if (t > 0)
+        if (int rc2 = mass_window(m, dtype, r, mc, t, st)) return rc2;
+      r.t_begin = t;
+      r.t_count = cut - t;
+      r.rounds = cut - t;
+      r.tb = 0;
+      MOD(f(dtype, &r, wpb, st), "nuts (lock-step rounds)");
+      t = cut;
+    }
     r.rounds = 0;
-    t = coupled;
   } else if (r.adapt_enabled && r.adapt_pooled) {
     const int coupled = r.num_adapt + 1 < T ? r.num_adapt + 1 : T;
+    const std::vector<int> cuts = mass_cuts(mc, 0, coupled);
     for (; t < coupled; ++t) {
+      if (std::find(cuts.begin(), cuts.end(), t) != cuts.end())
+        if (int rc2 = mass_window(m, dtype, r, mc, t, st)) return rc2;
       r.t_begin = t;
       r.t_count = 1;
       MOD(f(dtype, &r, wpb, st), nuts ? "nuts (lock-step)" : "hmc (lock-step)");
@@ -724,6 +841,13 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
     if (freeze > (ends.empty() ? t : ends.back()) + 10 && freeze < T - 10) ends.push_back(freeze);
   }
   ends.push_back(T);
+  {  // per-chain step sizes: the mass-matrix windows cut the persistent launches
+    std::vector<int> cuts = mass_cuts(mc, t, T);
+    ends.insert(ends.end(), cuts.begin(), cuts.end());
+    std::sort(ends.begin(), ends.end());
+    ends.erase(std::unique(ends.begin(), ends.end()), ends.end());
+  }
+  const std::vector<int> window_starts = mass_cuts(mc, t, T);
   // persistent launches of the warp-per-chain path hand out (chain, block of tb transitions) items
   static const int tb_env = getenv("PM4_TB") ? atoi(getenv("PM4_TB")) : 10;
   r.tb = nuts && r.progress ? tb_env : 0;
@@ -755,6 +879,8 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
   };
   for (size_t k = 0; k < ends.size(); ++k) {
     if (ends[k] <= t) continue;
+    if (std::find(window_starts.begin(), window_starts.end(), t) != window_starts.end())
+      if (int rc2 = mass_window(m, dtype, r, mc, t, st)) return rc2;
     r.t_begin = t;
     r.t_count = ends[k] - t;
     MOD(f(dtype, &r, wpb, st), nuts ? "nuts" : "hmc");
@@ -913,8 +1039,37 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
   r.total_leapfrogs = total_leapfrogs_dev;
 
   fill_comm(m, r);
+  void* t0w = nullptr;  // first transition of the current dual-averaging window (mass-matrix windows move it)
+  if ((rc = buf.get(&t0w, 16))) return rc;
+  CU(cudaMemsetAsync(t0w, 0, 16, st));
+  r.da_t0 = (const int32_t*)t0w;
+  MassCtx mc;
+  if (r.adapt_enabled && cfg->adapt.mass_windows > 0) {
+    mc.windows = cfg->adapt.mass_windows;
+    mc.num_adapt = r.num_adapt;
+    void *ls = nullptr, *bad = nullptr;
+    if ((rc = buf.get(&ls, sizeof(double) * (size_t)m->D))) return rc;
+    if ((rc = buf.get(&bad, 16))) return rc;
+    CU(cudaMemsetAsync(bad, 0, 16, st));
+    mc.logsd = (double*)ls;
+    mc.bad = (int*)bad;
+    // the scale outlives the run (pm4_model_get_mass_scale): owned by the model
+    if (m->mass_scale && m->mass_scale_dtype != dtype) { cudaFree(m->mass_scale); m->mass_scale = nullptr; }
+    if (!m->mass_scale) CU(cudaMalloc(&m->mass_scale, rs * (size_t)m->D));
+    m->mass_scale_dtype = dtype;
+    mc.scale = m->mass_scale;
+    if (step_scale_dev) CU(cudaMemcpyAsync(mc.scale, step_scale_dev, rs * (size_t)m->D, cudaMemcpyDeviceToDevice, st));
+    else {
+      std::vector<double> ones64((size_t)m->D, 1.0);
+      std::vector<float> ones32((size_t)m->D, 1.0f);
+      CU(cudaMemcpyAsync(mc.scale, dtype == PM4_F64 ? (const void*)ones64.data() : (const void*)ones32.data(), rs * (size_t)m->D,
+                         cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
+    }
+    r.step_scale = mc.scale;
+  }
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
-  if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, (int32_t*)order, st))) return rc;
+  if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, (int32_t*)order, st, mc))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   if (r.adapt_enabled && r.adapt_pooled) return check_comm(m, st);
   return PM4_OK;

@@ -268,6 +268,7 @@ template <typename real> struct RunParams {
   int team_reals, n_slots, n_fast, tb, rounds;
   int32_t* progress;
   int32_t* sync;
+  const int32_t* da_t0;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay, adapt_rate, rw_scale;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -305,7 +306,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
   p.adapt_kind = r.adapt_kind; p.random_walk = r.random_walk;
   p.adapt_rate = (real)r.adapt_rate; p.rw_scale = (real)r.rw_scale;
-  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress; p.rounds = r.rounds; p.sync = r.sync;
+  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress; p.rounds = r.rounds; p.sync = r.sync; p.da_t0 = r.da_t0;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -338,7 +339,7 @@ template <typename real> struct DualAvg {
       if (t < a.num_adapt) eps = accept > a.target_accept ? eps * ((real)1 + a.adapt_rate) : eps / ((real)1 + a.adapt_rate);
       return;
     }
-    const real step = (real)(t + 1);
+    const real step = (real)(t + 1 - (a.da_t0 ? __ldcg(a.da_t0) : 0));  // the recursion restarts at a mass-matrix window
     error_sum += a.target_accept - accept;
     const real log_eps = log_shrink_target - error_sum * m_sqrt(step) / ((a.smoothing + step) * a.shrinkage);
     const real eta = m_pow(step, -a.decay);

@@ -42,7 +42,7 @@ if not _log.handlers:
 _log.setLevel(logging.INFO)
 
 # keyword arguments of this backend that the reference does not have
-_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block", "comm", "trace_slabs")
+_BACKEND_KWARGS = ("dtype", "device", "chain_offset", "warps_per_block", "comm", "trace_slabs", "mass_windows")
 
 
 def register_sampler(cls):
@@ -251,10 +251,14 @@ class _BaseSampler(metaclass=abc.ABCMeta):
             return make_adapt(mode=mode, num_adaptation_steps=spec.num_adaptation_steps,
                               target_accept_prob=spec.target_accept_prob, kind=PM4_ADAPT_SIMPLE,
                               adaptation_rate=spec.adaptation_rate, enabled=True)
+        # mass_windows (backend extension, NUTS): diagonal mass-matrix adaptation from the cross-chain spread at that many
+        # points of the burn-in -- what the reference's radon notebook emulates by passing posterior standard deviations
+        # as per-dimension step sizes (notebooks/radon_hierarchical.ipynb:123-146)
         return make_adapt(mode=mode, num_adaptation_steps=spec.num_adaptation_steps,
                           target_accept_prob=spec.target_accept_prob,
                           exploration_shrinkage=spec.exploration_shrinkage,
-                          step_count_smoothing=spec.step_count_smoothing, decay_rate=spec.decay_rate, enabled=True)
+                          step_count_smoothing=spec.step_count_smoothing, decay_rate=spec.decay_rate, enabled=True,
+                          mass_windows=int(self.backend_kwargs.get("mass_windows", 0)) if self._name.startswith("nuts") else 0)
 
     def _check_chain_kwargs(self):
         ck = self.chain_kwargs
@@ -377,7 +381,7 @@ class NUTS(_BaseSampler):
         slabs = int(self.backend_kwargs.get("trace_slabs", 8 if trace_bytes >= (64 << 20) else 0))
         out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale, stream_trace=slabs)
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
-                              depth=out["depth"], kernel="nuts")
+                              depth=out["depth"], kernel="nuts", mass_scale=out.get("mass_scale"))
         self._last_states = out["states"]
         stats = self.trace_fn(out["states"], out)
         if "states_host" in out:

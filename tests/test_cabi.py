@@ -50,7 +50,8 @@ def test_struct_layouts_match_the_header(tmp_path):
                              "plans", "n_planf", "planf", "n_plani", "plani", "team_warps", "part_reals",
                              "elem_off", "spart_off", "phdr_off"]),
         "pm4_adapt_cfg_t": (_cstructs.AdaptCfg, ["mode", "num_adaptation_steps", "target_accept_prob",
-                                                 "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled"]),
+                                                 "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled",
+                                                 "kind", "adaptation_rate", "mass_windows"]),
         "pm4_hmc_cfg_t": (_cstructs.HMCCfg, ["C", "num_results", "num_burnin", "num_leapfrog_steps", "step_size",
                                              "seed", "adapt", "warps_per_block", "chain_offset"]),
         "pm4_nuts_cfg_t": (_cstructs.NUTSCfg, ["C", "num_results", "num_burnin", "max_tree_depth", "max_energy_diff",

@@ -658,3 +658,29 @@ def test_sample_chain_step_accounting_and_averaged_step_size(oracle_mod):
             eps = math.exp(log_avg)
     np.testing.assert_allclose(out["step_size"][0], eps, rtol=1e-10)
     assert out["total_leapfrogs"][0] == out["leapfrogs"].sum()  # every transition of the call is accounted for
+
+
+def test_diagonal_mass_matrix_windows_recover_the_scales(oracle_mod):
+    """pm4_adapt_cfg_t.mass_windows: on a Gaussian whose coordinates differ by a factor of 400 in
+    scale the adapted step scale is proportional to the standard deviations and the trees shrink from hundreds of
+    leapfrogs to a handful; the draws are still N(0, diag(sigma^2))."""
+    sig = np.array([0.05, 0.3, 1.0, 4.0, 20.0])
+
+    @pm.model
+    def m():
+        yield pm.Normal("x", np.zeros(5), sig)
+
+    ir, _, _ = lower_model(m())
+    res = {}
+    for K in (0, 4):
+        cfg = make_nuts_cfg(64, 200, 300, step_size=0.1, seed=1,
+                            adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=300, mass_windows=K))
+        res[K] = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(5), dtype=np.float64)
+    assert np.all(res[0]["mass_scale"] == 1.0)
+    s = res[4]["mass_scale"]
+    np.testing.assert_allclose(np.exp(np.log(s).mean()), 1.0, rtol=1e-12)  # geometric mean 1
+    np.testing.assert_allclose(s / s[2], sig / sig[2], rtol=0.25)
+    assert res[4]["leapfrogs"].mean() < 0.1 * res[0]["leapfrogs"].mean()
+    x = res[4]["states"].reshape(-1, 5)
+    np.testing.assert_allclose(x.std(axis=0), sig, rtol=0.05)
+    assert res[4]["diverging"].mean() == 0.0
