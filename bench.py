@@ -251,9 +251,71 @@ def cpu_baseline(ir, args):
     }
 
 
+def tfp_reference_rate(args):
+    """when TensorFlow Probability is importable on this box (it is not in this image: no wheel in
+    /opt/wheelhouse, no network), time the sampler the reference really runs -- tfp.mcmc.NoUTurnSampler under
+    DualAveragingStepSizeAdaptation, vectorised over chains, CPU only -- on the same synthetic radon inputs.  Returns
+    (grad-evals, seconds, description) or None."""
+    if WORKLOAD != "radon919":
+        return None
+    try:
+        os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
+        import tensorflow as tf
+        import tensorflow_probability as tfp
+    except Exception:
+        return None
+    from pymc4_b200 import benchmodels as M
+
+    idx, x, y, G = M.radon_synthetic(N_OBS, N_GROUPS)
+    idx_t, x_t, y_t = tf.constant(idx), tf.constant(x, tf.float32), tf.constant(y, tf.float32)
+    tfd = tfp.distributions
+
+    def logp(mu_a, mu_b, a, b, ls_a, ls_b, l_eps):  # the reference's joint density in unconstrained space
+        sa, sb, eps = tf.exp(ls_a), tf.exp(ls_b), tf.exp(l_eps)
+        lp = tfd.Normal(0., 1.).log_prob(mu_a) + tfd.Normal(0., 1.).log_prob(mu_b)
+        lp += tfd.HalfCauchy(0., 1.).log_prob(sa) + ls_a + tfd.HalfCauchy(0., 1.).log_prob(sb) + ls_b
+        lp += tfd.HalfCauchy(0., 1.).log_prob(eps) + l_eps
+        lp += tf.reduce_sum(tfd.Normal(mu_a[..., None], sa[..., None]).log_prob(a), -1)
+        lp += tf.reduce_sum(tfd.Normal(mu_b[..., None], sb[..., None]).log_prob(b), -1)
+        est = tf.gather(a, idx_t, axis=-1) + tf.gather(b, idx_t, axis=-1) * x_t
+        return lp + tf.reduce_sum(tfd.Normal(est, eps[..., None]).log_prob(y_t), -1)
+
+    C = args.cpu_chains or 64
+    init = [tf.zeros([C]), tf.zeros([C]), tf.zeros([C, G]), tf.zeros([C, G]), tf.zeros([C]), tf.zeros([C]), tf.zeros([C])]
+    kernel = tfp.mcmc.DualAveragingStepSizeAdaptation(
+        tfp.mcmc.NoUTurnSampler(logp, step_size=args.step_size), num_adaptation_steps=args.burn_in,
+        step_size_setter_fn=lambda pkr, s: pkr._replace(step_size=s), step_size_getter_fn=lambda pkr: pkr.step_size,
+        log_accept_prob_getter_fn=lambda pkr: pkr.log_accept_ratio)
+
+    @tf.function(autograph=False)
+    def run():
+        return tfp.mcmc.sample_chain(args.draws, init, kernel=kernel, num_burnin_steps=args.burn_in,
+                                     trace_fn=lambda _, pkr: pkr.inner_results.leapfrogs_taken, seed=args.seed)
+
+    run()  # trace + warm-up
+    t0 = time.perf_counter()
+    _, leaps = run()
+    dt = time.perf_counter() - t0
+    # burn-in leapfrogs are not traced by sample_chain: scale the kept draws' count to all transitions
+    evals = float(tf.reduce_sum(leaps)) * (args.burn_in + args.draws) / max(args.draws, 1)
+    return evals, dt, "tfp.mcmc.NoUTurnSampler + DualAveragingStepSizeAdaptation (TF %s, TFP %s), %d chains, CPU" % (
+        tf.__version__, tfp.__version__, C)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    tfp_run = tfp_reference_rate(args)
+    if tfp_run is not None:
+        evals, secs, what = tfp_run
+        value = evals / secs
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 1, "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference", "sample": what},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     _, ir = build_model()
     from oracle import pm4_oracle

@@ -10,6 +10,7 @@
 // (/root/reference/pymc4/mcmc/samplers.py:172-189).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -23,6 +24,12 @@
 #include "pm4_module.h"
 
 namespace {
+
+// NVTX range around a C-ABI call (header-only NVTX3: a no-op unless a profiler injects itself)
+struct Nvtx {
+  explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 thread_local int64_t g_launches = 0;
@@ -337,6 +344,7 @@ static int upload_pools(pm4_model* m, const double* dataf, int64_t nf, const int
 }
 
 extern "C" int pm4_model_create(const pm4_ir_t* ir, const char* module_path, int device, pm4_model_t** out) {
+  Nvtx nvtx_range("pm4_model_create");
   if (!ir || !module_path || !out) return fail(PM4_EINVAL, "pm4_model_create: null argument");
   if (ir->abi_version != PM4_ABI_VERSION) return fail(PM4_EINVAL, "IR ABI version %d != %d", ir->abi_version, PM4_ABI_VERSION);
   if (ir->D <= 0 || ir->n_terms <= 0) return fail(PM4_EINVAL, "IR has no free variables or no terms");
@@ -495,6 +503,7 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
 extern "C" int pm4_model_dim(const pm4_model_t* m) { return m ? m->D : PM4_EINVAL; }
 
 extern "C" int pm4_model_set_data(pm4_model_t* m, const double* dataf, int64_t n_dataf, const int32_t* datai, int64_t n_datai) {
+  Nvtx nvtx_range("pm4_model_set_data");
   if (!m) return fail(PM4_EINVAL, "null model");
   if (n_dataf != m->n_dataf || n_datai != m->n_datai)
     return fail(PM4_EINVAL, "pool sizes differ from the model's (%lld/%lld vs %lld/%lld)", (long long)n_dataf,
@@ -530,6 +539,7 @@ extern "C" int pm4_model_set_trace_sink(pm4_model_t* m, void* states_host, int n
 }
 
 extern "C" int pm4_model_set_plans(pm4_model_t* m, const pm4_ir_t* ir) {
+  Nvtx nvtx_range("pm4_model_set_plans");
   if (!m || !ir) return fail(PM4_EINVAL, "null argument");
   if (ir->n_plans != m->n_plans || ir->n_planf != m->n_planf || ir->n_plani != m->n_plani)
     return fail(PM4_EINVAL, "plan pool sizes differ from the model's");
@@ -545,6 +555,7 @@ static int check_dtype(const pm4_model* m, int dtype) {
 }
 
 extern "C" int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta_dev, void* lp_dev, void* grad_dev, void* stream) {
+  Nvtx nvtx_range("pm4_logp_grad");
   if (!m || !theta_dev || !lp_dev || C < 0) return fail(PM4_EINVAL, "pm4_logp_grad: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -560,6 +571,7 @@ extern "C" int pm4_logp_grad(pm4_model_t* m, int dtype, int C, const void* theta
 }
 
 extern "C" int pm4_deterministics(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, void* out_dev, void* stream) {
+  Nvtx nvtx_range("pm4_deterministics");
   if (!m || M < 0) return fail(PM4_EINVAL, "pm4_deterministics: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -574,6 +586,7 @@ extern "C" int pm4_deterministics(pm4_model_t* m, int dtype, int64_t M, const vo
 extern "C" int pm4_model_ll_row(const pm4_model_t* m) { return m ? m->info.ll_row : PM4_EINVAL; }
 
 extern "C" int pm4_log_likelihood(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, void* out_dev, void* stream) {
+  Nvtx nvtx_range("pm4_log_likelihood");
   if (!m || M < 0) return fail(PM4_EINVAL, "pm4_log_likelihood: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -591,6 +604,7 @@ extern "C" int pm4_log_likelihood(pm4_model_t* m, int dtype, int64_t M, const vo
 
 extern "C" int pm4_posterior_predictive(pm4_model_t* m, int dtype, int64_t M, const void* theta_dev, uint64_t seed,
                                         void* out_dev, void* stream) {
+  Nvtx nvtx_range("pm4_posterior_predictive");
   if (!m || M < 0) return fail(PM4_EINVAL, "pm4_posterior_predictive: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -609,6 +623,7 @@ extern "C" int pm4_gp_points(const pm4_model_t* m, int which) {
 
 extern "C" int pm4_gp_predictive(pm4_model_t* m, int dtype, int which, int64_t M, const void* theta_dev, uint64_t seed,
                                  void* out_dev, void* stream) {
+  Nvtx nvtx_range("pm4_gp_predictive");
   if (!m || M < 0 || which < 0 || which >= (int)m->gp.size()) return fail(PM4_EINVAL, "pm4_gp_predictive: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -635,6 +650,7 @@ extern "C" int pm4_gp_predictive(pm4_model_t* m, int dtype, int which, int64_t M
 
 extern "C" int pm4_prior_predictive(pm4_model_t* m, int dtype, int64_t M, uint64_t seed, void* x_dev, void* obs_dev,
                                     void* stream) {
+  Nvtx nvtx_range("pm4_prior_predictive");
   if (!m || M < 0) return fail(PM4_EINVAL, "pm4_prior_predictive: bad argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -991,6 +1007,7 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
                             const void* step_scale_dev, const void* momenta_dev, void* states_dev, void* lp_dev,
                             int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev, void* log_accept_dev,
                             int32_t* depth_dev, void* step_size_dev, int64_t* total_leapfrogs_dev, void* stream) {
+  Nvtx nvtx_range("pm4_nuts_run");
   if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_nuts_run: null argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
@@ -1149,6 +1166,7 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
                            const void* step_scale_dev, const void* momenta_dev, const void* uniforms_dev,
                            void* states_dev, void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev,
                            void* step_size_dev, void* traj_dev, void* stream) {
+  Nvtx nvtx_range("pm4_hmc_run");
   if (!m || !cfg || !theta0_dev) return fail(PM4_EINVAL, "pm4_hmc_run: null argument");
   int rc = check_dtype(m, dtype);
   if (rc) return rc;
