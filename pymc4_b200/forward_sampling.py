@@ -147,15 +147,15 @@ def sample_posterior_predictive(
     obs_terms = {t.label: t for t in ir.terms if t.observed}
     if var_names is None:
         var_names = list(obs_terms)
-    unknown = [v for v in var_names if v not in obs_terms]
-    if unknown:
-        defined = {rv.name for rv in ir.rvs} | {d.name for d in ir.dets} | set(obs_terms)
-        if not set(unknown) <= defined:
-            raise KeyError("The supplied var_names = {} are not defined in the model.\nDefined variables are = {}"
-                           .format(sorted(set(unknown) - defined), sorted(defined)))
-        raise NotImplementedError("posterior predictive draws are built for the observed variables only; "
-                                  "{} are already in the trace".format(unknown))
     posterior = trace.posterior
+    # var_names may also name variables that are NOT re-drawn (reference forward_sampling.py:318-323: the values of
+    # the executed model, i.e. the posterior values the trace was passed in with, and recomputed deterministics)
+    det_by_name = {d.name: d for d in ir.dets}
+    unknown = [v for v in var_names if v not in obs_terms and v not in det_by_name and v not in posterior]
+    if unknown:
+        defined = {rv.name for rv in ir.rvs} | set(det_by_name) | set(obs_terms)
+        raise KeyError("The supplied var_names = {} are not defined in the model.\nDefined variables are = {}"
+                       .format(sorted(unknown), sorted(defined)))
     missing = [rv.name for rv in ir.rvs if rv.name not in posterior]
     if missing:
         raise TypeError("the trace lacks the sampled variables {} of the model".format(missing))
@@ -173,7 +173,17 @@ def sample_posterior_predictive(
     draws = dm.posterior_predictive(theta, seed=seed, dtype=np.dtype(dtype)).cpu().numpy()
     gp_index = {t.label: k for k, t in enumerate(ir.gp_terms)}
     output = {}
+    dets = None
     for name in var_names:
+        if name not in obs_terms:
+            if name in det_by_name:  # deterministics (and back-transformed variables) are recomputed from the draws
+                if dets is None:
+                    dets = dm.deterministics(theta, dtype=np.dtype(dtype)).cpu().numpy()
+                d = det_by_name[name]
+                output[name] = dets[..., d.out_offset: d.out_offset + d.n].reshape(tuple(lead) + tuple(d.shape))
+            else:  # a sampled variable: its posterior values
+                output[name] = np.asarray(posterior[name])
+            continue
         t = obs_terms[name]
         if name in gp_index:  # MvNormal observation of a GP model: a vector per draw, loc + chol(K(theta)) z
             output[name] = dm.gp_predictive(theta, seed=seed, dtype=np.dtype(dtype), which=gp_index[name]).cpu().numpy()

@@ -165,6 +165,15 @@ def test_sample_posterior_predictive():
         pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=["schools_pm4/nope"])
     with pytest.raises(ValueError):
         pm.sample_posterior_predictive(M.schools_pm4(), trace, var_names=[])
+    # var_names may name variables that are not re-drawn: sampled variables come back with their posterior values,
+    # back-transformed variables / deterministics are recomputed from the draws (reference forward_sampling.py:318-323)
+    mixed = pm.sample_posterior_predictive(M.schools_pm4(), trace, seed=1, inplace=False,
+                                           var_names=["schools_pm4/obs", "schools_pm4/mu", "schools_pm4/tau"])
+    pp = mixed.posterior_predictive
+    assert sorted(pp) == ["schools_pm4/mu", "schools_pm4/obs", "schools_pm4/tau"]
+    np.testing.assert_array_equal(pp["schools_pm4/mu"], post["schools_pm4/mu"])
+    np.testing.assert_allclose(pp["schools_pm4/tau"], np.exp(post["schools_pm4/__log_tau"]), rtol=1e-5)
+    assert np.array_equal(pp["schools_pm4/obs"], ppc["schools_pm4/obs"])
 
 
 def test_sample_prior_predictive():
