@@ -3,8 +3,11 @@
 ``MvNormal`` mirrors /root/reference/pymc4/distributions/multivariate.py:159-199 (loc, covariance_matrix ->
 ``tfd.MultivariateNormalFullCovariance``).  On the device it is built for the marginal GP regression of
 BASELINE configs[3]: an *observed* vector whose covariance is ``ExpQuad(l, a)(X, X) + noise * I`` with free
-scalar hyper-parameters (pymc4_b200/ir.py: GP; csrc/pm4_gp.cu).  Host-side ``log_prob`` / ``sample`` work for
-any concrete covariance.
+scalar hyper-parameters (pymc4_b200/ir.py: GP; csrc/pm4_gp.cu).  ``MvNormalCholesky`` mirrors :331-375 (loc, scale_tril ->
+``tfd.MultivariateNormalTriL``).  With a CONSTANT covariance / Cholesky factor both also run as latent
+(sampled) variables or as observations with a free ``loc``: the quadratic form over the constant precision
+matrix is lowered to an element-wise potential over the k (k + 1) / 2 index pairs (pymc4_b200/ir.py:
+_mvn_constant_term).  Host-side ``log_prob`` / ``sample`` work for any concrete covariance.
 """
 import math
 
@@ -12,7 +15,7 @@ import numpy as np
 
 from .distribution import ContinuousDistribution
 
-__all__ = ["MvNormal"]
+__all__ = ["MvNormal", "MvNormalCholesky"]
 
 
 class MvNormal(ContinuousDistribution):
@@ -59,3 +62,31 @@ class MvNormal(ContinuousDistribution):
         L = np.linalg.cholesky(covariance_matrix)
         z = rng.standard_normal(shape)
         return loc + z @ L.T
+
+
+class MvNormalCholesky(MvNormal):
+    """Multivariate normal parameterised by ``loc`` and the lower-triangular Cholesky factor ``scale_tril`` of its
+    covariance (reference multivariate.py:331-375)."""
+
+    _kind = "mvn_chol"
+    _param_names = ("loc", "scale_tril")
+
+    def __init__(self, name, loc, scale_tril, **kwargs):
+        ContinuousDistribution.__init__(self, name, loc=loc, scale_tril=scale_tril, **kwargs)
+        L = self.params["scale_tril"]
+        if L.ndim != 2 or L.shape[0] != L.shape[1]:
+            raise ValueError("scale_tril must be square [k, k], got shape {}".format(L.shape))
+        if self.params["loc"].ndim > 1 or (self.params["loc"].ndim == 1 and self.params["loc"].shape[0] != L.shape[0]):
+            raise ValueError("loc must be a scalar or a vector of length {}".format(L.shape[0]))
+
+    @property
+    def event_shape(self):
+        return (self.params["scale_tril"].shape[0],)
+
+    def _log_prob_numpy(self, value, loc, scale_tril):
+        L = np.tril(scale_tril)
+        return MvNormal._log_prob_numpy(self, value, loc, L @ L.T)
+
+    def _sample_numpy(self, rng, shape, loc, scale_tril):
+        z = rng.standard_normal(shape)
+        return loc + z @ np.tril(scale_tril).T

@@ -500,6 +500,9 @@ def _scalar_param(e: "sym.Expr", rvs) -> Optional[Tuple[int, float]]:
 
 def _match_gp(kind: str, value, params: List[Any], rvs, pools, label: str) -> Optional[Term]:
     """MvNormal(loc, expquad(l, a; X, X) + noise * I [+ jitter * I]) with a constant value and loc -> GP term."""
+    if kind == "mvn_chol":
+        raise NotImplementedError("MvNormalCholesky runs on the device with a constant scale_tril (a latent vector, or an "
+                                  "observation with a free loc); a scale_tril that depends on free variables does not")
     if kind != "mvn":
         return None
     why = ("MvNormal runs on the device as the marginal likelihood of GP regression: an observed vector, a constant "
@@ -571,7 +574,38 @@ def _match_gp(kind: str, value, params: List[Any], rvs, pools, label: str) -> Op
                       elems=(ls[0], amp[0], ne)))
 
 
+def _mvn_constant_term(kind: str, value, params: List[Any], rvs, pools, label: str) -> Optional[Term]:
+    """MvNormal / MvNormalCholesky with a CONSTANT covariance (Cholesky factor): a latent vector, or an observation
+    with a free ``loc``.  With P = Sigma^-1 the density is ``-1/2 sum_ij P_ij r_i r_j - sum log L_ii - k/2 log 2 pi``,
+    r = value - loc: an element-wise potential over the k (k + 1) / 2 pairs i >= j (off-diagonal pairs count twice),
+    two gathers of r per element.  Reference: distributions/multivariate.py:159-199, 331-375."""
+    if kind not in ("mvn", "mvn_chol"):
+        return None
+    mat = sym.as_expr(params[1])
+    if mat.op != "const":
+        return None
+    M = np.asarray(mat.data, dtype=np.float64)
+    L = np.linalg.cholesky(M) if kind == "mvn" else np.tril(M)
+    k = L.shape[0]
+    if np.any(np.diag(L) <= 0):
+        raise ValueError("{}: the Cholesky factor needs a positive diagonal".format(label))
+    Linv = np.linalg.solve(L, np.eye(k))
+    P = Linv.T @ Linv
+    v, loc = sym.as_expr(value), sym.as_expr(params[0])
+    if v.ndim != 1 or v.shape[0] != k:
+        raise NotImplementedError("{}: batches of multivariate normal vectors are not lowered (value shape {})".format(label, v.shape))
+    r = v - (loc if loc.ndim == 1 else sym.broadcast_to(loc, (k,)))
+    I, J = np.tril_indices(k)
+    w = np.where(I == J, -0.5, -1.0) * P[I, J]
+    const = (-np.sum(np.log(np.diag(L))) - 0.5 * k * np.log(2.0 * np.pi)) / len(I)
+    quad = sym.const(w) * sym.gather(r, I) * sym.gather(r, J) + const
+    return _lower_term("potential", quad, [], rvs, pools, label=label)
+
+
 def _lower_term(kind: str, value, params: List[Any], rvs, pools, label="") -> Term:
+    mv = _mvn_constant_term(kind, value, params, rvs, pools, label)
+    if mv is not None:
+        return mv
     glm = _match_glm(kind, value, params, rvs, pools, label)
     if glm is not None:
         return glm

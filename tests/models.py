@@ -108,3 +108,27 @@ def outer_model():
     ddx = yield pm.Deterministic("ddx", dx)
     return ddx
 
+
+
+def mvn_latent_data(k=6, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((k, k))
+    cov = A @ A.T + np.eye(k)
+    return cov, rng.standard_normal(k)
+
+
+def mvn_latent_model(cov=None, y=None):
+    """A latent multivariate normal vector with a constant Cholesky factor under a Normal observation model
+    (reference distributions/multivariate.py:331-375 MvNormalCholesky as a sampled variable)."""
+    if cov is None:
+        cov, y = mvn_latent_data()
+    L = np.linalg.cholesky(cov)
+    k = L.shape[0]
+
+    @pm.model
+    def mvn_latent():
+        f = yield pm.MvNormalCholesky("f", loc=np.zeros(k), scale_tril=L)
+        s = yield pm.HalfNormal("s", 1.0)
+        yield pm.Normal("y", f, s, observed=y)
+
+    return mvn_latent()

@@ -29,6 +29,7 @@ MODELS = {
     "logistic": lambda: M.logistic_model(*M.logistic_data()),
     "poisson": lambda: M.poisson_model(*M.poisson_data()),
     "nested": lambda: M.outer_model(),
+    "mvn_latent": lambda: M.mvn_latent_model(),
 }
 
 
@@ -53,7 +54,7 @@ def test_logp_grad_parity_fp32(name, oracle_mod):
         assert _rel(g[c], g_ref[c]) < 1e-5, (name, c)
 
 
-@pytest.mark.parametrize("name", ["eight_schools", "radon_real", "logistic", "poisson"])
+@pytest.mark.parametrize("name", ["eight_schools", "radon_real", "logistic", "poisson", "mvn_latent"])
 def test_logp_grad_parity_fp64(name, oracle_mod):
     ir, _, _ = lower_model(MODELS[name]())
     rng = np.random.default_rng(12)

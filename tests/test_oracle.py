@@ -492,14 +492,25 @@ def test_gp_marginal_likelihood_oracle_against_scipy(oracle_mod):
     np.testing.assert_allclose(np.cov(draws.T), Ks, atol=0.06)
     assert np.all(np.abs(draws.mean(0)) < 0.06)
     np.testing.assert_array_equal(draws[:5], oracle_mod.Oracle(irs).gp_predictive(th[:5], seed=11))  # keyed by (state, element)
-    # unsupported spellings fail loudly at lowering time
+    # a latent vector with a CONSTANT covariance lowers (quadratic form over the precision matrix as a potential) ...
     @pm.model
     def latent():
         f = yield pm.MvNormal("f", loc=0.0, covariance_matrix=np.eye(3))
         yield pm.Normal("y", f, 1.0, observed=np.zeros(3))
 
+    irl, _, _ = lower_model(latent())
+    lpl, _ = oracle_mod.Oracle(irl).logp_grad(np.array([[0.3, -0.2, 0.1]]), dtype=np.float64)
+    np.testing.assert_allclose(lpl[0], 2 * stats.norm(0, 1).logpdf([0.3, -0.2, 0.1]).sum(), rtol=1e-12)
+
+    # ... a latent vector whose covariance depends on free variables does not: it fails loudly at lowering time
+    @pm.model
+    def latent_gp():
+        ls = yield pm.HalfNormal("ls", 1.0)
+        f = yield pm.MvNormal("f", loc=0.0, covariance_matrix=pm.gp.cov.ExpQuad(length_scale=ls, amplitude=1.0)(Xs, Xs))
+        yield pm.Normal("y", f, 1.0, observed=ys)
+
     with pytest.raises(NotImplementedError, match="marginal likelihood"):
-        lower_model(latent())
+        lower_model(latent_gp())
 
 
 def test_gp_term_spellings_lower_to_the_same_term(oracle_mod):
@@ -684,3 +695,40 @@ def test_diagonal_mass_matrix_windows_recover_the_scales(oracle_mod):
     x = res[4]["states"].reshape(-1, 5)
     np.testing.assert_allclose(x.std(axis=0), sig, rtol=0.05)
     assert res[4]["diverging"].mean() == 0.0
+
+
+def test_multivariate_normal_with_constant_covariance_against_scipy(oracle_mod):
+    """MvNormalCholesky as a LATENT vector and MvNormal as an observation with a free loc (row a16: reference
+    distributions/multivariate.py:159-199, 331-375): the constant precision matrix turns the quadratic form into an
+    element-wise potential; value and gradient against scipy / finite differences."""
+    cov, y = M.mvn_latent_data()
+    k = cov.shape[0]
+    ir, _, _ = lower_model(M.mvn_latent_model(cov, y))
+    assert ir.D == k + 1
+    rng = np.random.default_rng(3)
+    th = rng.normal(0, 0.5, (6, ir.D))
+    lp, g = oracle_mod.Oracle(ir).logp_grad(th, dtype=np.float64)
+
+    def ref(t):
+        f, z = t[:k], t[k]
+        return (stats.multivariate_normal(np.zeros(k), cov).logpdf(f) + stats.halfnorm(scale=1).logpdf(np.exp(z)) + z
+                + stats.norm(f, np.exp(z)).logpdf(y).sum())
+
+    np.testing.assert_allclose(lp, [ref(t) for t in th], rtol=1e-12)
+    for c in range(2):
+        for d in range(ir.D):
+            e = np.zeros(ir.D); e[d] = 1e-6
+            np.testing.assert_allclose(g[c, d], (ref(th[c] + e) - ref(th[c] - e)) / 2e-6, rtol=1e-5, atol=1e-6)
+
+    @pm.model
+    def obs_model():
+        mu = yield pm.Normal("mu", 0.0, 1.0)
+        yield pm.MvNormal("y", loc=mu, covariance_matrix=cov, observed=y)
+
+    ir2, _, _ = lower_model(obs_model())
+    t2 = rng.normal(0, 1, (4, 1))
+    lp2, _ = oracle_mod.Oracle(ir2).logp_grad(t2, dtype=np.float64)
+    np.testing.assert_allclose(lp2, [stats.norm(0, 1).logpdf(t[0]) + stats.multivariate_normal(np.full(k, t[0]), cov).logpdf(y)
+                                     for t in t2], rtol=1e-12)
+    d = pm.MvNormalCholesky("v", loc=np.zeros(k), scale_tril=np.linalg.cholesky(cov))
+    np.testing.assert_allclose(d.log_prob(y), stats.multivariate_normal(np.zeros(k), cov).logpdf(y), rtol=1e-10)

@@ -299,3 +299,24 @@ def test_streamed_trace_equals_the_plain_trace():
         np.testing.assert_array_equal(streamed.posterior[k], v)
     for k, v in plain.sample_stats.items():
         np.testing.assert_array_equal(streamed.sample_stats[k], v)
+
+
+def test_sample_latent_mvnormal_cholesky():
+    """pm.sample on a model with a latent MvNormalCholesky vector (constant factor): the posterior of f given Normal
+    observations with the noise scale fixed is Gaussian in closed form."""
+    cov, y = M.mvn_latent_data()
+    k = cov.shape[0]
+    L = np.linalg.cholesky(cov)
+    s = 0.7
+
+    @pm.model
+    def m():
+        f = yield pm.MvNormalCholesky("f", loc=np.zeros(k), scale_tril=L)
+        yield pm.Normal("y", f, s, observed=y)
+
+    tr = pm.sample(m(), step_size=0.3, num_chains=64, num_samples=400, burn_in=200, seed=4)
+    f = tr.posterior["m/f"].reshape(-1, k)
+    post_cov = np.linalg.inv(np.linalg.inv(cov) + np.eye(k) / s ** 2)
+    post_mean = post_cov @ (y / s ** 2)
+    np.testing.assert_allclose(f.mean(axis=0), post_mean, atol=0.05)
+    np.testing.assert_allclose(np.cov(f.T), post_cov, atol=0.05)
