@@ -709,6 +709,7 @@ class OwnedGen:
                 for nm in vecs:
                     E("gr[%d] += %s;" % (vidx[nm] * KS + own_slice, sink("%ss" % nm)), ind)
             else:
+                E("#pragma unroll 1", ind)
                 E("for (int q = 0; q < c.Q; ++q) {  // segmented shuffle reduction over the pieces of one group ...", ind)
                 for nm in vecs:
                     E("{ const real tq = __shfl_down_sync(pm4::FULL, %ss, 1u << q); if ((fm.z >> q) & 1) %ss += tq; }" % (nm, nm), ind + 2)

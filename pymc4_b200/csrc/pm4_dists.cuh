@@ -75,10 +75,10 @@ template <typename real> __device__ __forceinline__ real m_digamma(real x) {
          f * ((real)(1.0 / 12) - f * ((real)(1.0 / 120) - f * ((real)(1.0 / 252) - f * (real)(1.0 / 240))));
 }
 template <typename real> __device__ __forceinline__ real m_logaddexp(real a, real b) {
-  if (a == -m_inf<real>()) return b;
-  if (b == -m_inf<real>()) return a;
+  // branch-free: exp(-inf) = 0 covers an operand at -inf, d = 0 covers both at -inf (where a - b would be NaN)
   const real m = a > b ? a : b;
-  return m + m_log1p(m_exp(-m_abs(a - b)));
+  const real d = (a == b) ? (real)0 : -m_abs(a - b);
+  return m + m_log1p(m_exp(d));
 }
 
 // ---- log-densities: lp plus d/dvalue and d/dparams --------------------------------------------
