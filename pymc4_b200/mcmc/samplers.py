@@ -469,7 +469,7 @@ def _get_device_model(ir: irmod.ModelIR, dtype, device):
             del _device_models[key]
             dm.close()
             dm = None
-        elif not (np.array_equal(dm.ir.dataf, ir.dataf) and np.array_equal(dm.ir.datai, ir.datai)):
+        elif dm.ir is not ir and not (np.array_equal(dm.ir.dataf, ir.dataf) and np.array_equal(dm.ir.datai, ir.datai)):
             try:
                 dm.set_data(ir)
             except Exception:

@@ -430,3 +430,18 @@ def test_layout_key_separates_data_of_another_shape_or_plan():
     assert ir_a.struct_hash == ir_b.struct_hash
     same_pools = np.asarray(ir_a.plani).shape == np.asarray(ir_b.plani).shape and np.asarray(ir_a.planf).shape == np.asarray(ir_b.planf).shape
     assert (ir_a.layout_key() == ir_b.layout_key()) == same_pools
+
+
+def test_lowering_cache_follows_the_data():
+    """lower_model is cached per model object behind a fingerprint of the arrays the model can reach: the same object
+    lowers once, an in-place edit of its data lowers again, another model object never shares the entry."""
+    idx, x, y, g = M.radon_synthetic()
+    y = y.copy()
+    m = M.hierarchical_model(idx, x, y, g)
+    a = lower_model(m)
+    assert lower_model(m)[0] is a[0]
+    y[3] += 1.0
+    c = lower_model(m)
+    assert c[0] is not a[0] and not np.array_equal(c[0].dataf, a[0].dataf)
+    assert lower_model(M.hierarchical_model(idx, x, y, g))[0] is not c[0]
+    assert lower_model(m, observed={})[0] is not lower_model(m, observed={})[0]  # overrides are never cached
