@@ -732,7 +732,13 @@ def run_b200(args):
     # its log-prob pass"; the FP32-pipe figure is reported beside it, HBM for context
     roofline = {
         "bound": "smem", "achieved": ach_smem_tbs * 1e3, "peak": (smem_peak * 1e3) if smem_peak else None, "unit": "GB/s",
-        "frac": (ach_smem_tbs / smem_peak) if smem_peak else None, "traffic": None,
+        "frac": (ach_smem_tbs / smem_peak) if smem_peak else None,
+        # measured shared-memory traffic per unit of the dominant kernel, from the committed ncu --set full capture
+        # (profiles/r02_nuts_warp_kernel_summary.md): l1tex__data_pipe_lsu_wavefronts_mem_shared.sum x 128 B / leapfrogs of
+        # the launch = 167 wavefronts = 21.4 KB per unit against 11.0 KB algorithmic (records are read as 16-byte pair
+        # rows, the tree checkpoints and the subtree candidate live in shared memory); DRAM traffic is the trace only
+        "traffic": (21.4e3 * units_per_step_gpu) if WORKLOAD == "radon919" else None,
+        "traffic_unit": "shared-memory wavefront bytes per step (167 wavefronts x 128 B per unit, ncu)",
         "kernel": ("pm4::nuts_warp_kernel (one warp per chain, owner-computes layout; per step: ONE cooperative launch for the "
                    "burn_in + 1 lock-step transitions while the pooled step size adapts -- grid barrier + dual-averaging "
                    "update inside the kernel -- then one persistent launch for the draws; bootstrap and export kernels are "

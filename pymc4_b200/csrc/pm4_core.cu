@@ -850,7 +850,8 @@ int drive(pm4_model* m, int dtype, pm4_mod_run_t& r, bool nuts, int wpb, int T, 
   // phase boundaries: a short first phase (step sizes settle within ~20 transitions), the end of
   // adaptation, the end of the run
   std::vector<int> ends;
-  const bool phased = nuts && order_buf && r.launch_leaps;
+  // (a pooled step size is frozen after the lock-step phase: the chains are balanced, one launch is enough)
+  const bool phased = nuts && order_buf && r.launch_leaps && !(r.adapt_enabled && r.adapt_pooled);
   if (phased) {
     const int freeze = r.adapt_enabled ? r.num_adapt + 1 : 0;
     if (t + 20 < T - 20) ends.push_back(t + 20);
