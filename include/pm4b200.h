@@ -314,6 +314,42 @@ int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, const void*
                 void* states_dev, void* lp_dev, void* log_accept_dev, uint8_t* accepted_dev,
                 void* step_size_dev, void* traj_dev, void* stream);
 
+/* ---- compound step (discrete latents; reference pymc4/mcmc/samplers.py:490-726 CompoundStep, tf_support.py:52-163
+ * _CompoundStepTF.one_step, proposals distributions/state_functions.py) -------------------------------------------
+ * The free variables are partitioned into blocks; one compound transition runs ONE transition of every block's kernel
+ * in order, each conditioned on the current values of all other dimensions (the reference's
+ * _target_log_prob_fn_part_compound).  A block owns the dimensions whose `dim_scale` is non-zero: the other dimensions
+ * are frozen (no momentum, no proposal).  Gradient blocks adapt their own step size; random-walk blocks may give every
+ * dimension one of the proposals below (`rw_kind` NULL = the normal perturbation for all of them). */
+#define PM4_BLOCK_NUTS 0
+#define PM4_BLOCK_HMC 1
+#define PM4_BLOCK_RWM 2
+#define PM4_RW_NORMAL 0         /* x + rw_scale * N(0,1)         tfp random_walk_normal_fn (samplers.py:450-478)     */
+#define PM4_RW_BERNOULLI 1      /* (x + Bernoulli(1/2)) mod 2    state_functions.py:118-146 bernoulli_fn             */
+#define PM4_RW_CATEGORICAL 2    /* a fresh uniform class         state_functions.py:79-115 categorical_uniform_fn; classes in bits 8.. */
+#define PM4_RW_GAUSSIAN_ROUND 3 /* round(x + rw_scale * N(0,1))  state_functions.py:149-196 gaussian_round_fn        */
+
+typedef struct pm4_compound_block {
+  int32_t kind;               /* PM4_BLOCK_*                                                     */
+  int32_t num_leapfrog_steps; /* PM4_BLOCK_HMC                                                   */
+  int32_t max_tree_depth;     /* PM4_BLOCK_NUTS                                                  */
+  int32_t _pad;
+  double max_energy_diff;     /* PM4_BLOCK_NUTS                                                  */
+  double step_size;           /* gradient blocks: initial epsilon                                */
+  double rw_scale;            /* PM4_BLOCK_RWM: standard deviation of the normal perturbation    */
+  pm4_adapt_cfg_t adapt;      /* gradient blocks (mass_windows must be 0)                        */
+  const void* dim_scale_dev;  /* [D] reals: 0 = not in this block, else per-dimension step scale */
+  const int32_t* rw_kind_dev; /* [D] or NULL: PM4_RW_* | (classes << 8) of every dimension       */
+} pm4_compound_block_t;
+
+/* B + S compound transitions of C chains from theta0_dev [C, D].  Outputs (any may be NULL): states_dev [S, C, D],
+ * lp_dev [S, C] joint log-density of the kept states, step_size_dev [n_blocks, C] final epsilon of every block (1 for
+ * random-walk blocks), log_accept_dev [n_blocks, S, C] log acceptance ratio of every block's transition. */
+int pm4_compound_run(pm4_model_t* m, int dtype, int32_t C, int32_t num_results, int32_t num_burnin, uint64_t seed,
+                     int32_t chain_offset, int32_t warps_per_block, const pm4_compound_block_t* blocks, int32_t n_blocks,
+                     const void* theta0_dev, void* states_dev, void* lp_dev, void* step_size_dev, void* log_accept_dev,
+                     void* stream);
+
 typedef struct pm4_nuts_cfg {
   int32_t C;
   int32_t num_results;     /* S */

@@ -52,7 +52,7 @@ static inline REAL NAME(lpdf)(int kind, REAL x, const REAL* q, REAL* dx, REAL* d
       REAL a = (x == 0) ? 0 : x * RLOG(p);
       REAL b = (1 - x == 0) ? 0 : (1 - x) * RLOG1P(-p);
       dq[0] = ((x == 0) ? 0 : x / p) - ((1 - x == 0) ? 0 : (1 - x) / (1 - p));
-      *dx = RLOG(p) - RLOG1P(-p);
+      *dx = 0; /* a free Bernoulli value is a frozen coordinate of the gradient-based blocks (compound step) */
       return a + b;
     }
     case PM4_T_POISSON: {

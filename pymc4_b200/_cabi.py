@@ -16,7 +16,8 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import codegen
-from ._cstructs import HMCCfg, NUTSCfg, PM4_F32, PM4_F64
+from ._cstructs import (CompoundBlock, HMCCfg, NUTSCfg, PM4_BLOCK_HMC, PM4_BLOCK_NUTS, PM4_BLOCK_RWM, PM4_F32, PM4_F64,
+                       make_adapt)
 from .ir import CIR, ModelIR, PackedIR
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -31,7 +32,7 @@ _lib = None
 EXPORTS = [
     "pm4_model_create", "pm4_model_destroy", "pm4_model_dim", "pm4_model_set_data", "pm4_model_set_plans",
     "pm4_logp_grad",
-    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_prior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_scratch_bytes", "pm4_launch_count",
+    "pm4_deterministics", "pm4_log_likelihood", "pm4_model_ll_row", "pm4_posterior_predictive", "pm4_prior_predictive", "pm4_hmc_run", "pm4_nuts_run", "pm4_compound_run", "pm4_scratch_bytes", "pm4_launch_count",
     "pm4_last_error", "pm4_abi_version",
     "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm", "pm4_model_set_trace_sink", "pm4_model_get_mass_scale",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
@@ -87,6 +88,7 @@ def load_library():
     L.pm4_gp_points.argtypes = [vp, i32]
     L.pm4_hmc_run.argtypes = [vp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 11
     L.pm4_nuts_run.argtypes = [vp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
+    L.pm4_compound_run.argtypes = [vp, i32, i32, i32, i32, ctypes.c_uint64, i32, i32, ctypes.POINTER(CompoundBlock), i32] + [vp] * 6
     L.pm4_scratch_bytes.argtypes = [vp, i32, i32, i32]
     L.pm4_scratch_bytes.restype = i64
     L.pm4_launch_count.argtypes = [i32]
@@ -363,6 +365,42 @@ class DeviceModel:
                 self._p(out["step_size"]), self._p(out["traj"]), self._stream())
         self._check(rc)
         out["_keepalive"] = (th0, sc, mom, uni)
+        return out
+
+
+    def compound(self, blocks, theta0, num_results: int, num_burnin: int, seed: int = 0, dtype=np.float32,
+                 warps_per_block: int = 0, chain_offset: int = 0) -> Dict[str, "object"]:
+        """Compound step (``pm4_compound_run``): ``blocks`` is a list of dicts -- ``kind`` ("nuts" | "hmc" | "rwm"),
+        ``dim_scale`` [D] (0 = dimension not in the block) and, by kind, ``step_size``, ``adapt``, ``max_tree_depth``,
+        ``max_energy_diff``, ``num_leapfrog_steps`` / ``rw_scale``, ``rw_kind`` [D] int32 or None.  Returns device
+        tensors: states [S, C, D], lp [S, C], step_size [n_blocks, C], log_accept [n_blocks, S, C]."""
+        torch = self.torch
+        td = _tdtype(torch, dtype)
+        theta0 = np.asarray(theta0, dtype=dtype) if not isinstance(theta0, torch.Tensor) else theta0
+        C, D, S = int(theta0.shape[0]), self.ir.D, int(num_results)
+        th0 = self.to_device(theta0, dtype)
+        arr = (CompoundBlock * len(blocks))()
+        keep = [th0]
+        codes = {"nuts": PM4_BLOCK_NUTS, "hmc": PM4_BLOCK_HMC, "rwm": PM4_BLOCK_RWM}
+        for k, b in enumerate(blocks):
+            scale = self.to_device(np.asarray(b["dim_scale"], dtype=np.float64).reshape(D), dtype)
+            kinds = None
+            if b.get("rw_kind") is not None:
+                kinds = torch.from_numpy(np.ascontiguousarray(b["rw_kind"], dtype=np.int32).reshape(D)).to(self._dev())
+            keep += [scale, kinds]
+            arr[k] = CompoundBlock(codes[b["kind"]], int(b.get("num_leapfrog_steps", 0)), int(b.get("max_tree_depth", 10)), 0,
+                                   float(b.get("max_energy_diff", 1000.0)), float(b.get("step_size", 1.0)),
+                                   float(b.get("rw_scale", 1.0)), b.get("adapt") or make_adapt(enabled=False),
+                                   scale.data_ptr(), kinds.data_ptr() if kinds is not None else None)
+        out = dict(states=self.empty((S, C, D), td), lp=self.empty((S, C), td),
+                   step_size=self.empty((len(blocks), C), td), log_accept=self.empty((len(blocks), S, C), td))
+        with torch.cuda.device(self._dev()):
+            rc = self.lib.pm4_compound_run(self.handle, _code(dtype), C, S, int(num_burnin),
+                                           ctypes.c_uint64(int(seed) & (2**64 - 1)), int(chain_offset), int(warps_per_block),
+                                           arr, len(blocks), self._p(th0), self._p(out["states"]), self._p(out["lp"]),
+                                           self._p(out["step_size"]), self._p(out["log_accept"]), self._stream())
+        self._check(rc)
+        out["_keepalive"] = keep
         return out
 
 

@@ -5,6 +5,7 @@ PM4_F32, PM4_F64 = 0, 1
 PM4_EPS_POOLED, PM4_EPS_PER_CHAIN = 0, 1
 PM4_ADAPT_DUAL_AVERAGING, PM4_ADAPT_SIMPLE = 0, 1
 PM4_PROPOSAL_LEAPFROG, PM4_PROPOSAL_RANDOM_WALK = 0, 1
+PM4_BLOCK_NUTS, PM4_BLOCK_HMC, PM4_BLOCK_RWM = 0, 1, 2
 
 
 class AdaptCfg(ctypes.Structure):
@@ -52,6 +53,21 @@ class NUTSCfg(ctypes.Structure):
         ("adapt", AdaptCfg),
         ("warps_per_block", ctypes.c_int32),
         ("chain_offset", ctypes.c_int32),
+    ]
+
+
+class CompoundBlock(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("num_leapfrog_steps", ctypes.c_int32),
+        ("max_tree_depth", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("max_energy_diff", ctypes.c_double),
+        ("step_size", ctypes.c_double),
+        ("rw_scale", ctypes.c_double),
+        ("adapt", AdaptCfg),
+        ("dim_scale_dev", ctypes.c_void_p),
+        ("rw_kind_dev", ctypes.c_void_p),
     ]
 
 

@@ -1216,6 +1216,133 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
   return PM4_OK;
 }
 
+// Compound step (reference pymc4/mcmc/samplers.py:490-726, tf_support.py:52-163): per transition, one transition of
+// every block's kernel in order on the SAME chain state (th / gr / lp rows of the run): a block's kernel sees the other
+// blocks' dimensions frozen at their current values (step scale 0) -- the reference's
+// _target_log_prob_fn_part_compound.  Every block has its own adaptation state and its own Philox streams.
+extern "C" int pm4_compound_run(pm4_model_t* m, int dtype, int32_t C_, int32_t num_results, int32_t num_burnin, uint64_t seed,
+                                int32_t chain_offset, int32_t warps_per_block, const pm4_compound_block_t* blocks,
+                                int32_t n_blocks, const void* theta0_dev, void* states_dev, void* lp_dev,
+                                void* step_size_dev, void* log_accept_dev, void* stream) {
+  Nvtx nvtx_range("pm4_compound_run");
+  if (!m || !blocks || !theta0_dev || n_blocks < 1) return fail(PM4_EINVAL, "pm4_compound_run: null argument");
+  int rc = check_dtype(m, dtype);
+  if (rc) return rc;
+  if (C_ <= 0 || num_results < 0 || num_burnin < 0) return fail(PM4_EINVAL, "pm4_compound_run: bad chain/draw counts");
+  if (m->lockstep()) return fail(PM4_ENOSYS, "the compound step is not built for models with dense (GLM / GP) terms");
+  for (int b = 0; b < n_blocks; ++b) {
+    const pm4_compound_block_t& k = blocks[b];
+    if (k.kind != PM4_BLOCK_NUTS && k.kind != PM4_BLOCK_HMC && k.kind != PM4_BLOCK_RWM) return fail(PM4_EINVAL, "block %d: unknown kind %d", b, k.kind);
+    if (!k.dim_scale_dev) return fail(PM4_EINVAL, "block %d: dim_scale_dev is required", b);
+    if (k.kind == PM4_BLOCK_NUTS && (k.max_tree_depth < 1 || k.max_tree_depth > 20)) return fail(PM4_EINVAL, "block %d: max_tree_depth must be in [1, 20]", b);
+    if (k.kind == PM4_BLOCK_HMC && k.num_leapfrog_steps < 1) return fail(PM4_EINVAL, "block %d: num_leapfrog_steps must be positive", b);
+    if (k.kind != PM4_BLOCK_RWM && !(k.step_size > 0)) return fail(PM4_EINVAL, "block %d: step_size must be positive", b);
+    if (k.kind == PM4_BLOCK_RWM && !(k.rw_scale > 0)) return fail(PM4_EINVAL, "block %d: rw_scale must be positive", b);
+    if (k.kind != PM4_BLOCK_RWM && k.adapt.mass_windows > 0) return fail(PM4_ENOSYS, "block %d: mass-matrix windows are not built for the compound step", b);
+  }
+  CU(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(dtype), C = (size_t)C_, DP = (size_t)m->info.DP;
+  const int T = num_burnin + num_results, S = num_results;
+
+  pm4_mod_run_t base;
+  memset(&base, 0, sizeof base);
+  base.A = m->args(dtype);
+  base.C = C_; base.B = num_burnin; base.S = num_results;
+  base.chain_offset = chain_offset;
+  RunBuffers buf(st);
+  if ((rc = buf.get(&base.th, C * DP * rs))) return rc;
+  if ((rc = buf.get(&base.gr, C * DP * rs))) return rc;
+  if ((rc = buf.get(&base.lp, C * rs))) return rc;
+  if ((rc = buf.get(&base.accept, C * rs))) return rc;
+  int max_depth = 1;
+  for (int b = 0; b < n_blocks; ++b)
+    if (blocks[b].kind == PM4_BLOCK_NUTS && blocks[b].max_tree_depth > max_depth) max_depth = blocks[b].max_tree_depth;
+  const int64_t tree_bytes = m->f_scratch(dtype, &base.A, C_, warps_per_block, max_depth);
+  if (tree_bytes < 0) return fail(PM4_EINVAL, "kernel module cannot size its tree scratch");
+  if (tree_bytes > 0 && (rc = buf.get(&base.scratch, (size_t)tree_bytes))) return rc;
+  void *queue = nullptr, *sync = nullptr, *leaps = nullptr, *progress = nullptr, *t0w = nullptr;
+  if ((rc = buf.get(&queue, 64))) return rc;
+  if ((rc = buf.get(&sync, 16))) return rc;
+  if ((rc = buf.get(&leaps, C * sizeof(int32_t)))) return rc;
+  if ((rc = buf.get(&progress, C * sizeof(int32_t)))) return rc;
+  if ((rc = buf.get(&t0w, 16))) return rc;
+  CU(cudaMemsetAsync(t0w, 0, 16, st));
+  base.queue = (int32_t*)queue; base.sync = (int32_t*)sync; base.launch_leaps = (int32_t*)leaps;
+  base.progress = (int32_t*)progress; base.da_t0 = (const int32_t*)t0w;
+  base.comm_world = 1;  // the blocks' step sizes are not coupled across GPUs: every rank adapts on its own chains
+
+  // per-block run records: adaptation state, streams, outputs
+  std::vector<pm4_mod_run_t> runs((size_t)n_blocks, base);
+  std::vector<unsigned char> host_da;
+  for (int b = 0; b < n_blocks; ++b) {
+    const pm4_compound_block_t& k = blocks[b];
+    pm4_mod_run_t& r = runs[(size_t)b];
+    if (k.kind == PM4_BLOCK_RWM) {
+      pm4_adapt_cfg_t off;
+      memset(&off, 0, sizeof off);
+      off.mode = PM4_EPS_PER_CHAIN;
+      if ((rc = fill_adapt(r, off))) return rc;
+      r.random_walk = 1;
+      r.rw_scale = k.rw_scale;
+      r.rw_kind = k.rw_kind_dev;
+    } else {
+      if ((rc = fill_adapt(r, k.adapt))) return rc;
+      r.max_depth = k.max_tree_depth;
+      r.num_leapfrog = k.num_leapfrog_steps;
+      r.max_energy_diff = k.max_energy_diff;
+    }
+    r.step_scale = k.dim_scale_dev;
+    // independent streams per block: two Metropolis tests of one transition must not share their uniform
+    const uint64_t sb = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
+    r.seed_lo = (uint32_t)sb; r.seed_hi = (uint32_t)(sb >> 32);
+    if ((rc = buf.get(&r.da, C * 4 * rs))) return rc;
+    // dual-averaging state [eps, error_sum, log_avg, log(10 eps)] of every chain (the pooled mode reads row 0)
+    const double eps0 = k.kind == PM4_BLOCK_RWM ? 1.0 : k.step_size;
+    host_da.resize(C * 4 * rs);
+    for (size_t c = 0; c < C; ++c) {
+      const double row[4] = {eps0, 0.0, 0.0, log(10.0 * eps0)};
+      for (int q = 0; q < 4; ++q) {
+        if (dtype == PM4_F64) ((double*)host_da.data())[c * 4 + q] = row[q];
+        else ((float*)host_da.data())[c * 4 + q] = (float)row[q];
+      }
+    }
+    CU(cudaMemcpyAsync(r.da, host_da.data(), host_da.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // host_da is reused
+    // the last block of a transition writes the trace
+    const bool last = b == n_blocks - 1;
+    r.states = last ? states_dev : nullptr;
+    r.lp_out = last ? lp_dev : nullptr;
+    r.log_accept = log_accept_dev ? (void*)((char*)log_accept_dev + (size_t)b * (size_t)S * C * rs) : nullptr;
+  }
+  {  // bootstrap: log-density and gradient of the initial point (block 0's record; its da row is rewritten identically)
+    pm4_mod_run_t& r0 = runs[0];
+    MOD(m->f_init(dtype, &r0, theta0_dev, blocks[0].kind == PM4_BLOCK_RWM ? 1.0 : blocks[0].step_size, st), "bootstrap");
+  }
+  const bool persistent_cap = (m->info.caps & PM4_CAP_PERSISTENT_LOCKSTEP) != 0;
+  for (int t = 0; t < T; ++t) {
+    for (int b = 0; b < n_blocks; ++b) {
+      pm4_mod_run_t& r = runs[(size_t)b];
+      const bool nuts = blocks[b].kind == PM4_BLOCK_NUTS;
+      r.t_begin = t; r.t_count = 1; r.tb = 0; r.order = nullptr;
+      const bool coupled = r.adapt_enabled && r.adapt_pooled && t <= r.num_adapt;
+      if (coupled && nuts && persistent_cap) {
+        r.rounds = 1;
+        MOD(m->f_nuts(dtype, &r, warps_per_block, st), "compound: nuts (lock-step round)");
+        r.rounds = 0;
+      } else {
+        r.rounds = 0;
+        MOD((nuts ? m->f_nuts : m->f_hmc)(dtype, &r, warps_per_block, st), nuts ? "compound: nuts" : "compound: hmc / rwm");
+        if (coupled) MOD(m->f_da(dtype, &r, t, st), "compound: pooled dual averaging");
+      }
+    }
+  }
+  if (step_size_dev)
+    for (int b = 0; b < n_blocks; ++b)
+      MOD(m->f_eps(dtype, &runs[(size_t)b], (char*)step_size_dev + (size_t)b * C * rs, st), "export step size");
+  return PM4_OK;
+}
+
 extern "C" int pm4_comm_create(int device, int rank, int world, pm4_comm_t** out, unsigned char* handle_out) {
   if (!out || !handle_out || world < 1 || world > PM4_MAX_RANKS || rank < 0 || rank >= world)
     return fail(PM4_EINVAL, "pm4_comm_create: bad argument (at most %d ranks)", PM4_MAX_RANKS);

@@ -119,7 +119,7 @@ __device__ __forceinline__ real bernoulli_lpdf(real x, real p, real& dx, real& d
   const real lg = m_log(p), l1 = m_log1p(-p);
   const real omx = (real)1 - x;
   dp = (x == 0 ? (real)0 : x / p) - (omx == 0 ? (real)0 : omx / ((real)1 - p));
-  dx = lg - l1;
+  dx = 0;  // a free Bernoulli value is a frozen coordinate of the gradient-based blocks (compound step)
   return (x == 0 ? (real)0 : x * lg) + (omx == 0 ? (real)0 : omx * l1);
 }
 

@@ -269,6 +269,7 @@ template <typename real> struct RunParams {
   int32_t* progress;
   int32_t* sync;
   const int32_t* da_t0;
+  const int32_t* rw_kind;
   real max_energy_diff, target_accept, shrinkage, smoothing, decay, adapt_rate, rw_scale;
   uint32_t seed_lo, seed_hi;
   real* th;
@@ -306,7 +307,7 @@ template <typename real> __host__ inline RunParams<real> make_run_params(const p
   p.adapt_enabled = r.adapt_enabled; p.adapt_pooled = r.adapt_pooled; p.num_adapt = r.num_adapt;
   p.adapt_kind = r.adapt_kind; p.random_walk = r.random_walk;
   p.adapt_rate = (real)r.adapt_rate; p.rw_scale = (real)r.rw_scale;
-  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress; p.rounds = r.rounds; p.sync = r.sync; p.da_t0 = r.da_t0;
+  p.team_reals = 0; p.n_slots = 0; p.n_fast = 0; p.tb = r.tb; p.progress = r.progress; p.rounds = r.rounds; p.sync = r.sync; p.da_t0 = r.da_t0; p.rw_kind = r.rw_kind;
   p.max_energy_diff = (real)r.max_energy_diff; p.target_accept = (real)r.target_accept;
   p.shrinkage = (real)r.shrinkage; p.smoothing = (real)r.smoothing; p.decay = (real)r.decay;
   p.seed_lo = r.seed_lo; p.seed_hi = r.seed_hi;
@@ -628,6 +629,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_kernel(RunParams<real> a) {
       auto set_rho_sub = [&](int r, real v) { if constexpr (LEAN) stv(SL_RHO_SUB, r, v); else rho_sub_reg[r] = v; };
       const real eps = da.eps;
       draw_momentum<M, real>(a, chain, t, tl, p);
+      if (a.step_scale) {  // scale 0 = frozen dimension (compound step): no momentum
+#pragma unroll
+        for (int r = 0; r < M::R; ++r) p[r] = sc(r) == (real)0 ? (real)0 : p[r];
+      }
       real q[4];
       q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
       // both trajectory ends and the candidate start at the current point
@@ -871,6 +876,10 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
       const real eps = da.eps;
       auto es = [&](int r) -> real { return eps * sc(r); };
       draw_momentum<M, real>(a, chain, t, tl, p);
+      if (a.step_scale) {  // scale 0 = frozen dimension (compound step): no momentum
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = sc(r) == (real)0 ? (real)0 : p[r];
+      }
       q[0] = 0; q[1] = 0; q[2] = 0; q[3] = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -879,9 +888,27 @@ __global__ void __launch_bounds__(MAXT, 1) hmc_kernel(RunParams<real> a) {
       }
       real plp = clp, lar;
       if (a.random_walk) {
-        // tfp RandomWalkMetropolis, random_walk_normal_fn: symmetric proposal state + scale * N(0, 1)
+        // tfp RandomWalkMetropolis: symmetric proposal; random_walk_normal_fn (state + scale * N(0, 1)) unless the
+        // dimension carries one of the discrete proposals of the compound step (pm4_module.h: PM4_RW_*)
+        if (a.rw_kind) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) th[r] = th[r] + a.rw_scale * p[r];
+          for (int r = 0; r < R; ++r) {
+            const int j = tl + TL * r;
+            if (j >= D || sc(r) == (real)0) continue;
+            const int kd = __ldg(a.rw_kind + j), kind = kd & 0xff;
+            const real z = p[r];
+            if (kind == PM4_RW_BERNOULLI) th[r] = z > 0 ? (real)1 - th[r] : th[r];
+            else if (kind == PM4_RW_CATEGORICAL) {
+              const int K = kd >> 8;
+              int k = (int)((real)K * (real)0.5 * (real)erfc((double)(-z) * 0.70710678118654752440));
+              th[r] = (real)(k < 0 ? 0 : (k > K - 1 ? K - 1 : k));
+            } else if (kind == PM4_RW_GAUSSIAN_ROUND) th[r] = (real)rint((double)(th[r] + a.rw_scale * z));
+            else th[r] = th[r] + a.rw_scale * z;
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) th[r] = th[r] + a.rw_scale * p[r];
+        }
         plp = logp_grad<M, real>(th, g, c, own);
         lar = plp - clp;
       } else {

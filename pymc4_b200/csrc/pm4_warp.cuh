@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(MAXT, 1) nuts_warp_kernel(RunParams<real> a) {
       real th[R], p[R], g[R], rho[R], rho_sub[R];
       const real eps = da.eps;
       lay.momentum(a, chain, t, p);
+      if constexpr (SCALED) {  // scale 0 = frozen dimension (compound step): no momentum
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r] = scl[r] == (real)0 ? (real)0 : p[r];
+      }
       real q0 = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {

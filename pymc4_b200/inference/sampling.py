@@ -1,15 +1,30 @@
 """``pm.sample``: the user-facing MCMC entry point.
 
 Signature, sampler selection and the ``num_adaptation_steps = burn_in`` rule are the reference's
-(pymc4/inference/sampling.py:52-184, :187-214).  Samplers available in this backend: ``"nuts"``
-(default for models without free discrete variables) and ``"hmc"``.
+(pymc4/inference/sampling.py:52-184, :187-214).  Samplers: ``"nuts"`` (default for models without free
+discrete variables), ``"hmc"``, ``"nuts_simple"``, ``"hmc_simple"``, ``"rwm"`` and ``"compound"`` (default when the
+model has free discrete variables).
 """
 from typing import Any, Dict, List, Optional
 
 from .. import flow
 from ..coroutine_model import Model
 from ..mcmc.samplers import _log, reg_samplers
-from ..mcmc.utils import initialize_state
+from ..mcmc.utils import initialize_state, scope_remove_transformed_part_if_required
+
+
+def check_proposal_functions(model: Model, state: Optional[flow.SamplingState] = None,
+                             observed: Optional[dict] = None) -> bool:
+    """True when a free variable's distribution carries a non-default proposal function (reference :14-49)."""
+    (_, state, _, _, continuous_distrs, discrete_distrs) = initialize_state(model, observed=observed, state=state)
+    for key in state.all_unobserved_values:
+        untrs_var, _ = scope_remove_transformed_part_if_required(key, state.transformed_values)
+        distr = continuous_distrs.get(untrs_var, None)
+        if distr is None:
+            distr = discrete_distrs[untrs_var]
+        if callable(distr._default_new_state_part):
+            return True
+    return False
 
 
 def sample(
@@ -51,6 +66,13 @@ def sample(
     if any(x in sampler_assigned for x in ["nuts", "hmc"]):
         kwargs["num_adaptation_steps"] = burn_in
     sampler = sampler(model, **kwargs)
+    # distributions with their own proposal function (Bernoulli, Categorical) turn "rwm" into the compound step
+    if sampler_assigned == "rwm":
+        if check_proposal_functions(model, state=state, observed=observed):
+            sampler_assigned = "compound"
+            sampler = reg_samplers[sampler_assigned](model, **kwargs)
+    if sampler_assigned == "compound":
+        sampler._assign_default_methods(sampler_methods=sampler_methods, state=state, observed=observed)
     return sampler(
         num_samples=num_samples,
         num_chains=num_chains,
@@ -74,7 +96,5 @@ def auto_assign_sampler(model: Model, sampler_type: Optional[str] = None) -> str
     if not free_disc_names:
         _log.info("Auto-assigning NUTS sampler")
         return "nuts"
-    raise ValueError(
-        "The model contains free discrete variables {}; the compound / Metropolis step methods are "
-        "outside this backend's scope (gradient-based NUTS/HMC only)".format(free_disc_names)
-    )
+    _log.info("The model contains discrete distributions. " "\nCompound step is chosen.")
+    return "compound"

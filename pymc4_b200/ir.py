@@ -70,6 +70,7 @@ class RV:
     shift: float = 0.0
     scale: float = 1.0
     untransformed_name: Optional[str] = None  # "m/tau" for transformed variables
+    discrete: bool = False  # a free discrete variable (float-typed integers): moved by the compound step's random-walk blocks only
 
 
 @dataclass
@@ -755,10 +756,10 @@ def _lower_model(model: Model, observed: Optional[dict] = None, state=None,
             if tname in rvs:
                 rvs[tname].transform, rvs[tname].shift, rvs[tname].scale = _transform_record(dist)
                 continue
-        if name in rvs and not dist._grad_support:
-            raise ValueError("Discrete distributions can't be used with gradient-based sampler")
-        if name in rvs and dist._kind in ("bernoulli", "poisson"):
-            raise ValueError("Discrete distributions can't be used with gradient-based sampler")
+        if name in rvs and (not dist._grad_support or name in st.discrete_distributions):
+            # a free discrete variable: a coordinate of the state the gradient-based kernels keep frozen; the sampler
+            # classes refuse it unless a random-walk block owns it (reference samplers.py:62-66, compound step :490-726)
+            rvs[name].discrete = True
 
     pools = _Pools()
     terms: List[Term] = []
@@ -768,6 +769,9 @@ def _lower_model(model: Model, observed: Optional[dict] = None, state=None,
                 "{} has no device log-density (supported kinds: {})".format(type(dist).__name__, sorted(TERM_KINDS))
             )
         value = st.all_values[name]
+        if dist._kind == "categorical":  # log-mass as an element-wise expression of the value (distributions/discrete.py)
+            terms.append(_lower_term("potential", dist.log_prob_expr(value), [], rvs, pools, label=name))
+            continue
         params = [dist.params[p] for p in dist._param_names]
         terms.append(_lower_term(dist._kind, value, params, rvs, pools, label=name))
         terms[-1].observed = name in st.observed_values

@@ -93,9 +93,14 @@ class RandomWalkMetropolis:
     extension) sets its standard deviation."""
 
     def __init__(self, target_log_prob_fn, new_state_fn=None, seed=None, name=None, scale=1.0):
-        if new_state_fn is not None:
-            raise NotImplementedError("custom new_state_fn is not supported; the device proposal is "
-                                      "state + scale * Normal(0, 1) (tfp random_walk_normal_fn)")
+        # besides the default, the proposals of pymc4_b200.distributions.state_functions run on the device (compound step)
+        proposal = getattr(new_state_fn, "__self__", None)
+        if new_state_fn is not None and not hasattr(proposal, "device_code"):
+            raise NotImplementedError("custom new_state_fn is not supported; the device proposals are "
+                                      "state + scale * Normal(0, 1) (tfp random_walk_normal_fn) and pm.bernoulli_fn / "
+                                      "pm.categorical_uniform_fn / pm.gaussian_round_fn")
+        self.new_state_fn = new_state_fn
+        self.proposal = proposal
         self.target_log_prob_fn = target_log_prob_fn
         self.scale = float(scale)
         self.seed = seed
@@ -106,6 +111,20 @@ class RandomWalkMetropolis:
     @property
     def parameters(self):
         return dict(scale=self.scale)
+
+
+class _CompoundStepTF:
+    """Configuration carrier of the compound transition kernel (reference pymc4/mcmc/tf_support.py:52-163): one
+    transition of every sub-kernel in turn, each on its subset of the free variables with the others held fixed.
+    The transition runs in ``pm4_compound_run`` (csrc/pm4_core.cu)."""
+
+    def __init__(self, target_log_prob_fn, compound_samplers, compound_set_lengths, name=None):
+        self.target_log_prob_fn = target_log_prob_fn
+        self.compound_samplers = list(compound_samplers)
+        self.compound_set_lengths = list(compound_set_lengths)
+        self.name = name
+
+    is_calibrated = True
 
 
 def sample_chain(num_results, current_state, previous_kernel_results=None, kernel=None, num_burnin_steps=0,

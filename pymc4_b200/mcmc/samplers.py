@@ -7,12 +7,15 @@ Class protocol, kwarg routing and return layout follow the reference
 ``tfp.mcmc.sample_chain`` it calls ``pm4_nuts_run`` / ``pm4_hmc_run`` of libpm4b200 through
 ctypes, with torch tensors as device buffers.  ``hmc_simple`` / ``nuts_simple`` (:318-339, :422-447:
 ``SimpleStepSizeAdaptation``) and ``rwm`` (:450-478: random-walk Metropolis) run on the same kernels;
-``compound`` (discrete latents, :481-726) is out of scope for this backend.
+``compound`` (discrete latents, :481-726) partitions the free variables into blocks and calls ``pm4_compound_run``:
+one transition of every block's kernel per compound transition, the other blocks' dimensions frozen.
 """
 import abc
 import inspect
+import itertools
 import logging
 import os
+from functools import partial
 from typing import Any, Dict, List, Optional
 
 from collections import OrderedDict
@@ -33,7 +36,7 @@ from .utils import (
     trace_to_arviz,
 )
 
-__all__ = ["HMC", "HMCSimple", "NUTS", "NUTSSimple", "RandomWalkM"]
+__all__ = ["HMC", "HMCSimple", "NUTS", "NUTSSimple", "RandomWalkM", "CompoundStep"]
 reg_samplers: Dict[str, type] = {}
 
 _log = logging.getLogger("pymc4.sampling")
@@ -442,6 +445,223 @@ class RandomWalkM(_BaseSampler):
         return results, self.trace_fn(out["states"], out)
 
 
+@register_sampler
+class CompoundStep(_BaseSampler):
+    """The compound step (reference :481-726): every free variable gets a sampler -- the user's ``sampler_methods``
+    entry, else random-walk Metropolis with the distribution's own proposal function (Bernoulli, Categorical), else
+    NUTS when the distribution has a gradient and random-walk Metropolis when not; variables with the same sampler
+    and arguments are merged into one block; a transition runs every block's kernel once, in order.
+
+    ``stat_names = ["compound_results"]``; like the reference the sampler statistics are not put in the trace."""
+
+    _name = "compound"
+    _adaptation = None
+    _kernel = mcmc._CompoundStepTF
+    _grad = False
+
+    default_adapter_kwargs: dict = {}
+    default_kernel_kwargs: dict = {}
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.stat_names = ["compound_results"]
+        self._block_vars: List[List[str]] = []
+
+    def trace_fn(self, current_state, pkr):
+        return (pkr["log_accept"],) + tuple(self._deterministic_values(current_state))
+
+    @staticmethod
+    def _convert_sampler_methods(sampler_methods):
+        if not sampler_methods:
+            return {}
+        sampler_methods_dict = {}
+        for sampler_item in sampler_methods:
+            if len(sampler_item) not in [2, 3]:
+                raise ValueError(
+                    "You need to provide `sampler_methods` as the tuple of the length in [2, 3]. If additional kwargs "
+                    "for kernel are provided then the lenght of tuple is equal to 3."
+                )
+            if len(sampler_item) < 3:
+                var, sampler = sampler_item
+                kwargs = {}
+            else:
+                var, sampler, kwargs = sampler_item
+            if isinstance(var, (list, tuple)):
+                for var_ in var:
+                    sampler_methods_dict[var_] = (sampler, kwargs)
+            else:
+                sampler_methods_dict[var] = (sampler, kwargs)
+        return sampler_methods_dict
+
+    def _merge_samplers(self, make_kernel_fn, part_kernel_kwargs):
+        """Union variables whose sampler class and arguments are equal (proposal functions compared as instances);
+        returns (one (sampler, kwargs) per set, set sizes) and stores the variable order in ``parent_inds``."""
+        num_vars = len(make_kernel_fn)
+        parents = list(range(num_vars))
+        key = "new_state_fn"
+
+        def same_kwargs(item1, item2):
+            if (key in item1) != (key in item2):
+                return False
+            if key in item1 and not (item1[key].__self__ == item2[key].__self__):
+                return False
+            rest1 = {k: v for k, v in item1.items() if k != key}
+            rest2 = {k: v for k, v in item2.items() if k != key}
+            return rest1 == rest2
+
+        def get_set(p):
+            return p if parents[p] == p else get_set(parents[p])
+
+        for i, j in itertools.combinations(range(num_vars), 2):
+            if make_kernel_fn[i] == make_kernel_fn[j] and same_kwargs(part_kernel_kwargs[i], part_kernel_kwargs[j]):
+                p1, p2 = get_set(i), get_set(j)
+                if p1 != p2:
+                    parents[max(p1, p2)] = min(p1, p2)
+        parents = [get_set(p) for p in parents]
+        kernels, used = [], {}
+        for i, p in enumerate(parents):
+            if p not in used:
+                kernels.append((make_kernel_fn[i], part_kernel_kwargs[i]))
+                used[p] = True
+        parent_used, set_lengths = {}, []
+        for p in parents:
+            if p in parent_used:
+                set_lengths[parent_used[p]] += 1
+            else:
+                parent_used[p] = len(set_lengths)
+                set_lengths.append(1)
+        self.parent_inds = sorted(range(len(parents)), key=lambda k: parents[k])
+        return kernels, set_lengths
+
+    def _assign_default_methods(self, *, sampler_methods: Optional[List] = None,
+                                state: Optional[flow.SamplingState] = None, observed: Optional[dict] = None):
+        converted = CompoundStep._convert_sampler_methods(sampler_methods)
+        (_, state, _, _, continuous_distrs, discrete_distrs) = initialize_state(self.model, observed=observed, state=state)
+        init_keys = list(state.all_unobserved_values.keys())
+
+        make_kernel_fn: list = []
+        part_kernel_kwargs: list = []
+        func_names: list = []
+        for key in init_keys:
+            untrs_var, unscoped_tr_var = scope_remove_transformed_part_if_required(key, state.transformed_values)
+            distr = continuous_distrs.get(untrs_var, None)
+            if distr is None:
+                distr = discrete_distrs[untrs_var]
+            func = distr._default_new_state_part
+            if unscoped_tr_var in converted:
+                sampler, kwargs = converted[unscoped_tr_var]
+                if not distr._grad_support and sampler._grad:
+                    raise ValueError(
+                        "The `{}` doesn't support gradient, please provide an appropriate sampler method".format(
+                            unscoped_tr_var))
+                make_kernel_fn.append(sampler)
+                part_kernel_kwargs.append(dict(kwargs))
+                user_fn = part_kernel_kwargs[-1].get("new_state_fn", None)
+                if user_fn is not None:
+                    func = user_fn
+                if func and sampler._name == "rwm":
+                    part_kernel_kwargs[-1]["new_state_fn"] = partial(func)()
+            elif callable(func):
+                make_kernel_fn.append(RandomWalkM)
+                part_kernel_kwargs.append({"new_state_fn": partial(func)()})
+            else:
+                make_kernel_fn.append(NUTS if distr._grad_support else RandomWalkM)
+                part_kernel_kwargs.append({})
+            func_names.append(func._name if func else "default")
+
+        kernels, set_lengths = self._merge_samplers(make_kernel_fn, part_kernel_kwargs)
+        CompoundStep._log_variables(init_keys, kernels, set_lengths, self.parent_inds, func_names)
+        self.kernel_kwargs["compound_samplers"] = kernels
+        self.kernel_kwargs["compound_set_lengths"] = set_lengths
+        ordered = [init_keys[i] for i in self.parent_inds]
+        self._block_vars, at = [], 0
+        for n in set_lengths:
+            self._block_vars.append(ordered[at: at + n])
+            at += n
+
+    def __call__(self, *args, **kwargs):
+        if "compound_samplers" not in self.kernel_kwargs:
+            self._assign_default_methods(observed=kwargs.get("observed"), state=kwargs.get("state"))
+        return self._sample(*args, is_compound=True, **kwargs)
+
+    @staticmethod
+    def _log_variables(var_keys, kernel_kwargs, set_lengths, parent_inds, func_names):
+        var_keys = [var_keys[i] for i in parent_inds]
+        func_names = [func_names[i] for i in parent_inds]
+        log_output, curr = "", 0
+        for i, ((kernel, _), set_len) in enumerate(zip(kernel_kwargs, set_lengths)):
+            vars_ = var_keys[curr: curr + set_len]
+            log_output += ("\n" if i > 0 else "") + " -- {}[vars={}, proposal_function={}]".format(
+                kernel._name, [item.split("/")[1] for item in vars_], func_names[curr])
+            curr += set_len
+        _log.info(log_output)
+
+    def _blocks(self, burn_in: int):
+        """(block records for ``DeviceModel.compound``, one per merged sampler) from ``compound_samplers``."""
+        ir = self._device_model.ir
+        by_name = {rv.name: rv for rv in ir.rvs}
+        blocks = []
+        for (sampler, user_kwargs), names in zip(self.kernel_kwargs["compound_samplers"], self._block_vars):
+            mask = np.zeros(ir.D, dtype=np.float64)
+            for n in names:
+                rv = by_name[n]
+                mask[rv.offset: rv.offset + rv.size] = 1.0
+            mk = sampler._default_kernel_maker()
+            # the reference builds the sub-kernel from {**user kwargs, **class defaults} (tf_support.py:41): keep that
+            # precedence for the keys the class defines, pass everything else through
+            kk = {**{k: v for k, v in user_kwargs.items()}, **mk.kernel_kwargs}
+            if sampler._name in ("nuts", "nuts_simple", "hmc", "hmc_simple"):
+                discrete = [n for n in names if by_name[n].discrete]
+                if discrete:
+                    raise ValueError("Discrete distributions can't be used with gradient-based sampler: {}".format(discrete))
+                ak = dict(mk.adaptive_kwargs)
+                spec_kwargs = {k: v for k, v in kk.items() if k in _signature_keys(mk.kernel.__init__, 1)}
+                spec = mk.kernel(target_log_prob_fn=None, **spec_kwargs)
+                adapt_keys = _signature_keys(mk.adaptive_kernel.__init__, 1)
+                ak.update({k: v for k, v in user_kwargs.items() if k in adapt_keys})
+                ak.setdefault("num_adaptation_steps", burn_in)
+                ad = mk.adaptive_kernel(inner_kernel=None, **{k: v for k, v in ak.items() if not callable(v)})
+                eps0, scale, mode = self._step_size_policy(spec.step_size, self._num_chains)
+                if isinstance(ad, mcmc.SimpleStepSizeAdaptation):
+                    adapt = make_adapt(mode=mode, num_adaptation_steps=ad.num_adaptation_steps,
+                                       target_accept_prob=ad.target_accept_prob, kind=PM4_ADAPT_SIMPLE,
+                                       adaptation_rate=ad.adaptation_rate, enabled=True)
+                else:
+                    adapt = make_adapt(mode=mode, num_adaptation_steps=ad.num_adaptation_steps,
+                                       target_accept_prob=ad.target_accept_prob,
+                                       exploration_shrinkage=ad.exploration_shrinkage,
+                                       step_count_smoothing=ad.step_count_smoothing, decay_rate=ad.decay_rate, enabled=True)
+                blocks.append(dict(kind="nuts" if sampler._name.startswith("nuts") else "hmc", step_size=eps0,
+                                   dim_scale=mask if scale is None else mask * scale, adapt=adapt,
+                                   max_tree_depth=getattr(spec, "max_tree_depth", 10),
+                                   max_energy_diff=getattr(spec, "max_energy_diff", 1000.0),
+                                   num_leapfrog_steps=getattr(spec, "num_leapfrog_steps", 0)))
+            elif sampler._name == "rwm":
+                spec = mk.kernel(target_log_prob_fn=None,
+                                 **{k: v for k, v in kk.items() if k in _signature_keys(mk.kernel.__init__, 1)})
+                rw_kind, rw_scale = None, spec.scale
+                if spec.proposal is not None:
+                    rw_kind = np.zeros(ir.D, dtype=np.int32)
+                    rw_kind[mask > 0] = spec.proposal.device_code()
+                    rw_scale = spec.proposal.device_scale()
+                blocks.append(dict(kind="rwm", rw_scale=rw_scale, rw_kind=rw_kind, dim_scale=mask))
+            else:
+                raise NotImplementedError("sampler `{}` cannot be a block of the compound step".format(sampler._name))
+        return blocks
+
+    def _run_chains(self, init, burn_in):
+        self._check_chain_kwargs()
+        dm = self._device_model
+        theta0 = self._pack_init(init)
+        self._num_chains = theta0.shape[0]
+        out = dm.compound(self._blocks(burn_in), theta0, self._num_samples, burn_in, seed=self._seed_value(),
+                          dtype=self._dtype, warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
+                          chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        self._run_info = dict(kernel="compound", step_size=out["step_size"], blocks=self._block_vars)
+        self._last_states = out["states"]
+        return self._unpack_states(out["states"]), self.trace_fn(out["states"], out)
+
+
 # ---------------------------------------------------------------------------
 # log-density builder (reference :729-829)
 # ---------------------------------------------------------------------------
@@ -510,8 +730,8 @@ def build_logp_and_deterministic_functions(
         raise ValueError("Can't use both `state` and `observed` arguments")
     ir, init_state, deterministic_names = irmod.lower_model(model, observed=observed, state=state)
     unobserved_keys = list(init_state.all_unobserved_values.keys())
-    if parent_inds:
-        raise NotImplementedError("compound-step parent selection is outside this backend's scope")
+    # `parent_inds` (compound step): the reference reorders the state parts so that the variables of one sub-kernel
+    # are adjacent; the device state keeps the model's order and the blocks are masks over its dimensions
     dtype = np.dtype(dtype)
     holder: Dict[str, Any] = {}
 
