@@ -36,6 +36,7 @@ EXPORTS = [
     "pm4_last_error", "pm4_abi_version",
     "pm4_comm_create", "pm4_comm_connect", "pm4_comm_destroy", "pm4_model_attach_comm", "pm4_model_set_trace_sink", "pm4_model_get_mass_scale",
     "pm4_glm_work_bytes", "pm4_glm_logp_grad", "pm4_glm_gemm_tile",
+    "pm4_glm_image_bytes", "pm4_glm_build_image", "pm4_glm_fused_work_bytes", "pm4_glm_fused_logp_grad",
     "pm4_gp_work_bytes", "pm4_gp_logp_grad", "pm4_gp_launches", "pm4_gp_sample", "pm4_gp_predictive", "pm4_gp_points",
 ]
 

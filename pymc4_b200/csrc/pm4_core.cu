@@ -73,6 +73,7 @@ struct GlmTerm {
   int n = 0, P = 0, base = 0, ldxt = 0;
   int64_t x_off = 0, y_off = 0;
   float* d_xt = nullptr;  // [P, ldxt]
+  void* d_img = nullptr;   // pre-split tile image of X for the fused kernel (pm4_glm_build_image), or NULL
 };
 
 // a marginal GP likelihood term (PM4_T_MVN_EXPQUAD): pool offsets + how its three scalars are read from theta
@@ -240,6 +241,21 @@ static int upload_glm(pm4_model* m, const double*) {
     transpose_kernel<<<dim3((unsigned)((g.ldxt + 31) / 32), (unsigned)((g.P + 31) / 32)), dim3(32, 8)>>>(
         m->d_f32 + g.x_off, g.n, g.P, g.d_xt, g.ldxt);
     CU(cudaGetLastError());
+    // pre-split image for the fused kernel (2 x the bytes of X and of X^T): built when it fits comfortably
+    static const bool fused_off = getenv("PM4_GLM_FUSED") && atoi(getenv("PM4_GLM_FUSED")) == 0;
+    const int64_t img_bytes = fused_off ? -1 : pm4_glm_image_bytes(g.n, g.P);
+    if (img_bytes > 0 && !g.d_img) {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      if ((size_t)img_bytes < free_b / 2 && cudaMalloc(&g.d_img, (size_t)img_bytes) != cudaSuccess) {
+        g.d_img = nullptr;
+        cudaGetLastError();
+      }
+    }
+    if (g.d_img) {
+      int rc = pm4_glm_build_image(m->d_f32 + g.x_off, g.n, g.P, g.d_img, nullptr);
+      if (rc != 0) return fail(PM4_ECUDA, "GLM image kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    }
   }
   CU(cudaDeviceSynchronize());
   return PM4_OK;
@@ -301,7 +317,8 @@ static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, 
   if (m->glm.empty()) return PM4_OK;
   if (dtype != PM4_F32) return fail(PM4_ENOSYS, "dense GLM terms are evaluated in 3xTF32 on the tensor cores: float32 only");
   for (const GlmTerm& g : m->glm) {
-    const size_t need = (size_t)pm4_glm_work_bytes(g.n, g.P, C);
+    const bool fused = g.d_img && grad;
+    const size_t need = (size_t)(fused ? pm4_glm_fused_work_bytes(g.n, g.P, C) : pm4_glm_work_bytes(g.n, g.P, C));
     if (need > m->glm_work_bytes) {
       CU(cudaStreamSynchronize(st));
       if (m->glm_work) CU(cudaFree(m->glm_work));
@@ -310,9 +327,11 @@ static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, 
       if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GLM residuals: %s", need, cudaGetErrorString(e));
       m->glm_work_bytes = need;
     }
-    int rc = pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
-                               g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
-    g_launches += grad ? 4 : 3;
+    int rc = fused ? pm4_glm_fused_logp_grad(g.d_img, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D, g.base, C,
+                                             (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st)
+                   : pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
+                                       g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
+    g_launches += fused ? 2 : (grad ? 4 : 3);
     if (rc != 0) return fail(rc < 0 ? PM4_EINVAL : PM4_ECUDA, "GLM kernels: %s", rc < 0 ? "unsupported shape (at most 104 covariates)" : cudaGetErrorString((cudaError_t)rc));
   }
   return PM4_OK;
@@ -490,7 +509,7 @@ extern "C" int pm4_model_destroy(pm4_model_t* m) {
   if (!m) return PM4_OK;
   cudaFree(m->d_f32); cudaFree(m->d_f64); cudaFree(m->d_datai); cudaFree(m->d_term_n); cudaFree(m->d_op_blob);
   cudaFree(m->d_pf32); cudaFree(m->d_pf64); cudaFree(m->d_plani); cudaFree(m->d_plan_off);
-  for (GlmTerm& g : m->glm) cudaFree(g.d_xt);
+  for (GlmTerm& g : m->glm) { cudaFree(g.d_xt); cudaFree(g.d_img); }
   cudaFree(m->glm_work); cudaFree(m->d_glm_err); cudaFree(m->gp_work);
   cudaFree(m->mass_scale);
   if (m->sink_event) cudaEventDestroy(m->sink_event);

@@ -542,20 +542,443 @@ __global__ void glm_reduce_kernel(const double* __restrict__ LP2, const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused evaluation (value + gradient in ONE kernel; the residual matrix never leaves the SM):
+//   per (32 observations) x (128 chains) tile
+//     GEMM1   eta^T[chain, obs]  = beta[128 x K] . Xtile[32 x K]^T          -> TMEM (double-buffered, 2 x 32 columns)
+//     epilogue r = y - sigmoid(eta), ll += y eta - softplus(eta); r split hi/lo and written back to TENSOR MEMORY as
+//              GEMM2's A operand (beta, GEMM1's A operand, sits there too): with both A operands out of shared
+//              memory an MMA only reads its small B block, so the 128 B/cycle shared-memory port no longer bounds
+//              the 32-observation tiles (with A in shared memory every MMA re-read 4 KB of it)
+//     GEMM2   G[chain, p]       += R[128 x 32] . Xt_tile[Pp x 32]^T          -> TMEM (Pp columns, lives for the whole CTA)
+// The constant operand is PRE-SPLIT once at upload (glm_image_kernel): per tile the two TF32 terms of the X rows as
+// GEMM1's B image and of the transposed tile as GEMM2's B image, already in the core-matrix layout the UMMA
+// descriptors describe, so a tile arrives with two TMA bulk copies and no CUDA core touches it.  Roles (warp
+// specialised, mbarrier pipeline): warp 0 = TMA producer, warp 1 / warp 10 = MMA issuers of GEMM1 / GEMM2, warps 2..9 = epilogue (warp w owns TMEM
+// lanes 32 (w % 4) .. +31 = 32 chains, and 16 of the tile's 32 observations).  A lane of the accumulator is a CHAIN
+// here, so the residuals of one chain are 16 consecutive K elements (columns) of GEMM2's A operand -- one tcgen05.st
+// per TF32 term -- and the log-likelihood sum of a chain needs no cross-lane reduction.
+// ------------------------------------------------------------------------------------------
+constexpr int FT = 32;                               // observations per tile
+constexpr int F_EPI = 8;                             // epilogue warps
+constexpr int F_THREADS = 32 * (3 + F_EPI);          // TMA producer, GEMM1 issuer, 8 epilogue warps, GEMM2 issuer
+constexpr int F_NSX = 4, F_NSXT = 2;                 // pipeline stages of the two operand images
+// tensor-memory map (512 columns): eta buffers | G | beta hi | beta lo | R[buffer][hi, lo]
+constexpr uint32_t F_TMEM_COLS = 512;
+constexpr uint32_t F_G_COL = 64, F_BHI_COL = 176, F_BLO_COL = 280, F_R_COL = 384;
+enum { FB_FULL_X = 0, FB_EMPTY_X = FB_FULL_X + F_NSX, FB_FULL_XT = FB_EMPTY_X + F_NSX, FB_EMPTY_XT = FB_FULL_XT + F_NSXT,
+       FB_ETA_FULL = FB_EMPTY_XT + F_NSXT, FB_ETA_EMPTY = FB_ETA_FULL + 2, FB_R_FULL = FB_ETA_EMPTY + 2 /* [buffer][half] */,
+       FB_R_EMPTY = FB_R_FULL + 4, FB_G_DONE = FB_R_EMPTY + 4, FB_COUNT };
+
+__device__ __forceinline__ bool mbar_wait_short(uint64_t* mbar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 400000000ll) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// A operand in TENSOR MEMORY (tcgen05.mma ".ts" form): lane i of the A block holds row i, one 32-bit column per tf32
+// element of K.  A constant (or register-produced) A operand then costs no shared-memory bandwidth per MMA -- with the
+// operand in shared memory every 128 x N x 8 MMA re-reads the 4 KB A block, which bounds small-N tiles at 128 bytes per
+// cycle.  Test kernel for that form: same contract as gemm_nt_3xtf32_kernel.
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(128, 1) gemm_ts_3xtf32_kernel(const float* __restrict__ A, int lda,
+                                                                const float* __restrict__ B, int ldb,
+                                                                float* __restrict__ C, int ldc, int K, int passes,
+                                                                int* __restrict__ error) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t op_bytes = (uint32_t)TILE * (uint32_t)K * 4u;
+  unsigned char* b_hi = smem;
+  unsigned char* b_lo = b_hi + op_bytes;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(b_lo + op_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t A_HI = 128, A_LO = 256;  // columns of the two A terms (K <= 104 each); D at 0 .. 127
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int idx = tid; idx < TILE * K; idx += blockDim.x) {
+    const int row = idx / K, k = idx - row * K;
+    const float b = B[(size_t)row * ldb + k];
+    const float bh = to_tf32(b);
+    const uint32_t off = op_offset(row, k, K);
+    *reinterpret_cast<float*>(b_hi + off) = bh;
+    *reinterpret_cast<float*>(b_lo + off) = to_tf32(b - bh);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  {  // row = this thread's TMEM lane: its K values go to consecutive columns, 8 at a time
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = A[(size_t)row * lda + k0 + j];
+        const float h = to_tf32(a);
+        hi[j] = __float_as_uint(h);
+        lo[j] = __float_as_uint(to_tf32(a - h));
+      }
+      tmem_st8(lane_addr + A_HI + (uint32_t)k0, hi);
+      tmem_st8(lane_addr + A_LO + (uint32_t)k0, lo);
+    }
+    tmem_st_wait();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(TILE, TILE);
+    const uint32_t sbo = (uint32_t)(K / 4) * 128u, lbo = 128u;
+    uint32_t acc = 0;
+    for (int pass = 0; pass < passes; ++pass) {  // hi*hi, lo*hi, hi*lo
+      const uint32_t ac = pass == 1 ? A_LO : A_HI;
+      const unsigned char* bp = pass == 2 ? b_lo : b_hi;
+      for (int ks = 0; ks < K / UMMA_K; ++ks) {
+        mma_tf32_ts(tmem, tmem + ac + (uint32_t)ks * UMMA_K, make_desc(smem_u32(bp) + (uint32_t)ks * 256u, lbo, sbo), idesc, acc);
+        acc = 1;
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+  }
+  const bool done = mbar_wait_short(mbar, 0u);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!done) {
+    if (tid == 0 && error) *error = 1;
+  } else {
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < TILE; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) C[(size_t)row * ldc + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// bytes of one tile of the pre-split image: [X rows hi | lo] (GEMM1's B, 32 x K) then [X^T hi | lo] (GEMM2's B, Pp x 32)
+__host__ __device__ inline size_t fused_tile_bytes(int K, int Pp) { return 2 * (size_t)FT * K * 4 + 2 * (size_t)Pp * FT * 4; }
+
+__global__ void __launch_bounds__(256) glm_image_kernel(const float* __restrict__ X, int n, int P, int K, int Pp,
+                                                        unsigned char* __restrict__ img) {
+  const int tile = blockIdx.x, n0 = tile * FT;
+  unsigned char* xa_hi = img + (size_t)tile * fused_tile_bytes(K, Pp);
+  unsigned char* xa_lo = xa_hi + (size_t)FT * K * 4;
+  unsigned char* xb_hi = xa_lo + (size_t)FT * K * 4;
+  unsigned char* xb_lo = xb_hi + (size_t)Pp * FT * 4;
+  for (int idx = threadIdx.x; idx < FT * K; idx += blockDim.x) {
+    const int r = idx / K, k = idx - r * K;
+    const float v = (n0 + r < n && k < P) ? X[(size_t)(n0 + r) * P + k] : 0.0f;
+    const float h = to_tf32(v);
+    const uint32_t off = op_offset(r, k, K);
+    *reinterpret_cast<float*>(xa_hi + off) = h;
+    *reinterpret_cast<float*>(xa_lo + off) = to_tf32(v - h);
+  }
+  for (int idx = threadIdx.x; idx < Pp * FT; idx += blockDim.x) {
+    const int k = idx / Pp, p = idx - k * Pp;  // consecutive threads read consecutive covariates of one observation
+    const float v = (p < P && n0 + k < n) ? X[(size_t)(n0 + k) * P + p] : 0.0f;
+    const float h = to_tf32(v);
+    const uint32_t off = op_offset(p, k, FT);
+    *reinterpret_cast<float*>(xb_hi + off) = h;
+    *reinterpret_cast<float*>(xb_lo + off) = to_tf32(v - h);
+  }
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned char* __restrict__ img,
+                                                                 const float* __restrict__ y, int n, int P,
+                                                                 const float* __restrict__ theta, int ldt, int base, int C,
+                                                                 double* __restrict__ LPp, float* __restrict__ GP, int Cp,
+                                                                 int Pp, int* __restrict__ error) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int K = (P + 7) & ~7, K4 = K >> 2;
+  const uint32_t xa_part = (uint32_t)FT * K * 4u, xb_part = (uint32_t)Pp * FT * 4u;
+  unsigned char* xa0 = smem;                           // F_NSX stages of [hi | lo] (GEMM1's B)
+  unsigned char* xb0 = xa0 + (size_t)F_NSX * 2 * xa_part;  // F_NSXT stages of [hi | lo] (GEMM2's B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xb0 + (size_t)F_NSXT * 2 * xb_part);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + FB_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = blockIdx.y * TILE, n_tiles = (n + FT - 1) / FT;
+  const int stride = (int)gridDim.x;
+  const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + stride - 1) / stride : 0;
+  const size_t tile_bytes = fused_tile_bytes(K, Pp);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(F_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    for (int b = 0; b < FB_COUNT; ++b) {
+      const uint32_t cnt = (b >= FB_ETA_EMPTY && b < FB_ETA_EMPTY + 2) ? (uint32_t)F_EPI
+                           : (b >= FB_R_FULL && b < FB_R_FULL + 4)     ? (uint32_t)(F_EPI / 2)
+                                                                       : 1u;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(cnt));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const bool epi = warp >= 2 && warp < 2 + F_EPI;
+  const int q = warp & 3, h = (warp - 2) >> 2, row = q * 32 + lane;  // epilogue warps: TMEM lane quarter, observation half
+  const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+  if (epi) {
+    // the CTA's chain tile beta[c0 .. c0 + 127, :] goes to tensor memory once, split into its two TF32 terms: GEMM1's
+    // A operand (lane = chain, one column per covariate), which then costs no shared-memory bandwidth
+    const bool live_row = c0 + row < C;
+    const float* tp = theta + (size_t)(c0 + row) * ldt + base;
+    for (int k0 = 8 * h; k0 < K; k0 += 16) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = (live_row && k0 + j < P) ? tp[k0 + j] : 0.0f;
+        const float hv = to_tf32(v);
+        hi[j] = __float_as_uint(hv);
+        lo[j] = __float_as_uint(to_tf32(v - hv));
+      }
+      tmem_st8(lane_addr + F_BHI_COL + (uint32_t)k0, hi);
+      tmem_st8(lane_addr + F_BLO_COL + (uint32_t)k0, lo);
+    }
+    tmem_st_wait();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  bool ok = true;
+
+  if (warp == 0) {
+    // ---- TMA producer ------------------------------------------------------------------------------------------
+    if (lane == 0 && nt > 0) {
+      auto src = [&](int i) { return img + (size_t)((int)blockIdx.x + i * stride) * tile_bytes; };
+      auto load_x = [&](int i) { tma_load(xa0 + (size_t)(i % F_NSX) * 2 * xa_part, src(i), 2 * xa_part, bars + FB_FULL_X + (i % F_NSX)); };
+      auto load_xt = [&](int i) { tma_load(xb0 + (size_t)(i % F_NSXT) * 2 * xb_part, src(i) + 2 * xa_part, 2 * xb_part, bars + FB_FULL_XT + (i % F_NSXT)); };
+      for (int i = 0; i < F_NSX && i < nt; ++i) load_x(i);
+      for (int i = 0; i < F_NSXT && i < nt; ++i) load_xt(i);
+      for (int i = 0; i < nt && ok; ++i) {
+        if (i + F_NSX < nt) {  // the stage is free once GEMM1 of tile i has read it
+          ok = mbar_wait_short(bars + FB_EMPTY_X + (i % F_NSX), (uint32_t)(i / F_NSX) & 1u);
+          if (ok) load_x(i + F_NSX);
+        }
+        if (ok && i + F_NSXT < nt) {  // ... once GEMM2 of tile i has read it
+          ok = mbar_wait_short(bars + FB_EMPTY_XT + (i % F_NSXT), (uint32_t)(i / F_NSXT) & 1u);
+          if (ok) load_xt(i + F_NSXT);
+        }
+      }
+      if (!ok && error) *error = 3;
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer of GEMM1 (eta tiles): A = beta in tensor memory, B = the X rows of the tile in shared memory ----
+    // (descriptors are built once; a K step of 8 tf32 = 256 bytes = 16 units of the descriptor's 16-byte address field)
+    if (lane == 0 && nt > 0) {
+      const uint32_t idesc1 = make_idesc(TILE, FT);
+      const uint32_t sbo1 = (uint32_t)K4 * 128u, lbo = 128u;
+      const int KS = K / UMMA_K;
+      for (int i = 0; i < nt && ok; ++i) {
+        const int b = i & 1, s2 = i % F_NSX;
+        if (i >= 2) ok = mbar_wait_short(bars + FB_ETA_EMPTY + b, (uint32_t)((i - 2) >> 1) & 1u);  // epilogue of tile i - 2
+        if (ok) ok = mbar_wait_short(bars + FB_FULL_X + s2, (uint32_t)(i / F_NSX) & 1u);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t dx_hi = make_desc(smem_u32(xa0 + (size_t)s2 * 2 * xa_part), lbo, sbo1);
+        const uint64_t dx_lo = make_desc(smem_u32(xa0 + (size_t)s2 * 2 * xa_part + xa_part), lbo, sbo1);
+        const uint32_t d = tmem + (uint32_t)b * FT, a_hi = tmem + F_BHI_COL, a_lo = tmem + F_BLO_COL;
+        mma_tf32_ts(d, a_hi, dx_hi, idesc1, 0u);  // hi*hi
+#pragma unroll 4
+        for (int ks = 1; ks < KS; ++ks) mma_tf32_ts(d, a_hi + (uint32_t)(ks * UMMA_K), dx_hi + (uint64_t)(ks * 16), idesc1, 1u);
+#pragma unroll 4
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, a_lo + (uint32_t)(ks * UMMA_K), dx_hi + (uint64_t)(ks * 16), idesc1, 1u);  // lo*hi
+#pragma unroll 4
+        for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, a_hi + (uint32_t)(ks * UMMA_K), dx_lo + (uint64_t)(ks * 16), idesc1, 1u);  // hi*lo
+        mma_commit(bars + FB_ETA_FULL + b);
+        mma_commit(bars + FB_EMPTY_X + s2);
+      }
+      if (!ok && error) *error = 4;
+    }
+  } else if (warp == 2 + F_EPI) {
+    // ---- MMA issuer of GEMM2 (gradient accumulator): A = the residuals in tensor memory (written by the epilogue),
+    // B = the transposed tile; its own thread, so neither instruction stream waits for the other
+    if (lane == 0 && nt > 0) {
+      const uint32_t idesc2 = make_idesc(TILE, Pp);
+      const uint32_t sbo2 = (uint32_t)(FT / 4) * 128u, lbo = 128u;
+      const uint32_t d = tmem + F_G_COL;
+      uint32_t acc_g = 0;
+      for (int i = 0; i < nt && ok; ++i) {
+        const int b = i & 1, s2 = i % F_NSXT;
+        ok = mbar_wait_short(bars + FB_FULL_XT + s2, (uint32_t)(i / F_NSXT) & 1u);
+        const uint64_t dt_hi = make_desc(smem_u32(xb0 + (size_t)s2 * 2 * xb_part), lbo, sbo2);
+        const uint64_t dt_lo = make_desc(smem_u32(xb0 + (size_t)s2 * 2 * xb_part + xb_part), lbo, sbo2);
+        const uint32_t r_hi = tmem + F_R_COL + (uint32_t)b * 64u, r_lo = r_hi + 32u;
+        for (int hh = 0; hh < 2 && ok; ++hh) {  // the two 16-observation halves of R become ready independently
+          ok = mbar_wait_short(bars + FB_R_FULL + 2 * b + hh, (uint32_t)(i >> 1) & 1u);
+          if (!ok) break;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t c0k = (uint32_t)(2 * hh) * UMMA_K, c1k = c0k + UMMA_K;
+          const uint64_t o0 = (uint64_t)(2 * hh * 16), o1 = o0 + 16;
+          mma_tf32_ts(d, r_hi + c0k, dt_hi + o0, idesc2, acc_g);
+          mma_tf32_ts(d, r_hi + c1k, dt_hi + o1, idesc2, 1u);
+          mma_tf32_ts(d, r_lo + c0k, dt_hi + o0, idesc2, 1u);
+          mma_tf32_ts(d, r_lo + c1k, dt_hi + o1, idesc2, 1u);
+          mma_tf32_ts(d, r_hi + c0k, dt_lo + o0, idesc2, 1u);
+          mma_tf32_ts(d, r_hi + c1k, dt_lo + o1, idesc2, 1u);
+          acc_g = 1;
+          mma_commit(bars + FB_R_EMPTY + 2 * b + hh);
+        }
+        if (ok) mma_commit(bars + FB_EMPTY_XT + s2);
+      }
+      if (ok) mma_commit(bars + FB_G_DONE);
+      if (!ok && error) *error = 6;
+    }
+  } else {
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (chains), observations 16 h .. 16 h + 15 -----------
+    double ll_acc = 0.0;
+    for (int i = 0; i < nt && ok; ++i) {
+      const int b = i & 1, n0 = ((int)blockIdx.x + i * stride) * FT;
+      ok = mbar_wait_short(bars + FB_ETA_FULL + b, (uint32_t)(i >> 1) & 1u);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[16];
+      tmem_ld16(lane_addr + (uint32_t)b * FT + (uint32_t)(16 * h), v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + FB_ETA_EMPTY + b);
+      uint32_t rh[16], rl[16];
+      float ll = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int obs = n0 + 16 * h + j;
+        const bool live = obs < n;
+        const float yv = live ? __ldg(y + obs) : 0.0f;
+        const float eta = __uint_as_float(v[j]);
+        // softplus(eta) = max(eta, 0) + log1p(exp(-|eta|)); sigmoid from the same exponential (MUFU ex2 / lg2 / rcp)
+        const float e = __expf(-fabsf(eta));
+        const float sp = fmaxf(eta, 0.0f) + __logf(1.0f + e);
+        const float rc = __fdividef(1.0f, 1.0f + e);
+        const float sg = eta >= 0.0f ? rc : e * rc;
+        ll += live ? yv * eta - sp : 0.0f;
+        const float r = live ? yv - sg : 0.0f;
+        const float hv = to_tf32(r);
+        rh[j] = __float_as_uint(hv);
+        rl[j] = __float_as_uint(to_tf32(r - hv));
+      }
+      ll_acc += (double)ll;
+      if (i >= 2) {  // GEMM2 of tile i - 2 has read this half of this R buffer
+        ok = mbar_wait_short(bars + FB_R_EMPTY + 2 * b + h, (uint32_t)((i - 2) >> 1) & 1u);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      // the residuals of a chain are 16 consecutive K elements of GEMM2's A operand: straight into tensor memory
+      tmem_st16(lane_addr + F_R_COL + (uint32_t)b * 64u + (uint32_t)(16 * h), rh);
+      tmem_st16(lane_addr + F_R_COL + (uint32_t)b * 64u + 32u + (uint32_t)(16 * h), rl);
+      tmem_st_wait();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + FB_R_FULL + 2 * b + h);
+    }
+    // per-chain partial of the log-likelihood (this CTA's observations, this half) and of the gradient
+    LPp[((size_t)blockIdx.x * 2 + h) * Cp + c0 + row] = ok ? ll_acc : 0.0;
+    if (ok && nt > 0) ok = mbar_wait_short(bars + FB_G_DONE, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* dst = GP + ((size_t)blockIdx.x * Cp + c0 + row) * Pp;
+    for (int cc = 16 * h; cc < Pp; cc += 32) {
+      uint32_t v[16];
+      if (ok && nt > 0) tmem_ld16(lane_addr + F_G_COL + (uint32_t)cc, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[cc + j] = (ok && nt > 0) ? __uint_as_float(v[j]) : 0.0f;
+    }
+    if (!ok && lane == 0 && error) *error = 5;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(F_TMEM_COLS));
+}
+
+// fixed-order reductions in double precision of the fused kernel's partials
+__global__ void glm_fused_reduce_kernel(const double* __restrict__ LPp, const float* __restrict__ GP, int groups, int Cp,
+                                        int Pp, int C, int P, float* __restrict__ lp, float* __restrict__ grad, int ldg, int base) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < C) {
+    double s = 0;
+    for (int g = 0; g < 2 * groups; ++g) s += LPp[(size_t)g * Cp + idx];
+    lp[idx] += (float)s;
+  }
+  if (idx < C * P) {
+    const int c = idx / P, p = idx - c * P;
+    double s = 0;
+    for (int g = 0; g < groups; ++g) s += (double)GP[((size_t)g * Cp + c) * Pp + p];
+    grad[(size_t)c * ldg + base + p] += (float)s;
+  }
+}
+
 }  // namespace
 
 // test entry: one 128 x 128 tile; passes = 1 (plain TF32) or 3 (3xTF32); returns 0, a CUDA error code, or
 // -62 (ETIME) when the MMA never completed
 extern "C" int pm4_glm_gemm_tile(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int K, int passes,
                                  void* stream) {
+  const bool ts = passes < 0;  // negative: the same product with the A operand in tensor memory
+  if (ts) passes = -passes;
   if (K <= 0 || K % UMMA_K != 0 || K > 104 || passes < 1 || passes > 3) return -22;
   const size_t smem = 4 * (size_t)TILE * K * 4 + 64;
   cudaError_t e = cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_ts_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int* d_err = nullptr;
   if ((e = cudaMalloc(&d_err, sizeof(int))) != cudaSuccess) return (int)e;
   cudaMemsetAsync(d_err, 0, sizeof(int), (cudaStream_t)stream);
-  gemm_nt_3xtf32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, K, passes, d_err);
+  if (ts) gemm_ts_3xtf32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, K, passes, d_err);
+  else gemm_nt_3xtf32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, K, passes, d_err);
   int err = 0;
   e = cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
@@ -610,5 +1033,51 @@ extern "C" int pm4_glm_logp_grad(const float* X, const float* Xt, int ldxt, cons
   const int work_items = grad ? C * P : C;
   glm_lp_kernel<<<dim3(Cp / 32, LP_GROUPS), 256, 0, st>>>(LP, n_tiles, Cp, LP2);
   glm_reduce_kernel<<<(work_items + 255) / 256, 256, 0, st>>>(LP2, GP, splits, Cp, Pp, C, P, lp, grad, ldg, base);
+  return (int)cudaGetLastError();
+}
+
+// ---- fused path: pre-split image of the constant operand + one kernel per evaluation ------------------------------
+static int fused_groups(int n, int Cp) {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n_tiles = (n + FT - 1) / FT;
+  int groups = sms / (Cp / TILE);
+  if (groups < 1) groups = 1;
+  return groups > n_tiles ? n_tiles : groups;
+}
+
+extern "C" int64_t pm4_glm_image_bytes(int n, int P) {
+  if (n <= 0 || P <= 0 || P > 104) return -1;
+  const int K = (P + 7) & ~7, Pp = (P + 15) / 16 * 16;
+  return (int64_t)((n + FT - 1) / FT) * (int64_t)fused_tile_bytes(K, Pp);
+}
+
+extern "C" int pm4_glm_build_image(const float* X, int n, int P, void* image, void* stream) {
+  if (!X || !image || n <= 0 || P <= 0 || P > 104) return -22;
+  const int K = (P + 7) & ~7, Pp = (P + 15) / 16 * 16;
+  glm_image_kernel<<<(unsigned)((n + FT - 1) / FT), 256, 0, (cudaStream_t)stream>>>(X, n, P, K, Pp, (unsigned char*)image);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int64_t pm4_glm_fused_work_bytes(int n, int P, int C) {
+  const int64_t Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16;
+  const int64_t groups = fused_groups(n, (int)Cp);
+  return 8 * 2 * groups * Cp + 4 * groups * Cp * Pp + 256;
+}
+
+extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n, int P, const float* theta, int ldt, int base,
+                                       int C, float* lp, float* grad, int ldg, void* work, int* error_dev, void* stream) {
+  if (!image || !y || !theta || !lp || !grad || !work || n <= 0 || P <= 0 || P > 104 || C <= 0) return -22;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16, K = (P + 7) & ~7;
+  const int groups = fused_groups(n, Cp);
+  double* LPp = (double*)work;
+  float* GP = (float*)(LPp + (size_t)2 * groups * Cp);
+  const size_t smem = (size_t)F_NSX * 2 * FT * K * 4 + (size_t)F_NSXT * 2 * Pp * FT * 4 + 8 * FB_COUNT + 16;
+  cudaError_t e = cudaFuncSetAttribute(glm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  glm_fused_kernel<<<dim3(groups, Cp / TILE), F_THREADS, smem, st>>>((const unsigned char*)image, y, n, P, theta, ldt, base, C,
+                                                                      LPp, GP, Cp, Pp, error_dev);
+  glm_fused_reduce_kernel<<<(C * P + 255) / 256, 256, 0, st>>>(LPp, GP, groups, Cp, Pp, C, P, lp, grad, ldg, base);
   return (int)cudaGetLastError();
 }

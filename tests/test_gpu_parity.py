@@ -601,6 +601,14 @@ def test_tcgen05_gemm_tile_3xtf32():
             assert rc == 0
             errs.append(float((C.double() - ref).abs().max() / ref.abs().max()))
         assert 1e-5 < errs[0] < 2e-3 and errs[1] < 5e-6, errs
+        # the same products with the A operand held in tensor memory (negative `passes`): the form the fused GLM kernel uses
+        errs = []
+        for passes in (-1, -3):
+            C = torch.zeros(128, 128, device="cuda")
+            rc = L.pm4_glm_gemm_tile(A.data_ptr(), K, B.data_ptr(), K, C.data_ptr(), 128, K, passes, None)
+            assert rc == 0
+            errs.append(float((C.double() - ref).abs().max() / ref.abs().max()))
+        assert 1e-5 < errs[0] < 2e-3 and errs[1] < 5e-6, errs
 
 
 @pytest.mark.parametrize("n,p,C", [(3000, 20, 96), (700, 100, 300), (500, 10, 40), (333, 7, 5)])
