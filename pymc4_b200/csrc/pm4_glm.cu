@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/pm4b200.h"
 
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
                                                                  const float* __restrict__ y, int n, int P,
                                                                  const float* __restrict__ theta, int ldt, int base, int C,
                                                                  double* __restrict__ LPp, float* __restrict__ GP, int Cp,
-                                                                 int Pp, int* __restrict__ error) {
+                                                                 int Pp, int* __restrict__ pace, int* __restrict__ error) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int K = (P + 7) & ~7, K4 = K >> 2;
   const uint32_t xa_part = (uint32_t)FT * K * 4u, xb_part = (uint32_t)Pp * FT * 4u;
@@ -825,23 +826,48 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
 
   if (warp == 0) {
     // ---- TMA producer ------------------------------------------------------------------------------------------
-    if (lane == 0 && nt > 0) {
+    // The CTAs of one observation group (same blockIdx.x, one per chain tile) stream the SAME tile images: the first
+    // one to ask brings a tile in from HBM, the others find it in L2 -- as long as they stay close together.  They
+    // drift apart by a few per cent over ~1700 tiles, which is more than L2 holds, so every PACE_EVERY tiles a
+    // producer publishes its position and waits until the slowest CTA of its group is within PACE_WINDOW tiles
+    // (`pace` is NULL when the grid is not co-resident).
+    constexpr int PACE_EVERY = 8, PACE_WINDOW = 24;
+    if (nt > 0) {
       auto src = [&](int i) { return img + (size_t)((int)blockIdx.x + i * stride) * tile_bytes; };
       auto load_x = [&](int i) { tma_load(xa0 + (size_t)(i % F_NSX) * 2 * xa_part, src(i), 2 * xa_part, bars + FB_FULL_X + (i % F_NSX)); };
       auto load_xt = [&](int i) { tma_load(xb0 + (size_t)(i % F_NSXT) * 2 * xb_part, src(i) + 2 * xa_part, 2 * xb_part, bars + FB_FULL_XT + (i % F_NSXT)); };
-      for (int i = 0; i < F_NSX && i < nt; ++i) load_x(i);
-      for (int i = 0; i < F_NSXT && i < nt; ++i) load_xt(i);
-      for (int i = 0; i < nt && ok; ++i) {
-        if (i + F_NSX < nt) {  // the stage is free once GEMM1 of tile i has read it
-          ok = mbar_wait_short(bars + FB_EMPTY_X + (i % F_NSX), (uint32_t)(i / F_NSX) & 1u);
-          if (ok) load_x(i + F_NSX);
-        }
-        if (ok && i + F_NSXT < nt) {  // ... once GEMM2 of tile i has read it
-          ok = mbar_wait_short(bars + FB_EMPTY_XT + (i % F_NSXT), (uint32_t)(i / F_NSXT) & 1u);
-          if (ok) load_xt(i + F_NSXT);
-        }
+      if (lane == 0) {
+        for (int i = 0; i < F_NSX && i < nt; ++i) load_x(i);
+        for (int i = 0; i < F_NSXT && i < nt; ++i) load_xt(i);
       }
-      if (!ok && error) *error = 3;
+      int* const my_pace = pace ? pace + (size_t)blockIdx.x * gridDim.y : nullptr;
+      for (int i = 0; i < nt && ok; ++i) {
+        if (my_pace && (i % PACE_EVERY) == 0) {
+          if (lane == 0) atomicMax(my_pace + blockIdx.y, i);
+          const long long t0 = clock64();
+          for (;;) {  // lane l watches chain tile l of the group
+            int lo = i;
+            for (int c = lane; c < (int)gridDim.y; c += 32) lo = min(lo, *((volatile int*)my_pace + c));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            if (lo + PACE_WINDOW >= i || clock64() - t0 > 20000000ll) break;
+            __nanosleep(200);
+          }
+        }
+        if (lane == 0) {
+          if (i + F_NSX < nt) {  // the stage is free once GEMM1 of tile i has read it
+            ok = mbar_wait_short(bars + FB_EMPTY_X + (i % F_NSX), (uint32_t)(i / F_NSX) & 1u);
+            if (ok) load_x(i + F_NSX);
+          }
+          if (ok && i + F_NSXT < nt) {  // ... once GEMM2 of tile i has read it
+            ok = mbar_wait_short(bars + FB_EMPTY_XT + (i % F_NSXT), (uint32_t)(i / F_NSXT) & 1u);
+            if (ok) load_xt(i + F_NSXT);
+          }
+        }
+        ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+      }
+      if (my_pace && lane == 0) atomicMax(my_pace + blockIdx.y, 0x7fffffff);  // done: never hold the others back
+      if (!ok && lane == 0 && error) *error = 3;
     }
   } else if (warp >= F_W_G1 && warp < F_W_G1 + 3) {
     // ---- MMA issuers of GEMM1 (eta tiles): A = beta in tensor memory, B = the X rows of the tile in shared memory.
@@ -1107,7 +1133,7 @@ extern "C" int pm4_glm_build_image(const float* X, int n, int P, void* image, vo
 extern "C" int64_t pm4_glm_fused_work_bytes(int n, int P, int C) {
   const int64_t Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16;
   const int64_t groups = fused_groups(n, (int)Cp);
-  return 8 * F_NQ * groups * Cp + 4 * groups * Cp * Pp + 256;
+  return 8 * F_NQ * groups * Cp + 4 * groups * Cp * Pp + 4 * groups * (Cp / TILE) + 256;
 }
 
 extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n, int P, const float* theta, int ldt, int base,
@@ -1121,8 +1147,15 @@ extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n,
   const size_t smem = (size_t)F_NSX * 2 * FT * K * 4 + (size_t)F_NSXT * 2 * Pp * FT * 4 + 8 * FB_COUNT + 16;
   cudaError_t e = cudaFuncSetAttribute(glm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  // pacing of the CTAs that share tile images needs them co-resident (one CTA per SM): otherwise off
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int* pace = (int*)(GP + (size_t)groups * Cp * Pp);
+  static const bool pace_off = getenv("PM4_GLM_PACE") && atoi(getenv("PM4_GLM_PACE")) == 0;
+  if (groups * (Cp / TILE) > sms || Cp / TILE < 2 || pace_off) pace = nullptr;
+  if (pace && (e = cudaMemsetAsync(pace, 0, sizeof(int) * (size_t)groups * (Cp / TILE), st)) != cudaSuccess) return (int)e;
   glm_fused_kernel<<<dim3(groups, Cp / TILE), F_THREADS, smem, st>>>((const unsigned char*)image, y, n, P, theta, ldt, base, C,
-                                                                      LPp, GP, Cp, Pp, error_dev);
+                                                                      LPp, GP, Cp, Pp, pace, error_dev);
   glm_fused_reduce_kernel<<<(C * P + 255) / 256, 256, 0, st>>>(LPp, GP, groups, Cp, Pp, C, P, lp, grad, ldg, base);
   return (int)cudaGetLastError();
 }
