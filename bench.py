@@ -72,6 +72,11 @@ def parse_args():
     ap.add_argument("--leapfrogs", type=int, default=3, help="HMC leapfrog steps (logit workload; reference default 3)")
     ap.add_argument("--mass-windows", type=int, default=0,
                     help="diagonal mass-matrix windows during burn-in (backend extension; 0 = the reference behaviour)")
+    ap.add_argument("--couple-step-size", action="store_true",
+                    help="N > 1, pooled step size: ONE epsilon for the chains of ALL ranks (the box runs one pm.sample call: "
+                         "a 16-byte exchange over NVLink peer memory inside the sampler per burn-in transition).  Default: "
+                         "every rank is its own pm.sample call on its shard of the chains -- the reference has one process "
+                         "per device and pools the step size over that process's chains -- and no data-path collective")
     ap.add_argument("--no-secondary", action="store_true",
                     help="radon919 only: do not append the bounded runs of the other BASELINE configurations "
                          "(logit, gp, radon100k) as the line's \"secondary\" object")
@@ -172,12 +177,15 @@ def workload_config(args, n_gpus):
         "step": "one full sampling call: bootstrap + burn_in adaptive + draws kept NUTS transitions",
         "step_size": ("per-chain dual averaging from %.3g (leading chain axis; no cross-chain coupling)" % args.step_size)
                      if args.eps_mode == "per-chain" else
-                     ("pooled dual averaging from %.3g (scalar step_size, reference default; ONE epsilon for the chains "
-                      "of all ranks: per-transition exchange over NVLink peer memory inside the adaptation kernel)"
-                      % args.step_size),
+                     (("pooled dual averaging from %.3g (scalar step_size, reference default; ONE epsilon for the chains "
+                       "of all ranks: per-transition exchange over NVLink peer memory inside the sampler kernel)"
+                       if (n_gpus > 1 and args.couple_step_size) else
+                       "pooled dual averaging from %.3g (scalar step_size, reference default: one epsilon per pm.sample call "
+                       "= per rank, adapted from the mean acceptance of that rank's chains)") % args.step_size),
         "max_tree_depth": args.max_tree_depth,
         "parallelism": ("chains sharded, %d per GPU; " % args.chains)
-                       + ("no data-path collective" if (n_gpus == 1 or args.eps_mode == "per-chain") else
+                       + ("no data-path collective (NCCL all-gather of the monitored columns for R-hat / ESS only)"
+                          if (n_gpus == 1 or args.eps_mode == "per-chain" or not args.couple_step_size) else
                           "one 16-byte all-reduce per burn-in transition (pooled step size), none afterwards"),
         "l2": "L2 flushed (256 MiB write) between timed steps",
     }
@@ -535,7 +543,7 @@ def run_b200(args):
     C, B, S = args.chains, args.burn_in, args.draws
     shard = args.shard_rank if (world == 1 and args.shard_rank >= 0) else rank  # global chain offsets of this process
     comm = None
-    if world > 1 and args.eps_mode == "pooled":
+    if world > 1 and args.eps_mode == "pooled" and args.couple_step_size:
         # one pm.sample call sharded over the box: the scalar step size is adapted from the mean acceptance
         # of the chains of ALL ranks (mailboxes in peer memory, read over NVLink by the dual-averaging kernel)
         comm = _cabi.Communicator(local_rank, rank, world)

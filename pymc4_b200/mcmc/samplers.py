@@ -265,10 +265,26 @@ class _BaseSampler(metaclass=abc.ABCMeta):
 
     def _check_chain_kwargs(self):
         ck = self.chain_kwargs
-        if ck.get("num_steps_between_results", 0):
-            raise NotImplementedError("thinning (num_steps_between_results) is not supported")
+        if int(ck.get("num_steps_between_results", 0) or 0) < 0:
+            raise ValueError("num_steps_between_results must be non-negative")
         if ck.get("return_final_kernel_results", False) or ck.get("previous_kernel_results") is not None:
             raise NotImplementedError("resuming from kernel results is not supported")
+
+    # thinning (tfp sample_chain: `num_steps_between_results + 1` kernel steps per kept result, the result being the
+    # state after the last of them): the device runs every step and the kept draws are the strided view
+    def _thin(self) -> int:
+        return int(self.chain_kwargs.get("num_steps_between_results", 0) or 0)
+
+    def _draws_to_run(self) -> int:
+        return self._num_samples * (self._thin() + 1)
+
+    def _thin_out(self, out: dict, keys):
+        k = self._thin()
+        if k:
+            for key in keys:
+                if out.get(key) is not None:
+                    out[key] = out[key][k::k + 1]
+        return out
 
     def _deterministic_values(self, states):
         ir = self._device_model.ir
@@ -311,13 +327,13 @@ class HMC(_BaseSampler):
         spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
         eps0, scale, mode = self._step_size_policy(spec.step_size, C)
         adapt = self._adapt_cfg(mode)
-        cfg = make_hmc_cfg(C, self._num_samples, burn_in, step_size=eps0,
+        cfg = make_hmc_cfg(C, self._draws_to_run(), burn_in, step_size=eps0,
                            num_leapfrog_steps=spec.num_leapfrog_steps, seed=self._seed_value(), adapt=adapt,
                            warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
                            chain_offset=self.backend_kwargs.get("chain_offset", 0))
         if "comm" in self.backend_kwargs:
             dm.attach_comm(self.backend_kwargs["comm"])
-        out = dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale)
+        out = self._thin_out(dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale), ("states", "lp", "log_accept", "accepted"))
         self._run_info = dict(step_size=out["step_size"], kernel="hmc",
                               leapfrogs_per_transition=spec.num_leapfrog_steps)
         self._last_states = out["states"]
@@ -371,7 +387,7 @@ class NUTS(_BaseSampler):
         C = theta0.shape[0]
         spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
         eps0, scale, mode = self._step_size_policy(spec.step_size, C)
-        cfg = make_nuts_cfg(C, self._num_samples, burn_in, step_size=eps0, seed=self._seed_value(),
+        cfg = make_nuts_cfg(C, self._draws_to_run(), burn_in, step_size=eps0, seed=self._seed_value(),
                             max_tree_depth=spec.max_tree_depth, max_energy_diff=spec.max_energy_diff,
                             adapt=self._adapt_cfg(mode),
                             warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
@@ -380,9 +396,12 @@ class NUTS(_BaseSampler):
             dm.attach_comm(self.backend_kwargs["comm"])
         # a large trace leaves the device in slabs while the sampler keeps running (pm4_model_set_trace_sink): the
         # posterior arrays are then views of one pinned host buffer instead of per-variable copies made afterwards
-        trace_bytes = self._num_samples * C * dm.ir.D * np.dtype(self._dtype).itemsize
+        trace_bytes = self._draws_to_run() * C * dm.ir.D * np.dtype(self._dtype).itemsize
         slabs = int(self.backend_kwargs.get("trace_slabs", 8 if trace_bytes >= (64 << 20) else 0))
         out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale, stream_trace=slabs)
+        if "states_host" in out and self._thin():
+            out["states_host_ready"]()
+        self._thin_out(out, ("states", "lp", "leapfrogs", "diverging", "energy", "log_accept", "depth", "states_host"))
         self._run_info = dict(step_size=out["step_size"], total_leapfrogs=out["total_leapfrogs"],
                               depth=out["depth"], kernel="nuts", mass_scale=out.get("mass_scale"))
         self._last_states = out["states"]
@@ -433,12 +452,12 @@ class RandomWalkM(_BaseSampler):
         theta0 = self._pack_init(init)
         C = theta0.shape[0]
         spec = self._kernel(target_log_prob_fn=self.parallel_logpfn, **self.kernel_kwargs)
-        cfg = make_hmc_cfg(C, self._num_samples, burn_in, step_size=1.0, num_leapfrog_steps=0,
+        cfg = make_hmc_cfg(C, self._draws_to_run(), burn_in, step_size=1.0, num_leapfrog_steps=0,
                            seed=self._seed_value(), adapt=make_adapt(enabled=False),
                            warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
                            chain_offset=self.backend_kwargs.get("chain_offset", 0),
                            proposal=PM4_PROPOSAL_RANDOM_WALK, rw_scale=spec.scale)
-        out = dm.hmc(cfg, theta0, dtype=self._dtype)
+        out = self._thin_out(dm.hmc(cfg, theta0, dtype=self._dtype), ("states", "lp", "log_accept", "accepted"))
         self._run_info = dict(kernel="rwm", accepted=out["accepted"])
         self._last_states = out["states"]
         results = self._unpack_states(out["states"])
@@ -654,9 +673,12 @@ class CompoundStep(_BaseSampler):
         dm = self._device_model
         theta0 = self._pack_init(init)
         self._num_chains = theta0.shape[0]
-        out = dm.compound(self._blocks(burn_in), theta0, self._num_samples, burn_in, seed=self._seed_value(),
+        out = dm.compound(self._blocks(burn_in), theta0, self._draws_to_run(), burn_in, seed=self._seed_value(),
                           dtype=self._dtype, warps_per_block=self.backend_kwargs.get("warps_per_block", 0),
                           chain_offset=self.backend_kwargs.get("chain_offset", 0))
+        k = self._thin()
+        if k:
+            out["states"], out["lp"], out["log_accept"] = out["states"][k::k + 1], out["lp"][k::k + 1], out["log_accept"][:, k::k + 1]
         self._run_info = dict(kernel="compound", step_size=out["step_size"], blocks=self._block_vars)
         self._last_states = out["states"]
         return self._unpack_states(out["states"]), self.trace_fn(out["states"], out)

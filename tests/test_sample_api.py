@@ -320,3 +320,17 @@ def test_sample_latent_mvnormal_cholesky():
     post_mean = post_cov @ (y / s ** 2)
     np.testing.assert_allclose(f.mean(axis=0), post_mean, atol=0.05)
     np.testing.assert_allclose(np.cov(f.T), post_cov, atol=0.05)
+
+
+@pytest.mark.parametrize("sampler_type", ["nuts", "hmc", "rwm"])
+def test_thinning_keeps_every_kth_state(sampler_type):
+    """tfp sample_chain(num_steps_between_results=k): k + 1 kernel steps per kept result (reference samplers.py:191-207
+    forwards the keyword): the thinned trace is the strided view of the unthinned one from the same seed."""
+    kw = dict(num_chains=6, burn_in=20, seed=9, sampler_type=sampler_type)
+    full = pm.sample(M.schools_pm4(), num_samples=30, **kw)
+    thin = pm.sample(M.schools_pm4(), num_samples=10, num_steps_between_results=2, **kw)
+    for name in ("schools_pm4/eta", "schools_pm4/mu", "schools_pm4/tau"):
+        assert thin.posterior[name].shape[1] == 10
+        np.testing.assert_array_equal(thin.posterior[name], full.posterior[name][:, 2::3])
+    for name, v in thin.sample_stats.items():
+        np.testing.assert_array_equal(v, full.sample_stats[name][:, 2::3])
