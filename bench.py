@@ -671,6 +671,39 @@ def run_b200(args):
         }
         del om
 
+    # ---- the same data with the group effects written as offsets (one extra step): the configuration on which the
+    # reference-default sampler settings meet north_star check (c) -- split R-hat < 1.01, no divergences to speak of
+    noncentered = None
+    if args.workload == "radon919" and args.mass_windows == 0 and not is_logit and N_OBS == 919:
+        from pymc4_b200 import benchmodels as BM
+        from pymc4_b200.ir import lower_model as _lower
+
+        ir_n, _, _ = _lower(BM.hierarchical_model_noncentered(*BM.radon_synthetic(N_OBS, N_GROUPS)))
+        dm_n = _cabi.DeviceModel(ir_n, device=local_rank)
+        cfg_n = make_nuts_cfg(C, S, B, step_size=args.step_size, seed=args.seed + 78, adapt=adapt,
+                              max_tree_depth=args.max_tree_depth, warps_per_block=args.warps_per_block, chain_offset=shard * C)
+        dm_n.nuts(cfg_n, theta0, dtype=np.float32)  # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        on = dm_n.nuts(cfg_n, theta0, dtype=np.float32)
+        e1.record()
+        e1.synchronize()
+        ms_n = e0.elapsed_time(e1)
+        sn = diagnostics.summarize(on["states"], columns=cols)
+        noncentered = {
+            "what": "same data, same sampler settings, group effects written as offsets (alpha = mu_alpha + sigma_alpha * "
+                    "alpha_raw; pymc4_b200.benchmodels.hierarchical_model_noncentered): one step",
+            "value_this_rank": float(on["total_leapfrogs"].sum().item()) / (ms_n / 1e3), "unit": UNIT, "ms_per_step": ms_n,
+            "ess_per_sec_this_rank": sn["min_ess"] / (ms_n / 1e3),
+            "diagnostics": {"min_bulk_ess": sn["min_ess"], "max_split_rhat": sn["max_rhat"],
+                            "divergent_frac": float(on["diverging"].float().mean().item()),
+                            "mean_leapfrogs_per_draw": float(on["leapfrogs"].float().mean().item()),
+                            "step_size": float(on["step_size"][0].item())},
+        }
+        del on
+        dm_n.close()
+
     # ---- end-to-end arm: public sampler API, host buffers in, host trace out --------------
     e2e = None
     if not args.no_e2e:
@@ -849,6 +882,8 @@ def run_b200(args):
     }
     if mass_adapted is not None:
         line["mass_adapted"] = mass_adapted
+    if noncentered is not None:
+        line["noncentered"] = noncentered
     line["diagnostics"]["stuck_chain_frac"] = stuck_frac
     if secondary is not None:
         line["secondary"] = secondary

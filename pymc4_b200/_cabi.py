@@ -152,6 +152,7 @@ class DeviceModel:
             raise RuntimeError("libpm4b200: %s (code %d)" % (self.lib.pm4_last_error().decode(), rc))
 
     def close(self):
+        self.__dict__.pop("_pinned_pool", None)
         if getattr(self, "handle", None) is not None and self.handle.value:
             self.lib.pm4_model_destroy(self.handle)
             self.handle = ctypes.c_void_p()
@@ -184,6 +185,26 @@ class DeviceModel:
     @staticmethod
     def _p(t):
         return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def _pinned(self, shape, dtype):
+        """A pinned host tensor for a streamed trace.  Pinning gigabytes costs hundreds of milliseconds, so the model
+        keeps the last buffer and hands it out again once nothing but the pool refers to its storage (the posterior
+        arrays of a trace are NumPy views of it: while the caller holds the trace a new call gets a fresh buffer)."""
+        torch = self.torch
+        key = (tuple(int(v) for v in shape), dtype)
+        use_count = getattr(torch._C, "_storage_Use_Count", None)
+        pool = self.__dict__.setdefault("_pinned_pool", {})
+        base = pool.get(key)
+        if base is not None and use_count is not None:
+            try:
+                if use_count(base.untyped_storage()._cdata) <= 2:  # the pool's tensor + the temporary storage handle
+                    return base.view(key[0])
+            except Exception:
+                pass
+        base = torch.empty(key[0], dtype=dtype, pin_memory=True)
+        pool.clear()  # one buffer at a time
+        pool[key] = base
+        return base.view(key[0])
 
     def empty(self, shape, dtype):
         return self.torch.empty(shape, dtype=dtype, device=self._dev())
@@ -318,7 +339,7 @@ class DeviceModel:
         )
         host = copy_stream = None
         if stream_trace > 0 and want_states and S > 0 and not self.ir.lockstep:
-            host = torch.empty((S, C, D), dtype=td, pin_memory=True)
+            host = self._pinned((S, C, D), td)
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=self._dev())
             copy_stream = self._copy_stream

@@ -249,6 +249,47 @@ def test_radon_pooled_step_size_matches_the_oracle_regime(oracle_mod):
     assert abs(eg - eo) / eo < 0.15, (eg, eo)
 
 
+def test_radon_noncentered_meets_check_c_in_full(oracle_mod):
+    """(c) in FULL on a configuration that converges: the radon-919 data with the group effects written as offsets
+    (benchmodels.hierarchical_model_noncentered), reference-default sampler settings (scalar step size 0.1, pooled dual
+    averaging over the burn-in).  GPU FP32 (1024 chains) against the oracle's FP64 NUTS (96 chains): posterior means and
+    variances of the seven monitored columns within 3 Monte Carlo standard errors, split R-hat < 1.01 on every one of
+    them, divergent transitions equal to the oracle's (2.6 % after this short burn-in, 0.4 % after the bench's 1000), the same adapted step size and tree sizes."""
+    import torch
+
+    from pymc4_b200 import benchmodels as BM, diagnostics
+
+    idx, x, y, g = BM.radon_synthetic(919, 85)
+    ir, _, _ = lower_model(BM.hierarchical_model_noncentered(idx, x, y, g))
+    D = ir.D
+    B, S = 400, 400
+    Cg, Co = 1024, 96
+    adapt = make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B)
+    out = _dm(ir).nuts(make_nuts_cfg(Cg, S, B, step_size=0.1, seed=41, adapt=adapt), np.zeros((Cg, D), np.float32),
+                       dtype=np.float32)
+    ref = oracle_mod.Oracle(ir).nuts(make_nuts_cfg(Co, S, B, step_size=0.1, seed=43, adapt=adapt), np.zeros(D),
+                                     dtype=np.float64)
+    cols = [0, 1, 2, 87, 172, 173, 174]  # mu_a, mu_b, alpha_raw[0], beta_raw[0], log sigma_a, log sigma_b, log eps
+    summ = diagnostics.summarize(out["states"], columns=cols, gather=False)
+    assert summ["max_rhat"] < 1.01, summ["rhat"]
+    dg, do = float(out["diverging"].float().mean()), float(ref["diverging"].mean())
+    assert dg < 0.04 and abs(dg - do) < 0.01, (dg, do)  # 2.6 % after this short burn-in; 0.4 % after the bench's 1000 transitions
+    summ_ref = diagnostics.summarize(torch.as_tensor(ref["states"], dtype=torch.float32), columns=cols, gather=False)
+    assert summ_ref["max_rhat"] < 1.02, summ_ref["rhat"]  # 96 chains x 400 draws: the oracle agrees that it converges
+    xs = out["states"].cpu().numpy().astype(np.float64)[:, :, cols]
+    xr = ref["states"][:, :, cols]
+    # means: chain means are the independent unit; variances: per-chain variances likewise
+    for stat in (lambda v: v.mean(axis=0), lambda v: v.var(axis=0, ddof=1)):
+        sg, so = stat(xs), stat(xr)  # [C, 7]
+        se = np.sqrt(sg.var(axis=0, ddof=1) / Cg + so.var(axis=0, ddof=1) / Co)
+        z = np.abs(sg.mean(axis=0) - so.mean(axis=0)) / se
+        assert np.all(z < 3.0), z
+    eg, eo = float(out["step_size"][0]), float(ref["step_size"][0])
+    assert abs(eg - eo) / eo < 0.1, (eg, eo)
+    lg, lo = out["leapfrogs"].float().mean().item(), ref["leapfrogs"].mean()
+    assert abs(lg - lo) / lo < 0.08, (lg, lo)
+
+
 @pytest.mark.parametrize("mode", [PM4_EPS_POOLED, PM4_EPS_PER_CHAIN])
 def test_mass_matrix_windows_replay_against_the_oracle(mode, oracle_mod):
     """Diagonal mass-matrix windows (cross-chain spread -> step scale, dual averaging restarted): FP64 replay with
