@@ -456,12 +456,14 @@ int pm4_glm_gemm_tile(const float* A, int lda, const float* B, int ldb, float* C
  * bulk copies, runs eta = beta X^T, the Bernoulli epilogue and G += R Xt^T back to back on the tensor cores -- the
  * residual matrix stays in shared memory.  pm4_logp_grad / pm4_hmc_run / pm4_nuts_run use it whenever the image fits in
  * device memory (PM4_GLM_FUSED=0 keeps the two-kernel path).  Same contract as pm4_glm_logp_grad; grad must not be NULL;
- * work: pm4_glm_fused_work_bytes(n, P, C) bytes. */
+ * work: pm4_glm_fused_work_bytes(n, P, C) bytes.  gate_dev (device int or NULL): when it reads 0 at run time the call
+ * does nothing -- lock-step NUTS enqueues several leapfrogs ahead and lets the unused ones fall through. */
 int64_t pm4_glm_image_bytes(int n, int P);
 int pm4_glm_build_image(const float* X, int n, int P, void* image, void* stream);
 int64_t pm4_glm_fused_work_bytes(int n, int P, int C);
 int pm4_glm_fused_logp_grad(const void* image, const float* y, int n, int P, const float* theta, int ldt, int base,
-                            int C, float* lp, float* grad, int ldg, void* work, int* error_dev, void* stream);
+                            int C, float* lp, float* grad, int ldg, void* work, int* error_dev, const int* gate_dev,
+                            void* stream);
 
 /* Bytes of device scratch pm4_nuts_run / pm4_hmc_run allocate internally for C chains. */
 int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int max_tree_depth);

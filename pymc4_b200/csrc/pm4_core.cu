@@ -309,7 +309,8 @@ static int add_gp(pm4_model* m, int dtype, int C, const void* theta, void* lp, i
 }
 
 // add the dense terms' log-likelihood and gradient for C chains (theta [C, D] -> lp [C], grad [C, D] or NULL)
-static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, void* grad, cudaStream_t st) {
+static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, void* grad, cudaStream_t st,
+                   const int* gate = nullptr) {
   if (!m->gp.empty()) {
     int rc = add_gp(m, dtype, C, theta, lp, 1, true, grad, st);
     if (rc) return rc;
@@ -327,8 +328,9 @@ static int add_glm(pm4_model* m, int dtype, int C, const void* theta, void* lp, 
       if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMalloc(%zu) for the GLM residuals: %s", need, cudaGetErrorString(e));
       m->glm_work_bytes = need;
     }
+    if (gate && !fused) return fail(PM4_EINVAL, "gated evaluation needs the fused GLM path");
     int rc = fused ? pm4_glm_fused_logp_grad(g.d_img, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D, g.base, C,
-                                             (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st)
+                                             (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, gate, st)
                    : pm4_glm_logp_grad(m->d_f32 + g.x_off, g.d_xt, g.ldxt, m->d_f32 + g.y_off, g.n, g.P, (const float*)theta, m->D,
                                        g.base, C, (float*)lp, (float*)grad, m->D, m->glm_work, m->d_glm_err, st);
     g_launches += fused ? 2 : (grad ? 4 : 3);
@@ -978,7 +980,8 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
   if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.lpb = (float*)q;
   if ((rc = buf.get(&q, (size_t)C * 16))) return rc; p.h.da = (float*)q;
   if ((rc = buf.get(&q, (size_t)C * 4))) return rc; p.h.accept = (float*)q;
-  if ((rc = buf.get(&q, 16))) return rc; p.active = (int*)q;
+  if ((rc = buf.get(&q, 64 * sizeof(int)))) return rc; p.active = (int*)q;
+  int* const active_ring = (int*)q;
   p.h.C = C; p.h.D = D; p.h.B = cfg->num_burnin; p.h.S = cfg->num_results;
   p.h.chain_offset = cfg->chain_offset;
   p.h.adapt_enabled = r.adapt_enabled; p.h.adapt_pooled = r.adapt_pooled; p.h.adapt_kind = r.adapt_kind; p.h.num_adapt = r.num_adapt;
@@ -992,27 +995,44 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
   r.da = p.h.da; r.accept = p.h.accept;
   if (!m->h_flag) CU(cudaMallocHost((void**)&m->h_flag, sizeof(int)));
   pm4_mod_args_t a = m->args(dtype);
-  auto full_grad = [&](const float* th, float* lp, float* g) -> int {
+  auto full_grad = [&](const float* th, float* lp, float* g, const int* gate) -> int {
     MOD(m->f_logp(dtype, &a, C, th, lp, g, st), "logp_grad (lock-step)");
-    return add_glm(m, dtype, C, th, lp, g, st);
+    return add_glm(m, dtype, C, th, lp, g, st, gate);
   };
   const unsigned warp_grid = (unsigned)((C + 7) / 8);
   CU(cudaMemcpyAsync(p.h.th, theta0_dev, CD * 4, cudaMemcpyDeviceToDevice, st));
   if (total_leapfrogs_dev) CU(cudaMemsetAsync(total_leapfrogs_dev, 0, sizeof(int64_t) * (size_t)C, st));
-  if ((rc = full_grad(p.h.th, p.h.lp, p.h.g))) return rc;
+  if ((rc = full_grad(p.h.th, p.h.lp, p.h.g, nullptr))) return rc;
   pm4ls::init_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(p.h, (float)cfg->step_size);
+  // The leapfrogs of a transition are enqueued in BATCHES without a host round trip in between: every iteration
+  // counts the chains that asked for another gradient in its own word of a ring, the dense evaluation of the next
+  // iteration is gated on that word (a kernel that finds 0 returns at once), and the host reads one word per batch.
+  // Only the fused GLM evaluation can be gated; with GP terms (0.7 s per evaluation) the batch is one iteration.
+  bool gated = m->gp.empty() && !m->glm.empty();
+  for (const GlmTerm& g : m->glm) gated = gated && g.d_img != nullptr;
+  const bool no_batch = getenv("PM4_LOCKSTEP_BATCH") && atoi(getenv("PM4_LOCKSTEP_BATCH")) == 0;  // (read per call: tests toggle it)
+  if (no_batch) gated = false;
+  constexpr int RING = 64;
+  int* const ring = active_ring;
   for (int t = 0; t < T; ++t) {
     p.h.t = t;
     pm4ls::nuts_begin_kernel<<<warp_grid, 256, 0, st>>>(p);
     g_launches += 2;
+    int j = 0, batch = gated ? 4 : 1;
     for (;;) {
-      if ((rc = full_grad(p.thb, p.lpb, p.gb))) return rc;
-      CU(cudaMemsetAsync(p.active, 0, sizeof(int), st));
-      pm4ls::nuts_advance_kernel<<<warp_grid, 256, 0, st>>>(p);
-      g_launches += 1;
-      CU(cudaMemcpyAsync(m->h_flag, p.active, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemsetAsync(ring, 0, sizeof(int) * RING, st));  // the words this batch will count into (batch <= RING / 2)
+      const int j0 = j;
+      for (; j < j0 + batch; ++j) {
+        const int* gate = (gated && j > j0) ? ring + (j - 1 - j0) : nullptr;  // the first iteration of a batch is known to be needed
+        if ((rc = full_grad(p.thb, p.lpb, p.gb, gate))) return rc;
+        p.active = ring + (j - j0);
+        pm4ls::nuts_advance_kernel<<<warp_grid, 256, 0, st>>>(p);
+        g_launches += 1;
+      }
+      CU(cudaMemcpyAsync(m->h_flag, ring + (batch - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       if (*m->h_flag == 0) break;
+      if (gated && batch < RING / 2) batch *= 2;
     }
     pm4ls::nuts_finish_kernel<<<warp_grid, 256, 0, st>>>(p);
     if (p.h.adapt_enabled && p.h.adapt_pooled) MOD(m->f_da(dtype, &r, t, st), "pooled dual averaging");

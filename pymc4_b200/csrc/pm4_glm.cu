@@ -765,8 +765,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
                                                                  const float* __restrict__ y, int n, int P,
                                                                  const float* __restrict__ theta, int ldt, int base, int C,
                                                                  double* __restrict__ LPp, float* __restrict__ GP, int Cp,
-                                                                 int Pp, int* __restrict__ pace, int* __restrict__ error) {
+                                                                 int Pp, int* __restrict__ pace, const int* __restrict__ gate,
+                                                                 int* __restrict__ error) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  if (gate && *(const volatile int*)gate == 0) return;  // batched lock-step iterations: nobody asked for this gradient
   const int K = (P + 7) & ~7, K4 = K >> 2;
   const uint32_t xa_part = (uint32_t)FT * K * 4u, xb_part = (uint32_t)Pp * FT * 4u;
   unsigned char* xa0 = smem;                           // F_NSX stages of [hi | lo] (GEMM1's B)
@@ -1017,7 +1019,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
 
 // fixed-order reductions in double precision of the fused kernel's partials
 __global__ void glm_fused_reduce_kernel(const double* __restrict__ LPp, const float* __restrict__ GP, int groups, int Cp,
-                                        int Pp, int C, int P, float* __restrict__ lp, float* __restrict__ grad, int ldg, int base) {
+                                        int Pp, int C, int P, float* __restrict__ lp, float* __restrict__ grad, int ldg, int base,
+                                        const int* __restrict__ gate) {
+  if (gate && *(const volatile int*)gate == 0) return;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C) {
     double s = 0;
@@ -1137,7 +1141,8 @@ extern "C" int64_t pm4_glm_fused_work_bytes(int n, int P, int C) {
 }
 
 extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n, int P, const float* theta, int ldt, int base,
-                                       int C, float* lp, float* grad, int ldg, void* work, int* error_dev, void* stream) {
+                                       int C, float* lp, float* grad, int ldg, void* work, int* error_dev, const int* gate_dev,
+                                       void* stream) {
   if (!image || !y || !theta || !lp || !grad || !work || n <= 0 || P <= 0 || P > 104 || C <= 0) return -22;
   cudaStream_t st = (cudaStream_t)stream;
   const int Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16, K = (P + 7) & ~7;
@@ -1155,7 +1160,7 @@ extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n,
   if (groups * (Cp / TILE) > sms || Cp / TILE < 2 || pace_off) pace = nullptr;
   if (pace && (e = cudaMemsetAsync(pace, 0, sizeof(int) * (size_t)groups * (Cp / TILE), st)) != cudaSuccess) return (int)e;
   glm_fused_kernel<<<dim3(groups, Cp / TILE), F_THREADS, smem, st>>>((const unsigned char*)image, y, n, P, theta, ldt, base, C,
-                                                                      LPp, GP, Cp, Pp, pace, error_dev);
-  glm_fused_reduce_kernel<<<(C * P + 255) / 256, 256, 0, st>>>(LPp, GP, groups, Cp, Pp, C, P, lp, grad, ldg, base);
+                                                                      LPp, GP, Cp, Pp, pace, gate_dev, error_dev);
+  glm_fused_reduce_kernel<<<(C * P + 255) / 256, 256, 0, st>>>(LPp, GP, groups, Cp, Pp, C, P, lp, grad, ldg, base, gate_dev);
   return (int)cudaGetLastError();
 }

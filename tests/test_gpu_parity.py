@@ -723,6 +723,17 @@ def test_dense_glm_lockstep_nuts_parity(oracle_mod):
     assert np.median(d0[same]) < 1e-4
     np.testing.assert_allclose(out["energy"].cpu().numpy()[0][same], ref["energy"][0][same], rtol=1e-3, atol=1e-2)
     assert np.array_equal(out["total_leapfrogs"].cpu().numpy(), lf.sum(0))
+    # the leapfrogs of a transition are enqueued in batches, the dense evaluation of an iteration nobody asked for falls
+    # through on a device-side gate: bit-identical to one host round trip per leapfrog (PM4_LOCKSTEP_BATCH=0)
+    import os
+
+    os.environ["PM4_LOCKSTEP_BATCH"] = "0"
+    try:
+        one = _dm(ir).nuts(cfg, theta0.astype(np.float32), dtype=np.float32)
+    finally:
+        del os.environ["PM4_LOCKSTEP_BATCH"]
+    for key in ("states", "leapfrogs", "depth", "diverging", "energy", "lp"):
+        assert np.array_equal(out[key].cpu().numpy(), one[key].cpu().numpy()), key
     # adaptive runs, pooled and per-chain: same regime as the oracle
     B, S = 40, 30
     for mode in (PM4_EPS_POOLED, PM4_EPS_PER_CHAIN):
