@@ -213,6 +213,15 @@ int pm4o_nuts_run(const pm4_ir_t* ir, int dtype, const pm4_nuts_cfg_t* cfg, cons
                                  diverging, energy, log_accept, depth, step_size_out, total_leapfrogs, mass_scale_out);
 }
 
+int pm4o_compound_run(const pm4_ir_t* ir, int dtype, int C, int S, int B, uint64_t seed, int chain_offset,
+                      const pm4_compound_block_t* blocks, int n_blocks, const void* theta0, void* states, void* lp,
+                      void* step_size, void* log_accept, int32_t* leapfrogs) {
+  return dtype == PM4_F64 ? pm4o_compound_run_f64(ir, C, S, B, seed, chain_offset, blocks, n_blocks, theta0, states, lp,
+                                                  step_size, log_accept, leapfrogs)
+                          : pm4o_compound_run_f32(ir, C, S, B, seed, chain_offset, blocks, n_blocks, theta0, states, lp,
+                                                  step_size, log_accept, leapfrogs);
+}
+
 int pm4o_hmc_run(const pm4_ir_t* ir, int dtype, const pm4_hmc_cfg_t* cfg, const void* theta0,
                  const void* step_scale, const void* momenta, const void* uniforms, void* states,
                  void* lp, void* log_accept, uint8_t* accepted, void* step_size_out, void* traj) {

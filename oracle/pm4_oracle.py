@@ -10,7 +10,7 @@ import subprocess
 
 import numpy as np
 
-from pymc4_b200._cstructs import HMCCfg, NUTSCfg, PM4_F32, PM4_F64
+from pymc4_b200._cstructs import CompoundBlock, HMCCfg, NUTSCfg, PM4_F32, PM4_F64
 from pymc4_b200.ir import CIR, ModelIR, PackedIR
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -46,6 +46,7 @@ def lib():
         L.pm4o_prior_predictive.argtypes = [irp, i32, i64, i32, ctypes.c_uint64, vp, vp]
         L.pm4o_nuts_run.argtypes = [irp, i32, ctypes.POINTER(NUTSCfg)] + [vp] * 13
         L.pm4o_hmc_run.argtypes = [irp, i32, ctypes.POINTER(HMCCfg)] + [vp] * 10
+        L.pm4o_compound_run.argtypes = [irp, i32, i32, i32, i32, ctypes.c_uint64, i32, ctypes.POINTER(CompoundBlock), i32] + [vp] * 6
         L.pm4o_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint32,
                                          ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
         L.pm4o_philox4x32_10.restype = None
@@ -197,3 +198,33 @@ class Oracle:
             _ptr(out["accepted"]), _ptr(out["step_size"]), _ptr(out["traj"]))
         _check(rc, "hmc_run")
         return out
+
+
+def _compound(self, blocks, theta0, num_results, num_burnin, seed=0, dtype=np.float64, chain_offset=0):
+    """Oracle of ``pm4_compound_run``: ``blocks`` as for ``DeviceModel.compound`` (host arrays)."""
+    from pymc4_b200._cstructs import PM4_BLOCK_HMC, PM4_BLOCK_NUTS, PM4_BLOCK_RWM, make_adapt
+
+    theta0 = np.ascontiguousarray(theta0, dtype=dtype)
+    C, D, S = theta0.shape[0], self.ir.D, int(num_results)
+    arr = (CompoundBlock * len(blocks))()
+    keep = []
+    codes = {"nuts": PM4_BLOCK_NUTS, "hmc": PM4_BLOCK_HMC, "rwm": PM4_BLOCK_RWM}
+    for k, b in enumerate(blocks):
+        scale = np.ascontiguousarray(np.asarray(b["dim_scale"], dtype=np.float64).reshape(D), dtype=dtype)
+        kinds = None if b.get("rw_kind") is None else np.ascontiguousarray(b["rw_kind"], dtype=np.int32).reshape(D)
+        keep += [scale, kinds]
+        arr[k] = CompoundBlock(codes[b["kind"]], int(b.get("num_leapfrog_steps", 0)), int(b.get("max_tree_depth", 10)), 0,
+                               float(b.get("max_energy_diff", 1000.0)), float(b.get("step_size", 1.0)),
+                               float(b.get("rw_scale", 1.0)), b.get("adapt") or make_adapt(enabled=False),
+                               scale.ctypes.data, kinds.ctypes.data if kinds is not None else None)
+    out = dict(states=np.empty((S, C, D), dtype=dtype), lp=np.empty((S, C), dtype=dtype),
+               step_size=np.empty((len(blocks), C), dtype=dtype), log_accept=np.empty((len(blocks), S, C), dtype=dtype),
+               leapfrogs=np.zeros((len(blocks), S, C), dtype=np.int32))
+    rc = lib().pm4o_compound_run(self.packed.byref(), _code(dtype), C, S, int(num_burnin), ctypes.c_uint64(int(seed) & (2**64 - 1)),
+                                 int(chain_offset), arr, len(blocks), _ptr(theta0), _ptr(out["states"]), _ptr(out["lp"]),
+                                 _ptr(out["step_size"]), _ptr(out["log_accept"]), _ptr(out["leapfrogs"]))
+    _check(rc, "compound_run")
+    return out
+
+
+Oracle.compound = _compound

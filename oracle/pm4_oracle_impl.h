@@ -766,6 +766,9 @@ static void NAME(nuts_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, NAME(nuts_
   const REAL NEG_INF = -(REAL)INFINITY;
   if (injected_p) memcpy(b->p0, injected_p, nb);
   else NAME(draw_momentum)(cfg->seed, chain, t, D, b->p0);
+  if (scale) /* step scale 0 = frozen dimension (a block of the compound step conditions on it): no momentum */
+    for (int j = 0; j < D; ++j)
+      if (scale[j] == 0) b->p0[j] = 0;
   const REAL H0 = *lp - (REAL)0.5 * NAME(dot)(b->p0, b->p0, D);
 
   /* both ends of the trajectory start at the current point; `cur` is the end being extended,
@@ -1069,5 +1072,140 @@ int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL*
   for (int c = 0; c < C; ++c) if (step_size_out) step_size_out[c] = da[pooled ? 0 : c].eps;
   NAME(ws_free)(&ws);
   free(pth); free(th); free(gr); free(lp); free(acc); free(da);
+  return PM4_OK;
+}
+
+
+/* ----------------------------------------------------------------------------------------
+ * Compound step (/root/reference/pymc4/mcmc/samplers.py:490-726 CompoundStep,
+ * mcmc/tf_support.py:52-163 _CompoundStepTF.one_step, distributions/state_functions.py): per transition one
+ * transition of every block's kernel in order on the same chain state; a block's kernel sees the dimensions it does
+ * not own (step scale 0) frozen at their current values -- _target_log_prob_fn_part_compound.  Every block has its
+ * own adaptation state and its own Philox key (seed + golden ratio * block).  Mirrors pm4_compound_run
+ * (csrc/pm4_core.cu); `dim_scale_dev` / `rw_kind_dev` are HOST pointers here.
+ * -------------------------------------------------------------------------------------- */
+static void NAME(mh_transition)(const pm4_ir_t* ir, NAME(ws_t)* ws, const pm4_compound_block_t* k, uint64_t seed,
+                                uint32_t chain, uint32_t t, REAL eps, REAL* work /* 3 D */, REAL* cth, REAL* cgr, REAL* lp,
+                                REAL* lar_out, int* ok_out) {
+  const int D = ir->D;
+  const REAL* scale = (const REAL*)k->dim_scale_dev;
+  REAL *pth = work, *pp = work + D, *pg = work + 2 * D;
+  NAME(draw_momentum)(seed, chain, t, D, pp);
+  for (int j = 0; j < D; ++j)
+    if (scale[j] == 0) pp[j] = 0;
+  const REAL k0 = (REAL)0.5 * NAME(dot)(pp, pp, D);
+  memcpy(pth, cth, sizeof(REAL) * (size_t)D);
+  memcpy(pg, cgr, sizeof(REAL) * (size_t)D);
+  REAL plp = *lp, lar;
+  if (k->kind == PM4_BLOCK_RWM) {
+    const int32_t* kinds = k->rw_kind_dev;
+    for (int j = 0; j < D; ++j) {
+      if (scale[j] == 0) continue;
+      const int kd = kinds ? kinds[j] : PM4_RW_NORMAL, kind = kd & 0xff;
+      const REAL z = pp[j];
+      if (kind == PM4_RW_BERNOULLI) pth[j] = z > 0 ? (REAL)1 - pth[j] : pth[j];
+      else if (kind == PM4_RW_CATEGORICAL) {
+        const int K = kd >> 8;
+        int c = (int)((REAL)K * (REAL)0.5 * (REAL)erfc((double)(-z) * 0.70710678118654752440));
+        pth[j] = (REAL)(c < 0 ? 0 : (c > K - 1 ? K - 1 : c));
+      } else if (kind == PM4_RW_GAUSSIAN_ROUND) pth[j] = (REAL)rint((double)(pth[j] + (REAL)k->rw_scale * z));
+      else pth[j] = pth[j] + (REAL)k->rw_scale * z;
+    }
+    plp = NAME(logp_grad1)(ir, ws, pth, pg);
+    lar = plp - *lp;
+  } else {
+    NAME(leapfrog)(ir, ws, k->num_leapfrog_steps, eps, scale, pth, pp, pg, &plp);
+    const REAL k1 = (REAL)0.5 * NAME(dot)(pp, pp, D);
+    lar = (plp - *lp) + (k0 - k1);
+  }
+  if (!isfinite(lar)) lar = -(REAL)INFINITY;
+  const REAL u = NAME(draw_u)(seed, chain, t, 0, PM4_RNG_HMC, 0);
+  const int ok = RLOG(u) < lar;
+  if (ok) {
+    memcpy(cth, pth, sizeof(REAL) * (size_t)D);
+    memcpy(cgr, pg, sizeof(REAL) * (size_t)D);
+    *lp = plp;
+  }
+  *lar_out = lar;
+  *ok_out = ok;
+}
+
+int NAME(pm4o_compound_run)(const pm4_ir_t* ir, int C, int S, int B, uint64_t seed, int chain_offset,
+                            const pm4_compound_block_t* blocks, int n_blocks, const REAL* theta0, REAL* states,
+                            REAL* lp_out, REAL* step_size_out, REAL* log_accept, int32_t* leapfrogs_out) {
+  const int D = ir->D, T = B + S;
+  if (n_blocks < 1 || C < 1) return PM4_EINVAL;
+  REAL* th = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* gr = (REAL*)malloc(sizeof(REAL) * (size_t)C * D);
+  REAL* lp = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  REAL* acc = (REAL*)malloc(sizeof(REAL) * (size_t)C);
+  REAL* work = (REAL*)malloc(sizeof(REAL) * (size_t)D * 3);
+  memcpy(th, theta0, sizeof(REAL) * (size_t)C * D);
+  NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)C * (size_t)n_blocks);
+  int max_depth = 1;
+  for (int b = 0; b < n_blocks; ++b) {
+    const REAL eps0 = blocks[b].kind == PM4_BLOCK_RWM ? (REAL)1 : (REAL)blocks[b].step_size;
+    for (int c = 0; c < C; ++c) NAME(da_init)(&da[(size_t)b * C + c], eps0);
+    if (blocks[b].kind == PM4_BLOCK_NUTS && blocks[b].max_tree_depth > max_depth) max_depth = blocks[b].max_tree_depth;
+  }
+  NAME(ws_t) ws = NAME(ws_new)(D);
+  NAME(nuts_buf_t) nb = NAME(nuts_buf_new)(D, max_depth);
+  REAL* base = nb.p0;
+  for (int c = 0; c < C; ++c) lp[c] = NAME(logp_grad1)(ir, &ws, th + (size_t)c * D, gr + (size_t)c * D);
+  for (int t = 0; t < T; ++t) {
+    for (int b = 0; b < n_blocks; ++b) {
+      const pm4_compound_block_t* k = &blocks[b];
+      const uint64_t sb = seed + 0x9E3779B97F4A7C15ull * (uint64_t)b;
+      const int adaptive = k->kind != PM4_BLOCK_RWM && k->adapt.enabled;
+      const int pooled = adaptive && k->adapt.mode == PM4_EPS_POOLED;
+      NAME(da_t)* dab = da + (size_t)b * C;
+      pm4_nuts_cfg_t ncfg;
+      memset(&ncfg, 0, sizeof ncfg);
+      ncfg.C = C; ncfg.num_results = S; ncfg.num_burnin = B; ncfg.max_tree_depth = k->max_tree_depth;
+      ncfg.max_energy_diff = k->max_energy_diff; ncfg.seed = sb; ncfg.adapt = k->adapt; ncfg.chain_offset = chain_offset;
+      for (int c = 0; c < C; ++c) {
+        const REAL eps = dab[pooled ? 0 : c].eps;
+        REAL la;
+        int nleap = 0;
+        if (k->kind == PM4_BLOCK_NUTS) {
+          NAME(nuts_out_t) o;
+          NAME(nuts_transition)(ir, &ws, &nb, &ncfg, (uint32_t)(chain_offset + c), (uint32_t)t, eps,
+                                (const REAL*)k->dim_scale_dev, NULL, th + (size_t)c * D, gr + (size_t)c * D, &lp[c], &o);
+          la = o.log_accept;
+          acc[c] = REXP(o.log_accept);
+          nleap = o.leapfrogs;
+        } else {
+          int ok;
+          NAME(mh_transition)(ir, &ws, k, sb, (uint32_t)(chain_offset + c), (uint32_t)t, eps, work, th + (size_t)c * D,
+                              gr + (size_t)c * D, &lp[c], &la, &ok);
+          acc[c] = REXP(la < 0 ? la : 0);
+        }
+        if (adaptive && !pooled) NAME(da_update)(&dab[c], &k->adapt, t, acc[c]);
+        if (t >= B) {
+          const size_t kk = (size_t)(t - B) * C + c;
+          if (log_accept) log_accept[(size_t)b * S * C + kk] = la;
+          if (leapfrogs_out) leapfrogs_out[(size_t)b * S * C + kk] = nleap;
+          if (b == n_blocks - 1) {
+            if (states) memcpy(states + kk * D, th + (size_t)c * D, sizeof(REAL) * (size_t)D);
+            if (lp_out) lp_out[kk] = lp[c];
+          }
+        }
+      }
+      if (pooled && t <= k->adapt.num_adaptation_steps) { /* the device couples transitions 0 .. num_adapt */
+        REAL s = 0;
+        for (int c = 0; c < C; ++c) s += acc[c];
+        NAME(da_update)(&dab[0], &k->adapt, t, s / (REAL)C);
+      }
+    }
+  }
+  if (step_size_out)
+    for (int b = 0; b < n_blocks; ++b) {
+      const int pooled = blocks[b].kind != PM4_BLOCK_RWM && blocks[b].adapt.enabled && blocks[b].adapt.mode == PM4_EPS_POOLED;
+      for (int c = 0; c < C; ++c) step_size_out[(size_t)b * C + c] = da[(size_t)b * C + (pooled ? 0 : c)].eps;
+    }
+  nb.p0 = base;
+  NAME(nuts_buf_free)(&nb);
+  NAME(ws_free)(&ws);
+  free(work); free(th); free(gr); free(lp); free(acc); free(da);
   return PM4_OK;
 }

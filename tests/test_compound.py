@@ -129,9 +129,9 @@ def poisson_latent_model():
 
 
 def all_models():
-    """every model structure of this file (prebuilt by __graft_entry__.build())"""
-    return [compound_model(), simple_model(), model_symmetric(), mixture_model(), categorical_normal_model(),
-            poisson_latent_model()] + discrete_models()
+    """(model, needs float64 kernels) for every model structure of this file (prebuilt by __graft_entry__.build())"""
+    return ([(m, False) for m in (compound_model(), simple_model(), model_symmetric(), poisson_latent_model())]
+            + [(m, True) for m in (mixture_model(), categorical_normal_model())] + [(m, False) for m in discrete_models()])
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -357,3 +357,57 @@ def test_free_poisson_with_the_gaussian_round_proposal():
     n = trace.posterior["m/n"]
     assert np.all(n == np.round(n)) and n.min() >= 0
     assert abs(n.mean() - 4.0) < 0.1 and abs(n.var() - 4.0) < 0.3
+
+
+def _replay_blocks(ir, which):
+    """Block records (host arrays) for DeviceModel.compound / Oracle.compound."""
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED, make_adapt
+    from pymc4_b200.distributions.state_functions import PM4_RW_BERNOULLI, PM4_RW_CATEGORICAL
+
+    disc = np.concatenate([np.full(rv.size, 1.0 if rv.discrete else 0.0) for rv in ir.rvs])
+    kinds = np.zeros(ir.D, np.int32)
+    if which == "categorical":
+        kinds[disc > 0] = PM4_RW_CATEGORICAL | (len(CAT_PROBS) << 8)
+        return [dict(kind="rwm", dim_scale=disc, rw_kind=kinds), dict(kind="rwm", dim_scale=1 - disc, rw_scale=1.5)]
+    kinds[disc > 0] = PM4_RW_BERNOULLI
+    first = dict(kind="rwm", dim_scale=disc, rw_kind=kinds)
+    if which == "nuts_pooled":
+        return [first, dict(kind="nuts", dim_scale=1 - disc, step_size=0.1, max_tree_depth=6,
+                            adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=12))]
+    if which == "nuts_per_chain":
+        return [dict(kind="nuts", dim_scale=1 - disc, step_size=0.1, max_tree_depth=6,
+                     adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=12)), first]
+    return [first, dict(kind="hmc", dim_scale=(1 - disc) * 0.5, step_size=0.2, num_leapfrog_steps=4,
+                        adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=12))]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["nuts_pooled", "nuts_per_chain", "hmc", "categorical"])
+def test_compound_replay_against_the_oracle(which):
+    """FP64 replay of pm4_compound_run against the oracle's restatement (oracle/pm4_oracle_impl.h: pm4o_compound_run):
+    same Philox streams, same block order -- the discrete coordinates agree exactly, the continuous ones and the
+    log acceptance ratios to rounding, the adapted step sizes too."""
+    from oracle import pm4_oracle
+    from pymc4_b200._cabi import DeviceModel
+
+    model = categorical_normal_model() if which == "categorical" else mixture_model()
+    ir, _, _ = lower_model(model)
+    blocks = _replay_blocks(ir, which)
+    C, B, S = 24, 14, 26
+    rng = np.random.default_rng(3)
+    theta0 = np.zeros((C, ir.D))
+    for rv in ir.rvs:
+        if not rv.discrete:
+            theta0[:, rv.offset: rv.offset + rv.size] = rng.normal(0, 0.3, (C, rv.size))
+    ref = pm4_oracle.Oracle(ir).compound(blocks, theta0, S, B, seed=17, dtype=np.float64)
+    out = DeviceModel(ir, device=0, f64=True).compound(blocks, theta0, S, B, seed=17, dtype=np.float64)
+    st, lacc = out["states"].cpu().numpy(), out["log_accept"].cpu().numpy()
+    disc = np.concatenate([np.full(rv.size, rv.discrete) for rv in ir.rvs])
+    assert np.array_equal(st[:, :, disc], ref["states"][:, :, disc])
+    assert len(np.unique(st[:, :, disc])) > 1  # the discrete block moves
+    np.testing.assert_allclose(st[:, :, ~disc], ref["states"][:, :, ~disc], atol=1e-9)
+    np.testing.assert_allclose(out["lp"].cpu().numpy(), ref["lp"], rtol=1e-10, atol=1e-10)
+    finite = np.isfinite(ref["log_accept"])
+    assert np.array_equal(np.isfinite(lacc), finite)
+    np.testing.assert_allclose(lacc[finite], ref["log_accept"][finite], atol=1e-8)
+    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
