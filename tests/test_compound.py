@@ -247,6 +247,27 @@ def test_sampler_assignment_rules():
     assert len(s.kernel_kwargs["compound_samplers"]) == 2  # var2 carries bernoulli_fn, var1 the default proposal
 
 
+def test_oracle_compound_targets_the_closed_form_posterior():
+    """The oracle's compound transition (the checker of the GPU replay test) is itself pinned to a closed form."""
+    from oracle import pm4_oracle
+    from pymc4_b200._cstructs import PM4_EPS_POOLED, make_adapt
+    from pymc4_b200.distributions.state_functions import PM4_RW_BERNOULLI
+
+    ir, _, _ = lower_model(mixture_model())
+    disc = np.concatenate([np.full(rv.size, 1.0 if rv.discrete else 0.0) for rv in ir.rvs])
+    kinds = np.where(disc > 0, PM4_RW_BERNOULLI, 0).astype(np.int32)
+    blocks = [dict(kind="rwm", dim_scale=disc, rw_kind=kinds),
+              dict(kind="nuts", dim_scale=1 - disc, step_size=0.1, adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=100))]
+    out = pm4_oracle.Oracle(ir).compound(blocks, np.zeros((384, ir.D)), 500, 150, seed=3)
+    w1, mu_mean = mixture_posterior()
+    z, mu = out["states"][:, :, disc > 0][..., 0], out["states"][:, :, disc == 0][..., 0]
+    se_z = z.mean(axis=0).std() / np.sqrt(z.shape[1])
+    se_mu = mu.mean(axis=0).std() / np.sqrt(mu.shape[1])
+    assert abs(z.mean() - w1) < 4 * se_z + 0.005, (z.mean(), w1, se_z)
+    assert abs(mu.mean() - mu_mean) < 4 * se_mu + 0.005, (mu.mean(), mu_mean, se_mu)
+    assert set(np.unique(z)) == {0.0, 1.0}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # sampling (GPU)
 # ---------------------------------------------------------------------------------------------------------------
