@@ -131,7 +131,8 @@ def poisson_latent_model():
 def all_models():
     """(model, needs float64 kernels) for every model structure of this file (prebuilt by __graft_entry__.build())"""
     return ([(m, False) for m in (compound_model(), simple_model(), model_symmetric(), poisson_latent_model())]
-            + [(m, True) for m in (mixture_model(), categorical_normal_model())] + [(m, False) for m in discrete_models()])
+            + [(m, True) for m in (mixture_model(), categorical_normal_model())] + [(m, False) for m in discrete_models()]
+            + [(mixture_with_deterministic(), False)])
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -432,3 +433,33 @@ def test_compound_replay_against_the_oracle(which):
     assert np.array_equal(np.isfinite(lacc), finite)
     np.testing.assert_allclose(lacc[finite], ref["log_accept"][finite], atol=1e-8)
     np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
+
+
+def mixture_with_deterministic():
+    @pm.model
+    def mixture_det():
+        z = yield pm.Bernoulli("z", 0.3)
+        mu = yield pm.Normal("mu", 0.0, 1.0)
+        shifted = yield pm.Deterministic("shifted", mu + 2.0 * z)
+        yield pm.Normal("y", shifted, 1.0, observed=Y_MIX)
+
+    return mixture_det()
+
+
+@pytest.mark.gpu
+def test_compound_with_deterministics_log_likelihood_and_predictive():
+    """The trace of a compound run carries deterministics, the pointwise log-likelihood and feeds posterior-predictive
+    sampling like any other sampler's (reference samplers.py:136-170 is sampler-agnostic)."""
+    model = mixture_with_deterministic()
+    trace = pm.sample(model, num_chains=64, num_samples=200, burn_in=100, seed=4, include_log_likelihood=True)
+    post = trace.posterior
+    z, mu, sh = post["mixture_det/z"], post["mixture_det/mu"], post["mixture_det/shifted"]
+    np.testing.assert_allclose(sh, mu + 2.0 * z, rtol=1e-6, atol=1e-6)
+    ll = trace.log_likelihood["mixture_det/y"]
+    assert ll.shape == (64, 200, len(Y_MIX))
+    ref = -0.5 * (Y_MIX[None, None, :] - sh[..., None]) ** 2 - 0.5 * np.log(2 * np.pi)
+    np.testing.assert_allclose(ll, ref, rtol=1e-4, atol=1e-4)
+    ppc = pm.sample_posterior_predictive(model, trace)
+    yp = ppc.posterior_predictive["mixture_det/y"]
+    assert yp.shape == (64, 200, len(Y_MIX))
+    assert abs(yp.mean() - sh.mean()) < 0.05 and abs(yp.std() - np.sqrt(1.0 + sh.var())) < 0.1
