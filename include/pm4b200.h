@@ -278,6 +278,8 @@ typedef struct pm4_adapt_cfg {
    * mass matrix diag(1 / s_d^2).  0 = off (the reference behaviour). */
   int32_t mass_windows;
   int32_t _pad;
+  double shrinkage_target;      /* tfp `shrinkage_target`: the step size dual averaging shrinks towards; 0 = the tfp default,
+                                   10 x the initial step size                 */
 } pm4_adapt_cfg_t;
 
 /* proposals of the Metropolis-Hastings kernel run by pm4_hmc_run */
@@ -299,6 +301,8 @@ typedef struct pm4_hmc_cfg {
   int32_t proposal;           /* PM4_PROPOSAL_*                                            */
   int32_t _pad;
   double rw_scale;            /* PM4_PROPOSAL_RANDOM_WALK: standard deviation of the normal perturbation (1.0) */
+  const void* step_size_dev;  /* [C] reals of the call's dtype or NULL: initial epsilon of every chain (a `step_size` with a
+                                 leading chain axis whose entries differ; per-chain adaptation mode only)          */
 } pm4_hmc_cfg_t;
 
 /* Fixed-L HMC (tfp HamiltonianMonteCarlo = MetropolisHastings(UncalibratedHMC); App. A.4).
@@ -361,6 +365,7 @@ typedef struct pm4_nuts_cfg {
   pm4_adapt_cfg_t adapt;
   int32_t warps_per_block; /* 0 = library default */
   int32_t chain_offset;    /* global index of chain 0 (RNG stream id) when chains are sharded */
+  const void* step_size_dev; /* [C] reals of the call's dtype or NULL: initial epsilon of every chain (see pm4_hmc_cfg_t) */
 } pm4_nuts_cfg_t;
 
 /* NUTS (tfp NoUTurnSampler: iterative tree doubling, generalised U-turn with checkpoints,

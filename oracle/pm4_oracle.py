@@ -160,8 +160,10 @@ class Oracle:
                                            int(seed) & (2**64 - 1), _ptr(x), _ptr(obs)), "prior_predictive")
         return x, obs
 
-    def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None):
+    def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, step_sizes=None):
         C, S, D = cfg.C, cfg.num_results, self.ir.D
+        eps_c = None if step_sizes is None else np.ascontiguousarray(np.asarray(step_sizes).reshape(C), dtype=dtype)
+        cfg.step_size_dev = eps_c.ctypes.data if eps_c is not None else None  # a HOST pointer for the oracle
         theta0 = np.ascontiguousarray(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D)))
         step_scale = None if step_scale is None else np.ascontiguousarray(step_scale, dtype=dtype)
         momenta = None if momenta is None else np.ascontiguousarray(momenta, dtype=dtype)
@@ -181,8 +183,10 @@ class Oracle:
         _check(rc, "nuts_run")
         return out
 
-    def hmc(self, cfg: HMCCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, uniforms=None):
+    def hmc(self, cfg: HMCCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, uniforms=None, step_sizes=None):
         C, S, D, T = cfg.C, cfg.num_results, self.ir.D, cfg.num_results + cfg.num_burnin
+        eps_c = None if step_sizes is None else np.ascontiguousarray(np.asarray(step_sizes).reshape(C), dtype=dtype)
+        cfg.step_size_dev = eps_c.ctypes.data if eps_c is not None else None  # a HOST pointer for the oracle
         theta0 = np.ascontiguousarray(np.broadcast_to(np.asarray(theta0, dtype=dtype), (C, D)))
         step_scale = None if step_scale is None else np.ascontiguousarray(step_scale, dtype=dtype)
         momenta = None if momenta is None else np.ascontiguousarray(momenta, dtype=dtype)

@@ -684,6 +684,12 @@ static void NAME(da_init)(NAME(da_t)* s, REAL eps0) {
   s->t0 = 0;
 }
 
+/* initial state of chain c (or of the pool): per-chain initial step sizes and tfp's `shrinkage_target` when given */
+static void NAME(da_init_cfg)(NAME(da_t)* s, double step_size, const void* step_size_c, int c, const pm4_adapt_cfg_t* a) {
+  NAME(da_init)(s, step_size_c ? ((const REAL*)step_size_c)[c] : (REAL)step_size);
+  if (a->shrinkage_target > 0) s->log_shrink_target = (REAL)log(a->shrinkage_target);
+}
+
 /* restart of the recursion at transition t0 from the current step size (after a mass-matrix update) */
 static void NAME(da_restart)(NAME(da_t)* s, int t0) {
   s->error_sum = 0;
@@ -900,7 +906,7 @@ int NAME(pm4o_nuts_run)(const pm4_ir_t* ir, const pm4_nuts_cfg_t* cfg, const REA
   memcpy(th, theta0, sizeof(REAL) * (size_t)C * D);
   const int pooled = cfg->adapt.mode == PM4_EPS_POOLED;
   NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)(pooled ? 1 : C));
-  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init)(&da[c], (REAL)cfg->step_size);
+  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init_cfg)(&da[c], cfg->step_size, pooled ? NULL : cfg->step_size_dev, c, &cfg->adapt);
 
   /* the step scale in effect: the caller's (or ones when mass windows will write it), updated at window starts */
   REAL* scale_buf = NULL;
@@ -1017,7 +1023,7 @@ int NAME(pm4o_hmc_run)(const pm4_ir_t* ir, const pm4_hmc_cfg_t* cfg, const REAL*
   REAL* acc = (REAL*)malloc(sizeof(REAL) * (size_t)C);
   memcpy(th, theta0, sizeof(REAL) * (size_t)C * D);
   NAME(da_t)* da = (NAME(da_t)*)malloc(sizeof(NAME(da_t)) * (size_t)(pooled ? 1 : C));
-  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init)(&da[c], (REAL)cfg->step_size);
+  for (int c = 0; c < (pooled ? 1 : C); ++c) NAME(da_init_cfg)(&da[c], cfg->step_size, pooled ? NULL : cfg->step_size_dev, c, &cfg->adapt);
   NAME(ws_t) ws = NAME(ws_new)(D);
   REAL* pth = (REAL*)malloc(sizeof(REAL) * (size_t)D * 3);
   REAL *pp = pth + D, *pg = pp + D;
@@ -1145,7 +1151,11 @@ int NAME(pm4o_compound_run)(const pm4_ir_t* ir, int C, int S, int B, uint64_t se
   int max_depth = 1;
   for (int b = 0; b < n_blocks; ++b) {
     const REAL eps0 = blocks[b].kind == PM4_BLOCK_RWM ? (REAL)1 : (REAL)blocks[b].step_size;
-    for (int c = 0; c < C; ++c) NAME(da_init)(&da[(size_t)b * C + c], eps0);
+    for (int c = 0; c < C; ++c) {
+      NAME(da_init)(&da[(size_t)b * C + c], eps0);
+      if (blocks[b].kind != PM4_BLOCK_RWM && blocks[b].adapt.shrinkage_target > 0)
+        da[(size_t)b * C + c].log_shrink_target = (REAL)log(blocks[b].adapt.shrinkage_target);
+    }
     if (blocks[b].kind == PM4_BLOCK_NUTS && blocks[b].max_tree_depth > max_depth) max_depth = blocks[b].max_tree_depth;
   }
   NAME(ws_t) ws = NAME(ws_new)(D);

@@ -314,7 +314,7 @@ class DeviceModel:
         return x, obs
 
     def nuts(self, cfg: NUTSCfg, theta0, dtype=np.float32, step_scale=None, momenta=None,
-             want_states: bool = True, stream_trace: int = 0) -> Dict[str, "object"]:
+             want_states: bool = True, stream_trace: int = 0, step_sizes=None) -> Dict[str, "object"]:
         """Run NUTS; every result is a device tensor in the reference layout [S, C, ...].
 
         ``stream_trace = n > 0``: the kept draws also travel to a pinned host tensor ``out["states_host"]`` in n slabs
@@ -326,6 +326,8 @@ class DeviceModel:
                              if not isinstance(theta0, torch.Tensor) else theta0, dtype)
         sc = self.to_device(step_scale, dtype)
         mom = self.to_device(momenta, dtype)
+        eps_c = self.to_device(None if step_sizes is None else np.asarray(step_sizes).reshape(C), dtype)  # initial epsilon per chain
+        cfg.step_size_dev = eps_c.data_ptr() if eps_c is not None else None
         out = dict(
             states=self.empty((S, C, D), td) if want_states else None,
             lp=self.empty((S, C), td),
@@ -362,11 +364,11 @@ class DeviceModel:
             with torch.cuda.device(self._dev()):
                 self._check(self.lib.pm4_model_get_mass_scale(self.handle, _code(dtype), self._p(out["mass_scale"]),
                                                               self._stream()))
-        out["_keepalive"] = (th0, sc, mom)
+        out["_keepalive"] = (th0, sc, mom, eps_c)
         return out
 
     def hmc(self, cfg: HMCCfg, theta0, dtype=np.float32, step_scale=None, momenta=None, uniforms=None,
-            want_traj: bool = False) -> Dict[str, "object"]:
+            want_traj: bool = False, step_sizes=None) -> Dict[str, "object"]:
         torch = self.torch
         td = _tdtype(torch, dtype)
         C, S, D, T = cfg.C, cfg.num_results, self.ir.D, cfg.num_results + cfg.num_burnin
@@ -375,6 +377,8 @@ class DeviceModel:
         sc = self.to_device(step_scale, dtype)
         mom = self.to_device(momenta, dtype)
         uni = self.to_device(uniforms, dtype)
+        eps_c = self.to_device(None if step_sizes is None else np.asarray(step_sizes).reshape(C), dtype)
+        cfg.step_size_dev = eps_c.data_ptr() if eps_c is not None else None
         out = dict(
             states=self.empty((S, C, D), td), lp=self.empty((S, C), td), log_accept=self.empty((S, C), td),
             accepted=self.empty((S, C), torch.uint8), step_size=self.empty((C,), td),
@@ -386,7 +390,7 @@ class DeviceModel:
                 self._p(out["states"]), self._p(out["lp"]), self._p(out["log_accept"]), self._p(out["accepted"]),
                 self._p(out["step_size"]), self._p(out["traj"]), self._stream())
         self._check(rc)
-        out["_keepalive"] = (th0, sc, mom, uni)
+        out["_keepalive"] = (th0, sc, mom, uni, eps_c)
         return out
 
 

@@ -21,6 +21,7 @@ class AdaptCfg(ctypes.Structure):
         ("adaptation_rate", ctypes.c_double),
         ("mass_windows", ctypes.c_int32),
         ("_pad", ctypes.c_int32),
+        ("shrinkage_target", ctypes.c_double),
     ]
 
 
@@ -38,6 +39,7 @@ class HMCCfg(ctypes.Structure):
         ("proposal", ctypes.c_int32),
         ("_pad", ctypes.c_int32),
         ("rw_scale", ctypes.c_double),
+        ("step_size_dev", ctypes.c_void_p),
     ]
 
 
@@ -53,6 +55,7 @@ class NUTSCfg(ctypes.Structure):
         ("adapt", AdaptCfg),
         ("warps_per_block", ctypes.c_int32),
         ("chain_offset", ctypes.c_int32),
+        ("step_size_dev", ctypes.c_void_p),
     ]
 
 
@@ -73,10 +76,12 @@ class CompoundBlock(ctypes.Structure):
 
 def make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=0, target_accept_prob=0.75,
                exploration_shrinkage=0.05, step_count_smoothing=10.0, decay_rate=0.75,
-               enabled=True, kind=PM4_ADAPT_DUAL_AVERAGING, adaptation_rate=0.01, mass_windows=0) -> AdaptCfg:
+               enabled=True, kind=PM4_ADAPT_DUAL_AVERAGING, adaptation_rate=0.01, mass_windows=0,
+               shrinkage_target=None) -> AdaptCfg:
     return AdaptCfg(int(mode), int(num_adaptation_steps), float(target_accept_prob),
                     float(exploration_shrinkage), float(step_count_smoothing), float(decay_rate),
-                    int(bool(enabled)), int(kind), float(adaptation_rate), int(mass_windows), 0)
+                    int(bool(enabled)), int(kind), float(adaptation_rate), int(mass_windows), 0,
+                    float(shrinkage_target) if shrinkage_target else 0.0)
 
 
 def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_depth=10,
@@ -84,7 +89,7 @@ def make_nuts_cfg(C, num_results, num_burnin, step_size=0.1, seed=0, max_tree_de
     adapt = adapt if adapt is not None else make_adapt(num_adaptation_steps=num_burnin)
     return NUTSCfg(int(C), int(num_results), int(num_burnin), int(max_tree_depth),
                    float(max_energy_diff), float(step_size), int(seed) & (2**64 - 1), adapt,
-                   int(warps_per_block), int(chain_offset))
+                   int(warps_per_block), int(chain_offset), None)
 
 
 def make_hmc_cfg(C, num_results, num_burnin, step_size=0.1, num_leapfrog_steps=3, seed=0,
@@ -93,4 +98,4 @@ def make_hmc_cfg(C, num_results, num_burnin, step_size=0.1, num_leapfrog_steps=3
     adapt = adapt if adapt is not None else make_adapt(num_adaptation_steps=num_burnin)
     return HMCCfg(int(C), int(num_results), int(num_burnin), int(num_leapfrog_steps),
                   float(step_size), int(seed) & (2**64 - 1), adapt, int(warps_per_block),
-                  int(chain_offset), int(proposal), 0, float(rw_scale))
+                  int(chain_offset), int(proposal), 0, float(rw_scale), None)

@@ -775,6 +775,31 @@ struct RunBuffers {
   }
 };
 
+// Rewrites the initial dual-averaging state the module's bootstrap left: per-chain initial step sizes (`eps_c`, or
+// NULL) and a shrinkage target other than 10 x the initial step size (`log_target`, or NaN).  Rows: [eps, error_sum,
+// log_avg, log_shrink_target].
+template <typename real>
+__global__ void da_override_kernel(real* __restrict__ da, int rows, const real* __restrict__ eps_c, double log_target) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= rows) return;
+  real* d = da + (size_t)c * 4;
+  if (eps_c) {
+    d[0] = eps_c[c];
+    d[3] = (real)log(10.0 * (double)eps_c[c]);
+  }
+  if (log_target == log_target) d[3] = (real)log_target;
+}
+
+static int da_override(int dtype, void* da, int rows, const void* eps_c, double shrinkage_target, cudaStream_t st) {
+  if (!eps_c && !(shrinkage_target > 0)) return PM4_OK;
+  const double lt = shrinkage_target > 0 ? log(shrinkage_target) : (double)NAN;
+  const unsigned grid = (unsigned)((rows + 255) / 256);
+  if (dtype == PM4_F64) da_override_kernel<double><<<grid, 256, 0, st>>>((double*)da, rows, (const double*)eps_c, lt);
+  else da_override_kernel<float><<<grid, 256, 0, st>>>((float*)da, rows, (const float*)eps_c, lt);
+  CU(cudaGetLastError());
+  return PM4_OK;
+}
+
 int fill_adapt(pm4_mod_run_t& r, const pm4_adapt_cfg_t& a) {
   if (a.mode != PM4_EPS_POOLED && a.mode != PM4_EPS_PER_CHAIN) return fail(PM4_EINVAL, "unknown step-size mode %d", a.mode);
   if (a.kind != PM4_ADAPT_DUAL_AVERAGING && a.kind != PM4_ADAPT_SIMPLE) return fail(PM4_EINVAL, "unknown adaptation kind %d", a.kind);
@@ -1004,6 +1029,8 @@ static int nuts_lockstep(pm4_model* m, int dtype, const pm4_nuts_cfg_t* cfg, con
   if (total_leapfrogs_dev) CU(cudaMemsetAsync(total_leapfrogs_dev, 0, sizeof(int64_t) * (size_t)C, st));
   if ((rc = full_grad(p.h.th, p.h.lp, p.h.g, nullptr))) return rc;
   pm4ls::init_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(p.h, (float)cfg->step_size);
+  if (cfg->step_size_dev && r.adapt_pooled) return fail(PM4_EINVAL, "per-chain initial step sizes need the per-chain adaptation mode");
+  if ((rc = da_override(dtype, p.h.da, r.adapt_pooled ? 1 : C, cfg->step_size_dev, cfg->adapt.shrinkage_target, st))) return rc;
   // The leapfrogs of a transition are enqueued in BATCHES without a host round trip in between: every iteration
   // counts the chains that asked for another gradient in its own word of a ring, the dense evaluation of the next
   // iteration is gated on that word (a kernel that finds 0 returns at once), and the host reads one word per batch.
@@ -1126,6 +1153,8 @@ extern "C" int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg
     r.step_scale = mc.scale;
   }
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
+  if (cfg->step_size_dev && r.adapt_pooled) return fail(PM4_EINVAL, "per-chain initial step sizes need the per-chain adaptation mode");
+  if ((rc = da_override(dtype, r.da, r.adapt_pooled ? 1 : r.C, cfg->step_size_dev, cfg->adapt.shrinkage_target, st))) return rc;
   if ((rc = drive(m, dtype, r, true, cfg->warps_per_block, T, (int32_t*)order, st, mc))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   if (r.adapt_enabled && r.adapt_pooled) return check_comm(m, st);
@@ -1181,6 +1210,8 @@ static int hmc_lockstep(pm4_model* m, int dtype, const pm4_hmc_cfg_t* cfg, const
   CU(cudaMemcpyAsync(p.th, theta0_dev, CD * 4, cudaMemcpyDeviceToDevice, st));
   if ((rc = full_grad(p.th, p.lp, p.g))) return rc;
   pm4ls::init_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(p, (float)cfg->step_size);
+  if (cfg->step_size_dev && r.adapt_pooled) return fail(PM4_EINVAL, "per-chain initial step sizes need the per-chain adaptation mode");
+  if ((rc = da_override(dtype, p.da, r.adapt_pooled ? 1 : C, cfg->step_size_dev, cfg->adapt.shrinkage_target, st))) return rc;
   for (int t = 0; t < T; ++t) {
     p.t = t;
     pm4ls::begin_kernel<<<warp_grid, 256, 0, st>>>(p);
@@ -1249,6 +1280,8 @@ extern "C" int pm4_hmc_run(pm4_model_t* m, int dtype, const pm4_hmc_cfg_t* cfg, 
 
   fill_comm(m, r);
   MOD(m->f_init(dtype, &r, theta0_dev, cfg->step_size, st), "bootstrap");
+  if (cfg->step_size_dev && r.adapt_pooled) return fail(PM4_EINVAL, "per-chain initial step sizes need the per-chain adaptation mode");
+  if ((rc = da_override(dtype, r.da, r.adapt_pooled ? 1 : r.C, cfg->step_size_dev, cfg->adapt.shrinkage_target, st))) return rc;
   if ((rc = drive(m, dtype, r, false, cfg->warps_per_block, T, nullptr, st))) return rc;
   if (step_size_dev) MOD(m->f_eps(dtype, &r, step_size_dev, st), "export step size");
   if (r.adapt_enabled && r.adapt_pooled) return check_comm(m, st);
@@ -1340,7 +1373,8 @@ extern "C" int pm4_compound_run(pm4_model_t* m, int dtype, int32_t C_, int32_t n
     const double eps0 = k.kind == PM4_BLOCK_RWM ? 1.0 : k.step_size;
     host_da.resize(C * 4 * rs);
     for (size_t c = 0; c < C; ++c) {
-      const double row[4] = {eps0, 0.0, 0.0, log(10.0 * eps0)};
+      const double target = (k.kind != PM4_BLOCK_RWM && k.adapt.shrinkage_target > 0) ? k.adapt.shrinkage_target : 10.0 * eps0;
+      const double row[4] = {eps0, 0.0, 0.0, log(target)};
       for (int q = 0; q < 4; ++q) {
         if (dtype == PM4_F64) ((double*)host_da.data())[c * 4 + q] = row[q];
         else ((float*)host_da.data())[c * 4 + q] = (float)row[q];

@@ -57,8 +57,9 @@ class DualAveragingStepSizeAdaptation:
                  step_size_setter_fn: Optional[Callable] = None, step_size_getter_fn: Optional[Callable] = None,
                  log_accept_prob_getter_fn: Optional[Callable] = None, reduce_fn: Any = None,
                  validate_args=False, name=None):
-        if shrinkage_target is not None:
-            raise NotImplementedError("shrinkage_target other than the default 10 * step_size is not supported")
+        self.shrinkage_target = None if shrinkage_target is None else float(shrinkage_target)
+        if self.shrinkage_target is not None and not self.shrinkage_target > 0:
+            raise ValueError("shrinkage_target must be positive")
         self.inner_kernel = inner_kernel
         self.num_adaptation_steps = int(num_adaptation_steps)
         self.target_accept_prob = float(target_accept_prob)

@@ -205,6 +205,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
                                         scale (all dimensions of a chain see the same update).
         """
         ir = self._device_model.ir
+        self._chain_step_sizes = None
         if isinstance(step_size, (list, tuple)) and len(step_size) == len(ir.rvs):
             scale = np.ones(ir.D, dtype=np.float64)
             for rv, part in zip(ir.rvs, step_size):
@@ -219,8 +220,10 @@ class _BaseSampler(metaclass=abc.ABCMeta):
             return float(arr), None, PM4_EPS_POOLED
         if arr.shape[0] == num_chains and arr.size == num_chains:
             flat = arr.reshape(-1)
-            if not np.allclose(flat, flat[0]):
-                raise NotImplementedError("step sizes that differ between chains at start are not supported")
+            if not np.all(flat > 0):
+                raise ValueError("step sizes must be positive")
+            # chains that start from different step sizes: the array travels to the device (cfg.step_size_dev)
+            self._chain_step_sizes = None if np.allclose(flat, flat[0]) else flat.copy()
             return float(flat[0]), None, PM4_EPS_PER_CHAIN
         if arr.size == ir.D:
             return 1.0, arr.reshape(-1), PM4_EPS_POOLED
@@ -261,7 +264,8 @@ class _BaseSampler(metaclass=abc.ABCMeta):
                           target_accept_prob=spec.target_accept_prob,
                           exploration_shrinkage=spec.exploration_shrinkage,
                           step_count_smoothing=spec.step_count_smoothing, decay_rate=spec.decay_rate, enabled=True,
-                          mass_windows=int(self.backend_kwargs.get("mass_windows", 0)) if self._name.startswith("nuts") else 0)
+                          mass_windows=int(self.backend_kwargs.get("mass_windows", 0)) if self._name.startswith("nuts") else 0,
+                          shrinkage_target=spec.shrinkage_target)
 
     def _check_chain_kwargs(self):
         ck = self.chain_kwargs
@@ -333,7 +337,8 @@ class HMC(_BaseSampler):
                            chain_offset=self.backend_kwargs.get("chain_offset", 0))
         if "comm" in self.backend_kwargs:
             dm.attach_comm(self.backend_kwargs["comm"])
-        out = self._thin_out(dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale), ("states", "lp", "log_accept", "accepted"))
+        out = self._thin_out(dm.hmc(cfg, theta0, dtype=self._dtype, step_scale=scale, step_sizes=self._chain_step_sizes),
+                             ("states", "lp", "log_accept", "accepted"))
         self._run_info = dict(step_size=out["step_size"], kernel="hmc",
                               leapfrogs_per_transition=spec.num_leapfrog_steps)
         self._last_states = out["states"]
@@ -398,7 +403,7 @@ class NUTS(_BaseSampler):
         # posterior arrays are then views of one pinned host buffer instead of per-variable copies made afterwards
         trace_bytes = self._draws_to_run() * C * dm.ir.D * np.dtype(self._dtype).itemsize
         slabs = int(self.backend_kwargs.get("trace_slabs", 8 if trace_bytes >= (64 << 20) else 0))
-        out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale, stream_trace=slabs)
+        out = dm.nuts(cfg, theta0, dtype=self._dtype, step_scale=scale, stream_trace=slabs, step_sizes=self._chain_step_sizes)
         if "states_host" in out and self._thin():
             out["states_host_ready"]()
         self._thin_out(out, ("states", "lp", "leapfrogs", "diverging", "energy", "log_accept", "depth", "states_host"))

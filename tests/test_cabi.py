@@ -51,11 +51,15 @@ def test_struct_layouts_match_the_header(tmp_path):
                              "elem_off", "spart_off", "phdr_off"]),
         "pm4_adapt_cfg_t": (_cstructs.AdaptCfg, ["mode", "num_adaptation_steps", "target_accept_prob",
                                                  "exploration_shrinkage", "step_count_smoothing", "decay_rate", "enabled",
-                                                 "kind", "adaptation_rate", "mass_windows"]),
+                                                 "kind", "adaptation_rate", "mass_windows", "shrinkage_target"]),
         "pm4_hmc_cfg_t": (_cstructs.HMCCfg, ["C", "num_results", "num_burnin", "num_leapfrog_steps", "step_size",
-                                             "seed", "adapt", "warps_per_block", "chain_offset"]),
+                                             "seed", "adapt", "warps_per_block", "chain_offset", "proposal", "rw_scale",
+                                             "step_size_dev"]),
+        "pm4_compound_block_t": (_cstructs.CompoundBlock, ["kind", "num_leapfrog_steps", "max_tree_depth", "max_energy_diff",
+                                                           "step_size", "rw_scale", "adapt", "dim_scale_dev", "rw_kind_dev"]),
         "pm4_nuts_cfg_t": (_cstructs.NUTSCfg, ["C", "num_results", "num_burnin", "max_tree_depth", "max_energy_diff",
-                                               "step_size", "seed", "adapt", "warps_per_block", "chain_offset"]),
+                                               "step_size", "seed", "adapt", "warps_per_block", "chain_offset",
+                                               "step_size_dev"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, "int main(void) {"]
     for cname, (_, fields) in structs.items():

@@ -272,7 +272,16 @@ def test_step_size_conventions():
     from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN, PM4_EPS_POOLED
 
     assert s._step_size_policy(0.28, 4) == (0.28, None, PM4_EPS_POOLED)
-    assert s._step_size_policy(np.full((4, 1), 0.2), 4) == (0.2, None, PM4_EPS_PER_CHAIN)
+    assert s._step_size_policy(np.full((4, 1), 0.2), 4) == (0.2, None, PM4_EPS_PER_CHAIN) and s._chain_step_sizes is None
+    # chains that start from different step sizes: the array goes to the device next to the first value
+    assert s._step_size_policy(np.array([0.1, 0.2, 0.3, 0.4]), 4) == (0.1, None, PM4_EPS_PER_CHAIN)
+    np.testing.assert_allclose(s._chain_step_sizes, [0.1, 0.2, 0.3, 0.4])
+    with pytest.raises(ValueError):
+        s._step_size_policy(np.array([0.1, -0.2, 0.3, 0.4]), 4)
+    # tfp's shrinkage_target reaches the adaptation record
+    s2 = pm.mcmc.samplers.NUTS(M.schools_pm4(), num_adaptation_steps=10, shrinkage_target=0.5)
+    s2._device_model = dm
+    assert s2._adapt_cfg(PM4_EPS_POOLED).shrinkage_target == 0.5 and s._adapt_cfg(PM4_EPS_POOLED).shrinkage_target == 0.0
     parts = [np.full((4, 8), 0.5), np.full((4,), 0.25), np.full((4,), 2.0)]
     eps0, scale, mode = s._step_size_policy(parts, 4)
     assert eps0 == 1.0 and mode == PM4_EPS_PER_CHAIN

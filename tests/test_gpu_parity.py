@@ -124,6 +124,35 @@ def test_hmc_chain_parity_with_adaptation(oracle_mod):
         np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-9)
 
 
+def test_per_chain_initial_step_sizes_and_shrinkage_target_replay(oracle_mod):
+    """`step_size` with a leading chain axis whose entries differ (cfg.step_size_dev) and tfp's `shrinkage_target`: FP64
+    replay of NUTS and HMC against the oracle -- integer statistics bit-exact, adapted step sizes equal."""
+    ir, _, _ = lower_model(M.schools_pm4())
+    C, D, B, S = 10, ir.D, 20, 15
+    rng = np.random.default_rng(33)
+    momenta = rng.standard_normal((B + S, C, D))
+    eps_c = np.linspace(0.05, 0.4, C)
+    adapt = make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B, shrinkage_target=0.7)
+    cfg = make_nuts_cfg(C, S, B, step_size=0.1, seed=4, adapt=adapt)
+    ref = oracle_mod.Oracle(ir).nuts(cfg, np.zeros(D), dtype=np.float64, momenta=momenta, step_sizes=eps_c)
+    out = _dm(ir, f64=True).nuts(cfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta, step_sizes=eps_c)
+    for key in ("leapfrogs", "depth", "diverging"):
+        assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
+    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-7)
+    assert np.ptp(ref["leapfrogs"][0]) > 0  # the chains really started from different step sizes
+    # the default recursion (10 x the initial step) ends elsewhere
+    dflt = oracle_mod.Oracle(ir).nuts(make_nuts_cfg(C, S, B, step_size=0.1, seed=4, adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, num_adaptation_steps=B)),
+                                      np.zeros(D), dtype=np.float64, momenta=momenta, step_sizes=eps_c)
+    assert not np.allclose(dflt["step_size"], ref["step_size"])
+    uniforms = rng.random((B + S, C))
+    hcfg = make_hmc_cfg(C, S, B, step_size=0.1, num_leapfrog_steps=3, seed=3, adapt=adapt)
+    ref = oracle_mod.Oracle(ir).hmc(hcfg, np.zeros(D), dtype=np.float64, momenta=momenta, uniforms=uniforms, step_sizes=eps_c)
+    out = _dm(ir, f64=True).hmc(hcfg, np.zeros((C, D)), dtype=np.float64, momenta=momenta, uniforms=uniforms, step_sizes=eps_c)
+    assert np.array_equal(out["accepted"].cpu().numpy(), ref["accepted"])
+    np.testing.assert_allclose(out["states"].cpu().numpy(), ref["states"], atol=1e-9)
+    np.testing.assert_allclose(out["step_size"].cpu().numpy(), ref["step_size"], rtol=1e-7)
+
+
 @pytest.mark.parametrize("name,mode", [("eight_schools", PM4_EPS_POOLED), ("eight_schools", PM4_EPS_PER_CHAIN),
                                        ("radon_synth", PM4_EPS_PER_CHAIN)])
 def test_nuts_replay_bit_exact_integers(name, mode, oracle_mod):

@@ -222,6 +222,40 @@ def test_dual_averaging_recursion(oracle_mod):
     assert out["step_size"][0] > 1e-4  # the step size grew as the recursion demands
 
 
+def test_shrinkage_target_and_per_chain_initial_step_sizes(oracle_mod):
+    """tfp `shrinkage_target` replaces 10 x the initial step size in the recursion; a `step_size` with a leading chain
+    axis starts every chain from its own value (each then shrinks towards 10 x ITS initial step size)."""
+    import pymc4_b200 as pm
+
+    @pm.model
+    def m():
+        yield pm.Normal("x", 0.0, 1.0)
+
+    ir, _, _ = lower_model(m())
+    B, target = 2, 3e-4
+    cfg = make_hmc_cfg(1, 1, B, step_size=1e-4, num_leapfrog_steps=1, seed=5,
+                       adapt=make_adapt(mode=PM4_EPS_POOLED, num_adaptation_steps=B, shrinkage_target=target))
+    out = oracle_mod.Oracle(ir).hmc(cfg, np.zeros(1), dtype=np.float64)
+    err, log_avg = 0.0, 0.0
+    for t in range(B + 1):  # accept prob == 1 to ~1e-8 while eps stays tiny
+        step = t + 1.0
+        err += 0.75 - 1.0
+        log_eps = math.log(target) - err * math.sqrt(step) / ((10 + step) * 0.05)
+        log_avg = step ** -0.75 * log_eps + (1 - step ** -0.75) * log_avg
+    np.testing.assert_allclose(out["step_size"][0], math.exp(log_avg), rtol=1e-5)
+    # per-chain initial step sizes, no adaptation: the step sizes come back unchanged, and the first proposal of chain c
+    # is the leapfrog with ITS step size
+    from pymc4_b200._cstructs import PM4_EPS_PER_CHAIN
+
+    eps_c = np.array([0.05, 0.2, 0.8])
+    cfg = make_hmc_cfg(3, 1, 0, step_size=0.05, num_leapfrog_steps=1, seed=9, adapt=make_adapt(mode=PM4_EPS_PER_CHAIN, enabled=False))
+    mom = np.ones((1, 3, 1))
+    out = oracle_mod.Oracle(ir).hmc(cfg, np.full((3, 1), 0.5), dtype=np.float64, momenta=mom, step_sizes=eps_c)
+    np.testing.assert_allclose(out["step_size"], eps_c)
+    # one leapfrog from x = 0.5, p = 1 on the standard normal: x' = x + e (p - e x / 2)
+    np.testing.assert_allclose(out["traj"][0, :, 0], 0.5 + eps_c * (1.0 - 0.5 * eps_c * 0.5), rtol=1e-12)
+
+
 def test_nuts_standard_normal_and_determinism(oracle_mod):
     """Statistical sanity of the restated NUTS (reference tests/test_compound.py:124-146: |mean| < 0.1,
     same seed => same trace)."""

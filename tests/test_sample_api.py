@@ -334,3 +334,13 @@ def test_thinning_keeps_every_kth_state(sampler_type):
         np.testing.assert_array_equal(thin.posterior[name], full.posterior[name][:, 2::3])
     for name, v in thin.sample_stats.items():
         np.testing.assert_array_equal(v, full.sample_stats[name][:, 2::3])
+
+
+def test_step_sizes_that_differ_between_chains():
+    """`step_size` with a leading chain axis (reference samplers.py:406 passes it to tfp unchanged): with adaptation off
+    every chain keeps its own step size -- small steps accept almost always, a huge one almost never."""
+    eps = np.array([0.02, 0.02, 5.0, 5.0])
+    # (the sampler class without `num_adaptation_steps`: no adaptation, like the reference's _BaseSampler)
+    tr = pm.mcmc.samplers.HMC(M.schools_pm4(), step_size=eps)(num_samples=200, num_chains=4, burn_in=0, seed=2)
+    acc = np.exp(np.minimum(tr.sample_stats["mean_tree_accept"], 0.0)).mean(axis=1)
+    assert acc[0] > 0.9 and acc[1] > 0.9 and acc[2] < 0.3 and acc[3] < 0.3, acc
