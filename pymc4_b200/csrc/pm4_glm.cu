@@ -556,26 +556,26 @@ __global__ void glm_reduce_kernel(const double* __restrict__ LP2, const float* _
 // The constant operand is PRE-SPLIT once at upload (glm_image_kernel): per tile the two TF32 terms of the X rows as
 // GEMM1's B image and of the transposed tile as GEMM2's B image, already in the core-matrix layout the UMMA
 // descriptors describe, so a tile arrives with two TMA bulk copies and no CUDA core touches it.  Roles (warp
-// specialised, mbarrier pipeline): warp 0 = TMA producer, warps 1..3 = MMA issuers of GEMM1, warp 4 = of GEMM2, warps 5..20 = epilogue (warp w owns TMEM
-// lanes 32 (w % 4) .. +31 = 32 chains, and 8 of the tile's 32 observations).  A lane of the accumulator is a CHAIN
+// specialised, mbarrier pipeline): warp 0 = TMA producer, warp 1 = MMA issuer of GEMM1, warp 2 = of GEMM2, warps 3..18 = epilogue in two groups that take alternate tiles (warp w owns TMEM
+// lanes 32 (w % 4) .. +31 = 32 chains, and 16 of the tile's 32 observations).  A lane of the accumulator is a CHAIN
 // here, so the residuals of one chain are 16 consecutive K elements (columns) of GEMM2's A operand -- one tcgen05.st
 // per TF32 term -- and the log-likelihood sum of a chain needs no cross-lane reduction.
 // ------------------------------------------------------------------------------------------
 constexpr int FT = 32;                               // observations per tile
-constexpr int F_EPI = 16;                            // epilogue warps: 4 TMEM lane quarters x F_NQ column groups
-constexpr int F_NQ = F_EPI / 4, F_CW = FT / F_NQ;    // column groups per tile, observations per group (= one K step of GEMM2)
-static_assert(F_CW == UMMA_K, "one epilogue column group = one K step of the gradient GEMM");
-constexpr int F_W_G1 = 1, F_W_G2 = 4, F_W_EPI = 5;    // warp roles: 0 TMA producer, 1..3 GEMM1 (one accumulation chain each), 4 GEMM2, 5.. epilogue
+constexpr int F_EPI = 16;                            // epilogue warps: two groups of 8 that take alternate tiles
+constexpr int F_NQ = 2, F_CW = FT / F_NQ;            // column groups per tile (16 observations = two K steps of GEMM2)
+constexpr int F_W_G1 = 1, F_W_G2 = 2, F_W_EPI = 3;   // warp roles: 0 TMA producer, 1 GEMM1 issuer, 2 GEMM2 issuer, 3.. epilogue
 constexpr int F_THREADS = 32 * (F_W_EPI + F_EPI);
 constexpr int F_NSX = 4, F_NSXT = 2;                 // pipeline stages of the two operand images
-// tensor-memory map (512 columns): three eta accumulators (hi*hi, lo*hi, hi*lo: independent accumulation chains -- an MMA
-// that accumulates into the tile of its predecessor waits for it, and a 128 x 32 x 8 MMA is much shorter than that
-// latency) | G | beta hi | beta lo | R hi | R lo
+// tensor-memory map (512 columns, all of them): eta[buffer] | G | beta hi | beta lo | R[buffer][hi, lo].  Everything a
+// tile touches is double-buffered, so GEMM1 of tile i + 1 and GEMM2 of tile i - 1 run under the epilogue of tile i, and
+// the two epilogue groups (even / odd tiles) are half a period apart: the latencies of one (accumulator load, MUFU
+// chains, tcgen05.st, barrier round trips) hide behind the arithmetic of the other.
 constexpr uint32_t F_TMEM_COLS = 512;
-constexpr uint32_t F_G_COL = 96, F_BHI_COL = 208, F_BLO_COL = 312, F_R_COL = 416;
+constexpr uint32_t F_G_COL = 64, F_BHI_COL = 176, F_BLO_COL = 280, F_R_COL = 384;
 enum { FB_FULL_X = 0, FB_EMPTY_X = FB_FULL_X + F_NSX, FB_FULL_XT = FB_EMPTY_X + F_NSX, FB_EMPTY_XT = FB_FULL_XT + F_NSXT,
-       FB_ETA_FULL = FB_EMPTY_XT + F_NSXT, FB_ETA_EMPTY = FB_ETA_FULL + 1, FB_R_FULL = FB_ETA_EMPTY + 1 /* [column group] */,
-       FB_R_EMPTY = FB_R_FULL + F_NQ, FB_G_DONE = FB_R_EMPTY + F_NQ, FB_COUNT };
+       FB_ETA_FULL = FB_EMPTY_XT + F_NSXT, FB_ETA_EMPTY = FB_ETA_FULL + 2, FB_R_FULL = FB_ETA_EMPTY + 2 /* [buffer][column group] */,
+       FB_R_EMPTY = FB_R_FULL + 2 * F_NQ, FB_G_DONE = FB_R_EMPTY + 2 * F_NQ, FB_COUNT };
 
 __device__ __forceinline__ bool mbar_wait_short(uint64_t* mbar, uint32_t parity) {
   uint32_t done = 0;
@@ -787,10 +787,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
   }
   if (tid == 0) {
     for (int b = 0; b < FB_COUNT; ++b) {
-      const uint32_t cnt = b == FB_ETA_EMPTY ? (uint32_t)F_EPI
-                           : (b >= FB_R_FULL && b < FB_R_FULL + F_NQ) ? 4u
-                           : (b == FB_ETA_FULL || (b >= FB_EMPTY_X && b < FB_EMPTY_X + F_NSX)) ? 3u  /* one commit per chain issuer */
-                                                                       : 1u;
+      const uint32_t cnt = (b >= FB_ETA_EMPTY && b < FB_ETA_EMPTY + 2) ? (uint32_t)(F_EPI / 2)
+                           : (b >= FB_R_FULL && b < FB_R_FULL + 2 * F_NQ) ? 4u
+                                                                          : 1u;
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bars + b)), "r"(cnt));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -800,14 +799,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const bool epi = warp >= F_W_EPI;
-  const int q = warp & 3, h = (warp - F_W_EPI) >> 2, row = q * 32 + lane;  // epilogue warps: TMEM lane quarter, column group
+  // epilogue warps: TMEM lane quarter q, column group h of the tile, tile parity grp (group 0: even tiles, 1: odd)
+  const int q = warp & 3, ew = (warp - F_W_EPI) >> 2, h = ew & (F_NQ - 1), grp = ew >> 1, row = q * 32 + lane;
   const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
   if (epi) {
     // the CTA's chain tile beta[c0 .. c0 + 127, :] goes to tensor memory once, split into its two TF32 terms: GEMM1's
     // A operand (lane = chain, one column per covariate), which then costs no shared-memory bandwidth
     const bool live_row = c0 + row < C;
     const float* tp = theta + (size_t)(c0 + row) * ldt + base;
-    for (int k0 = 8 * h; k0 < K; k0 += 8 * F_NQ) {
+    for (int k0 = 8 * ew; k0 < K; k0 += 8 * (F_EPI / 4)) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -871,30 +871,34 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
       if (my_pace && lane == 0) atomicMax(my_pace + blockIdx.y, 0x7fffffff);  // done: never hold the others back
       if (!ok && lane == 0 && error) *error = 3;
     }
-  } else if (warp >= F_W_G1 && warp < F_W_G1 + 3) {
-    // ---- MMA issuers of GEMM1 (eta tiles): A = beta in tensor memory, B = the X rows of the tile in shared memory.
-    // One warp per accumulation chain (hi*hi, lo*hi, hi*lo -> three accumulators the epilogue adds): an MMA that
-    // accumulates into the tile of its predecessor waits for it, and one thread cannot issue 39 small MMAs per tile
-    // fast enough.  The whole warp runs the loop (waits are warp-uniform); one elected lane issues.
+  } else if (warp == F_W_G1) {
+    // ---- MMA issuer of GEMM1 (eta tiles): A = beta in tensor memory, B = the X rows of the tile in shared memory.
+    // The whole warp runs the loop (waits are warp-uniform); one elected lane issues -- under `if (lane == 0)` the
+    // compiler wraps every MMA in an election loop and one thread cannot issue 39 small MMAs per tile fast enough.
     // (a K step of 8 tf32 = 256 bytes = 16 units of the descriptor's 16-byte address field)
-    const int chain = warp - F_W_G1;
     if (nt > 0) {
       const uint32_t idesc1 = make_idesc(TILE, FT);
       const uint32_t sbo1 = (uint32_t)K4 * 128u, lbo = 128u;
       const int KS = K / UMMA_K;
-      const uint32_t a_base = tmem + (chain == 1 ? F_BLO_COL : F_BHI_COL), d = tmem + (uint32_t)chain * FT;
+      const uint32_t a_hi = tmem + F_BHI_COL, a_lo = tmem + F_BLO_COL;
       for (int i = 0; i < nt && ok; ++i) {
-        const int s2 = i % F_NSX;
-        if (i >= 1) ok = mbar_wait_short(bars + FB_ETA_EMPTY, (uint32_t)(i - 1) & 1u);  // the epilogue has read tile i - 1
+        const int s2 = i % F_NSX, bsel = i & 1;
+        if (i >= 2) ok = mbar_wait_short(bars + FB_ETA_EMPTY + bsel, (uint32_t)((i - 2) >> 1) & 1u);  // the epilogue has read tile i - 2
         if (ok) ok = mbar_wait_short(bars + FB_FULL_X + s2, (uint32_t)(i / F_NSX) & 1u);
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint64_t db = make_desc(smem_u32(xa0 + (size_t)s2 * 2 * xa_part + (chain == 2 ? xa_part : 0u)), lbo, sbo1);
-          mma_tf32_ts(d, a_base, db, idesc1, 0u);
+          const uint64_t dx_hi = make_desc(smem_u32(xa0 + (size_t)s2 * 2 * xa_part), lbo, sbo1);
+          const uint64_t dx_lo = dx_hi + (uint64_t)(xa_part >> 4);
+          const uint32_t d = tmem + (uint32_t)bsel * FT;
+          mma_tf32_ts(d, a_hi, dx_hi, idesc1, 0u);  // hi*hi
 #pragma unroll 4
-          for (int ks = 1; ks < KS; ++ks) mma_tf32_ts(d, a_base + (uint32_t)(ks * UMMA_K), db + (uint64_t)(ks * 16), idesc1, 1u);
-          mma_commit(bars + FB_ETA_FULL);
+          for (int ks = 1; ks < KS; ++ks) mma_tf32_ts(d, a_hi + (uint32_t)(ks * UMMA_K), dx_hi + (uint64_t)(ks * 16), idesc1, 1u);
+#pragma unroll 4
+          for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, a_lo + (uint32_t)(ks * UMMA_K), dx_hi + (uint64_t)(ks * 16), idesc1, 1u);  // lo*hi
+#pragma unroll 4
+          for (int ks = 0; ks < KS; ++ks) mma_tf32_ts(d, a_hi + (uint32_t)(ks * UMMA_K), dx_lo + (uint64_t)(ks * 16), idesc1, 1u);  // hi*lo
+          mma_commit(bars + FB_ETA_FULL + bsel);
           mma_commit(bars + FB_EMPTY_X + s2);
         }
         __syncwarp();
@@ -910,22 +914,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
       const uint32_t d = tmem + F_G_COL;
       uint32_t acc_g = 0;
       for (int i = 0; i < nt && ok; ++i) {
-        const int s2 = i % F_NSXT;
+        const int s2 = i % F_NSXT, bsel = i & 1;
         ok = mbar_wait_short(bars + FB_FULL_XT + s2, (uint32_t)(i / F_NSXT) & 1u);
         const uint64_t dt_hi = make_desc(smem_u32(xb0 + (size_t)s2 * 2 * xb_part), lbo, sbo2);
         const uint64_t dt_lo = make_desc(smem_u32(xb0 + (size_t)s2 * 2 * xb_part + xb_part), lbo, sbo2);
-        const uint32_t r_hi = tmem + F_R_COL, r_lo = r_hi + 32u;
-        for (int hh = 0; hh < F_NQ && ok; ++hh) {  // the column groups of R (8 observations = one K step) become ready independently
-          ok = mbar_wait_short(bars + FB_R_FULL + hh, (uint32_t)i & 1u);
+        const uint32_t r_hi = tmem + F_R_COL + (uint32_t)bsel * 64u, r_lo = r_hi + 32u;
+        for (int hh = 0; hh < F_NQ && ok; ++hh) {  // the column groups of R (16 observations = two K steps) become ready independently
+          ok = mbar_wait_short(bars + FB_R_FULL + F_NQ * bsel + hh, (uint32_t)(i >> 1) & 1u);
           if (!ok) break;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
-            const uint32_t ck = (uint32_t)hh * UMMA_K;
-            const uint64_t o = (uint64_t)(hh * 16);
-            mma_tf32_ts(d, r_hi + ck, dt_hi + o, idesc2, acc_g);
-            mma_tf32_ts(d, r_lo + ck, dt_hi + o, idesc2, 1u);
-            mma_tf32_ts(d, r_hi + ck, dt_lo + o, idesc2, 1u);
-            mma_commit(bars + FB_R_EMPTY + hh);
+#pragma unroll
+            for (int kk = 0; kk < F_CW / UMMA_K; ++kk) {
+              const uint32_t ck = (uint32_t)(hh * (F_CW / UMMA_K) + kk) * UMMA_K;
+              const uint64_t o = (uint64_t)((hh * (F_CW / UMMA_K) + kk) * 16);
+              mma_tf32_ts(d, r_hi + ck, dt_hi + o, idesc2, (kk == 0) ? acc_g : 1u);
+              mma_tf32_ts(d, r_lo + ck, dt_hi + o, idesc2, 1u);
+              mma_tf32_ts(d, r_hi + ck, dt_lo + o, idesc2, 1u);
+            }
+            mma_commit(bars + FB_R_EMPTY + F_NQ * bsel + hh);
             if (hh == F_NQ - 1) {
               mma_commit(bars + FB_EMPTY_XT + s2);
               if (i == nt - 1) mma_commit(bars + FB_G_DONE);
@@ -938,39 +945,40 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
       if (!ok && lane == 0 && error) *error = 6;
     }
   } else {
-    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (chains), observations F_CW h .. F_CW h + F_CW - 1 ----
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. + 31 (chains), observations F_CW h .. F_CW h + F_CW - 1 of the
+    // tiles of its group's parity ----
     double ll_acc = 0.0;
     float yv[F_CW];
-    auto fetch_y = [&](int i) {  // the tile's observations of this column group (prefetched one tile ahead)
+    auto fetch_y = [&](int i) {  // the tile's observations of this column group (prefetched one tile of the group ahead)
       const int o0 = ((int)blockIdx.x + i * stride) * FT + F_CW * h;
       if (o0 + F_CW <= n) {
-        const float4 a4 = __ldg(reinterpret_cast<const float4*>(y + o0)), b4 = __ldg(reinterpret_cast<const float4*>(y + o0 + 4));
-        yv[0] = a4.x; yv[1] = a4.y; yv[2] = a4.z; yv[3] = a4.w; yv[4] = b4.x; yv[5] = b4.y; yv[6] = b4.z; yv[7] = b4.w;
+#pragma unroll
+        for (int j4 = 0; j4 < F_CW / 4; ++j4) {
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(y + o0) + j4);
+          yv[4 * j4] = a4.x; yv[4 * j4 + 1] = a4.y; yv[4 * j4 + 2] = a4.z; yv[4 * j4 + 3] = a4.w;
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < F_CW; ++j) yv[j] = o0 + j < n ? __ldg(y + o0 + j) : 0.0f;
       }
     };
-    if (nt > 0) fetch_y(0);
-    for (int i = 0; i < nt && ok; ++i) {
+    if (grp < nt) fetch_y(grp);
+    for (int i = grp; i < nt && ok; i += 2) {
       const int o0 = ((int)blockIdx.x + i * stride) * FT + F_CW * h;
-      ok = mbar_wait_short(bars + FB_ETA_FULL, (uint32_t)i & 1u);
+      ok = mbar_wait_short(bars + FB_ETA_FULL + grp, (uint32_t)(i >> 1) & 1u);
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t v[F_CW], v1[F_CW], v2[F_CW];
-      tmem_ld8_nowait(lane_addr + (uint32_t)(F_CW * h), v);
-      tmem_ld8_nowait(lane_addr + FT + (uint32_t)(F_CW * h), v1);
-      tmem_ld8_nowait(lane_addr + 2 * FT + (uint32_t)(F_CW * h), v2);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      uint32_t v[F_CW];
+      tmem_ld16(lane_addr + (uint32_t)grp * FT + (uint32_t)(F_CW * h), v);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + FB_ETA_EMPTY);
+      if (lane == 0) mbar_arrive(bars + FB_ETA_EMPTY + grp);
       uint32_t rh[F_CW], rl[F_CW];
       float ll = 0.0f;
       const int n_live = n - o0;  // observations of this group that exist (>= F_CW except in the last tile)
 #pragma unroll
       for (int j = 0; j < F_CW; ++j) {
-        const float eta = (__uint_as_float(v[j]) + __uint_as_float(v1[j])) + __uint_as_float(v2[j]);
+        const float eta = __uint_as_float(v[j]);
         // softplus(eta) = max(eta, 0) + log1p(exp(-|eta|)); sigmoid from the same exponential (MUFU ex2 / lg2 / rcp)
         const float e = fast_ex2(-1.4426950408889634f * fabsf(eta));
         const float d1 = 1.0f + e;
@@ -985,26 +993,26 @@ __global__ void __launch_bounds__(F_THREADS, 1) glm_fused_kernel(const unsigned 
         rl[j] = __float_as_uint(to_tf32(r - hv));
       }
       ll_acc += (double)ll;
-      if (i + 1 < nt) fetch_y(i + 1);
-      if (i >= 1) {  // GEMM2 of tile i - 1 has read this column group of R
-        ok = mbar_wait_short(bars + FB_R_EMPTY + h, (uint32_t)(i - 1) & 1u);
+      if (i + 2 < nt) fetch_y(i + 2);
+      if (i >= 2) {  // GEMM2 of tile i - 2 has read this column group of this R buffer
+        ok = mbar_wait_short(bars + FB_R_EMPTY + F_NQ * grp + h, (uint32_t)((i - 2) >> 1) & 1u);
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       // the residuals of a chain are consecutive K elements of GEMM2's A operand: straight into tensor memory
-      tmem_st8(lane_addr + F_R_COL + (uint32_t)(F_CW * h), rh);
-      tmem_st8(lane_addr + F_R_COL + 32u + (uint32_t)(F_CW * h), rl);
+      tmem_st16(lane_addr + F_R_COL + (uint32_t)grp * 64u + (uint32_t)(F_CW * h), rh);
+      tmem_st16(lane_addr + F_R_COL + (uint32_t)grp * 64u + 32u + (uint32_t)(F_CW * h), rl);
       tmem_st_wait();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + FB_R_FULL + h);
+      if (lane == 0) mbar_arrive(bars + FB_R_FULL + F_NQ * grp + h);
     }
     // per-chain partial of the log-likelihood (this CTA's observations, this half) and of the gradient
-    LPp[((size_t)blockIdx.x * F_NQ + h) * Cp + c0 + row] = ok ? ll_acc : 0.0;
+    LPp[((size_t)blockIdx.x * (F_EPI / 4) + ew) * Cp + c0 + row] = ok ? ll_acc : 0.0;
     if (ok && nt > 0) ok = mbar_wait_short(bars + FB_G_DONE, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float* dst = GP + ((size_t)blockIdx.x * Cp + c0 + row) * Pp;
-    for (int cc = 8 * h; cc < Pp; cc += 8 * F_NQ) {
+    for (int cc = 8 * ew; cc < Pp; cc += 8 * (F_EPI / 4)) {
       uint32_t v[8];
       if (ok && nt > 0) tmem_ld8(lane_addr + F_G_COL + (uint32_t)cc, v);
 #pragma unroll
@@ -1025,7 +1033,7 @@ __global__ void glm_fused_reduce_kernel(const double* __restrict__ LPp, const fl
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < C) {
     double s = 0;
-    for (int g = 0; g < F_NQ * groups; ++g) s += LPp[(size_t)g * Cp + idx];
+    for (int g = 0; g < (F_EPI / 4) * groups; ++g) s += LPp[(size_t)g * Cp + idx];
     lp[idx] += (float)s;
   }
   if (idx < C * P) {
@@ -1137,7 +1145,7 @@ extern "C" int pm4_glm_build_image(const float* X, int n, int P, void* image, vo
 extern "C" int64_t pm4_glm_fused_work_bytes(int n, int P, int C) {
   const int64_t Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16;
   const int64_t groups = fused_groups(n, (int)Cp);
-  return 8 * F_NQ * groups * Cp + 4 * groups * Cp * Pp + 4 * groups * (Cp / TILE) + 256;
+  return 8 * (F_EPI / 4) * groups * Cp + 4 * groups * Cp * Pp + 4 * groups * (Cp / TILE) + 256;
 }
 
 extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n, int P, const float* theta, int ldt, int base,
@@ -1148,7 +1156,7 @@ extern "C" int pm4_glm_fused_logp_grad(const void* image, const float* y, int n,
   const int Cp = (C + TILE - 1) / TILE * TILE, Pp = (P + 15) / 16 * 16, K = (P + 7) & ~7;
   const int groups = fused_groups(n, Cp);
   double* LPp = (double*)work;
-  float* GP = (float*)(LPp + (size_t)F_NQ * groups * Cp);
+  float* GP = (float*)(LPp + (size_t)(F_EPI / 4) * groups * Cp);
   const size_t smem = (size_t)F_NSX * 2 * FT * K * 4 + (size_t)F_NSXT * 2 * Pp * FT * 4 + 8 * FB_COUNT + 16;
   cudaError_t e = cudaFuncSetAttribute(glm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
