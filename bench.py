@@ -385,6 +385,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout=5.0):
+        """Block until the first sample has arrived (the start-up of nvidia-smi is over)."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def mark(self):
+        """The timed region starts now: earlier samples are dropped."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -395,7 +405,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -583,13 +593,17 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm: inputs already in HBM ------------------------------------
-    for w in range(args.warmup):
-        out = run_step(cfg_for(1000 + w))
-    torch.cuda.synchronize()
-
+    # the clock sampler (one long-running `nvidia-smi -lms 100`) starts BEFORE the warm-up steps: its start-up (NVML
+    # attach, ~0.5 s) stalls whatever step it lands in by ~100 ms; only the samples taken during the timed region count
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for w in range(args.warmup):
+        out = run_step(cfg_for(1000 + w))
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark()
     barrier()
     _cabi.launch_count(reset=True)
     step_ms, leaps, detail = [], 0, []
