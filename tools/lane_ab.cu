@@ -27,16 +27,16 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(1); } } while (0)
 
 constexpr int G = 85, N = 919, D = 2 * G + 5;
-constexpr int MAXW = 16;
+constexpr int MAXW = 32;
 
 __constant__ float2 c_obs[N];          // (x, y) per observation, sorted by group
 __constant__ int c_gstart[G + 1];      // first observation of every group
 __constant__ int c_wstart[MAXW + 1];   // first group of every warp (filled per W before a launch)
 
-template <int W, bool OBS_CONST>
+template <int W, bool OBS_CONST, bool MASKED>
 __global__ void __launch_bounds__(32 * W) lane_leapfrog(const float* __restrict__ th0, const float* __restrict__ p0,
                                                        float* __restrict__ th_out, float* __restrict__ p_out,
-                                                       int C, int L, float eps) {
+                                                       int C, int L, float eps, const int* __restrict__ Lc) {
     extern __shared__ float sm[];
     float* th = sm;
     float* p = th + D * 32;
@@ -53,7 +53,12 @@ __global__ void __launch_bounds__(32 * W) lane_leapfrog(const float* __restrict_
         for (int i = threadIdx.x; i < N; i += 32 * W) obs[i] = c_obs[i];
     __syncthreads();
     const int gs = c_wstart[w], ge = c_wstart[w + 1];
+    // `Lc` (masked mode): every chain walks its own number of leapfrogs, the CTA walks the longest of its 32 chains (what
+    // a NUTS kernel in this layout does with trees of different sizes); every warp of the CTA sees the same 32 chains
+    const int myL = MASKED ? Lc[chain] : L;
+    if (MASKED) L = __reduce_max_sync(0xffffffffu, myL);
     for (int step = 0; step < L; ++step) {
+        const bool act = !MASKED || step < myL;
         const float mua = th[0 * 32 + lane], lsa = th[1 * 32 + lane], mub = th[2 * 32 + lane], lsb = th[3 * 32 + lane];
         const float le = th[(D - 1) * 32 + lane];
         const float isa2 = __expf(-2.f * lsa), isb2 = __expf(-2.f * lsb), ie2 = __expf(-2.f * le);
@@ -77,9 +82,11 @@ __global__ void __launch_bounds__(32 * W) lane_leapfrog(const float* __restrict_
             acc_s2 += s2;
             // kick + drift of the owned coordinates right away (nobody else reads them)
             const float pa = fmaf(eps, ga, p[(4 + g) * 32 + lane]), pb = fmaf(eps, gb, p[(4 + G + g) * 32 + lane]);
-            p[(4 + g) * 32 + lane] = pa; p[(4 + G + g) * 32 + lane] = pb;
-            gr[(4 + g) * 32 + lane] = ga; gr[(4 + G + g) * 32 + lane] = gb;
-            th[(4 + g) * 32 + lane] = fmaf(eps, pa, a); th[(4 + G + g) * 32 + lane] = fmaf(eps, pb, b);
+            if (act) {
+                p[(4 + g) * 32 + lane] = pa; p[(4 + G + g) * 32 + lane] = pb;
+                gr[(4 + g) * 32 + lane] = ga; gr[(4 + G + g) * 32 + lane] = gb;
+                th[(4 + g) * 32 + lane] = fmaf(eps, pa, a); th[(4 + G + g) * 32 + lane] = fmaf(eps, pb, b);
+            }
         }
         red[(w * 5 + 0) * 32 + lane] = acc_ma * isa2;
         red[(w * 5 + 1) * 32 + lane] = acc_za * isa2;
@@ -105,9 +112,11 @@ __global__ void __launch_bounds__(32 * W) lane_leapfrog(const float* __restrict_
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const float pk = fmaf(eps, gsc[k], p[dd[k] * 32 + lane]);
-                p[dd[k] * 32 + lane] = pk;
-                gr[dd[k] * 32 + lane] = gsc[k];
-                th[dd[k] * 32 + lane] = fmaf(eps, pk, cur[k]);
+                if (act) {
+                    p[dd[k] * 32 + lane] = pk;
+                    gr[dd[k] * 32 + lane] = gsc[k];
+                    th[dd[k] * 32 + lane] = fmaf(eps, pk, cur[k]);
+                }
             }
         }
         __syncthreads();
@@ -162,7 +171,7 @@ static void run_one(int C, int L, float eps, const float* d_th0, const float* d_
     }
     CK(cudaMemcpyToSymbol(c_wstart, ws.data(), sizeof(int) * (MAXW + 1)));
     const size_t smem = sizeof(float) * (3 * D * 32 + W * 5 * 32) + (OC ? 0 : sizeof(float2) * N);
-    auto kern = lane_leapfrog<W, OC>;
+    auto kern = lane_leapfrog<W, OC, false>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
@@ -170,7 +179,7 @@ static void run_one(int C, int L, float eps, const float* d_th0, const float* d_
     float best = 1e30f, ms[4];
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(e0));
-        kern<<<C / 32, 32 * W, smem>>>(d_th0, d_p0, d_th, d_p, C, L, eps);
+        kern<<<C / 32, 32 * W, smem>>>(d_th0, d_p0, d_th, d_p, C, L, eps, nullptr);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
@@ -195,6 +204,71 @@ static void run_one(int C, int L, float eps, const float* d_th0, const float* d_
            best * 1e3 / L / std::max(1.0, ceil((double)(C / 32) / (148.0 * occ))), occ, smem, maxerr);
     fflush(stdout);
     CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+}
+
+// Masked mode: tree sizes drawn from the distribution measured on the headline run (tools/tree_stats.py: 77 % of the
+// trees 31 leapfrogs, 15 % 63, 0.12 % 127, 0.011 % 255, the rest 15), one launch = one lock-step transition of all
+// chains in this layout (its duration is set by the CTA with the deepest tree); no tree bookkeeping is executed.
+template <int W>
+static void run_masked(int C, float eps, const float* d_th0, const float* d_p0, float* d_th, float* d_p,
+                       const std::vector<int>& gstart, const std::vector<float>& h_th0, const std::vector<float>& h_p0,
+                       const std::vector<float2>& obs, std::mt19937_64& rng) {
+    std::vector<int> ws(MAXW + 1, G);
+    {
+        double total = 7.0 * N + 35.0 * G, acc = 0; int w = 0; ws[0] = 0;
+        for (int g = 0; g < G; ++g) {
+            acc += 7.0 * (gstart[g + 1] - gstart[g]) + 35.0;
+            while (w + 1 < W && acc >= total * (w + 1) / W) ws[++w] = g + 1;
+        }
+        for (int v = w + 1; v <= MAXW; ++v) ws[v] = G;
+    }
+    CK(cudaMemcpyToSymbol(c_wstart, ws.data(), sizeof(int) * (MAXW + 1)));
+    const size_t smem = sizeof(float) * (3 * D * 32 + W * 5 * 32) + sizeof(float2) * N;
+    auto kern = lane_leapfrog<W, false, true>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int* d_L; CK(cudaMalloc(&d_L, sizeof(int) * C));
+    std::uniform_real_distribution<double> ud(0.0, 1.0);
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int R = 24;
+    double sum_ms = 0, max_ms = 0, useful = 0, walked = 0, maxerr = 0; int deepest = 0;
+    std::vector<int> hL(C);
+    std::vector<float> h_th((size_t)D * C);
+    for (int rep = 0; rep < R + 1; ++rep) {
+        for (int c = 0; c < C; ++c) {
+            const double u = ud(rng);
+            hL[c] = u < 0.77 ? 31 : u < 0.92 ? 63 : u < 0.9212 ? 127 : u < 0.92131 ? 255 : 15;
+        }
+        CK(cudaMemcpy(d_L, hL.data(), sizeof(int) * C, cudaMemcpyHostToDevice));
+        CK(cudaEventRecord(e0));
+        kern<<<C / 32, 32 * W, smem>>>(d_th0, d_p0, d_th, d_p, C, 0, eps, d_L);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaGetLastError());
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep == 0) continue;   // warm-up
+        sum_ms += ms; max_ms = std::max(max_ms, (double)ms);
+        for (int b = 0; b < C / 32; ++b) {
+            int mx = 0;
+            for (int l = 0; l < 32; ++l) { useful += hL[b * 32 + l]; mx = std::max(mx, hL[b * 32 + l]); }
+            walked += 32.0 * mx; deepest = std::max(deepest, mx);
+        }
+        if (rep == 1) {
+            CK(cudaMemcpy(h_th.data(), d_th, sizeof(float) * D * C, cudaMemcpyDeviceToHost));
+            const int probe[3] = {0, C / 2 + 7, C - 1};
+            for (int c : probe) {
+                std::vector<double> th(D), p(D);
+                for (int d = 0; d < D; ++d) { th[d] = h_th0[(size_t)d * C + c]; p[d] = h_p0[(size_t)d * C + c]; }
+                host_chain(obs, gstart, th, p, hL[c], eps);
+                for (int d = 0; d < D; ++d) maxerr = std::max(maxerr, fabs(th[d] - (double)h_th[(size_t)d * C + c]));
+            }
+        }
+    }
+    printf("{\"layout\": \"lane-per-chain, tree sizes of the headline run (masked lanes)\", \"chains\": %d, \"warps_per_cta\": %d, "
+           "\"launches\": %d, \"mean_ms_per_transition\": %.4f, \"max_ms_per_transition\": %.4f, \"useful_units_per_s\": %.4e, "
+           "\"useful_lane_fraction\": %.4f, \"deepest_tree\": %d, \"max_abs_err_vs_f64\": %.3e}\n",
+           C, W, R, sum_ms / R, max_ms, useful / (sum_ms * 1e-3), useful / walked, deepest, maxerr);
+    fflush(stdout);
+    CK(cudaFree(d_L)); CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
 }
 
 int main(int argc, char** argv) {
@@ -246,10 +320,13 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(d_p0, h_p0.data(), bytes, cudaMemcpyHostToDevice));
 #define RUN(W, OC) run_one<W, OC>(C, L, eps, d_th0, d_p0, d_th, d_p, gstart, h_th0, h_p0, obs)
         if (one) {
-            if (oneW == 4) RUN(4, false); else if (oneW == 8) RUN(8, false); else RUN(16, false);
+            if (oneW == 4) RUN(4, false); else if (oneW == 8) RUN(8, false); else if (oneW == 32) RUN(32, false); else RUN(16, false);
         } else {
-        RUN(1, false); RUN(2, false); RUN(4, false); RUN(8, false); RUN(16, false);
+        RUN(1, false); RUN(2, false); RUN(4, false); RUN(8, false); RUN(16, false); RUN(32, false);
         RUN(1, true); RUN(4, true); RUN(8, true); RUN(16, true);
+        run_masked<8>(C, eps, d_th0, d_p0, d_th, d_p, gstart, h_th0, h_p0, obs, rng);
+        run_masked<16>(C, eps, d_th0, d_p0, d_th, d_p, gstart, h_th0, h_p0, obs, rng);
+        run_masked<32>(C, eps, d_th0, d_p0, d_th, d_p, gstart, h_th0, h_p0, obs, rng);
         }
 #undef RUN
         CK(cudaFree(d_th0)); CK(cudaFree(d_p0)); CK(cudaFree(d_th)); CK(cudaFree(d_p));
