@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <string>
+#include <atomic>
 #include <vector>
 
 #include "../../include/pm4b200.h"
@@ -760,10 +761,25 @@ extern "C" int64_t pm4_scratch_bytes(const pm4_model_t* m, int dtype, int C, int
 
 namespace {
 // device buffers of one run; freed on scope exit (stream-ordered)
+// The default stream-ordered pool hands freed memory back to the driver at the next synchronisation (release
+// threshold 0): every run would map its scratch again and every host synchronisation after a run would pay for the
+// unmapping.  Keep up to 256 MiB of freed scratch in the pool (set once per device).
+static void retain_run_scratch() {
+  static std::atomic<unsigned> done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) { cudaGetLastError(); return; }
+  if (done.fetch_or(1u << dev) & (1u << dev)) return;
+  cudaMemPool_t pool;
+  uint64_t keep = 256ull << 20;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess ||
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess)
+    cudaGetLastError();
+}
+
 struct RunBuffers {
   cudaStream_t st;
   std::vector<void*> ptrs;
-  explicit RunBuffers(cudaStream_t s) : st(s) {}
+  explicit RunBuffers(cudaStream_t s) : st(s) { retain_run_scratch(); }
   ~RunBuffers() {
     for (void* p : ptrs) cudaFreeAsync(p, st);
   }

@@ -135,8 +135,10 @@ def _fetch_all(groups):
     if pending:
         import torch
 
+        # the copies were issued on each device's current stream: wait for those streams only (a device-wide
+        # synchronisation also waits for whatever else the driver has pending on the device)
         for dev in set(pending):
-            torch.cuda.synchronize(dev)
+            torch.cuda.current_stream(dev).synchronize()
     return [({k: _to_numpy(v) for k, v in g.items()} if isinstance(g, dict) else g) for g in out]
 
 
