@@ -787,6 +787,11 @@ struct RunBuffers {
     cudaError_t e = cudaMallocAsync(out, bytes ? bytes : 16, st);
     if (e != cudaSuccess) return fail(PM4_ENOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
     ptrs.push_back(*out);
+    // run scratch starts zeroed: the padded tails of the state rows (columns D .. DP of th / gr) are read by the team
+    // kernels and never written, and with the pool retaining memory a buffer may come back with a previous run's
+    // contents (a freshly mapped one reads as zeros)
+    e = cudaMemsetAsync(*out, 0, bytes ? bytes : 16, st);
+    if (e != cudaSuccess) return fail(PM4_ECUDA, "cudaMemsetAsync(%zu): %s", bytes, cudaGetErrorString(e));
     return PM4_OK;
   }
 };
