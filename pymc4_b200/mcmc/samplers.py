@@ -160,6 +160,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
         self.seed = seed
         self._dtype = dtype
         self._device_model = logpfn.device_model
+        self._ir_own = logpfn.ir  # names come from THIS model: a cached device model may have been built for a same-structure model with other names
         if xla:
             _log.debug("`xla=True` has no effect: the sampler is already one fused CUDA kernel")
 
@@ -179,12 +180,12 @@ class _BaseSampler(metaclass=abc.ABCMeta):
             sample_stats = sample_stats[: len(self.stat_names)]
         sampler_stats = dict(zip(self.stat_names, sample_stats))
         if len(deterministic_names) > 0:
-            det_names = [d.name for d in self._device_model.ir.dets]
+            det_names = [d.name for d in self._ir.dets]
             posterior.update(dict(zip(det_names, deterministic_values)))
 
         log_likelihood_dict = dict()
         if include_log_likelihood:
-            log_likelihood_dict = _log_likelihood_from_states(self._device_model, self._last_states, self._dtype)
+            log_likelihood_dict = _log_likelihood_from_states(self._device_model, self._last_states, self._dtype, ir=self._ir)
         self.last_run_info = self._run_info
         return trace_to_arviz(
             posterior,
@@ -204,7 +205,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
                                      -> per-chain adaptation of a multiplier of a fixed per-dimension
                                         scale (all dimensions of a chain see the same update).
         """
-        ir = self._device_model.ir
+        ir = self._ir
         self._chain_step_sizes = None
         if isinstance(step_size, (list, tuple)) and len(step_size) == len(ir.rvs):
             scale = np.ones(ir.D, dtype=np.float64)
@@ -229,8 +230,16 @@ class _BaseSampler(metaclass=abc.ABCMeta):
             return 1.0, arr.reshape(-1), PM4_EPS_POOLED
         raise ValueError("cannot interpret step_size of shape {} for {} chains, D={}".format(arr.shape, num_chains, ir.D))
 
+    @property
+    def _ir(self):
+        """The lowered model of this sampler's own model.  `_get_device_model` shares device models between models of
+        identical structure and layout, whose variable names may differ: offsets and shapes are the cached model's,
+        names must be this model's."""
+        own = getattr(self, "_ir_own", None)
+        return own if own is not None else self._device_model.ir
+
     def _pack_init(self, init: List[np.ndarray]) -> np.ndarray:
-        ir = self._device_model.ir
+        ir = self._ir
         C = int(np.shape(init[0])[0])
         theta0 = np.empty((C, ir.D), dtype=np.float64)
         for rv, part in zip(ir.rvs, init):
@@ -241,7 +250,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
         """device [S, C, D] -> list of per-variable views [S, C, *core] in trace order."""
         S, C = states.shape[0], states.shape[1]
         return [states[:, :, rv.offset: rv.offset + rv.size].reshape((S, C) + rv.shape)
-                for rv in self._device_model.ir.rvs]
+                for rv in self._ir.rvs]
 
     def _seed_value(self) -> int:
         if self.seed is None:
@@ -291,7 +300,7 @@ class _BaseSampler(metaclass=abc.ABCMeta):
         return out
 
     def _deterministic_values(self, states):
-        ir = self._device_model.ir
+        ir = self._ir
         if not ir.dets:
             return ()
         out = self._device_model.deterministics(states, dtype=self._dtype)
@@ -415,7 +424,7 @@ class NUTS(_BaseSampler):
             out["states_host_ready"]()
             host = out["states_host"].numpy()
             S = host.shape[0]
-            results = [host[:, :, rv.offset: rv.offset + rv.size].reshape((S, C) + rv.shape) for rv in dm.ir.rvs]
+            results = [host[:, :, rv.offset: rv.offset + rv.size].reshape((S, C) + rv.shape) for rv in self._ir.rvs]
         else:
             results = self._unpack_states(out["states"])
         return results, stats
@@ -622,7 +631,7 @@ class CompoundStep(_BaseSampler):
 
     def _blocks(self, burn_in: int):
         """(block records for ``DeviceModel.compound``, one per merged sampler) from ``compound_samplers``."""
-        ir = self._device_model.ir
+        ir = self._ir
         by_name = {rv.name: rv for rv in ir.rvs}
         blocks = []
         for (sampler, user_kwargs), names in zip(self.kernel_kwargs["compound_samplers"], self._block_vars):
@@ -839,10 +848,10 @@ def tile_init(init, num_repeats):
     return [np.tile(np.expand_dims(np.asarray(t), 0), [num_repeats] + [1] * np.ndim(t)) for t in init]
 
 
-def _log_likelihood_from_states(dm, states, dtype) -> Dict[str, Any]:
+def _log_likelihood_from_states(dm, states, dtype, ir=None) -> Dict[str, Any]:
     """states [S, C, D] (device) -> {observed name: [S, C, *shape]} device tensors: one kernel evaluates
     every observed term element-wise for every state (no reduction)."""
-    ir = dm.ir
+    ir = dm.ir if ir is None else ir  # labels of the caller's model (the device model may be shared, see _BaseSampler._ir)
     ll = dm.log_likelihood(states, dtype=dtype)
     lead = tuple(ll.shape[:-1])
     out = {}
@@ -871,4 +880,4 @@ def calculate_log_likelihood(model: Model, posterior: Dict[str, Any], sampling_s
         part = posterior[rv.name]
         part = part if isinstance(part, torch.Tensor) else torch.as_tensor(np.asarray(part))
         theta[:, :, rv.offset: rv.offset + rv.size] = part.to(theta.device, theta.dtype).reshape(S, C, rv.size)
-    return _log_likelihood_from_states(dm, theta, np.dtype(dtype))
+    return _log_likelihood_from_states(dm, theta, np.dtype(dtype), ir=ir)
