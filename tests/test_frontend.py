@@ -192,6 +192,28 @@ def test_kwarg_routing_by_signature():
     assert s.stat_names == ["lp", "tree_size", "diverging", "energy", "mean_tree_accept"]
 
 
+def test_sampler_names_come_from_its_own_lowered_model():
+    """Device models are shared between models of one structure and layout (`_get_device_model`); the IR they carry
+    was lowered for the first of them.  A sampler therefore reads names from the IR of ITS model (`_ir`), and two
+    models that differ only in names do hash to the same structure."""
+    import types
+
+    @pm.model
+    def other_names():
+        value = yield pm.Normal("value", 0, 1)
+        return value
+
+    ir_a, _, _ = I.lower_model(M.simple_model())
+    ir_b, _, _ = I.lower_model(other_names())
+    assert ir_a.struct_hash == ir_b.struct_hash and ir_a.layout_key() == ir_b.layout_key()
+    assert [rv.name for rv in ir_a.rvs] != [rv.name for rv in ir_b.rvs]
+    s = pm.mcmc.samplers.NUTS(other_names())
+    s._device_model = types.SimpleNamespace(ir=ir_a)  # the cached device model of the first model
+    assert s._ir is ir_a  # nothing lowered yet: the device model's
+    s._ir_own = ir_b
+    assert s._ir is ir_b and [rv.name for rv in s._ir.rvs] == ["other_names/value"]
+
+
 @pytest.mark.parametrize("sorted_idx,team", [(True, 1), (False, 1), (True, 4), (False, 2)])
 def test_execution_plan_is_a_permutation(sorted_idx, team):
     rng = np.random.default_rng(1)
