@@ -132,3 +132,20 @@ def mvn_latent_model(cov=None, y=None):
         yield pm.Normal("y", f, s, observed=y)
 
     return mvn_latent()
+
+
+def same_structure_models():
+    """Two models of one structure and layout whose variable names differ (they share a device model)."""
+    @pm.model
+    def first():
+        a = yield pm.Normal("a", 0.0, 1.0)
+        yield pm.Deterministic("twice_a", a * 2)
+        yield pm.Normal("ya", a, 1.0, observed=np.array([0.5, -0.25]))
+
+    @pm.model
+    def second():
+        b = yield pm.Normal("b", 0.0, 1.0)
+        yield pm.Deterministic("twice_b", b * 2)
+        yield pm.Normal("yb", b, 1.0, observed=np.array([0.5, -0.25]))
+
+    return first(), second()

@@ -350,25 +350,14 @@ def test_models_of_one_structure_with_other_names_share_a_device_model():
     """Device models are cached by structure and layout, not by variable names: a second model of the same structure
     gets its own names in the trace, in the deterministics, in the pointwise log-likelihood and in the compound
     step's blocks (the cached model was built for the first one)."""
-    @pm.model
-    def first():
-        a = yield pm.Normal("a", 0.0, 1.0)
-        yield pm.Deterministic("twice_a", a * 2)
-        yield pm.Normal("ya", a, 1.0, observed=np.array([0.5, -0.25]))
-
-    @pm.model
-    def second():
-        b = yield pm.Normal("b", 0.0, 1.0)
-        yield pm.Deterministic("twice_b", b * 2)
-        yield pm.Normal("yb", b, 1.0, observed=np.array([0.5, -0.25]))
-
     kw = dict(num_chains=4, num_samples=20, burn_in=10, seed=3, include_log_likelihood=True)
-    t1 = pm.sample(first(), **kw)
-    t2 = pm.sample(second(), **kw)
+    first, second = M.same_structure_models()
+    t1 = pm.sample(first, **kw)
+    t2 = pm.sample(second, **kw)
     assert {"first/a", "first/twice_a"} <= set(t1.posterior) and "first/ya" in t1.log_likelihood
     assert {"second/b", "second/twice_b"} <= set(t2.posterior) and "second/yb" in t2.log_likelihood
     assert not any(k.startswith("first/") for k in list(t2.posterior) + list(t2.log_likelihood))
     np.testing.assert_array_equal(t1.posterior["first/a"], t2.posterior["second/b"])
     np.testing.assert_array_equal(t1.posterior["first/twice_a"], t2.posterior["second/twice_b"])
-    t3 = pm.sample(second(), sampler_type="compound", num_chains=4, num_samples=20, burn_in=10, seed=3)
+    t3 = pm.sample(M.same_structure_models()[1], sampler_type="compound", num_chains=4, num_samples=20, burn_in=10, seed=3)
     assert "second/b" in t3.posterior and t3.posterior["second/b"].shape == (4, 20)
