@@ -375,7 +375,11 @@ typedef struct pm4_nuts_cfg {
  * outputs (any may be NULL), all for the S kept draws, reference layout [S, C, ...]:
  *   states_dev [S,C,D], lp_dev [S,C], leapfrogs_dev [S,C] i32, diverging_dev [S,C] u8,
  *   energy_dev [S,C], log_accept_dev [S,C], depth_dev [S,C] i32, step_size_dev [C] final epsilon,
- *   total_leapfrogs_dev [C] i64: leapfrogs over ALL B+S transitions (throughput accounting). */
+ *   total_leapfrogs_dev [C] i64: leapfrogs over ALL B+S transitions (throughput accounting).
+ * Device memory of a run (every pm4_*_run entry): the caller owns the inputs and outputs; the run's scratch
+ * (chain states, tree scratch, queues) comes from the device's default stream-ordered pool
+ * (cudaMallocAsync / cudaFreeAsync on `stream`), is zeroed before use, and the library raises that pool's release
+ * threshold to 256 MiB once per device so that the scratch of one run is still mapped for the next one. */
 int pm4_nuts_run(pm4_model_t* m, int dtype, const pm4_nuts_cfg_t* cfg, const void* theta0_dev,
                  const void* step_scale_dev, const void* momenta_dev, void* states_dev,
                  void* lp_dev, int32_t* leapfrogs_dev, uint8_t* diverging_dev, void* energy_dev,
