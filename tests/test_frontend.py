@@ -476,3 +476,93 @@ def test_lowering_cache_follows_the_data():
     assert c[0] is not a[0] and not np.array_equal(c[0].dataf, a[0].dataf)
     assert lower_model(M.hierarchical_model(idx, x, y, g))[0] is not c[0]
     assert lower_model(m, observed={})[0] is not lower_model(m, observed={})[0]  # overrides are never cached
+
+
+# ---- owner-computes plan of the warp path (pymc4_b200/owned.py), walked on the CPU the way pm4_warp.cuh walks it ----
+def _decode_owned(ir):
+    from pymc4_b200 import owned as OW
+
+    lay = ir.owned
+    hdr_at = ir.phdr_off + 4 * max(len(ir.plans), 1)
+    en, i_off, i_len, f_off, f_len, NF, Q, n = [int(v) for v in ir.plani[hdr_at:hdr_at + OW.HDR_INTS]]
+    assert en == 1 and n == ir.terms[lay.term].n
+    sec = np.asarray(ir.plani[i_off:i_off + i_len], dtype=np.int64)
+    RI, KS = lay.RI, lay.KS
+    perm = sec[:RI * 32]
+    p = RI * 32
+    own_len = sec[p:p + max(KS, 1) * 32]
+    p += max(KS, 1) * 32
+    nsl = KS + NF + 1
+    sl_base = sec[p:p + nsl]
+    p += nsl + ((-nsl) % 4)
+    fmeta = sec[p:p + NF * 32 * 4].reshape(NF, 32, 4)
+    W = max(lay.width, 1)
+    rows = int(sl_base[-1])
+    rec = np.asarray(ir.planf[f_off:f_off + f_len]).reshape(-1)[:rows * 32 * W * 2].reshape(rows, 32, W, 2)
+    return dict(NF=NF, Q=Q, perm=perm, own_len=own_len, sl_base=sl_base, fmeta=fmeta, rec=rec)
+
+
+@pytest.mark.parametrize("G,n,conc", [(85, 919, None), (31, 200, 0.3), (33, 64, 0.3), (100, 2000, 0.3), (5, 1000, 0.3)])
+def test_owned_plan_visits_every_observation_once_on_its_groups_lane(G, n, conc):
+    """The owned plan (records as pair rows per lane and slice, the group -> (slice, lane) map, the foreign pieces of
+    the biggest groups with their segmented shuffle reduction) is walked here exactly like `terms_o` walks it: every
+    observation must be visited once, by a lane that holds (or is handed) the parameters of ITS group, padding must
+    be zero, and the segmented reduction must deliver every owner the total of its pieces."""
+    from pymc4_b200 import benchmodels as BM
+
+    if conc is None:
+        idx, x, y, G = BM.radon_synthetic(n, G)
+    else:
+        rng = np.random.default_rng(5 + G)
+        sizes = 1 + rng.multinomial(n - G, rng.dirichlet(np.full(G, conc)))
+        idx = np.repeat(np.arange(G, dtype=np.int32), sizes)
+        x, y = (rng.random(n) < 0.3).astype(float), rng.standard_normal(n)
+    ir, _, _ = lower_model(BM.hierarchical_model(idx, x, y, G))
+    lay = ir.owned
+    assert lay is not None and lay.NV == 2 and lay.G == G
+    d = _decode_owned(ir)
+    KS, NF, Q, base0 = lay.KS, d["NF"], d["Q"], lay.vec_bases[0]
+    got = [[] for _ in range(G)]
+    group_of_lane = {}
+    for s in range(KS):
+        rows = int(d["sl_base"][s + 1] - d["sl_base"][s])
+        for lane in range(32):
+            pj, cnt = int(d["perm"][s * 32 + lane]), int(d["own_len"][s * 32 + lane])
+            if pj < 0:
+                assert cnt == 0
+                continue
+            g = pj - base0
+            for v, b in enumerate(lay.vec_bases):  # every gathered vector of the group: same lane, same slice
+                assert d["perm"][(v * KS + s) * 32 + lane] == b + g
+            if s == 0:
+                group_of_lane[lane] = g
+            assert cnt <= 2 * rows
+            for r in range(2 * rows):
+                cell = d["rec"][d["sl_base"][s] + r // 2, lane, :, r % 2]
+                if r < cnt:
+                    got[g].append(tuple(cell))
+                else:
+                    assert not cell.any()
+    for f in range(NF):
+        meta = d["fmeta"][f]
+        rows = int(d["sl_base"][KS + f + 1] - d["sl_base"][KS + f])
+        part = np.zeros(32)
+        for lane in range(32):
+            cnt, owner = int(meta[lane][0]), int(meta[lane][1])
+            assert cnt <= 2 * rows
+            for r in range(cnt):
+                got[group_of_lane[owner]].append(tuple(d["rec"][d["sl_base"][KS + f] + r // 2, lane, :, r % 2]))
+            part[lane] = cnt
+        for st in range(Q):  # the kernel's segmented reduction: step st adds lane + 2^st where the mask bit is set
+            part = np.array([part[l] + (part[l + (1 << st)] if int(meta[l][2]) >> st & 1 else 0) for l in range(32)])
+        for owner in range(32):
+            head = int(meta[owner][3])
+            if head >= 0:
+                assert int(meta[head][1]) == owner
+                assert part[head] == sum(int(m[0]) for m in meta if int(m[1]) == owner and int(m[0]) > 0)
+    t = ir.terms[lay.term]
+    by_dst = {o.dst: o for o in t.ops}
+    cols = [np.asarray(ir.dataf[by_dst[c].blob: by_dst[c].blob + t.n]) for c in t.plan.record_ops]
+    for g in range(G):
+        assert sorted(got[g]) == sorted(zip(*[c[idx == g] for c in cols])), g
+    assert sum(len(v) for v in got) == n
